@@ -1,0 +1,128 @@
+// adb_common.cuh -- device helpers shared by the operator kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "adb_engine.h"
+
+namespace adb {
+
+constexpr int kWarp = 32;
+constexpr uint32_t kFull = 0xffffffffu;
+
+// ---- streaming global accesses -------------------------------------------------------
+// Column scans touch every byte exactly once: keep them out of L1 so the position
+// lists / gather targets that *are* reused keep the cache.
+__device__ __forceinline__ int4 ld_stream(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int32_t ld_stream(const int32_t *p) {
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(int4 *p, const int4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// ---- 64-bit status words for the decoupled look-back ------------------------------------
+// One word carries {epoch, flag, value}; a single relaxed 64-bit access moves all three
+// atomically, so no fence is needed between "value" and "flag".
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---- warp primitives ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+        uint32_t y = __shfl_up_sync(kFull, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    return x;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+    return x;
+}
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+    return x;
+}
+__device__ __forceinline__ int32_t warp_min_i32(int32_t x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x = min(x, __shfl_xor_sync(kFull, x, d));
+    return x;
+}
+__device__ __forceinline__ int32_t warp_max_i32(int32_t x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x = max(x, __shfl_xor_sync(kFull, x, d));
+    return x;
+}
+
+// ---- range predicate -------------------------------------------------------------------
+// The reference tests `v >= low && v < high` with either bound optional
+// (src/query.c:97-127).  Host code folds that into an inclusive pair [lo, hi_incl]:
+// absent low -> INT32_MIN, absent high -> INT32_MAX, high == INT32_MIN or lo > hi_incl ->
+// the canonical empty range (1, 0).  Exact for every int32 input.
+struct Range {
+    int32_t lo, hi_incl;
+};
+__device__ __forceinline__ bool in_range(int32_t v, const Range &r) {
+    return v >= r.lo && v <= r.hi_incl;
+}
+
+// splitmix64 finaliser: the counter-based generator behind adb_synth_uniform
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace adb
+
+// ---- engine-internal launch interface (engine.cu <-> kernel files) --------------------
+// Every launch_* returns the number of kernels it enqueued (0 for an empty input).
+namespace adb {
+
+struct SelectArgs {
+    const int32_t *val;       // values the predicate reads
+    const int32_t *pos_in;    // paired positions (select_pairs) or nullptr
+    const int64_t *d_n;       // optional device-side length
+    uint32_t n;               // host-side length / upper bound (< 2^31)
+    Range range;
+    int32_t base_pos;
+    int32_t *out;
+    int64_t *d_count;
+    unsigned long long *status;   // per-tile look-back words
+    uint32_t epoch;               // 30-bit launch tag; stale words never match
+};
+int launch_select(const SelectArgs &a, cudaStream_t s);
+uint32_t select_tile_count(uint32_t n);
+
+int launch_fetch(const int32_t *col, const int32_t *pos, int64_t n_max, const int64_t *d_n,
+                  int32_t base_pos, int32_t *out, int sm_count, cudaStream_t s);
+int launch_aggregate(const int32_t *v, int64_t n_max, const int64_t *d_n, adb_agg *out,
+                      adb_agg *scratch, unsigned int *ticket, int sm_count, cudaStream_t s);
+int launch_agg_combine(const adb_agg *parts, int32_t k, adb_agg *out, cudaStream_t s);
+int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_t *d_n,
+                  int32_t *out, bool subtract, int sm_count, cudaStream_t s);
+int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
+                          uint32_t span, int sm_count, cudaStream_t s);
+constexpr int kAggMaxBlocks = 148 * 8;
+
+}  // namespace adb

@@ -1,0 +1,339 @@
+// engine.cu -- the C-ABI of libadb_b200.so (include/adb_engine.h): context, memory, and
+// the host half of every operator (argument checks, bound folding, launches).
+//
+// There is deliberately no CPU path in this file: if no CUDA device can be opened,
+// adb_init() fails and every operator reports ADB_ERR_NOT_INITIALISED.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "adb_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Engine {
+    bool up = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // select look-back state
+    unsigned long long *status = nullptr;
+    uint32_t epoch = 0;
+    // aggregate fold state
+    adb_agg *agg_scratch = nullptr;
+    unsigned int *agg_ticket = nullptr;
+    // small device scratch for chained operators
+    int64_t launches = 0;
+} g;
+
+constexpr uint32_t kMaxTiles = (1u << 31) / 4096 + 1;
+
+adb_status fail(adb_status code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail(ADB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define NEED_UP()                                                                      \
+    do {                                                                               \
+        if (!g.up) return fail(ADB_ERR_NOT_INITIALISED, "adb_init() has not succeeded"); \
+    } while (0)
+
+adb_status after_launch(const char *what, int launches) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ADB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    g.launches += launches;
+    return ADB_OK;
+}
+
+// src/server.c:144-154 passes NULL for an absent bound; the predicate is low <= v < high.
+adb_status fold_range(const int32_t *lo, const int32_t *hi, adb::Range *out) {
+    adb::Range r{lo ? *lo : INT32_MIN, INT32_MAX};
+    if (hi) {
+        if (*hi == INT32_MIN) r = adb::Range{1, 0};     // v < INT32_MIN: nothing
+        else r.hi_incl = *hi - 1;
+    }
+    if (r.lo > r.hi_incl) r = adb::Range{1, 0};
+    *out = r;
+    return ADB_OK;
+}
+
+adb_status check_len(int64_t n, const char *what) {
+    if (n < 0 || n >= (int64_t)1 << 31)
+        return fail(ADB_ERR_INVALID, "%s: length %lld outside [0, 2^31) (positions are int32, "
+                    "src/query.c:94-95)", what, (long long)n);
+    return ADB_OK;
+}
+
+uint32_t next_epoch() {
+    g.epoch = (g.epoch + 1) & 0x3fffffffu;
+    if (g.epoch == 0) {                                   // wrapped: retire every stale word
+        cudaMemsetAsync(g.status, 0, sizeof(unsigned long long) * kMaxTiles, g.stream);
+        g.epoch = 1;
+    }
+    return g.epoch;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *adb_last_error(void) { return g_err.c_str(); }
+const char *adb_version(void) { return "adb_b200 0.1 (sm_100a)"; }
+int adb_sm_count(void) { return g.sm_count; }
+int64_t adb_launch_count(void) { return g.launches; }
+
+adb_status adb_init(int device_ordinal) {
+    if (g.up) return ADB_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ADB_ERR_CUDA, "no CUDA device: %s (this engine has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_ordinal < 0 || device_ordinal >= count)
+        return fail(ADB_ERR_INVALID, "device %d not in [0, %d)", device_ordinal, count);
+    CU(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_ordinal));
+    g.device = device_ordinal;
+    g.sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.own_stream = true;
+    CU(cudaEventCreate(&g.ev0));
+    CU(cudaEventCreate(&g.ev1));
+    // keep freed blocks cached in the stream-ordered pool: result buffers are recycled
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+    uint64_t keep = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    CU(cudaMalloc(&g.status, sizeof(unsigned long long) * kMaxTiles));
+    CU(cudaMemset(g.status, 0, sizeof(unsigned long long) * kMaxTiles));
+    CU(cudaMalloc(&g.agg_scratch, sizeof(adb_agg) * adb::kAggMaxBlocks));
+    CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int)));
+    CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int)));
+    g.epoch = 0;
+    g.launches = 0;
+    g.up = true;
+    return ADB_OK;
+}
+
+adb_status adb_shutdown(void) {
+    if (!g.up) return ADB_OK;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaFree(g.status);
+    cudaFree(g.agg_scratch);
+    cudaFree(g.agg_ticket);
+    cudaEventDestroy(g.ev0);
+    cudaEventDestroy(g.ev1);
+    if (g.own_stream) cudaStreamDestroy(g.stream);
+    g = Engine{};
+    return ADB_OK;
+}
+
+void *adb_stream(void) { return g.stream; }
+
+adb_status adb_set_stream(void *cuda_stream) {
+    NEED_UP();
+    CU(cudaStreamSynchronize(g.stream));
+    if (g.own_stream) cudaStreamDestroy(g.stream);
+    g.stream = static_cast<cudaStream_t>(cuda_stream);
+    g.own_stream = false;
+    return ADB_OK;
+}
+
+adb_status adb_alloc(void **d_ptr, size_t bytes) {
+    NEED_UP();
+    if (!d_ptr) return fail(ADB_ERR_INVALID, "adb_alloc: NULL out pointer");
+    cudaError_t e = cudaMallocAsync(d_ptr, bytes ? bytes : 16, g.stream);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(ADB_ERR_NOMEM, "adb_alloc: out of device memory for %zu bytes", bytes);
+    }
+    CU(e);
+    return ADB_OK;
+}
+adb_status adb_free(void *d_ptr) {
+    NEED_UP();
+    if (d_ptr) CU(cudaFreeAsync(d_ptr, g.stream));
+    return ADB_OK;
+}
+adb_status adb_upload_async(void *d_dst, const void *h_src, size_t bytes) {
+    NEED_UP();
+    if (bytes) CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g.stream));
+    return ADB_OK;
+}
+adb_status adb_download_async(void *h_dst, const void *d_src, size_t bytes) {
+    NEED_UP();
+    if (bytes) CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+    return ADB_OK;
+}
+adb_status adb_upload(void *d_dst, const void *h_src, size_t bytes) {
+    adb_status s = adb_upload_async(d_dst, h_src, bytes);
+    return s ? s : adb_sync();
+}
+adb_status adb_download(void *h_dst, const void *d_src, size_t bytes) {
+    adb_status s = adb_download_async(h_dst, d_src, bytes);
+    return s ? s : adb_sync();
+}
+adb_status adb_memset(void *d_dst, int byte, size_t bytes) {
+    NEED_UP();
+    if (bytes) CU(cudaMemsetAsync(d_dst, byte, bytes, g.stream));
+    return ADB_OK;
+}
+adb_status adb_sync(void) {
+    NEED_UP();
+    CU(cudaStreamSynchronize(g.stream));
+    return ADB_OK;
+}
+adb_status adb_host_alloc(void **h_ptr, size_t bytes) {
+    NEED_UP();
+    CU(cudaMallocHost(h_ptr, bytes ? bytes : 16));
+    return ADB_OK;
+}
+adb_status adb_host_free(void *h_ptr) {
+    NEED_UP();
+    if (h_ptr) CU(cudaFreeHost(h_ptr));
+    return ADB_OK;
+}
+adb_status adb_timer_start(void) {
+    NEED_UP();
+    CU(cudaEventRecord(g.ev0, g.stream));
+    return ADB_OK;
+}
+adb_status adb_timer_stop(float *ms) {
+    NEED_UP();
+    CU(cudaEventRecord(g.ev1, g.stream));
+    CU(cudaEventSynchronize(g.ev1));
+    if (ms) CU(cudaEventElapsedTime(ms, g.ev0, g.ev1));
+    return ADB_OK;
+}
+
+// ---- operators ---------------------------------------------------------------------------
+static adb_status finish_count(int64_t *d_count, int64_t *h_count) {
+    if (!h_count) return ADB_OK;
+    CU(cudaMemcpyAsync(h_count, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return ADB_OK;
+}
+
+adb_status adb_select_scan(const int32_t *d_col, int64_t n, const int32_t *lo, const int32_t *hi,
+                           int32_t base_pos, int32_t *d_pos_out, int64_t *d_count,
+                           int64_t *h_count) {
+    NEED_UP();
+    if (adb_status s = check_len(n, "adb_select_scan")) return s;
+    if (!d_count || (n > 0 && (!d_col || !d_pos_out)))
+        return fail(ADB_ERR_INVALID, "adb_select_scan: NULL device pointer");
+    adb::SelectArgs a{};
+    a.val = d_col; a.pos_in = nullptr; a.d_n = nullptr; a.n = (uint32_t)n;
+    fold_range(lo, hi, &a.range);
+    a.base_pos = base_pos; a.out = d_pos_out; a.d_count = d_count;
+    a.status = g.status; a.epoch = next_epoch();
+    const int k_ = adb::launch_select(a, g.stream);
+    if (adb_status s = after_launch("select_scan", k_)) return s;
+    return finish_count(d_count, h_count);
+}
+
+adb_status adb_select_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n_max,
+                            const int64_t *d_n, const int32_t *lo, const int32_t *hi,
+                            int32_t *d_pos_out, int64_t *d_count, int64_t *h_count) {
+    NEED_UP();
+    if (adb_status s = check_len(n_max, "adb_select_pairs")) return s;
+    if (!d_count || (n_max > 0 && (!d_val || !d_pos || !d_pos_out)))
+        return fail(ADB_ERR_INVALID, "adb_select_pairs: NULL device pointer");
+    adb::SelectArgs a{};
+    a.val = d_val; a.pos_in = d_pos; a.d_n = d_n; a.n = (uint32_t)n_max;
+    fold_range(lo, hi, &a.range);
+    a.base_pos = 0; a.out = d_pos_out; a.d_count = d_count;
+    a.status = g.status; a.epoch = next_epoch();
+    const int k_ = adb::launch_select(a, g.stream);
+    if (adb_status s = after_launch("select_pairs", k_)) return s;
+    return finish_count(d_count, h_count);
+}
+
+adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
+                     const int64_t *d_n, int32_t base_pos, int32_t *d_val_out) {
+    NEED_UP();
+    if (adb_status s = check_len(n_max, "adb_fetch")) return s;
+    if (n_max == 0) return ADB_OK;
+    if (!d_col || !d_pos || !d_val_out) return fail(ADB_ERR_INVALID, "adb_fetch: NULL device pointer");
+    const int k_ = adb::launch_fetch(d_col, d_pos, n_max, d_n, base_pos, d_val_out, g.sm_count, g.stream);
+    return after_launch("fetch", k_);
+}
+
+adb_status adb_aggregate(const int32_t *d_val, int64_t n_max, const int64_t *d_n,
+                         adb_agg *d_out, adb_agg *h_out) {
+    NEED_UP();
+    if (adb_status s = check_len(n_max, "adb_aggregate")) return s;
+    if (!d_out || (n_max > 0 && !d_val)) return fail(ADB_ERR_INVALID, "adb_aggregate: NULL device pointer");
+    const int k_ = adb::launch_aggregate(d_val, n_max, d_n, d_out, g.agg_scratch, g.agg_ticket, g.sm_count, g.stream);
+    if (adb_status s = after_launch("aggregate", k_)) return s;
+    if (h_out) {
+        CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+    }
+    return ADB_OK;
+}
+
+adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, adb_agg *h_out) {
+    NEED_UP();
+    if (k < 0 || !d_out || (k > 0 && !d_parts)) return fail(ADB_ERR_INVALID, "adb_agg_combine: bad arguments");
+    const int k_ = adb::launch_agg_combine(d_parts, k, d_out, g.stream);
+    if (adb_status s = after_launch("agg_combine", k_)) return s;
+    if (h_out) {
+        CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+    }
+    return ADB_OK;
+}
+
+static adb_status ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_t *d_n,
+                        int32_t *out, bool subtract) {
+    NEED_UP();
+    if (adb_status s = check_len(n_max, subtract ? "adb_sub" : "adb_add")) return s;
+    if (n_max == 0) return ADB_OK;
+    if (!a || !b || !out) return fail(ADB_ERR_INVALID, "adb_add/adb_sub: NULL device pointer");
+    const int k_ = adb::launch_ewise(a, b, n_max, d_n, out, subtract, g.sm_count, g.stream);
+    return after_launch("ewise", k_);
+}
+adb_status adb_add(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
+                   int32_t *d_out) { return ewise(d_a, d_b, n_max, d_n, d_out, false); }
+adb_status adb_sub(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
+                   int32_t *d_out) { return ewise(d_a, d_b, n_max, d_n, d_out, true); }
+
+adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d_fetch_col,
+                                      int64_t n, const int32_t *lo, const int32_t *hi,
+                                      int32_t *d_pos_out, int32_t *d_val_out,
+                                      int64_t *d_count, adb_agg *d_agg) {
+    if (adb_status s = adb_select_scan(d_sel_col, n, lo, hi, 0, d_pos_out, d_count, nullptr)) return s;
+    if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, n, d_count, 0, d_val_out)) return s;
+    return adb_aggregate(d_val_out, n, d_count, d_agg, nullptr);
+}
+
+adb_status adb_synth_uniform(int32_t *d_out, int64_t n, uint64_t seed, uint64_t first_row,
+                             int32_t lo, uint32_t span) {
+    NEED_UP();
+    if (n < 0 || (n > 0 && !d_out)) return fail(ADB_ERR_INVALID, "adb_synth_uniform: bad arguments");
+    if (n == 0) return ADB_OK;
+    const int k_ = adb::launch_synth_uniform(d_out, n, seed, first_row, lo, span, g.sm_count, g.stream);
+    return after_launch("synth_uniform", k_);
+}
+
+}  // extern "C"

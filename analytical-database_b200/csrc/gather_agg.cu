@@ -1,0 +1,262 @@
+// gather_agg.cu -- fetch (gather), sum/min/max, element-wise add/sub, synthetic fill.
+//
+// Replaces the loops of fetch_column (/root/reference/src/query.c:229-231), sum / average /
+// min / max (query.c:311-313,333-341,397-402,422-427) and add / sub (query.c:361-363,
+// 379-381).  All are HBM-bound streaming kernels: persistent grids (a multiple of the SM
+// count), 16-byte accesses, several independent loads in flight per thread, lengths
+// optionally read from a device int64 so a select's hit count never visits the host.
+#include "adb_common.cuh"
+
+namespace adb {
+
+constexpr int STREAM_THREADS = 256;
+
+__device__ __forceinline__ int64_t resolve_n(int64_t n_max, const int64_t *d_n) {
+    if (!d_n) return n_max;
+    const int64_t dn = *d_n;
+    return dn < 0 ? 0 : (dn < n_max ? dn : n_max);
+}
+
+// ---- fetch: out[i] = col[pos[i] - base] ------------------------------------------------
+// Position lists from a select are ascending, so neighbouring hits share 32-byte sectors;
+// each thread keeps eight independent gathers in flight.
+__global__ void __launch_bounds__(STREAM_THREADS)
+fetch_kernel(const int32_t *__restrict__ col, const int32_t *__restrict__ pos, int64_t n_max,
+             const int64_t *__restrict__ d_n, int32_t base, int32_t *__restrict__ out) {
+    const int64_t n = resolve_n(n_max, d_n);
+    const int64_t nvec = n >> 2;                         // pos/out come from adb_alloc: 16B aligned
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int4 *pos4 = reinterpret_cast<const int4 *>(pos);
+    int4 *out4 = reinterpret_cast<int4 *>(out);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (aligned) {
+        for (; i + stride < nvec; i += 2 * stride) {
+            const int4 p0 = ld_stream(pos4 + i), p1 = ld_stream(pos4 + i + stride);
+            int4 v0, v1;
+            v0.x = __ldg(col + (p0.x - base)); v0.y = __ldg(col + (p0.y - base));
+            v0.z = __ldg(col + (p0.z - base)); v0.w = __ldg(col + (p0.w - base));
+            v1.x = __ldg(col + (p1.x - base)); v1.y = __ldg(col + (p1.y - base));
+            v1.z = __ldg(col + (p1.z - base)); v1.w = __ldg(col + (p1.w - base));
+            out4[i] = v0;
+            out4[i + stride] = v1;
+        }
+        for (; i < nvec; i += stride) {
+            const int4 p0 = ld_stream(pos4 + i);
+            int4 v0;
+            v0.x = __ldg(col + (p0.x - base)); v0.y = __ldg(col + (p0.y - base));
+            v0.z = __ldg(col + (p0.z - base)); v0.w = __ldg(col + (p0.w - base));
+            out4[i] = v0;
+        }
+        for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+            out[t] = __ldg(col + (pos[t] - base));
+    } else {
+        for (; i < n; i += stride) out[i] = __ldg(col + (pos[i] - base));
+    }
+}
+
+// ---- aggregate: {sum (int64), min, max, count} in one pass --------------------------------
+struct AggAcc {
+    int64_t sum;
+    int32_t mn, mx;
+    __device__ __forceinline__ void add(int32_t v) {
+        sum += v;
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    __device__ __forceinline__ void add4(const int4 &v) {
+        // pairwise int64 adds keep the carry chain short
+        sum += ((int64_t)v.x + (int64_t)v.y) + ((int64_t)v.z + (int64_t)v.w);
+        mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
+        mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+    }
+};
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+aggregate_kernel(const int32_t *__restrict__ v, int64_t n_max, const int64_t *__restrict__ d_n,
+                 adb_agg *__restrict__ out, adb_agg *scratch, unsigned int *ticket) {
+    __shared__ int64_t s_sum[STREAM_THREADS / kWarp];
+    __shared__ int32_t s_mn[STREAM_THREADS / kWarp], s_mx[STREAM_THREADS / kWarp];
+    __shared__ bool s_last;
+    const int64_t n = resolve_n(n_max, d_n);
+    AggAcc acc{0, INT32_MAX, INT32_MIN};
+
+    // peel to 16-byte alignment, then vector body, then tail
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(v);
+    int64_t head = ((16 - (addr & 15u)) & 15u) >> 2;
+    if (head > n) head = n;
+    const int64_t nvec = (n - head) >> 2;
+    const int4 *v4 = reinterpret_cast<const int4 *>(v + head);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = tid;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const int4 a = ld_stream(v4 + i), b = ld_stream(v4 + i + stride);
+        const int4 c = ld_stream(v4 + i + 2 * stride), d = ld_stream(v4 + i + 3 * stride);
+        acc.add4(a); acc.add4(b); acc.add4(c); acc.add4(d);
+    }
+    for (; i < nvec; i += stride) acc.add4(ld_stream(v4 + i));
+    if (tid < head) acc.add(v[tid]);
+    for (int64_t t = head + (nvec << 2) + tid; t < n; t += stride) acc.add(v[t]);
+
+    // warp -> block
+    acc.sum = warp_sum_i64(acc.sum);
+    acc.mn = warp_min_i32(acc.mn);
+    acc.mx = warp_max_i32(acc.mx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_sum[warp] = acc.sum; s_mn[warp] = acc.mn; s_mx[warp] = acc.mx; }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int W = STREAM_THREADS / kWarp;
+        AggAcc b{lane < W ? s_sum[lane] : 0, lane < W ? s_mn[lane] : INT32_MAX,
+                 lane < W ? s_mx[lane] : INT32_MIN};
+        b.sum = warp_sum_i64(b.sum);
+        b.mn = warp_min_i32(b.mn);
+        b.mx = warp_max_i32(b.mx);
+        if (lane == 0) {
+            scratch[blockIdx.x] = adb_agg{b.sum, 0, b.mn, b.mx};
+            __threadfence();
+            const unsigned int done = atomicAdd(ticket, 1u);
+            s_last = (done == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // block -> grid: the last block to finish folds every partial (deterministic order)
+    __threadfence();
+    AggAcc g{0, INT32_MAX, INT32_MIN};
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
+        const volatile adb_agg *p = scratch + k;        // written by other CTAs: no .nc path
+        g.sum += p->sum;
+        g.mn = min(g.mn, p->min);
+        g.mx = max(g.mx, p->max);
+    }
+    g.sum = warp_sum_i64(g.sum);
+    g.mn = warp_min_i32(g.mn);
+    g.mx = warp_max_i32(g.mx);
+    __syncthreads();
+    if (lane == 0) { s_sum[warp] = g.sum; s_mn[warp] = g.mn; s_mx[warp] = g.mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        AggAcc f{0, INT32_MAX, INT32_MIN};
+        for (int w = 0; w < STREAM_THREADS / kWarp; ++w) {
+            f.sum += s_sum[w];
+            f.mn = min(f.mn, s_mn[w]);
+            f.mx = max(f.mx, s_mx[w]);
+        }
+        *out = adb_agg{f.sum, n, f.mn, f.mx};
+        *ticket = 0;                                    // re-arm for the next launch
+    }
+}
+
+__global__ void agg_combine_kernel(const adb_agg *__restrict__ parts, int32_t k,
+                                   adb_agg *__restrict__ out) {
+    AggAcc g{0, INT32_MAX, INT32_MIN};
+    int64_t cnt = 0;
+    for (int i = threadIdx.x; i < k; i += kWarp) {
+        const adb_agg p = parts[i];
+        g.sum += p.sum;
+        cnt += p.count;
+        g.mn = min(g.mn, p.min);
+        g.mx = max(g.mx, p.max);
+    }
+    g.sum = warp_sum_i64(g.sum);
+    cnt = warp_sum_i64(cnt);
+    g.mn = warp_min_i32(g.mn);
+    g.mx = warp_max_i32(g.mx);
+    if (threadIdx.x == 0) *out = adb_agg{g.sum, cnt, g.mn, g.mx};
+}
+
+// ---- element-wise add / sub (int32, two's-complement wrap) ------------------------------
+template <bool SUB>
+__global__ void __launch_bounds__(STREAM_THREADS)
+ewise_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t n_max,
+             const int64_t *__restrict__ d_n, int32_t *__restrict__ out) {
+    const int64_t n = resolve_n(n_max, d_n);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                           reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    auto op = [](int32_t x, int32_t y) {
+        return SUB ? (int32_t)((uint32_t)x - (uint32_t)y) : (int32_t)((uint32_t)x + (uint32_t)y);
+    };
+    if (aligned) {
+        const int64_t nvec = n >> 2;
+        const int4 *a4 = reinterpret_cast<const int4 *>(a), *b4 = reinterpret_cast<const int4 *>(b);
+        int4 *o4 = reinterpret_cast<int4 *>(out);
+        int64_t i = tid;
+        for (; i + stride < nvec; i += 2 * stride) {
+            const int4 x0 = ld_stream(a4 + i), y0 = ld_stream(b4 + i);
+            const int4 x1 = ld_stream(a4 + i + stride), y1 = ld_stream(b4 + i + stride);
+            st_stream(o4 + i, make_int4(op(x0.x, y0.x), op(x0.y, y0.y), op(x0.z, y0.z), op(x0.w, y0.w)));
+            st_stream(o4 + i + stride, make_int4(op(x1.x, y1.x), op(x1.y, y1.y), op(x1.z, y1.z), op(x1.w, y1.w)));
+        }
+        for (; i < nvec; i += stride) {
+            const int4 x0 = ld_stream(a4 + i), y0 = ld_stream(b4 + i);
+            st_stream(o4 + i, make_int4(op(x0.x, y0.x), op(x0.y, y0.y), op(x0.z, y0.z), op(x0.w, y0.w)));
+        }
+        for (int64_t t = (nvec << 2) + tid; t < n; t += stride) out[t] = op(a[t], b[t]);
+    } else {
+        for (int64_t t = tid; t < n; t += stride) out[t] = op(a[t], b[t]);
+    }
+}
+
+// ---- synthetic columns ------------------------------------------------------------------
+__global__ void __launch_bounds__(STREAM_THREADS)
+synth_uniform_kernel(int32_t *__restrict__ out, int64_t n, uint64_t seed, uint64_t first_row,
+                     int32_t lo, uint32_t span) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t z = mix64(seed, first_row + (uint64_t)i);
+        out[i] = (int32_t)((uint32_t)lo + (uint32_t)(((z >> 32) * (uint64_t)span) >> 32));
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------------
+static int stream_grid(int64_t work_items, int sm_count, int per_sm) {
+    const int64_t want = (work_items + STREAM_THREADS - 1) / STREAM_THREADS;
+    const int64_t cap = (int64_t)sm_count * per_sm;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+int launch_fetch(const int32_t *col, const int32_t *pos, int64_t n_max, const int64_t *d_n,
+                  int32_t base_pos, int32_t *out, int sm_count, cudaStream_t s) {
+    if (n_max <= 0) return 0;
+    fetch_kernel<<<stream_grid(n_max / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(
+        col, pos, n_max, d_n, base_pos, out);
+    return 1;
+}
+
+int launch_aggregate(const int32_t *v, int64_t n_max, const int64_t *d_n, adb_agg *out,
+                      adb_agg *scratch, unsigned int *ticket, int sm_count, cudaStream_t s) {
+    int grid = stream_grid(n_max / 16 + 1, sm_count, 8);
+    if (grid > kAggMaxBlocks) grid = kAggMaxBlocks;
+    aggregate_kernel<<<grid, STREAM_THREADS, 0, s>>>(v, n_max < 0 ? 0 : n_max, d_n, out, scratch, ticket);
+    return 1;
+}
+
+int launch_agg_combine(const adb_agg *parts, int32_t k, adb_agg *out, cudaStream_t s) {
+    agg_combine_kernel<<<1, kWarp, 0, s>>>(parts, k, out);
+    return 1;
+}
+
+int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_t *d_n,
+                  int32_t *out, bool subtract, int sm_count, cudaStream_t s) {
+    if (n_max <= 0) return 0;
+    const int grid = stream_grid(n_max / 8 + 1, sm_count, 8);
+    if (subtract)
+        ewise_kernel<true><<<grid, STREAM_THREADS, 0, s>>>(a, b, n_max, d_n, out);
+    else
+        ewise_kernel<false><<<grid, STREAM_THREADS, 0, s>>>(a, b, n_max, d_n, out);
+    return 1;
+}
+
+int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
+                          uint32_t span, int sm_count, cudaStream_t s) {
+    if (n <= 0) return 0;
+    synth_uniform_kernel<<<stream_grid(n / 4 + 1, sm_count, 16), STREAM_THREADS, 0, s>>>(
+        out, n, seed, first_row, lo, span);
+    return 1;
+}
+
+}  // namespace adb

@@ -1,0 +1,243 @@
+"""ctypes binding of the engine's C-ABI (``include/adb_engine.h`` -> ``libadb_b200.so``).
+
+Plumbing only: this module moves numpy arrays in and out of HBM and forwards every
+operator to the CUDA library.  It never computes a result itself and has no fallback --
+``Engine()`` raises ``EngineError`` when the library is missing or no device opens.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_I32P = C.POINTER(C.c_int32)
+_I64P = C.POINTER(C.c_int64)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libadb_b200.so")
+
+
+def build_native(quiet: bool = True) -> str:
+    """Compile every CUDA source for sm_100a into libadb_b200.so (nvcc cross-compiles)."""
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")] + (["-s"] if quiet else []),
+                   check=True)
+    host = os.path.join(_HERE, "host")
+    if os.path.exists(os.path.join(host, "Makefile")):
+        subprocess.run(["make", "-C", host] + (["-s"] if quiet else []), check=True)
+    return lib_path()
+
+
+class _AggStruct(C.Structure):
+    _fields_ = [("sum", C.c_int64), ("count", C.c_int64), ("min", C.c_int32), ("max", C.c_int32)]
+
+
+@dataclass
+class Agg:
+    sum: int
+    count: int
+    min: int
+    max: int
+
+    @property
+    def avg(self) -> float:
+        """(double)sum / (double)num_tuples, /root/reference/src/query.c:314."""
+        return float(np.float64(self.sum) / np.float64(self.count)) if self.count else float("nan")
+
+
+class DevBuf:
+    """A device allocation owned by the engine's stream-ordered pool."""
+
+    def __init__(self, eng: "Engine", nbytes: int):
+        self.eng, self.nbytes = eng, int(nbytes)
+        p = C.c_void_p()
+        eng._ck(eng.lib.adb_alloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            self.eng.lib.adb_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def i32(self, offset_elems: int = 0):
+        return C.cast(C.c_void_p(self.ptr + 4 * offset_elems), _I32P)
+
+    def i64(self, offset_elems: int = 0):
+        return C.cast(C.c_void_p(self.ptr + 8 * offset_elems), _I64P)
+
+    def void(self, offset_bytes: int = 0):
+        return C.c_void_p(self.ptr + offset_bytes)
+
+    def to_host(self, n: int, dtype=np.int32, offset_bytes: int = 0) -> np.ndarray:
+        out = np.empty(int(n), dtype=dtype)
+        if n:
+            self.eng._ck(self.eng.lib.adb_download(out.ctypes.data_as(C.c_void_p),
+                                                   self.void(offset_bytes), out.nbytes))
+        return out
+
+
+def _bound(x):
+    if x is None:
+        return None, None
+    box = C.c_int32(int(x))
+    return C.pointer(box), box
+
+
+class Engine:
+    """One engine per process (one process per GPU)."""
+
+    _SIGS = {
+        "adb_init": (C.c_int32, [C.c_int]),
+        "adb_shutdown": (C.c_int32, []),
+        "adb_last_error": (C.c_char_p, []),
+        "adb_version": (C.c_char_p, []),
+        "adb_sm_count": (C.c_int, []),
+        "adb_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
+        "adb_free": (C.c_int32, [C.c_void_p]),
+        "adb_upload": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "adb_download": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "adb_upload_async": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "adb_download_async": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "adb_memset": (C.c_int32, [C.c_void_p, C.c_int, C.c_size_t]),
+        "adb_sync": (C.c_int32, []),
+        "adb_stream": (C.c_void_p, []),
+        "adb_set_stream": (C.c_int32, [C.c_void_p]),
+        "adb_host_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
+        "adb_host_free": (C.c_int32, [C.c_void_p]),
+        "adb_timer_start": (C.c_int32, []),
+        "adb_timer_stop": (C.c_int32, [C.POINTER(C.c_float)]),
+        "adb_launch_count": (C.c_int64, []),
+        "adb_select_scan": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I32P, _I64P, _I64P]),
+        "adb_select_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P, _I32P, _I32P, _I64P, _I64P]),
+        "adb_fetch": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, C.c_int32, _I32P]),
+        "adb_aggregate": (C.c_int32, [_I32P, C.c_int64, _I64P, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
+        "adb_agg_combine": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
+        "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
+        "adb_sub": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
+        "adb_chain_select_fetch_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P, C.POINTER(_AggStruct)]),
+        "adb_synth_uniform": (C.c_int32, [_I32P, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32]),
+    }
+
+    def __init__(self, device: int = 0):
+        path = lib_path()
+        if not os.path.exists(path):
+            raise EngineError(f"{path} is not built (run __graft_entry__.build()); "
+                              "the engine has no CPU fallback")
+        self.lib = C.CDLL(path)
+        for name, (res, args) in self._SIGS.items():
+            fn = getattr(self.lib, name)
+            fn.restype, fn.argtypes = res, args
+        self._ck(self.lib.adb_init(int(device)))
+        self.device = device
+        self.sm_count = self.lib.adb_sm_count()
+
+    # ---- plumbing ------------------------------------------------------------------
+    def _ck(self, status: int):
+        if status != 0:
+            raise EngineError(f"adb status {status}: {self.lib.adb_last_error().decode()}")
+
+    def close(self):
+        self.lib.adb_shutdown()
+
+    def alloc(self, nbytes: int) -> DevBuf:
+        return DevBuf(self, nbytes)
+
+    def alloc_i32(self, n: int) -> DevBuf:
+        return DevBuf(self, 4 * max(int(n), 1))
+
+    def upload(self, a: np.ndarray) -> DevBuf:
+        a = np.ascontiguousarray(a)
+        buf = DevBuf(self, max(a.nbytes, 16))
+        if a.nbytes:
+            self._ck(self.lib.adb_upload(buf.void(), a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return buf
+
+    def sync(self):
+        self._ck(self.lib.adb_sync())
+
+    def timer_start(self):
+        self._ck(self.lib.adb_timer_start())
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._ck(self.lib.adb_timer_stop(C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self.lib.adb_launch_count())
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self.lib.adb_set_stream(C.c_void_p(cuda_stream_ptr)))
+
+    # ---- operators (thin: arguments in, device buffers out) -------------------------------
+    def select_scan(self, col: DevBuf, n: int, lo=None, hi=None, base: int = 0,
+                    out: DevBuf | None = None, d_count: DevBuf | None = None, sync: bool = True,
+                    col_offset: int = 0):
+        """select_column_scan (query.c:92).  Returns (pos DevBuf, d_count DevBuf, count|None)."""
+        out = out or self.alloc_i32(n)
+        d_count = d_count or self.alloc(8)
+        (plo, _a), (phi, _b) = _bound(lo), _bound(hi)
+        h = C.c_int64(-1)
+        self._ck(self.lib.adb_select_scan(col.i32(col_offset), n, plo, phi, base, out.i32(),
+                                          d_count.i64(), C.byref(h) if sync else None))
+        return out, d_count, (int(h.value) if sync else None)
+
+    def select_pairs(self, val: DevBuf, pos: DevBuf, n_max: int, lo=None, hi=None,
+                     d_n: DevBuf | None = None, sync: bool = True):
+        """select_result (query.c:38)."""
+        out, d_count = self.alloc_i32(n_max), self.alloc(8)
+        (plo, _a), (phi, _b) = _bound(lo), _bound(hi)
+        h = C.c_int64(-1)
+        self._ck(self.lib.adb_select_pairs(val.i32(), pos.i32(), n_max, d_n.i64() if d_n else None,
+                                           plo, phi, out.i32(), d_count.i64(),
+                                           C.byref(h) if sync else None))
+        return out, d_count, (int(h.value) if sync else None)
+
+    def fetch(self, col: DevBuf, pos: DevBuf, n_max: int, d_n: DevBuf | None = None, base: int = 0,
+              out: DevBuf | None = None) -> DevBuf:
+        """fetch_column (query.c:223)."""
+        out = out or self.alloc_i32(n_max)
+        self._ck(self.lib.adb_fetch(col.i32(), pos.i32(), n_max, d_n.i64() if d_n else None, base,
+                                    out.i32()))
+        return out
+
+    def aggregate(self, val: DevBuf, n_max: int, d_n: DevBuf | None = None, offset: int = 0) -> Agg:
+        """sum / average / min / max partials in one pass (query.c:306-437)."""
+        d_out = self.alloc(C.sizeof(_AggStruct))
+        h = _AggStruct()
+        self._ck(self.lib.adb_aggregate(val.i32(offset), n_max, d_n.i64() if d_n else None,
+                                        C.cast(d_out.void(), C.POINTER(_AggStruct)), C.byref(h)))
+        d_out.free()
+        return Agg(h.sum, h.count, h.min, h.max)
+
+    def ewise(self, a: DevBuf, b: DevBuf, n_max: int, subtract: bool, d_n: DevBuf | None = None) -> DevBuf:
+        """add / sub (query.c:356,374)."""
+        out = self.alloc_i32(n_max)
+        fn = self.lib.adb_sub if subtract else self.lib.adb_add
+        self._ck(fn(a.i32(), b.i32(), n_max, d_n.i64() if d_n else None, out.i32()))
+        return out
+
+    def synth_uniform(self, n: int, seed: int, first_row: int = 0, lo: int = 0,
+                      span: int = 1 << 31, out: DevBuf | None = None, out_offset: int = 0) -> DevBuf:
+        out = out or self.alloc_i32(n)
+        self._ck(self.lib.adb_synth_uniform(out.i32(out_offset), n, seed, first_row, lo, span))
+        return out
+
+    def agg_ptr(self, buf: DevBuf, index: int = 0):
+        return C.cast(buf.void(index * C.sizeof(_AggStruct)), C.POINTER(_AggStruct))
+
+    def read_agg(self, buf: DevBuf, index: int = 0) -> Agg:
+        raw = buf.to_host(C.sizeof(_AggStruct), np.uint8, index * C.sizeof(_AggStruct))
+        h = _AggStruct.from_buffer_copy(raw.tobytes())
+        return Agg(h.sum, h.count, h.min, h.max)
+
+
+AGG_BYTES = C.sizeof(_AggStruct)

@@ -1,0 +1,138 @@
+/*
+ * adb_engine.h -- C-ABI of the B200 operator engine (libadb_b200.so).
+ *
+ * This is the drop-in boundary for the reference column store's operator path: the
+ * functions a C host (the reference's server.c dispatcher through the query.h shim in
+ * analytical-database_b200/host/query_shim.c, or any FFI) binds instead of the loops in
+ * /root/reference/src/query.c, multimap.c and the lookup half of index.c.  Plain
+ * pointers and sizes only.  Each entry point cites the reference interface it
+ * replaces (path:line under /root/reference).
+ *
+ * Conventions
+ *  - Every function returns ADB_OK (0) or a negative adb_status; adb_last_error()
+ *    returns the message of the calling thread's last failure.  There is no CPU
+ *    fallback: without a CUDA device adb_init() fails and every operator returns
+ *    ADB_ERR_NOT_INITIALISED.
+ *  - Pointers named d_* are device (HBM) addresses obtained from adb_alloc(); all
+ *    others are host addresses.  Columns, position lists and value vectors are int32
+ *    (reference: `int`, src/include/cs165_api.h:77-92,179-183); row counts and hit
+ *    counts are int64 but must stay below 2^31 per column shard because positions
+ *    are int32 (src/query.c:94-95).
+ *  - An absent range bound is a NULL `lo` / `hi` pointer, exactly as the dispatcher
+ *    passes it (src/server.c:144-154).  The predicate is lo <= v < hi
+ *    (src/query.c:101).
+ *  - Operators are enqueued on the engine stream (adb_stream()); they are asynchronous
+ *    unless a host out-parameter (h_count, h_value ...) is non-NULL, in which case the
+ *    call synchronises and fills it.  Every operator that produces a variable-length
+ *    result also writes its length to a device int64 (d_count) so the next operator
+ *    can consume it without a host round trip.
+ */
+#ifndef ADB_ENGINE_H
+#define ADB_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADB_API __attribute__((visibility("default")))
+
+typedef int32_t adb_status;
+enum {
+    ADB_OK = 0,
+    ADB_ERR_NOT_INITIALISED = -1,
+    ADB_ERR_CUDA = -2,          /* a CUDA runtime call failed; see adb_last_error() */
+    ADB_ERR_INVALID = -3,       /* bad argument (NULL pointer, n >= 2^31, misalignment) */
+    ADB_ERR_NOMEM = -4,
+    ADB_ERR_NCCL = -5
+};
+
+/* ---- lifecycle (no reference equivalent; SURVEY.md section 8b "new hooks") ---------- */
+ADB_API adb_status adb_init(int device_ordinal);      /* call from main(), src/server.c:616 */
+ADB_API adb_status adb_shutdown(void);                /* call from shutdown_server(), src/server.c:40 */
+ADB_API const char *adb_last_error(void);
+ADB_API const char *adb_version(void);
+ADB_API int adb_sm_count(void);
+
+/* ---- device memory and stream plumbing ----------------------------------------------- */
+ADB_API adb_status adb_alloc(void **d_ptr, size_t bytes);            /* stream-ordered pool */
+ADB_API adb_status adb_free(void *d_ptr);
+ADB_API adb_status adb_upload(void *d_dst, const void *h_src, size_t bytes);     /* H2D, synchronous */
+ADB_API adb_status adb_download(void *h_dst, const void *d_src, size_t bytes);   /* D2H, synchronous */
+ADB_API adb_status adb_upload_async(void *d_dst, const void *h_src, size_t bytes);
+ADB_API adb_status adb_download_async(void *h_dst, const void *d_src, size_t bytes);
+ADB_API adb_status adb_memset(void *d_dst, int byte, size_t bytes);
+ADB_API adb_status adb_sync(void);
+ADB_API void *adb_stream(void);                       /* the cudaStream_t operators run on */
+ADB_API adb_status adb_set_stream(void *cuda_stream); /* adopt a caller's stream (NULL = legacy default) */
+ADB_API adb_status adb_host_alloc(void **h_ptr, size_t bytes);       /* pinned host memory */
+ADB_API adb_status adb_host_free(void *h_ptr);
+/* CUDA-event stopwatch on the engine stream: start, run operators, stop -> milliseconds. */
+ADB_API adb_status adb_timer_start(void);
+ADB_API adb_status adb_timer_stop(float *ms);
+/* number of engine kernels launched since adb_init (bench.py's gpu_launches) */
+ADB_API int64_t adb_launch_count(void);
+
+/* ---- range select over a base column -- replaces select_column_scan, src/query.c:92-137
+ * d_pos_out must hold n int32 (the reference mallocs row_count ints, query.c:94).
+ * Emits base_pos + row for every row with lo <= d_col[row] < hi, ascending.
+ * d_count (device int64, required) receives the hit count; h_count optional. */
+ADB_API adb_status adb_select_scan(const int32_t *d_col, int64_t n, const int32_t *lo, const int32_t *hi,
+                           int32_t base_pos, int32_t *d_pos_out, int64_t *d_count,
+                           int64_t *h_count);
+
+/* ---- range select over a (value, position) pair list -- replaces select_result,
+ * src/query.c:38-86.  n_max bounds the input length; when d_n is non-NULL the actual
+ * length is read from that device int64 (<= n_max). */
+ADB_API adb_status adb_select_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n_max,
+                            const int64_t *d_n, const int32_t *lo, const int32_t *hi,
+                            int32_t *d_pos_out, int64_t *d_count, int64_t *h_count);
+
+/* ---- fetch (gather) -- replaces fetch_column, src/query.c:223-243
+ * d_val_out[i] = d_col[d_pos[i] - base_pos], i < n (n from d_n when non-NULL). */
+ADB_API adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
+                     const int64_t *d_n, int32_t base_pos, int32_t *d_val_out);
+
+/* ---- aggregates -- replace sum / average / min / max, src/query.c:306-437
+ * One pass produces all three partials; sum is int64 (query.c:326-327).  Empty input:
+ * sum 0, min INT32_MAX, max INT32_MIN (the reference reads payload[0], query.c:395,420:
+ * oracle-undefined).  average = (double)sum / (double)count on the host
+ * (query.c:314).  d_out is a device adb_agg; h_out optional (synchronises). */
+typedef struct adb_agg {
+    int64_t sum;
+    int64_t count;
+    int32_t min;
+    int32_t max;
+} adb_agg;
+ADB_API adb_status adb_aggregate(const int32_t *d_val, int64_t n_max, const int64_t *d_n,
+                         adb_agg *d_out, adb_agg *h_out);
+/* Combine `k` device partials (one per shard) into d_out[0] on the device. */
+ADB_API adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, adb_agg *h_out);
+
+/* ---- element-wise add / sub -- replace add / sub, src/query.c:356-390 (int32, wraps) */
+ADB_API adb_status adb_add(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
+                   int32_t *d_out);
+ADB_API adb_status adb_sub(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
+                   int32_t *d_out);
+
+/* ---- fused north-star chain: select -> fetch -> sum/min/max on one shard ---------------
+ * Equivalent to adb_select_scan + adb_fetch + adb_aggregate with the position list and
+ * the fetched values still materialised in d_pos_out / d_val_out (the handles stay
+ * observable, src/server.c:184,205), enqueued back to back with no host round trip. */
+ADB_API adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d_fetch_col,
+                                      int64_t n, const int32_t *lo, const int32_t *hi,
+                                      int32_t *d_pos_out, int32_t *d_val_out,
+                                      int64_t *d_count, adb_agg *d_agg);
+
+/* ---- synthetic data (bench / tests): counter-based generator, identical on host ------
+ * d_out[i] = lo + mix64(seed, first_row + i) % span, the same sequence
+ * analytical-database_b200/synth.py produces with numpy. */
+ADB_API adb_status adb_synth_uniform(int32_t *d_out, int64_t n, uint64_t seed, uint64_t first_row,
+                             int32_t lo, uint32_t span);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADB_ENGINE_H */
