@@ -119,6 +119,8 @@ int launch_fetch(const int32_t *col, const int32_t *pos, int64_t n_max, const in
 int launch_aggregate(const int32_t *v, int64_t n_max, const int64_t *d_n, adb_agg *out,
                       adb_agg *scratch, unsigned int *ticket, int sm_count, cudaStream_t s);
 int launch_agg_combine(const adb_agg *parts, int32_t k, adb_agg *out, cudaStream_t s);
+int launch_agg_export(const adb_agg *a, int64_t *sum_count, int32_t *max_notmin, cudaStream_t s);
+int launch_agg_import(const int64_t *sum_count, const int32_t *max_notmin, adb_agg *a, cudaStream_t s);
 int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_t *d_n,
                   int32_t *out, bool subtract, int sm_count, cudaStream_t s);
 int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,

@@ -21,6 +21,7 @@ struct Engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t marks[ADB_MAX_MARKS] = {};
     // select look-back state
     unsigned long long *status = nullptr;
     uint32_t epoch = 0;
@@ -143,6 +144,8 @@ adb_status adb_shutdown(void) {
     cudaFree(g.agg_ticket);
     cudaEventDestroy(g.ev0);
     cudaEventDestroy(g.ev1);
+    for (cudaEvent_t &m : g.marks)
+        if (m) cudaEventDestroy(m);
     if (g.own_stream) cudaStreamDestroy(g.stream);
     g = Engine{};
     return ADB_OK;
@@ -226,6 +229,23 @@ adb_status adb_timer_stop(float *ms) {
     return ADB_OK;
 }
 
+adb_status adb_mark(int32_t slot) {
+    NEED_UP();
+    if (slot < 0 || slot >= ADB_MAX_MARKS) return fail(ADB_ERR_INVALID, "adb_mark: slot %d out of range", slot);
+    if (!g.marks[slot]) CU(cudaEventCreate(&g.marks[slot]));
+    CU(cudaEventRecord(g.marks[slot], g.stream));
+    return ADB_OK;
+}
+adb_status adb_mark_elapsed(int32_t from_slot, int32_t to_slot, float *ms) {
+    NEED_UP();
+    if (from_slot < 0 || from_slot >= ADB_MAX_MARKS || to_slot < 0 || to_slot >= ADB_MAX_MARKS ||
+        !g.marks[from_slot] || !g.marks[to_slot] || !ms)
+        return fail(ADB_ERR_INVALID, "adb_mark_elapsed: unrecorded or invalid slot");
+    CU(cudaEventSynchronize(g.marks[to_slot]));
+    CU(cudaEventElapsedTime(ms, g.marks[from_slot], g.marks[to_slot]));
+    return ADB_OK;
+}
+
 // ---- operators ---------------------------------------------------------------------------
 static adb_status finish_count(int64_t *d_count, int64_t *h_count) {
     if (!h_count) return ADB_OK;
@@ -302,6 +322,17 @@ adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, ad
         CU(cudaStreamSynchronize(g.stream));
     }
     return ADB_OK;
+}
+
+adb_status adb_agg_export(const adb_agg *d_agg, int64_t *d_sum_count, int32_t *d_max_notmin) {
+    NEED_UP();
+    if (!d_agg || !d_sum_count || !d_max_notmin) return fail(ADB_ERR_INVALID, "adb_agg_export: NULL pointer");
+    return after_launch("agg_export", adb::launch_agg_export(d_agg, d_sum_count, d_max_notmin, g.stream));
+}
+adb_status adb_agg_import(const int64_t *d_sum_count, const int32_t *d_max_notmin, adb_agg *d_agg) {
+    NEED_UP();
+    if (!d_agg || !d_sum_count || !d_max_notmin) return fail(ADB_ERR_INVALID, "adb_agg_import: NULL pointer");
+    return after_launch("agg_import", adb::launch_agg_import(d_sum_count, d_max_notmin, d_agg, g.stream));
 }
 
 static adb_status ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_t *d_n,

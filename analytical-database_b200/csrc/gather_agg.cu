@@ -167,6 +167,28 @@ __global__ void agg_combine_kernel(const adb_agg *__restrict__ parts, int32_t k,
     if (threadIdx.x == 0) *out = adb_agg{g.sum, cnt, g.mn, g.mx};
 }
 
+// Split a partial into allreduce-ready operands: {sum, count} for ncclSum and
+// {max, ~min} for ncclMax (~x = -x-1 reverses the order without overflowing).
+__global__ void agg_export_kernel(const adb_agg *__restrict__ a, int64_t *__restrict__ sum_count,
+                                  int32_t *__restrict__ max_notmin) {
+    sum_count[0] = a->sum;
+    sum_count[1] = a->count;
+    max_notmin[0] = a->max;
+    max_notmin[1] = ~a->min;
+}
+__global__ void agg_import_kernel(const int64_t *__restrict__ sum_count,
+                                  const int32_t *__restrict__ max_notmin, adb_agg *__restrict__ a) {
+    *a = adb_agg{sum_count[0], sum_count[1], ~max_notmin[1], max_notmin[0]};
+}
+int launch_agg_export(const adb_agg *a, int64_t *sum_count, int32_t *max_notmin, cudaStream_t s) {
+    agg_export_kernel<<<1, 1, 0, s>>>(a, sum_count, max_notmin);
+    return 1;
+}
+int launch_agg_import(const int64_t *sum_count, const int32_t *max_notmin, adb_agg *a, cudaStream_t s) {
+    agg_import_kernel<<<1, 1, 0, s>>>(sum_count, max_notmin, a);
+    return 1;
+}
+
 // ---- element-wise add / sub (int32, two's-complement wrap) ------------------------------
 template <bool SUB>
 __global__ void __launch_bounds__(STREAM_THREADS)

@@ -115,11 +115,15 @@ class Engine:
         "adb_timer_start": (C.c_int32, []),
         "adb_timer_stop": (C.c_int32, [C.POINTER(C.c_float)]),
         "adb_launch_count": (C.c_int64, []),
+        "adb_mark": (C.c_int32, [C.c_int32]),
+        "adb_mark_elapsed": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
         "adb_select_scan": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I32P, _I64P, _I64P]),
         "adb_select_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P, _I32P, _I32P, _I64P, _I64P]),
         "adb_fetch": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, C.c_int32, _I32P]),
         "adb_aggregate": (C.c_int32, [_I32P, C.c_int64, _I64P, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_agg_combine": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
+        "adb_agg_export": (C.c_int32, [C.POINTER(_AggStruct), C.c_void_p, C.c_void_p]),
+        "adb_agg_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(_AggStruct)]),
         "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_sub": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_chain_select_fetch_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P, C.POINTER(_AggStruct)]),
@@ -169,6 +173,14 @@ class Engine:
     def timer_stop(self) -> float:
         ms = C.c_float(0)
         self._ck(self.lib.adb_timer_stop(C.byref(ms)))
+        return float(ms.value)
+
+    def mark(self, slot: int):
+        self._ck(self.lib.adb_mark(slot))
+
+    def mark_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._ck(self.lib.adb_mark_elapsed(a, b, C.byref(ms)))
         return float(ms.value)
 
     def launch_count(self) -> int:

@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py -- the north-star measurement: rows/s for select -> fetch -> sum/min/max over
+the 4 B-row int32 table of BASELINE.json config 5, row-range partitioned into 8 shards of
+500 M rows (positions are int32, /root/reference/src/query.c:94-95, so a shard must stay
+below 2^31 rows) spread over N B200s, aggregate partials combined with an NCCL allreduce.
+
+One "step" = one pass of the chain over every shard of the table on every rank:
+  s = select(tbl.col1, lo, hi)      adb_select_scan   (query.c:92)
+  f = fetch(tbl.col2, s)            adb_fetch         (query.c:223)
+  a = sum(f) / min(f) / max(f)      adb_aggregate     (query.c:325,392,417)
+with the position list and the fetched vector materialised, as the operator API defines.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            engine arm
+  python bench.py --impl reference ...                           reference CPU arm
+N > 1 is launched by torchrun (one rank per GPU); total work is fixed (strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_ROWS = 4_000_000_000
+N_SHARDS = 8
+SEED = 42
+SPAN = 1 << 30                       # col1 uniform in [0, 2^30)
+FETCH_LO, FETCH_SPAN = 2**31 - 10000, 10000     # col2 near INT_MAX (milestone1.py:119)
+METRIC = "rows/sec for select+fetch+sum"
+UNIT = "rows/s"
+
+
+def predicate(selectivity: float):
+    lo = 1000
+    return lo, lo + int(SPAN * selectivity)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
+                          for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU operators on the host cores
+# ------------------------------------------------------------------------------------------
+def host_columns(rows: int, first_row: int, threads: int):
+    """The same rows the GPU scans, regenerated on the host (counter-based generator)."""
+    from analytical_database_b200 import synth
+    from concurrent.futures import ThreadPoolExecutor
+    sel = np.empty(rows, np.int32)
+    fet = np.empty(rows, np.int32)
+    chunk = 1 << 24
+
+    def fill(b):
+        e = min(rows, b + chunk)
+        sel[b:e] = synth.uniform(e - b, SEED, first_row + b, 0, SPAN)
+        fet[b:e] = synth.uniform(e - b, SEED + 1, first_row + b, FETCH_LO, FETCH_SPAN)
+
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        list(ex.map(fill, range(0, rows, chunk)))
+    return sel, fet
+
+
+def cpu_ops():
+    from oracle import oracle
+    ref = oracle.reference("O2")
+    if ref is not None:
+        return ref, "reference", "oracle/_ref/libref_O2.so = unmodified reference query.c at -O2"
+    return oracle.port(), "port", "oracle/liboracle.so restatement at -O2"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    ops, kind, what = cpu_ops()
+    lo, hi = predicate(args.selectivity)
+    rows = args.cpu_rows
+    sel, fet = host_columns(rows, 0, cores)
+    for _ in range(args.warmup):
+        ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s, h = ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32 (int64 accumulate)", "data": "synthetic",
+        "config": workload_config(args, rows_per_step=rows),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{rows} rows of the same table per step, one reference "
+                                   f"instance per row range on {cores} threads; {what}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "check": {"sum": s, "hits": h},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, rows_per_step):
+    return {
+        "workload": "BASELINE config 5: 4B-row multi-column int32 table row-partitioned "
+                    "across 1/2/4/8 B200: select+fetch+sum/min/max with NCCL allreduce",
+        "total_rows": TOTAL_ROWS, "shards": N_SHARDS, "rows_per_shard": TOTAL_ROWS // N_SHARDS,
+        "rows_per_step": rows_per_step, "selectivity": args.selectivity,
+        "columns": "col1 uniform [0,2^30) (select), col2 uniform [2^31-10000,2^31) (fetch)",
+        "l2": "inputs exceed L2 (>= 2 GB per shard column vs 126 MB)",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# engine arm
+# ------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import analytical_database_b200 as adb
+    from analytical_database_b200.engine import AGG_BYTES
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = adb.Engine(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)          # engine kernels and NCCL share one stream
+    torch.cuda.set_stream(stream)
+
+    lo, hi = predicate(args.selectivity)
+    shard_rows = TOTAL_ROWS // N_SHARDS
+    my_shards = [s for s in range(N_SHARDS) if s % world == rank] if world > 1 else list(range(N_SHARDS))
+    if args.shards_limit:
+        my_shards = my_shards[:args.shards_limit]
+    # ---- load: columns become HBM-resident int32 arrays -------------------------------
+    cols = []
+    for s in my_shards:
+        c1 = eng.synth_uniform(shard_rows, SEED, s * shard_rows, 0, SPAN)
+        c2 = eng.synth_uniform(shard_rows, SEED + 1, s * shard_rows, FETCH_LO, FETCH_SPAN)
+        cols.append((c1, c2))
+    cap = int(shard_rows * min(1.0, args.selectivity * 1.5 + 0.001)) + 4096
+    # one (pos, val, count) result set per shard: every handle stays materialised
+    res = [(eng.alloc_i32(cap), eng.alloc_i32(cap), eng.alloc(8)) for _ in my_shards]
+    parts = eng.alloc(AGG_BYTES * max(len(my_shards), 1))
+    # the allreduce operands live in torch tensors (plumbing for NCCL)
+    t_sum = torch.zeros(2, dtype=torch.int64, device="cuda")      # {sum, count}
+    t_mm = torch.zeros(2, dtype=torch.int32, device="cuda")       # {max, ~min}
+    combined = eng.alloc(AGG_BYTES)
+    blo, bhi = C.c_int32(lo), C.c_int32(hi)
+    lib = eng.lib
+    AggP = eng.agg_ptr
+
+    def step(mark_base=None):
+        for i, (c1, c2) in enumerate(cols):
+            pos, val, cnt = res[i]
+            if mark_base is not None:
+                eng.mark(mark_base + 2 * i)
+            eng._ck(lib.adb_select_scan(c1.i32(), shard_rows, C.byref(blo), C.byref(bhi), 0,
+                                        pos.i32(), cnt.i64(), None))
+            if mark_base is not None:
+                eng.mark(mark_base + 2 * i + 1)
+            eng._ck(lib.adb_fetch(c2.i32(), pos.i32(), cap, cnt.i64(), 0, val.i32()))
+            eng._ck(lib.adb_aggregate(val.i32(), cap, cnt.i64(), AggP(parts, i), None))
+        eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
+        if dist is not None:
+            eng._ck(lib.adb_agg_export(AggP(combined), C.c_void_p(t_sum.data_ptr()),
+                                       C.c_void_p(t_mm.data_ptr())))
+            dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_mm, op=dist.ReduceOp.MAX)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    marks_per_step = 2 * len(cols)
+    timed_marks = args.steps * marks_per_step <= 8000
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k * marks_per_step if timed_marks else None)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    rows_step = shard_rows * (len(my_shards) * world if args.shards_limit else N_SHARDS)
+    ms_step = ms_total / args.steps
+    value = rows_step / (ms_step * 1e-3)
+
+    # ---- result of the last step (device-resident) -----------------------------------------
+    if dist is not None:
+        g_sum, g_cnt = int(t_sum[0].item()), int(t_sum[1].item())
+        g_max, g_min = int(t_mm[0].item()), ~int(t_mm[1].item())
+    else:
+        a = eng.read_agg(combined)
+        g_sum, g_cnt, g_min, g_max = a.sum, a.count, a.min, a.max
+
+    # ---- roofline of the dominant kernel (select_kernel), from the in-region event marks -----
+    peak, peak_src = measured_peak()
+    hits_local = [int(r[2].to_host(1, np.int64)[0]) for r in res]
+    sel_ms = []
+    if timed_marks:
+        for k in range(args.steps):
+            for i in range(len(cols)):
+                sel_ms.append(eng.mark_elapsed(k * marks_per_step + 2 * i, k * marks_per_step + 2 * i + 1))
+    roofline = None
+    if sel_ms:
+        avg_ms = float(np.mean(sel_ms))
+        alg_bytes = 4.0 * shard_rows + 4.0 * float(np.mean(hits_local))
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "select_kernel_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "adb::select_kernel<false>", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "share_of_step": float(np.sum(sel_ms) / ms_total)}
+    chain_bytes = 4.0 * rows_step + 20.0 * g_cnt
+    chain_gbs = chain_bytes / (ms_step * 1e-3) / 1e9
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(world, 1),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 (int64 accumulate)", "data": "synthetic",
+            "config": workload_config(args, rows_step),
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "chain": {"algorithmic_bytes_per_step": chain_bytes, "achieved_gbs": chain_gbs,
+                      "frac_of_aggregate_peak": chain_gbs / (peak * max(world, 1)),
+                      "formula": "4N + 20H (SURVEY.md 8d)"},
+            "result": {"sum": g_sum, "count": g_cnt, "min": g_min, "max": g_max},
+        }
+
+    # ---- e2e and cpu_baseline (rank 0; the CPU leg only at N = 1) ----------------------------
+    e2e = measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
+                      combined, parts)
+    if rank == 0:
+        line["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = measure_cpu(args, eng, cols, res, shard_rows, lo, hi)
+        print(json.dumps(line))
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
+                combined, parts):
+    """The same chain through the host-facing calls: every operator returns its num_tuples
+    to the host before the next is issued (Result.num_tuples must be host-visible,
+    parse.c:799), bounds come from host memory, and the aggregate is read back (D2H)
+    every step.  Columns are HBM-resident after load, as the reference keeps them in RAM
+    after load.  `cold` additionally re-uploads both columns of one shard from pinned host
+    memory inside the timed region (the first-touch cost of a table)."""
+    import torch
+    lib = eng.lib
+    blo, bhi = C.c_int32(lo), C.c_int32(hi)
+    h_cnt = C.c_int64(0)
+    from analytical_database_b200.engine import _AggStruct, AGG_BYTES
+    h_agg = _AggStruct()
+
+    def step():
+        tot = 0
+        for i, (c1, c2) in enumerate(cols):
+            pos, val, cnt = res[i]
+            eng._ck(lib.adb_select_scan(c1.i32(), shard_rows, C.byref(blo), C.byref(bhi), 0,
+                                        pos.i32(), cnt.i64(), C.byref(h_cnt)))      # D2H 8 B
+            h = h_cnt.value
+            eng._ck(lib.adb_fetch(c2.i32(), pos.i32(), h, None, 0, val.i32()))
+            eng._ck(lib.adb_aggregate(val.i32(), h, None, eng.agg_ptr(parts, i), None))
+            tot += h
+        eng._ck(lib.adb_agg_combine(eng.agg_ptr(parts), len(cols), eng.agg_ptr(combined),
+                                    C.byref(h_agg)))                                # D2H 24 B
+        if dist is not None:
+            eng._ck(lib.adb_agg_export(eng.agg_ptr(combined), C.c_void_p(t_sum.data_ptr()),
+                                       C.c_void_p(t_mm.data_ptr())))
+            dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_mm, op=dist.ReduceOp.MAX)
+            return int(t_sum[0].item())                                             # D2H 8 B
+        return h_agg.sum
+
+    steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    rows_step = shard_rows * len(cols) * max(world, 1)
+    out = {"value": rows_step * steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": 8 * len(cols),          # the two int32 bounds per operator call
+           "d2h_bytes_per_step": 8 * len(cols) + 24,
+           "ms_per_step": 1e3 * dt / steps, "steps": steps,
+           "mode": "warm: columns HBM-resident after load; per operator the host waits for "
+                   "num_tuples; aggregate read back every step; wall clock"}
+    # cold: one shard's two columns uploaded from pinned host memory inside the timed region
+    if rank == 0 and world == 1 and not args.no_cold:
+        nbytes = 4 * shard_rows
+        hp1, hp2 = C.c_void_p(), C.c_void_p()
+        eng._ck(lib.adb_host_alloc(C.byref(hp1), nbytes))
+        eng._ck(lib.adb_host_alloc(C.byref(hp2), nbytes))
+        c1, c2 = cols[0]
+        eng._ck(lib.adb_download(hp1, c1.void(), nbytes))
+        eng._ck(lib.adb_download(hp2, c2.void(), nbytes))
+        pos, val, cnt = res[0]
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng._ck(lib.adb_upload_async(c1.void(), hp1, nbytes))
+            eng._ck(lib.adb_upload_async(c2.void(), hp2, nbytes))
+            eng._ck(lib.adb_select_scan(c1.i32(), shard_rows, C.byref(blo), C.byref(bhi), 0,
+                                        pos.i32(), cnt.i64(), C.byref(h_cnt)))
+            eng._ck(lib.adb_fetch(c2.i32(), pos.i32(), h_cnt.value, None, 0, val.i32()))
+            eng._ck(lib.adb_aggregate(val.i32(), h_cnt.value, None, eng.agg_ptr(parts, 0),
+                                      C.byref(h_agg)))
+        dtc = time.perf_counter() - t0
+        out["cold"] = {"value": shard_rows * reps / dtc, "unit": UNIT,
+                       "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 32,
+                       "sample": f"one {shard_rows}-row shard, both columns uploaded from pinned "
+                                 "host memory every step (PCIe-bound)"}
+        lib.adb_host_free(hp1)
+        lib.adb_host_free(hp2)
+    return out
+
+
+def measure_cpu(args, eng, cols, res, shard_rows, lo, hi):
+    """The reference's CPU operators on a bounded sample of the same table, on the box's
+    host cores, checked against the GPU's result for the same rows."""
+    ops, kind, what = cpu_ops()
+    cores = os.cpu_count() or 1
+    rows = min(args.cpu_rows, shard_rows)
+    c1, c2 = cols[0]
+    sel, fet = c1.to_host(rows), c2.to_host(rows)          # the very rows the GPU scanned
+    (s1, h1) = ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=1)
+    t0 = time.perf_counter()
+    ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=1)
+    t_single = time.perf_counter() - t0
+    reps, t_all = 0, 0.0
+    ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+    t0 = time.perf_counter()
+    while t_all < 8.0 and reps < 200:
+        s2, h2 = ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+        reps += 1
+        t_all = time.perf_counter() - t0
+    # parity: GPU chain on the same rows
+    pos, val, cnt = res[0]
+    h_cnt = C.c_int64(0)
+    blo, bhi = C.c_int32(lo), C.c_int32(hi)
+    eng._ck(eng.lib.adb_select_scan(c1.i32(), rows, C.byref(blo), C.byref(bhi), 0, pos.i32(),
+                                    cnt.i64(), C.byref(h_cnt)))
+    eng.fetch(c2, pos, h_cnt.value, out=val)
+    g = eng.aggregate(val, h_cnt.value)
+    ok = (g.sum, h_cnt.value) == (s1, h1) == (s2, h2)
+    out = {"value": rows * reps / t_all, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"first {rows} rows of shard 0 (downloaded from HBM: identical rows), "
+                     f"{reps} passes on {cores} threads (one reference instance per row range); {what}",
+           "single_thread_value": rows / t_single, "parity_with_gpu": bool(ok)}
+    from oracle import oracle
+    r0 = oracle.reference("O0")
+    if r0 is not None:
+        t0 = time.perf_counter()
+        r0.chain_select_fetch_sum(sel, fet, lo, hi, threads=1)
+        out["single_thread_O0_value"] = rows / (time.perf_counter() - t0)
+    if not ok:
+        raise SystemExit(f"PARITY FAILURE: gpu {(g.sum, h_cnt.value)} cpu {(s1, h1)}")
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--selectivity", type=float, default=0.01)
+    ap.add_argument("--cpu-rows", type=int, default=500_000_000)
+    ap.add_argument("--shards-limit", type=int, default=0, help="debug: fewer shards per rank")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cold", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_engine(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

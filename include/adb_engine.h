@@ -72,6 +72,11 @@ ADB_API adb_status adb_host_free(void *h_ptr);
 /* CUDA-event stopwatch on the engine stream: start, run operators, stop -> milliseconds. */
 ADB_API adb_status adb_timer_start(void);
 ADB_API adb_status adb_timer_stop(float *ms);
+/* Per-kernel timing: record CUDA event `slot` on the engine stream between operators,
+ * then read the milliseconds between two recorded slots (synchronises on to_slot). */
+#define ADB_MAX_MARKS 8192
+ADB_API adb_status adb_mark(int32_t slot);
+ADB_API adb_status adb_mark_elapsed(int32_t from_slot, int32_t to_slot, float *ms);
 /* number of engine kernels launched since adb_init (bench.py's gpu_launches) */
 ADB_API int64_t adb_launch_count(void);
 
@@ -110,6 +115,11 @@ ADB_API adb_status adb_aggregate(const int32_t *d_val, int64_t n_max, const int6
                          adb_agg *d_out, adb_agg *h_out);
 /* Combine `k` device partials (one per shard) into d_out[0] on the device. */
 ADB_API adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, adb_agg *h_out);
+
+/* Multi-GPU: split a device partial into allreduce operands -- {sum, count} (int64 x 2,
+ * ncclSum) and {max, ~min} (int32 x 2, ncclMax) -- and fold the reduced operands back. */
+ADB_API adb_status adb_agg_export(const adb_agg *d_agg, int64_t *d_sum_count, int32_t *d_max_notmin);
+ADB_API adb_status adb_agg_import(const int64_t *d_sum_count, const int32_t *d_max_notmin, adb_agg *d_agg);
 
 /* ---- element-wise add / sub -- replace add / sub, src/query.c:356-390 (int32, wraps) */
 ADB_API adb_status adb_add(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
