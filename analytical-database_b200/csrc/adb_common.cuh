@@ -108,11 +108,13 @@ struct SelectArgs {
     int32_t base_pos;
     int32_t *out;
     int64_t *d_count;
-    unsigned long long *status;   // per-tile look-back words
-    uint32_t epoch;               // 30-bit launch tag; stale words never match
+    uint32_t *mask;               // selection bitmap scratch (select_mask_words() words)
+    uint32_t *counts;             // per-warp-chunk hit counts (kMaxSelectChunks)
+    int sm_count;
 };
 int launch_select(const SelectArgs &a, cudaStream_t s);
-uint32_t select_tile_count(uint32_t n);
+size_t select_mask_words(uint32_t n, int sm_count);
+constexpr uint32_t kMaxSelectChunks = 1u << 16;
 
 int launch_fetch(const int32_t *col, const int32_t *pos, int64_t n_max, const int64_t *d_n,
                   int32_t base_pos, int32_t *out, int sm_count, cudaStream_t s);

@@ -22,9 +22,10 @@ struct Engine {
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t marks[ADB_MAX_MARKS] = {};
-    // select look-back state
-    unsigned long long *status = nullptr;
-    uint32_t epoch = 0;
+    // select scratch: selection bitmap (grown on demand) + per-chunk counts
+    uint32_t *sel_mask = nullptr;
+    size_t sel_mask_words = 0;
+    uint32_t *sel_counts = nullptr;
     // aggregate fold state
     adb_agg *agg_scratch = nullptr;
     unsigned int *agg_ticket = nullptr;
@@ -32,7 +33,6 @@ struct Engine {
     int64_t launches = 0;
 } g;
 
-constexpr uint32_t kMaxTiles = (1u << 31) / 4096 + 1;
 
 adb_status fail(adb_status code, const char *fmt, ...) {
     char buf[512];
@@ -83,13 +83,24 @@ adb_status check_len(int64_t n, const char *what) {
     return ADB_OK;
 }
 
-uint32_t next_epoch() {
-    g.epoch = (g.epoch + 1) & 0x3fffffffu;
-    if (g.epoch == 0) {                                   // wrapped: retire every stale word
-        cudaMemsetAsync(g.status, 0, sizeof(unsigned long long) * kMaxTiles, g.stream);
-        g.epoch = 1;
+// The bitmap scratch only ever grows; a select over the largest shard (2^31 rows) needs 256 MB.
+adb_status ensure_select_scratch(uint32_t n) {
+    const size_t need = adb::select_mask_words(n, g.sm_count);
+    if (need <= g.sel_mask_words) return ADB_OK;
+    if (g.sel_mask) {
+        CU(cudaStreamSynchronize(g.stream));
+        CU(cudaFree(g.sel_mask));
+        g.sel_mask = nullptr;
+        g.sel_mask_words = 0;
     }
-    return g.epoch;
+    const size_t words = need + need / 8 + 4096;
+    cudaError_t e = cudaMalloc(&g.sel_mask, words * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ADB_ERR_NOMEM, "select bitmap scratch: %s", cudaGetErrorString(e));
+    }
+    g.sel_mask_words = words;
+    return ADB_OK;
 }
 
 }  // namespace
@@ -124,12 +135,10 @@ adb_status adb_init(int device_ordinal) {
     CU(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
     uint64_t keep = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    CU(cudaMalloc(&g.status, sizeof(unsigned long long) * kMaxTiles));
-    CU(cudaMemset(g.status, 0, sizeof(unsigned long long) * kMaxTiles));
+    CU(cudaMalloc(&g.sel_counts, sizeof(uint32_t) * adb::kMaxSelectChunks));
     CU(cudaMalloc(&g.agg_scratch, sizeof(adb_agg) * adb::kAggMaxBlocks));
     CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int)));
     CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int)));
-    g.epoch = 0;
     g.launches = 0;
     g.up = true;
     return ADB_OK;
@@ -139,7 +148,8 @@ adb_status adb_shutdown(void) {
     if (!g.up) return ADB_OK;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
-    cudaFree(g.status);
+    cudaFree(g.sel_mask);
+    cudaFree(g.sel_counts);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     cudaEventDestroy(g.ev0);
@@ -265,7 +275,8 @@ adb_status adb_select_scan(const int32_t *d_col, int64_t n, const int32_t *lo, c
     a.val = d_col; a.pos_in = nullptr; a.d_n = nullptr; a.n = (uint32_t)n;
     fold_range(lo, hi, &a.range);
     a.base_pos = base_pos; a.out = d_pos_out; a.d_count = d_count;
-    a.status = g.status; a.epoch = next_epoch();
+    if (adb_status s = ensure_select_scratch(a.n)) return s;
+    a.mask = g.sel_mask; a.counts = g.sel_counts; a.sm_count = g.sm_count;
     const int k_ = adb::launch_select(a, g.stream);
     if (adb_status s = after_launch("select_scan", k_)) return s;
     return finish_count(d_count, h_count);
@@ -282,7 +293,8 @@ adb_status adb_select_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t 
     a.val = d_val; a.pos_in = d_pos; a.d_n = d_n; a.n = (uint32_t)n_max;
     fold_range(lo, hi, &a.range);
     a.base_pos = 0; a.out = d_pos_out; a.d_count = d_count;
-    a.status = g.status; a.epoch = next_epoch();
+    if (adb_status s = ensure_select_scratch(a.n)) return s;
+    a.mask = g.sel_mask; a.counts = g.sel_counts; a.sm_count = g.sm_count;
     const int k_ = adb::launch_select(a, g.stream);
     if (adb_status s = after_launch("select_pairs", k_)) return s;
     return finish_count(d_count, h_count);

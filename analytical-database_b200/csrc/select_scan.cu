@@ -1,205 +1,272 @@
-// select_scan.cu -- range select as a single-pass, order-preserving stream compaction.
+// select_scan.cu -- range select as a dependency-free, order-preserving bitmap compaction.
 //
 // Replaces select_column_scan (/root/reference/src/query.c:92-137) and select_result
 // (query.c:38-86).  The reference appends `position[index++] = i` in one sequential
-// loop, so the output must be the ascending list of qualifying rows.  An atomicAdd
-// cursor would be unordered; a count/scan/write design reads the column twice.  This
-// kernel reads every column byte once and writes every hit once (4N + 4H bytes, the
-// algorithmic minimum of SURVEY.md section 8d):
+// loop, so the output must be the ascending list of qualifying rows.
 //
-//   * one CTA per 4096-row tile, 256 threads x 4 x 16-byte streaming loads, laid out so
-//     each warp-wide load is one contiguous 512-byte span (fully coalesced);
-//   * the 16 predicate bits of a thread are ranked with ONE packed warp scan (the four
-//     per-vector hit counts ride in the four bytes of a word) and a block scan over
-//     the eight warp totals;
-//   * tile offsets come from a decoupled look-back over 64-bit {epoch, flag, value}
-//     status words, so tiles never wait for more than their nearest finished
-//     predecessor and nothing is re-read; the epoch tag makes the status array
-//     reusable across launches without a memset;
-//   * sparse tiles store hits straight from registers; dense tiles stage the compacted
-//     tile in shared memory and write it back as fully coalesced rows.
+// r01a tried the textbook single-pass design (decoupled look-back over 16 KB tiles).  ncu
+// showed DRAM traffic == algorithmic bytes but only 24 % of peak: with ~1200 resident
+// tiles the look-back chain, not HBM, was the critical path (profiles/r01a_*).  This
+// version has no inter-CTA dependency at all:
+//
+//   mask_kernel    streams the column once (16-byte loads, one contiguous row range per
+//                  warp, next tile prefetched into registers), writes a 1-bit-per-row
+//                  selection bitmap (N/8 bytes) and one hit count per warp-chunk;
+//   expand_kernel  each CTA sums the counts of the chunks before it (<= 9472 ints, from
+//                  L2), then every warp turns its slice of the bitmap into positions at
+//                  its exact output offset -- sparse words store straight from registers,
+//                  dense words are compacted in shared memory and written as full rows.
+//
+// DRAM traffic: 4N (column) + N/8 + N/8 (bitmap out and back, mostly L2-resident) + 4H
+// (positions) against the algorithmic 4N + 4H of SURVEY.md section 8d.
 #include "adb_common.cuh"
 
 namespace adb {
 
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_WARPS = SEL_THREADS / kWarp;
-constexpr int SEL_VEC = 4;                               // int4 loads per thread
-constexpr int SEL_ITEMS = SEL_VEC * 4;                   // 16 rows per thread
-constexpr int SEL_WARP_ITEMS = kWarp * SEL_ITEMS;        // 512 rows per warp
-constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;        // 4096 rows per CTA
-constexpr uint32_t SEL_DENSE = SEL_TILE / 8;             // >= this many hits: staged write-out
+constexpr int SEL_WARPS = SEL_THREADS / kWarp;           // 8
+constexpr int SEL_VEC = 4;                               // int4 loads per thread per tile
+constexpr int SEL_WTILE = kWarp * SEL_VEC * 4;           // 512 rows per warp-tile (16 mask words)
+constexpr int EXP_WORDS = 4;                             // mask words per lane per step
 
-constexpr unsigned long long kFlagAgg = 1ull << 32;      // tile aggregate available
-constexpr unsigned long long kFlagPfx = 2ull << 32;      // inclusive prefix available
-
-__device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsigned long long flag,
-                                                          uint32_t v) {
-    return ((unsigned long long)epoch << 34) | flag | v;
+// ------------------------------------------------------------------------------------------
+// mask_kernel: warp `c` (global) owns rows [c*chunk_rows, (c+1)*chunk_rows).
+// Bit (4*j + k) of a thread's nibble set is row  tile + 128*j + 4*lane + k, so 8 adjacent
+// lanes own one 32-row mask word; the nibbles are OR-combined with three xor-shuffles.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_tile(int4 (&v)[SEL_VEC], const int32_t *__restrict__ val,
+                                          uint32_t row0, uint32_t lane) {
+#pragma unroll
+    for (int j = 0; j < SEL_VEC; ++j)
+        v[j] = ld_stream(reinterpret_cast<const int4 *>(val + row0 + j * 128 + lane * 4));
 }
 
-// Warp 0 walks the predecessors 32 at a time, nearest first, until it meets a tile whose
-// inclusive prefix is already known.  Returns this tile's exclusive prefix.
-__device__ __forceinline__ uint32_t lookback(const unsigned long long *status, uint32_t epoch,
-                                             int tile, uint32_t lane) {
-    uint32_t excl = 0;
-    int look = tile - 1;
-    while (true) {
-        const int idx = look - (int)lane;
-        unsigned long long w;
-        if (idx >= 0) {
-            do {
-                w = ld_relaxed_u64(status + idx);
-            } while ((uint32_t)(w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
-        } else {
-            w = pack_status(epoch, kFlagPfx, 0);         // before the first tile: prefix 0
+__device__ __forceinline__ uint32_t tile_nibbles(const int4 (&v)[SEL_VEC], const Range &rg) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < SEL_VEC; ++j) {
+        m |= (in_range(v[j].x, rg) ? 1u : 0u) << (4 * j);
+        m |= (in_range(v[j].y, rg) ? 2u : 0u) << (4 * j);
+        m |= (in_range(v[j].z, rg) ? 4u : 0u) << (4 * j);
+        m |= (in_range(v[j].w, rg) ? 8u : 0u) << (4 * j);
+    }
+    return m;
+}
+
+__device__ __forceinline__ uint32_t tile_nibbles_guarded(const int32_t *__restrict__ val,
+                                                         uint32_t row0, uint32_t lane, uint32_t n,
+                                                         const Range &rg) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < SEL_VEC; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = row0 + j * 128 + lane * 4 + k;
+            if (idx < n && in_range(ld_stream(val + idx), rg)) m |= 1u << (4 * j + k);
         }
-        const uint32_t has_pfx = __ballot_sync(kFull, (w & kFlagPfx) != 0);
-        const uint32_t v = (uint32_t)w;
-        if (has_pfx) {
-            const uint32_t first = __ffs(has_pfx) - 1;   // nearest predecessor with a prefix
-            return excl + warp_sum(lane <= first ? v : 0u);
-        }
-        excl += warp_sum(v);
-        look -= kWarp;
+    return m;
+}
+
+// nibbles -> the 16 natural-order mask words of the warp-tile, stored as one 64-byte row
+__device__ __forceinline__ void store_mask_words(uint32_t nib, uint32_t lane,
+                                                 uint32_t *__restrict__ words) {
+    const uint32_t sh = 4 * (lane & 7);
+    uint32_t w[SEL_VEC];
+#pragma unroll
+    for (int j = 0; j < SEL_VEC; ++j) {
+        uint32_t x = ((nib >> (4 * j)) & 0xFu) << sh;
+        x |= __shfl_xor_sync(kFull, x, 1);
+        x |= __shfl_xor_sync(kFull, x, 2);
+        x |= __shfl_xor_sync(kFull, x, 4);
+        w[j] = x;                                       // rows tile + 128*j + 32*(lane>>3) ...
+    }
+    const uint32_t j = lane & 7;                        // lanes with (lane & 7) < 4 write
+    if (j < SEL_VEC) {
+        const uint32_t x = j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+        words[j * 4 + (lane >> 3)] = x;
     }
 }
 
-template <bool PAIRS>
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const SelectArgs a) {
-    __shared__ int32_t s_stage[SEL_TILE];
-    __shared__ uint32_t s_wtot[SEL_WARPS];
-    __shared__ uint32_t s_excl;
-
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x;
-    uint32_t n = a.n;
-    if (a.d_n) {
-        const long long dn = *a.d_n;
-        n = dn < (long long)a.n ? (uint32_t)(dn < 0 ? 0 : dn) : a.n;
+__global__ void __launch_bounds__(SEL_THREADS)
+mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, uint32_t n_host,
+            Range rg, uint32_t chunk_rows, uint32_t num_chunks, uint32_t *__restrict__ mask,
+            uint32_t *__restrict__ counts) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t chunk = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+    if (chunk >= num_chunks) return;
+    uint32_t n = n_host;
+    if (d_n) {
+        const long long dn = *d_n;
+        n = dn < (long long)n_host ? (uint32_t)(dn < 0 ? 0 : dn) : n_host;
     }
-    const uint32_t tile_start = tile * (uint32_t)SEL_TILE;
-    const uint32_t wbase = tile_start + warp * SEL_WARP_ITEMS;
-    const int32_t *__restrict__ val = a.val;
-    const Range rg = a.range;
+    const uint32_t row_begin = chunk * chunk_rows;
+    const uint32_t tiles = chunk_rows / SEL_WTILE;
+    uint32_t *__restrict__ words = mask + row_begin / 32;
+    const bool aligned = (reinterpret_cast<uintptr_t>(val) & 15u) == 0;
+    uint32_t hits = 0;
 
-    // ---- load + predicate: bit (4*j + k) of `mask` is row wbase + 128*j + 4*lane + k ----
-    uint32_t mask = 0;
-    if (tile_start + SEL_TILE <= n && (reinterpret_cast<uintptr_t>(val) & 15u) == 0) {
-        int4 v[SEL_VEC];
+    // number of leading tiles that are completely inside [0, n) -> vector path
+    uint32_t full = 0;
+    if (aligned && n > row_begin) {
+        const uint32_t avail = (n - row_begin) / SEL_WTILE;
+        full = avail < tiles ? avail : tiles;
+    }
+    if (full) {
+        int4 cur[SEL_VEC];
+        load_tile(cur, val, row_begin, lane);
+        for (uint32_t t = 0; t < full; ++t) {
+            int4 nxt[SEL_VEC];
+            if (t + 1 < full) load_tile(nxt, val, row_begin + (t + 1) * SEL_WTILE, lane);
+            const uint32_t nib = tile_nibbles(cur, rg);
+            hits += __popc(nib);
+            store_mask_words(nib, lane, words + t * (SEL_WTILE / 32));
+            if (t + 1 < full) {
 #pragma unroll
-        for (int j = 0; j < SEL_VEC; ++j)
-            v[j] = ld_stream(reinterpret_cast<const int4 *>(val + wbase + j * 128 + lane * 4));
-#pragma unroll
-        for (int j = 0; j < SEL_VEC; ++j) {
-            mask |= (in_range(v[j].x, rg) ? 1u : 0u) << (4 * j);
-            mask |= (in_range(v[j].y, rg) ? 2u : 0u) << (4 * j);
-            mask |= (in_range(v[j].z, rg) ? 4u : 0u) << (4 * j);
-            mask |= (in_range(v[j].w, rg) ? 8u : 0u) << (4 * j);
-        }
-    } else if (tile_start < n) {                         // ragged last tile / unaligned column
-#pragma unroll
-        for (int j = 0; j < SEL_VEC; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t idx = wbase + j * 128 + lane * 4 + k;
-                if (idx < n && in_range(ld_stream(val + idx), rg)) mask |= 1u << (4 * j + k);
+                for (int j = 0; j < SEL_VEC; ++j) cur[j] = nxt[j];
             }
-    }
-
-    // ---- rank: four per-vector counts packed into one word, one warp scan --------------
-    const uint32_t c = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) |
-                       (__popc(mask & 0xF00u) << 16) | (__popc(mask & 0xF000u) << 24);
-    const uint32_t incl = warp_incl_scan(c, lane);       // bytes stay <= 128: no carries
-    const uint32_t tot = __shfl_sync(kFull, incl, 31);
-    const uint32_t ex = incl - c;                        // per-vector exclusive rank in warp
-    const uint32_t t0 = tot & 0xFF, t1 = (tot >> 8) & 0xFF, t2 = (tot >> 16) & 0xFF;
-    const uint32_t wtot = t0 + t1 + t2 + (tot >> 24);
-    // rank (inside the warp) of this thread's first hit in vector j
-    const uint32_t r0 = (ex & 0xFF);
-    const uint32_t r1 = t0 + ((ex >> 8) & 0xFF);
-    const uint32_t r2 = t0 + t1 + ((ex >> 16) & 0xFF);
-    const uint32_t r3 = t0 + t1 + t2 + (ex >> 24);
-
-    if (lane == 0) s_wtot[warp] = wtot;
-    __syncthreads();
-    uint32_t wexcl = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < SEL_WARPS; ++w) {
-        const uint32_t x = s_wtot[w];
-        tile_total += x;
-        if ((uint32_t)w < warp) wexcl += x;
-    }
-
-    // ---- tile offset: decoupled look-back (warp 0) --------------------------------------
-    if (warp == 0) {
-        unsigned long long *st = a.status + tile;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(st, pack_status(a.epoch, kFlagPfx, tile_total));
-        } else {
-            if (lane == 0) st_relaxed_u64(st, pack_status(a.epoch, kFlagAgg, tile_total));
-            excl = lookback(a.status, a.epoch, (int)tile, lane);
-            if (lane == 0) st_relaxed_u64(st, pack_status(a.epoch, kFlagPfx, excl + tile_total));
-        }
-        if (lane == 0) {
-            s_excl = excl;
-            if (tile == gridDim.x - 1) *a.d_count = (int64_t)(excl + tile_total);
         }
     }
-    __syncthreads();
-    if (tile_total == 0) return;
-    const uint32_t tile_excl = s_excl;
+    for (uint32_t t = full; t < tiles; ++t) {            // ragged tail / unaligned view / past n
+        const uint32_t row0 = row_begin + t * SEL_WTILE;
+        const uint32_t nib = row0 < n ? tile_nibbles_guarded(val, row0, lane, n, rg) : 0u;
+        hits += __popc(nib);
+        store_mask_words(nib, lane, words + t * (SEL_WTILE / 32));
+    }
+    hits = warp_sum(hits);
+    if (lane == 0) counts[chunk] = hits;
+}
 
-    // ---- write-out ----------------------------------------------------------------------
-    if (tile_total >= SEL_DENSE) {
-        // dense: compact the tile in shared memory, then stream it out coalesced
-        const uint32_t rr[SEL_VEC] = {r0, r1, r2, r3};
+// ------------------------------------------------------------------------------------------
+// expand_kernel: bitmap -> ascending positions.
+// ------------------------------------------------------------------------------------------
+template <bool PAIRS>
+__global__ void __launch_bounds__(SEL_THREADS)
+expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
+              uint32_t chunk_rows, uint32_t num_chunks, const int32_t *__restrict__ pos_in,
+              int32_t base_pos, int32_t *__restrict__ out, int64_t *__restrict__ d_count) {
+    __shared__ uint32_t s_red[SEL_WARPS];
+    __shared__ int32_t s_stage[SEL_WARPS][kWarp * 32 * EXP_WORDS / 4];   // 1024 positions per warp
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first_chunk = blockIdx.x * SEL_WARPS;
+
+    // exclusive prefix of this CTA: sum of every chunk count before it
+    uint32_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < first_chunk; i += SEL_THREADS) acc += counts[i];
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    uint32_t base = 0;
 #pragma unroll
-        for (int j = 0; j < SEL_VEC; ++j) {
-            uint32_t r = wexcl + rr[j];
+    for (int w = 0; w < SEL_WARPS; ++w) base += s_red[w];
+    uint32_t my_count = 0;
+    for (uint32_t w = 0; w < SEL_WARPS; ++w) {
+        const uint32_t c = first_chunk + w < num_chunks ? counts[first_chunk + w] : 0u;
+        if (w < warp) base += c;
+        if (w == warp) my_count = c;
+    }
+    const uint32_t chunk = first_chunk + warp;
+    if (chunk == num_chunks - 1 && lane == 0) *d_count = (int64_t)base + my_count;
+    if (chunk >= num_chunks || my_count == 0) return;
+
+    const uint32_t row_begin = chunk * chunk_rows;
+    const uint32_t nwords = chunk_rows / 32;
+    const uint32_t *__restrict__ words = mask + row_begin / 32;
+    int32_t *stage = s_stage[warp];
+    uint32_t out_off = base;
+    // each step: lane owns EXP_WORDS consecutive words (128 rows); warp covers 4096 rows
+    for (uint32_t w0 = 0; w0 < nwords && out_off < base + my_count; w0 += kWarp * EXP_WORDS) {
+        const uint32_t wi = w0 + lane * EXP_WORDS;
+        uint4 m = make_uint4(0, 0, 0, 0);
+        if (wi < nwords) m = *reinterpret_cast<const uint4 *>(words + wi);   // nwords % 16 == 0
+        const uint32_t c = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+        const uint32_t incl = warp_incl_scan(c, lane);
+        const uint32_t step_total = __shfl_sync(kFull, incl, 31);
+        if (step_total == 0) continue;
+        uint32_t r = incl - c;                               // rank of this lane's first hit
+        const uint32_t row0 = row_begin + wi * 32;
+        const uint32_t mm[EXP_WORDS] = {m.x, m.y, m.z, m.w};
+        if (step_total <= 2 * kWarp) {
+            // sparse: straight from registers
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (mask & (1u << (4 * j + k))) {
-                    const uint32_t idx = wbase + j * 128 + lane * 4 + k;
-                    s_stage[r++] = PAIRS ? a.pos_in[idx] : (int32_t)idx + a.base_pos;
+            for (int q = 0; q < EXP_WORDS; ++q) {
+                uint32_t bits = mm[q];
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t row = row0 + q * 32 + b;
+                    out[out_off + r++] = PAIRS ? pos_in[row] : (int32_t)row + base_pos;
                 }
+            }
+        } else {
+            // dense: compact into shared memory (<= 1024 at a time), write full rows
+            uint32_t done = 0;                               // positions already flushed
+            while (done < step_total) {
+                const uint32_t lim = done + 1024;
+                uint32_t rr = r;
+#pragma unroll
+                for (int q = 0; q < EXP_WORDS; ++q) {
+                    uint32_t bits = mm[q];
+                    while (bits) {
+                        const uint32_t b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if (rr >= done && rr < lim) {
+                            const uint32_t row = row0 + q * 32 + b;
+                            stage[rr - done] = PAIRS ? pos_in[row] : (int32_t)row + base_pos;
+                        }
+                        ++rr;
+                    }
+                }
+                __syncwarp();
+                const uint32_t cnt = step_total - done < 1024 ? step_total - done : 1024;
+                for (uint32_t i = lane; i < cnt; i += kWarp) out[out_off + done + i] = stage[i];
+                __syncwarp();
+                done += cnt;
+            }
         }
-        __syncthreads();
-        int32_t *__restrict__ out = a.out + tile_excl;
-        for (uint32_t i = threadIdx.x; i < tile_total; i += SEL_THREADS) out[i] = s_stage[i];
-    } else {
-        // sparse: a handful of hits per warp, store them straight from registers
-        const unsigned long long rpack = (unsigned long long)r0 | ((unsigned long long)r1 << 16) |
-                                         ((unsigned long long)r2 << 32) |
-                                         ((unsigned long long)r3 << 48);
-        int32_t *__restrict__ out = a.out + tile_excl + wexcl;
-        uint32_t m = mask;
-        while (m) {
-            const uint32_t b = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t j = b >> 2;
-            const uint32_t below = __popc(mask & ((1u << b) - 1u) & (0xFu << (4 * j)));
-            const uint32_t r = (uint32_t)(rpack >> (16 * j)) & 0xFFFFu;
-            const uint32_t idx = wbase + j * 128 + lane * 4 + (b & 3);
-            out[r + below] = PAIRS ? a.pos_in[idx] : (int32_t)idx + a.base_pos;
-        }
+        out_off += step_total;
     }
 }
 
-uint32_t select_tile_count(uint32_t n) { return (n + SEL_TILE - 1) / SEL_TILE; }
+// ------------------------------------------------------------------------------------------
+// launch geometry shared by both kernels
+// ------------------------------------------------------------------------------------------
+struct SelectGeom {
+    uint32_t chunk_rows, num_chunks, grid;
+};
+static SelectGeom select_geom(uint32_t n, int sm_count) {
+    SelectGeom g{};
+    const uint32_t wtiles = (n + SEL_WTILE - 1) / SEL_WTILE;
+    const uint32_t max_chunks = (uint32_t)sm_count * 8u * SEL_WARPS;      // 8 CTAs per SM resident
+    uint32_t tiles_per_chunk = (wtiles + max_chunks - 1) / max_chunks;
+    if (tiles_per_chunk == 0) tiles_per_chunk = 1;
+    g.chunk_rows = tiles_per_chunk * SEL_WTILE;
+    g.num_chunks = (wtiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    g.grid = (g.num_chunks + SEL_WARPS - 1) / SEL_WARPS;
+    return g;
+}
+
+size_t select_mask_words(uint32_t n, int sm_count) {
+    const SelectGeom g = select_geom(n, sm_count);
+    return (size_t)g.num_chunks * (g.chunk_rows / 32);
+}
 
 int launch_select(const SelectArgs &a, cudaStream_t s) {
-    const uint32_t tiles = select_tile_count(a.n);
-    if (tiles == 0) {
+    if (a.n == 0) {
         cudaMemsetAsync(a.d_count, 0, sizeof(int64_t), s);
         return 0;
     }
+    const SelectGeom g = select_geom(a.n, a.sm_count);
+    mask_kernel<<<g.grid, SEL_THREADS, 0, s>>>(a.val, a.d_n, a.n, a.range, g.chunk_rows,
+                                               g.num_chunks, a.mask, a.counts);
     if (a.pos_in)
-        select_kernel<true><<<tiles, SEL_THREADS, 0, s>>>(a);
+        expand_kernel<true><<<g.grid, SEL_THREADS, 0, s>>>(a.mask, a.counts, g.chunk_rows,
+                                                           g.num_chunks, a.pos_in, a.base_pos,
+                                                           a.out, a.d_count);
     else
-        select_kernel<false><<<tiles, SEL_THREADS, 0, s>>>(a);
-    return 1;
+        expand_kernel<false><<<g.grid, SEL_THREADS, 0, s>>>(a.mask, a.counts, g.chunk_rows,
+                                                            g.num_chunks, nullptr, a.base_pos,
+                                                            a.out, a.d_count);
+    return 2;
 }
 
 }  // namespace adb

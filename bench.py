@@ -286,7 +286,9 @@ def run_engine(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "adb::select_kernel<false>", "achieved": achieved,
+        roofline = {"bound": "hbm",
+                    "kernel": "adb_select_scan = adb::mask_kernel + adb::expand_kernel<false> "
+                              "(both launches timed together)", "achieved": achieved,
                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
