@@ -129,4 +129,18 @@ int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_
                           uint32_t span, int sm_count, cudaStream_t s);
 constexpr int kAggMaxBlocks = 148 * 8;
 
+// Implicit fan-out-32 B+-tree over a sorted value array (index_lookup.cu).
+constexpr int kBTreeMaxDepth = 8;
+struct BTreeView {
+    const int32_t *levels[kBTreeMaxDepth];   // levels[0] sits just above the leaves
+    int64_t lens[kBTreeMaxDepth];
+    int depth;
+};
+int launch_btree_level(const int32_t *below, int64_t below_len, int32_t *level, int64_t level_len,
+                       int sm_count, cudaStream_t s);
+int launch_index_select(const int32_t *values, const int32_t *positions, int64_t n,
+                        const BTreeView *tree, const int32_t *lo, const int32_t *hi,
+                        int32_t *out, int64_t *bounds, int64_t *d_count, int sm_count,
+                        cudaStream_t s);
+
 }  // namespace adb

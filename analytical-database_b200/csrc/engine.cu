@@ -5,6 +5,7 @@
 // adb_init() fails and every operator reports ADB_ERR_NOT_INITIALISED.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -29,7 +30,7 @@ struct Engine {
     // aggregate fold state
     adb_agg *agg_scratch = nullptr;
     unsigned int *agg_ticket = nullptr;
-    // small device scratch for chained operators
+    int64_t *idx_bounds = nullptr;      // {first, count} of the last index select
     int64_t launches = 0;
 } g;
 
@@ -136,6 +137,16 @@ adb_status adb_init(int device_ordinal) {
     uint64_t keep = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CU(cudaMalloc(&g.sel_counts, sizeof(uint32_t) * adb::kMaxSelectChunks));
+    CU(cudaMalloc(&g.idx_bounds, 2 * sizeof(int64_t)));
+    // Gathers over sparse position lists touch one 32-byte sector per hit; ask L2 not to
+    // widen those misses (r01b: 570 MB of DRAM reads for 180 MB of requested sectors).
+    // A hint only -- streaming kernels request whole lines anyway.  ADB_L2_FETCH overrides.
+    {
+        size_t gran = 32;
+        if (const char *e = getenv("ADB_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     CU(cudaMalloc(&g.agg_scratch, sizeof(adb_agg) * adb::kAggMaxBlocks));
     CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int)));
     CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int)));
@@ -150,6 +161,7 @@ adb_status adb_shutdown(void) {
     cudaStreamSynchronize(g.stream);
     cudaFree(g.sel_mask);
     cudaFree(g.sel_counts);
+    cudaFree(g.idx_bounds);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     cudaEventDestroy(g.ev0);
@@ -368,6 +380,78 @@ adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d
     if (adb_status s = adb_select_scan(d_sel_col, n, lo, hi, 0, d_pos_out, d_count, nullptr)) return s;
     if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, n, d_count, 0, d_val_out)) return s;
     return adb_aggregate(d_val_out, n, d_count, d_agg, nullptr);
+}
+
+// ---- sorted index / B+-tree --------------------------------------------------------------
+struct adb_index {
+    const int32_t *values;
+    const int32_t *positions;
+    int64_t n;
+    int32_t *tree_mem;
+    adb::BTreeView tree;
+};
+
+adb_status adb_index_create(const int32_t *d_values, const int32_t *d_positions, int64_t n,
+                            int32_t with_btree, adb_index **out) {
+    NEED_UP();
+    if (adb_status s = check_len(n, "adb_index_create")) return s;
+    if (!out || (n > 0 && (!d_values || !d_positions)))
+        return fail(ADB_ERR_INVALID, "adb_index_create: NULL pointer");
+    adb_index *ix = new adb_index{d_values, d_positions, n, nullptr, adb::BTreeView{}};
+    if (with_btree && n > 32) {
+        int64_t lens[adb::kBTreeMaxDepth], total = 0;
+        int depth = 0;
+        for (int64_t len = (n + 31) / 32;; len = (len + 31) / 32) {
+            lens[depth++] = len;
+            total += len;
+            if (len <= 32 || depth == adb::kBTreeMaxDepth) break;
+        }
+        cudaError_t e = cudaMalloc(&ix->tree_mem, total * sizeof(int32_t));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            delete ix;
+            return fail(ADB_ERR_NOMEM, "adb_index_create: %s", cudaGetErrorString(e));
+        }
+        int32_t *p = ix->tree_mem;
+        const int32_t *below = d_values;
+        int64_t below_len = n;
+        int launches = 0;
+        for (int l = 0; l < depth; ++l) {
+            ix->tree.levels[l] = p;
+            ix->tree.lens[l] = lens[l];
+            launches += adb::launch_btree_level(below, below_len, p, lens[l], g.sm_count, g.stream);
+            below = p;
+            below_len = lens[l];
+            p += lens[l];
+        }
+        ix->tree.depth = depth;
+        if (adb_status s = after_launch("btree_level", launches)) { cudaFree(ix->tree_mem); delete ix; return s; }
+    }
+    *out = ix;
+    return ADB_OK;
+}
+
+adb_status adb_index_destroy(adb_index *ix) {
+    NEED_UP();
+    if (!ix) return ADB_OK;
+    CU(cudaStreamSynchronize(g.stream));
+    if (ix->tree_mem) cudaFree(ix->tree_mem);
+    delete ix;
+    return ADB_OK;
+}
+
+adb_status adb_select_index(const adb_index *ix, int32_t use_btree, const int32_t *lo,
+                            const int32_t *hi, int32_t *d_pos_out, int64_t *d_count,
+                            int64_t *h_count) {
+    NEED_UP();
+    if (!ix || !d_count || (ix->n > 0 && !d_pos_out))
+        return fail(ADB_ERR_INVALID, "adb_select_index: NULL pointer");
+    const int k_ = adb::launch_index_select(ix->values, ix->positions, ix->n,
+                                            use_btree && ix->tree.depth > 0 ? &ix->tree : nullptr,
+                                            lo, hi, d_pos_out, g.idx_bounds, d_count, g.sm_count,
+                                            g.stream);
+    if (adb_status s = after_launch("index_select", k_)) return s;
+    return finish_count(d_count, h_count);
 }
 
 adb_status adb_synth_uniform(int32_t *d_out, int64_t n, uint64_t seed, uint64_t first_row,

@@ -1,0 +1,131 @@
+// index_lookup.cu -- range select through a sorted index: sorted-array binary search and a
+// bulk-loaded implicit B+-tree, both ending in one contiguous copy of index positions.
+//
+// Replaces select_column_sorted_index + binary_search (/root/reference/src/query.c:143-198).
+// The reference's btree.c is a stub (btree_insert is empty, src/btree.c:31-33), so a
+// `btree` index behaves exactly like a `sorted` one (query.c:205-217): the B+-tree here
+// is required to return the same positions as the sorted-array path, which it does by
+// construction -- both compute the two lower bounds below and share the emit kernel.
+//
+// Closed form of the reference's result (derived in DESIGN.md, checked against the
+// oracle and the reference objects in tests):  with lb(x) = first index whose value >= x,
+//   defined domain  (n > 0, low >= values[0], high >= values[0]):
+//       low > high                      -> nothing
+//       some value == high              -> positions[lb(low) .. lb(low) + max(lb(high)-lb(low), 1))
+//                                          (the "one spurious tuple" quirk, query.c:181-188)
+//       otherwise                       -> positions[lb(low) .. lb(high))
+//   oracle-undefined (the reference underflows a size_t and crashes, query.c:145-153):
+//       scan semantics                  -> positions[lb(low) .. lb(high))
+//
+// B+-tree layout: fan-out 32, pointer-free.  Level 0 holds the maximum of every 32-value
+// leaf block, level k+1 the maximum of every 32-key node of level k, until a level fits
+// in one node.  A lookup is one coalesced 128-byte node load + one ballot per level
+// (6 levels for 500 M keys, against 29 dependent probes for the binary search).
+#include "adb_common.cuh"
+
+namespace adb {
+
+// ---- B+-tree build: one strided gather per level ---------------------------------------------
+__global__ void btree_level_kernel(const int32_t *__restrict__ below, int64_t below_len,
+                                   int32_t *__restrict__ level, int64_t level_len) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < level_len; i += stride) {
+        const int64_t last = i * 32 + 31;
+        level[i] = below[last < below_len ? last : below_len - 1];      // max of the node
+    }
+}
+
+int launch_btree_level(const int32_t *below, int64_t below_len, int32_t *level, int64_t level_len,
+                       int sm_count, cudaStream_t s) {
+    int64_t blocks = (level_len + 255) / 256;
+    if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    btree_level_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, s>>>(below, below_len, level, level_len);
+    return 1;
+}
+
+// ---- lower bounds ------------------------------------------------------------------------------
+__device__ int64_t lb_binary(const int32_t *__restrict__ v, int64_t n, int32_t x) {
+    int64_t lo = 0, hi = n;                      // first index with v[idx] >= x
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (v[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Warp-cooperative descent.  levels[0] is the level just above the leaves; the top level has
+// <= 32 keys.  At each node the first key >= x names the child; none -> x is above every key.
+__device__ int64_t lb_btree(const int32_t *__restrict__ leaves, int64_t n, const BTreeView &t,
+                            int32_t x, uint32_t lane) {
+    int64_t node = 0;                            // node index within the current level
+    for (int l = t.depth - 1; l >= -1; --l) {
+        const int32_t *keys = l >= 0 ? t.levels[l] : leaves;
+        const int64_t len = l >= 0 ? t.lens[l] : n;
+        const int64_t idx = node * 32 + lane;
+        const bool ge = idx < len && keys[idx] >= x;
+        const uint32_t m = __ballot_sync(kFull, ge);
+        if (m == 0) return n;                    // only reachable on the rightmost path
+        node = node * 32 + (__ffs(m) - 1);
+    }
+    return node;                                 // after the leaf step `node` is the row index
+}
+
+struct IndexQuery {
+    int32_t low, high;
+    int32_t has_low, has_high;
+};
+
+// One warp resolves the query and publishes {first, count}; *d_count mirrors count.
+__global__ void index_bounds_kernel(const int32_t *__restrict__ values, int64_t n, BTreeView tree,
+                                    int use_tree, IndexQuery q, int64_t *__restrict__ bounds,
+                                    int64_t *__restrict__ d_count) {
+    const uint32_t lane = threadIdx.x;
+    int64_t lbl = 0, lbh = n;
+    if (n > 0) {
+        if (use_tree) {
+            if (q.has_low) lbl = lb_btree(values, n, tree, q.low, lane);
+            if (q.has_high) lbh = lb_btree(values, n, tree, q.high, lane);
+        } else {
+            if (q.has_low) lbl = lb_binary(values, n, q.low);
+            if (q.has_high) lbh = lb_binary(values, n, q.high);
+        }
+    }
+    if (lane != 0) return;
+    int64_t count = lbh > lbl ? lbh - lbl : 0;
+    const bool defined = n > 0 && q.has_low && q.has_high && q.low >= values[0] && q.high >= values[0];
+    if (defined) {
+        if (q.low > q.high) count = 0;
+        else if (lbh < n && values[lbh] == q.high && count == 0) count = 1;   // query.c:181-188
+    }
+    bounds[0] = lbl;
+    bounds[1] = count;
+    *d_count = count;
+}
+
+// out[i] = positions[first + i]: a contiguous, fully coalesced copy (index order).
+__global__ void __launch_bounds__(256)
+index_emit_kernel(const int32_t *__restrict__ positions, const int64_t *__restrict__ bounds,
+                  int32_t *__restrict__ out) {
+    const int64_t first = bounds[0], count = bounds[1];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        out[i] = positions[first + i];
+}
+
+int launch_index_select(const int32_t *values, const int32_t *positions, int64_t n,
+                        const BTreeView *tree, const int32_t *lo, const int32_t *hi,
+                        int32_t *out, int64_t *bounds, int64_t *d_count, int sm_count,
+                        cudaStream_t s) {
+    IndexQuery q{lo ? *lo : 0, hi ? *hi : 0, lo != nullptr, hi != nullptr};
+    BTreeView view{};
+    if (tree) view = *tree;
+    index_bounds_kernel<<<1, kWarp, 0, s>>>(values, n, view, tree != nullptr && view.depth > 0, q,
+                                            bounds, d_count);
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    index_emit_kernel<<<(int)blocks, 256, 0, s>>>(positions, bounds, out);
+    return 2;
+}
+
+}  // namespace adb

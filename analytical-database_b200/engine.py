@@ -127,6 +127,9 @@ class Engine:
         "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_sub": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_chain_select_fetch_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P, C.POINTER(_AggStruct)]),
+        "adb_index_create": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+        "adb_index_destroy": (C.c_int32, [C.c_void_p]),
+        "adb_select_index": (C.c_int32, [C.c_void_p, C.c_int32, _I32P, _I32P, _I32P, _I64P, _I64P]),
         "adb_synth_uniform": (C.c_int32, [_I32P, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32]),
     }
 
@@ -236,6 +239,25 @@ class Engine:
         fn = self.lib.adb_sub if subtract else self.lib.adb_add
         self._ck(fn(a.i32(), b.i32(), n_max, d_n.i64() if d_n else None, out.i32()))
         return out
+
+    def index_create(self, values: DevBuf, positions: DevBuf, n: int, with_btree: bool = True):
+        """Wrap device-resident (sorted values, int32 positions) as an index handle."""
+        h = C.c_void_p()
+        self._ck(self.lib.adb_index_create(values.i32(), positions.i32(), n, int(with_btree), C.byref(h)))
+        return h
+
+    def index_destroy(self, handle):
+        self._ck(self.lib.adb_index_destroy(handle))
+
+    def select_index(self, handle, n: int, lo=None, hi=None, use_btree: bool = False):
+        """select_column_sorted_index (query.c:165).  Returns (pos DevBuf, count)."""
+        out, d_count = self.alloc_i32(n), self.alloc(8)
+        (plo, _a), (phi, _b) = _bound(lo), _bound(hi)
+        h = C.c_int64(-1)
+        self._ck(self.lib.adb_select_index(handle, int(use_btree), plo, phi, out.i32(),
+                                           d_count.i64(), C.byref(h)))
+        d_count.free()
+        return out, int(h.value)
 
     def synth_uniform(self, n: int, seed: int, first_row: int = 0, lo: int = 0,
                       span: int = 1 << 31, out: DevBuf | None = None, out_offset: int = 0) -> DevBuf:

@@ -136,6 +136,25 @@ ADB_API adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const in
                                       int32_t *d_pos_out, int32_t *d_val_out,
                                       int64_t *d_count, adb_agg *d_agg);
 
+/* ---- sorted index and B+-tree range select -- replace select_column_sorted_index +
+ * binary_search, src/query.c:143-198 (and the stub src/btree.c, whose only defined
+ * behaviour is "same as sorted", query.c:205-217).
+ * An adb_index wraps a device-resident sorted copy of a column (d_values ascending) and
+ * its row permutation (d_positions, int32: the reference truncates its size_t positions
+ * to int when it emits them, query.c:187).  The arrays stay owned by the caller -- upload
+ * the reference's own ColumnIndex for bit-exact tie order, or build one with
+ * adb_index_sort().  with_btree additionally bulk-loads a fan-out-32 implicit B+-tree.
+ * adb_select_index emits d_positions[first .. first+count) in index order with exactly the
+ * reference's result in its defined domain (including the low == high quirk) and scan
+ * semantics where the reference crashes (low/high below the minimum, NULL bounds). */
+typedef struct adb_index adb_index;
+ADB_API adb_status adb_index_create(const int32_t *d_values, const int32_t *d_positions, int64_t n,
+                                    int32_t with_btree, adb_index **out);
+ADB_API adb_status adb_index_destroy(adb_index *ix);
+ADB_API adb_status adb_select_index(const adb_index *ix, int32_t use_btree, const int32_t *lo,
+                                    const int32_t *hi, int32_t *d_pos_out, int64_t *d_count,
+                                    int64_t *h_count);
+
 /* ---- synthetic data (bench / tests): counter-based generator, identical on host ------
  * d_out[i] = lo + mix64(seed, first_row + i) % span, the same sequence
  * analytical-database_b200/synth.py produces with numpy. */
