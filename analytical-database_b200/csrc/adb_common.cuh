@@ -129,6 +129,25 @@ int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_
                           uint32_t span, int sm_count, cudaStream_t s);
 constexpr int kAggMaxBlocks = 148 * 8;
 
+// Batched shared scan (shared_scan.cu).  All pointers are device addresses.
+struct SharedScanPlan {
+    const int32_t *bounds;     // m ascending distinct bounds
+    const uint16_t *cov_off;   // m + 2 CSR offsets: interval k covers cov_q[cov_off[k] .. cov_off[k+1])
+    const uint8_t *cov_q;      // covering query ids, ascending inside an interval
+    uint32_t m;
+    uint32_t q_count;
+};
+struct SharedScanGeom {
+    uint32_t chunk_rows, num_chunks, grid;
+};
+SharedScanGeom shared_scan_geom(uint32_t n, int sm_count);
+int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan &plan,
+                           const SharedScanGeom &g, uint16_t *cls, uint32_t *counts,
+                           int64_t *totals, cudaStream_t s);
+int launch_shared_emit(const uint16_t *cls, const SharedScanPlan &plan, const SharedScanGeom &g,
+                       const uint32_t *offsets, int32_t *const *outs, int64_t capacity,
+                       cudaStream_t s);
+
 // Implicit fan-out-32 B+-tree over a sorted value array (index_lookup.cu).
 constexpr int kBTreeMaxDepth = 8;
 struct BTreeView {

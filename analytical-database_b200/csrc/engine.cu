@@ -3,7 +3,9 @@
 //
 // There is deliberately no CPU path in this file: if no CUDA device can be opened,
 // adb_init() fails and every operator reports ADB_ERR_NOT_INITIALISED.
+#include <algorithm>
 #include <cstdarg>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +33,16 @@ struct Engine {
     adb_agg *agg_scratch = nullptr;
     unsigned int *agg_ticket = nullptr;
     int64_t *idx_bounds = nullptr;      // {first, count} of the last index select
+    // batched shared scan state (count phase -> emit phase)
+    unsigned char *ss_plan_mem = nullptr;   // bounds | cov_off | cov_q
+    uint16_t *ss_cls = nullptr;
+    size_t ss_cls_rows = 0;
+    uint32_t *ss_counts = nullptr;
+    int64_t *ss_totals = nullptr;
+    int32_t **ss_outs = nullptr;
+    adb::SharedScanPlan ss_plan{};
+    adb::SharedScanGeom ss_geom{};
+    bool ss_ready = false;
     int64_t launches = 0;
 } g;
 
@@ -162,6 +174,11 @@ adb_status adb_shutdown(void) {
     cudaFree(g.sel_mask);
     cudaFree(g.sel_counts);
     cudaFree(g.idx_bounds);
+    cudaFree(g.ss_plan_mem);
+    cudaFree(g.ss_cls);
+    cudaFree(g.ss_counts);
+    cudaFree(g.ss_totals);
+    cudaFree(g.ss_outs);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     cudaEventDestroy(g.ev0);
@@ -380,6 +397,105 @@ adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d
     if (adb_status s = adb_select_scan(d_sel_col, n, lo, hi, 0, d_pos_out, d_count, nullptr)) return s;
     if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, n, d_count, 0, d_val_out)) return s;
     return adb_aggregate(d_val_out, n, d_count, d_agg, nullptr);
+}
+
+// ---- batched shared scan -------------------------------------------------------------------
+constexpr size_t kSsBoundsBytes = 4 * 2 * ADB_MAX_BATCH;                 // 1200
+constexpr size_t kSsOffBytes = 2 * (2 * ADB_MAX_BATCH + 2);              // 604 -> padded to 640
+constexpr size_t kSsCovBytes = 2 * ADB_MAX_BATCH * ADB_MAX_BATCH;        // 45000
+constexpr size_t kSsPlanBytes = kSsBoundsBytes + 640 + kSsCovBytes;
+constexpr size_t kSsMaxChunks = 8192;
+
+adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
+                                   const int32_t *highs, int32_t q_count, int64_t *h_counts) {
+    NEED_UP();
+    g.ss_ready = false;
+    if (adb_status s = check_len(n, "adb_shared_select_count")) return s;
+    if (q_count < 1 || q_count > ADB_MAX_BATCH)
+        return fail(ADB_ERR_INVALID, "adb_shared_select_count: q_count %d outside [1, %d] (server.c:366-371 chunks "
+                    "batches to 150)", q_count, ADB_MAX_BATCH);
+    if (!lows || !highs || (n > 0 && !d_col)) return fail(ADB_ERR_INVALID, "adb_shared_select_count: NULL pointer");
+    if (!g.ss_plan_mem) {
+        CU(cudaMalloc(&g.ss_plan_mem, kSsPlanBytes));
+        CU(cudaMalloc(&g.ss_counts, sizeof(uint32_t) * ADB_MAX_BATCH * kSsMaxChunks));
+        CU(cudaMalloc(&g.ss_totals, sizeof(int64_t) * ADB_MAX_BATCH));
+        CU(cudaMalloc(&g.ss_outs, sizeof(int32_t *) * ADB_MAX_BATCH));
+    }
+    // ---- plan: elementary intervals and their covering queries ------------------------------
+    int32_t bounds[2 * ADB_MAX_BATCH];
+    uint32_t m = 0;
+    for (int32_t q = 0; q < q_count; ++q)
+        if (lows[q] < highs[q]) { bounds[m++] = lows[q]; bounds[m++] = highs[q]; }
+    std::sort(bounds, bounds + m);
+    m = (uint32_t)(std::unique(bounds, bounds + m) - bounds);
+    std::vector<uint16_t> off(m + 2, 0);
+    std::vector<uint8_t> cov;
+    for (uint32_t k = 1; k < m; ++k) {                      // interval k = [bounds[k-1], bounds[k])
+        for (int32_t q = 0; q < q_count; ++q)
+            if (lows[q] < highs[q] && lows[q] <= bounds[k - 1] && bounds[k] <= highs[q])
+                cov.push_back((uint8_t)q);
+        off[k + 1] = (uint16_t)cov.size();
+    }
+    if (m >= 1) off[m + 1] = (uint16_t)cov.size();
+    if (m == 0) off[1] = 0;
+    if (m) CU(cudaMemcpyAsync(g.ss_plan_mem, bounds, m * sizeof(int32_t), cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(g.ss_plan_mem + kSsBoundsBytes, off.data(), off.size() * sizeof(uint16_t),
+                       cudaMemcpyHostToDevice, g.stream));
+    if (!cov.empty())
+        CU(cudaMemcpyAsync(g.ss_plan_mem + kSsBoundsBytes + 640, cov.data(), cov.size(),
+                           cudaMemcpyHostToDevice, g.stream));
+    CU(cudaStreamSynchronize(g.stream));                    // host vectors go out of scope
+    g.ss_plan = adb::SharedScanPlan{reinterpret_cast<const int32_t *>(g.ss_plan_mem),
+                                    reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsBoundsBytes),
+                                    g.ss_plan_mem + kSsBoundsBytes + 640, m, (uint32_t)q_count};
+    if (n == 0) {
+        for (int32_t q = 0; q < q_count; ++q) if (h_counts) h_counts[q] = 0;
+        g.ss_geom = adb::SharedScanGeom{0, 0, 0};
+        g.ss_ready = true;
+        return ADB_OK;
+    }
+    g.ss_geom = adb::shared_scan_geom((uint32_t)n, g.sm_count);
+    if (g.ss_geom.num_chunks > kSsMaxChunks) return fail(ADB_ERR_INVALID, "shared scan: chunk table overflow");
+    const size_t rows = (size_t)g.ss_geom.num_chunks * g.ss_geom.chunk_rows;
+    if (rows > g.ss_cls_rows) {
+        if (g.ss_cls) { CU(cudaFree(g.ss_cls)); g.ss_cls = nullptr; g.ss_cls_rows = 0; }
+        cudaError_t e = cudaMalloc(&g.ss_cls, (rows + rows / 8 + 4096) * sizeof(uint16_t));
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "shared scan interval-id scratch: %s", cudaGetErrorString(e)); }
+        g.ss_cls_rows = rows + rows / 8 + 4096;
+    }
+    const int k_ = adb::launch_shared_classify(d_col, (uint32_t)n, g.ss_plan, g.ss_geom, g.ss_cls,
+                                               g.ss_counts, g.ss_totals, g.stream);
+    if (adb_status s = after_launch("shared_classify", k_)) return s;
+    if (h_counts) {
+        CU(cudaMemcpyAsync(h_counts, g.ss_totals, sizeof(int64_t) * q_count, cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+    }
+    g.ss_ready = true;
+    return ADB_OK;
+}
+
+adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity) {
+    NEED_UP();
+    if (!g.ss_ready) return fail(ADB_ERR_INVALID, "adb_shared_select_emit: no preceding adb_shared_select_count");
+    if (!d_out_ptrs) return fail(ADB_ERR_INVALID, "adb_shared_select_emit: NULL pointer");
+    g.ss_ready = false;
+    if (g.ss_geom.num_chunks == 0) return ADB_OK;
+    CU(cudaMemcpyAsync(g.ss_outs, d_out_ptrs, sizeof(int32_t *) * g.ss_plan.q_count,
+                       cudaMemcpyHostToDevice, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    const int k_ = adb::launch_shared_emit(g.ss_cls, g.ss_plan, g.ss_geom, g.ss_counts, g.ss_outs, capacity, g.stream);
+    return after_launch("shared_emit", k_);
+}
+
+adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *lows,
+                             const int32_t *highs, int32_t q_count, int32_t *d_pos_out,
+                             int64_t stride, int64_t *h_counts) {
+    int64_t tmp[ADB_MAX_BATCH];
+    if (adb_status s = adb_shared_select_count(d_col, n, lows, highs, q_count, h_counts ? h_counts : tmp)) return s;
+    if (!d_pos_out && n > 0) return fail(ADB_ERR_INVALID, "adb_shared_select: NULL output");
+    int32_t *ptrs[ADB_MAX_BATCH];
+    for (int32_t q = 0; q < q_count; ++q) ptrs[q] = d_pos_out + (size_t)q * stride;
+    return adb_shared_select_emit(ptrs, stride);
 }
 
 // ---- sorted index / B+-tree --------------------------------------------------------------

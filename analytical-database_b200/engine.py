@@ -127,6 +127,9 @@ class Engine:
         "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_sub": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_chain_select_fetch_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P, C.POINTER(_AggStruct)]),
+        "adb_shared_select_count": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I64P]),
+        "adb_shared_select_emit": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int64]),
+        "adb_shared_select": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I32P, C.c_int64, _I64P]),
         "adb_index_create": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
         "adb_index_destroy": (C.c_int32, [C.c_void_p]),
         "adb_select_index": (C.c_int32, [C.c_void_p, C.c_int32, _I32P, _I32P, _I32P, _I64P, _I64P]),
@@ -239,6 +242,21 @@ class Engine:
         fn = self.lib.adb_sub if subtract else self.lib.adb_add
         self._ck(fn(a.i32(), b.i32(), n_max, d_n.i64() if d_n else None, out.i32()))
         return out
+
+    def shared_select(self, col: DevBuf, n: int, lows, highs):
+        """shared_select (query.c:496): count phase, exact-size outputs, emit phase.
+        Returns a list of (pos DevBuf, count) per query."""
+        lows = np.ascontiguousarray(lows, dtype=np.int32)
+        highs = np.ascontiguousarray(highs, dtype=np.int32)
+        q = lows.size
+        counts = (C.c_int64 * q)()
+        self._ck(self.lib.adb_shared_select_count(col.i32(), n, lows.ctypes.data_as(_I32P),
+                                                  highs.ctypes.data_as(_I32P), q, counts))
+        outs = [self.alloc_i32(counts[i]) for i in range(q)]
+        ptrs = (C.c_void_p * q)(*[o.ptr for o in outs])
+        cap = max(list(counts) + [1])
+        self._ck(self.lib.adb_shared_select_emit(ptrs, cap))
+        return [(outs[i], int(counts[i])) for i in range(q)]
 
     def index_create(self, values: DevBuf, positions: DevBuf, n: int, with_btree: bool = True):
         """Wrap device-resident (sorted values, int32 positions) as an index handle."""

@@ -136,6 +136,24 @@ ADB_API adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const in
                                       int32_t *d_pos_out, int32_t *d_val_out,
                                       int64_t *d_count, adb_agg *d_agg);
 
+/* ---- batched shared scan -- replaces shared_select + select_task, src/query.c:450-583
+ * One pass over d_col evaluates q_count (<= ADB_MAX_BATCH, the dispatcher's chunk,
+ * src/server.c:366-371) predicates lows[q] <= v < highs[q]; has_low/has_high are ignored
+ * exactly as query.c:474 does.  Two phases so the caller can size each position list
+ * exactly (the reference mallocs row_count ints per query, query.c:556):
+ *   adb_shared_select_count  scans, classifies, returns every query's hit count;
+ *   adb_shared_select_emit   writes query q's ascending positions to d_out_ptrs[q]
+ *                            (a HOST array of q_count device pointers), at most `capacity`
+ *                            positions each.
+ * adb_shared_select is the one-shot form: query q's list lands at d_pos_out + q * stride. */
+#define ADB_MAX_BATCH 150
+ADB_API adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
+                                           const int32_t *highs, int32_t q_count, int64_t *h_counts);
+ADB_API adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity);
+ADB_API adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *lows,
+                                     const int32_t *highs, int32_t q_count, int32_t *d_pos_out,
+                                     int64_t stride, int64_t *h_counts);
+
 /* ---- sorted index and B+-tree range select -- replace select_column_sorted_index +
  * binary_search, src/query.c:143-198 (and the stub src/btree.c, whose only defined
  * behaviour is "same as sorted", query.c:205-217).
