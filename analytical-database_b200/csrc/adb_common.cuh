@@ -148,6 +148,35 @@ int launch_shared_emit(const uint16_t *cls, const SharedScanPlan &plan, const Sh
                        const uint32_t *offsets, int32_t *const *outs, int64_t capacity,
                        cudaStream_t s);
 
+// Stable radix partition passes + generic exclusive scan (radix.cu).
+struct RadixPass {
+    int shift, bits;           // digit = (f(key) >> shift) & ((1 << bits) - 1), bits <= 8
+    bool hash;                 // f = key * 0x9E3779B1 (join) or key ^ 0x80000000 (signed order)
+};
+struct RadixGeom {
+    uint32_t rows_per_cta, ctas;
+};
+RadixGeom radix_geom(uint32_t n, int sm_count);
+int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
+                      uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
+                      uint32_t *base, int sm_count, cudaStream_t s);
+uint32_t scan_ctas(uint32_t n, int sm_count);
+int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, unsigned long long *sums,
+                          int64_t *total, int sm_count, cudaStream_t s);
+
+// Hash join (hash_join.cu).
+int launch_hj_count(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t *cnt, int sm_count,
+                    cudaStream_t s);
+size_t hj_smem_bytes();
+uint32_t hj_smem_tuples();
+int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint32_t *pkeys,
+                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts,
+                        const unsigned long long *big_off, unsigned char *big_mem,
+                        uint32_t *gs_by_j, uint32_t *cnt_by_j, cudaStream_t s);
+int launch_hj_expand(const uint32_t *gs_by_j, const uint32_t *cnt_by_j, const uint32_t *off_by_j,
+                     uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
+                     int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);
+
 // Implicit fan-out-32 B+-tree over a sorted value array (index_lookup.cu).
 constexpr int kBTreeMaxDepth = 8;
 struct BTreeView {

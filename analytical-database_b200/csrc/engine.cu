@@ -43,6 +43,18 @@ struct Engine {
     adb::SharedScanPlan ss_plan{};
     adb::SharedScanGeom ss_geom{};
     bool ss_ready = false;
+    // radix / join scratch
+    uint32_t *rx_hist = nullptr, *rx_totals = nullptr, *rx_base = nullptr;
+    unsigned long long *sc_sums = nullptr;
+    struct JoinState {
+        bool ready = false;
+        uint32_t n_probe = 0;
+        int64_t matches = 0;
+        uint32_t *gs_by_j = nullptr, *cnt_by_j = nullptr, *off_by_j = nullptr;
+        int32_t *build_pos_sorted = nullptr;
+        const int32_t *probe_pos = nullptr;
+        bool swapped = false;
+    } join;
     int64_t launches = 0;
 } g;
 
@@ -179,6 +191,10 @@ adb_status adb_shutdown(void) {
     cudaFree(g.ss_counts);
     cudaFree(g.ss_totals);
     cudaFree(g.ss_outs);
+    cudaFree(g.rx_hist);
+    cudaFree(g.rx_totals);
+    cudaFree(g.rx_base);
+    cudaFree(g.sc_sums);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     cudaEventDestroy(g.ev0);
@@ -496,6 +512,217 @@ adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *low
     int32_t *ptrs[ADB_MAX_BATCH];
     for (int32_t q = 0; q < q_count; ++q) ptrs[q] = d_pos_out + (size_t)q * stride;
     return adb_shared_select_emit(ptrs, stride);
+}
+
+// ---- radix sort / partition helpers ---------------------------------------------------------
+static adb_status ensure_radix_scratch() {
+    if (g.rx_hist) return ADB_OK;
+    CU(cudaMalloc(&g.rx_hist, sizeof(uint32_t) * 256 * (size_t)(g.sm_count * 6 + 8)));
+    CU(cudaMalloc(&g.rx_totals, sizeof(uint32_t) * 256));
+    CU(cudaMalloc(&g.rx_base, sizeof(uint32_t) * 256));
+    CU(cudaMalloc(&g.sc_sums, sizeof(unsigned long long) * (size_t)(g.sm_count * 2 + 8)));
+    return ADB_OK;
+}
+
+// Runs `npass` stable passes over (keys, payload); payload starts as the row index.  The
+// result lands in (*keys_out, *pay_out); the other ping-pong pair is freed.  With npass == 0
+// the keys are copied and the payload is left NULL (meaning identity).
+static adb_status radix_run(const uint32_t *keys_in, uint32_t n, const adb::RadixPass *passes,
+                            int npass, uint32_t **keys_out, uint32_t **pay_out, int *launches) {
+    *keys_out = nullptr;
+    *pay_out = nullptr;
+    if (adb_status s = ensure_radix_scratch()) return s;
+    uint32_t *k[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
+    const size_t bytes = (size_t)(n ? n : 1) * sizeof(uint32_t);
+    for (int i = 0; i < (npass > 1 ? 2 : 1); ++i) {
+        CU(cudaMallocAsync(&k[i], bytes, g.stream));
+        if (npass > 0) CU(cudaMallocAsync(&v[i], bytes, g.stream));
+    }
+    if (npass == 0) {
+        if (n) CU(cudaMemcpyAsync(k[0], keys_in, bytes, cudaMemcpyDeviceToDevice, g.stream));
+        *keys_out = k[0];
+        return ADB_OK;
+    }
+    const uint32_t *src_k = keys_in, *src_v = nullptr;
+    int cur = 0;
+    for (int p = 0; p < npass; ++p) {
+        *launches += adb::launch_radix_pass(src_k, src_v, k[cur], v[cur], n, passes[p], g.rx_hist,
+                                            g.rx_totals, g.rx_base, g.sm_count, g.stream);
+        src_k = k[cur];
+        src_v = v[cur];
+        cur ^= 1;
+    }
+    const int last = cur ^ 1;
+    *keys_out = k[last];
+    *pay_out = v[last];
+    if (npass > 1) {
+        CU(cudaFreeAsync(k[last ^ 1], g.stream));
+        CU(cudaFreeAsync(v[last ^ 1], g.stream));
+    }
+    return ADB_OK;
+}
+
+adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_values_out,
+                          int32_t *d_positions_out) {
+    NEED_UP();
+    if (adb_status s = check_len(n, "adb_index_sort")) return s;
+    if (n == 0) return ADB_OK;
+    if (!d_col || !d_values_out || !d_positions_out) return fail(ADB_ERR_INVALID, "adb_index_sort: NULL pointer");
+    const adb::RadixPass passes[4] = {{0, 8, false}, {8, 8, false}, {16, 8, false}, {24, 8, false}};
+    uint32_t *k = nullptr, *v = nullptr;
+    int launches = 0;
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(d_col), (uint32_t)n, passes, 4, &k, &v, &launches)) return s;
+    CU(cudaMemcpyAsync(d_values_out, k, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_positions_out, v, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, g.stream));
+    CU(cudaFreeAsync(k, g.stream));
+    CU(cudaFreeAsync(v, g.stream));
+    return after_launch("index_sort", launches);
+}
+
+// ---- hash join ------------------------------------------------------------------------------------
+static void join_release() {
+    auto &j = g.join;
+    if (j.gs_by_j) cudaFreeAsync(j.gs_by_j, g.stream);
+    if (j.cnt_by_j) cudaFreeAsync(j.cnt_by_j, g.stream);
+    if (j.off_by_j) cudaFreeAsync(j.off_by_j, g.stream);
+    if (j.build_pos_sorted) cudaFreeAsync(j.build_pos_sorted, g.stream);
+    j = Engine::JoinState{};
+}
+
+// build = the side whose rows are grouped (the reference's column_one for hash_join);
+// probe = the side walked in row order.  Output pair k is (build position, probe position).
+static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64, const int32_t *pv,
+                             const int32_t *pp, int64_t np64, bool swapped, int64_t *h_matches) {
+    NEED_UP();
+    join_release();
+    if (adb_status s = check_len(nb64, "adb_join")) return s;
+    if (adb_status s = check_len(np64, "adb_join")) return s;
+    if ((nb64 > 0 && (!bv || !bp)) || (np64 > 0 && (!pv || !pp)))
+        return fail(ADB_ERR_INVALID, "adb_join: NULL device pointer");
+    auto &j = g.join;
+    j.swapped = swapped;
+    j.n_probe = (uint32_t)np64;
+    j.probe_pos = pp;
+    const uint32_t nb = (uint32_t)nb64, np = (uint32_t)np64;
+    if (nb == 0 || np == 0) {
+        j.matches = 0;
+        j.ready = true;
+        if (h_matches) *h_matches = 0;
+        return ADB_OK;
+    }
+    int launches = 0;
+    uint32_t part_bits = 0;
+    while (part_bits < 16 && (nb >> part_bits) > 1024) ++part_bits;
+    const uint32_t num_parts = 1u << part_bits;
+    // 1. build side: full stable sort on the bijective hash
+    const adb::RadixPass sort4[4] = {{0, 8, true}, {8, 8, true}, {16, 8, true}, {24, 8, true}};
+    uint32_t *bk = nullptr, *bi = nullptr;
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, &bk, &bi, &launches)) return s;
+    CU(cudaMallocAsync(&j.build_pos_sorted, (size_t)nb * 4, g.stream));
+    launches += adb::launch_fetch(bp, reinterpret_cast<const int32_t *>(bi), nb, nullptr, 0,
+                                  j.build_pos_sorted, g.sm_count, g.stream);
+    CU(cudaFreeAsync(bi, g.stream));
+    // 2. probe side: stable partition on the top hash bits
+    adb::RadixPass pp_pass[2];
+    int npp = 0;
+    if (part_bits > 8) {
+        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits - 8, true};
+        pp_pass[npp++] = adb::RadixPass{24, 8, true};
+    } else if (part_bits > 0) {
+        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits, true};
+    }
+    uint32_t *pk = nullptr, *pj = nullptr;
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(pv), np, pp_pass, npp, &pk, &pj, &launches)) return s;
+    // 3. partition offsets (num_parts + 1 entries each; the extra zero makes the scan emit the total)
+    uint32_t *cnt1 = nullptr, *cnt2 = nullptr, *off1 = nullptr, *off2 = nullptr;
+    int64_t *tot = nullptr;
+    const size_t pbytes = (size_t)(num_parts + 1) * 4;
+    CU(cudaMallocAsync(&cnt1, pbytes, g.stream));
+    CU(cudaMallocAsync(&cnt2, pbytes, g.stream));
+    CU(cudaMallocAsync(&off1, pbytes, g.stream));
+    CU(cudaMallocAsync(&off2, pbytes, g.stream));
+    CU(cudaMallocAsync(&tot, 16, g.stream));
+    CU(cudaMemsetAsync(cnt1, 0, pbytes, g.stream));
+    CU(cudaMemsetAsync(cnt2, 0, pbytes, g.stream));
+    launches += adb::launch_hj_count(bk, nb, part_bits, cnt1, g.sm_count, g.stream);
+    launches += adb::launch_hj_count(pk, np, part_bits, cnt2, g.sm_count, g.stream);
+    launches += adb::launch_exclusive_scan(cnt1, off1, num_parts + 1, g.sc_sums, tot, g.sm_count, g.stream);
+    launches += adb::launch_exclusive_scan(cnt2, off2, num_parts + 1, g.sc_sums, tot + 1, g.sm_count, g.stream);
+    // 4. partitions that do not fit the shared-memory table get a table in global memory
+    std::vector<uint32_t> h_off1(num_parts + 1);
+    CU(cudaMemcpyAsync(h_off1.data(), off1, pbytes, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    unsigned long long *big_off = nullptr;
+    unsigned char *big_mem = nullptr;
+    {
+        std::vector<unsigned long long> h_big(num_parts, ~0ull);
+        unsigned long long need = 0;
+        for (uint32_t p = 0; p < num_parts; ++p) {
+            const uint32_t sz = h_off1[p + 1] - h_off1[p];
+            if (sz > adb::hj_smem_tuples()) {
+                h_big[p] = need;
+                need += ((16ull * 2 * sz) + 255) & ~255ull;
+            }
+        }
+        if (need) {
+            CU(cudaMallocAsync(&big_off, num_parts * sizeof(unsigned long long), g.stream));
+            cudaError_t e = cudaMallocAsync(&big_mem, need, g.stream);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join: %llu bytes for skewed partitions: %s", need, cudaGetErrorString(e)); }
+            CU(cudaMemcpyAsync(big_off, h_big.data(), num_parts * sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream));
+            CU(cudaStreamSynchronize(g.stream));
+        }
+    }
+    // 5. per-partition build + probe
+    CU(cudaMallocAsync(&j.gs_by_j, (size_t)np * 4, g.stream));
+    CU(cudaMallocAsync(&j.cnt_by_j, (size_t)np * 4, g.stream));
+    CU(cudaMallocAsync(&j.off_by_j, (size_t)np * 4, g.stream));
+    CU(cudaMemsetAsync(j.cnt_by_j, 0, (size_t)np * 4, g.stream));
+    launches += adb::launch_hj_partition(bk, off1, pk, pj, off2, num_parts, big_off, big_mem,
+                                         j.gs_by_j, j.cnt_by_j, g.stream);
+    // 6. output offsets in probe-row order
+    launches += adb::launch_exclusive_scan(j.cnt_by_j, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
+    CU(cudaMemcpyAsync(&j.matches, tot, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    for (void *q : {(void *)bk, (void *)pk, (void *)pj, (void *)cnt1, (void *)cnt2, (void *)off1,
+                    (void *)off2, (void *)tot, (void *)big_off, (void *)big_mem})
+        if (q) CU(cudaFreeAsync(q, g.stream));
+    if (adb_status s = after_launch("join_count", launches)) return s;
+    if (j.matches >= (int64_t)1 << 31) {
+        const long long m = j.matches;
+        join_release();
+        return fail(ADB_ERR_INVALID, "join produces %lld pairs; the reference indexes its output with an int "
+                    "(query.c:657) so the result must stay below 2^31", m);
+    }
+    j.ready = true;
+    if (h_matches) *h_matches = j.matches;
+    return ADB_OK;
+}
+
+adb_status adb_hash_join_count(const int32_t *d_v1, const int32_t *d_p1, int64_t n1,
+                               const int32_t *d_v2, const int32_t *d_p2, int64_t n2,
+                               int64_t *h_matches) {
+    return join_count(d_v1, d_p1, n1, d_v2, d_p2, n2, false, h_matches);
+}
+adb_status adb_nested_loop_join_count(const int32_t *d_v1, const int32_t *d_p1, int64_t n1,
+                                      const int32_t *d_v2, const int32_t *d_p2, int64_t n2,
+                                      int64_t *h_matches) {
+    // outer-major over side one (query.c:597-611) == probe-major with side one probing
+    return join_count(d_v2, d_p2, n2, d_v1, d_p1, n1, true, h_matches);
+}
+adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2) {
+    NEED_UP();
+    auto &j = g.join;
+    if (!j.ready) return fail(ADB_ERR_INVALID, "adb_join_emit: no preceding *_join_count");
+    adb_status rc = ADB_OK;
+    if (j.matches > 0) {
+        if (!d_out1 || !d_out2) return fail(ADB_ERR_INVALID, "adb_join_emit: NULL output");
+        int32_t *ob = j.swapped ? d_out2 : d_out1, *op = j.swapped ? d_out1 : d_out2;
+        const int k_ = adb::launch_hj_expand(j.gs_by_j, j.cnt_by_j, j.off_by_j, j.n_probe,
+                                             j.build_pos_sorted, j.probe_pos, ob, op, g.sm_count, g.stream);
+        rc = after_launch("join_expand", k_);
+    }
+    join_release();
+    return rc;
 }
 
 // ---- sorted index / B+-tree --------------------------------------------------------------

@@ -1,0 +1,215 @@
+// hash_join.cu -- equi-join of two (value, position) pair lists with a reproducible order.
+//
+// Replaces hash_join + multimap (/root/reference/src/query.c:652-696, src/multimap.c) and,
+// with the sides swapped, nested_loop_join (query.c:585-650).  The reference inserts the
+// build side (column_one, the larger input, parse.c:798-813) row by row into an open
+// addressing multimap and then walks the probe side in row order, appending for every
+// probe row all stored positions of its key in insertion order.  The output is therefore
+// probe-major, build-insertion order inside a key -- and must be reproduced exactly.
+//
+// GPU formulation (shared-memory-partitioned hash build and probe):
+//   1. build side: stable LSD radix sort on h = key * 0x9E3779B1 (radix.cu).  The odd
+//      multiplier is a bijection on 32 bits, so equal h <=> equal key: one sort both groups
+//      equal keys (insertion order kept inside a group: the sort is stable) and orders
+//      the groups by partition id = top bits of h;
+//   2. probe side: stable radix partition on the same top bits, payload = probe row j;
+//   3. one CTA per partition: group leaders insert (key -> group start) into an open
+//      addressing table in shared memory (64-bit CAS, no sentinel key needed), group
+//      tails store the group end, then every probe row of the partition looks its key up
+//      and scatters {group start, match count} to slot j;
+//   4. exclusive scan of the match counts in probe-row order = output offsets (radix.cu);
+//   5. expand: probe row j copies its group's positions to out1[off[j] ..] and its own
+//      position to out2[off[j] ..]; long groups (skewed keys) are spread over a warp.
+// Partitions too large for the shared-memory table (heavy skew) run the same code on a
+// table in global memory.
+#include "adb_common.cuh"
+
+namespace adb {
+
+constexpr int HJ_THREADS = 256;
+constexpr uint32_t HJ_SLOTS = 4096;                    // shared-memory table slots
+constexpr uint32_t HJ_SMEM_TUPLES = 3072;              // largest build partition it holds (75 %)
+constexpr uint32_t kHashMul = 0x9E3779B1u;
+
+__device__ __forceinline__ uint32_t hj_pid(uint32_t key, uint32_t part_bits) {
+    return part_bits ? (key * kHashMul) >> (32 - part_bits) : 0u;
+}
+
+// ---- partition sizes ------------------------------------------------------------------------
+__global__ void hj_count_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t part_bits,
+                                uint32_t *__restrict__ cnt) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&cnt[hj_pid(keys[i], part_bits)], 1u);
+}
+
+// ---- per-partition build + probe ----------------------------------------------------------------
+struct HjTable {
+    unsigned long long *key;      // (1 << 32) | key when occupied, 0 when free
+    uint32_t *gs;                 // group start (index into the sorted build arrays)
+    uint32_t *ge;                 // group end
+    uint32_t slots;               // power of two for shared memory, arbitrary for global
+};
+
+__device__ __forceinline__ uint32_t hj_home(uint32_t key, uint32_t slots) {
+    // the low hash bits are independent of the (top-bit) partition id
+    const uint32_t h = (key * kHashMul) ^ ((key * kHashMul) >> 15);
+    return (h * 0x85EBCA6Bu >> 7) % slots;
+}
+
+__device__ __forceinline__ uint32_t hj_insert(const HjTable &t, uint32_t key) {
+    const unsigned long long want = (1ull << 32) | key;
+    uint32_t s = hj_home(key, t.slots);
+    while (true) {
+        const unsigned long long cur = atomicCAS(&t.key[s], 0ull, want);
+        if (cur == 0ull || cur == want) return s;
+        s = s + 1 == t.slots ? 0 : s + 1;
+    }
+}
+
+__device__ __forceinline__ int hj_find(const HjTable &t, uint32_t key) {
+    const unsigned long long want = (1ull << 32) | key;
+    uint32_t s = hj_home(key, t.slots);
+    while (true) {
+        const unsigned long long cur = t.key[s];
+        if (cur == want) return (int)s;
+        if (cur == 0ull) return -1;
+        s = s + 1 == t.slots ? 0 : s + 1;
+    }
+}
+
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
+                    const uint32_t *__restrict__ off1, const uint32_t *__restrict__ pkeys,
+                    const uint32_t *__restrict__ prows /* nullptr: identity */,
+                    const uint32_t *__restrict__ off2,
+                    const unsigned long long *__restrict__ big_off /* per partition, ~0 = smem */,
+                    unsigned char *__restrict__ big_mem, uint32_t *__restrict__ gs_by_j,
+                    uint32_t *__restrict__ cnt_by_j) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t p = blockIdx.x;
+    const uint32_t b0 = off1[p], b1 = off1[p + 1], q0 = off2[p], q1 = off2[p + 1];
+    if (q0 == q1) return;                                   // nobody probes this partition
+    const uint32_t nb = b1 - b0;
+    if (nb == 0) {
+        for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
+            const uint32_t j = prows ? prows[u] : u;
+            cnt_by_j[j] = 0;
+            gs_by_j[j] = 0;
+        }
+        return;
+    }
+    HjTable t;
+    const bool big = big_off && big_off[p] != ~0ull;
+    if (!big) {
+        t.slots = HJ_SLOTS;
+        t.key = reinterpret_cast<unsigned long long *>(smem);
+        t.gs = reinterpret_cast<uint32_t *>(smem + 8 * HJ_SLOTS);
+        t.ge = t.gs + HJ_SLOTS;
+    } else {
+        t.slots = 2 * nb;
+        unsigned char *base = big_mem + big_off[p];
+        t.key = reinterpret_cast<unsigned long long *>(base);
+        t.gs = reinterpret_cast<uint32_t *>(base + 8ull * t.slots);
+        t.ge = t.gs + t.slots;
+    }
+    for (uint32_t s = threadIdx.x; s < t.slots; s += HJ_THREADS) t.key[s] = 0ull;
+    __syncthreads();
+    // group leaders claim a slot and record where their group starts
+    for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
+        const uint32_t k = bkeys[i];
+        if (i == b0 || bkeys[i - 1] != k) t.gs[hj_insert(t, k)] = i;
+    }
+    __syncthreads();
+    // group tails record where it ends
+    for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
+        const uint32_t k = bkeys[i];
+        if (i + 1 == b1 || bkeys[i + 1] != k) t.ge[hj_find(t, k)] = i + 1;
+    }
+    __syncthreads();
+    for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
+        const uint32_t j = prows ? prows[u] : u;
+        const int s = hj_find(t, pkeys[u]);
+        gs_by_j[j] = s >= 0 ? t.gs[s] : 0u;
+        cnt_by_j[j] = s >= 0 ? t.ge[s] - t.gs[s] : 0u;
+    }
+}
+
+// ---- expand ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_expand_kernel(const uint32_t *__restrict__ gs_by_j, const uint32_t *__restrict__ cnt_by_j,
+                 const uint32_t *__restrict__ off_by_j, uint32_t n_probe,
+                 const int32_t *__restrict__ build_pos_sorted, const int32_t *__restrict__ probe_pos,
+                 int32_t *__restrict__ out_build, int32_t *__restrict__ out_probe) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (HJ_THREADS / kWarp);
+    const uint32_t warp_id = blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5);
+    for (uint32_t j0 = warp_id * kWarp; j0 < n_probe; j0 += warps * kWarp) {
+        const uint32_t j = j0 + lane;
+        uint32_t cnt = 0, gs = 0, off = 0;
+        int32_t pp = 0;
+        if (j < n_probe) {
+            cnt = cnt_by_j[j];
+            if (cnt) { gs = gs_by_j[j]; off = off_by_j[j]; pp = probe_pos[j]; }
+        }
+        if (cnt && cnt <= 8) {
+            for (uint32_t r = 0; r < cnt; ++r) {
+                out_build[off + r] = build_pos_sorted[gs + r];
+                out_probe[off + r] = pp;
+            }
+        }
+        uint32_t longs = __ballot_sync(kFull, cnt > 8);
+        while (longs) {
+            const int src = __ffs(longs) - 1;
+            longs &= longs - 1;
+            const uint32_t c = __shfl_sync(kFull, cnt, src), g = __shfl_sync(kFull, gs, src);
+            const uint32_t o = __shfl_sync(kFull, off, src);
+            const int32_t q = __shfl_sync(kFull, pp, src);
+            for (uint32_t r = lane; r < c; r += kWarp) {
+                out_build[o + r] = build_pos_sorted[g + r];
+                out_probe[o + r] = q;
+            }
+        }
+    }
+}
+
+// ---- launchers --------------------------------------------------------------------------------------
+int launch_hj_count(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t *cnt, int sm_count,
+                    cudaStream_t s) {
+    if (n == 0) return 0;
+    uint32_t blocks = (n + 1023) / 1024;
+    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
+    hj_count_kernel<<<blocks, 256, 0, s>>>(keys, n, part_bits, cnt);
+    return 1;
+}
+
+size_t hj_smem_bytes() { return 16ull * HJ_SLOTS; }
+uint32_t hj_smem_tuples() { return HJ_SMEM_TUPLES; }
+
+int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint32_t *pkeys,
+                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts,
+                        const unsigned long long *big_off, unsigned char *big_mem,
+                        uint32_t *gs_by_j, uint32_t *cnt_by_j, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(hj_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)hj_smem_bytes());
+        attr_set = true;
+    }
+    hj_partition_kernel<<<num_parts, HJ_THREADS, hj_smem_bytes(), s>>>(
+        bkeys, off1, pkeys, prows, off2, big_off, big_mem, gs_by_j, cnt_by_j);
+    return 1;
+}
+
+int launch_hj_expand(const uint32_t *gs_by_j, const uint32_t *cnt_by_j, const uint32_t *off_by_j,
+                     uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
+                     int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
+    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
+    hj_expand_kernel<<<blocks, HJ_THREADS, 0, s>>>(gs_by_j, cnt_by_j, off_by_j, n_probe,
+                                                   build_pos_sorted, probe_pos, out_build, out_probe);
+    return 1;
+}
+
+}  // namespace adb

@@ -1,0 +1,233 @@
+// radix.cu -- stable radix partition passes over (key, payload) pairs, and a generic
+// exclusive scan.  Two users:
+//
+//   * index build  (replaces quicksort/partition, /root/reference/src/index.c:25-46): four
+//     8-bit LSD passes on the sign-flipped key give (values ascending, positions) with ties
+//     in ascending row order -- the canonical stable order; identical to the reference's
+//     unstable quicksort whenever keys are unique;
+//   * hash join    (hash_join.cu): one or two passes on the top bits of a multiplicative
+//     hash split both inputs into partitions small enough for a shared-memory table while
+//     keeping the original row order inside every partition (stability is what makes the
+//     join's output order reproducible).
+//
+// One pass = histogram (per-CTA, per-bucket counts) -> row scan of the [bucket][cta] matrix
+// -> bucket bases -> stable scatter.  Inside the scatter a step covers 256 consecutive rows:
+// lanes that share a bucket are ranked with match_any in lane order, warps are ordered
+// through a small per-warp count table, so equal digits keep their input order.
+#include "adb_common.cuh"
+
+namespace adb {
+
+constexpr int RX_THREADS = 256;
+constexpr int RX_WARPS = RX_THREADS / kWarp;
+constexpr int RX_BUCKETS = 256;
+
+__device__ __forceinline__ uint32_t rx_digit(uint32_t key, const RadixPass &p) {
+    const uint32_t f = p.hash ? key * 0x9E3779B1u : key ^ 0x80000000u;
+    return (f >> p.shift) & ((1u << p.bits) - 1u);
+}
+
+__global__ void __launch_bounds__(RX_THREADS)
+rx_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t rows_per_cta, RadixPass p,
+               uint32_t *__restrict__ hist /* [bucket][gridDim.x] */) {
+    __shared__ uint32_t s_h[RX_BUCKETS];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t begin = blockIdx.x * rows_per_cta;
+    const uint32_t end = min(n, begin + rows_per_cta);
+    for (uint32_t i = begin + threadIdx.x; i < end; i += RX_THREADS)
+        atomicAdd(&s_h[rx_digit(keys[i], p)], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// Exclusive scan of every row of a [rows][cols] uint32 matrix in place; row totals out.
+__global__ void __launch_bounds__(1024)
+rx_row_scan_kernel(uint32_t *__restrict__ mat, uint32_t cols, uint32_t *__restrict__ totals) {
+    __shared__ uint32_t s_warp[32];
+    uint32_t *row = mat + (size_t)blockIdx.x * cols;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < cols; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < cols ? row[i] : 0u;
+        const uint32_t incl = warp_incl_scan(x, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) s_warp[lane] = warp_incl_scan(s_warp[lane], lane);
+        __syncthreads();
+        const uint32_t wexcl = warp ? s_warp[warp - 1] : 0u;
+        if (i < cols) row[i] = carry + wexcl + incl - x;
+        carry += s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+// base[b] = sum of totals[0..b)  (<= 256 buckets, one CTA of 256 threads)
+__global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals, uint32_t *__restrict__ base) {
+    __shared__ uint32_t s_warp[RX_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = totals[threadIdx.x];
+    const uint32_t incl = warp_incl_scan(x, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wexcl = 0;
+    for (uint32_t w = 0; w < warp; ++w) wexcl += s_warp[w];
+    base[threadIdx.x] = wexcl + incl - x;
+}
+
+__global__ void __launch_bounds__(RX_THREADS)
+rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
+                  uint32_t rows_per_cta, RadixPass p, const uint32_t *__restrict__ hist,
+                  const uint32_t *__restrict__ base, uint32_t *__restrict__ keys_out,
+                  uint32_t *__restrict__ pay_out) {
+    __shared__ uint32_t s_off[RX_BUCKETS];                 // next free slot of every bucket
+    __shared__ uint32_t s_wcnt[RX_WARPS][RX_BUCKETS];      // per-warp digit counts of the step
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s_off[threadIdx.x] = base[threadIdx.x] + hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    const uint32_t begin = blockIdx.x * rows_per_cta;
+    const uint32_t end = min(n, begin + rows_per_cta);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t step = begin; step < end; step += RX_THREADS) {
+#pragma unroll
+        for (int w = 0; w < RX_WARPS; ++w) s_wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = step + threadIdx.x;
+        const bool live = i < end;
+        uint32_t key = 0, val = 0, d = 0, rank = 0;
+        if (live) {
+            key = keys[i];
+            val = pay ? pay[i] : i;
+            d = rx_digit(key, p);
+        }
+        const uint32_t active = __ballot_sync(kFull, live);
+        if (live) {
+            const uint32_t peers = __match_any_sync(active, d);
+            rank = __popc(peers & lt);
+            if (rank == 0) s_wcnt[warp][d] = __popc(peers);
+        }
+        __syncthreads();
+        if (live) {
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; ++w) before += s_wcnt[w][d];
+            const uint32_t dst = s_off[d] + before + rank;
+            keys_out[dst] = key;
+            pay_out[dst] = val;
+        }
+        __syncthreads();
+        {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < RX_WARPS; ++w) tot += s_wcnt[w][threadIdx.x];
+            s_off[threadIdx.x] += tot;
+        }
+        __syncthreads();
+    }
+}
+
+RadixGeom radix_geom(uint32_t n, int sm_count) {
+    RadixGeom g{};
+    uint32_t ctas = (n + 4095) / 4096;
+    const uint32_t cap = (uint32_t)sm_count * 6u;
+    if (ctas > cap) ctas = cap;
+    if (ctas == 0) ctas = 1;
+    uint32_t rows = (n + ctas - 1) / ctas;
+    rows = (rows + RX_THREADS - 1) / RX_THREADS * RX_THREADS;
+    if (rows == 0) rows = RX_THREADS;
+    g.rows_per_cta = rows;
+    g.ctas = (n + rows - 1) / rows;
+    if (g.ctas == 0) g.ctas = 1;
+    return g;
+}
+
+// scratch: hist = 256 * ctas uint32, totals = 256, base = 256
+int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
+                      uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
+                      uint32_t *base, int sm_count, cudaStream_t s) {
+    if (n == 0) return 0;
+    const RadixGeom g = radix_geom(n, sm_count);
+    rx_hist_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+    rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
+    rx_bucket_base_kernel<<<1, RX_BUCKETS, 0, s>>>(totals, base);
+    rx_scatter_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, pay_in, n, g.rows_per_cta, p, hist, base,
+                                                    keys_out, pay_out);
+    return 4;
+}
+
+// ---- generic exclusive scan: out[i] = sum(in[0..i)), *total = sum(in[0..n)) -------------------
+constexpr int SC_THREADS = 1024;
+
+__global__ void __launch_bounds__(SC_THREADS)
+sc_chunk_sum_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t rows_per_cta,
+                    unsigned long long *__restrict__ sums) {
+    __shared__ unsigned long long s_w[32];
+    const uint32_t begin = blockIdx.x * rows_per_cta, end = min(n, begin + rows_per_cta);
+    unsigned long long acc = 0;
+    for (uint32_t i = begin + threadIdx.x; i < end; i += SC_THREADS) acc += in[i];
+    acc = (unsigned long long)warp_sum_i64((int64_t)acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 32; ++w) t += s_w[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+sc_chunk_scan_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t rows_per_cta,
+                     const unsigned long long *__restrict__ sums, uint32_t *__restrict__ out,
+                     int64_t *__restrict__ total) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ uint32_t s_warp[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long acc = 0;
+    for (uint32_t c = threadIdx.x; c < blockIdx.x; c += SC_THREADS) acc += sums[c];
+    acc = (unsigned long long)warp_sum_i64((int64_t)acc);
+    if (lane == 0) s_w[warp] = acc;
+    __syncthreads();
+    unsigned long long base64 = 0;
+    for (int w = 0; w < 32; ++w) base64 += s_w[w];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = (int64_t)(base64 + sums[blockIdx.x]);
+    uint32_t carry = (uint32_t)base64;                      // offsets fit 32 bits (total < 2^31 checked by caller)
+    const uint32_t begin = blockIdx.x * rows_per_cta, end = min(n, begin + rows_per_cta);
+    for (uint32_t b = begin; b < end; b += SC_THREADS) {
+        const uint32_t i = b + threadIdx.x;
+        const uint32_t x = i < end ? in[i] : 0u;
+        const uint32_t incl = warp_incl_scan(x, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) s_warp[lane] = warp_incl_scan(s_warp[lane], lane);
+        __syncthreads();
+        const uint32_t wexcl = warp ? s_warp[warp - 1] : 0u;
+        if (i < end) out[i] = carry + wexcl + incl - x;
+        carry += s_warp[31];
+        __syncthreads();
+    }
+}
+
+// sums scratch: >= scan_ctas(n) entries of 8 bytes
+uint32_t scan_ctas(uint32_t n, int sm_count) {
+    uint32_t ctas = (n + 8191) / 8192;
+    const uint32_t cap = (uint32_t)sm_count * 2u;
+    if (ctas > cap) ctas = cap;
+    return ctas ? ctas : 1;
+}
+
+int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, unsigned long long *sums,
+                          int64_t *total, int sm_count, cudaStream_t s) {
+    if (n == 0) {
+        cudaMemsetAsync(total, 0, sizeof(int64_t), s);
+        return 0;
+    }
+    const uint32_t ctas = scan_ctas(n, sm_count);
+    uint32_t rows = (n + ctas - 1) / ctas;
+    rows = (rows + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
+    const uint32_t grid = (n + rows - 1) / rows;
+    sc_chunk_sum_kernel<<<grid, SC_THREADS, 0, s>>>(in, n, rows, sums);
+    sc_chunk_scan_kernel<<<grid, SC_THREADS, 0, s>>>(in, n, rows, sums, out, total);
+    return 2;
+}
+
+}  // namespace adb

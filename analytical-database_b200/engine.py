@@ -133,6 +133,10 @@ class Engine:
         "adb_index_create": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
         "adb_index_destroy": (C.c_int32, [C.c_void_p]),
         "adb_select_index": (C.c_int32, [C.c_void_p, C.c_int32, _I32P, _I32P, _I32P, _I64P, _I64P]),
+        "adb_index_sort": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P]),
+        "adb_hash_join_count": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, C.c_int64, _I64P]),
+        "adb_nested_loop_join_count": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, C.c_int64, _I64P]),
+        "adb_join_emit": (C.c_int32, [_I32P, _I32P]),
         "adb_synth_uniform": (C.c_int32, [_I32P, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32]),
     }
 
@@ -257,6 +261,22 @@ class Engine:
         cap = max(list(counts) + [1])
         self._ck(self.lib.adb_shared_select_emit(ptrs, cap))
         return [(outs[i], int(counts[i])) for i in range(q)]
+
+    def index_sort(self, col: DevBuf, n: int):
+        """build_unclustered_index's sort (index.c:140): (values DevBuf, positions DevBuf)."""
+        values, positions = self.alloc_i32(n), self.alloc_i32(n)
+        self._ck(self.lib.adb_index_sort(col.i32(), n, values.i32(), positions.i32()))
+        return values, positions
+
+    def join(self, v1: DevBuf, p1: DevBuf, n1: int, v2: DevBuf, p2: DevBuf, n2: int,
+             nested_loop: bool = False):
+        """hash_join / nested_loop_join (query.c:652,585): (out1 DevBuf, out2 DevBuf, pairs)."""
+        m = C.c_int64(-1)
+        fn = self.lib.adb_nested_loop_join_count if nested_loop else self.lib.adb_hash_join_count
+        self._ck(fn(v1.i32(), p1.i32(), n1, v2.i32(), p2.i32(), n2, C.byref(m)))
+        o1, o2 = self.alloc_i32(m.value), self.alloc_i32(m.value)
+        self._ck(self.lib.adb_join_emit(o1.i32(), o2.i32()))
+        return o1, o2, int(m.value)
 
     def index_create(self, values: DevBuf, positions: DevBuf, n: int, with_btree: bool = True):
         """Wrap device-resident (sorted values, int32 positions) as an index handle."""

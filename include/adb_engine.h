@@ -173,6 +173,31 @@ ADB_API adb_status adb_select_index(const adb_index *ix, int32_t use_btree, cons
                                     const int32_t *hi, int32_t *d_pos_out, int64_t *d_count,
                                     int64_t *h_count);
 
+/* ---- index build -- replaces quicksort / partition / init_column_index, src/index.c:25-101
+ * (values ascending, positions) of d_col by a stable LSD radix sort: ties come out in
+ * ascending row order.  The reference's unstable Lomuto quicksort leaves another tie
+ * order; the two agree whenever keys are unique.  A clustered index then
+ * permutes the sibling columns with adb_fetch(sibling, positions) (index.c:105-135). */
+ADB_API adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_values_out,
+                                  int32_t *d_positions_out);
+
+/* ---- joins -- replace hash_join + multimap (src/query.c:652-696, src/multimap.c) and
+ * nested_loop_join (src/query.c:585-650).  Inputs are two (value, position) pair lists;
+ * outputs two aligned position lists.  Order is the reference's: hash join probe-major
+ * over side two with side one's insertion order inside a key; nested-loop outer-major
+ * over side one.  Two phases so the result can be sized exactly:
+ *   *_join_count   does all the work up to the output offsets, returns the pair count;
+ *   adb_join_emit  writes the pairs (d_out1 = side-one positions, d_out2 = side-two).
+ * Negative keys and an empty build side, on which the reference crashes,
+ * follow the equi-join definition.  The pair count must stay below 2^31 (query.c:657). */
+ADB_API adb_status adb_hash_join_count(const int32_t *d_v1, const int32_t *d_p1, int64_t n1,
+                                       const int32_t *d_v2, const int32_t *d_p2, int64_t n2,
+                                       int64_t *h_matches);
+ADB_API adb_status adb_nested_loop_join_count(const int32_t *d_v1, const int32_t *d_p1, int64_t n1,
+                                              const int32_t *d_v2, const int32_t *d_p2, int64_t n2,
+                                              int64_t *h_matches);
+ADB_API adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2);
+
 /* ---- synthetic data (bench / tests): counter-based generator, identical on host ------
  * d_out[i] = lo + mix64(seed, first_row + i) % span, the same sequence
  * analytical-database_b200/synth.py produces with numpy. */

@@ -1,0 +1,125 @@
+"""GPU parity for the joins (BASELINE config 4) and the index build.
+
+hash_join / nested_loop_join: pair lists must equal the oracle's element for element --
+probe-major over side two with side one's insertion order inside a key for the hash join,
+outer-major over side one for the nested loop.  Inputs mirror milestone4.py:
+many-one and many-many joins, zipfian keys (:31-53), selective prefilters; plus the
+oracle-undefined domain (negative keys, empty sides) as equi-join semantics.
+index sort: stable order; equals the reference's quicksort whenever keys are unique (A3)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from analytical_database_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def run_join(eng, k1, p1, k2, p2, nested=False):
+    d = [eng.upload(x) for x in (k1, p1, k2, p2)]
+    o1, o2, m = eng.join(d[0], d[1], k1.size, d[2], d[3], k2.size, nested_loop=nested)
+    a, b = o1.to_host(m), o2.to_host(m)
+    for x in d + [o1, o2]:
+        x.free()
+    return a, b
+
+
+def inputs(rng, n1, n2, kind):
+    if kind == "zipf":
+        k1 = (rng.zipf(1.3, n1) % 1000).astype(np.int32)
+        k2 = (rng.zipf(1.3, n2) % 1000).astype(np.int32)
+    elif kind == "unique":
+        k1 = rng.permutation(4 * max(n1, 1))[:n1].astype(np.int32)
+        k2 = rng.permutation(4 * max(n1, 1))[:n2].astype(np.int32)
+    elif kind == "negative":
+        k1 = rng.integers(-max(n1 // 4, 2), max(n1 // 4, 2), n1).astype(np.int32)
+        k2 = rng.integers(-max(n1 // 4, 2), max(n1 // 4, 2), n2).astype(np.int32)
+    else:
+        k1 = rng.integers(0, max(n1 // 4, 2), n1).astype(np.int32)
+        k2 = rng.integers(0, max(n1 // 4, 2), n2).astype(np.int32)
+    p1 = rng.permutation(10 * max(n1, 1))[:n1].astype(np.int32)
+    p2 = rng.permutation(10 * max(n2, 1) + 1)[:n2].astype(np.int32)
+    return k1, p1, k2, p2
+
+
+@pytest.mark.parametrize("kind", ["uniform", "unique", "zipf", "negative"])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (4, 1), (100, 7), (2000, 1500), (1500, 0), (0, 9),
+                                   (5000, 5000), (40000, 9000)])
+def test_hash_join_order(eng, port, rng, kind, n1, n2):
+    if kind == "zipf" and n1 * n2 > 3e7:
+        n2 = 2000                                  # keep the many-many blow-up bounded
+    k1, p1, k2, p2 = inputs(rng, n1, n2, kind)
+    a, b = run_join(eng, k1, p1, k2, p2)
+    e1, e2 = port.hash_join(k1, p1, k2, p2)
+    assert a.size == e1.size, (kind, n1, n2)
+    assert np.array_equal(a, e1) and np.array_equal(b, e2), (kind, n1, n2)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "zipf"])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (300, 200), (1500, 1500), (1500, 0)])
+def test_nested_loop_join_order(eng, port, rng, kind, n1, n2):
+    k1, p1, k2, p2 = inputs(rng, n1, n2, kind)
+    a, b = run_join(eng, k1, p1, k2, p2, nested=True)
+    e1, e2 = port.nested_loop_join(k1, p1, k2, p2)
+    assert np.array_equal(a, e1) and np.array_equal(b, e2), (kind, n1, n2)
+
+
+def test_hash_join_vs_reference_objects(eng, ref, rng):
+    k1, p1, k2, p2 = inputs(rng, 30000, 20000, "uniform")
+    a, b = run_join(eng, k1, p1, k2, p2)
+    e1, e2 = ref.hash_join(k1, p1, k2, p2)
+    assert np.array_equal(a, e1) and np.array_equal(b, e2)
+
+
+def test_hash_join_skewed_partition(eng, port, rng):
+    """One key owns 40 % of the build side: its partition overflows the shared-memory table
+    and takes the global-memory path; the probe side hits it a few times."""
+    n1, n2 = 60000, 300
+    k1 = rng.integers(0, 50000, n1).astype(np.int32)
+    k1[rng.random(n1) < 0.4] = 777
+    k2 = rng.integers(0, 50000, n2).astype(np.int32)
+    k2[:5] = 777
+    p1 = np.arange(n1, dtype=np.int32)[::-1].copy()
+    p2 = np.arange(n2, dtype=np.int32) + 5
+    a, b = run_join(eng, k1, p1, k2, p2)
+    e1, e2 = port.hash_join(k1, p1, k2, p2)
+    assert np.array_equal(a, e1) and np.array_equal(b, e2)
+
+
+def test_hash_join_multi_pass_partitioning(eng, port, rng):
+    """3 M x 2 M many-one join: 12 partition bits (two probe passes)."""
+    n1, n2 = 3_000_000, 2_000_000
+    k1 = rng.permutation(2 * n1)[:n1].astype(np.int32)
+    k2 = rng.integers(0, 2 * n1, n2).astype(np.int32)
+    p1 = rng.permutation(n1).astype(np.int32)
+    p2 = rng.permutation(n2).astype(np.int32)
+    a, b = run_join(eng, k1, p1, k2, p2)
+    e1, e2 = port.hash_join(k1, p1, k2, p2)
+    assert a.size == e1.size
+    assert np.array_equal(a, e1) and np.array_equal(b, e2)
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 5000, 1_000_003])
+def test_index_sort(eng, port, rng, n):
+    for data in (rng.integers(-2**31, 2**31 - 1, n, dtype=np.int64).astype(np.int32),
+                 rng.integers(-50, 50, n).astype(np.int32),
+                 rng.permutation(n).astype(np.int32)):
+        col = eng.upload(data)
+        dv, dp = eng.index_sort(col, n)
+        values, positions = dv.to_host(n), dp.to_host(n)
+        order = np.argsort(data, kind="stable").astype(np.int32)
+        assert np.array_equal(positions, order)
+        assert np.array_equal(values, data[order])
+        for x in (col, dv, dp):
+            x.free()
+    if n <= 5000:                                 # unique keys: identical to the reference quicksort
+        data = rng.permutation(n).astype(np.int32)
+        col = eng.upload(data)
+        dv, dp = eng.index_sort(col, n)
+        ev, ep = port.index_sort(data)
+        assert np.array_equal(dv.to_host(n), ev) and np.array_equal(dp.to_host(n), ep.astype(np.int32))
