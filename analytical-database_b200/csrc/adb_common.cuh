@@ -113,6 +113,9 @@ struct SelectArgs {
     int sm_count;
 };
 int launch_select(const SelectArgs &a, cudaStream_t s);
+// two-phase form: mask + per-chunk counts (+ total into a.d_count), then expand into a.out
+int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s);
+int launch_select_expand(const SelectArgs &a, cudaStream_t s);
 size_t select_mask_words(uint32_t n, int sm_count);
 constexpr uint32_t kMaxSelectChunks = 1u << 16;
 
@@ -186,9 +189,9 @@ struct BTreeView {
 };
 int launch_btree_level(const int32_t *below, int64_t below_len, int32_t *level, int64_t level_len,
                        int sm_count, cudaStream_t s);
-int launch_index_select(const int32_t *values, const int32_t *positions, int64_t n,
-                        const BTreeView *tree, const int32_t *lo, const int32_t *hi,
-                        int32_t *out, int64_t *bounds, int64_t *d_count, int sm_count,
-                        cudaStream_t s);
+int launch_index_bounds(const int32_t *values, int64_t n, const BTreeView *tree, const int32_t *lo,
+                        const int32_t *hi, int64_t *bounds, int64_t *d_count, cudaStream_t s);
+int launch_index_emit(const int32_t *positions, int64_t n, const int64_t *bounds, int32_t *out,
+                      int sm_count, cudaStream_t s);
 
 }  // namespace adb

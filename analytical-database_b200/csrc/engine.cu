@@ -33,6 +33,10 @@ struct Engine {
     adb_agg *agg_scratch = nullptr;
     unsigned int *agg_ticket = nullptr;
     int64_t *idx_bounds = nullptr;      // {first, count} of the last index select
+    int64_t idx_pending_n = -1;         // >= 0 between adb_select_index_count and _emit
+    adb::SelectArgs sel_pending{};      // valid between adb_select_*_count and adb_select_emit
+    bool sel_ready = false;
+    int64_t *scratch_count = nullptr;   // device int64 for callers that pass no d_count
     // batched shared scan state (count phase -> emit phase)
     unsigned char *ss_plan_mem = nullptr;   // bounds | cov_off | cov_q
     uint16_t *ss_cls = nullptr;
@@ -162,6 +166,7 @@ adb_status adb_init(int device_ordinal) {
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CU(cudaMalloc(&g.sel_counts, sizeof(uint32_t) * adb::kMaxSelectChunks));
     CU(cudaMalloc(&g.idx_bounds, 2 * sizeof(int64_t)));
+    CU(cudaMalloc(&g.scratch_count, sizeof(int64_t)));
     // Gathers over sparse position lists touch one 32-byte sector per hit; ask L2 not to
     // widen those misses (r01b: 570 MB of DRAM reads for 180 MB of requested sectors).
     // A hint only -- streaming kernels request whole lines anyway.  ADB_L2_FETCH overrides.
@@ -186,6 +191,7 @@ adb_status adb_shutdown(void) {
     cudaFree(g.sel_mask);
     cudaFree(g.sel_counts);
     cudaFree(g.idx_bounds);
+    cudaFree(g.scratch_count);
     cudaFree(g.ss_plan_mem);
     cudaFree(g.ss_cls);
     cudaFree(g.ss_counts);
@@ -309,40 +315,74 @@ static adb_status finish_count(int64_t *d_count, int64_t *h_count) {
     return ADB_OK;
 }
 
+static adb_status select_prepare(const char *what, const int32_t *d_val, const int32_t *d_pos,
+                                 int64_t n_max, const int64_t *d_n, const int32_t *lo,
+                                 const int32_t *hi, int64_t *d_count, adb::SelectArgs *a) {
+    NEED_UP();
+    g.sel_ready = false;
+    if (adb_status s = check_len(n_max, what)) return s;
+    if (n_max > 0 && !d_val) return fail(ADB_ERR_INVALID, "%s: NULL device pointer", what);
+    *a = adb::SelectArgs{};
+    a->val = d_val; a->pos_in = d_pos; a->d_n = d_n; a->n = (uint32_t)n_max;
+    fold_range(lo, hi, &a->range);
+    a->d_count = d_count ? d_count : g.scratch_count;
+    if (adb_status s = ensure_select_scratch(a->n)) return s;
+    a->mask = g.sel_mask; a->counts = g.sel_counts; a->sm_count = g.sm_count;
+    return ADB_OK;
+}
+
 adb_status adb_select_scan(const int32_t *d_col, int64_t n, const int32_t *lo, const int32_t *hi,
                            int32_t base_pos, int32_t *d_pos_out, int64_t *d_count,
                            int64_t *h_count) {
-    NEED_UP();
-    if (adb_status s = check_len(n, "adb_select_scan")) return s;
-    if (!d_count || (n > 0 && (!d_col || !d_pos_out)))
+    adb::SelectArgs a;
+    if (!d_count || (n > 0 && !d_pos_out)) {
+        NEED_UP();
         return fail(ADB_ERR_INVALID, "adb_select_scan: NULL device pointer");
-    adb::SelectArgs a{};
-    a.val = d_col; a.pos_in = nullptr; a.d_n = nullptr; a.n = (uint32_t)n;
-    fold_range(lo, hi, &a.range);
-    a.base_pos = base_pos; a.out = d_pos_out; a.d_count = d_count;
-    if (adb_status s = ensure_select_scratch(a.n)) return s;
-    a.mask = g.sel_mask; a.counts = g.sel_counts; a.sm_count = g.sm_count;
-    const int k_ = adb::launch_select(a, g.stream);
-    if (adb_status s = after_launch("select_scan", k_)) return s;
+    }
+    if (adb_status s = select_prepare("adb_select_scan", d_col, nullptr, n, nullptr, lo, hi, d_count, &a)) return s;
+    a.base_pos = base_pos; a.out = d_pos_out;
+    if (adb_status s = after_launch("select_scan", adb::launch_select(a, g.stream))) return s;
     return finish_count(d_count, h_count);
 }
 
 adb_status adb_select_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n_max,
                             const int64_t *d_n, const int32_t *lo, const int32_t *hi,
                             int32_t *d_pos_out, int64_t *d_count, int64_t *h_count) {
-    NEED_UP();
-    if (adb_status s = check_len(n_max, "adb_select_pairs")) return s;
-    if (!d_count || (n_max > 0 && (!d_val || !d_pos || !d_pos_out)))
+    adb::SelectArgs a;
+    if (!d_count || (n_max > 0 && (!d_pos || !d_pos_out))) {
+        NEED_UP();
         return fail(ADB_ERR_INVALID, "adb_select_pairs: NULL device pointer");
-    adb::SelectArgs a{};
-    a.val = d_val; a.pos_in = d_pos; a.d_n = d_n; a.n = (uint32_t)n_max;
-    fold_range(lo, hi, &a.range);
-    a.base_pos = 0; a.out = d_pos_out; a.d_count = d_count;
-    if (adb_status s = ensure_select_scratch(a.n)) return s;
-    a.mask = g.sel_mask; a.counts = g.sel_counts; a.sm_count = g.sm_count;
-    const int k_ = adb::launch_select(a, g.stream);
-    if (adb_status s = after_launch("select_pairs", k_)) return s;
+    }
+    if (adb_status s = select_prepare("adb_select_pairs", d_val, d_pos, n_max, d_n, lo, hi, d_count, &a)) return s;
+    a.base_pos = 0; a.out = d_pos_out;
+    if (adb_status s = after_launch("select_pairs", adb::launch_select(a, g.stream))) return s;
     return finish_count(d_count, h_count);
+}
+
+// Two-phase form: the count phase streams the column once and leaves the selection bitmap in
+// the engine's scratch; the emit phase turns it into positions in a buffer of exactly the
+// right size.  Any other select in between invalidates the pending bitmap.
+adb_status adb_select_count(const int32_t *d_val, int64_t n_max, const int64_t *d_n,
+                            const int32_t *lo, const int32_t *hi, int64_t *d_count,
+                            int64_t *h_count) {
+    adb::SelectArgs a;
+    if (adb_status s = select_prepare("adb_select_count", d_val, nullptr, n_max, d_n, lo, hi, d_count, &a)) return s;
+    if (adb_status s = after_launch("select_count", adb::launch_select_mask(a, true, g.stream))) return s;
+    g.sel_pending = a;
+    g.sel_ready = true;
+    return finish_count(a.d_count, h_count);
+}
+
+adb_status adb_select_emit(const int32_t *d_pos_in, int32_t base_pos, int32_t *d_pos_out) {
+    NEED_UP();
+    if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit: no pending adb_select_count");
+    g.sel_ready = false;
+    adb::SelectArgs a = g.sel_pending;
+    if (a.n == 0) return ADB_OK;
+    if (!d_pos_out) return fail(ADB_ERR_INVALID, "adb_select_emit: NULL output");
+    a.pos_in = d_pos_in; a.base_pos = base_pos; a.out = d_pos_out;
+    a.d_count = g.scratch_count;                    // expand rewrites the same total
+    return after_launch("select_emit", adb::launch_select_expand(a, g.stream));
 }
 
 adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
@@ -783,17 +823,39 @@ adb_status adb_index_destroy(adb_index *ix) {
     return ADB_OK;
 }
 
+adb_status adb_select_index_count(const adb_index *ix, int32_t use_btree, const int32_t *lo,
+                                  const int32_t *hi, int64_t *d_count, int64_t *h_count) {
+    NEED_UP();
+    g.idx_pending_n = -1;
+    if (!ix) return fail(ADB_ERR_INVALID, "adb_select_index_count: NULL index");
+    int64_t *dc = d_count ? d_count : g.scratch_count;
+    const int k_ = adb::launch_index_bounds(ix->values, ix->n,
+                                            use_btree && ix->tree.depth > 0 ? &ix->tree : nullptr,
+                                            lo, hi, g.idx_bounds, dc, g.stream);
+    if (adb_status s = after_launch("index_bounds", k_)) return s;
+    g.idx_pending_n = ix->n;
+    return finish_count(dc, h_count);
+}
+
+adb_status adb_select_index_emit(const adb_index *ix, int32_t *d_pos_out) {
+    NEED_UP();
+    if (!ix || g.idx_pending_n != ix->n)
+        return fail(ADB_ERR_INVALID, "adb_select_index_emit: no pending adb_select_index_count on this index");
+    g.idx_pending_n = -1;
+    if (ix->n == 0) return ADB_OK;
+    if (!d_pos_out) return fail(ADB_ERR_INVALID, "adb_select_index_emit: NULL output");
+    return after_launch("index_emit", adb::launch_index_emit(ix->positions, ix->n, g.idx_bounds,
+                                                             d_pos_out, g.sm_count, g.stream));
+}
+
 adb_status adb_select_index(const adb_index *ix, int32_t use_btree, const int32_t *lo,
                             const int32_t *hi, int32_t *d_pos_out, int64_t *d_count,
                             int64_t *h_count) {
     NEED_UP();
     if (!ix || !d_count || (ix->n > 0 && !d_pos_out))
         return fail(ADB_ERR_INVALID, "adb_select_index: NULL pointer");
-    const int k_ = adb::launch_index_select(ix->values, ix->positions, ix->n,
-                                            use_btree && ix->tree.depth > 0 ? &ix->tree : nullptr,
-                                            lo, hi, d_pos_out, g.idx_bounds, d_count, g.sm_count,
-                                            g.stream);
-    if (adb_status s = after_launch("index_select", k_)) return s;
+    if (adb_status s = adb_select_index_count(ix, use_btree, lo, hi, d_count, nullptr)) return s;
+    if (adb_status s = adb_select_index_emit(ix, d_pos_out)) return s;
     return finish_count(d_count, h_count);
 }
 

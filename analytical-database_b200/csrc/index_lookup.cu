@@ -112,20 +112,24 @@ index_emit_kernel(const int32_t *__restrict__ positions, const int64_t *__restri
         out[i] = positions[first + i];
 }
 
-int launch_index_select(const int32_t *values, const int32_t *positions, int64_t n,
-                        const BTreeView *tree, const int32_t *lo, const int32_t *hi,
-                        int32_t *out, int64_t *bounds, int64_t *d_count, int sm_count,
-                        cudaStream_t s) {
+int launch_index_bounds(const int32_t *values, int64_t n, const BTreeView *tree, const int32_t *lo,
+                        const int32_t *hi, int64_t *bounds, int64_t *d_count, cudaStream_t s) {
     IndexQuery q{lo ? *lo : 0, hi ? *hi : 0, lo != nullptr, hi != nullptr};
     BTreeView view{};
     if (tree) view = *tree;
     index_bounds_kernel<<<1, kWarp, 0, s>>>(values, n, view, tree != nullptr && view.depth > 0, q,
                                             bounds, d_count);
+    return 1;
+}
+
+// `n` only bounds the grid; the kernel copies exactly bounds[1] positions.
+int launch_index_emit(const int32_t *positions, int64_t n, const int64_t *bounds, int32_t *out,
+                      int sm_count, cudaStream_t s) {
     int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
     if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
     if (blocks < 1) blocks = 1;
     index_emit_kernel<<<(int)blocks, 256, 0, s>>>(positions, bounds, out);
-    return 2;
+    return 1;
 }
 
 }  // namespace adb

@@ -250,7 +250,25 @@ size_t select_mask_words(uint32_t n, int sm_count) {
     return (size_t)g.num_chunks * (g.chunk_rows / 32);
 }
 
-int launch_select(const SelectArgs &a, cudaStream_t s) {
+// One CTA folds the per-chunk hit counts into the select's total (count phase of the
+// two-phase form: the caller sizes the position list before expand_kernel runs).
+__global__ void __launch_bounds__(1024)
+count_total_kernel(const uint32_t *__restrict__ counts, uint32_t num_chunks,
+                   int64_t *__restrict__ d_count) {
+    __shared__ unsigned long long s_w[32];
+    unsigned long long acc = 0;
+    for (uint32_t i = threadIdx.x; i < num_chunks; i += 1024) acc += counts[i];
+    acc = (unsigned long long)warp_sum_i64((int64_t)acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 32; ++w) t += s_w[w];
+        *d_count = (int64_t)t;
+    }
+}
+
+int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s) {
     if (a.n == 0) {
         cudaMemsetAsync(a.d_count, 0, sizeof(int64_t), s);
         return 0;
@@ -258,6 +276,14 @@ int launch_select(const SelectArgs &a, cudaStream_t s) {
     const SelectGeom g = select_geom(a.n, a.sm_count);
     mask_kernel<<<g.grid, SEL_THREADS, 0, s>>>(a.val, a.d_n, a.n, a.range, g.chunk_rows,
                                                g.num_chunks, a.mask, a.counts);
+    if (!with_total) return 1;
+    count_total_kernel<<<1, 1024, 0, s>>>(a.counts, g.num_chunks, a.d_count);
+    return 2;
+}
+
+int launch_select_expand(const SelectArgs &a, cudaStream_t s) {
+    if (a.n == 0) return 0;
+    const SelectGeom g = select_geom(a.n, a.sm_count);
     if (a.pos_in)
         expand_kernel<true><<<g.grid, SEL_THREADS, 0, s>>>(a.mask, a.counts, g.chunk_rows,
                                                            g.num_chunks, a.pos_in, a.base_pos,
@@ -266,7 +292,11 @@ int launch_select(const SelectArgs &a, cudaStream_t s) {
         expand_kernel<false><<<g.grid, SEL_THREADS, 0, s>>>(a.mask, a.counts, g.chunk_rows,
                                                             g.num_chunks, nullptr, a.base_pos,
                                                             a.out, a.d_count);
-    return 2;
+    return 1;
+}
+
+int launch_select(const SelectArgs &a, cudaStream_t s) {
+    return launch_select_mask(a, false, s) + launch_select_expand(a, s);
 }
 
 }  // namespace adb

@@ -119,6 +119,10 @@ class Engine:
         "adb_mark_elapsed": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
         "adb_select_scan": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I32P, _I64P, _I64P]),
         "adb_select_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P, _I32P, _I32P, _I64P, _I64P]),
+        "adb_select_count": (C.c_int32, [_I32P, C.c_int64, _I64P, _I32P, _I32P, _I64P, _I64P]),
+        "adb_select_emit": (C.c_int32, [_I32P, C.c_int32, _I32P]),
+        "adb_select_index_count": (C.c_int32, [C.c_void_p, C.c_int32, _I32P, _I32P, _I64P, _I64P]),
+        "adb_select_index_emit": (C.c_int32, [C.c_void_p, _I32P]),
         "adb_fetch": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, C.c_int32, _I32P]),
         "adb_aggregate": (C.c_int32, [_I32P, C.c_int64, _I64P, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_agg_combine": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
@@ -223,6 +227,17 @@ class Engine:
                                            C.byref(h) if sync else None))
         return out, d_count, (int(h.value) if sync else None)
 
+    def select_exact(self, val: DevBuf, n: int, lo=None, hi=None, pos_in: DevBuf | None = None,
+                     base: int = 0, d_n: DevBuf | None = None):
+        """Two-phase select (count, then emit into an exactly sized list): (pos DevBuf, count)."""
+        (plo, _a), (phi, _b) = _bound(lo), _bound(hi)
+        h = C.c_int64(-1)
+        self._ck(self.lib.adb_select_count(val.i32(), n, d_n.i64() if d_n else None, plo, phi,
+                                           None, C.byref(h)))
+        out = self.alloc_i32(h.value)
+        self._ck(self.lib.adb_select_emit(pos_in.i32() if pos_in else None, base, out.i32()))
+        return out, int(h.value)
+
     def fetch(self, col: DevBuf, pos: DevBuf, n_max: int, d_n: DevBuf | None = None, base: int = 0,
               out: DevBuf | None = None) -> DevBuf:
         """fetch_column (query.c:223)."""
@@ -295,6 +310,15 @@ class Engine:
         self._ck(self.lib.adb_select_index(handle, int(use_btree), plo, phi, out.i32(),
                                            d_count.i64(), C.byref(h)))
         d_count.free()
+        return out, int(h.value)
+
+    def select_index_exact(self, handle, lo=None, hi=None, use_btree: bool = False):
+        """Two-phase index select: (pos DevBuf, count)."""
+        (plo, _a), (phi, _b) = _bound(lo), _bound(hi)
+        h = C.c_int64(-1)
+        self._ck(self.lib.adb_select_index_count(handle, int(use_btree), plo, phi, None, C.byref(h)))
+        out = self.alloc_i32(h.value)
+        self._ck(self.lib.adb_select_index_emit(handle, out.i32()))
         return out, int(h.value)
 
     def synth_uniform(self, n: int, seed: int, first_row: int = 0, lo: int = 0,

@@ -95,6 +95,18 @@ ADB_API adb_status adb_select_pairs(const int32_t *d_val, const int32_t *d_pos, 
                             const int64_t *d_n, const int32_t *lo, const int32_t *hi,
                             int32_t *d_pos_out, int64_t *d_count, int64_t *h_count);
 
+/* ---- two-phase select: size the position list exactly (the reference mallocs row_count
+ * ints per select, query.c:94; 2 GB per handle on a 500 M-row shard is not an option in
+ * HBM).  adb_select_count runs the predicate pass over d_val (a base column or the value
+ * half of a pair list) and returns the hit count; adb_select_emit then writes the positions:
+ * base_pos + row when d_pos_in is NULL (select_column_scan), d_pos_in[row] otherwise
+ * (select_result).  d_count may be NULL.  Any other select between the two calls
+ * invalidates the pending count. */
+ADB_API adb_status adb_select_count(const int32_t *d_val, int64_t n_max, const int64_t *d_n,
+                            const int32_t *lo, const int32_t *hi, int64_t *d_count,
+                            int64_t *h_count);
+ADB_API adb_status adb_select_emit(const int32_t *d_pos_in, int32_t base_pos, int32_t *d_pos_out);
+
 /* ---- fetch (gather) -- replaces fetch_column, src/query.c:223-243
  * d_val_out[i] = d_col[d_pos[i] - base_pos], i < n (n from d_n when non-NULL). */
 ADB_API adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
@@ -172,6 +184,11 @@ ADB_API adb_status adb_index_destroy(adb_index *ix);
 ADB_API adb_status adb_select_index(const adb_index *ix, int32_t use_btree, const int32_t *lo,
                                     const int32_t *hi, int32_t *d_pos_out, int64_t *d_count,
                                     int64_t *h_count);
+
+/* two-phase form, as adb_select_count / adb_select_emit */
+ADB_API adb_status adb_select_index_count(const adb_index *ix, int32_t use_btree, const int32_t *lo,
+                                          const int32_t *hi, int64_t *d_count, int64_t *h_count);
+ADB_API adb_status adb_select_index_emit(const adb_index *ix, int32_t *d_pos_out);
 
 /* ---- index build -- replaces quicksort / partition / init_column_index, src/index.c:25-101
  * (values ascending, positions) of d_col by a stable LSD radix sort: ties come out in

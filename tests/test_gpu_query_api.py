@@ -1,0 +1,228 @@
+"""GPU parity of the drop-in operator API (host/query_shim.c -> libadb_query.so): the
+reference's own function names (src/include/query.h:20-44) driven the way the dispatcher
+drives them (src/server.c:137-435), compared bit for bit with the reference's objects
+(oracle/_ref) or the oracle port on the same seeded inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from query_api import Api, ERROR, GeneralizedColumn, RESULT, SelectOperator, Status
+
+pytestmark = pytest.mark.gpu
+I32MAX = 2**31 - 1
+
+
+@pytest.fixture(scope="module")
+def api():
+    a = Api()
+    assert a.lib.adb_host_init(0) == 0, a.lib.adb_host_last_error()
+    yield a
+    a.lib.adb_host_shutdown()
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    from oracle import oracle
+    return oracle.reference("O2") or oracle.port()
+
+
+def table(rng, n):
+    """milestone1.py:112-121: col1,col2 in [-n/2, n/2), col3 in [0,100), col4 near INT_MAX."""
+    return (rng.integers(-n // 2, n // 2, n).astype(np.int32),
+            rng.integers(-n // 2, n // 2, n).astype(np.int32),
+            rng.integers(0, 100, n).astype(np.int32),
+            rng.integers(I32MAX - 10000, I32MAX, n, dtype=np.int64).astype(np.int32))
+
+
+@pytest.mark.parametrize("n", [1, 1000, 4097, 250_003])
+def test_select_fetch_aggregate_print(api, cpu, rng, n):
+    c1, c2, c3, c4 = table(rng, n)
+    col1, col4 = api.column(c1), api.column(c4)
+    for lo, hi in [(None, None), (None, 20), (-17, None), (-n // 8, n // 8), (5, 5), (n, None)]:
+        s = api.select_column(col1, lo, hi)
+        epos = cpu.select_scan(c1, lo, hi)
+        assert s.contents.num_tuples == epos.size and s.contents.data_type == 0
+        assert np.array_equal(api.tuples(s), epos)
+        f = api.fetch_column(col4, s)
+        evals = cpu.fetch(c4, epos)
+        assert np.array_equal(api.tuples(f), evals)
+        a = api.sum_result(f)
+        assert a.contents.data_type == 1 and a.contents.num_tuples == 1
+        assert int(api.tuples(a)[0]) == cpu.sum(evals)
+        assert api.print(a) == "%d" % cpu.sum(evals)                   # "%ld", query.c:284
+        if epos.size:
+            avg, mn, mx = api.unary("average", f), api.unary("min", f), api.unary("max", f)
+            assert api.tuples(avg)[0].tobytes() == np.float64(cpu.avg(evals)).tobytes()
+            assert int(api.tuples(mn)[0]) == cpu.min(evals) and int(api.tuples(mx)[0]) == cpu.max(evals)
+            assert api.print(avg) == "%.2f" % cpu.avg(evals)           # query.c:293
+            assert api.print(mn, mx) == "%d,%d" % (cpu.min(evals), cpu.max(evals))   # query.c:255-260
+            if epos.size <= 5000:
+                assert api.print(f) == "\n".join(str(int(v)) for v in evals)
+            for r in (avg, mn, mx):
+                api.drop(r)
+        else:
+            avg = api.unary("average", f)
+            assert np.isnan(api.tuples(avg)[0]) and api.print(avg) == "-nan"   # A7: empty avg
+            assert api.print(f) == ""
+            api.drop(avg)
+        for r in (s, f, a):
+            api.drop(r)
+    assert api.lib.adb_host_live_device_results() == 0
+
+
+def test_sum_over_a_whole_column_and_ewise(api, cpu, rng):
+    n = 123_457
+    c1, c2, c3, c4 = table(rng, n)
+    col1, col2, col4 = api.column(c1), api.column(c2), api.column(c4)
+    a = api.sum_column(col4)                                           # query.c:336-341
+    assert int(api.tuples(a)[0]) == cpu.sum_column(c4)
+    s = api.select_column(col1, -1000, 30000)
+    f2, f4 = api.fetch_column(col2, s), api.fetch_column(col4, s)
+    epos = cpu.select_scan(c1, -1000, 30000)
+    e2, e4 = cpu.fetch(c2, epos), cpu.fetch(c4, epos)
+    ad, sb = api.binary("add", f2, f4), api.binary("sub", f2, f4)      # wraps in int32 (A7)
+    assert np.array_equal(api.tuples(ad), cpu.add(e2, e4))
+    assert np.array_equal(api.tuples(sb), cpu.sub(e2, e4))
+    # chained select over an intermediate: s2=select(s1,f1,lo,hi), milestone1.py:300
+    s2 = api.select_result(f2, s, -500, 500)
+    assert np.array_equal(api.tuples(s2), cpu.select_result(e2, epos, -500, 500))
+    s3 = api.select_result(f2, s, None, None)
+    assert np.array_equal(api.tuples(s3), epos)
+    for r in (a, s, f2, f4, ad, sb, s2, s3):
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == 0
+
+
+def test_host_payload_operands_are_staged(api, cpu, rng):
+    """A Result built by foreign code (plain host int array) is a valid operand."""
+    n = 5000
+    c1, c2, _, _ = table(rng, n)
+    col2 = api.column(c2)
+    pos = np.sort(rng.choice(n, 700, replace=False)).astype(np.int32)
+    hp = api.host_result(pos)
+    f = api.fetch_column(col2, C.pointer(hp))
+    assert np.array_equal(api.tuples(f), c2[pos])
+    hv = api.host_result(c2[pos])
+    s = api.select_result(C.pointer(hv), C.pointer(hp), 0, None)
+    assert np.array_equal(api.tuples(s), cpu.select_result(c2[pos], pos, 0, None))
+    api.drop(f)
+    api.drop(s)
+
+
+@pytest.mark.parametrize("kind", ["sorted_unclustered", "btree_unclustered", "sorted_clustered",
+                                  "btree_clustered"])
+def test_indexed_select_matches_the_reference_index_path(api, cpu, rng, kind):
+    """select_column routes clustered / indexed columns through the ColumnIndex
+    (query.c:203-217); the shim uploads the index the reference built (its own quicksort
+    tie order) and must return positions in exactly the reference's order."""
+    n = 60_000
+    data = rng.integers(0, 3000, n).astype(np.int32)                   # heavy duplicates
+    values, positions = cpu.index_sort(data)
+    clustered = kind.endswith("_clustered")
+    if clustered:                                                      # index.c:119-135: identity
+        positions = np.arange(n, dtype=np.uint64)
+    col = api.column(data, index=(values, positions), sorted_=kind.startswith("sorted"),
+                     clustered=clustered)
+    vmin = int(values[0])
+    for lo, hi in [(vmin, vmin + 1), (10, 20), (100, 100), (2990, 5000), (vmin, 4000), (1500, 1400),
+                   (17, 18), (2999, 3000)]:
+        s = api.select_column(col, lo, hi)
+        exp, undefined = cpu.select_sorted_index(values, positions, lo, hi)
+        assert not undefined
+        assert np.array_equal(api.tuples(s), exp), (kind, lo, hi)
+        api.drop(s)
+    # oracle-undefined inputs (the reference crashes): scan semantics in index order
+    for lo, hi in [(-50, 5), (None, 7), (2995, None)]:
+        s = api.select_column(col, lo, hi)
+        got = api.tuples(s)
+        scan = cpu.select_scan(data, lo, hi)
+        if clustered:
+            v = values[got]                   # positions are identity over the sorted copy
+            assert got.size == scan.size and np.all((v >= (lo if lo is not None else -2**31)))
+        else:
+            assert np.array_equal(np.sort(got), scan), (kind, lo, hi)
+        api.drop(s)
+
+
+def test_shared_select(api, cpu, rng):
+    n, q = 200_003, 100
+    data = rng.integers(0, n, n).astype(np.int32)
+    col = api.column(data)
+    lows = rng.integers(0, n, q)
+    highs = lows + rng.integers(0, n // 50, q)
+    highs[3] = lows[3] - 5                                             # an empty range
+    res = api.shared_select(col, lows, highs)
+    from oracle import oracle
+    exp = oracle.port().shared_select(data, lows, highs)
+    for r, e in zip(res, exp):
+        assert np.array_equal(api.tuples(r), e)
+        api.drop(r)
+    # has_low / has_high are ignored exactly as query.c:474 does
+    ops = (SelectOperator * 1)()
+    ops[0].low, ops[0].high, ops[0].has_low, ops[0].has_high = 10, 500, 0, 0
+    st = Status(99, None)
+    r = api.lib.shared_select(ops, 1, C.byref(col), C.byref(st))
+    assert st.code == 0 and np.array_equal(api.tuples(r[0]), cpu.select_scan(data, 10, 500))
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_joins(api, cpu, rng, nested):
+    n1, n2 = (3000, 1200) if nested else (90_000, 40_000)
+    v1 = rng.integers(1, 20_000, n1).astype(np.int32)
+    v2 = rng.integers(1, 20_000, n2).astype(np.int32)
+    p1 = rng.permutation(n1).astype(np.int32)
+    p2 = rng.permutation(n2).astype(np.int32)
+    R = [C.pointer(api.host_result(x)) for x in (v1, p1, v2, p2)]
+    name = "nested_loop_join" if nested else "hash_join"
+    o1, o2 = api.join(name, *R)
+    e1, e2 = getattr(cpu, name)(v1, p1, v2, p2)
+    assert o1.contents.num_tuples == e1.size
+    assert np.array_equal(api.tuples(o1), e1) and np.array_equal(api.tuples(o2), e2)
+    api.drop(o1)
+    api.drop(o2)
+
+
+def test_error_behaviour(api, rng):
+    """Failures set code = ERROR and return NULL (the dispatcher replies "Failed",
+    src/server.c:171-174); nothing is computed on the host instead."""
+    a, b = api.host_result(np.arange(10)), api.host_result(np.arange(4))
+    st = Status(99, None)
+    assert not api.lib.add(C.pointer(a), C.pointer(b), C.byref(st)) and st.code == ERROR
+    col = api.column(np.arange(100, dtype=np.int32))
+    ops = (SelectOperator * 151)()
+    st = Status(99, None)
+    assert not api.lib.shared_select(ops, 151, C.byref(col), C.byref(st)) and st.code == ERROR
+    flagged = api.column(np.arange(100, dtype=np.int32))
+    flagged.has_index = True                                           # but no ColumnIndex
+    st = Status(99, None)
+    lo = C.c_int(1)
+    assert not api.lib.select_column(C.byref(flagged), C.byref(lo), C.byref(lo), C.byref(st))
+    assert st.code == ERROR and b"ColumnIndex" in api.lib.adb_host_last_error()
+
+
+def test_column_reupload_after_insert(api, cpu):
+    """insert_row appends in place or re-mmaps (db_manager.c:164-199): the shim notices a
+    changed row_count / data pointer and refreshes the HBM copy."""
+    buf = np.arange(1000, dtype=np.int32)
+    col = api.column(buf[:600])
+    s = api.select_column(col, 0, 10_000)
+    assert s.contents.num_tuples == 600
+    col.row_count = 1000                                               # 400 rows appended in place
+    s2 = api.select_column(col, 0, 10_000)
+    assert s2.contents.num_tuples == 1000
+    api.drop(s)
+    api.drop(s2)
+
+
+def test_payload_registry_reclaims_on_address_reuse(api):
+    """No patch and no interposer: freeing a payload behind the shim's back leaks HBM only
+    until malloc hands the address out again."""
+    import query_api
+    col = api.column(np.arange(50_000, dtype=np.int32))
+    base = api.lib.adb_host_live_device_results()
+    for _ in range(20):
+        s = api.select_column(col, 100, 200)                           # same size -> same malloc bin
+        query_api._libc.free(s.contents.payload)                       # plumbing-style free, no hook
+        query_api._libc.free(C.cast(s, C.c_void_p))
+    assert api.lib.adb_host_live_device_results() <= base + 3
