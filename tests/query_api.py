@@ -173,14 +173,14 @@ class Api:
             ops[i].low, ops[i].high, ops[i].has_low, ops[i].has_high = int(lows[i]), int(highs[i]), 1, 1
         st = Status(99, None)
         res = self.check(self.lib.shared_select(ops, q, C.byref(col), C.byref(st)), st, "shared_select")
-        out = [res[i] for i in range(q)]
+        out = [C.pointer(res[i].contents) for i in range(q)]    # detach from the array about to be freed
         _libc.free(C.cast(res, C.c_void_p))
         return out
 
     def join(self, name, v1, p1, v2, p2):
         st = Status(99, None)
         res = self.check(getattr(self.lib, name)(v1, p1, v2, p2, C.byref(st)), st, name)
-        out = (res[0], res[1])
+        out = (C.pointer(res[0].contents), C.pointer(res[1].contents))
         _libc.free(C.cast(res, C.c_void_p))      # src/server.c:432
         return out
 
