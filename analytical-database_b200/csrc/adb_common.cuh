@@ -85,6 +85,90 @@ __device__ __forceinline__ bool in_range(int32_t v, const Range &r) {
     return v >= r.lo && v <= r.hi_incl;
 }
 
+// ---- aggregate accumulator + the block -> grid fold shared by aggregate_kernel and the
+// fused chain kernel --------------------------------------------------------------------------
+struct AggAcc {
+    int64_t sum;
+    int32_t mn, mx;
+    __device__ __forceinline__ void add(int32_t v) {
+        sum += v;
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    __device__ __forceinline__ void add4(const int4 &v) {
+        // pairwise int64 adds keep the carry chain short
+        sum += ((int64_t)v.x + (int64_t)v.y) + ((int64_t)v.z + (int64_t)v.w);
+        mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
+        mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+    }
+};
+
+// Every thread of every CTA calls this once with its private accumulator and its share of
+// the tuple count.  Warp shuffles -> one partial per CTA in `scratch` -> the last CTA to
+// arrive (ticket) folds all partials in a fixed order and writes *out.  The ticket re-arms
+// itself, so back-to-back launches on one stream need no reset.
+template <int THREADS>
+__device__ __forceinline__ void agg_grid_fold(AggAcc acc, int64_t cnt, adb_agg *__restrict__ out,
+                                              adb_agg *scratch, unsigned int *ticket) {
+    constexpr int W = THREADS / kWarp;
+    __shared__ int64_t s_sum[W], s_cnt[W];
+    __shared__ int32_t s_mn[W], s_mx[W];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    acc.sum = warp_sum_i64(acc.sum);
+    cnt = warp_sum_i64(cnt);
+    acc.mn = warp_min_i32(acc.mn);
+    acc.mx = warp_max_i32(acc.mx);
+    if (lane == 0) { s_sum[warp] = acc.sum; s_cnt[warp] = cnt; s_mn[warp] = acc.mn; s_mx[warp] = acc.mx; }
+    __syncthreads();
+    if (warp == 0) {
+        AggAcc b{lane < W ? s_sum[lane] : 0, lane < W ? s_mn[lane] : INT32_MAX,
+                 lane < W ? s_mx[lane] : INT32_MIN};
+        int64_t c = lane < W ? s_cnt[lane] : 0;
+        b.sum = warp_sum_i64(b.sum);
+        c = warp_sum_i64(c);
+        b.mn = warp_min_i32(b.mn);
+        b.mx = warp_max_i32(b.mx);
+        if (lane == 0) {
+            scratch[blockIdx.x] = adb_agg{b.sum, c, b.mn, b.mx};
+            __threadfence();
+            const unsigned int done = atomicAdd(ticket, 1u);
+            s_last = (done == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    AggAcc g{0, INT32_MAX, INT32_MIN};
+    int64_t gc = 0;
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += THREADS) {
+        const volatile adb_agg *p = scratch + k;        // written by other CTAs: no .nc path
+        g.sum += p->sum;
+        gc += p->count;
+        g.mn = min(g.mn, p->min);
+        g.mx = max(g.mx, p->max);
+    }
+    g.sum = warp_sum_i64(g.sum);
+    gc = warp_sum_i64(gc);
+    g.mn = warp_min_i32(g.mn);
+    g.mx = warp_max_i32(g.mx);
+    __syncthreads();
+    if (lane == 0) { s_sum[warp] = g.sum; s_cnt[warp] = gc; s_mn[warp] = g.mn; s_mx[warp] = g.mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        AggAcc f{0, INT32_MAX, INT32_MIN};
+        int64_t fc = 0;
+        for (int w = 0; w < W; ++w) {
+            f.sum += s_sum[w];
+            fc += s_cnt[w];
+            f.mn = min(f.mn, s_mn[w]);
+            f.mx = max(f.mx, s_mx[w]);
+        }
+        *out = adb_agg{f.sum, fc, f.mn, f.mx};
+        *ticket = 0;                                    // re-arm for the next launch
+    }
+}
+
 // splitmix64 finaliser: the counter-based generator behind adb_synth_uniform
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
     uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
@@ -111,11 +195,17 @@ struct SelectArgs {
     uint32_t *mask;               // selection bitmap scratch (select_mask_words() words)
     uint32_t *counts;             // per-warp-chunk hit counts (kMaxSelectChunks)
     int sm_count;
+    // fused chain (launch_select_expand_fetch_agg): gather + aggregate while expanding
+    const int32_t *fetch_col;     // values gathered at every emitted row
+    int32_t *val_out;
+    adb_agg *agg_out, *agg_scratch;
+    unsigned int *agg_ticket;
 };
 int launch_select(const SelectArgs &a, cudaStream_t s);
 // two-phase form: mask + per-chunk counts (+ total into a.d_count), then expand into a.out
 int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s);
 int launch_select_expand(const SelectArgs &a, cudaStream_t s);
+int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s);
 size_t select_mask_words(uint32_t n, int sm_count);
 constexpr uint32_t kMaxSelectChunks = 1u << 16;
 

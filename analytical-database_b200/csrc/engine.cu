@@ -60,6 +60,7 @@ struct Engine {
         bool swapped = false;
     } join;
     int64_t launches = 0;
+    int32_t chain_mark_base = -1;       // adb_chain_marks(): slots for the next chain call
 } g;
 
 
@@ -307,6 +308,14 @@ adb_status adb_mark_elapsed(int32_t from_slot, int32_t to_slot, float *ms) {
     return ADB_OK;
 }
 
+adb_status adb_chain_marks(int32_t base_slot) {
+    NEED_UP();
+    if (base_slot >= 0 && base_slot + 2 >= ADB_MAX_MARKS)
+        return fail(ADB_ERR_INVALID, "adb_chain_marks: slot %d out of range", base_slot);
+    g.chain_mark_base = base_slot;
+    return ADB_OK;
+}
+
 // ---- operators ---------------------------------------------------------------------------
 static adb_status finish_count(int64_t *d_count, int64_t *h_count) {
     if (!h_count) return ADB_OK;
@@ -450,7 +459,28 @@ adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d
                                       int64_t n, const int32_t *lo, const int32_t *hi,
                                       int32_t *d_pos_out, int32_t *d_val_out,
                                       int64_t *d_count, adb_agg *d_agg) {
-    if (adb_status s = adb_select_scan(d_sel_col, n, lo, hi, 0, d_pos_out, d_count, nullptr)) return s;
+    adb::SelectArgs a;
+    if (!d_count || !d_agg || (n > 0 && (!d_pos_out || !d_val_out || !d_fetch_col))) {
+        NEED_UP();
+        return fail(ADB_ERR_INVALID, "adb_chain_select_fetch_agg: NULL device pointer");
+    }
+    if (adb_status s = select_prepare("adb_chain_select_fetch_agg", d_sel_col, nullptr, n, nullptr, lo, hi, d_count, &a)) return s;
+    a.base_pos = 0; a.out = d_pos_out;
+    a.fetch_col = d_fetch_col; a.val_out = d_val_out;
+    a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
+    // two launches: predicate pass -> bitmap, then expansion with the gather and the
+    // aggregates fused in (positions and values are still materialised)
+    const int32_t mb = g.chain_mark_base;
+    g.chain_mark_base = -1;
+    if (mb >= 0) adb_mark(mb);
+    int k_ = adb::launch_select_mask(a, false, g.stream);
+    if (mb >= 0) adb_mark(mb + 1);
+    const int f_ = adb::launch_select_expand_fetch_agg(a, g.stream);
+    if (mb >= 0) adb_mark(mb + 2);
+    if (f_ > 0) return after_launch("chain", k_ + f_);
+    // empty column (or a grid larger than the fold scratch): the three-operator form
+    k_ += adb::launch_select_expand(a, g.stream);
+    if (adb_status s = after_launch("chain", k_)) return s;
     if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, n, d_count, 0, d_val_out)) return s;
     return adb_aggregate(d_val_out, n, d_count, d_agg, nullptr);
 }

@@ -56,28 +56,9 @@ fetch_kernel(const int32_t *__restrict__ col, const int32_t *__restrict__ pos, i
 }
 
 // ---- aggregate: {sum (int64), min, max, count} in one pass --------------------------------
-struct AggAcc {
-    int64_t sum;
-    int32_t mn, mx;
-    __device__ __forceinline__ void add(int32_t v) {
-        sum += v;
-        mn = min(mn, v);
-        mx = max(mx, v);
-    }
-    __device__ __forceinline__ void add4(const int4 &v) {
-        // pairwise int64 adds keep the carry chain short
-        sum += ((int64_t)v.x + (int64_t)v.y) + ((int64_t)v.z + (int64_t)v.w);
-        mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
-        mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
-    }
-};
-
 __global__ void __launch_bounds__(STREAM_THREADS)
 aggregate_kernel(const int32_t *__restrict__ v, int64_t n_max, const int64_t *__restrict__ d_n,
                  adb_agg *__restrict__ out, adb_agg *scratch, unsigned int *ticket) {
-    __shared__ int64_t s_sum[STREAM_THREADS / kWarp];
-    __shared__ int32_t s_mn[STREAM_THREADS / kWarp], s_mx[STREAM_THREADS / kWarp];
-    __shared__ bool s_last;
     const int64_t n = resolve_n(n_max, d_n);
     AggAcc acc{0, INT32_MAX, INT32_MIN};
 
@@ -98,55 +79,7 @@ aggregate_kernel(const int32_t *__restrict__ v, int64_t n_max, const int64_t *__
     for (; i < nvec; i += stride) acc.add4(ld_stream(v4 + i));
     if (tid < head) acc.add(v[tid]);
     for (int64_t t = head + (nvec << 2) + tid; t < n; t += stride) acc.add(v[t]);
-
-    // warp -> block
-    acc.sum = warp_sum_i64(acc.sum);
-    acc.mn = warp_min_i32(acc.mn);
-    acc.mx = warp_max_i32(acc.mx);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { s_sum[warp] = acc.sum; s_mn[warp] = acc.mn; s_mx[warp] = acc.mx; }
-    __syncthreads();
-    if (warp == 0) {
-        constexpr int W = STREAM_THREADS / kWarp;
-        AggAcc b{lane < W ? s_sum[lane] : 0, lane < W ? s_mn[lane] : INT32_MAX,
-                 lane < W ? s_mx[lane] : INT32_MIN};
-        b.sum = warp_sum_i64(b.sum);
-        b.mn = warp_min_i32(b.mn);
-        b.mx = warp_max_i32(b.mx);
-        if (lane == 0) {
-            scratch[blockIdx.x] = adb_agg{b.sum, 0, b.mn, b.mx};
-            __threadfence();
-            const unsigned int done = atomicAdd(ticket, 1u);
-            s_last = (done == gridDim.x - 1);
-        }
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // block -> grid: the last block to finish folds every partial (deterministic order)
-    __threadfence();
-    AggAcc g{0, INT32_MAX, INT32_MIN};
-    for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
-        const volatile adb_agg *p = scratch + k;        // written by other CTAs: no .nc path
-        g.sum += p->sum;
-        g.mn = min(g.mn, p->min);
-        g.mx = max(g.mx, p->max);
-    }
-    g.sum = warp_sum_i64(g.sum);
-    g.mn = warp_min_i32(g.mn);
-    g.mx = warp_max_i32(g.mx);
-    __syncthreads();
-    if (lane == 0) { s_sum[warp] = g.sum; s_mn[warp] = g.mn; s_mx[warp] = g.mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        AggAcc f{0, INT32_MAX, INT32_MIN};
-        for (int w = 0; w < STREAM_THREADS / kWarp; ++w) {
-            f.sum += s_sum[w];
-            f.mn = min(f.mn, s_mn[w]);
-            f.mx = max(f.mx, s_mx[w]);
-        }
-        *out = adb_agg{f.sum, n, f.mn, f.mx};
-        *ticket = 0;                                    // re-arm for the next launch
-    }
+    agg_grid_fold<STREAM_THREADS>(acc, blockIdx.x == 0 && threadIdx.x == 0 ? n : 0, out, scratch, ticket);
 }
 
 __global__ void agg_combine_kernel(const adb_agg *__restrict__ parts, int32_t k,

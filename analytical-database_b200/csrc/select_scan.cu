@@ -139,21 +139,36 @@ mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, ui
 // ------------------------------------------------------------------------------------------
 // expand_kernel: bitmap -> ascending positions.
 // ------------------------------------------------------------------------------------------
-template <bool PAIRS>
+// FETCH fuses the rest of the north-star chain into the expansion: every emitted row is
+// also gathered from `fetch_col` into `val_out` and folded into {sum, min, max, count}
+// (fetch_column + sum/min/max, query.c:223-243,325-437), so the position list and the value
+// vector are still materialised but neither is read back from HBM by a later kernel.
+struct ChainArgs {
+    const int32_t *fetch_col;
+    int32_t *val_out;
+    adb_agg *agg_out, *agg_scratch;
+    unsigned int *agg_ticket;
+};
+
+template <bool PAIRS, bool FETCH>
 __global__ void __launch_bounds__(SEL_THREADS)
 expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
               uint32_t chunk_rows, uint32_t num_chunks, const int32_t *__restrict__ pos_in,
-              int32_t base_pos, int32_t *__restrict__ out, int64_t *__restrict__ d_count) {
+              int32_t base_pos, int32_t *__restrict__ out, int64_t *__restrict__ d_count,
+              ChainArgs ch) {
     __shared__ uint32_t s_red[SEL_WARPS];
     __shared__ int32_t s_stage[SEL_WARPS][kWarp * 32 * EXP_WORDS / 4];   // 1024 positions per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t first_chunk = blockIdx.x * SEL_WARPS;
+    const int32_t *__restrict__ fcol = ch.fetch_col;
+    int32_t *__restrict__ vout = ch.val_out;
+    AggAcc acc{0, INT32_MAX, INT32_MIN};
 
     // exclusive prefix of this CTA: sum of every chunk count before it
-    uint32_t acc = 0;
-    for (uint32_t i = threadIdx.x; i < first_chunk; i += SEL_THREADS) acc += counts[i];
-    acc = warp_sum(acc);
-    if (lane == 0) s_red[warp] = acc;
+    uint32_t accum = 0;
+    for (uint32_t i = threadIdx.x; i < first_chunk; i += SEL_THREADS) accum += counts[i];
+    accum = warp_sum(accum);
+    if (lane == 0) s_red[warp] = accum;
     __syncthreads();
     uint32_t base = 0;
 #pragma unroll
@@ -166,65 +181,92 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
     }
     const uint32_t chunk = first_chunk + warp;
     if (chunk == num_chunks - 1 && lane == 0) *d_count = (int64_t)base + my_count;
-    if (chunk >= num_chunks || my_count == 0) return;
+    const bool active = chunk < num_chunks && my_count != 0;
+    if (!FETCH && !active) return;
 
-    const uint32_t row_begin = chunk * chunk_rows;
-    const uint32_t nwords = chunk_rows / 32;
-    const uint32_t *__restrict__ words = mask + row_begin / 32;
-    int32_t *stage = s_stage[warp];
-    uint32_t out_off = base;
-    // each step: lane owns EXP_WORDS consecutive words (128 rows); warp covers 4096 rows
-    for (uint32_t w0 = 0; w0 < nwords && out_off < base + my_count; w0 += kWarp * EXP_WORDS) {
-        const uint32_t wi = w0 + lane * EXP_WORDS;
-        uint4 m = make_uint4(0, 0, 0, 0);
-        if (wi < nwords) m = *reinterpret_cast<const uint4 *>(words + wi);   // nwords % 16 == 0
-        const uint32_t c = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
-        const uint32_t incl = warp_incl_scan(c, lane);
-        const uint32_t step_total = __shfl_sync(kFull, incl, 31);
-        if (step_total == 0) continue;
-        uint32_t r = incl - c;                               // rank of this lane's first hit
-        const uint32_t row0 = row_begin + wi * 32;
-        const uint32_t mm[EXP_WORDS] = {m.x, m.y, m.z, m.w};
-        if (step_total <= 2 * kWarp) {
-            // sparse: straight from registers
-#pragma unroll
-            for (int q = 0; q < EXP_WORDS; ++q) {
-                uint32_t bits = mm[q];
-                while (bits) {
-                    const uint32_t b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const uint32_t row = row0 + q * 32 + b;
-                    out[out_off + r++] = PAIRS ? pos_in[row] : (int32_t)row + base_pos;
-                }
-            }
-        } else {
-            // dense: compact into shared memory (<= 1024 at a time), write full rows
-            uint32_t done = 0;                               // positions already flushed
-            while (done < step_total) {
-                const uint32_t lim = done + 1024;
-                uint32_t rr = r;
+    if (active) {
+        const uint32_t row_begin = chunk * chunk_rows;
+        const uint32_t nwords = chunk_rows / 32;
+        const uint32_t *__restrict__ words = mask + row_begin / 32;
+        int32_t *stage = s_stage[warp];
+        uint32_t out_off = base;
+        // each step: lane owns EXP_WORDS consecutive words (128 rows); warp covers 4096 rows.
+        // The next step's words are requested before this step's hits are written out.
+        uint4 m_next = make_uint4(0, 0, 0, 0);
+        if (lane * EXP_WORDS < nwords) m_next = *reinterpret_cast<const uint4 *>(words + lane * EXP_WORDS);
+        for (uint32_t w0 = 0; w0 < nwords && out_off < base + my_count; w0 += kWarp * EXP_WORDS) {
+            const uint32_t wi = w0 + lane * EXP_WORDS;
+            const uint4 m = m_next;
+            const uint32_t wn = wi + kWarp * EXP_WORDS;
+            m_next = make_uint4(0, 0, 0, 0);
+            if (wn < nwords) m_next = *reinterpret_cast<const uint4 *>(words + wn);   // nwords % 16 == 0
+            const uint32_t c = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+            const uint32_t incl = warp_incl_scan(c, lane);
+            const uint32_t step_total = __shfl_sync(kFull, incl, 31);
+            if (step_total == 0) continue;
+            uint32_t r = incl - c;                               // rank of this lane's first hit
+            const uint32_t row0 = row_begin + wi * 32;
+            const uint32_t mm[EXP_WORDS] = {m.x, m.y, m.z, m.w};
+            if (step_total <= 2 * kWarp) {
+                // sparse: straight from registers
 #pragma unroll
                 for (int q = 0; q < EXP_WORDS; ++q) {
                     uint32_t bits = mm[q];
                     while (bits) {
                         const uint32_t b = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        if (rr >= done && rr < lim) {
-                            const uint32_t row = row0 + q * 32 + b;
-                            stage[rr - done] = PAIRS ? pos_in[row] : (int32_t)row + base_pos;
+                        const uint32_t row = row0 + q * 32 + b;
+                        out[out_off + r] = PAIRS ? pos_in[row] : (int32_t)row + base_pos;
+                        if (FETCH) {
+                            const int32_t v = __ldg(fcol + row);
+                            vout[out_off + r] = v;
+                            acc.add(v);
                         }
-                        ++rr;
+                        ++r;
                     }
                 }
-                __syncwarp();
-                const uint32_t cnt = step_total - done < 1024 ? step_total - done : 1024;
-                for (uint32_t i = lane; i < cnt; i += kWarp) out[out_off + done + i] = stage[i];
-                __syncwarp();
-                done += cnt;
+            } else {
+                // dense: compact into shared memory (<= 1024 at a time), write full rows
+                uint32_t done = 0;                               // positions already flushed
+                while (done < step_total) {
+                    const uint32_t lim = done + 1024;
+                    uint32_t rr = r;
+#pragma unroll
+                    for (int q = 0; q < EXP_WORDS; ++q) {
+                        uint32_t bits = mm[q];
+                        while (bits) {
+                            const uint32_t b = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            if (rr >= done && rr < lim) {
+                                const uint32_t row = row0 + q * 32 + b;
+                                stage[rr - done] = (PAIRS && !FETCH) ? pos_in[row] : (int32_t)row;
+                            }
+                            ++rr;
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t cnt = step_total - done < 1024 ? step_total - done : 1024;
+                    for (uint32_t i = lane; i < cnt; i += kWarp) {
+                        const int32_t row = stage[i];
+                        if (FETCH) {
+                            out[out_off + done + i] = PAIRS ? pos_in[row] : row + base_pos;
+                            const int32_t v = __ldg(fcol + row);
+                            vout[out_off + done + i] = v;
+                            acc.add(v);
+                        } else {
+                            out[out_off + done + i] = PAIRS ? row : row + base_pos;
+                        }
+                    }
+                    __syncwarp();
+                    done += cnt;
+                }
             }
+            out_off += step_total;
         }
-        out_off += step_total;
     }
+    if (FETCH)
+        agg_grid_fold<SEL_THREADS>(acc, lane == 0 && chunk < num_chunks ? (int64_t)my_count : 0,
+                                   ch.agg_out, ch.agg_scratch, ch.agg_ticket);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -285,13 +327,24 @@ int launch_select_expand(const SelectArgs &a, cudaStream_t s) {
     if (a.n == 0) return 0;
     const SelectGeom g = select_geom(a.n, a.sm_count);
     if (a.pos_in)
-        expand_kernel<true><<<g.grid, SEL_THREADS, 0, s>>>(a.mask, a.counts, g.chunk_rows,
-                                                           g.num_chunks, a.pos_in, a.base_pos,
-                                                           a.out, a.d_count);
+        expand_kernel<true, false><<<g.grid, SEL_THREADS, 0, s>>>(
+            a.mask, a.counts, g.chunk_rows, g.num_chunks, a.pos_in, a.base_pos, a.out, a.d_count,
+            ChainArgs{});
     else
-        expand_kernel<false><<<g.grid, SEL_THREADS, 0, s>>>(a.mask, a.counts, g.chunk_rows,
-                                                            g.num_chunks, nullptr, a.base_pos,
-                                                            a.out, a.d_count);
+        expand_kernel<false, false><<<g.grid, SEL_THREADS, 0, s>>>(
+            a.mask, a.counts, g.chunk_rows, g.num_chunks, nullptr, a.base_pos, a.out, a.d_count,
+            ChainArgs{});
+    return 1;
+}
+
+// select_column_scan's expansion with fetch_column and the aggregates fused in.  Row r of the
+// scanned column pairs with row r of fetch_col (same table, same shard).
+int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s) {
+    const SelectGeom g = select_geom(a.n ? a.n : 1, a.sm_count);
+    if (a.n == 0 || (int)g.grid > kAggMaxBlocks) return -1;          // caller falls back to 3 launches
+    expand_kernel<false, true><<<g.grid, SEL_THREADS, 0, s>>>(
+        a.mask, a.counts, g.chunk_rows, g.num_chunks, nullptr, a.base_pos, a.out, a.d_count,
+        ChainArgs{a.fetch_col, a.val_out, a.agg_out, a.agg_scratch, a.agg_ticket});
     return 1;
 }
 

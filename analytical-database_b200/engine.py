@@ -116,6 +116,7 @@ class Engine:
         "adb_timer_stop": (C.c_int32, [C.POINTER(C.c_float)]),
         "adb_launch_count": (C.c_int64, []),
         "adb_mark": (C.c_int32, [C.c_int32]),
+        "adb_chain_marks": (C.c_int32, [C.c_int32]),
         "adb_mark_elapsed": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
         "adb_select_scan": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I32P, _I64P, _I64P]),
         "adb_select_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P, _I32P, _I32P, _I64P, _I64P]),

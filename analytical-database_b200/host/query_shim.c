@@ -52,6 +52,7 @@ typedef struct DevColumn {
     const int *host_data;
     size_t rows;
     int32_t *d_data;
+    int adopted;                /* d_data belongs to the caller (adb_host_column_adopt) */
     /* index */
     const int *host_ix_values;
     size_t ix_rows;
@@ -160,7 +161,7 @@ static void dev_column_drop(DevColumn *c) {
     if (c->ix) adb_index_destroy(c->ix);
     if (c->d_ix_values) adb_free(c->d_ix_values);
     if (c->d_ix_positions) adb_free(c->d_ix_positions);
-    if (c->d_data) adb_free(c->d_data);
+    if (c->d_data && !c->adopted) adb_free(c->d_data);
     const Column *key = c->key;
     memset(c, 0, sizeof *c);
     c->key = key;
@@ -190,7 +191,7 @@ void adb_host_shutdown(void) {
 }
 
 /* ---- base columns ----------------------------------------------------------------------- */
-static DevColumn *dev_column(Column *column) {
+static DevColumn *dev_column_slot(Column *column) {
     if (!column) {
         set_err("NULL column");
         return NULL;
@@ -218,6 +219,12 @@ static DevColumn *dev_column(Column *column) {
         memset(c, 0, sizeof *c);
         c->key = column;
     }
+    return c;
+}
+
+static DevColumn *dev_column(Column *column) {
+    DevColumn *c = dev_column_slot(column);
+    if (!c) return NULL;
     if (c->d_data && c->host_data == column->data && c->rows == column->row_count) return c;
     dev_column_drop(c);
     void *p = NULL;
@@ -236,6 +243,21 @@ static DevColumn *dev_column(Column *column) {
 int adb_host_column_upload(Column *column) {
     if (ensure_up()) return -1;
     return dev_column(column) ? 0 : -1;
+}
+
+/* The column's rows are already in HBM (a GPU-side loader put them there: SURVEY.md 8f
+ * rank 1).  The shim uses d_data as is until the column's data pointer or row_count
+ * changes; the buffer stays the caller's. */
+int adb_host_column_adopt(Column *column, const void *d_data) {
+    if (ensure_up()) return -1;
+    DevColumn *c = dev_column_slot(column);
+    if (!c || !d_data) return -1;
+    dev_column_drop(c);
+    c->d_data = (int32_t *)d_data;
+    c->adopted = 1;
+    c->host_data = column->data;
+    c->rows = column->row_count;
+    return 0;
 }
 
 void adb_host_column_invalidate(Column *column) {

@@ -209,13 +209,12 @@ def run_engine(args):
         for i, (c1, c2) in enumerate(cols):
             pos, val, cnt = res[i]
             if mark_base is not None:
-                eng.mark(mark_base + 2 * i)
-            eng._ck(lib.adb_select_scan(c1.i32(), shard_rows, C.byref(blo), C.byref(bhi), 0,
-                                        pos.i32(), cnt.i64(), None))
-            if mark_base is not None:
-                eng.mark(mark_base + 2 * i + 1)
-            eng._ck(lib.adb_fetch(c2.i32(), pos.i32(), cap, cnt.i64(), 0, val.i32()))
-            eng._ck(lib.adb_aggregate(val.i32(), cap, cnt.i64(), AggP(parts, i), None))
+                eng._ck(lib.adb_chain_marks(mark_base + 3 * i))
+            # predicate pass + expansion with the gather and the aggregates fused in; the
+            # position list and the fetched vector are still materialised (pos, val)
+            eng._ck(lib.adb_chain_select_fetch_agg(c1.i32(), c2.i32(), shard_rows, C.byref(blo),
+                                                   C.byref(bhi), pos.i32(), val.i32(), cnt.i64(),
+                                                   AggP(parts, i)))
         eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
         if dist is not None:
             eng._ck(lib.adb_agg_export(AggP(combined), C.c_void_p(t_sum.data_ptr()),
@@ -231,7 +230,7 @@ def run_engine(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    marks_per_step = 2 * len(cols)
+    marks_per_step = 3 * len(cols)
     timed_marks = args.steps * marks_per_step <= 8000
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
@@ -266,18 +265,21 @@ def run_engine(args):
         a = eng.read_agg(combined)
         g_sum, g_cnt, g_min, g_max = a.sum, a.count, a.min, a.max
 
-    # ---- roofline of the dominant kernel (select_kernel), from the in-region event marks -----
+    # ---- roofline of the dominant kernel (mask_kernel: the predicate pass over the selected
+    # column), from CUDA events recorded on the engine stream inside the timed region -------
     peak, peak_src = measured_peak()
     hits_local = [int(r[2].to_host(1, np.int64)[0]) for r in res]
-    sel_ms = []
+    mask_ms, fused_ms = [], []
     if timed_marks:
         for k in range(args.steps):
             for i in range(len(cols)):
-                sel_ms.append(eng.mark_elapsed(k * marks_per_step + 2 * i, k * marks_per_step + 2 * i + 1))
+                b = k * marks_per_step + 3 * i
+                mask_ms.append(eng.mark_elapsed(b, b + 1))
+                fused_ms.append(eng.mark_elapsed(b + 1, b + 2))
     roofline = None
-    if sel_ms:
-        avg_ms = float(np.mean(sel_ms))
-        alg_bytes = 4.0 * shard_rows + 4.0 * float(np.mean(hits_local))
+    if mask_ms:
+        avg_ms = float(np.mean(mask_ms))
+        alg_bytes = 4.0 * shard_rows                     # the 4N of select's 4N + 4H
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "select_kernel_traffic.json")
@@ -286,13 +288,24 @@ def run_engine(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm",
-                    "kernel": "adb_select_scan = adb::mask_kernel + adb::expand_kernel<false> "
-                              "(both launches timed together)", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": peak_src, "avg_launch_ms": avg_ms,
+        h_avg = float(np.mean(hits_local))
+        f_ms = float(np.mean(fused_ms))
+        roofline = {"bound": "hbm", "kernel": "adb::mask_kernel (predicate pass of adb_select_scan / "
+                    "adb_chain_select_fetch_agg: column -> 1 bit/row bitmap + per-chunk counts)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "share_of_step": float(np.sum(sel_ms) / ms_total)}
+                    "share_of_step": float(np.sum(mask_ms) / ms_total),
+                    "second_kernel": {
+                        "kernel": "adb::expand_kernel<false,true> (bitmap -> positions, gather, "
+                                  "sum/min/max fused)",
+                        "avg_launch_ms": f_ms, "share_of_step": float(np.sum(fused_ms) / ms_total),
+                        "algorithmic_bytes_per_launch": 16.0 * h_avg,
+                        "achieved": 16.0 * h_avg / (f_ms * 1e-3) / 1e9,
+                        "line_granular_bytes_per_launch": 128.0 * h_avg + 8.0 * h_avg + shard_rows / 8.0,
+                        "note": "a sparse gather moves one 128-byte line per hit on this part "
+                                "(profiles/r01c_gather_probe.md), so the kernel is DRAM-bound at "
+                                "about 8x its algorithmic bytes"}}
     chain_bytes = 4.0 * rows_step + 20.0 * g_cnt
     chain_gbs = chain_bytes / (ms_step * 1e-3) / 1e9
 
@@ -318,6 +331,11 @@ def run_engine(args):
         line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = measure_cpu(args, eng, cols, res, shard_rows, lo, hi)
+        if world == 1 and args.ops:
+            for c1, c2 in cols[1:]:
+                c1.free()
+                c2.free()
+            line["ops"] = measure_ops(args)
         print(json.dumps(line))
     barrier()
     if dist is not None:
@@ -327,38 +345,69 @@ def run_engine(args):
 
 def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
                 combined, parts):
-    """The same chain through the host-facing calls: every operator returns its num_tuples
-    to the host before the next is issued (Result.num_tuples must be host-visible,
-    parse.c:799), bounds come from host memory, and the aggregate is read back (D2H)
-    every step.  Columns are HBM-resident after load, as the reference keeps them in RAM
-    after load.  `cold` additionally re-uploads both columns of one shard from pinned host
-    memory inside the timed region (the first-touch cost of a table)."""
+    """The same chain through the reference-facing operator API -- the C host drop-in
+    (host/query_shim.c -> libadb_query.so) called exactly as src/server.c:137-290 calls
+    query.c: select_column(Column*, &lo, &hi) -> fetch_column(Column*, Result*) ->
+    sum(GeneralizedColumn*) with host Column / Result / Status structs, every operator
+    returning its num_tuples to the host before the next is issued (parse.c:799 needs it),
+    the long read back from the scalar Result, and the handles released the way
+    client_context.c does.  Wall clock.
+
+    warm: a table is uploaded to HBM once, when the shim first touches it (the reference
+          keeps loaded columns in RAM the same way); the timed steps then move only the
+          bounds down and the counts / sum up.
+    cold: one shard whose two columns live in HOST memory and are invalidated before every
+          step, so each step pays the H2D copy of 2 x 2 GB inside the timed region."""
     import torch
-    lib = eng.lib
-    blo, bhi = C.c_int32(lo), C.c_int32(hi)
-    h_cnt = C.c_int64(0)
-    from analytical_database_b200.engine import _AggStruct, AGG_BYTES
-    h_agg = _AggStruct()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import query_api as q                      # ctypes view of include/adb_query_api.h
+    api = q.Api()
+    L = api.lib
+
+    def make_col(devbuf, host=None):
+        c = q.Column()
+        c.name = b"col"
+        c.row_count = shard_rows
+        if host is not None:
+            c.data = host.ctypes.data_as(C.POINTER(C.c_int))
+        return c
+
+    hcols = []
+    for (c1, c2) in cols:
+        a, b = make_col(c1), make_col(c2)
+        assert L.adb_host_column_adopt(C.byref(a), c1.void()) == 0
+        assert L.adb_host_column_adopt(C.byref(b), c2.void()) == 0
+        hcols.append((a, b))
+    blo, bhi = C.c_int(lo), C.c_int(hi)
+    st = q.Status(99, None)
+    gen = q.GeneralizedColumn(q.RESULT)
+
+    def chain(a, b):
+        s_ = L.select_column(C.byref(a), C.byref(blo), C.byref(bhi), C.byref(st))
+        if st.code != q.OK:
+            raise SystemExit("select_column: " + L.adb_host_last_error().decode())
+        f_ = L.fetch_column(C.byref(b), s_, C.byref(st))
+        gen.column_pointer.result = f_
+        r_ = L.sum(C.byref(gen), C.byref(st))
+        if st.code != q.OK:
+            raise SystemExit("fetch/sum: " + L.adb_host_last_error().decode())
+        total = C.cast(r_.contents.payload, C.POINTER(C.c_long))[0]
+        hits = s_.contents.num_tuples
+        for h_ in (s_, f_, r_):
+            api.drop(h_)
+        return total, hits
 
     def step():
-        tot = 0
-        for i, (c1, c2) in enumerate(cols):
-            pos, val, cnt = res[i]
-            eng._ck(lib.adb_select_scan(c1.i32(), shard_rows, C.byref(blo), C.byref(bhi), 0,
-                                        pos.i32(), cnt.i64(), C.byref(h_cnt)))      # D2H 8 B
-            h = h_cnt.value
-            eng._ck(lib.adb_fetch(c2.i32(), pos.i32(), h, None, 0, val.i32()))
-            eng._ck(lib.adb_aggregate(val.i32(), h, None, eng.agg_ptr(parts, i), None))
-            tot += h
-        eng._ck(lib.adb_agg_combine(eng.agg_ptr(parts), len(cols), eng.agg_ptr(combined),
-                                    C.byref(h_agg)))                                # D2H 24 B
+        tot = hits = 0
+        for (a, b) in hcols:
+            t_, h_ = chain(a, b)
+            tot += t_
+            hits += h_
         if dist is not None:
-            eng._ck(lib.adb_agg_export(eng.agg_ptr(combined), C.c_void_p(t_sum.data_ptr()),
-                                       C.c_void_p(t_mm.data_ptr())))
+            t_sum[0], t_sum[1] = tot, hits
             dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
-            dist.all_reduce(t_mm, op=dist.ReduceOp.MAX)
-            return int(t_sum[0].item())                                             # D2H 8 B
-        return h_agg.sum
+            tot, hits = int(t_sum[0].item()), int(t_sum[1].item())
+        return tot, hits
 
     steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -368,7 +417,7 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        tot, hits = step()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -379,38 +428,56 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
         dt = float(t.item())
     rows_step = shard_rows * len(cols) * max(world, 1)
     out = {"value": rows_step * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": 8 * len(cols),          # the two int32 bounds per operator call
-           "d2h_bytes_per_step": 8 * len(cols) + 24,
+           "h2d_bytes_per_step": 0,
+           "d2h_bytes_per_step": (8 + 24) * len(cols),
            "ms_per_step": 1e3 * dt / steps, "steps": steps,
-           "mode": "warm: columns HBM-resident after load; per operator the host waits for "
-                   "num_tuples; aggregate read back every step; wall clock"}
-    # cold: one shard's two columns uploaded from pinned host memory inside the timed region
+           "api": "select_column -> fetch_column -> sum of include/adb_query_api.h "
+                  "(libadb_query.so = host/query_shim.c), one call chain per shard",
+           "mode": "warm: columns HBM-resident after load; bounds travel as kernel arguments "
+                   "(no H2D copy); per shard the host reads num_tuples (8 B) after select and "
+                   "the aggregate (24 B) after sum; wall clock; see `cold` for the H2D-inclusive figure",
+           "check": {"sum": tot, "hits": hits}}
+    # cold: HOST columns, re-uploaded by the shim inside every timed step
     if rank == 0 and world == 1 and not args.no_cold:
-        nbytes = 4 * shard_rows
-        hp1, hp2 = C.c_void_p(), C.c_void_p()
-        eng._ck(lib.adb_host_alloc(C.byref(hp1), nbytes))
-        eng._ck(lib.adb_host_alloc(C.byref(hp2), nbytes))
         c1, c2 = cols[0]
-        eng._ck(lib.adb_download(hp1, c1.void(), nbytes))
-        eng._ck(lib.adb_download(hp2, c2.void(), nbytes))
-        pos, val, cnt = res[0]
+        h1, h2 = c1.to_host(shard_rows), c2.to_host(shard_rows)
+        a, b = make_col(c1, h1), make_col(c2, h2)
+        chain(a, b)                                         # first touch
         reps = 3
         t0 = time.perf_counter()
         for _ in range(reps):
-            eng._ck(lib.adb_upload_async(c1.void(), hp1, nbytes))
-            eng._ck(lib.adb_upload_async(c2.void(), hp2, nbytes))
-            eng._ck(lib.adb_select_scan(c1.i32(), shard_rows, C.byref(blo), C.byref(bhi), 0,
-                                        pos.i32(), cnt.i64(), C.byref(h_cnt)))
-            eng._ck(lib.adb_fetch(c2.i32(), pos.i32(), h_cnt.value, None, 0, val.i32()))
-            eng._ck(lib.adb_aggregate(val.i32(), h_cnt.value, None, eng.agg_ptr(parts, 0),
-                                      C.byref(h_agg)))
+            L.adb_host_column_invalidate(C.byref(a))
+            L.adb_host_column_invalidate(C.byref(b))
+            ctot, chits = chain(a, b)
         dtc = time.perf_counter() - t0
+        L.adb_host_column_invalidate(C.byref(a))
+        L.adb_host_column_invalidate(C.byref(b))
         out["cold"] = {"value": shard_rows * reps / dtc, "unit": UNIT,
-                       "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 32,
-                       "sample": f"one {shard_rows}-row shard, both columns uploaded from pinned "
-                                 "host memory every step (PCIe-bound)"}
-        lib.adb_host_free(hp1)
-        lib.adb_host_free(hp2)
+                       "h2d_bytes_per_step": 8 * shard_rows, "d2h_bytes_per_step": 32,
+                       "ms_per_step": 1e3 * dtc / reps,
+                       "sample": f"one {shard_rows}-row shard whose two columns are host arrays; the "
+                                 "shim uploads both (pageable -> HBM) inside every timed step",
+                       "check": {"sum": ctot, "hits": chits}}
+    for (a, b) in hcols:
+        L.adb_host_column_invalidate(C.byref(a))
+        L.adb_host_column_invalidate(C.byref(b))
+    return out
+
+
+def measure_ops(args):
+    """The other BASELINE.json configs on one GPU, bounded: batched shared scan (config 2),
+    index range select + fetch (config 3), hash join with prefilters (config 4)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_ops
+    import analytical_database_b200 as adb
+    eng = adb.Engine(int(os.environ.get("LOCAL_RANK", "0")))     # same library instance
+    out = {}
+    try:
+        out["shared_scan_100q_100M"] = bench_ops.bench_shared(eng, 1.0)
+        out["index_500M"] = bench_ops.bench_index(eng, 1.0)
+        out["hash_join_100Mx100M"] = bench_ops.bench_join(eng, 1.0)
+    except Exception as e:                                        # the headline line must survive
+        out["error"] = repr(e)
     return out
 
 
@@ -468,6 +535,8 @@ def main():
     ap.add_argument("--shards-limit", type=int, default=0, help="debug: fewer shards per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
+    ap.add_argument("--ops", action="store_true",
+                    help="also time shared scan / index / join at the BASELINE config sizes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":

@@ -77,6 +77,10 @@ ADB_API adb_status adb_timer_stop(float *ms);
 #define ADB_MAX_MARKS 8192
 ADB_API adb_status adb_mark(int32_t slot);
 ADB_API adb_status adb_mark_elapsed(int32_t from_slot, int32_t to_slot, float *ms);
+/* Per-kernel timing inside the fused chain: the next adb_chain_select_fetch_agg records
+ * slots base, base+1, base+2 before the predicate pass, between its two kernels and after
+ * the fused expansion.  One-shot; a negative base cancels. */
+ADB_API adb_status adb_chain_marks(int32_t base_slot);
 /* number of engine kernels launched since adb_init (bench.py's gpu_launches) */
 ADB_API int64_t adb_launch_count(void);
 

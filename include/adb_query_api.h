@@ -145,6 +145,7 @@ extern "C" {
 int adb_host_init(int device);                    /* call from main(), src/server.c:616 */
 void adb_host_shutdown(void);                     /* call from shutdown_server(), src/server.c:40 */
 int adb_host_column_upload(Column *column);       /* after load_db + build_index, src/server.c:120-125 */
+int adb_host_column_adopt(Column *column, const void *d_data);   /* rows already in HBM (GPU-side load) */
 void adb_host_column_invalidate(Column *column);  /* after insert_row, src/server.c:250 */
 /* Device-resident results: Result.payload of a position list / value vector is a small
  * malloc'd descriptor, so the plumbing's free(payload) (src/client_context.c:35,82) stays

@@ -71,6 +71,7 @@ HOOKS = {
     "adb_host_init": (C.c_int, [C.c_int]),
     "adb_host_shutdown": (None, []),
     "adb_host_column_upload": (C.c_int, [C.POINTER(Column)]),
+    "adb_host_column_adopt": (C.c_int, [C.POINTER(Column), C.c_void_p]),
     "adb_host_column_invalidate": (None, [C.POINTER(Column)]),
     "adb_host_result_release": (None, [RP]),
     "adb_host_payload_freed": (None, [C.c_void_p]),

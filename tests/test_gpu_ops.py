@@ -138,17 +138,21 @@ def test_add_sub_wrap(eng, port, rng, n):
     assert np.array_equal(eng.ewise(da, db, n, True).to_host(n), port.sub(a, b))
 
 
-def test_chain_matches_oracle_and_reference(eng, port, rng):
-    """s=select(col1,lo,hi); f=fetch(col2,s); a=sum(f)/min/max/avg -- the north-star chain."""
+@pytest.mark.parametrize("n", [0, 1, 513, 4097, 1_000_003])
+def test_chain_matches_oracle_and_reference(eng, port, rng, n):
+    """s=select(col1,lo,hi); f=fetch(col2,s); a=sum(f)/min/max/avg -- the north-star chain
+    (predicate pass + expansion with the gather and the aggregates fused in)."""
     import ctypes as C
     from oracle import oracle
     ref = oracle.reference("O2")
-    n = 1_000_003
-    sel = rng.integers(-n // 2, n // 2, n).astype(np.int32)
+    sel = rng.integers(-n // 2 - 1, n // 2 + 1, n).astype(np.int32)
+    if n > 100000:
+        sel[200000:260000] = 7          # a dense run: the shared-memory staged write-out
     fet = rng.integers(I32MAX - 10000, I32MAX, n, dtype=np.int64).astype(np.int32)   # milestone1 col4
     ds, df = eng.upload(sel), eng.upload(fet)
     pos, val, dcnt, dagg = eng.alloc_i32(n), eng.alloc_i32(n), eng.alloc(8), eng.alloc(64)
-    for lo, hi in [(None, None), (-100, 5000), (0, None), (None, -490000), (5, 5), (-1000, 1000)]:
+    for lo, hi in [(None, None), (-100, 5000), (0, None), (None, -490000), (5, 5), (-1000, 1000),
+                   (7, 8)]:
         (plo, _a), (phi, _b) = (None, None), (None, None)
         blo = C.c_int32(lo) if lo is not None else None
         bhi = C.c_int32(hi) if hi is not None else None

@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Per-operator timings at the BASELINE.json config sizes (development tool; bench.py is
+the contract).  python tools/bench_ops.py [shared|index|join|all] [--scale 1.0]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import analytical_database_b200 as adb  # noqa: E402
+
+
+def timed(eng, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    eng.sync()
+    ms = []
+    for _ in range(reps):
+        eng.timer_start()
+        fn()
+        ms.append(eng.timer_stop())
+    return float(np.median(ms)), float(min(ms))
+
+
+def bench_shared(eng, scale):
+    n, q = int(100_000_000 * scale), 100
+    col = eng.synth_uniform(n, 42, 0, 0, n)
+    rng = np.random.default_rng(42)
+    lows = rng.integers(0, n - n // 1000, q).astype(np.int32)
+    highs = (lows + n // 1000).astype(np.int32)
+    out = {}
+
+    def run():
+        res = eng.shared_select(col, n, lows, highs)
+        for b, _ in res:
+            b.free()
+        return res
+    med, best = timed(eng, run)
+    hits = sum(c for _, c in run())
+    out = {"rows": n, "queries": q, "hits": hits, "ms": med, "best_ms": best,
+           "rows_per_s": n / (med * 1e-3), "pred_evals_per_s": n * q / (med * 1e-3),
+           "alg_gbs": (4 * n + 4 * hits) / (med * 1e-3) / 1e9}
+    # unbatched: the same 100 selects one by one
+    def run_seq():
+        for i in range(q):
+            p, c = eng.select_exact(col, n, int(lows[i]), int(highs[i]))
+            p.free()
+    med2, _ = timed(eng, run_seq, reps=3, warm=1)
+    out["unbatched_ms"] = med2
+    col.free()
+    return out
+
+
+def bench_index(eng, scale):
+    n = int(500_000_000 * scale)
+    key = eng.synth_uniform(n, 7, 0, 0, 1 << 31 - 1)
+    pay = eng.synth_uniform(n, 8, 0, 0, 10000)
+    t0 = time.perf_counter()
+    vals, poss = eng.index_sort(key, n)
+    eng.sync()
+    build_s = time.perf_counter() - t0
+    med_b, _ = timed(eng, lambda: [b.free() for b in eng.index_sort(key, n)], reps=2, warm=0)
+    ix = eng.index_create(vals, poss, n, True)
+    out = {"rows": n, "index_sort_ms": med_b, "first_build_s": build_s,
+           "sort_mkeys_per_s": n / (med_b * 1e-3) / 1e6}
+    for sel in (0.0002, 0.01, 0.1):
+        lo = 1 << 20
+        hi = lo + int((1 << 31) * sel)
+        for tree in (False, True):
+            def run():
+                p, c = eng.select_index_exact(ix, lo, hi, use_btree=tree)
+                f = eng.fetch(pay, p, c)
+                p.free(); f.free()
+                return c
+            med, best = timed(eng, run)
+            c = run()
+            out[f"sel{sel}_{'btree' if tree else 'sorted'}"] = {
+                "hits": c, "ms": med, "best_ms": best, "alg_gbs": 16.0 * c / (med * 1e-3) / 1e9}
+        def run_scan():
+            p, c = eng.select_exact(key, n, lo, hi)
+            f = eng.fetch(pay, p, c)
+            p.free(); f.free()
+        med, _ = timed(eng, run_scan, reps=3, warm=1)
+        out[f"sel{sel}_scan_ms"] = med
+    eng.index_destroy(ix)
+    for b in (key, pay, vals, poss):
+        b.free()
+    return out
+
+
+def bench_join(eng, scale):
+    n = int(100_000_000 * scale)
+    out = {}
+    k1 = eng.synth_uniform(n, 11, 0, 1, n)
+    k2 = eng.synth_uniform(n, 12, 0, 1, n)
+    f1 = eng.synth_uniform(n, 13, 0, 0, 1000)
+    f2 = eng.synth_uniform(n, 14, 0, 0, 1000)
+    for s1, s2 in ((0.8, 0.15), (0.15, 0.15), (1.0, 1.0)):
+        p1, c1 = eng.select_exact(f1, n, None, int(1000 * s1))
+        p2, c2 = eng.select_exact(f2, n, None, int(1000 * s2))
+        v1 = eng.fetch(k1, p1, c1)
+        v2 = eng.fetch(k2, p2, c2)
+        # parse.c:798-813: the larger side is column_one (build)
+        if c2 > c1:
+            (v1, p1, c1), (v2, p2, c2) = (v2, p2, c2), (v1, p1, c1)
+        def run():
+            o1, o2, m = eng.join(v1, p1, c1, v2, p2, c2)
+            o1.free(); o2.free()
+            return m
+        med, best = timed(eng, run, reps=3, warm=1)
+        m = run()
+        out[f"prefilter_{s1}_{s2}"] = {
+            "build": c1, "probe": c2, "matches": m, "ms": med, "best_ms": best,
+            "tuples_per_s": (c1 + c2) / (med * 1e-3),
+            "alg_gbs": (8.0 * (c1 + c2) + 8.0 * m) / (med * 1e-3) / 1e9}
+        for b in (p1, p2, v1, v2):
+            b.free()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--scale", type=float, default=1.0)
+    a = ap.parse_args()
+    eng = adb.Engine(0)
+    res = {}
+    if a.what in ("shared", "all"):
+        res["shared_scan"] = bench_shared(eng, a.scale)
+    if a.what in ("index", "all"):
+        res["index"] = bench_index(eng, a.scale)
+    if a.what in ("join", "all"):
+        res["join"] = bench_join(eng, a.scale)
+    print(json.dumps(res, indent=1))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
