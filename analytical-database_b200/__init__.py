@@ -7,6 +7,8 @@ Layout (only what the hot path needs):
 * ``host/``       the C host side: ``query_shim.c`` implements the reference's
                   ``query.h`` operator API on top of the C-ABI (the drop-in);
 * ``engine.py``   ctypes binding of the C-ABI for tests / bench (plumbing only);
+* ``sharded.py``  row-range sharding over N GPUs: count / aggregate / join exchange steps
+                  on ``torch.distributed`` (one process per GPU);
 * ``synth.py``    the counter-based synthetic column generator (numpy twin of
                   ``adb_synth_uniform``).
 

@@ -244,7 +244,8 @@ int launch_shared_emit(const uint16_t *cls, const SharedScanPlan &plan, const Sh
 // Stable radix partition passes + generic exclusive scan (radix.cu).
 struct RadixPass {
     int shift, bits;           // digit = (f(key) >> shift) & ((1 << bits) - 1), bits <= 8
-    bool hash;                 // f = key * 0x9E3779B1 (join) or key ^ 0x80000000 (signed order)
+    int hash;                  // f = key ^ 0x80000000 (0: signed order), key * 0x9E3779B1 (1: join
+                               // hash) or key * 0x85EBCA6B (2: routing hash, multi-GPU exchange)
 };
 struct RadixGeom {
     uint32_t rows_per_cta, ctas;

@@ -638,7 +638,7 @@ adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_values_out
     if (adb_status s = check_len(n, "adb_index_sort")) return s;
     if (n == 0) return ADB_OK;
     if (!d_col || !d_values_out || !d_positions_out) return fail(ADB_ERR_INVALID, "adb_index_sort: NULL pointer");
-    const adb::RadixPass passes[4] = {{0, 8, false}, {8, 8, false}, {16, 8, false}, {24, 8, false}};
+    const adb::RadixPass passes[4] = {{0, 8, 0}, {8, 8, 0}, {16, 8, 0}, {24, 8, 0}};
     uint32_t *k = nullptr, *v = nullptr;
     int launches = 0;
     if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(d_col), (uint32_t)n, passes, 4, &k, &v, &launches)) return s;
@@ -647,6 +647,42 @@ adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_values_out
     CU(cudaFreeAsync(k, g.stream));
     CU(cudaFreeAsync(v, g.stream));
     return after_launch("index_sort", launches);
+}
+
+// Multi-GPU join exchange, send side: stable partition of a (value, position) pair list by
+// destination rank = top log2(parts) bits of the routing hash (independent of the join's own
+// partition hash, so the receiving rank's local partitions stay balanced).
+adb_status adb_route_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n, int32_t parts,
+                           int32_t *d_val_out, int32_t *d_pos_out, int64_t *h_counts) {
+    NEED_UP();
+    if (adb_status s = check_len(n, "adb_route_pairs")) return s;
+    if (parts < 1 || parts > 256 || (parts & (parts - 1)) || !h_counts)
+        return fail(ADB_ERR_INVALID, "adb_route_pairs: parts must be a power of two in [1, 256]");
+    if (n > 0 && (!d_val || !d_pos || !d_val_out || !d_pos_out))
+        return fail(ADB_ERR_INVALID, "adb_route_pairs: NULL device pointer");
+    for (int32_t r = 0; r < parts; ++r) h_counts[r] = 0;
+    if (n == 0) return ADB_OK;
+    if (parts == 1) {
+        CU(cudaMemcpyAsync(d_val_out, d_val, n * 4, cudaMemcpyDeviceToDevice, g.stream));
+        CU(cudaMemcpyAsync(d_pos_out, d_pos, n * 4, cudaMemcpyDeviceToDevice, g.stream));
+        h_counts[0] = n;
+        return ADB_OK;
+    }
+    if (adb_status s = ensure_radix_scratch()) return s;
+    int bits = 0;
+    while ((1 << bits) < parts) ++bits;
+    const int k_ = adb::launch_radix_pass(reinterpret_cast<const uint32_t *>(d_val),
+                                          reinterpret_cast<const uint32_t *>(d_pos),
+                                          reinterpret_cast<uint32_t *>(d_val_out),
+                                          reinterpret_cast<uint32_t *>(d_pos_out), (uint32_t)n,
+                                          adb::RadixPass{32 - bits, bits, 2}, g.rx_hist, g.rx_totals,
+                                          g.rx_base, g.sm_count, g.stream);
+    if (adb_status s = after_launch("route_pairs", k_)) return s;
+    uint32_t totals[256];
+    CU(cudaMemcpyAsync(totals, g.rx_totals, sizeof(uint32_t) * parts, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    for (int32_t r = 0; r < parts; ++r) h_counts[r] = totals[r];
+    return ADB_OK;
 }
 
 // ---- hash join ------------------------------------------------------------------------------------
@@ -685,7 +721,7 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     while (part_bits < 16 && (nb >> part_bits) > 1024) ++part_bits;
     const uint32_t num_parts = 1u << part_bits;
     // 1. build side: full stable sort on the bijective hash
-    const adb::RadixPass sort4[4] = {{0, 8, true}, {8, 8, true}, {16, 8, true}, {24, 8, true}};
+    const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
     uint32_t *bk = nullptr, *bi = nullptr;
     if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, &bk, &bi, &launches)) return s;
     CU(cudaMallocAsync(&j.build_pos_sorted, (size_t)nb * 4, g.stream));
@@ -696,10 +732,10 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     adb::RadixPass pp_pass[2];
     int npp = 0;
     if (part_bits > 8) {
-        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits - 8, true};
-        pp_pass[npp++] = adb::RadixPass{24, 8, true};
+        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits - 8, 1};
+        pp_pass[npp++] = adb::RadixPass{24, 8, 1};
     } else if (part_bits > 0) {
-        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits, true};
+        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits, 1};
     }
     uint32_t *pk = nullptr, *pj = nullptr;
     if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(pv), np, pp_pass, npp, &pk, &pj, &launches)) return s;

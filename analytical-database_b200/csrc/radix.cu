@@ -23,7 +23,7 @@ constexpr int RX_WARPS = RX_THREADS / kWarp;
 constexpr int RX_BUCKETS = 256;
 
 __device__ __forceinline__ uint32_t rx_digit(uint32_t key, const RadixPass &p) {
-    const uint32_t f = p.hash ? key * 0x9E3779B1u : key ^ 0x80000000u;
+    const uint32_t f = p.hash == 1 ? key * 0x9E3779B1u : p.hash == 2 ? key * 0x85EBCA6Bu : key ^ 0x80000000u;
     return (f >> p.shift) & ((1u << p.bits) - 1u);
 }
 

@@ -142,6 +142,7 @@ class Engine:
         "adb_hash_join_count": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, C.c_int64, _I64P]),
         "adb_nested_loop_join_count": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, C.c_int64, _I64P]),
         "adb_join_emit": (C.c_int32, [_I32P, _I32P]),
+        "adb_route_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int32, _I32P, _I32P, _I64P]),
         "adb_synth_uniform": (C.c_int32, [_I32P, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32]),
     }
 

@@ -219,6 +219,15 @@ ADB_API adb_status adb_nested_loop_join_count(const int32_t *d_v1, const int32_t
                                               int64_t *h_matches);
 ADB_API adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2);
 
+/* ---- multi-GPU join exchange, send side (no reference equivalent: SURVEY.md 8e) ----------
+ * Stable partition of a (value, position) pair list by destination rank = the top
+ * log2(parts) bits of a routing hash of the value; parts is a power of two <= 256 (the
+ * world size).  Pairs bound for rank r land contiguously, in their original order, at
+ * offset sum(h_counts[0..r)) of the outputs -- exactly the send buffer and split sizes of an
+ * all-to-all-v.  Equal keys always meet on the same rank. */
+ADB_API adb_status adb_route_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n, int32_t parts,
+                                   int32_t *d_val_out, int32_t *d_pos_out, int64_t *h_counts);
+
 /* ---- synthetic data (bench / tests): counter-based generator, identical on host ------
  * d_out[i] = lo + mix64(seed, first_row + i) % span, the same sequence
  * analytical-database_b200/synth.py produces with numpy. */

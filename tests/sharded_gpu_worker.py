@@ -1,0 +1,60 @@
+"""torchrun worker for tests/test_gpu_sharded.py: the sharded operator path on real GPUs over
+NCCL, one process per GPU.  Rank 0 saves what the test compares with the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def table(n, seed=42):
+    rng = np.random.default_rng(seed)
+    return {"c1": rng.integers(-n // 2, n // 2, n).astype(np.int32),
+            "c2": rng.integers(2**31 - 10000, 2**31 - 1, n, dtype=np.int64).astype(np.int32),
+            "k": rng.integers(1, n // 8, n).astype(np.int32)}
+
+
+def main():
+    out, n = sys.argv[1], int(sys.argv[2])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import analytical_database_b200 as adb
+    from analytical_database_b200.sharded import EngineOps, ShardedTable, shard_range
+    eng = adb.Engine(local)
+    ops = EngineOps(eng, dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    tab = table(n)
+    b, e = shard_range(n, rank, world)
+    t = ShardedTable(ops, {k: torch.from_numpy(v[b:e].copy()).to(dev) for k, v in tab.items()}, n, dist)
+    res = {"world": world}
+    s = t.select("c1", -n // 20, n // 10)
+    f = t.fetch("c2", s)
+    res["agg"] = t.aggregate(f)
+    res["pos"] = t.gather_global(s.local, s.base).cpu().numpy()
+    res["off"] = (s.offset, s.total, s.local.numel())
+    lows = [-100, 0, n // 4, 7]
+    highs = [100, n // 16, n // 4 + n // 50, 3]
+    ss = t.shared_select("c1", lows, highs)
+    res["ss"] = [t.gather_global(p.local, p.base).cpu().numpy() for p in ss]
+    s1, s2 = t.select("c1", None, n // 4), t.select("c1", -n // 10, -n // 20)
+    v1, v2 = t.fetch("k", s1), t.fetch("k", s2)
+    p1, p2 = s1.local + s1.base, s2.local + s2.base
+    o1, o2 = t.hash_join(v1, p1, v2, p2)
+    res["join"] = np.stack([t.gather_global(o1).cpu().numpy(), t.gather_global(o2).cpu().numpy()], 1)
+    res["join_local"] = o1.numel()
+    res["launches"] = eng.launch_count()
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
