@@ -255,19 +255,20 @@ int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t 
                       uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
                       uint32_t *base, int sm_count, cudaStream_t s);
 uint32_t scan_ctas(uint32_t n, int sm_count);
-int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, unsigned long long *sums,
-                          int64_t *total, int sm_count, cudaStream_t s);
+// in_stride: distance (in uint32) between consecutive inputs (2 reads the .y of a uint2 array)
+int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out, uint32_t n,
+                          unsigned long long *sums, int64_t *total, int sm_count, cudaStream_t s);
 
 // Hash join (hash_join.cu).
-int launch_hj_count(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t *cnt, int sm_count,
-                    cudaStream_t s);
+int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
+                     uint32_t *off, cudaStream_t s);
 size_t hj_smem_bytes();
 uint32_t hj_smem_tuples();
 int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint32_t *pkeys,
                         const uint32_t *prows, const uint32_t *off2, uint32_t num_parts,
                         const unsigned long long *big_off, unsigned char *big_mem,
-                        uint32_t *gs_by_j, uint32_t *cnt_by_j, cudaStream_t s);
-int launch_hj_expand(const uint32_t *gs_by_j, const uint32_t *cnt_by_j, const uint32_t *off_by_j,
+                        uint2 *gc_by_j, cudaStream_t s);
+int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
                      int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);
 

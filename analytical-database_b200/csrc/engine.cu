@@ -4,6 +4,7 @@
 // There is deliberately no CPU path in this file: if no CUDA device can be opened,
 // adb_init() fails and every operator reports ADB_ERR_NOT_INITIALISED.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <vector>
 #include <cstdio>
@@ -54,11 +55,16 @@ struct Engine {
         bool ready = false;
         uint32_t n_probe = 0;
         int64_t matches = 0;
-        uint32_t *gs_by_j = nullptr, *cnt_by_j = nullptr, *off_by_j = nullptr;
-        int32_t *build_pos_sorted = nullptr;
+        uint2 *gc_by_j = nullptr;           // {group start, match count} per probe row
+        uint32_t *off_by_j = nullptr;
+        int32_t *build_pos_sorted = nullptr;   // all three live in the arena
         const int32_t *probe_pos = nullptr;
         bool swapped = false;
     } join;
+    // grow-only scratch arena for the sort / join temporaries: cudaMallocAsync of many
+    // differently sized multi-hundred-MB blocks made the pool re-map memory on every join
+    unsigned char *arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
     int64_t launches = 0;
     int32_t chain_mark_base = -1;       // adb_chain_marks(): slots for the next chain call
 } g;
@@ -202,6 +208,7 @@ adb_status adb_shutdown(void) {
     cudaFree(g.rx_totals);
     cudaFree(g.rx_base);
     cudaFree(g.sc_sums);
+    cudaFree(g.arena);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     cudaEventDestroy(g.ev0);
@@ -594,41 +601,74 @@ static adb_status ensure_radix_scratch() {
     return ADB_OK;
 }
 
-// Runs `npass` stable passes over (keys, payload); payload starts as the row index.  The
-// result lands in (*keys_out, *pay_out); the other ping-pong pair is freed.  With npass == 0
-// the keys are copied and the payload is left NULL (meaning identity).
+// ---- scratch arena ------------------------------------------------------------------------------
+static size_t arena_round(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+// Make room for `bytes` of temporaries and start a fresh bump allocation.  Whatever lived in
+// the arena before (a join waiting for its emit phase) is gone.
+static adb_status arena_reserve(size_t bytes) {
+    g.join = Engine::JoinState{};
+    g.arena_used = 0;
+    if (bytes <= g.arena_cap) return ADB_OK;
+    CU(cudaStreamSynchronize(g.stream));
+    if (g.arena) CU(cudaFree(g.arena));
+    g.arena = nullptr;
+    g.arena_cap = 0;
+    const size_t want = bytes + bytes / 8 + (1 << 20);
+    cudaError_t e = cudaMalloc(&g.arena, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ADB_ERR_NOMEM, "sort/join scratch of %zu bytes: %s", want, cudaGetErrorString(e));
+    }
+    g.arena_cap = want;
+    return ADB_OK;
+}
+static void *arena_take_bytes(size_t bytes) {
+    void *p = g.arena + g.arena_used;
+    g.arena_used += arena_round(bytes);
+    return p;
+}
+#define ARENA_TAKE(T, count) static_cast<T *>(arena_take_bytes((size_t)(count) * sizeof(T)))
+static size_t radix_scratch_bytes(uint32_t n, int npass) {
+    const size_t one = arena_round((size_t)(n ? n : 1) * 4);
+    return npass == 0 ? one : (npass > 1 ? 4 : 2) * one;
+}
+
+// Runs `npass` stable passes over (keys, payload); payload starts as the row index.  Buffers
+// come from the arena (reserve radix_scratch_bytes first).  The last pass writes to
+// (final_k, final_v) when given.  With npass == 0 the keys are copied and the payload is
+// left NULL (meaning identity).
 static adb_status radix_run(const uint32_t *keys_in, uint32_t n, const adb::RadixPass *passes,
-                            int npass, uint32_t **keys_out, uint32_t **pay_out, int *launches) {
+                            int npass, uint32_t *final_k, uint32_t *final_v, uint32_t **keys_out,
+                            uint32_t **pay_out, int *launches) {
     *keys_out = nullptr;
     *pay_out = nullptr;
     if (adb_status s = ensure_radix_scratch()) return s;
-    uint32_t *k[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
-    const size_t bytes = (size_t)(n ? n : 1) * sizeof(uint32_t);
-    for (int i = 0; i < (npass > 1 ? 2 : 1); ++i) {
-        CU(cudaMallocAsync(&k[i], bytes, g.stream));
-        if (npass > 0) CU(cudaMallocAsync(&v[i], bytes, g.stream));
-    }
+    const size_t cnt = n ? n : 1;
     if (npass == 0) {
-        if (n) CU(cudaMemcpyAsync(k[0], keys_in, bytes, cudaMemcpyDeviceToDevice, g.stream));
-        *keys_out = k[0];
+        uint32_t *k0 = final_k ? final_k : ARENA_TAKE(uint32_t, cnt);
+        if (n) CU(cudaMemcpyAsync(k0, keys_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, g.stream));
+        *keys_out = k0;
         return ADB_OK;
+    }
+    uint32_t *k[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
+    for (int i = 0; i < (npass > 1 ? 2 : 1); ++i) {
+        k[i] = ARENA_TAKE(uint32_t, cnt);
+        v[i] = ARENA_TAKE(uint32_t, cnt);
     }
     const uint32_t *src_k = keys_in, *src_v = nullptr;
     int cur = 0;
     for (int p = 0; p < npass; ++p) {
-        *launches += adb::launch_radix_pass(src_k, src_v, k[cur], v[cur], n, passes[p], g.rx_hist,
+        uint32_t *dk = k[cur], *dv = v[cur];
+        if (p == npass - 1 && final_k && final_v) { dk = final_k; dv = final_v; }
+        *launches += adb::launch_radix_pass(src_k, src_v, dk, dv, n, passes[p], g.rx_hist,
                                             g.rx_totals, g.rx_base, g.sm_count, g.stream);
-        src_k = k[cur];
-        src_v = v[cur];
+        src_k = dk;
+        src_v = dv;
         cur ^= 1;
     }
-    const int last = cur ^ 1;
-    *keys_out = k[last];
-    *pay_out = v[last];
-    if (npass > 1) {
-        CU(cudaFreeAsync(k[last ^ 1], g.stream));
-        CU(cudaFreeAsync(v[last ^ 1], g.stream));
-    }
+    *keys_out = const_cast<uint32_t *>(src_k);
+    *pay_out = const_cast<uint32_t *>(src_v);
     return ADB_OK;
 }
 
@@ -639,13 +679,12 @@ adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_values_out
     if (n == 0) return ADB_OK;
     if (!d_col || !d_values_out || !d_positions_out) return fail(ADB_ERR_INVALID, "adb_index_sort: NULL pointer");
     const adb::RadixPass passes[4] = {{0, 8, 0}, {8, 8, 0}, {16, 8, 0}, {24, 8, 0}};
+    if (adb_status s = arena_reserve(radix_scratch_bytes((uint32_t)n, 4))) return s;
     uint32_t *k = nullptr, *v = nullptr;
     int launches = 0;
-    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(d_col), (uint32_t)n, passes, 4, &k, &v, &launches)) return s;
-    CU(cudaMemcpyAsync(d_values_out, k, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, g.stream));
-    CU(cudaMemcpyAsync(d_positions_out, v, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, g.stream));
-    CU(cudaFreeAsync(k, g.stream));
-    CU(cudaFreeAsync(v, g.stream));
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(d_col), (uint32_t)n, passes, 4,
+                                 reinterpret_cast<uint32_t *>(d_values_out),
+                                 reinterpret_cast<uint32_t *>(d_positions_out), &k, &v, &launches)) return s;
     return after_launch("index_sort", launches);
 }
 
@@ -686,14 +725,22 @@ adb_status adb_route_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n
 }
 
 // ---- hash join ------------------------------------------------------------------------------------
-static void join_release() {
-    auto &j = g.join;
-    if (j.gs_by_j) cudaFreeAsync(j.gs_by_j, g.stream);
-    if (j.cnt_by_j) cudaFreeAsync(j.cnt_by_j, g.stream);
-    if (j.off_by_j) cudaFreeAsync(j.off_by_j, g.stream);
-    if (j.build_pos_sorted) cudaFreeAsync(j.build_pos_sorted, g.stream);
-    j = Engine::JoinState{};
-}
+static void join_release() { g.join = Engine::JoinState{}; }      // its buffers are arena memory
+
+// ADB_TRACE=1: synchronise after every stage of a join and print its wall-clock time.
+struct StageTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    StageTrace() : on(getenv("ADB_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(g.stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[adb trace] %-28s %9.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 // build = the side whose rows are grouped (the reference's column_one for hash_join);
 // probe = the side walked in row order.  Output pair k is (build position, probe position).
@@ -705,30 +752,18 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     if (adb_status s = check_len(np64, "adb_join")) return s;
     if ((nb64 > 0 && (!bv || !bp)) || (np64 > 0 && (!pv || !pp)))
         return fail(ADB_ERR_INVALID, "adb_join: NULL device pointer");
-    auto &j = g.join;
-    j.swapped = swapped;
-    j.n_probe = (uint32_t)np64;
-    j.probe_pos = pp;
     const uint32_t nb = (uint32_t)nb64, np = (uint32_t)np64;
     if (nb == 0 || np == 0) {
-        j.matches = 0;
-        j.ready = true;
+        auto &j0 = g.join;
+        j0.swapped = swapped; j0.n_probe = np; j0.probe_pos = pp; j0.matches = 0; j0.ready = true;
         if (h_matches) *h_matches = 0;
         return ADB_OK;
     }
     int launches = 0;
+    StageTrace tr;
     uint32_t part_bits = 0;
     while (part_bits < 16 && (nb >> part_bits) > 1024) ++part_bits;
     const uint32_t num_parts = 1u << part_bits;
-    // 1. build side: full stable sort on the bijective hash
-    const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
-    uint32_t *bk = nullptr, *bi = nullptr;
-    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, &bk, &bi, &launches)) return s;
-    CU(cudaMallocAsync(&j.build_pos_sorted, (size_t)nb * 4, g.stream));
-    launches += adb::launch_fetch(bp, reinterpret_cast<const int32_t *>(bi), nb, nullptr, 0,
-                                  j.build_pos_sorted, g.sm_count, g.stream);
-    CU(cudaFreeAsync(bi, g.stream));
-    // 2. probe side: stable partition on the top hash bits
     adb::RadixPass pp_pass[2];
     int npp = 0;
     if (part_bits > 8) {
@@ -737,27 +772,37 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     } else if (part_bits > 0) {
         pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits, 1};
     }
-    uint32_t *pk = nullptr, *pj = nullptr;
-    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(pv), np, pp_pass, npp, &pk, &pj, &launches)) return s;
-    // 3. partition offsets (num_parts + 1 entries each; the extra zero makes the scan emit the total)
-    uint32_t *cnt1 = nullptr, *cnt2 = nullptr, *off1 = nullptr, *off2 = nullptr;
-    int64_t *tot = nullptr;
     const size_t pbytes = (size_t)(num_parts + 1) * 4;
-    CU(cudaMallocAsync(&cnt1, pbytes, g.stream));
-    CU(cudaMallocAsync(&cnt2, pbytes, g.stream));
-    CU(cudaMallocAsync(&off1, pbytes, g.stream));
-    CU(cudaMallocAsync(&off2, pbytes, g.stream));
-    CU(cudaMallocAsync(&tot, 16, g.stream));
-    CU(cudaMemsetAsync(cnt1, 0, pbytes, g.stream));
-    CU(cudaMemsetAsync(cnt2, 0, pbytes, g.stream));
-    launches += adb::launch_hj_count(bk, nb, part_bits, cnt1, g.sm_count, g.stream);
-    launches += adb::launch_hj_count(pk, np, part_bits, cnt2, g.sm_count, g.stream);
-    launches += adb::launch_exclusive_scan(cnt1, off1, num_parts + 1, g.sc_sums, tot, g.sm_count, g.stream);
-    launches += adb::launch_exclusive_scan(cnt2, off2, num_parts + 1, g.sc_sums, tot + 1, g.sm_count, g.stream);
+    if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)nb * 4) +
+                                     radix_scratch_bytes(np, npp) + arena_round((size_t)np * 8) +
+                                     arena_round((size_t)np * 4) + 2 * arena_round(pbytes) + 4096))
+        return s;
+    auto &j = g.join;
+    j.swapped = swapped;
+    j.n_probe = np;
+    j.probe_pos = pp;
+    // 1. build side: full stable sort on the bijective hash
+    const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
+    uint32_t *bk = nullptr, *bi = nullptr;
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, nullptr, nullptr, &bk, &bi, &launches)) return s;
+    j.build_pos_sorted = ARENA_TAKE(int32_t, nb);
+    launches += adb::launch_fetch(bp, reinterpret_cast<const int32_t *>(bi), nb, nullptr, 0,
+                                  j.build_pos_sorted, g.sm_count, g.stream);
+    tr.lap("build sort + position gather");
+    // 2. probe side: stable partition on the top hash bits
+    uint32_t *pk = nullptr, *pj = nullptr;
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(pv), np, pp_pass, npp, nullptr, nullptr, &pk, &pj, &launches)) return s;
+    tr.lap("probe partition");
+    // 3. partition boundaries (num_parts + 1 entries each)
+    uint32_t *off1 = ARENA_TAKE(uint32_t, num_parts + 1), *off2 = ARENA_TAKE(uint32_t, num_parts + 1);
+    int64_t *tot = ARENA_TAKE(int64_t, 2);
+    launches += adb::launch_hj_bounds(bk, nb, part_bits, num_parts, off1, g.stream);
+    launches += adb::launch_hj_bounds(pk, np, part_bits, num_parts, off2, g.stream);
     // 4. partitions that do not fit the shared-memory table get a table in global memory
     std::vector<uint32_t> h_off1(num_parts + 1);
     CU(cudaMemcpyAsync(h_off1.data(), off1, pbytes, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    tr.lap("partition boundaries");
     unsigned long long *big_off = nullptr;
     unsigned char *big_mem = nullptr;
     {
@@ -779,19 +824,18 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
         }
     }
     // 5. per-partition build + probe
-    CU(cudaMallocAsync(&j.gs_by_j, (size_t)np * 4, g.stream));
-    CU(cudaMallocAsync(&j.cnt_by_j, (size_t)np * 4, g.stream));
-    CU(cudaMallocAsync(&j.off_by_j, (size_t)np * 4, g.stream));
-    CU(cudaMemsetAsync(j.cnt_by_j, 0, (size_t)np * 4, g.stream));
+    j.gc_by_j = ARENA_TAKE(uint2, np);
+    j.off_by_j = ARENA_TAKE(uint32_t, np);
     launches += adb::launch_hj_partition(bk, off1, pk, pj, off2, num_parts, big_off, big_mem,
-                                         j.gs_by_j, j.cnt_by_j, g.stream);
+                                         j.gc_by_j, g.stream);
+    tr.lap("per-partition build + probe");
     // 6. output offsets in probe-row order
-    launches += adb::launch_exclusive_scan(j.cnt_by_j, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
+    launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
     CU(cudaMemcpyAsync(&j.matches, tot, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
-    for (void *q : {(void *)bk, (void *)pk, (void *)pj, (void *)cnt1, (void *)cnt2, (void *)off1,
-                    (void *)off2, (void *)tot, (void *)big_off, (void *)big_mem})
-        if (q) CU(cudaFreeAsync(q, g.stream));
+    tr.lap("output offsets");
+    if (big_off) CU(cudaFreeAsync(big_off, g.stream));
+    if (big_mem) CU(cudaFreeAsync(big_mem, g.stream));
     if (adb_status s = after_launch("join_count", launches)) return s;
     if (j.matches >= (int64_t)1 << 31) {
         const long long m = j.matches;
@@ -823,7 +867,7 @@ adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2) {
     if (j.matches > 0) {
         if (!d_out1 || !d_out2) return fail(ADB_ERR_INVALID, "adb_join_emit: NULL output");
         int32_t *ob = j.swapped ? d_out2 : d_out1, *op = j.swapped ? d_out1 : d_out2;
-        const int k_ = adb::launch_hj_expand(j.gs_by_j, j.cnt_by_j, j.off_by_j, j.n_probe,
+        const int k_ = adb::launch_hj_expand(j.gc_by_j, j.off_by_j, j.n_probe,
                                              j.build_pos_sorted, j.probe_pos, ob, op, g.sm_count, g.stream);
         rc = after_launch("join_expand", k_);
     }

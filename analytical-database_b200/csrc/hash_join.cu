@@ -13,7 +13,8 @@
 //      equal keys (insertion order kept inside a group: the sort is stable) and orders
 //      the groups by partition id = top bits of h;
 //   2. probe side: stable radix partition on the same top bits, payload = probe row j;
-//   3. one CTA per partition: group leaders insert (key -> group start) into an open
+//   3. partition boundaries by binary search (both sides are ordered by partition id); one
+//      CTA per partition: group leaders insert (key -> group start) into an open
 //      addressing table in shared memory (64-bit CAS, no sentinel key needed), group
 //      tails store the group end, then every probe row of the partition looks its key up
 //      and scatters {group start, match count} to slot j;
@@ -35,12 +36,20 @@ __device__ __forceinline__ uint32_t hj_pid(uint32_t key, uint32_t part_bits) {
     return part_bits ? (key * kHashMul) >> (32 - part_bits) : 0u;
 }
 
-// ---- partition sizes ------------------------------------------------------------------------
-__global__ void hj_count_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t part_bits,
-                                uint32_t *__restrict__ cnt) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&cnt[hj_pid(keys[i], part_bits)], 1u);
+// ---- partition boundaries -----------------------------------------------------------------
+// Both inputs arrive ordered by partition id (the build side is sorted on the whole hash, the
+// probe side stably partitioned on its top bits), so partition p starts at the first row
+// whose id is >= p: one binary search per partition instead of one global atomic per row.
+__global__ void hj_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t part_bits,
+                                 uint32_t num_parts, uint32_t *__restrict__ off) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > num_parts) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (hj_pid(keys[mid], part_bits) < p) lo = mid + 1; else hi = mid;
+    }
+    off[p] = lo;                                  // off[num_parts] == n
 }
 
 // ---- per-partition build + probe ----------------------------------------------------------------
@@ -84,8 +93,7 @@ hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
                     const uint32_t *__restrict__ prows /* nullptr: identity */,
                     const uint32_t *__restrict__ off2,
                     const unsigned long long *__restrict__ big_off /* per partition, ~0 = smem */,
-                    unsigned char *__restrict__ big_mem, uint32_t *__restrict__ gs_by_j,
-                    uint32_t *__restrict__ cnt_by_j) {
+                    unsigned char *__restrict__ big_mem, uint2 *__restrict__ gc_by_j) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t p = blockIdx.x;
     const uint32_t b0 = off1[p], b1 = off1[p + 1], q0 = off2[p], q1 = off2[p + 1];
@@ -94,8 +102,7 @@ hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
     if (nb == 0) {
         for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
             const uint32_t j = prows ? prows[u] : u;
-            cnt_by_j[j] = 0;
-            gs_by_j[j] = 0;
+            gc_by_j[j] = make_uint2(0u, 0u);
         }
         return;
     }
@@ -130,14 +137,14 @@ hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
     for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
         const uint32_t j = prows ? prows[u] : u;
         const int s = hj_find(t, pkeys[u]);
-        gs_by_j[j] = s >= 0 ? t.gs[s] : 0u;
-        cnt_by_j[j] = s >= 0 ? t.ge[s] - t.gs[s] : 0u;
+        // {group start, match count} leaves as ONE 8-byte scattered store per probe row
+        gc_by_j[j] = s >= 0 ? make_uint2(t.gs[s], t.ge[s] - t.gs[s]) : make_uint2(0u, 0u);
     }
 }
 
 // ---- expand ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_expand_kernel(const uint32_t *__restrict__ gs_by_j, const uint32_t *__restrict__ cnt_by_j,
+hj_expand_kernel(const uint2 *__restrict__ gc_by_j,
                  const uint32_t *__restrict__ off_by_j, uint32_t n_probe,
                  const int32_t *__restrict__ build_pos_sorted, const int32_t *__restrict__ probe_pos,
                  int32_t *__restrict__ out_build, int32_t *__restrict__ out_probe) {
@@ -149,8 +156,9 @@ hj_expand_kernel(const uint32_t *__restrict__ gs_by_j, const uint32_t *__restric
         uint32_t cnt = 0, gs = 0, off = 0;
         int32_t pp = 0;
         if (j < n_probe) {
-            cnt = cnt_by_j[j];
-            if (cnt) { gs = gs_by_j[j]; off = off_by_j[j]; pp = probe_pos[j]; }
+            const uint2 gc = gc_by_j[j];
+            cnt = gc.y;
+            if (cnt) { gs = gc.x; off = off_by_j[j]; pp = probe_pos[j]; }
         }
         if (cnt && cnt <= 8) {
             for (uint32_t r = 0; r < cnt; ++r) {
@@ -174,12 +182,9 @@ hj_expand_kernel(const uint32_t *__restrict__ gs_by_j, const uint32_t *__restric
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
-int launch_hj_count(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t *cnt, int sm_count,
-                    cudaStream_t s) {
-    if (n == 0) return 0;
-    uint32_t blocks = (n + 1023) / 1024;
-    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
-    hj_count_kernel<<<blocks, 256, 0, s>>>(keys, n, part_bits, cnt);
+int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
+                     uint32_t *off, cudaStream_t s) {
+    hj_bounds_kernel<<<(num_parts + 1 + 255) / 256, 256, 0, s>>>(keys, n, part_bits, num_parts, off);
     return 1;
 }
 
@@ -189,7 +194,7 @@ uint32_t hj_smem_tuples() { return HJ_SMEM_TUPLES; }
 int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint32_t *pkeys,
                         const uint32_t *prows, const uint32_t *off2, uint32_t num_parts,
                         const unsigned long long *big_off, unsigned char *big_mem,
-                        uint32_t *gs_by_j, uint32_t *cnt_by_j, cudaStream_t s) {
+                        uint2 *gc_by_j, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(hj_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -197,17 +202,17 @@ int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint3
         attr_set = true;
     }
     hj_partition_kernel<<<num_parts, HJ_THREADS, hj_smem_bytes(), s>>>(
-        bkeys, off1, pkeys, prows, off2, big_off, big_mem, gs_by_j, cnt_by_j);
+        bkeys, off1, pkeys, prows, off2, big_off, big_mem, gc_by_j);
     return 1;
 }
 
-int launch_hj_expand(const uint32_t *gs_by_j, const uint32_t *cnt_by_j, const uint32_t *off_by_j,
+int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
                      int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s) {
     if (n_probe == 0) return 0;
     uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
     if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
-    hj_expand_kernel<<<blocks, HJ_THREADS, 0, s>>>(gs_by_j, cnt_by_j, off_by_j, n_probe,
+    hj_expand_kernel<<<blocks, HJ_THREADS, 0, s>>>(gc_by_j, off_by_j, n_probe,
                                                    build_pos_sorted, probe_pos, out_build, out_probe);
     return 1;
 }

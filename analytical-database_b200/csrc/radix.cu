@@ -77,50 +77,99 @@ __global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals, uint3
     base[threadIdx.x] = wexcl + incl - x;
 }
 
+// Stable scatter, one 4096-row tile at a time.  Warp w of the CTA owns the contiguous rows
+// tile + w*512 .. +512 (row = ... + i*32 + lane), so ranking its keys round by round with
+// match_any gives every key its rank among the warp's equal digits in row order.  Per-digit
+// prefixes over the eight warps and over the 256 digits turn that into a slot in the
+// tile-sorted order; keys and payloads are parked there in shared memory and written out
+// slot by slot, so each digit's run leaves as one contiguous (coalesced) piece instead of
+// thirty-two 4-byte scatters per warp.
+constexpr int RX_KPT = 16;
+constexpr int RX_TILE = RX_THREADS * RX_KPT;             // 4096 rows
+
 __global__ void __launch_bounds__(RX_THREADS)
 rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
                   uint32_t rows_per_cta, RadixPass p, const uint32_t *__restrict__ hist,
                   const uint32_t *__restrict__ base, uint32_t *__restrict__ keys_out,
                   uint32_t *__restrict__ pay_out) {
-    __shared__ uint32_t s_off[RX_BUCKETS];                 // next free slot of every bucket
-    __shared__ uint32_t s_wcnt[RX_WARPS][RX_BUCKETS];      // per-warp digit counts of the step
+    __shared__ uint32_t s_key[RX_TILE];
+    __shared__ uint32_t s_pay[RX_TILE];
+    __shared__ uint32_t s_wcnt[RX_WARPS][RX_BUCKETS];      // per-warp digit counts -> prefix over warps
+    __shared__ uint32_t s_off[RX_BUCKETS];                 // next free global slot of every digit
+    __shared__ uint32_t s_tbase[RX_BUCKETS];               // first tile slot of every digit
+    __shared__ uint32_t s_gofs[RX_BUCKETS];                // global address = s_gofs[d] + tile slot
+    __shared__ uint32_t s_ws[RX_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     s_off[threadIdx.x] = base[threadIdx.x] + hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
     const uint32_t begin = blockIdx.x * rows_per_cta;
     const uint32_t end = min(n, begin + rows_per_cta);
     const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t step = begin; step < end; step += RX_THREADS) {
+    for (uint32_t tile = begin; tile < end; tile += RX_TILE) {
 #pragma unroll
         for (int w = 0; w < RX_WARPS; ++w) s_wcnt[w][threadIdx.x] = 0;
         __syncthreads();
-        const uint32_t i = step + threadIdx.x;
-        const bool live = i < end;
-        uint32_t key = 0, val = 0, d = 0, rank = 0;
-        if (live) {
-            key = keys[i];
-            val = pay ? pay[i] : i;
-            d = rx_digit(key, p);
-        }
-        const uint32_t active = __ballot_sync(kFull, live);
-        if (live) {
-            const uint32_t peers = __match_any_sync(active, d);
-            rank = __popc(peers & lt);
-            if (rank == 0) s_wcnt[warp][d] = __popc(peers);
-        }
-        __syncthreads();
-        if (live) {
-            uint32_t before = 0;
-            for (uint32_t w = 0; w < warp; ++w) before += s_wcnt[w][d];
-            const uint32_t dst = s_off[d] + before + rank;
-            keys_out[dst] = key;
-            pay_out[dst] = val;
-        }
-        __syncthreads();
-        {
-            uint32_t tot = 0;
+        uint32_t key[RX_KPT];
+        uint32_t dr[RX_KPT];                               // digit | rank-in-warp << 8, ~0 = past the end
+        const uint32_t wrow = tile + warp * (kWarp * RX_KPT) + lane;
+        uint32_t *cnt = s_wcnt[warp];
 #pragma unroll
-            for (int w = 0; w < RX_WARPS; ++w) tot += s_wcnt[w][threadIdx.x];
-            s_off[threadIdx.x] += tot;
+        for (int i = 0; i < RX_KPT; ++i) {
+            const uint32_t row = wrow + i * kWarp;
+            const bool live = row < end;
+            key[i] = live ? keys[row] : 0u;
+            dr[i] = 0xFFFFFFFFu;
+            const uint32_t active = __ballot_sync(kFull, live);
+            uint32_t d = 0, peers = 0, before = 0;
+            if (live) {
+                d = rx_digit(key[i], p);
+                peers = __match_any_sync(active, d);
+                before = cnt[d];
+            }
+            __syncwarp();
+            if (live) {
+                const uint32_t r = __popc(peers & lt);
+                if (r == 0) cnt[d] = before + __popc(peers);
+                dr[i] = d | ((before + r) << 8);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // digit `threadIdx.x`: exclusive prefix over the warps, then over the digits
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < RX_WARPS; ++w) {
+            const uint32_t c = s_wcnt[w][threadIdx.x];
+            s_wcnt[w][threadIdx.x] = tot;
+            tot += c;
+        }
+        const uint32_t incl = warp_incl_scan(tot, lane);
+        if (lane == 31) s_ws[warp] = incl;
+        __syncthreads();
+        uint32_t wexcl = 0;
+#pragma unroll
+        for (int w = 0; w < RX_WARPS; ++w) wexcl += (uint32_t)w < warp ? s_ws[w] : 0u;
+        const uint32_t tbase = wexcl + incl - tot;
+        s_tbase[threadIdx.x] = tbase;
+        s_gofs[threadIdx.x] = s_off[threadIdx.x] - tbase;   // modular: slot >= tbase for this digit
+        s_off[threadIdx.x] += tot;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RX_KPT; ++i) {
+            if (dr[i] != 0xFFFFFFFFu) {
+                const uint32_t d = dr[i] & 0xFFu, r = dr[i] >> 8;
+                const uint32_t slot = s_tbase[d] + s_wcnt[warp][d] + r;
+                const uint32_t row = wrow + i * kWarp;
+                s_key[slot] = key[i];
+                s_pay[slot] = pay ? pay[row] : row;
+            }
+        }
+        __syncthreads();
+        const uint32_t count = min((uint32_t)RX_TILE, end - tile);
+        for (uint32_t slot = threadIdx.x; slot < count; slot += RX_THREADS) {
+            const uint32_t k = s_key[slot];
+            const uint32_t dst = s_gofs[rx_digit(k, p)] + slot;
+            keys_out[dst] = k;
+            pay_out[dst] = s_pay[slot];
         }
         __syncthreads();
     }
@@ -129,7 +178,7 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
 RadixGeom radix_geom(uint32_t n, int sm_count) {
     RadixGeom g{};
     uint32_t ctas = (n + 4095) / 4096;
-    const uint32_t cap = (uint32_t)sm_count * 6u;
+    const uint32_t cap = (uint32_t)sm_count * 4u;          // 4 resident CTAs per SM (64 regs x 256 threads)
     if (ctas > cap) ctas = cap;
     if (ctas == 0) ctas = 1;
     uint32_t rows = (n + ctas - 1) / ctas;
@@ -159,12 +208,12 @@ int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t 
 constexpr int SC_THREADS = 1024;
 
 __global__ void __launch_bounds__(SC_THREADS)
-sc_chunk_sum_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t rows_per_cta,
-                    unsigned long long *__restrict__ sums) {
+sc_chunk_sum_kernel(const uint32_t *__restrict__ in, uint32_t in_stride, uint32_t n,
+                    uint32_t rows_per_cta, unsigned long long *__restrict__ sums) {
     __shared__ unsigned long long s_w[32];
     const uint32_t begin = blockIdx.x * rows_per_cta, end = min(n, begin + rows_per_cta);
     unsigned long long acc = 0;
-    for (uint32_t i = begin + threadIdx.x; i < end; i += SC_THREADS) acc += in[i];
+    for (uint32_t i = begin + threadIdx.x; i < end; i += SC_THREADS) acc += in[(size_t)i * in_stride];
     acc = (unsigned long long)warp_sum_i64((int64_t)acc);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -176,9 +225,9 @@ sc_chunk_sum_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t rows_p
 }
 
 __global__ void __launch_bounds__(SC_THREADS)
-sc_chunk_scan_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t rows_per_cta,
-                     const unsigned long long *__restrict__ sums, uint32_t *__restrict__ out,
-                     int64_t *__restrict__ total) {
+sc_chunk_scan_kernel(const uint32_t *__restrict__ in, uint32_t in_stride, uint32_t n,
+                     uint32_t rows_per_cta, const unsigned long long *__restrict__ sums,
+                     uint32_t *__restrict__ out, int64_t *__restrict__ total) {
     __shared__ unsigned long long s_w[32];
     __shared__ uint32_t s_warp[32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -194,7 +243,7 @@ sc_chunk_scan_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t rows_
     const uint32_t begin = blockIdx.x * rows_per_cta, end = min(n, begin + rows_per_cta);
     for (uint32_t b = begin; b < end; b += SC_THREADS) {
         const uint32_t i = b + threadIdx.x;
-        const uint32_t x = i < end ? in[i] : 0u;
+        const uint32_t x = i < end ? in[(size_t)i * in_stride] : 0u;
         const uint32_t incl = warp_incl_scan(x, lane);
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
@@ -215,8 +264,8 @@ uint32_t scan_ctas(uint32_t n, int sm_count) {
     return ctas ? ctas : 1;
 }
 
-int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, unsigned long long *sums,
-                          int64_t *total, int sm_count, cudaStream_t s) {
+int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out, uint32_t n,
+                          unsigned long long *sums, int64_t *total, int sm_count, cudaStream_t s) {
     if (n == 0) {
         cudaMemsetAsync(total, 0, sizeof(int64_t), s);
         return 0;
@@ -225,8 +274,8 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, unsigne
     uint32_t rows = (n + ctas - 1) / ctas;
     rows = (rows + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
     const uint32_t grid = (n + rows - 1) / rows;
-    sc_chunk_sum_kernel<<<grid, SC_THREADS, 0, s>>>(in, n, rows, sums);
-    sc_chunk_scan_kernel<<<grid, SC_THREADS, 0, s>>>(in, n, rows, sums, out, total);
+    sc_chunk_sum_kernel<<<grid, SC_THREADS, 0, s>>>(in, in_stride, n, rows, sums);
+    sc_chunk_scan_kernel<<<grid, SC_THREADS, 0, s>>>(in, in_stride, n, rows, sums, out, total);
     return 2;
 }
 

@@ -62,7 +62,7 @@ def bench_index(eng, scale):
     vals, poss = eng.index_sort(key, n)
     eng.sync()
     build_s = time.perf_counter() - t0
-    med_b, _ = timed(eng, lambda: [b.free() for b in eng.index_sort(key, n)], reps=2, warm=0)
+    med_b, _ = timed(eng, lambda: [b.free() for b in eng.index_sort(key, n)], reps=2, warm=1)
     ix = eng.index_create(vals, poss, n, True)
     out = {"rows": n, "index_sort_ms": med_b, "first_build_s": build_s,
            "sort_mkeys_per_s": n / (med_b * 1e-3) / 1e6}
@@ -91,14 +91,22 @@ def bench_index(eng, scale):
     return out
 
 
-def bench_join(eng, scale):
+def bench_sort_only(eng, scale):
+    n = int(500_000_000 * scale)
+    key = eng.synth_uniform(n, 7, 0, 0, 1 << 31 - 1)
+    med, best = timed(eng, lambda: [b.free() for b in eng.index_sort(key, n)], reps=2, warm=1)
+    key.free()
+    return {"rows": n, "index_sort_ms": med, "sort_mkeys_per_s": n / (med * 1e-3) / 1e6}
+
+
+def bench_join(eng, scale, cases=((0.8, 0.15), (0.15, 0.15), (1.0, 1.0))):
     n = int(100_000_000 * scale)
     out = {}
     k1 = eng.synth_uniform(n, 11, 0, 1, n)
     k2 = eng.synth_uniform(n, 12, 0, 1, n)
     f1 = eng.synth_uniform(n, 13, 0, 0, 1000)
     f2 = eng.synth_uniform(n, 14, 0, 0, 1000)
-    for s1, s2 in ((0.8, 0.15), (0.15, 0.15), (1.0, 1.0)):
+    for s1, s2 in cases:
         p1, c1 = eng.select_exact(f1, n, None, int(1000 * s1))
         p2, c2 = eng.select_exact(f2, n, None, int(1000 * s2))
         v1 = eng.fetch(k1, p1, c1)
@@ -132,6 +140,10 @@ def main():
         res["shared_scan"] = bench_shared(eng, a.scale)
     if a.what in ("index", "all"):
         res["index"] = bench_index(eng, a.scale)
+    if a.what == "sort":
+        res["sort"] = bench_sort_only(eng, a.scale)
+    if a.what == "join11":
+        res["join"] = bench_join(eng, a.scale, ((1.0, 1.0),))
     if a.what in ("join", "all"):
         res["join"] = bench_join(eng, a.scale)
     print(json.dumps(res, indent=1))
