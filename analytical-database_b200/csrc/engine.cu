@@ -50,6 +50,7 @@ struct Engine {
     bool ss_ready = false;
     // radix / join scratch
     uint32_t *rx_hist = nullptr, *rx_totals = nullptr, *rx_base = nullptr;
+    size_t rx_hist_elems = 0;
     unsigned long long *sc_sums = nullptr;
     struct JoinState {
         bool ready = false;
@@ -592,12 +593,22 @@ adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *low
 }
 
 // ---- radix sort / partition helpers ---------------------------------------------------------
-static adb_status ensure_radix_scratch() {
-    if (g.rx_hist) return ADB_OK;
-    CU(cudaMalloc(&g.rx_hist, sizeof(uint32_t) * 256 * (size_t)(g.sm_count * 6 + 8)));
-    CU(cudaMalloc(&g.rx_totals, sizeof(uint32_t) * 256));
-    CU(cudaMalloc(&g.rx_base, sizeof(uint32_t) * 256));
-    CU(cudaMalloc(&g.sc_sums, sizeof(unsigned long long) * (size_t)(g.sm_count * 2 + 8)));
+static adb_status ensure_radix_scratch(uint32_t n) {
+    if (!g.rx_totals) {
+        CU(cudaMalloc(&g.rx_totals, sizeof(uint32_t) * 256));
+        CU(cudaMalloc(&g.rx_base, sizeof(uint32_t) * 256));
+        CU(cudaMalloc(&g.sc_sums, sizeof(unsigned long long) * (size_t)(g.sm_count * 2 + 8)));
+    }
+    const size_t need = 256 * (size_t)adb::radix_geom(n, g.sm_count).ctas;      // [bucket][tile]
+    if (need <= g.rx_hist_elems) return ADB_OK;
+    CU(cudaStreamSynchronize(g.stream));
+    if (g.rx_hist) CU(cudaFree(g.rx_hist));
+    g.rx_hist = nullptr;
+    g.rx_hist_elems = 0;
+    const size_t want = need + need / 4 + 256 * 64;
+    cudaError_t e = cudaMalloc(&g.rx_hist, want * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "radix histogram: %s", cudaGetErrorString(e)); }
+    g.rx_hist_elems = want;
     return ADB_OK;
 }
 
@@ -643,7 +654,7 @@ static adb_status radix_run(const uint32_t *keys_in, uint32_t n, const adb::Radi
                             uint32_t **pay_out, int *launches) {
     *keys_out = nullptr;
     *pay_out = nullptr;
-    if (adb_status s = ensure_radix_scratch()) return s;
+    if (adb_status s = ensure_radix_scratch(n)) return s;
     const size_t cnt = n ? n : 1;
     if (npass == 0) {
         uint32_t *k0 = final_k ? final_k : ARENA_TAKE(uint32_t, cnt);
@@ -707,7 +718,7 @@ adb_status adb_route_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n
         h_counts[0] = n;
         return ADB_OK;
     }
-    if (adb_status s = ensure_radix_scratch()) return s;
+    if (adb_status s = ensure_radix_scratch((uint32_t)n)) return s;
     int bits = 0;
     while ((1 << bits) < parts) ++bits;
     const int k_ = adb::launch_radix_pass(reinterpret_cast<const uint32_t *>(d_val),

@@ -112,19 +112,29 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
         uint32_t dr[RX_KPT];                               // digit | rank-in-warp << 8, ~0 = past the end
         const uint32_t wrow = tile + warp * (kWarp * RX_KPT) + lane;
         uint32_t *cnt = s_wcnt[warp];
+        // all sixteen loads are issued before the first rank round needs a key
+#pragma unroll
+        for (int i = 0; i < RX_KPT; ++i) {
+            const uint32_t row = wrow + i * kWarp;
+            key[i] = row < end ? ld_stream(reinterpret_cast<const int32_t *>(keys) + row) : 0u;
+        }
 #pragma unroll
         for (int i = 0; i < RX_KPT; ++i) {
             const uint32_t row = wrow + i * kWarp;
             const bool live = row < end;
-            key[i] = live ? keys[row] : 0u;
             dr[i] = 0xFFFFFFFFu;
             const uint32_t active = __ballot_sync(kFull, live);
             uint32_t d = 0, peers = 0, before = 0;
-            if (live) {
-                d = rx_digit(key[i], p);
-                peers = __match_any_sync(active, d);
-                before = cnt[d];
+            if (live) d = rx_digit(key[i], p);
+            // lanes holding the same digit, one ballot per digit bit: MATCH.ANY runs on the
+            // XU pipe and saturated it at 16 rounds per tile (ncu r01f: xu 177 % of peak)
+            peers = active;
+            for (int b = 0; b < p.bits; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t vote = __ballot_sync(kFull, bit);
+                peers &= bit ? vote : ~vote;
             }
+            if (live) before = cnt[d];
             __syncwarp();
             if (live) {
                 const uint32_t r = __popc(peers & lt);
@@ -175,22 +185,20 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
     }
 }
 
+// One CTA per 4096-row tile, launched in row order: the CTAs resident at any moment work on
+// neighbouring tiles, so each of the 256 output streams is appended to by many CTAs at
+// neighbouring addresses (DRAM-page and L2 friendly) instead of every CTA opening its own 256
+// far-apart streams.  The price is a [256][tiles] histogram (1 KB per 32 KB of input).
 RadixGeom radix_geom(uint32_t n, int sm_count) {
+    (void)sm_count;
     RadixGeom g{};
-    uint32_t ctas = (n + 4095) / 4096;
-    const uint32_t cap = (uint32_t)sm_count * 4u;          // 4 resident CTAs per SM (64 regs x 256 threads)
-    if (ctas > cap) ctas = cap;
-    if (ctas == 0) ctas = 1;
-    uint32_t rows = (n + ctas - 1) / ctas;
-    rows = (rows + RX_THREADS - 1) / RX_THREADS * RX_THREADS;
-    if (rows == 0) rows = RX_THREADS;
-    g.rows_per_cta = rows;
-    g.ctas = (n + rows - 1) / rows;
+    g.rows_per_cta = RX_TILE;
+    g.ctas = (n + RX_TILE - 1) / RX_TILE;
     if (g.ctas == 0) g.ctas = 1;
     return g;
 }
 
-// scratch: hist = 256 * ctas uint32, totals = 256, base = 256
+// scratch: hist = 256 * radix_geom(n).ctas uint32, totals = 256, base = 256
 int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
                       uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
                       uint32_t *base, int sm_count, cudaStream_t s) {
