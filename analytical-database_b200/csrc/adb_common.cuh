@@ -235,11 +235,11 @@ struct SharedScanGeom {
 };
 SharedScanGeom shared_scan_geom(uint32_t n, int sm_count);
 int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan &plan,
-                           const SharedScanGeom &g, uint16_t *cls, uint32_t *counts,
-                           int64_t *totals, cudaStream_t s);
-int launch_shared_emit(const uint16_t *cls, const SharedScanPlan &plan, const SharedScanGeom &g,
-                       const uint32_t *offsets, int32_t *const *outs, int64_t capacity,
-                       cudaStream_t s);
+                           const SharedScanGeom &g, uint32_t *hitlist, uint32_t *chunk_hits,
+                           uint32_t *counts, int64_t *totals, cudaStream_t s);
+int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
+                       const SharedScanPlan &plan, const SharedScanGeom &g, const uint32_t *offsets,
+                       int32_t *const *outs, int64_t capacity, cudaStream_t s);
 
 // Stable radix partition passes + generic exclusive scan (radix.cu).
 struct RadixPass {

@@ -40,8 +40,9 @@ struct Engine {
     int64_t *scratch_count = nullptr;   // device int64 for callers that pass no d_count
     // batched shared scan state (count phase -> emit phase)
     unsigned char *ss_plan_mem = nullptr;   // bounds | cov_off | cov_q
-    uint16_t *ss_cls = nullptr;
-    size_t ss_cls_rows = 0;
+    uint32_t *ss_hits = nullptr;            // per-chunk hit lists, chunk_rows entries each
+    size_t ss_hits_rows = 0;
+    uint32_t *ss_chunk_hits = nullptr;
     uint32_t *ss_counts = nullptr;
     int64_t *ss_totals = nullptr;
     int32_t **ss_outs = nullptr;
@@ -201,7 +202,8 @@ adb_status adb_shutdown(void) {
     cudaFree(g.idx_bounds);
     cudaFree(g.scratch_count);
     cudaFree(g.ss_plan_mem);
-    cudaFree(g.ss_cls);
+    cudaFree(g.ss_hits);
+    cudaFree(g.ss_chunk_hits);
     cudaFree(g.ss_counts);
     cudaFree(g.ss_totals);
     cudaFree(g.ss_outs);
@@ -514,6 +516,7 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
         CU(cudaMalloc(&g.ss_counts, sizeof(uint32_t) * ADB_MAX_BATCH * kSsMaxChunks));
         CU(cudaMalloc(&g.ss_totals, sizeof(int64_t) * ADB_MAX_BATCH));
         CU(cudaMalloc(&g.ss_outs, sizeof(int32_t *) * ADB_MAX_BATCH));
+        CU(cudaMalloc(&g.ss_chunk_hits, sizeof(uint32_t) * kSsMaxChunks));
     }
     // ---- plan: elementary intervals and their covering queries ------------------------------
     int32_t bounds[2 * ADB_MAX_BATCH];
@@ -551,14 +554,14 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
     g.ss_geom = adb::shared_scan_geom((uint32_t)n, g.sm_count);
     if (g.ss_geom.num_chunks > kSsMaxChunks) return fail(ADB_ERR_INVALID, "shared scan: chunk table overflow");
     const size_t rows = (size_t)g.ss_geom.num_chunks * g.ss_geom.chunk_rows;
-    if (rows > g.ss_cls_rows) {
-        if (g.ss_cls) { CU(cudaFree(g.ss_cls)); g.ss_cls = nullptr; g.ss_cls_rows = 0; }
-        cudaError_t e = cudaMalloc(&g.ss_cls, (rows + rows / 8 + 4096) * sizeof(uint16_t));
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "shared scan interval-id scratch: %s", cudaGetErrorString(e)); }
-        g.ss_cls_rows = rows + rows / 8 + 4096;
+    if (rows > g.ss_hits_rows) {
+        if (g.ss_hits) { CU(cudaStreamSynchronize(g.stream)); CU(cudaFree(g.ss_hits)); g.ss_hits = nullptr; g.ss_hits_rows = 0; }
+        cudaError_t e = cudaMalloc(&g.ss_hits, (rows + rows / 8 + 4096) * sizeof(uint32_t));
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "shared scan hit-list scratch: %s", cudaGetErrorString(e)); }
+        g.ss_hits_rows = rows + rows / 8 + 4096;
     }
-    const int k_ = adb::launch_shared_classify(d_col, (uint32_t)n, g.ss_plan, g.ss_geom, g.ss_cls,
-                                               g.ss_counts, g.ss_totals, g.stream);
+    const int k_ = adb::launch_shared_classify(d_col, (uint32_t)n, g.ss_plan, g.ss_geom, g.ss_hits,
+                                               g.ss_chunk_hits, g.ss_counts, g.ss_totals, g.stream);
     if (adb_status s = after_launch("shared_classify", k_)) return s;
     if (h_counts) {
         CU(cudaMemcpyAsync(h_counts, g.ss_totals, sizeof(int64_t) * q_count, cudaMemcpyDeviceToHost, g.stream));
@@ -577,7 +580,8 @@ adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity) 
     CU(cudaMemcpyAsync(g.ss_outs, d_out_ptrs, sizeof(int32_t *) * g.ss_plan.q_count,
                        cudaMemcpyHostToDevice, g.stream));
     CU(cudaStreamSynchronize(g.stream));
-    const int k_ = adb::launch_shared_emit(g.ss_cls, g.ss_plan, g.ss_geom, g.ss_counts, g.ss_outs, capacity, g.stream);
+    const int k_ = adb::launch_shared_emit(g.ss_hits, g.ss_chunk_hits, g.ss_plan, g.ss_geom, g.ss_counts,
+                                           g.ss_outs, capacity, g.stream);
     return after_launch("shared_emit", k_);
 }
 

@@ -8,15 +8,16 @@
 //   host       the <= 2Q distinct bounds cut the value domain into elementary intervals;
 //              every interval knows the (few) queries that cover it (a CSR list, query
 //              ids ascending);
-//   classify   one streaming pass: each row binary-searches its interval in shared
-//              memory (log2(2Q) steps instead of Q range tests), stores the interval id
-//              (2 B/row) and bumps per-warp-chunk, per-query hit counters;
+//   classify   one streaming pass: a 1024-entry shared-memory table dismisses rows no query
+//              wants with one read; candidate rows are compacted per warp and resolved
+//              densely (exact interval, per-warp-chunk per-query counters, one packed
+//              {interval, row} entry in the chunk's hit list);
 //   offsets    one CTA per query scans its row of the [query][chunk] count matrix;
-//   emit       each warp walks its contiguous row range 32 rows at a time; in every round
-//              the smallest query id still pending among the 32 rows is served: the rows
-//              covering it are ranked in lane (= row) order and appended at that query's
-//              running offset.  Every list therefore comes out ascending, as the
-//              reference's memcpy-concatenated thread slices do (query.c:563-574).
+//   emit       each warp walks its chunk's hit list and queues (query, row) pairs in row
+//              order; 32 pairs at a time are ranked per query (one ballot per
+//              query-id bit) and appended at that query's running offset.  Every list
+//              therefore comes out ascending, as the reference's memcpy-concatenated
+//              thread slices do (query.c:563-574).
 //
 // has_low / has_high are ignored and all queries share one column, exactly as
 // query.c:474 and server.c:376 do.
@@ -29,73 +30,179 @@ constexpr int SS_WARPS = SS_THREADS / kWarp;
 constexpr int SS_WTILE = 512;                     // rows per warp-tile (same layout as select)
 constexpr int SS_QMAX = ADB_MAX_BATCH;            // 150
 constexpr int SS_BMAX = 2 * SS_QMAX;              // <= 300 distinct bounds
+constexpr int SS_LUT = 1024;                      // value -> first candidate interval
+constexpr int SS_QUEUE = 256;                     // (query, row) pairs parked per warp (power of two)
 
-// number of bounds <= v  (interval id in [0, m])
-__device__ __forceinline__ uint32_t interval_of(const int32_t *__restrict__ s_bounds, uint32_t m,
-                                                int32_t v) {
-    uint32_t lo = 0, hi = m;
+// Interval id of v = number of bounds <= v, in [0, m].  A 1024-entry table over
+// [bounds[0], bounds[m-1]) gives the id at the lower edge of v's bucket; a short forward walk
+// (or a binary search inside the bucket when many bounds crowd into it) finishes the job --
+// one subtraction, one shift and two or three shared-memory reads for typical batches,
+// against log2(2Q) dependent probes for a plain binary search.
+struct SsLookup {
+    const int32_t *bounds;
+    const uint16_t *lut;                          // SS_LUT + 1 entries
+    uint32_t m, shift;
+    int32_t lo, hi;                               // bounds[0], bounds[m-1]
+};
+
+__device__ __forceinline__ uint32_t interval_of(const SsLookup &L, int32_t v) {
+    if (L.m == 0 || v < L.lo) return 0u;
+    if (v >= L.hi) return L.m;
+    const uint32_t k = ((uint32_t)v - (uint32_t)L.lo) >> L.shift;
+    uint32_t id = L.lut[k];
+    if (id & 0x8000u) return 0u;                  // no query reaches into this bucket: "no hit"
+    const uint32_t id_end = L.lut[k + 1] & 0x7FFFu;   // every bound of this bucket is < id_end
+    if (id_end - id <= 4) {
+        while (id < id_end && L.bounds[id] <= v) ++id;
+        return id;
+    }
+    uint32_t lo = id, hi = id_end;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (s_bounds[mid] <= v) lo = mid + 1; else hi = mid;
+        if (L.bounds[mid] <= v) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
+// Every CTA rebuilds the table from the bounds (m <= 300: a few hundred instructions).  A
+// bucket none of whose intervals is covered by a query gets bit 15: its rows are classified
+// as interval 0 (= no hit) after a single table read -- most rows of a selective batch.
+__device__ __forceinline__ SsLookup build_lookup(const SharedScanPlan &plan, int32_t *s_bounds,
+                                                 uint16_t *s_lut, const uint16_t *s_off) {
+    for (uint32_t i = threadIdx.x; i < plan.m; i += SS_THREADS) s_bounds[i] = plan.bounds[i];
+    __syncthreads();
+    SsLookup L{s_bounds, s_lut, plan.m, 0u, 0, 0};
+    if (plan.m) {
+        L.lo = s_bounds[0];
+        L.hi = s_bounds[plan.m - 1];
+        const uint32_t span = (uint32_t)L.hi - (uint32_t)L.lo;
+        while ((span >> L.shift) >= (uint32_t)SS_LUT) ++L.shift;
+        for (uint32_t k = threadIdx.x; k <= (uint32_t)SS_LUT; k += SS_THREADS) {
+            // number of bounds <= lo + (k << shift) - 1, i.e. strictly below the bucket's edge,
+            // plus those equal to the edge are found by the forward walk
+            const uint64_t edge = (uint64_t)k << L.shift;
+            uint32_t a = 0, b = plan.m;
+            while (a < b) {
+                const uint32_t mid = (a + b) >> 1;
+                if ((uint64_t)((uint32_t)s_bounds[mid] - (uint32_t)L.lo) < edge) a = mid + 1; else b = mid;
+            }
+            s_lut[k] = (uint16_t)a;
+        }
+        __syncthreads();
+        uint16_t flagged[(SS_LUT + SS_THREADS - 1) / SS_THREADS];
+        for (uint32_t k = threadIdx.x, t = 0; k < (uint32_t)SS_LUT; k += SS_THREADS, ++t) {
+            bool covered = false;                  // ids reachable from bucket k: lut[k] .. lut[k+1]
+            for (uint32_t i = s_lut[k]; i <= s_lut[k + 1] && !covered; ++i) covered = s_off[i + 1] != s_off[i];
+            flagged[t] = covered ? s_lut[k] : (uint16_t)(s_lut[k] | 0x8000u);
+        }
+        __syncthreads();
+        for (uint32_t k = threadIdx.x, t = 0; k < (uint32_t)SS_LUT; k += SS_THREADS, ++t) s_lut[k] = flagged[t];
+    }
+    __syncthreads();
+    return L;
+}
+
+// Classify + count.  The common case of a selective batch is a row no query wants: it is
+// dismissed branch-free with one table read (bit 15 of the bucket entry).  The few rows that
+// may hit are compacted, in row order, into a per-warp work list and then resolved with all
+// lanes busy: exact interval, per-query counters, and -- if at least one query covers the
+// interval -- one packed {interval, row} entry appended to the chunk's hit list in global
+// memory.  The emit pass reads that list instead of the column.
+constexpr int SS_WORK = SS_WTILE;                 // work-list entries per warp: one tile's worth
+
 __global__ void __launch_bounds__(SS_THREADS)
 ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan plan,
-                   uint32_t chunk_rows, uint32_t num_chunks, uint16_t *__restrict__ cls,
-                   uint32_t *__restrict__ counts /* [q][num_chunks] */) {
+                   uint32_t chunk_rows, uint32_t num_chunks, uint32_t *__restrict__ hitlist,
+                   uint32_t *__restrict__ chunk_hits, uint32_t *__restrict__ counts /* [q][num_chunks] */) {
     __shared__ int32_t s_bounds[SS_BMAX];
+    __shared__ uint16_t s_lut[SS_LUT + 1];
     __shared__ uint16_t s_off[SS_BMAX + 2];
     __shared__ uint32_t s_cnt[SS_WARPS][SS_QMAX];
+    __shared__ uint2 s_work[SS_WARPS][SS_WORK];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < plan.m; i += SS_THREADS) s_bounds[i] = plan.bounds[i];
     for (uint32_t i = threadIdx.x; i < plan.m + 2; i += SS_THREADS) s_off[i] = plan.cov_off[i];
     for (uint32_t i = threadIdx.x; i < SS_WARPS * SS_QMAX; i += SS_THREADS) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
+    const SsLookup L = build_lookup(plan, s_bounds, s_lut, s_off);
     const uint32_t chunk = blockIdx.x * SS_WARPS + warp;
     if (chunk >= num_chunks) return;
     const uint32_t row_begin = chunk * chunk_rows;
     const uint32_t tiles = chunk_rows / SS_WTILE;
     const bool aligned = (reinterpret_cast<uintptr_t>(val) & 15u) == 0;
     uint32_t *my_cnt = s_cnt[warp];
+    uint2 *work = s_work[warp];
+    uint32_t *__restrict__ my_hits = hitlist + (size_t)chunk * chunk_rows;
+    const uint8_t *__restrict__ cov_q = plan.cov_q;
+    const uint32_t ulo = (uint32_t)L.lo;
+    const uint32_t span = L.m ? (uint32_t)L.hi - ulo : 0u;      // values in [lo, hi) can hit
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t nhits = 0;                                         // uniform across the warp
 
     for (uint32_t t = 0; t < tiles; ++t) {
         const uint32_t row0 = row_begin + t * SS_WTILE;
-        if (row0 >= n) {                                   // past the column: interval 0 (no hits)
+        if (row0 >= n) break;
+        int32_t v[16];
+        uint32_t okmask = 0xFFFFu;
+        if (aligned && row0 + SS_WTILE <= n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int4 x = ld_stream(reinterpret_cast<const int4 *>(val + row0 + j * 128 + lane * 4));
+                v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+            }
+        } else {
+            okmask = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint2 *>(cls + row0 + j * 128 + lane * 4) = make_uint2(0, 0);
-            continue;
-        }
-        const bool fast = aligned && row0 + SS_WTILE <= n;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t r = row0 + j * 128 + lane * 4;
-            int32_t v[4];
-            bool ok[4];
-            if (fast) {
-                const int4 x = ld_stream(reinterpret_cast<const int4 *>(val + r));
-                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-                ok[0] = ok[1] = ok[2] = ok[3] = true;
-            } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    ok[k] = r + k < n;
-                    v[k] = ok[k] ? ld_stream(val + r + k) : 0;
+                    const uint32_t r = row0 + j * 128 + lane * 4 + k;
+                    const bool ok = r < n;
+                    okmask |= ok ? 1u << (4 * j + k) : 0u;
+                    v[4 * j + k] = ok ? ld_stream(val + r) : 0;
                 }
-            }
-            uint32_t id[4];
+        }
+        uint32_t wcount = 0;                                     // uniform
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t need = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                id[k] = ok[k] ? interval_of(s_bounds, plan.m, v[k]) : 0u;
-                const uint32_t b = s_off[id[k]], e = s_off[id[k] + 1];
-                for (uint32_t c = b; c < e; ++c) atomicAdd(&my_cnt[plan.cov_q[c]], 1u);
+                const uint32_t d = (uint32_t)v[4 * j + k] - ulo;
+                const uint32_t e = d < span ? (uint32_t)s_lut[d >> L.shift] : 0x8000u;
+                need |= (e & 0x8000u) ? 0u : 1u << k;
             }
-            *reinterpret_cast<uint2 *>(cls + r) =
-                make_uint2(id[0] | (id[1] << 16), id[2] | (id[3] << 16));
+            need &= okmask >> (4 * j);
+            const uint32_t c = __popc(need);
+            const uint32_t incl = warp_incl_scan(c, lane);
+            const uint32_t tot = __shfl_sync(kFull, incl, 31);
+            if (tot == 0) continue;
+            uint32_t slot = wcount + incl - c;
+            const uint32_t rel0 = t * SS_WTILE + j * 128 + lane * 4;     // row within the chunk
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (need & (1u << k)) work[slot++] = make_uint2((uint32_t)v[4 * j + k], rel0 + k);
+            wcount += tot;
         }
+        if (wcount == 0) continue;
+        __syncwarp();
+        for (uint32_t base = 0; base < wcount; base += kWarp) {
+            const bool live = base + lane < wcount;
+            uint32_t id = 0, rel = 0, b = 0, e = 0;
+            if (live) {
+                const uint2 w = work[base + lane];
+                rel = w.y;
+                id = interval_of(L, (int32_t)w.x);
+                b = s_off[id];
+                e = s_off[id + 1];
+            }
+            for (uint32_t c = b; c < e; ++c) atomicAdd(&my_cnt[cov_q[c]], 1u);
+            const uint32_t m = __ballot_sync(kFull, e > b);
+            if (e > b) my_hits[nhits + __popc(m & lt)] = (id << 23) | rel;   // rel < 2^23, id <= 300
+            nhits += __popc(m);
+        }
+        __syncwarp();
     }
+    if (lane == 0) chunk_hits[chunk] = nhits;
     __syncwarp();
     for (uint32_t q = lane; q < plan.q_count; q += kWarp)
         counts[(size_t)q * num_chunks + chunk] = my_cnt[q];
@@ -124,46 +231,109 @@ ss_offsets_kernel(uint32_t *__restrict__ counts, uint32_t num_chunks, int64_t *_
     if (threadIdx.x == 0) totals[blockIdx.x] = (int64_t)carry;
 }
 
+// Emit.  A warp walks its row range 32 rows at a time and turns every covered row into
+// (query, row) pairs, row-major, in a small per-warp queue.  Whenever 32 pairs are parked
+// they are written out in one go: lanes holding the same query find each other with one
+// ballot per query-id bit, rank themselves in lane (= row) order and append behind that
+// query's running offset.  Cost per pair is a handful of instructions whatever the number
+// of distinct queries, where the previous version spent one reduce / ballot / update round
+// per (row group, query).
+__device__ __forceinline__ void ss_drain(uint32_t *queue, uint32_t head, uint32_t avail, uint32_t lane,
+                                         uint32_t *run, uint32_t row_begin,
+                                         int32_t *const *__restrict__ outs, int64_t capacity) {
+    const bool live = lane < avail;
+    uint32_t x = live ? queue[(head + lane) & (SS_QUEUE - 1)] : 0u;
+    const uint32_t q = x >> 24;
+    uint32_t peers = __ballot_sync(kFull, live);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (q >> b) & 1u;
+        const uint32_t vote = __ballot_sync(kFull, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    uint32_t old = 0;
+    if (live) old = run[q];
+    __syncwarp();
+    if (live) {
+        const uint32_t r = __popc(peers & ((1u << lane) - 1u));
+        if (r == 0) run[q] = old + __popc(peers);
+        const int64_t idx = (int64_t)old + r;
+        if (idx < capacity) outs[q][idx] = (int32_t)(row_begin + (x & 0xFFFFFFu));
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(SS_THREADS)
-ss_emit_kernel(const uint16_t *__restrict__ cls, SharedScanPlan plan, uint32_t chunk_rows,
-               uint32_t num_chunks, const uint32_t *__restrict__ offsets /* [q][num_chunks] */,
+ss_emit_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict__ chunk_hits,
+               SharedScanPlan plan, uint32_t chunk_rows, uint32_t num_chunks,
+               const uint32_t *__restrict__ offsets /* [q][num_chunks] */,
                int32_t *const *__restrict__ outs, int64_t capacity) {
     __shared__ uint16_t s_off[SS_BMAX + 2];
     __shared__ uint32_t s_run[SS_WARPS][SS_QMAX];
+    __shared__ uint32_t s_queue[SS_WARPS][SS_QUEUE];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < plan.m + 2; i += SS_THREADS) s_off[i] = plan.cov_off[i];
     __syncthreads();
     const uint32_t chunk = blockIdx.x * SS_WARPS + warp;
     if (chunk >= num_chunks) return;
+    const uint32_t nh = chunk_hits[chunk];
+    if (nh == 0) return;
     uint32_t *run = s_run[warp];
+    uint32_t *queue = s_queue[warp];
     for (uint32_t q = lane; q < plan.q_count; q += kWarp)
         run[q] = offsets[(size_t)q * num_chunks + chunk];
     __syncwarp();
     const uint32_t row_begin = chunk * chunk_rows;
-    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t *__restrict__ list = hitlist + (size_t)chunk * chunk_rows;
     const uint8_t *__restrict__ cov_q = plan.cov_q;
-    for (uint32_t r0 = 0; r0 < chunk_rows; r0 += kWarp) {
-        const uint32_t row = row_begin + r0 + lane;
-        const uint32_t id = cls[row];
-        uint32_t c = s_off[id];
-        const uint32_t e = s_off[id + 1];
-        while (true) {
-            const uint32_t q = c < e ? (uint32_t)cov_q[c] : 0xFFFFFFFFu;
-            const uint32_t qmin = __reduce_min_sync(kFull, q);
-            if (qmin == 0xFFFFFFFFu) break;
-            const bool mine = q == qmin;
-            const uint32_t peers = __ballot_sync(kFull, mine);
-            const uint32_t old = run[qmin];
+    uint32_t head = 0, avail = 0;                          // queue state, uniform across the warp
+    uint32_t nxt = lane < nh ? list[lane] : 0u;
+    for (uint32_t base = 0; base < nh; base += kWarp) {
+        const uint32_t x = nxt;
+        const bool live = base + lane < nh;
+        if (base + kWarp + lane < nh) nxt = list[base + kWarp + lane];
+        const uint32_t id = x >> 23, rel = x & 0x7FFFFFu;
+        const uint32_t b = live ? s_off[id] : 0u, e = live ? s_off[id + 1] : 0u;
+        const uint32_t ncov = e - b;                       // >= 1 for every listed row
+        const uint32_t incl = warp_incl_scan(ncov, lane);
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        if (avail + total <= (uint32_t)SS_QUEUE) {
+            uint32_t slot = head + avail + incl - ncov;
+            for (uint32_t c = b; c < e; ++c, ++slot)
+                queue[slot & (SS_QUEUE - 1)] = ((uint32_t)cov_q[c] << 24) | rel;
+            avail += total;
             __syncwarp();
-            if (lane == 0) run[qmin] = old + __popc(peers);
-            __syncwarp();
-            if (mine) {
-                const int64_t idx = (int64_t)old + __popc(peers & lt);
-                if (idx < capacity) outs[qmin][idx] = (int32_t)row;
-                ++c;
+            while (avail >= kWarp) {
+                ss_drain(queue, head, kWarp, lane, run, row_begin, outs, capacity);
+                head += kWarp;
+                avail -= kWarp;
+            }
+        } else {
+            // heavily overlapping queries: more pairs than the queue holds.  Flush what is
+            // parked, then serve these 32 rows query by query, smallest pending id first.
+            if (avail) ss_drain(queue, head, avail, lane, run, row_begin, outs, capacity);
+            head += avail;
+            avail = 0;
+            uint32_t c = b;
+            while (true) {
+                const uint32_t q = c < e ? (uint32_t)cov_q[c] : 0xFFFFFFFFu;
+                const uint32_t qmin = __reduce_min_sync(kFull, q);
+                if (qmin == 0xFFFFFFFFu) break;
+                const bool mine = q == qmin;
+                const uint32_t peers = __ballot_sync(kFull, mine);
+                const uint32_t old = run[qmin];
+                __syncwarp();
+                if (lane == 0) run[qmin] = old + __popc(peers);
+                __syncwarp();
+                if (mine) {
+                    const int64_t idx = (int64_t)old + __popc(peers & ((1u << lane) - 1u));
+                    if (idx < capacity) outs[qmin][idx] = (int32_t)(row_begin + rel);
+                    ++c;
+                }
             }
         }
     }
+    if (avail) ss_drain(queue, head, avail, lane, run, row_begin, outs, capacity);
 }
 
 // ---- launch -------------------------------------------------------------------------------------
@@ -180,19 +350,19 @@ SharedScanGeom shared_scan_geom(uint32_t n, int sm_count) {
 }
 
 int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan &plan,
-                           const SharedScanGeom &g, uint16_t *cls, uint32_t *counts,
-                           int64_t *totals, cudaStream_t s) {
-    ss_classify_kernel<<<g.grid, SS_THREADS, 0, s>>>(val, n, plan, g.chunk_rows, g.num_chunks, cls,
-                                                     counts);
+                           const SharedScanGeom &g, uint32_t *hitlist, uint32_t *chunk_hits,
+                           uint32_t *counts, int64_t *totals, cudaStream_t s) {
+    ss_classify_kernel<<<g.grid, SS_THREADS, 0, s>>>(val, n, plan, g.chunk_rows, g.num_chunks,
+                                                     hitlist, chunk_hits, counts);
     ss_offsets_kernel<<<plan.q_count, 1024, 0, s>>>(counts, g.num_chunks, totals);
     return 2;
 }
 
-int launch_shared_emit(const uint16_t *cls, const SharedScanPlan &plan, const SharedScanGeom &g,
-                       const uint32_t *offsets, int32_t *const *outs, int64_t capacity,
-                       cudaStream_t s) {
-    ss_emit_kernel<<<g.grid, SS_THREADS, 0, s>>>(cls, plan, g.chunk_rows, g.num_chunks, offsets, outs,
-                                                 capacity);
+int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
+                       const SharedScanPlan &plan, const SharedScanGeom &g, const uint32_t *offsets,
+                       int32_t *const *outs, int64_t capacity, cudaStream_t s) {
+    ss_emit_kernel<<<g.grid, SS_THREADS, 0, s>>>(hitlist, chunk_hits, plan, g.chunk_rows,
+                                                 g.num_chunks, offsets, outs, capacity);
     return 1;
 }
 
