@@ -53,38 +53,67 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region, in-process through NVML
+    (a sample every ~2 ms; the timed region is tens of milliseconds, too short for an
+    `nvidia-smi -lms` child to report from).  Falls back to one nvidia-smi query."""
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+            "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            self.reasons |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            try:
+                self.reasons |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nvml is None:
+            return
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
-                          for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join()
+            if not self.sm:
+                self._sample()
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, b in self.BITS.items() if self.reasons & b),
+                    "samples": len(self.sm), "source": "nvml, sampled inside the timed region"}
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 stdout=subprocess.PIPE, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [],
+                    "samples": 1, "source": "nvidia-smi after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------
@@ -324,6 +353,34 @@ def run_engine(args):
             "result": {"sum": g_sum, "count": g_cnt, "min": g_min, "max": g_max},
         }
 
+    # ---- selectivity sweep on one shard (SURVEY.md 8d lists 0.1 %, 1 %, 10 %, 50 %) -----------
+    if rank == 0 and not args.no_sweep:
+        sweep = {}
+        c1, c2 = cols[0]
+        for sel in (0.001, 0.01, 0.1, 0.5):
+            slo, shi = predicate(sel)
+            need = int(shard_rows * min(1.0, sel * 1.05 + 0.001)) + 4096
+            sp, sv = eng.alloc_i32(need), eng.alloc_i32(need)
+            b1, b2 = C.c_int32(slo), C.c_int32(shi)
+
+            def one():
+                eng._ck(lib.adb_chain_select_fetch_agg(c1.i32(), c2.i32(), shard_rows, C.byref(b1),
+                                                       C.byref(b2), sp.i32(), sv.i32(), res[0][2].i64(),
+                                                       AggP(parts, 0)))
+            for _ in range(2):
+                one()
+            eng.timer_start()
+            for _ in range(5):
+                one()
+            ms = eng.timer_stop() / 5
+            h = int(res[0][2].to_host(1, np.int64)[0])
+            gbs = (4.0 * shard_rows + 20.0 * h) / (ms * 1e-3) / 1e9
+            sweep[str(sel)] = {"ms_per_shard": ms, "hits": h, "rows_per_s_per_gpu": shard_rows / (ms * 1e-3),
+                               "chain_algorithmic_gbs": gbs, "frac_of_peak": gbs / peak}
+            sp.free()
+            sv.free()
+        line["selectivity_sweep"] = sweep
+
     # ---- e2e and cpu_baseline (rank 0; the CPU leg only at N = 1) ----------------------------
     e2e = measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
                       combined, parts)
@@ -535,6 +592,7 @@ def main():
     ap.add_argument("--shards-limit", type=int, default=0, help="debug: fewer shards per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--ops", action="store_true",
                     help="also time shared scan / index / join at the BASELINE config sizes")
     args = ap.parse_args()
