@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "check": {"sum": s, "hits": h},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -381,6 +381,10 @@ def run_engine(args):
             sv.free()
         line["selectivity_sweep"] = sweep
 
+    join_sharded = None
+    if world > 1 and args.ops:
+        join_sharded = measure_join_sharded(eng, dist, rank, world, local)
+
     # ---- e2e and cpu_baseline (rank 0; the CPU leg only at N = 1) ----------------------------
     e2e = measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
                       combined, parts)
@@ -393,7 +397,9 @@ def run_engine(args):
                 c1.free()
                 c2.free()
             line["ops"] = measure_ops(args)
-        print(json.dumps(line))
+        if world > 1 and args.ops:
+            line["ops"] = {"hash_join_sharded": join_sharded}
+        emit(line)
     barrier()
     if dist is not None:
         dist.destroy_process_group()
@@ -521,6 +527,52 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
     return out
 
 
+def measure_join_sharded(eng, dist, rank, world, local):
+    """BASELINE config 4: hash join of two 100 M-row tables with selective prefilters, both
+    row-range sharded over the ranks, pairs hash-routed by key (adb_route_pairs), exchanged
+    with NCCL all-to-all-v, joined locally.  Returns tuples/s over all ranks (max time)."""
+    import torch
+    from analytical_database_b200.sharded import EngineOps, ShardedTable, shard_range
+    dev = torch.device("cuda", local)
+    ops = EngineOps(eng, dev)                 # engine stream = torch's current stream
+    n = 100_000_000
+    out = {}
+    b, e = shard_range(n, rank, world)
+    rows = e - b
+
+    def col(seed, lo, span):
+        t = torch.empty(rows, dtype=torch.int32, device=dev)
+        eng._ck(eng.lib.adb_synth_uniform(C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_int32)),
+                                          rows, seed, b, lo, span))
+        return t
+    t1 = ShardedTable(ops, {"k": col(11, 1, n), "f": col(13, 0, 1000)}, n, dist)
+    t2 = ShardedTable(ops, {"k": col(12, 1, n), "f": col(14, 0, 1000)}, n, dist)
+    for s1, s2 in ((0.8, 0.15), (1.0, 1.0)):
+        p1, p2 = t1.select("f", None, int(1000 * s1)), t2.select("f", None, int(1000 * s2))
+        v1, v2 = t1.fetch("k", p1), t2.fetch("k", p2)
+        g1, g2 = p1.local + p1.base, p2.local + p2.base        # global positions (< 2^31)
+        ms = []
+        for it in range(4):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            o1, o2 = t1.hash_join(v1, g1, v2, g2)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(ms[1:])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        m = torch.tensor([o1.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        tup = p1.total + p2.total
+        out[f"prefilter_{s1}_{s2}"] = {"build": p1.total, "probe": p2.total, "matches": int(m.item()),
+                                       "ms": float(t.item()), "tuples_per_s": tup / (float(t.item()) * 1e-3),
+                                       "world": world,
+                                       "includes": "routing kernel, 2 x (count + 2 payload) all-to-all, local join"}
+    return out
+
+
 def measure_ops(args):
     """The other BASELINE.json configs on one GPU, bounded: batched shared scan (config 2),
     index range select + fetch (config 3), hash join with prefilters (config 4)."""
@@ -581,6 +633,25 @@ def measure_cpu(args, eng, cols, res, shard_rows, lo, hi):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun) write to fd 1; the contract is ONE JSON line
+    on stdout.  Point fd 1 at stderr for the run and keep the real stdout for the result."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -597,6 +668,7 @@ def main():
                     help="also time shared scan / index / join at the BASELINE config sizes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_engine(args)
