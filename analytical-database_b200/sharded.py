@@ -103,6 +103,23 @@ class EngineOps:
         self.eng._ck(self.lib.adb_shared_select_emit(ptrs, max(list(counts) + [1])))
         return outs
 
+    def index_build(self, col, with_btree=True):
+        """(values, positions, handle) of this shard's rows: adb_index_sort + adb_index_create."""
+        n = col.numel()
+        vals, poss = self.empty(n), self.empty(n)
+        self.eng._ck(self.lib.adb_index_sort(self._p(col), n, self._p(vals), self._p(poss)))
+        h = C.c_void_p()
+        self.eng._ck(self.lib.adb_index_create(self._p(vals), self._p(poss), n, int(with_btree), C.byref(h)))
+        return vals, poss, h
+
+    def select_index(self, index, lo, hi, use_btree):
+        h = C.c_int64(0)
+        self.eng._ck(self.lib.adb_select_index_count(index[2], int(use_btree), self._b(lo), self._b(hi),
+                                                     self._p(self._cnt, C.c_int64), C.byref(h)))
+        out = self.empty(h.value)
+        self.eng._ck(self.lib.adb_select_index_emit(index[2], self._p(out)))
+        return out
+
     def route_pairs(self, val, pos, parts):
         vo, po = self.empty(val.numel()), self.empty(val.numel())
         counts = (C.c_int64 * parts)()
@@ -160,6 +177,19 @@ class ShardedTable:
         before = allc[:self.rank].sum(0).tolist()
         totals = allc.sum(0).tolist()
         return [Positions(outs[i], self.begin, before[i], totals[i]) for i in range(q)]
+
+    def build_index(self, col: str, with_btree: bool = True):
+        """Per-shard sorted index (+ implicit B+-tree) over this shard's rows of `col`."""
+        self.indexes = getattr(self, "indexes", {})
+        self.indexes[col] = self.ops.index_build(self.cols[col], with_btree)
+
+    def select_index(self, col: str, lo, hi, use_btree: bool = False) -> Positions:
+        """Range select through the shard-local index.  The concatenation over shards is
+        shard-major, value order inside a shard: equal to the reference's
+        single-index result as a set; compare order-insensitively or merge for print."""
+        local = self.ops.select_index(self.indexes[col], lo, hi, use_btree)
+        off, total = self._offsets(local.numel())
+        return Positions(local, self.begin, off, total)
 
     def fetch(self, col: str, pos: Positions) -> torch.Tensor:
         return self.ops.fetch(self.cols[col], pos.local)       # positions never leave their shard

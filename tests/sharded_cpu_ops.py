@@ -45,6 +45,17 @@ class OracleOps:
     def shared_select(self, col, lows, highs):
         return [self._t(x) for x in self.o.shared_select(col.numpy(), lows, highs)]
 
+    def index_build(self, col, with_btree=True):
+        a = col.numpy()
+        order = np.argsort(a, kind="stable")
+        return self._t(a[order]), self._t(order), None
+
+    def select_index(self, index, lo, hi, use_btree):
+        vals, poss = index[0].numpy(), index[1].numpy()
+        l = 0 if lo is None else int(np.searchsorted(vals, lo, "left"))
+        h = vals.size if hi is None else int(np.searchsorted(vals, hi, "left"))
+        return self._t(poss[l:max(l, h)])
+
     def route_pairs(self, val, pos, parts):
         d = route_dest(val.numpy(), parts)
         order = np.argsort(d, kind="stable")

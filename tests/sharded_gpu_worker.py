@@ -43,6 +43,10 @@ def main():
     highs = [100, n // 16, n // 4 + n // 50, 3]
     ss = t.shared_select("c1", lows, highs)
     res["ss"] = [t.gather_global(p.local, p.base).cpu().numpy() for p in ss]
+    t.build_index("k")
+    for tree in (False, True):
+        si = t.select_index("k", 100, 140, use_btree=tree)
+        res["ix_tree" if tree else "ix"] = t.gather_global(si.local, si.base).cpu().numpy()
     s1, s2 = t.select("c1", None, n // 4), t.select("c1", -n // 10, -n // 20)
     v1, v2 = t.fetch("k", s1), t.fetch("k", s2)
     p1, p2 = s1.local + s1.base, s2.local + s2.base

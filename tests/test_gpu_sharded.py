@@ -83,6 +83,8 @@ def test_nccl_shards_equal_one_shard(port, tmp_path):
     exp = port.shared_select(tab["c1"], [-100, 0, n // 4, 7], [100, n // 16, n // 4 + n // 50, 3])
     for got, e in zip(res["ss"], exp):
         assert np.array_equal(got, e.astype(np.int64))
+    scan = port.select_scan(tab["k"], 100, 140).astype(np.int64)
+    assert np.array_equal(np.sort(res["ix"]), scan) and np.array_equal(res["ix"], res["ix_tree"])
     s1, s2 = port.select_scan(tab["c1"], None, n // 4), port.select_scan(tab["c1"], -n // 10, -n // 20)
     e1, e2 = port.hash_join(port.fetch(tab["k"], s1), s1, port.fetch(tab["k"], s2), s2)
     expj = np.stack([e1, e2], 1).astype(np.int64)

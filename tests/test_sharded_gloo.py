@@ -53,6 +53,11 @@ def _worker(rank, world, port, out):
     ss = t.shared_select("c1", lows, highs)
     res["ss"] = [t.gather_global(p.local, p.base).numpy() for p in ss]
     res["ss_off"] = [(p.offset, p.total) for p in ss]
+    # per-shard index: shard-major, value order inside a shard
+    t.build_index("k")
+    si = t.select_index("k", 100, 140)
+    res["ix"] = t.gather_global(si.local, si.base).numpy()
+    res["ix_fetch"] = t.gather_global(t.fetch("k", si)).numpy()
     # hash join of two prefiltered sides: global positions travel with the keys
     s1, s2 = t.select("c1", None, 9000), t.select("c1", -2000, -1500)
     v1, v2 = t.fetch("k", s1), t.fetch("k", s2)
@@ -93,6 +98,15 @@ def test_shared_select_equals_one_shard(two_shards, port):
     exp = port.shared_select(tab["c1"], [-100, 0, 9000, 7], [100, 2500, 9100, 3])
     for got, e, (off, total) in zip(two_shards["ss"], exp, two_shards["ss_off"]):
         assert np.array_equal(got, e.astype(np.int64)) and off == 0 and total == e.size
+
+
+def test_sharded_index_select_equals_scan_as_a_set(two_shards, port):
+    tab = _table()
+    exp = port.select_scan(tab["k"], 100, 140)
+    assert np.array_equal(np.sort(two_shards["ix"]), exp.astype(np.int64))
+    v = two_shards["ix_fetch"]
+    half = int(np.searchsorted(two_shards["ix"] >= (N // 2), True))      # shard-major ...
+    assert np.all(np.diff(v[:half]) >= 0) and np.all(np.diff(v[half:]) >= 0)   # ... value order inside
 
 
 def test_partitioned_join_equals_one_shard(two_shards, port):
