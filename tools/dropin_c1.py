@@ -33,7 +33,7 @@ def scripts(n, csv):
                 f'load("{csv}")\n',
         "select_fetch_sum": f"s1=select(db1.tbl2.col1,{-q},{q})\nf1=fetch(db1.tbl2.col3,s1)\na1=sum(f1)\nprint(a1)\n"
                             "a2=sum(db1.tbl2.col1)\nprint(a2)\n",
-        "select_fetch_avg": f"s1=select(db1.tbl2.col1,{-q // 10},{q // 10})\nf1=fetch(db1.tbl2.col4,s1)\n"
+        "select_fetch_avg": f"s1=select(db1.tbl2.col1,{-q // 10},{q // 10})\nf1=fetch(db1.tbl2.col3,s1)\n"
                             "a1=avg(f1)\nprint(a1)\n",
         "min_max": f"s1=select(db1.tbl2.col1,{-q},null)\nf1=fetch(db1.tbl2.col2,s1)\nm1=min(f1)\nm2=max(f1)\n"
                    "print(m1,m2)\n",
