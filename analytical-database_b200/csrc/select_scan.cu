@@ -207,8 +207,8 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
             uint32_t r = incl - c;                               // rank of this lane's first hit
             const uint32_t row0 = row_begin + wi * 32;
             const uint32_t mm[EXP_WORDS] = {m.x, m.y, m.z, m.w};
-            if (step_total <= 2 * kWarp) {
-                // sparse: straight from registers
+            if (!FETCH && step_total <= 2 * kWarp) {
+                // sparse: straight from registers (stores only, nothing waits on them)
 #pragma unroll
                 for (int q = 0; q < EXP_WORDS; ++q) {
                     uint32_t bits = mm[q];
@@ -246,14 +246,36 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
                     }
                     __syncwarp();
                     const uint32_t cnt = step_total - done < 1024 ? step_total - done : 1024;
-                    for (uint32_t i = lane; i < cnt; i += kWarp) {
-                        const int32_t row = stage[i];
-                        if (FETCH) {
-                            out[out_off + done + i] = PAIRS ? pos_in[row] : row + base_pos;
-                            const int32_t v = __ldg(fcol + row);
-                            vout[out_off + done + i] = v;
-                            acc.add(v);
-                        } else {
+                    if (FETCH) {
+                        // The gathers are the long pole (one 128-byte line each).  Rows were
+                        // dealt out by rank, so every lane issues up to GB independent loads
+                        // before the first value is consumed: one round trip per 32*GB hits
+                        // instead of one per hit of the busiest lane.
+                        constexpr int GB = 4;
+                        for (uint32_t i0 = 0; i0 < cnt; i0 += GB * kWarp) {
+                            int32_t row[GB], v[GB], p[GB];
+#pragma unroll
+                            for (int k = 0; k < GB; ++k) {
+                                const uint32_t i = i0 + k * kWarp + lane;
+                                row[k] = i < cnt ? stage[i] : -1;
+                            }
+#pragma unroll
+                            for (int k = 0; k < GB; ++k) {
+                                v[k] = row[k] >= 0 ? __ldg(fcol + row[k]) : 0;
+                                p[k] = PAIRS ? (row[k] >= 0 ? __ldg(pos_in + row[k]) : 0) : row[k] + base_pos;
+                            }
+#pragma unroll
+                            for (int k = 0; k < GB; ++k)
+                                if (row[k] >= 0) {
+                                    const uint32_t o = out_off + done + i0 + k * kWarp + lane;
+                                    out[o] = p[k];
+                                    vout[o] = v[k];
+                                    acc.add(v[k]);
+                                }
+                        }
+                    } else {
+                        for (uint32_t i = lane; i < cnt; i += kWarp) {
+                            const int32_t row = stage[i];
                             out[out_off + done + i] = PAIRS ? row : row + base_pos;
                         }
                     }
