@@ -222,6 +222,22 @@ int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_
                           uint32_t span, int sm_count, cudaStream_t s);
 constexpr int kAggMaxBlocks = 148 * 8;
 
+// Aggregate exchange over NVLink peer memory (peer_agg.cu).  One 32-byte record per
+// (bank, source rank) in every rank's mailbox; box[r] is rank r's mailbox as mapped into this
+// process (cudaIpcOpenMemHandle; box[rank] is the local allocation itself).
+constexpr int kMaxPeers = ADB_MAX_PEERS;
+struct PeerRecord {
+    int64_t sum, count;
+    int32_t min, max;
+    uint32_t epoch, pad;
+};
+struct PeerBoxes {
+    PeerRecord *box[kMaxPeers];
+};
+constexpr size_t kPeerBoxBytes = sizeof(PeerRecord) * 2 * kMaxPeers;
+int launch_agg_combine_allreduce(const adb_agg *parts, int32_t k, const PeerBoxes &boxes, int32_t rank,
+                                 int32_t world, uint32_t epoch, adb_agg *out, cudaStream_t s);
+
 // Batched shared scan (shared_scan.cu).  All pointers are device addresses.
 struct SharedScanPlan {
     const int32_t *bounds;     // m ascending distinct bounds

@@ -67,6 +67,12 @@ struct Engine {
     // differently sized multi-hundred-MB blocks made the pool re-map memory on every join
     unsigned char *arena = nullptr;
     size_t arena_cap = 0, arena_used = 0;
+    // aggregate exchange over peer memory (adb_peer_*): own mailbox + the peers' mappings
+    adb::PeerRecord *peer_box = nullptr;
+    adb::PeerBoxes peer_boxes{};
+    int32_t peer_world = 0, peer_rank = -1;
+    bool peer_connected = false;
+    uint32_t peer_epoch = 0;
     int64_t launches = 0;
     int32_t chain_mark_base = -1;       // adb_chain_marks(): slots for the next chain call
 } g;
@@ -139,6 +145,19 @@ adb_status ensure_select_scratch(uint32_t n) {
     }
     g.sel_mask_words = words;
     return ADB_OK;
+}
+
+void peer_close() {
+    for (int r = 0; r < g.peer_world; ++r)
+        if (r != g.peer_rank && g.peer_boxes.box[r]) cudaIpcCloseMemHandle(g.peer_boxes.box[r]);
+    if (g.peer_box) cudaFree(g.peer_box);
+    cudaGetLastError();
+    g.peer_box = nullptr;
+    g.peer_boxes = adb::PeerBoxes{};
+    g.peer_world = 0;
+    g.peer_rank = -1;
+    g.peer_connected = false;
+    g.peer_epoch = 0;
 }
 
 }  // namespace
@@ -214,6 +233,7 @@ adb_status adb_shutdown(void) {
     cudaFree(g.arena);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
+    peer_close();
     cudaEventDestroy(g.ev0);
     cudaEventDestroy(g.ev1);
     for (cudaEvent_t &m : g.marks)
@@ -437,6 +457,72 @@ adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, ad
         CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
         CU(cudaStreamSynchronize(g.stream));
     }
+    return ADB_OK;
+}
+
+// ---- aggregate exchange over NVLink peer memory ------------------------------------------
+adb_status adb_peer_create(int32_t world, int32_t rank, unsigned char *handle_out) {
+    NEED_UP();
+    static_assert(sizeof(cudaIpcMemHandle_t) == ADB_PEER_HANDLE_BYTES, "handle size");
+    if (world < 1 || world > ADB_MAX_PEERS || rank < 0 || rank >= world || !handle_out)
+        return fail(ADB_ERR_INVALID, "adb_peer_create: world %d (max %d), rank %d", world, ADB_MAX_PEERS, rank);
+    CU(cudaStreamSynchronize(g.stream));
+    peer_close();
+    CU(cudaMalloc(&g.peer_box, adb::kPeerBoxBytes));
+    CU(cudaMemset(g.peer_box, 0, adb::kPeerBoxBytes));          // epoch 0 = nothing arrived yet
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, g.peer_box));
+    memcpy(handle_out, &h, sizeof h);
+    g.peer_world = world;
+    g.peer_rank = rank;
+    g.peer_boxes.box[rank] = g.peer_box;
+    return ADB_OK;
+}
+
+adb_status adb_peer_connect(const unsigned char *handles) {
+    NEED_UP();
+    if (!g.peer_box || !handles) return fail(ADB_ERR_INVALID, "adb_peer_connect: adb_peer_create first");
+    for (int r = 0; r < g.peer_world; ++r) {
+        if (r == g.peer_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * ADB_PEER_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ADB_ERR_CUDA, "adb_peer_connect: cannot map rank %d's mailbox: %s (peer access over "
+                        "NVLink is required)", r, cudaGetErrorString(e));
+        }
+        g.peer_boxes.box[r] = static_cast<adb::PeerRecord *>(p);
+    }
+    g.peer_connected = true;
+    g.peer_epoch = 0;
+    return ADB_OK;
+}
+
+adb_status adb_agg_combine_allreduce(const adb_agg *d_parts, int32_t k, adb_agg *d_out, adb_agg *h_out) {
+    NEED_UP();
+    if (!g.peer_connected) return fail(ADB_ERR_INVALID, "adb_agg_combine_allreduce: adb_peer_connect first");
+    if (k < 0 || !d_out || (k > 0 && !d_parts))
+        return fail(ADB_ERR_INVALID, "adb_agg_combine_allreduce: bad arguments");
+    const uint32_t epoch = ++g.peer_epoch;
+    const int k_ = adb::launch_agg_combine_allreduce(d_parts, k, g.peer_boxes, g.peer_rank, g.peer_world,
+                                                     epoch, d_out, g.stream);
+    if (adb_status s = after_launch("agg_combine_allreduce", k_)) return s;
+    if (h_out) {
+        CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+        if (h_out->count < 0)
+            return fail(ADB_ERR_CUDA, "adb_agg_combine_allreduce: a peer did not arrive within 2 s (epoch %u)", epoch);
+    }
+    return ADB_OK;
+}
+
+adb_status adb_peer_destroy(void) {
+    NEED_UP();
+    CU(cudaStreamSynchronize(g.stream));
+    peer_close();
     return ADB_OK;
 }
 

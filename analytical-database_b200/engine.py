@@ -129,6 +129,10 @@ class Engine:
         "adb_agg_combine": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_agg_export": (C.c_int32, [C.POINTER(_AggStruct), C.c_void_p, C.c_void_p]),
         "adb_agg_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(_AggStruct)]),
+        "adb_peer_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_char_p]),
+        "adb_peer_connect": (C.c_int32, [C.c_char_p]),
+        "adb_agg_combine_allreduce": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
+        "adb_peer_destroy": (C.c_int32, []),
         "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_sub": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_chain_select_fetch_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P, C.POINTER(_AggStruct)]),
@@ -166,6 +170,22 @@ class Engine:
 
     def close(self):
         self.lib.adb_shutdown()
+
+    def peer_setup(self, dist) -> None:
+        """Map every rank's aggregate mailbox into this process (adb_peer_create ->
+        all-gather of the 64-byte IPC handles over `dist` -> adb_peer_connect).  After this,
+        adb_agg_combine_allreduce does the aggregate exchange inside one kernel over NVLink
+        peer memory.  `dist` is torch.distributed (plumbing: it only carries the handles)."""
+        import torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        mine = C.create_string_buffer(64)
+        self._ck(self.lib.adb_peer_create(world, rank, mine))
+        dev = torch.device("cuda", self.device)
+        t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(dev)
+        allh = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, t)
+        self._ck(self.lib.adb_peer_connect(bytes(allh.cpu().numpy().tobytes())))
+        dist.barrier()                                   # every mailbox is mapped everywhere
 
     def alloc(self, nbytes: int) -> DevBuf:
         return DevBuf(self, nbytes)

@@ -4,9 +4,12 @@ One process per GPU (torchrun).  Every table is split into contiguous row ranges
 of a table co-partitioned, so select / fetch / add / sub / shared scan run shard-locally with
 no data-path collective.  `torch.distributed` is plumbing only:
 
-* aggregates     each rank reduces its rows on the device, then ONE exchange step: {sum, count}
-                 (int64, SUM) and {max, ~min} (int32, MAX) all-reduces; avg is the fp64 divide
-                 of the reduced sum and count on the host (/root/reference/src/query.c:314);
+* aggregates     each rank reduces its rows on the device, then ONE exchange step: after
+                 ``EngineOps.connect_peers`` a single kernel folds the local partials and
+                 swaps them with every peer over NVLink peer memory
+                 (``adb_agg_combine_allreduce``); without it, {sum, count} (int64, SUM) and
+                 {max, ~min} (int32, MAX) NCCL all-reduces.  avg is the fp64 divide of the
+                 reduced sum and count on the host (/root/reference/src/query.c:314);
 * position lists stay shard-resident as (shard base row, local int32 positions); an all-gather
                  of the hit counts gives every shard its offset in the concatenated list, which
                  is only materialised for print / verification;
@@ -85,6 +88,24 @@ class EngineOps:
         mm = torch.empty(2, dtype=I32, device=self.device)
         self.eng._ck(self.lib.adb_agg_export(aggp, C.c_void_p(sc.data_ptr()), C.c_void_p(mm.data_ptr())))
         return sc, mm
+
+    def connect_peers(self, dist):
+        """Map the peers' aggregate mailboxes (Engine.peer_setup): aggregates then take the
+        one-kernel NVLink exchange instead of two NCCL all-reduces."""
+        self.eng.peer_setup(dist)
+        self.peers = True
+
+    def aggregate_fused(self, vals):
+        """Local reduction + exchange with every peer inside adb_agg_combine_allreduce; returns
+        the table-wide (sum, count, min, max) or None when the mailboxes are not mapped."""
+        if not getattr(self, "peers", False):
+            return None
+        from .engine import _AggStruct
+        aggp = C.cast(C.c_void_p(self._agg.data_ptr()), C.POINTER(_AggStruct))
+        self.eng._ck(self.lib.adb_aggregate(self._p(vals), vals.numel(), None, aggp, None))
+        h = _AggStruct()
+        self.eng._ck(self.lib.adb_agg_combine_allreduce(aggp, 1, aggp, C.byref(h)))
+        return h.sum, h.count, h.min, h.max
 
     def ewise(self, a, b, subtract):
         out = self.empty(a.numel())
@@ -202,6 +223,11 @@ class ShardedTable:
 
     # ---- aggregates: one exchange step -----------------------------------------------------
     def aggregate(self, vals: torch.Tensor) -> dict:
+        fused = self.ops.aggregate_fused(vals) if self.dist is not None and hasattr(self.ops, "aggregate_fused") else None
+        if fused is not None:
+            s, n, mn, mx = fused
+            return {"sum": s, "count": n, "min": mn, "max": mx,
+                    "avg": float("nan") if n == 0 else float(s) / float(n)}
         sc, mm = self.ops.aggregate_packed(vals)
         if self.dist is not None:
             self.dist.all_reduce(sc, op=self.dist.ReduceOp.SUM)

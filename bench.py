@@ -211,6 +211,9 @@ def run_engine(args):
     eng.set_stream(stream.cuda_stream)          # engine kernels and NCCL share one stream
     torch.cuda.set_stream(stream)
 
+    if dist is not None and args.exchange == "peer":
+        eng.peer_setup(dist)                    # map every rank's aggregate mailbox (NVLink P2P)
+
     lo, hi = predicate(args.selectivity)
     shard_rows = TOTAL_ROWS // N_SHARDS
     my_shards = [s for s in range(N_SHARDS) if s % world == rank] if world > 1 else list(range(N_SHARDS))
@@ -244,8 +247,14 @@ def run_engine(args):
             eng._ck(lib.adb_chain_select_fetch_agg(c1.i32(), c2.i32(), shard_rows, C.byref(blo),
                                                    C.byref(bhi), pos.i32(), val.i32(), cnt.i64(),
                                                    AggP(parts, i)))
-        eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
-        if dist is not None:
+        if dist is None:
+            eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
+        elif args.exchange == "peer":
+            # fold this rank's shard partials and swap them with every peer inside one
+            # kernel, over NVLink peer memory (csrc/peer_agg.cu)
+            eng._ck(lib.adb_agg_combine_allreduce(AggP(parts), len(cols), AggP(combined), None))
+        else:
+            eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
             eng._ck(lib.adb_agg_export(AggP(combined), C.c_void_p(t_sum.data_ptr()),
                                        C.c_void_p(t_mm.data_ptr())))
             dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
@@ -287,7 +296,7 @@ def run_engine(args):
     value = rows_step / (ms_step * 1e-3)
 
     # ---- result of the last step (device-resident) -----------------------------------------
-    if dist is not None:
+    if dist is not None and args.exchange == "nccl":
         g_sum, g_cnt = int(t_sum[0].item()), int(t_sum[1].item())
         g_max, g_min = int(t_mm[0].item()), ~int(t_mm[1].item())
     else:
@@ -352,6 +361,10 @@ def run_engine(args):
                       "formula": "4N + 20H (SURVEY.md 8d)"},
             "result": {"sum": g_sum, "count": g_cnt, "min": g_min, "max": g_max},
         }
+        if world > 1:
+            line["config"]["aggregate_exchange"] = (
+                "adb_agg_combine_allreduce: local fold + exchange in one kernel over NVLink peer memory"
+                if args.exchange == "peer" else "adb_agg_export + 2 NCCL all-reduces")
 
     # ---- selectivity sweep on one shard (SURVEY.md 8d lists 0.1 %, 1 %, 10 %, 50 %) -----------
     if rank == 0 and not args.no_sweep:
@@ -664,6 +677,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: aggregate exchange through the engine's peer-memory kernel or NCCL")
     ap.add_argument("--ops", action="store_true",
                     help="also time shared scan / index / join at the BASELINE config sizes")
     args = ap.parse_args()

@@ -137,6 +137,24 @@ ADB_API adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d
 ADB_API adb_status adb_agg_export(const adb_agg *d_agg, int64_t *d_sum_count, int32_t *d_max_notmin);
 ADB_API adb_status adb_agg_import(const int64_t *d_sum_count, const int32_t *d_max_notmin, adb_agg *d_agg);
 
+/* ---- multi-GPU aggregate exchange over NVLink peer memory (no reference equivalent: the
+ * reference is single-process; SURVEY.md 8e "sum / min / max / avg: one exchange step").
+ * One process per GPU.  Every rank calls adb_peer_create, the 64-byte handles are exchanged
+ * by the host plumbing (any all-gather), every rank calls adb_peer_connect with all `world`
+ * handles in rank order.  adb_agg_combine_allreduce then folds this rank's `k` shard
+ * partials and exchanges the result with every peer inside ONE kernel (stores into the
+ * peers' mailboxes, acquire-spin on its own): d_out holds the table-wide aggregate on every
+ * rank.  Collective: all ranks must call it, in the same order.  A peer that does not
+ * arrive within 2 s yields count = -1 (and ADB_ERR_CUDA from the next adb_sync-ing call
+ * that reads it through h_out). */
+#define ADB_MAX_PEERS 16
+#define ADB_PEER_HANDLE_BYTES 64
+ADB_API adb_status adb_peer_create(int32_t world, int32_t rank, unsigned char *handle_out);
+ADB_API adb_status adb_peer_connect(const unsigned char *handles);
+ADB_API adb_status adb_agg_combine_allreduce(const adb_agg *d_parts, int32_t k, adb_agg *d_out,
+                                             adb_agg *h_out);
+ADB_API adb_status adb_peer_destroy(void);
+
 /* ---- element-wise add / sub -- replace add / sub, src/query.c:356-390 (int32, wraps) */
 ADB_API adb_status adb_add(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
                    int32_t *d_out);

@@ -36,7 +36,10 @@ def main():
     res = {"world": world}
     s = t.select("c1", -n // 20, n // 10)
     f = t.fetch("c2", s)
-    res["agg"] = t.aggregate(f)
+    res["agg"] = t.aggregate(f)                       # two NCCL all-reduces
+    ops.connect_peers(dist)
+    res["agg_peer"] = [t.aggregate(f) for _ in range(5)]      # one kernel over NVLink peer memory
+    res["agg_peer_empty"] = t.aggregate(f[:0])
     res["pos"] = t.gather_global(s.local, s.base).cpu().numpy()
     res["off"] = (s.offset, s.total, s.local.numel())
     lows = [-100, 0, n // 4, 7]
