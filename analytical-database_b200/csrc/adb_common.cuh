@@ -278,10 +278,9 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out,
 // Hash join (hash_join.cu).
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s);
-size_t hj_smem_bytes();
 uint32_t hj_smem_tuples();
-int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint32_t *pkeys,
-                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts,
+int launch_hj_partition(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1, const uint32_t *pkeys,
+                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts, uint32_t part_bits,
                         const unsigned long long *big_off, unsigned char *big_mem,
                         uint2 *gc_by_j, cudaStream_t s);
 int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,

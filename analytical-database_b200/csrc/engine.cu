@@ -735,13 +735,13 @@ static size_t radix_scratch_bytes(uint32_t n, int npass) {
     return npass == 0 ? one : (npass > 1 ? 4 : 2) * one;
 }
 
-// Runs `npass` stable passes over (keys, payload); payload starts as the row index.  Buffers
+// Runs `npass` stable passes over (keys, payload); payload starts as pay0, or the row index.  Buffers
 // come from the arena (reserve radix_scratch_bytes first).  The last pass writes to
 // (final_k, final_v) when given.  With npass == 0 the keys are copied and the payload is
 // left NULL (meaning identity).
 static adb_status radix_run(const uint32_t *keys_in, uint32_t n, const adb::RadixPass *passes,
                             int npass, uint32_t *final_k, uint32_t *final_v, uint32_t **keys_out,
-                            uint32_t **pay_out, int *launches) {
+                            uint32_t **pay_out, int *launches, const uint32_t *pay0 = nullptr) {
     *keys_out = nullptr;
     *pay_out = nullptr;
     if (adb_status s = ensure_radix_scratch(n)) return s;
@@ -757,7 +757,7 @@ static adb_status radix_run(const uint32_t *keys_in, uint32_t n, const adb::Radi
         k[i] = ARENA_TAKE(uint32_t, cnt);
         v[i] = ARENA_TAKE(uint32_t, cnt);
     }
-    const uint32_t *src_k = keys_in, *src_v = nullptr;
+    const uint32_t *src_k = keys_in, *src_v = pay0;       // pay0 == NULL: payload = row index
     int cur = 0;
     for (int p = 0; p < npass; ++p) {
         uint32_t *dk = k[cur], *dv = v[cur];
@@ -862,7 +862,7 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     }
     int launches = 0;
     StageTrace tr;
-    uint32_t part_bits = 0;
+    uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
     while (part_bits < 16 && (nb >> part_bits) > 1024) ++part_bits;
     const uint32_t num_parts = 1u << part_bits;
     adb::RadixPass pp_pass[2];
@@ -885,11 +885,11 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     // 1. build side: full stable sort on the bijective hash
     const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
     uint32_t *bk = nullptr, *bi = nullptr;
-    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, nullptr, nullptr, &bk, &bi, &launches)) return s;
-    j.build_pos_sorted = ARENA_TAKE(int32_t, nb);
-    launches += adb::launch_fetch(bp, reinterpret_cast<const int32_t *>(bi), nb, nullptr, 0,
-                                  j.build_pos_sorted, g.sm_count, g.stream);
-    tr.lap("build sort + position gather");
+    //    (the payload carried through the passes is the build position itself: no gather after)
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, nullptr, nullptr, &bk, &bi,
+                                 &launches, reinterpret_cast<const uint32_t *>(bp))) return s;
+    j.build_pos_sorted = reinterpret_cast<int32_t *>(bi);
+    tr.lap("build sort");
     // 2. probe side: stable partition on the top hash bits
     uint32_t *pk = nullptr, *pj = nullptr;
     if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(pv), np, pp_pass, npp, nullptr, nullptr, &pk, &pj, &launches)) return s;
@@ -927,8 +927,8 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     // 5. per-partition build + probe
     j.gc_by_j = ARENA_TAKE(uint2, np);
     j.off_by_j = ARENA_TAKE(uint32_t, np);
-    launches += adb::launch_hj_partition(bk, off1, pk, pj, off2, num_parts, big_off, big_mem,
-                                         j.gc_by_j, g.stream);
+    launches += adb::launch_hj_partition(bk, j.build_pos_sorted, off1, pk, pj, off2, num_parts, part_bits,
+                                         big_off, big_mem, j.gc_by_j, g.stream);
     tr.lap("per-partition build + probe");
     // 6. output offsets in probe-row order
     launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);

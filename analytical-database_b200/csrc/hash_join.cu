@@ -17,7 +17,8 @@
 //      CTA per partition: group leaders insert (key -> group start) into an open
 //      addressing table in shared memory (64-bit CAS, no sentinel key needed), group
 //      tails store the group end, then every probe row of the partition looks its key up
-//      and scatters {group start, match count} to slot j;
+//      and scatters {group start, match count} -- or, for a single match, {build position,
+//      1} -- to slot j;
 //   4. exclusive scan of the match counts in probe-row order = output offsets (radix.cu);
 //   5. expand: probe row j copies its group's positions to out1[off[j] ..] and its own
 //      position to out2[off[j] ..]; long groups (skewed keys) are spread over a warp.
@@ -87,39 +88,99 @@ __device__ __forceinline__ int hj_find(const HjTable &t, uint32_t key) {
     }
 }
 
+// ---- per-partition build + probe, shared-memory table ------------------------------------------
+// All keys of a partition share the top `part_bits` bits of h = key * kHashMul, and the
+// multiplier is a bijection, so the remaining low bits of h identify the key: the table
+// stores that 32-bit tag (+1, 0 = free) instead of the 64-bit {occupied, key} word, and one
+// packed word {group start within the partition : 16, group size : 16} per slot.  8 bytes
+// per slot instead of 16: 32 KB per CTA, 7 resident CTAs per SM instead of 3 (ncu r01k: the
+// 64 KB version ran at 35 % occupancy, long-scoreboard stall 23 per issue, 1.8 TB/s).
+// Build is ONE phase: every build row claims / finds its key's slot and adds 1 to the size;
+// the group leader (first row of the run of equal keys) adds its offset in the same atomic.
+__device__ __forceinline__ uint32_t hj_tag(uint32_t key, uint32_t part_bits) {
+    return (((key * kHashMul) << part_bits) >> part_bits) + 1u;       // part_bits >= 1: never wraps to 0
+}
+__device__ __forceinline__ uint32_t hj_tag_home(uint32_t tag) { return (tag * 0x85EBCA6Bu) >> 20; }   // 12 bits
+
 __global__ void __launch_bounds__(HJ_THREADS)
 hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
+                    const int32_t *__restrict__ bpos /* build positions in the same order */,
+                    const uint32_t *__restrict__ off1, const uint32_t *__restrict__ pkeys,
+                    const uint32_t *__restrict__ prows /* nullptr: identity */,
+                    const uint32_t *__restrict__ off2,
+                    const unsigned long long *__restrict__ big_off /* per partition, ~0 = smem */,
+                    uint32_t part_bits, uint2 *__restrict__ gc_by_j) {
+    __shared__ uint32_t s_tag[HJ_SLOTS];
+    __shared__ uint32_t s_gc[HJ_SLOTS];
+    static_assert(HJ_SLOTS == 4096, "hj_tag_home yields 12 bits");
+    const uint32_t p = blockIdx.x;
+    const uint32_t b0 = off1[p], b1 = off1[p + 1], q0 = off2[p], q1 = off2[p + 1];
+    if (q0 == q1) return;                                   // nobody probes this partition
+    if (b1 == b0) {
+        for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS)
+            gc_by_j[prows ? prows[u] : u] = make_uint2(0u, 0u);
+        return;
+    }
+    if (big_off && big_off[p] != ~0ull) return;             // hj_partition_big_kernel's job
+    for (uint32_t s = threadIdx.x; s < HJ_SLOTS; s += HJ_THREADS) { s_tag[s] = 0u; s_gc[s] = 0u; }
+    __syncthreads();
+    for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
+        const uint32_t k = bkeys[i];
+        const bool leader = i == b0 || bkeys[i - 1] != k;
+        const uint32_t tag = hj_tag(k, part_bits);
+        uint32_t s = hj_tag_home(tag);
+        while (true) {
+            const uint32_t cur = atomicCAS(&s_tag[s], 0u, tag);
+            if (cur == 0u || cur == tag) break;
+            s = (s + 1) & (HJ_SLOTS - 1);
+        }
+        atomicAdd(&s_gc[s], 1u + (leader ? (i - b0) << 16 : 0u));
+    }
+    __syncthreads();
+    for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
+        const uint32_t j = prows ? prows[u] : u;
+        const uint32_t tag = hj_tag(pkeys[u], part_bits);
+        uint32_t s = hj_tag_home(tag);
+        uint2 r = make_uint2(0u, 0u);
+        while (true) {
+            const uint32_t cur = s_tag[s];
+            if (cur == tag) {
+                // {group start, match count} leaves as ONE 8-byte scattered store per probe
+                // row.  A single match (the common case) is resolved here, where the
+                // partition's build positions are a contiguous, cache-resident run: the
+                // expansion then has no random gather left for it.
+                const uint32_t w = s_gc[s], c = w & 0xFFFFu, gs = b0 + (w >> 16);
+                r = make_uint2(c == 1 ? (uint32_t)bpos[gs] : gs, c);
+                break;
+            }
+            if (cur == 0u) break;
+            s = (s + 1) & (HJ_SLOTS - 1);
+        }
+        gc_by_j[j] = r;
+    }
+}
+
+// Partitions too large for the shared-memory table (heavy skew): the same build / probe on a
+// 64-bit-keyed table in global memory, two build phases (leaders, then tails).
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_partition_big_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
+                    const int32_t *__restrict__ bpos /* build positions in the same order */,
                     const uint32_t *__restrict__ off1, const uint32_t *__restrict__ pkeys,
                     const uint32_t *__restrict__ prows /* nullptr: identity */,
                     const uint32_t *__restrict__ off2,
                     const unsigned long long *__restrict__ big_off /* per partition, ~0 = smem */,
                     unsigned char *__restrict__ big_mem, uint2 *__restrict__ gc_by_j) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t p = blockIdx.x;
+    if (big_off[p] == ~0ull) return;                        // fits shared memory: done there
     const uint32_t b0 = off1[p], b1 = off1[p + 1], q0 = off2[p], q1 = off2[p + 1];
     if (q0 == q1) return;                                   // nobody probes this partition
     const uint32_t nb = b1 - b0;
-    if (nb == 0) {
-        for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
-            const uint32_t j = prows ? prows[u] : u;
-            gc_by_j[j] = make_uint2(0u, 0u);
-        }
-        return;
-    }
     HjTable t;
-    const bool big = big_off && big_off[p] != ~0ull;
-    if (!big) {
-        t.slots = HJ_SLOTS;
-        t.key = reinterpret_cast<unsigned long long *>(smem);
-        t.gs = reinterpret_cast<uint32_t *>(smem + 8 * HJ_SLOTS);
-        t.ge = t.gs + HJ_SLOTS;
-    } else {
-        t.slots = 2 * nb;
-        unsigned char *base = big_mem + big_off[p];
-        t.key = reinterpret_cast<unsigned long long *>(base);
-        t.gs = reinterpret_cast<uint32_t *>(base + 8ull * t.slots);
-        t.ge = t.gs + t.slots;
-    }
+    t.slots = 2 * nb;
+    unsigned char *base = big_mem + big_off[p];
+    t.key = reinterpret_cast<unsigned long long *>(base);
+    t.gs = reinterpret_cast<uint32_t *>(base + 8ull * t.slots);
+    t.ge = t.gs + t.slots;
     for (uint32_t s = threadIdx.x; s < t.slots; s += HJ_THREADS) t.key[s] = 0ull;
     __syncthreads();
     // group leaders claim a slot and record where their group starts
@@ -137,8 +198,16 @@ hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
     for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
         const uint32_t j = prows ? prows[u] : u;
         const int s = hj_find(t, pkeys[u]);
-        // {group start, match count} leaves as ONE 8-byte scattered store per probe row
-        gc_by_j[j] = s >= 0 ? make_uint2(t.gs[s], t.ge[s] - t.gs[s]) : make_uint2(0u, 0u);
+        // {group start, match count} leaves as ONE 8-byte scattered store per probe row.  A
+        // single match (the common case) is resolved here, where the partition's build
+        // positions are a contiguous, cache-resident run: the expansion then has no random
+        // gather left for it.
+        uint2 r = make_uint2(0u, 0u);
+        if (s >= 0) {
+            const uint32_t gs = t.gs[s], c = t.ge[s] - gs;
+            r = make_uint2(c == 1 ? (uint32_t)bpos[gs] : gs, c);
+        }
+        gc_by_j[j] = r;
     }
 }
 
@@ -160,7 +229,10 @@ hj_expand_kernel(const uint2 *__restrict__ gc_by_j,
             cnt = gc.y;
             if (cnt) { gs = gc.x; off = off_by_j[j]; pp = probe_pos[j]; }
         }
-        if (cnt && cnt <= 8) {
+        if (cnt == 1) {                                  // gs already is the build position
+            out_build[off] = (int32_t)gs;
+            out_probe[off] = pp;
+        } else if (cnt && cnt <= 8) {
             for (uint32_t r = 0; r < cnt; ++r) {
                 out_build[off + r] = build_pos_sorted[gs + r];
                 out_probe[off + r] = pp;
@@ -188,22 +260,18 @@ int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint3
     return 1;
 }
 
-size_t hj_smem_bytes() { return 16ull * HJ_SLOTS; }
 uint32_t hj_smem_tuples() { return HJ_SMEM_TUPLES; }
 
-int launch_hj_partition(const uint32_t *bkeys, const uint32_t *off1, const uint32_t *pkeys,
-                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts,
+int launch_hj_partition(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1, const uint32_t *pkeys,
+                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts, uint32_t part_bits,
                         const unsigned long long *big_off, unsigned char *big_mem,
                         uint2 *gc_by_j, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(hj_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)hj_smem_bytes());
-        attr_set = true;
-    }
-    hj_partition_kernel<<<num_parts, HJ_THREADS, hj_smem_bytes(), s>>>(
-        bkeys, off1, pkeys, prows, off2, big_off, big_mem, gc_by_j);
-    return 1;
+    hj_partition_kernel<<<num_parts, HJ_THREADS, 0, s>>>(bkeys, bpos, off1, pkeys, prows, off2, big_off,
+                                                         part_bits, gc_by_j);
+    if (!big_off) return 1;
+    hj_partition_big_kernel<<<num_parts, HJ_THREADS, 0, s>>>(bkeys, bpos, off1, pkeys, prows, off2, big_off,
+                                                             big_mem, gc_by_j);
+    return 2;
 }
 
 int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,

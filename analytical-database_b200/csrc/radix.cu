@@ -87,6 +87,9 @@ __global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals, uint3
 constexpr int RX_KPT = 16;
 constexpr int RX_TILE = RX_THREADS * RX_KPT;             // 4096 rows
 
+// (r01k tried finding the peers through a per-warp shared-memory table -- atomicOr of the
+// lane bit, sync, read back, leader clears -- instead of one ballot per digit bit: 20.4 ms
+// against 19.6 ms for the 500 M-key sort, so the ballots stayed.)
 __global__ void __launch_bounds__(RX_THREADS)
 rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
                   uint32_t rows_per_cta, RadixPass p, const uint32_t *__restrict__ hist,
