@@ -278,11 +278,16 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out,
 // Hash join (hash_join.cu).
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s);
+int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff, cudaStream_t s);
 uint32_t hj_smem_tuples();
-int launch_hj_partition(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1, const uint32_t *pkeys,
-                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts, uint32_t part_bits,
-                        const unsigned long long *big_off, unsigned char *big_mem,
-                        uint2 *gc_by_j, cudaStream_t s);
+uint32_t hj_smem_slots();
+// toff: num_parts + 1 slot offsets (capacity of partition p = toff[p+1] - toff[p], 0 or a
+// power of two); table: toff[num_parts] 16-byte slots
+int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,
+                          const unsigned long long *toff, uint32_t num_parts, uint32_t part_bits,
+                          uint4 *table, cudaStream_t s);
+int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const unsigned long long *toff,
+                    uint32_t part_bits, const uint4 *table, uint2 *gc_by_j, int sm_count, cudaStream_t s);
 int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
                      int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);

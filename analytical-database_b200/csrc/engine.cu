@@ -67,6 +67,9 @@ struct Engine {
     // differently sized multi-hundred-MB blocks made the pool re-map memory on every join
     unsigned char *arena = nullptr;
     size_t arena_cap = 0, arena_used = 0;
+    // join tables: one open-addressing table per build partition, 16-byte slots (grow-only)
+    void *hj_table = nullptr;
+    unsigned long long hj_table_slots = 0;
     // aggregate exchange over peer memory (adb_peer_*): own mailbox + the peers' mappings
     adb::PeerRecord *peer_box = nullptr;
     adb::PeerBoxes peer_boxes{};
@@ -231,6 +234,7 @@ adb_status adb_shutdown(void) {
     cudaFree(g.rx_base);
     cudaFree(g.sc_sums);
     cudaFree(g.arena);
+    cudaFree(g.hj_table);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     peer_close();
@@ -865,78 +869,58 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
     while (part_bits < 16 && (nb >> part_bits) > 1024) ++part_bits;
     const uint32_t num_parts = 1u << part_bits;
-    adb::RadixPass pp_pass[2];
-    int npp = 0;
-    if (part_bits > 8) {
-        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits - 8, 1};
-        pp_pass[npp++] = adb::RadixPass{24, 8, 1};
-    } else if (part_bits > 0) {
-        pp_pass[npp++] = adb::RadixPass{32 - (int)part_bits, (int)part_bits, 1};
-    }
     const size_t pbytes = (size_t)(num_parts + 1) * 4;
-    if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)nb * 4) +
-                                     radix_scratch_bytes(np, npp) + arena_round((size_t)np * 8) +
-                                     arena_round((size_t)np * 4) + 2 * arena_round(pbytes) + 4096))
+    if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
+                                     arena_round((size_t)np * 4) + arena_round(pbytes) +
+                                     arena_round((size_t)(num_parts + 1) * 8) + 4096))
         return s;
     auto &j = g.join;
     j.swapped = swapped;
     j.n_probe = np;
     j.probe_pos = pp;
-    // 1. build side: full stable sort on the bijective hash
+    // 1. build side: full stable sort on the bijective hash; the payload carried through the
+    //    passes is the build position itself, so nothing is gathered afterwards
     const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
     uint32_t *bk = nullptr, *bi = nullptr;
-    //    (the payload carried through the passes is the build position itself: no gather after)
     if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, nullptr, nullptr, &bk, &bi,
                                  &launches, reinterpret_cast<const uint32_t *>(bp))) return s;
     j.build_pos_sorted = reinterpret_cast<int32_t *>(bi);
     tr.lap("build sort");
-    // 2. probe side: stable partition on the top hash bits
-    uint32_t *pk = nullptr, *pj = nullptr;
-    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(pv), np, pp_pass, npp, nullptr, nullptr, &pk, &pj, &launches)) return s;
-    tr.lap("probe partition");
-    // 3. partition boundaries (num_parts + 1 entries each)
-    uint32_t *off1 = ARENA_TAKE(uint32_t, num_parts + 1), *off2 = ARENA_TAKE(uint32_t, num_parts + 1);
+    // 2. partition boundaries -> table geometry: partition p gets a power-of-two slot range
+    //    holding its rows at <= 80 % load (<= 4096 slots: built in shared memory)
+    uint32_t *off1 = ARENA_TAKE(uint32_t, num_parts + 1);
+    unsigned long long *toff = ARENA_TAKE(unsigned long long, num_parts + 1);
     int64_t *tot = ARENA_TAKE(int64_t, 2);
     launches += adb::launch_hj_bounds(bk, nb, part_bits, num_parts, off1, g.stream);
-    launches += adb::launch_hj_bounds(pk, np, part_bits, num_parts, off2, g.stream);
-    // 4. partitions that do not fit the shared-memory table get a table in global memory
-    std::vector<uint32_t> h_off1(num_parts + 1);
-    CU(cudaMemcpyAsync(h_off1.data(), off1, pbytes, cudaMemcpyDeviceToHost, g.stream));
+    launches += adb::launch_hj_geometry(off1, num_parts, toff, g.stream);
+    unsigned long long slots = 0;
+    CU(cudaMemcpyAsync(&slots, toff + num_parts, sizeof slots, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
-    tr.lap("partition boundaries");
-    unsigned long long *big_off = nullptr;
-    unsigned char *big_mem = nullptr;
-    {
-        std::vector<unsigned long long> h_big(num_parts, ~0ull);
-        unsigned long long need = 0;
-        for (uint32_t p = 0; p < num_parts; ++p) {
-            const uint32_t sz = h_off1[p + 1] - h_off1[p];
-            if (sz > adb::hj_smem_tuples()) {
-                h_big[p] = need;
-                need += ((16ull * 2 * sz) + 255) & ~255ull;
-            }
-        }
-        if (need) {
-            CU(cudaMallocAsync(&big_off, num_parts * sizeof(unsigned long long), g.stream));
-            cudaError_t e = cudaMallocAsync(&big_mem, need, g.stream);
-            if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join: %llu bytes for skewed partitions: %s", need, cudaGetErrorString(e)); }
-            CU(cudaMemcpyAsync(big_off, h_big.data(), num_parts * sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream));
-            CU(cudaStreamSynchronize(g.stream));
-        }
+    if (slots > g.hj_table_slots) {
+        if (g.hj_table) CU(cudaFree(g.hj_table));
+        g.hj_table = nullptr;
+        g.hj_table_slots = 0;
+        const unsigned long long want = slots + slots / 8 + 4096;
+        cudaError_t e = cudaMalloc(&g.hj_table, want * 16);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join tables (%llu slots): %s", want, cudaGetErrorString(e)); }
+        g.hj_table_slots = want;
     }
-    // 5. per-partition build + probe
+    tr.lap("partition boundaries");
+    // 3. one table per partition
+    launches += adb::launch_hj_table_build(bk, j.build_pos_sorted, off1, toff, num_parts, part_bits,
+                                           static_cast<uint4 *>(g.hj_table), g.stream);
+    tr.lap("per-partition tables");
+    // 4. probe in row order
     j.gc_by_j = ARENA_TAKE(uint2, np);
     j.off_by_j = ARENA_TAKE(uint32_t, np);
-    launches += adb::launch_hj_partition(bk, j.build_pos_sorted, off1, pk, pj, off2, num_parts, part_bits,
-                                         big_off, big_mem, j.gc_by_j, g.stream);
-    tr.lap("per-partition build + probe");
-    // 6. output offsets in probe-row order
+    launches += adb::launch_hj_probe(reinterpret_cast<const uint32_t *>(pv), np, toff, part_bits,
+                                     static_cast<const uint4 *>(g.hj_table), j.gc_by_j, g.sm_count, g.stream);
+    tr.lap("probe");
+    // 5. output offsets in probe-row order
     launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
     CU(cudaMemcpyAsync(&j.matches, tot, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
     tr.lap("output offsets");
-    if (big_off) CU(cudaFreeAsync(big_off, g.stream));
-    if (big_mem) CU(cudaFreeAsync(big_mem, g.stream));
     if (adb_status s = after_launch("join_count", launches)) return s;
     if (j.matches >= (int64_t)1 << 31) {
         const long long m = j.matches;

@@ -7,23 +7,21 @@
 // probe row all stored positions of its key in insertion order.  The output is therefore
 // probe-major, build-insertion order inside a key -- and must be reproduced exactly.
 //
-// GPU formulation (shared-memory-partitioned hash build and probe):
-//   1. build side: stable LSD radix sort on h = key * 0x9E3779B1 (radix.cu).  The odd
-//      multiplier is a bijection on 32 bits, so equal h <=> equal key: one sort both groups
-//      equal keys (insertion order kept inside a group: the sort is stable) and orders
-//      the groups by partition id = top bits of h;
-//   2. probe side: stable radix partition on the same top bits, payload = probe row j;
-//   3. partition boundaries by binary search (both sides are ordered by partition id); one
-//      CTA per partition: group leaders insert (key -> group start) into an open
-//      addressing table in shared memory (64-bit CAS, no sentinel key needed), group
-//      tails store the group end, then every probe row of the partition looks its key up
-//      and scatters {group start, match count} -- or, for a single match, {build position,
-//      1} -- to slot j;
+// GPU formulation (shared-memory-partitioned hash build, probe in row order):
+//   1. build side: stable LSD radix sort on h = key * 0x9E3779B1 (radix.cu), payload = the
+//      build position.  The odd multiplier is a bijection on 32 bits, so equal h <=> equal
+//      key: one sort both groups equal keys (insertion order kept inside a group: the sort
+//      is stable) and orders the groups by partition id = top bits of h;
+//   2. partition boundaries by binary search; one CTA per partition builds an open
+//      addressing table {key tag -> group start / single build position, group size} in
+//      shared memory and streams it to the partition's slot range in global memory;
+//   3. probe rows, in their original order, look their key up in their partition's table:
+//      {group start or build position, match count} per probe row, stored coalesced;
 //   4. exclusive scan of the match counts in probe-row order = output offsets (radix.cu);
 //   5. expand: probe row j copies its group's positions to out1[off[j] ..] and its own
 //      position to out2[off[j] ..]; long groups (skewed keys) are spread over a warp.
-// Partitions too large for the shared-memory table (heavy skew) run the same code on a
-// table in global memory.
+// Partitions too large for the shared-memory table (heavy skew) build directly in their
+// global slots.
 #include "adb_common.cuh"
 
 namespace adb {
@@ -38,8 +36,7 @@ __device__ __forceinline__ uint32_t hj_pid(uint32_t key, uint32_t part_bits) {
 }
 
 // ---- partition boundaries -----------------------------------------------------------------
-// Both inputs arrive ordered by partition id (the build side is sorted on the whole hash, the
-// probe side stably partitioned on its top bits), so partition p starts at the first row
+// The build side arrives sorted on the whole hash, so partition p starts at the first row
 // whose id is >= p: one binary search per partition instead of one global atomic per row.
 __global__ void hj_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t part_bits,
                                  uint32_t num_parts, uint32_t *__restrict__ off) {
@@ -53,159 +50,161 @@ __global__ void hj_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, 
     off[p] = lo;                                  // off[num_parts] == n
 }
 
-// ---- per-partition build + probe ----------------------------------------------------------------
-struct HjTable {
-    unsigned long long *key;      // (1 << 32) | key when occupied, 0 when free
-    uint32_t *gs;                 // group start (index into the sorted build arrays)
-    uint32_t *ge;                 // group end
-    uint32_t slots;               // power of two for shared memory, arbitrary for global
-};
-
-__device__ __forceinline__ uint32_t hj_home(uint32_t key, uint32_t slots) {
-    // the low hash bits are independent of the (top-bit) partition id
-    const uint32_t h = (key * kHashMul) ^ ((key * kHashMul) >> 15);
-    return (h * 0x85EBCA6Bu >> 7) % slots;
-}
-
-__device__ __forceinline__ uint32_t hj_insert(const HjTable &t, uint32_t key) {
-    const unsigned long long want = (1ull << 32) | key;
-    uint32_t s = hj_home(key, t.slots);
-    while (true) {
-        const unsigned long long cur = atomicCAS(&t.key[s], 0ull, want);
-        if (cur == 0ull || cur == want) return s;
-        s = s + 1 == t.slots ? 0 : s + 1;
+// ---- table geometry ------------------------------------------------------------------------------
+// Partition p gets a power-of-two slot range holding its rows at <= 80 % load (0 slots when it
+// is empty); toff = exclusive scan of the capacities, toff[num_parts] = total.  One CTA.
+__global__ void __launch_bounds__(1024)
+hj_geometry_kernel(const uint32_t *__restrict__ off1, uint32_t num_parts,
+                   unsigned long long *__restrict__ toff) {
+    __shared__ unsigned long long s_w[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0;
+    for (uint32_t base = 0; base < num_parts; base += 1024) {
+        const uint32_t p = base + threadIdx.x;
+        unsigned long long cap = 0;
+        if (p < num_parts) {
+            const unsigned long long sz = off1[p + 1] - off1[p];
+            if (sz) {
+                cap = 16;
+                while (cap < sz + sz / 4 + 1) cap <<= 1;
+            }
+        }
+        unsigned long long incl = cap;
+#pragma unroll
+        for (int d = 1; d < kWarp; d <<= 1) {
+            const unsigned long long y = __shfl_up_sync(kFull, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        unsigned long long wexcl = 0, tot = 0;
+        for (uint32_t w = 0; w < 32; ++w) {
+            if (w < warp) wexcl += s_w[w];
+            tot += s_w[w];
+        }
+        if (p < num_parts) toff[p] = carry + wexcl + incl - cap;
+        carry += tot;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) toff[num_parts] = carry;
 }
 
-__device__ __forceinline__ int hj_find(const HjTable &t, uint32_t key) {
-    const unsigned long long want = (1ull << 32) | key;
-    uint32_t s = hj_home(key, t.slots);
-    while (true) {
-        const unsigned long long cur = t.key[s];
-        if (cur == want) return (int)s;
-        if (cur == 0ull) return -1;
-        s = s + 1 == t.slots ? 0 : s + 1;
-    }
-}
-
-// ---- per-partition build + probe, shared-memory table ------------------------------------------
+// ---- per-partition tables ---------------------------------------------------------------------
 // All keys of a partition share the top `part_bits` bits of h = key * kHashMul, and the
-// multiplier is a bijection, so the remaining low bits of h identify the key: the table
-// stores that 32-bit tag (+1, 0 = free) instead of the 64-bit {occupied, key} word, and one
-// packed word {group start within the partition : 16, group size : 16} per slot.  8 bytes
-// per slot instead of 16: 32 KB per CTA, 7 resident CTAs per SM instead of 3 (ncu r01k: the
-// 64 KB version ran at 35 % occupancy, long-scoreboard stall 23 per issue, 1.8 TB/s).
-// Build is ONE phase: every build row claims / finds its key's slot and adds 1 to the size;
-// the group leader (first row of the run of equal keys) adds its offset in the same atomic.
+// multiplier is a bijection, so the remaining low bits of h identify the key: a slot stores
+// that 32-bit tag (+1, 0 = free), the group's size, and -- for a single-row group, the common
+// case -- the build position itself, else the group's start in the sorted build arrays.
+//
+// r01k history.  (1) One CTA per partition built a shared-memory table and probed it with the
+// partition's probe rows (probe side radix-partitioned too), scattering {start, count} to slot
+// j: ncu showed 7.9 GB of DRAM traffic at 1.8 TB/s for 100 M probes -- every 8-byte store is a
+// 32-byte read-modify-write at a random address (3.1 GB of fill reads, 3.2 GB of writes), and
+// shrinking the table from 64 KB to 32 KB per CTA (35 % -> 80 % occupancy) changed nothing:
+// the random-access rate of HBM was the limit.  (2) Now the tables are written to global
+// memory (16-byte slots, one coalesced burst per partition) and the probe side is walked in
+// its ORIGINAL order: one random 16-byte read per probe row, every store coalesced, no probe
+// partitioning passes, no scatter.
+struct HjSlot {                       // 16 bytes, read with one ld.global.v4
+    uint32_t tag;                     // hj_tag(key), 0 = free
+    uint32_t val;                     // cnt == 1: build position; else group start
+    uint32_t cnt;                     // group size
+    uint32_t pad;
+};
+static_assert(sizeof(HjSlot) == 16, "slot layout");
+
 __device__ __forceinline__ uint32_t hj_tag(uint32_t key, uint32_t part_bits) {
     return (((key * kHashMul) << part_bits) >> part_bits) + 1u;       // part_bits >= 1: never wraps to 0
 }
-__device__ __forceinline__ uint32_t hj_tag_home(uint32_t tag) { return (tag * 0x85EBCA6Bu) >> 20; }   // 12 bits
+// well-mixed 32 bits of the tag; the caller masks with capacity - 1 (a power of two)
+__device__ __forceinline__ uint32_t hj_mix(uint32_t tag) {
+    return (uint32_t)(((unsigned long long)tag * 0x9E3779B97F4A7C15ull) >> 29);
+}
 
+// One CTA per partition.  Partitions of up to HJ_SMEM_TUPLES build rows (capacity <= HJ_SLOTS)
+// build in shared memory in ONE phase -- every build row claims / finds its key's slot and
+// adds 1 to the size, the group leader (first row of the run of equal keys) adds its offset
+// in the same atomic -- and stream the finished table out.  Larger partitions (heavy skew)
+// run the same steps directly on their global slots.
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_partition_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
-                    const int32_t *__restrict__ bpos /* build positions in the same order */,
-                    const uint32_t *__restrict__ off1, const uint32_t *__restrict__ pkeys,
-                    const uint32_t *__restrict__ prows /* nullptr: identity */,
-                    const uint32_t *__restrict__ off2,
-                    const unsigned long long *__restrict__ big_off /* per partition, ~0 = smem */,
-                    uint32_t part_bits, uint2 *__restrict__ gc_by_j) {
+hj_table_build_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
+                      const int32_t *__restrict__ bpos /* build positions in the same order */,
+                      const uint32_t *__restrict__ off1, const unsigned long long *__restrict__ toff,
+                      uint32_t part_bits, uint4 *__restrict__ table) {
     __shared__ uint32_t s_tag[HJ_SLOTS];
-    __shared__ uint32_t s_gc[HJ_SLOTS];
-    static_assert(HJ_SLOTS == 4096, "hj_tag_home yields 12 bits");
+    __shared__ uint32_t s_gc[HJ_SLOTS];                 // {group start within the partition : 16, size : 16}
     const uint32_t p = blockIdx.x;
-    const uint32_t b0 = off1[p], b1 = off1[p + 1], q0 = off2[p], q1 = off2[p + 1];
-    if (q0 == q1) return;                                   // nobody probes this partition
-    if (b1 == b0) {
-        for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS)
-            gc_by_j[prows ? prows[u] : u] = make_uint2(0u, 0u);
+    const uint32_t b0 = off1[p], b1 = off1[p + 1];
+    if (b1 == b0) return;                               // capacity 0: nothing to write
+    const unsigned long long t0 = toff[p], cap64 = toff[p + 1] - t0;
+    if (cap64 <= HJ_SLOTS) {
+        const uint32_t cap = (uint32_t)cap64, mask = cap - 1;
+        for (uint32_t s = threadIdx.x; s < cap; s += HJ_THREADS) { s_tag[s] = 0u; s_gc[s] = 0u; }
+        __syncthreads();
+        for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
+            const uint32_t k = bkeys[i];
+            const bool leader = i == b0 || bkeys[i - 1] != k;
+            const uint32_t tag = hj_tag(k, part_bits);
+            uint32_t s = hj_mix(tag) & mask;
+            while (true) {
+                const uint32_t cur = atomicCAS(&s_tag[s], 0u, tag);
+                if (cur == 0u || cur == tag) break;
+                s = (s + 1) & mask;
+            }
+            atomicAdd(&s_gc[s], 1u + (leader ? (i - b0) << 16 : 0u));
+        }
+        __syncthreads();
+        uint4 *__restrict__ out = table + t0;
+        for (uint32_t s = threadIdx.x; s < cap; s += HJ_THREADS) {
+            const uint32_t w = s_gc[s], c = w & 0xFFFFu, gs = b0 + (w >> 16);
+            out[s] = make_uint4(s_tag[s], c == 1 ? (uint32_t)bpos[gs] : gs, c, 0u);
+        }
         return;
     }
-    if (big_off && big_off[p] != ~0ull) return;             // hj_partition_big_kernel's job
-    for (uint32_t s = threadIdx.x; s < HJ_SLOTS; s += HJ_THREADS) { s_tag[s] = 0u; s_gc[s] = 0u; }
+    uint32_t *T = reinterpret_cast<uint32_t *>(table + t0);          // 4 words per slot
+    const unsigned long long mask = cap64 - 1;
+    for (unsigned long long s = threadIdx.x; s < cap64; s += HJ_THREADS)
+        reinterpret_cast<uint4 *>(T)[s] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
         const uint32_t k = bkeys[i];
         const bool leader = i == b0 || bkeys[i - 1] != k;
         const uint32_t tag = hj_tag(k, part_bits);
-        uint32_t s = hj_tag_home(tag);
+        unsigned long long s = hj_mix(tag) & mask;
         while (true) {
-            const uint32_t cur = atomicCAS(&s_tag[s], 0u, tag);
+            const uint32_t cur = atomicCAS(&T[4 * s], 0u, tag);
             if (cur == 0u || cur == tag) break;
-            s = (s + 1) & (HJ_SLOTS - 1);
+            s = (s + 1) & mask;
         }
-        atomicAdd(&s_gc[s], 1u + (leader ? (i - b0) << 16 : 0u));
+        atomicAdd(&T[4 * s + 2], 1u);
+        if (leader) T[4 * s + 1] = i;                    // only the leader writes this word
     }
     __syncthreads();
-    for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
-        const uint32_t j = prows ? prows[u] : u;
-        const uint32_t tag = hj_tag(pkeys[u], part_bits);
-        uint32_t s = hj_tag_home(tag);
-        uint2 r = make_uint2(0u, 0u);
-        while (true) {
-            const uint32_t cur = s_tag[s];
-            if (cur == tag) {
-                // {group start, match count} leaves as ONE 8-byte scattered store per probe
-                // row.  A single match (the common case) is resolved here, where the
-                // partition's build positions are a contiguous, cache-resident run: the
-                // expansion then has no random gather left for it.
-                const uint32_t w = s_gc[s], c = w & 0xFFFFu, gs = b0 + (w >> 16);
-                r = make_uint2(c == 1 ? (uint32_t)bpos[gs] : gs, c);
-                break;
-            }
-            if (cur == 0u) break;
-            s = (s + 1) & (HJ_SLOTS - 1);
-        }
-        gc_by_j[j] = r;
-    }
+    for (unsigned long long s = threadIdx.x; s < cap64; s += HJ_THREADS)
+        if (T[4 * s + 2] == 1u) T[4 * s + 1] = (uint32_t)bpos[T[4 * s + 1]];
 }
 
-// Partitions too large for the shared-memory table (heavy skew): the same build / probe on a
-// 64-bit-keyed table in global memory, two build phases (leaders, then tails).
+// Probe side in its original row order: one random 16-byte slot read per row (linear probing
+// almost always ends inside the same 128-byte line), results stored coalesced.
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_partition_big_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
-                    const int32_t *__restrict__ bpos /* build positions in the same order */,
-                    const uint32_t *__restrict__ off1, const uint32_t *__restrict__ pkeys,
-                    const uint32_t *__restrict__ prows /* nullptr: identity */,
-                    const uint32_t *__restrict__ off2,
-                    const unsigned long long *__restrict__ big_off /* per partition, ~0 = smem */,
-                    unsigned char *__restrict__ big_mem, uint2 *__restrict__ gc_by_j) {
-    const uint32_t p = blockIdx.x;
-    if (big_off[p] == ~0ull) return;                        // fits shared memory: done there
-    const uint32_t b0 = off1[p], b1 = off1[p + 1], q0 = off2[p], q1 = off2[p + 1];
-    if (q0 == q1) return;                                   // nobody probes this partition
-    const uint32_t nb = b1 - b0;
-    HjTable t;
-    t.slots = 2 * nb;
-    unsigned char *base = big_mem + big_off[p];
-    t.key = reinterpret_cast<unsigned long long *>(base);
-    t.gs = reinterpret_cast<uint32_t *>(base + 8ull * t.slots);
-    t.ge = t.gs + t.slots;
-    for (uint32_t s = threadIdx.x; s < t.slots; s += HJ_THREADS) t.key[s] = 0ull;
-    __syncthreads();
-    // group leaders claim a slot and record where their group starts
-    for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
-        const uint32_t k = bkeys[i];
-        if (i == b0 || bkeys[i - 1] != k) t.gs[hj_insert(t, k)] = i;
-    }
-    __syncthreads();
-    // group tails record where it ends
-    for (uint32_t i = b0 + threadIdx.x; i < b1; i += HJ_THREADS) {
-        const uint32_t k = bkeys[i];
-        if (i + 1 == b1 || bkeys[i + 1] != k) t.ge[hj_find(t, k)] = i + 1;
-    }
-    __syncthreads();
-    for (uint32_t u = q0 + threadIdx.x; u < q1; u += HJ_THREADS) {
-        const uint32_t j = prows ? prows[u] : u;
-        const int s = hj_find(t, pkeys[u]);
-        // {group start, match count} leaves as ONE 8-byte scattered store per probe row.  A
-        // single match (the common case) is resolved here, where the partition's build
-        // positions are a contiguous, cache-resident run: the expansion then has no random
-        // gather left for it.
+hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe,
+                const unsigned long long *__restrict__ toff, uint32_t part_bits,
+                const uint4 *__restrict__ table, uint2 *__restrict__ gc_by_j) {
+    const uint32_t stride = gridDim.x * HJ_THREADS;
+    for (uint32_t j = blockIdx.x * HJ_THREADS + threadIdx.x; j < n_probe; j += stride) {
+        const uint32_t k = (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(pkeys) + j);
+        const uint32_t p = hj_pid(k, part_bits);
+        const unsigned long long t0 = toff[p], cap = toff[p + 1] - t0;
         uint2 r = make_uint2(0u, 0u);
-        if (s >= 0) {
-            const uint32_t gs = t.gs[s], c = t.ge[s] - gs;
-            r = make_uint2(c == 1 ? (uint32_t)bpos[gs] : gs, c);
+        if (cap) {
+            const uint32_t tag = hj_tag(k, part_bits);
+            const unsigned long long mask = cap - 1;
+            unsigned long long s = hj_mix(tag) & mask;
+            while (true) {
+                const uint4 sl = __ldg(table + t0 + s);
+                if (sl.x == tag) { r = make_uint2(sl.y, sl.z); break; }
+                if (sl.x == 0u) break;
+                s = (s + 1) & mask;
+            }
         }
         gc_by_j[j] = r;
     }
@@ -260,18 +259,28 @@ int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint3
     return 1;
 }
 
-uint32_t hj_smem_tuples() { return HJ_SMEM_TUPLES; }
+int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff, cudaStream_t s) {
+    hj_geometry_kernel<<<1, 1024, 0, s>>>(off1, num_parts, toff);
+    return 1;
+}
 
-int launch_hj_partition(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1, const uint32_t *pkeys,
-                        const uint32_t *prows, const uint32_t *off2, uint32_t num_parts, uint32_t part_bits,
-                        const unsigned long long *big_off, unsigned char *big_mem,
-                        uint2 *gc_by_j, cudaStream_t s) {
-    hj_partition_kernel<<<num_parts, HJ_THREADS, 0, s>>>(bkeys, bpos, off1, pkeys, prows, off2, big_off,
-                                                         part_bits, gc_by_j);
-    if (!big_off) return 1;
-    hj_partition_big_kernel<<<num_parts, HJ_THREADS, 0, s>>>(bkeys, bpos, off1, pkeys, prows, off2, big_off,
-                                                             big_mem, gc_by_j);
-    return 2;
+uint32_t hj_smem_tuples() { return HJ_SMEM_TUPLES; }
+uint32_t hj_smem_slots() { return HJ_SLOTS; }
+
+int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,
+                          const unsigned long long *toff, uint32_t num_parts, uint32_t part_bits,
+                          uint4 *table, cudaStream_t s) {
+    hj_table_build_kernel<<<num_parts, HJ_THREADS, 0, s>>>(bkeys, bpos, off1, toff, part_bits, table);
+    return 1;
+}
+
+int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const unsigned long long *toff,
+                    uint32_t part_bits, const uint4 *table, uint2 *gc_by_j, int sm_count, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
+    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
+    hj_probe_kernel<<<blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, toff, part_bits, table, gc_by_j);
+    return 1;
 }
 
 int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
