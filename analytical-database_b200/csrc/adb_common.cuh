@@ -275,6 +275,18 @@ uint32_t scan_ctas(uint32_t n, int sm_count);
 int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out, uint32_t n,
                           unsigned long long *sums, int64_t *total, int sm_count, cudaStream_t s);
 
+// Bulk CSV load (csv_load.cu).
+uint32_t csv_blocks(size_t bytes);
+int launch_csv_count(const unsigned char *text, size_t bytes, uint32_t *block_counts, cudaStream_t s);
+int launch_csv_index(const unsigned char *text, size_t bytes, const uint32_t *block_base,
+                     unsigned long long *line_end, cudaStream_t s);
+int launch_csv_parse(const unsigned char *text, size_t bytes, const unsigned long long *line_end,
+                     unsigned long long n_newlines, uint32_t skip_lines, unsigned long long rows,
+                     uint32_t n_cols, int32_t *const *cols, unsigned char *n_fields, uint32_t *flags,
+                     cudaStream_t s);
+int launch_csv_fixup(unsigned long long rows, uint32_t n_cols, int32_t *const *cols,
+                     const unsigned char *n_fields, cudaStream_t s);
+
 // Hash join (hash_join.cu).
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s);

@@ -4,7 +4,9 @@
 // There is deliberately no CPU path in this file: if no CUDA device can be opened,
 // adb_init() fails and every operator reports ADB_ERR_NOT_INITIALISED.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdarg>
 #include <vector>
 #include <cstdio>
@@ -70,6 +72,28 @@ struct Engine {
     // join tables: one open-addressing table per build partition, 16-byte slots (grow-only)
     void *hj_table = nullptr;
     unsigned long long hj_table_slots = 0;
+    // bulk CSV load state (adb_csv_index -> adb_csv_parse); scratch is grow-only
+    struct CsvState {
+        const unsigned char *text = nullptr;
+        size_t bytes = 0;
+        unsigned long long newlines = 0, rows = 0;
+        uint32_t skip = 0;
+        bool ready = false;
+        uint32_t *block_counts = nullptr, *block_base = nullptr;
+        size_t blocks_cap = 0;
+        unsigned long long *line_end = nullptr;
+        size_t lines_cap = 0;
+        unsigned char *n_fields = nullptr;
+        size_t fields_cap = 0;
+        int32_t **col_table = nullptr;          // 256 device pointers
+        uint32_t *flags = nullptr;
+        int64_t *total = nullptr;
+    } csv;
+    // pinned staging lanes for large pageable copies (staged_copy)
+    struct StageLane { void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; cudaStream_t st = nullptr; };
+    StageLane stage[8];
+    int stage_lanes = 0;
+    cudaEvent_t stage_ready = nullptr;
     // aggregate exchange over peer memory (adb_peer_*): own mailbox + the peers' mappings
     adb::PeerRecord *peer_box = nullptr;
     adb::PeerBoxes peer_boxes{};
@@ -163,6 +187,94 @@ void peer_close() {
     g.peer_epoch = 0;
 }
 
+// ---- large host <-> device copies of pageable memory ----------------------------------------
+// Loaded columns are plain (mmap'd / malloc'd) host arrays (src/db_manager.c:178-186), which
+// cudaMemcpy moves through one internal staging buffer at ~11 GB/s (r01g: 4 GB in 354 ms).
+// Here `lanes` host threads each own two pinned 16 MB buffers and a stream: while a lane's
+// DMA engine drains one buffer the thread memcpys the next chunk into the other, and the
+// lanes together keep the PCIe link busy (the replacement for load_db's row-at-a-time
+// ingest).  Synchronous: returns when every byte has landed.
+constexpr size_t kStageChunk = 16u << 20;
+constexpr size_t kStageMinBytes = 64u << 20;
+constexpr int kStageMaxLanes = 8;
+
+bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+adb_status ensure_stager() {
+    if (g.stage_lanes) return ADB_OK;
+    int lanes = (int)std::thread::hardware_concurrency() / 2;
+    if (const char *e = getenv("ADB_STAGE_LANES")) lanes = atoi(e);
+    lanes = lanes < 1 ? 1 : lanes > kStageMaxLanes ? kStageMaxLanes : lanes;
+    for (int l = 0; l < lanes; ++l) {
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaHostAlloc(&g.stage[l].buf[b], kStageChunk, cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&g.stage[l].ev[b], cudaEventDisableTiming));
+        }
+        CU(cudaStreamCreateWithFlags(&g.stage[l].st, cudaStreamNonBlocking));
+    }
+    CU(cudaEventCreateWithFlags(&g.stage_ready, cudaEventDisableTiming));
+    g.stage_lanes = lanes;
+    return ADB_OK;
+}
+
+// up: host `h` -> device `d`; else device `d` -> host `h`
+adb_status staged_copy(void *d, void *h, size_t bytes, bool up) {
+    if (adb_status s = ensure_stager()) return s;
+    // the device buffer may come from the stream-ordered pool / be written by queued kernels
+    CU(cudaEventRecord(g.stage_ready, g.stream));
+    const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+    const int lanes = g.stage_lanes;
+    std::atomic<int> err{(int)cudaSuccess};
+    auto work = [&](int l) {
+        auto &L = g.stage[l];
+        cudaSetDevice(g.device);
+        auto ck = [&](cudaError_t e) { if (e != cudaSuccess) { int ok = (int)cudaSuccess; err.compare_exchange_strong(ok, (int)e); } };
+        ck(cudaStreamWaitEvent(L.st, g.stage_ready, 0));
+        char *dp = static_cast<char *>(d), *hp = static_cast<char *>(h);
+        if (up) {
+            int b = 0;
+            for (size_t c = l; c < nchunks; c += lanes, b ^= 1) {
+                const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+                ck(cudaEventSynchronize(L.ev[b]));                    // buffer b's previous DMA is done
+                memcpy(L.buf[b], hp + off, len);
+                ck(cudaMemcpyAsync(dp + off, L.buf[b], len, cudaMemcpyHostToDevice, L.st));
+                ck(cudaEventRecord(L.ev[b], L.st));
+            }
+        } else {
+            // chunk k+1's DMA runs while chunk k is copied out of its pinned buffer
+            size_t prev_off = 0, prev_len = 0;
+            int b = 0, prev_b = -1;
+            for (size_t c = l; c < nchunks; c += lanes, b ^= 1) {
+                const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+                ck(cudaMemcpyAsync(L.buf[b], dp + off, len, cudaMemcpyDeviceToHost, L.st));
+                ck(cudaEventRecord(L.ev[b], L.st));
+                if (prev_b >= 0) {
+                    ck(cudaEventSynchronize(L.ev[prev_b]));
+                    memcpy(hp + prev_off, L.buf[prev_b], prev_len);
+                }
+                prev_b = b; prev_off = off; prev_len = len;
+            }
+            if (prev_b >= 0) {
+                ck(cudaEventSynchronize(L.ev[prev_b]));
+                memcpy(hp + prev_off, L.buf[prev_b], prev_len);
+            }
+        }
+        ck(cudaStreamSynchronize(L.st));
+    };
+    std::vector<std::thread> th;
+    for (int l = 1; l < lanes; ++l) th.emplace_back(work, l);
+    work(0);
+    for (auto &t : th) t.join();
+    if (err.load() != (int)cudaSuccess)
+        return fail(ADB_ERR_CUDA, "staged %s of %zu bytes: %s", up ? "upload" : "download", bytes,
+                    cudaGetErrorString((cudaError_t)err.load()));
+    return ADB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -235,9 +347,21 @@ adb_status adb_shutdown(void) {
     cudaFree(g.sc_sums);
     cudaFree(g.arena);
     cudaFree(g.hj_table);
+    cudaFree(g.csv.block_counts);
+    cudaFree(g.csv.block_base);
+    cudaFree(g.csv.line_end);
+    cudaFree(g.csv.n_fields);
+    cudaFree(g.csv.col_table);
+    cudaFree(g.csv.flags);
+    cudaFree(g.csv.total);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     peer_close();
+    for (int l = 0; l < g.stage_lanes; ++l) {
+        for (int b = 0; b < 2; ++b) { cudaFreeHost(g.stage[l].buf[b]); cudaEventDestroy(g.stage[l].ev[b]); }
+        cudaStreamDestroy(g.stage[l].st);
+    }
+    if (g.stage_ready) cudaEventDestroy(g.stage_ready);
     cudaEventDestroy(g.ev0);
     cudaEventDestroy(g.ev1);
     for (cudaEvent_t &m : g.marks)
@@ -285,10 +409,14 @@ adb_status adb_download_async(void *h_dst, const void *d_src, size_t bytes) {
     return ADB_OK;
 }
 adb_status adb_upload(void *d_dst, const void *h_src, size_t bytes) {
+    NEED_UP();
+    if (bytes >= kStageMinBytes && host_is_pageable(h_src)) return staged_copy(d_dst, const_cast<void *>(h_src), bytes, true);
     adb_status s = adb_upload_async(d_dst, h_src, bytes);
     return s ? s : adb_sync();
 }
 adb_status adb_download(void *h_dst, const void *d_src, size_t bytes) {
+    NEED_UP();
+    if (bytes >= kStageMinBytes && host_is_pageable(h_dst)) return staged_copy(const_cast<void *>(d_src), h_dst, bytes, false);
     adb_status s = adb_download_async(h_dst, d_src, bytes);
     return s ? s : adb_sync();
 }
@@ -826,6 +954,90 @@ adb_status adb_route_pairs(const int32_t *d_val, const int32_t *d_pos, int64_t n
     CU(cudaMemcpyAsync(totals, g.rx_totals, sizeof(uint32_t) * parts, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
     for (int32_t r = 0; r < parts; ++r) h_counts[r] = totals[r];
+    return ADB_OK;
+}
+
+// ---- bulk CSV load ---------------------------------------------------------------------------------
+static adb_status csv_grow_bytes(void **p, size_t *cap, size_t need, size_t elem) {
+    if (need <= *cap) return ADB_OK;
+    if (*p) { CU(cudaStreamSynchronize(g.stream)); CU(cudaFree(*p)); }
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = need + need / 8 + 1024;
+    cudaError_t e = cudaMalloc(p, want * elem);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "csv scratch (%zu elements): %s", want, cudaGetErrorString(e)); }
+    *cap = want;
+    return ADB_OK;
+}
+#define csv_grow(pp, cap, need) csv_grow_bytes(reinterpret_cast<void **>(pp), cap, need, sizeof(**(pp)))
+
+adb_status adb_csv_index(const char *d_text, size_t bytes, int32_t skip_lines, int64_t *h_rows) {
+    NEED_UP();
+    auto &c = g.csv;
+    c.ready = false;
+    if (skip_lines < 0 || !h_rows || (bytes && !d_text)) return fail(ADB_ERR_INVALID, "adb_csv_index: bad arguments");
+    if (!c.col_table) {
+        CU(cudaMalloc(&c.col_table, 256 * sizeof(int32_t *)));
+        CU(cudaMalloc(&c.flags, 4 * sizeof(uint32_t)));
+        CU(cudaMalloc(&c.total, 2 * sizeof(int64_t)));
+    }
+    c.text = reinterpret_cast<const unsigned char *>(d_text);
+    c.bytes = bytes;
+    c.skip = (uint32_t)skip_lines;
+    c.newlines = 0;
+    c.rows = 0;
+    if (bytes == 0) { *h_rows = 0; c.ready = true; return ADB_OK; }
+    if (reinterpret_cast<uintptr_t>(d_text) & 15u) return fail(ADB_ERR_INVALID, "adb_csv_index: text must be 16-byte aligned (adb_alloc is)");
+    const uint32_t blocks = adb::csv_blocks(bytes);
+    size_t cap2 = c.blocks_cap;
+    if (adb_status s = csv_grow(&c.block_counts, &c.blocks_cap, blocks)) return s;
+    if (adb_status s = csv_grow(&c.block_base, &cap2, blocks)) return s;
+    if (adb_status s = ensure_radix_scratch(1)) return s;            // the scan's chunk sums live there
+    int k_ = adb::launch_csv_count(c.text, bytes, c.block_counts, g.stream);
+    k_ += adb::launch_exclusive_scan(c.block_counts, 1, c.block_base, blocks, g.sc_sums, c.total, g.sm_count, g.stream);
+    int64_t newlines = 0;
+    unsigned char last = 0;
+    CU(cudaMemcpyAsync(&newlines, c.total, sizeof newlines, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(&last, c.text + bytes - 1, 1, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if (newlines >= (int64_t)1 << 32) return fail(ADB_ERR_INVALID, "adb_csv_index: %lld lines in one call; split the text at a line boundary", (long long)newlines);
+    if (adb_status s = csv_grow(&c.line_end, &c.lines_cap, (size_t)newlines + 1)) return s;
+    k_ += adb::launch_csv_index(c.text, bytes, c.block_base, c.line_end, g.stream);
+    if (adb_status s = after_launch("csv_index", k_)) return s;
+    const unsigned long long lines = (unsigned long long)newlines + (last != '\n' ? 1 : 0);
+    c.newlines = (unsigned long long)newlines;
+    c.rows = lines > c.skip ? lines - c.skip : 0;
+    if (adb_status s = check_len((int64_t)c.rows, "adb_csv_index")) return s;
+    *h_rows = (int64_t)c.rows;
+    c.ready = true;
+    return ADB_OK;
+}
+
+adb_status adb_csv_parse(int32_t n_cols, int32_t *const *d_cols) {
+    NEED_UP();
+    auto &c = g.csv;
+    if (!c.ready) return fail(ADB_ERR_INVALID, "adb_csv_parse: no preceding adb_csv_index");
+    c.ready = false;
+    if (n_cols < 1 || n_cols > 254 || !d_cols) return fail(ADB_ERR_INVALID, "adb_csv_parse: n_cols %d outside [1, 254]", n_cols);
+    if (c.rows == 0) return ADB_OK;
+    for (int32_t i = 0; i < n_cols; ++i)
+        if (!d_cols[i]) return fail(ADB_ERR_INVALID, "adb_csv_parse: column %d is NULL", i);
+    if (adb_status s = csv_grow(&c.n_fields, &c.fields_cap, (size_t)c.rows)) return s;
+    CU(cudaMemcpyAsync(c.col_table, d_cols, sizeof(int32_t *) * n_cols, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemsetAsync(c.flags, 0, 4 * sizeof(uint32_t), g.stream));
+    int k_ = adb::launch_csv_parse(c.text, c.bytes, c.line_end, c.newlines, c.skip, c.rows, (uint32_t)n_cols,
+                                   c.col_table, c.n_fields, c.flags, g.stream);
+    uint32_t flags[2] = {0, 0};
+    CU(cudaMemcpyAsync(flags, c.flags, sizeof flags, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if (adb_status s = after_launch("csv_parse", k_)) return s;
+    if (flags[1])
+        return fail(ADB_ERR_INVALID, "adb_csv_parse: a line is longer than 1023 bytes (fgets would split it, "
+                    "src/db_manager.c:23,306)");
+    if (flags[0]) {
+        k_ = adb::launch_csv_fixup(c.rows, (uint32_t)n_cols, c.col_table, c.n_fields, g.stream);
+        if (adb_status s = after_launch("csv_fixup", k_)) return s;
+    }
     return ADB_OK;
 }
 

@@ -129,6 +129,8 @@ class Engine:
         "adb_agg_combine": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_agg_export": (C.c_int32, [C.POINTER(_AggStruct), C.c_void_p, C.c_void_p]),
         "adb_agg_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(_AggStruct)]),
+        "adb_csv_index": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, _I64P]),
+        "adb_csv_parse": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
         "adb_peer_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_char_p]),
         "adb_peer_connect": (C.c_int32, [C.c_char_p]),
         "adb_agg_combine_allreduce": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
@@ -199,6 +201,35 @@ class Engine:
         if a.nbytes:
             self._ck(self.lib.adb_upload(buf.void(), a.ctypes.data_as(C.c_void_p), a.nbytes))
         return buf
+
+    def csv_load(self, text, n_cols: int, skip_lines: int = 1, d_text: DevBuf | None = None):
+        """Bulk load: the bytes of a CSV file -> n_cols device columns (adb_csv_index +
+        adb_csv_parse; replaces load_db's ingest loop, db_manager.c:304-318).  `text` is
+        bytes / a uint8 numpy array on the host, or pass the device copy as d_text together
+        with the byte count as `text`.  Returns ([DevBuf per column], rows)."""
+        own = d_text is None
+        if own:
+            a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else text
+            nbytes = int(a.size)
+            d_text = self.upload(a) if nbytes else self.alloc(16)
+        else:
+            nbytes = int(text)
+        rows = C.c_int64(0)
+        try:
+            self._ck(self.lib.adb_csv_index(d_text.void(), nbytes, skip_lines, C.byref(rows)))
+            cols = [self.alloc_i32(rows.value) for _ in range(n_cols)]
+            ptrs = (C.c_void_p * n_cols)(*[c.ptr for c in cols])
+            try:
+                self._ck(self.lib.adb_csv_parse(n_cols, ptrs))
+            except EngineError:
+                for c in cols:
+                    c.free()
+                raise
+        finally:
+            if own:
+                self.sync()
+                d_text.free()
+        return cols, int(rows.value)
 
     def sync(self):
         self._ck(self.lib.adb_sync())

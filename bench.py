@@ -532,7 +532,8 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
                        "h2d_bytes_per_step": 8 * shard_rows, "d2h_bytes_per_step": 32,
                        "ms_per_step": 1e3 * dtc / reps,
                        "sample": f"one {shard_rows}-row shard whose two columns are host arrays; the "
-                                 "shim uploads both (pageable -> HBM) inside every timed step",
+                                 "shim uploads both inside every timed step (pageable memory staged "
+                                 "through the engine's pinned multi-lane pipeline, adb_upload)",
                        "check": {"sum": ctot, "hits": chits}}
     for (a, b) in hcols:
         L.adb_host_column_invalidate(C.byref(a))

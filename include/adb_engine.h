@@ -137,6 +137,25 @@ ADB_API adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d
 ADB_API adb_status adb_agg_export(const adb_agg *d_agg, int64_t *d_sum_count, int32_t *d_max_notmin);
 ADB_API adb_status adb_agg_import(const int64_t *d_sum_count, const int32_t *d_max_notmin, adb_agg *d_agg);
 
+/* ---- bulk load: CSV text -> int32 columns -- replaces the ingest loop of load_db,
+ * src/db_manager.c:304-318 (fgets line by line, strsep at ',', atoi per token, insert_row
+ * per row); SURVEY.md 8f rank 1.  The text (the file's bytes) is already in device memory
+ * (adb_alloc + adb_upload, which stages large pageable buffers through pinned lanes).
+ *   adb_csv_index   builds the line index; *h_rows = lines after `skip_lines` header lines
+ *                   (load_db consumes one, db_manager.c:263), counted as fgets counts them:
+ *                   every '\n'-terminated line, plus a non-empty unterminated last line.
+ *   adb_csv_parse   fills n_cols caller-allocated device columns of >= *h_rows ints.  Field
+ *                   values are bit-identical to atoi's (glibc: (int) strtol): leading
+ *                   whitespace, sign, digits to the first non-digit, saturation at
+ *                   LONG_MAX/LONG_MIN then truncation.  Fields beyond n_cols are ignored; a
+ *                   missing field repeats the previous row's value as the reference's
+ *                   reused row[] does (0 in the first row, where the reference reads
+ *                   uninitialised stack).  A line longer than 1023 bytes (fgets would split
+ *                   it, db_manager.c:23) is ADB_ERR_INVALID.  n_cols <= 254.
+ * d_cols is a HOST array of n_cols device pointers. */
+ADB_API adb_status adb_csv_index(const char *d_text, size_t bytes, int32_t skip_lines, int64_t *h_rows);
+ADB_API adb_status adb_csv_parse(int32_t n_cols, int32_t *const *d_cols);
+
 /* ---- multi-GPU aggregate exchange over NVLink peer memory (no reference equivalent: the
  * reference is single-process; SURVEY.md 8e "sum / min / max / avg: one exchange step").
  * One process per GPU.  Every rank calls adb_peer_create, the 64-byte handles are exchanged

@@ -21,7 +21,9 @@
  * that select_column_scan's predicate (low <= v < high) implies, and sets
  * *undefined_out when the caller passed one.
  */
+#define _DEFAULT_SOURCE              /* strsep (load_db's tokeniser) under -std=c99 */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -381,4 +383,47 @@ ORC_API int64_t orc_chain_select_fetch_sum_mt(const int32_t *sel_col, const int3
     free(tid); free(jobs);
     if (hits_out) *hits_out = hits;
     return total;
+}
+
+/* ---- bulk load: the ingest loop of load_db, src/db_manager.c:304-318 -----------------
+ * `text` holds the bytes of the CSV file.  fgets(line, MAX_LINE_SIZE = 1024, stream)
+ * (db_manager.c:23,306) is restated over the buffer: up to 1023 bytes, stopping after a
+ * '\n'.  The first `skip_lines` lines are consumed as load_db consumes the header
+ * (db_manager.c:263).  Each further line is tokenised with strsep(",") and the first n_cols
+ * tokens go through atoi (db_manager.c:309-311); `row` lives outside the loop, so a line
+ * with fewer tokens keeps the previous line's values (oracle-undefined for the first line,
+ * where the reference reads uninitialised stack: 0 here).  Every line becomes a row
+ * (insert_row, db_manager.c:312).  out is column-major: out[c * rows_cap + r].
+ * Returns the number of rows; with out == NULL it only counts. */
+static int64_t orc_fgets(char *line, int size, const char *text, int64_t bytes, int64_t *cursor) {
+    int64_t i = *cursor, n = 0;
+    if (i >= bytes) return -1;                           /* EOF before any byte: NULL */
+    while (n < size - 1 && i < bytes) {
+        const char c = text[i++];
+        line[n++] = c;
+        if (c == '\n') break;
+    }
+    line[n] = 0;
+    *cursor = i;
+    return n;
+}
+
+ORC_API int64_t orc_csv_parse(const char *text, int64_t bytes, int32_t skip_lines, int32_t n_cols,
+                              int32_t *out, int64_t rows_cap) {
+    char line[1024];
+    int64_t cursor = 0, rows = 0;
+    int32_t *row = (int32_t *)calloc((size_t)(n_cols > 0 ? n_cols : 1), sizeof(int32_t));
+    for (int32_t k = 0; k < skip_lines; ++k)
+        if (orc_fgets(line, (int)sizeof line, text, bytes, &cursor) < 0) break;
+    while (orc_fgets(line, (int)sizeof line, text, bytes, &cursor) >= 0) {
+        char *temp = line, *token;
+        int32_t index = 0;
+        while ((token = strsep(&temp, ",")) != NULL && index < n_cols)      /* db_manager.c:309 */
+            row[index++] = atoi(token);
+        if (out && rows < rows_cap)
+            for (int32_t c = 0; c < n_cols; ++c) out[(int64_t)c * rows_cap + rows] = row[c];
+        ++rows;
+    }
+    free(row);
+    return rows;
 }

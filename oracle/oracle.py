@@ -86,6 +86,18 @@ class CpuOps:
         fn.restype, fn.argtypes = restype, argtypes
         setattr(self, "_" + name, fn)
 
+    # ---- bulk load (restatement only: load_db is not part of the reference objects) ---
+    def csv_parse(self, text: bytes, n_cols: int, skip_lines: int = 1) -> np.ndarray:
+        """The ingest loop of load_db (db_manager.c:304-318) over the bytes of a CSV file:
+        int32 array of shape (n_cols, rows)."""
+        fn = self.lib.orc_csv_parse
+        fn.restype = C.c_int64
+        fn.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+        rows = fn(text, len(text), skip_lines, n_cols, None, 0)
+        out = np.zeros((n_cols, max(rows, 1)), dtype=np.int32)
+        fn(text, len(text), skip_lines, n_cols, out.ctypes.data, max(rows, 1))
+        return out[:, :rows].copy()
+
     # ---- selects -------------------------------------------------------------
     def select_scan(self, data, lo=None, hi=None) -> np.ndarray:
         data = _i32(data)

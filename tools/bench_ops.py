@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-operator timings at the BASELINE.json config sizes (development tool; bench.py is
-the contract).  python tools/bench_ops.py [shared|index|join|all] [--scale 1.0]"""
+the contract).  python tools/bench_ops.py [shared|index|join|load|all] [--scale 1.0]"""
 import argparse
 import json
 import os
@@ -129,6 +129,51 @@ def bench_join(eng, scale, cases=((0.8, 0.15), (0.15, 0.15), (1.0, 1.0))):
     return out
 
 
+def bench_load(eng, scale):
+    """CSV text -> columns.  The milestone-1 table shape (4 int columns,
+    milestone1.py:115-119) at 4 M rows; host text -> HBM columns, staged upload included.
+    CPU leg: the oracle's restatement of load_db's ingest loop on the same bytes."""
+    import pandas as pd
+    import time as _t
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle
+    rows = int(4_000_000 * scale)
+    rng = np.random.default_rng(42)
+    df = pd.DataFrame({"a": rng.integers(-rows // 2, rows // 2, rows), "b": rng.integers(-rows // 2, rows // 2, rows),
+                       "c": rng.integers(0, 100, rows), "d": rng.integers(2**31 - 10000, 2**31, rows)})
+    text = ("db1.tbl2.col1,db1.tbl2.col2,db1.tbl2.col3,db1.tbl2.col4\n" +
+            df.to_csv(index=False, header=False)).encode()
+    a = np.frombuffer(text, dtype=np.uint8)
+
+    def run():
+        cols, r = eng.csv_load(a, 4)
+        for c in cols:
+            c.free()
+        return r
+    med, best = timed(eng, run, reps=3, warm=1)
+    d_text = eng.upload(a)
+
+    def run_dev():
+        cols, r = eng.csv_load(a.size, 4, d_text=d_text)
+        for c in cols:
+            c.free()
+    med_d, _ = timed(eng, run_dev, reps=5, warm=1)
+    d_text.free()
+    cols, r = eng.csv_load(a, 4)
+    ok = all(np.array_equal(c.to_host(r), df[k].to_numpy().astype(np.int32)) for c, k in zip(cols, "abcd"))
+    for c in cols:
+        c.free()
+    t0 = _t.perf_counter()
+    ref = oracle.port().csv_parse(text, 4)
+    cpu_s = _t.perf_counter() - t0
+    ok = ok and all(np.array_equal(ref[i], df[k].to_numpy().astype(np.int32)) for i, k in enumerate("abcd"))
+    return {"rows": rows, "text_bytes": len(text), "parity": bool(ok),
+            "host_text_to_hbm_columns_ms": med, "best_ms": best, "text_gbs": len(text) / (med * 1e-3) / 1e9,
+            "rows_per_s": rows / (med * 1e-3),
+            "device_text_to_columns_ms": med_d, "device_text_gbs": len(text) / (med_d * 1e-3) / 1e9,
+            "cpu_port_s": cpu_s, "cpu_port_text_gbs": len(text) / cpu_s / 1e9}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -146,6 +191,8 @@ def main():
         res["join"] = bench_join(eng, a.scale, ((1.0, 1.0),))
     if a.what in ("join", "all"):
         res["join"] = bench_join(eng, a.scale)
+    if a.what in ("load", "all"):
+        res["load"] = bench_load(eng, a.scale)
     print(json.dumps(res, indent=1))
     eng.close()
 
