@@ -287,6 +287,12 @@ int launch_csv_parse(const unsigned char *text, size_t bytes, const unsigned lon
 int launch_csv_fixup(unsigned long long rows, uint32_t n_cols, int32_t *const *cols,
                      const unsigned char *n_fields, cudaStream_t s);
 
+// Result text for print (format_text.cu).
+uint32_t fmt_blocks(int64_t n);
+int launch_fmt_len(const int32_t *val, int64_t n, uint32_t *block_len, cudaStream_t s);
+int launch_fmt_emit(const int32_t *val, int64_t n, const uint32_t *block_off, unsigned char *text,
+                    uint64_t text_bytes, cudaStream_t s);
+
 // Hash join (hash_join.cu).
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s);

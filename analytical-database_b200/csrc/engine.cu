@@ -89,6 +89,15 @@ struct Engine {
         uint32_t *flags = nullptr;
         int64_t *total = nullptr;
     } csv;
+    // print formatting state (adb_format_i32_count -> _emit)
+    struct FmtState {
+        const int32_t *val = nullptr;
+        int64_t n = 0, bytes = 0;
+        bool ready = false;
+        uint32_t *block_len = nullptr, *block_off = nullptr;
+        size_t cap_len = 0, cap_off = 0;
+        int64_t *total = nullptr;
+    } fmt;
     // pinned staging lanes for large pageable copies (staged_copy)
     struct StageLane { void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; cudaStream_t st = nullptr; };
     StageLane stage[8];
@@ -347,6 +356,9 @@ adb_status adb_shutdown(void) {
     cudaFree(g.sc_sums);
     cudaFree(g.arena);
     cudaFree(g.hj_table);
+    cudaFree(g.fmt.block_len);
+    cudaFree(g.fmt.block_off);
+    cudaFree(g.fmt.total);
     cudaFree(g.csv.block_counts);
     cudaFree(g.csv.block_base);
     cudaFree(g.csv.line_end);
@@ -1039,6 +1051,49 @@ adb_status adb_csv_parse(int32_t n_cols, int32_t *const *d_cols) {
         if (adb_status s = after_launch("csv_fixup", k_)) return s;
     }
     return ADB_OK;
+}
+
+// ---- result text ------------------------------------------------------------------------------------
+adb_status adb_format_i32_count(const int32_t *d_val, int64_t n, int64_t *h_bytes) {
+    NEED_UP();
+    auto &f = g.fmt;
+    f.ready = false;
+    if (adb_status s = check_len(n, "adb_format_i32_count")) return s;
+    if (!h_bytes || (n > 0 && !d_val)) return fail(ADB_ERR_INVALID, "adb_format_i32_count: NULL pointer");
+    f.val = d_val;
+    f.n = n;
+    f.bytes = 0;
+    if (n == 0) { *h_bytes = 0; f.ready = true; return ADB_OK; }
+    if (!f.total) CU(cudaMalloc(&f.total, 2 * sizeof(int64_t)));
+    const uint32_t blocks = adb::fmt_blocks(n);
+    if (adb_status s = csv_grow(&f.block_len, &f.cap_len, blocks)) return s;
+    if (adb_status s = csv_grow(&f.block_off, &f.cap_off, blocks)) return s;
+    if (adb_status s = ensure_radix_scratch(1)) return s;
+    int k_ = adb::launch_fmt_len(d_val, n, f.block_len, g.stream);
+    k_ += adb::launch_exclusive_scan(f.block_len, 1, f.block_off, blocks, g.sc_sums, f.total, g.sm_count, g.stream);
+    int64_t total = 0;
+    CU(cudaMemcpyAsync(&total, f.total, sizeof total, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if (adb_status s = after_launch("format_count", k_)) return s;
+    if (total - 1 >= (int64_t)1 << 32)
+        return fail(ADB_ERR_INVALID, "adb_format_i32_count: %lld bytes of text; format at most 4 GiB per call", (long long)total - 1);
+    f.bytes = total - 1;                            // no separator after the last value
+    *h_bytes = f.bytes;
+    f.ready = true;
+    return ADB_OK;
+}
+
+adb_status adb_format_i32_emit(char *d_text) {
+    NEED_UP();
+    auto &f = g.fmt;
+    if (!f.ready) return fail(ADB_ERR_INVALID, "adb_format_i32_emit: no preceding adb_format_i32_count");
+    f.ready = false;
+    if (f.n == 0) return ADB_OK;
+    if (!d_text || (reinterpret_cast<uintptr_t>(d_text) & 15u))
+        return fail(ADB_ERR_INVALID, "adb_format_i32_emit: the text buffer must be 16-byte aligned device memory");
+    const int k_ = adb::launch_fmt_emit(f.val, f.n, f.block_off, reinterpret_cast<unsigned char *>(d_text),
+                                        (uint64_t)f.bytes, g.stream);
+    return after_launch("format_emit", k_);
 }
 
 // ---- hash join ------------------------------------------------------------------------------------

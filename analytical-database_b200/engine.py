@@ -129,6 +129,8 @@ class Engine:
         "adb_agg_combine": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_agg_export": (C.c_int32, [C.POINTER(_AggStruct), C.c_void_p, C.c_void_p]),
         "adb_agg_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(_AggStruct)]),
+        "adb_format_i32_count": (C.c_int32, [_I32P, C.c_int64, _I64P]),
+        "adb_format_i32_emit": (C.c_int32, [C.c_void_p]),
         "adb_csv_index": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, _I64P]),
         "adb_csv_parse": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
         "adb_peer_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_char_p]),
@@ -230,6 +232,20 @@ class Engine:
                 self.sync()
                 d_text.free()
         return cols, int(rows.value)
+
+    def format_i32(self, val: DevBuf, n: int) -> bytes:
+        """print's text for an INT result ("%d" joined by newlines, query.c:262-269), formatted
+        on the device and downloaded as text."""
+        nb = C.c_int64(0)
+        self._ck(self.lib.adb_format_i32_count(val.i32(), n, C.byref(nb)))
+        if nb.value == 0:
+            self._ck(self.lib.adb_format_i32_emit(None))
+            return b""
+        d = self.alloc(nb.value)
+        self._ck(self.lib.adb_format_i32_emit(d.void()))
+        out = d.to_host(nb.value, np.uint8).tobytes()
+        d.free()
+        return out
 
     def sync(self):
         self._ck(self.lib.adb_sync())

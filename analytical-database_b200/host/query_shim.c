@@ -854,6 +854,7 @@ Result **hash_join(Result *column_one, Result *position_one, Result *column_two,
 }
 
 /* ---- print ------------------------------------------------------------------------------------------ */
+#define PRINT_ON_DEVICE_MIN 4096       /* shorter results: the download + host loop is cheaper than three launches */
 typedef struct Text {
     char *s;
     size_t len, cap;
@@ -900,6 +901,29 @@ char *print(Result **results, int result_num, Status *ret_status) {
         }
         const size_t n = r->num_tuples;
         const size_t w = r->data_type == INT || r->data_type == FLOAT ? 4 : 8;
+        if (r->data_type == INT && n >= PRINT_ON_DEVICE_MIN) {
+            /* a long device-resident INT result is formatted where it lives; the text, not
+             * the integers, crosses PCIe and no sprintf runs */
+            lock();
+            DevResult *e = registry_find(r->payload);
+            const int32_t *d = e ? e->d_ptr : NULL;
+            unlock();
+            if (d) {
+                int64_t bytes = 0;
+                void *d_text = NULL;
+                if (adb_format_i32_count(d, (int64_t)n, &bytes) != ADB_OK) goto dev_fail;
+                if (text_room(&t, (size_t)bytes)) goto oom;
+                if (adb_alloc(&d_text, (size_t)bytes) != ADB_OK) goto dev_fail;
+                if (adb_format_i32_emit(d_text) != ADB_OK ||
+                    adb_download(t.s + t.len, d_text, (size_t)bytes) != ADB_OK) {
+                    adb_free(d_text);
+                    goto dev_fail;
+                }
+                adb_free(d_text);
+                t.len += (size_t)bytes;
+                continue;
+            }
+        }
         host = malloc(n ? n * w : 1);
         if (!host) goto oom;
         if (adb_host_result_to_host(r, host)) {
@@ -921,6 +945,10 @@ char *print(Result **results, int result_num, Status *ret_status) {
     t.s[t.len] = '\0';
     op_ok(ret_status);
     return t.s;
+dev_fail:
+    set_err("print: %s", adb_last_error());
+    free(t.s);
+    return op_fail(ret_status, "print");
 oom:
     free(host);
     free(t.s);

@@ -156,6 +156,15 @@ ADB_API adb_status adb_agg_import(const int64_t *d_sum_count, const int32_t *d_m
 ADB_API adb_status adb_csv_index(const char *d_text, size_t bytes, int32_t skip_lines, int64_t *h_rows);
 ADB_API adb_status adb_csv_parse(int32_t n_cols, int32_t *const *d_cols);
 
+/* ---- result text: the INT branch of print, src/query.c:262-269 ("%d" per tuple, "\n"
+ * between tuples, nothing after the last); SURVEY.md 8f rank 2.  Two-phase like the
+ * selects: adb_format_i32_count sizes the text (*h_bytes, without a terminating NUL),
+ * adb_format_i32_emit writes it to a 16-byte-aligned device buffer of that size; the caller
+ * downloads text instead of integers and never runs sprintf.  The text must stay below
+ * 4 GiB per call (the reference's reply path stops at a few MB, server.c:522). */
+ADB_API adb_status adb_format_i32_count(const int32_t *d_val, int64_t n, int64_t *h_bytes);
+ADB_API adb_status adb_format_i32_emit(char *d_text);
+
 /* ---- multi-GPU aggregate exchange over NVLink peer memory (no reference equivalent: the
  * reference is single-process; SURVEY.md 8e "sum / min / max / avg: one exchange step").
  * One process per GPU.  Every rank calls adb_peer_create, the 64-byte handles are exchanged

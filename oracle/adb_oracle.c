@@ -427,3 +427,18 @@ ORC_API int64_t orc_csv_parse(const char *text, int64_t bytes, int32_t skip_line
     free(row);
     return rows;
 }
+
+/* ---- print of one INT result: src/query.c:262-269 ---------------------------------------
+ * "%d" per tuple, "\n" between tuples, nothing after the last.  out needs 12 bytes per
+ * tuple (the reference allocates 11, query.c:253, and overruns on wide values -- SURVEY.md
+ * A8).  Returns the text length (no NUL counted); an empty result gives "" (the reference
+ * returns its uninitialised malloc(0): oracle-undefined). */
+ORC_API int64_t orc_print_i32(const int32_t *v, int64_t n, char *out, int64_t cap) {
+    int64_t index = 0;
+    (void)cap;
+    for (int64_t i = 0; i < n; ++i) {
+        index += sprintf(&out[index], "%d", v[i]);
+        if (i != n - 1) index += sprintf(&out[index], "\n");
+    }
+    return index;
+}

@@ -98,6 +98,16 @@ class CpuOps:
         fn(text, len(text), skip_lines, n_cols, out.ctypes.data, max(rows, 1))
         return out[:, :rows].copy()
 
+    def print_i32(self, vals) -> bytes:
+        """print of one INT result (query.c:245-304): the text, without a NUL."""
+        vals = _i32(vals)
+        fn = getattr(self.lib, self.prefix + "print_i32")
+        fn.restype = C.c_int64
+        fn.argtypes = [_I32P, C.c_int64, C.c_char_p, C.c_int64]
+        buf = C.create_string_buffer(12 * max(vals.size, 1) + 16)
+        n = fn(_p(vals), vals.size, buf, len(buf))
+        return buf.raw[:n]
+
     # ---- selects -------------------------------------------------------------
     def select_scan(self, data, lo=None, hi=None) -> np.ndarray:
         data = _i32(data)

@@ -268,3 +268,20 @@ REF_API int64_t ref_chain_select_fetch_sum_mt(const int32_t *sel_col, const int3
     if (hits_out) *hits_out = hits;
     return total;
 }
+
+/* print, src/query.c:245-304, for one INT result.  Returns the strlen of the text; the text
+ * itself is copied to out (capacity cap) when out != NULL.  The reference sizes its buffer at
+ * 11 bytes per tuple (query.c:253): only call with values whose "%d\n" fits that on average. */
+REF_API int64_t ref_print_i32(const int32_t *v, int64_t n, char *out, int64_t cap) {
+    Result r = mk_result(v, n);
+    Result *rs[1] = {&r};
+    Status st;
+    char *text = print(rs, 1, &st);
+    int64_t len = 0;
+    if (n > 0) {
+        len = (int64_t)strlen(text);
+        if (out && len <= cap) memcpy(out, text, (size_t)len);
+    }
+    free(text);
+    return len;
+}

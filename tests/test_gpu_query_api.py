@@ -57,8 +57,11 @@ def test_select_fetch_aggregate_print(api, cpu, rng, n):
             assert int(api.tuples(mn)[0]) == cpu.min(evals) and int(api.tuples(mx)[0]) == cpu.max(evals)
             assert api.print(avg) == "%.2f" % cpu.avg(evals)           # query.c:293
             assert api.print(mn, mx) == "%d,%d" % (cpu.min(evals), cpu.max(evals))   # query.c:255-260
-            if epos.size <= 5000:
-                assert api.print(f) == "\n".join(str(int(v)) for v in evals)
+            # short results are rendered on the host, >= 4096 tuples on the device
+            assert api.print(f) == "\n".join(str(int(v)) for v in evals)
+            if 4096 <= epos.size <= 100_000:                          # two long results: column-major, ','
+                assert api.print(s, f) == "\n".join(map(str, epos.tolist())) + "," + \
+                    "\n".join(map(str, evals.tolist()))
             for r in (avg, mn, mx):
                 api.drop(r)
         else:

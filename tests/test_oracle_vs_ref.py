@@ -199,3 +199,13 @@ def test_chain(port, ref, rng, threads):
         exp = (int(fet[mask].astype(np.int64).sum()), int(mask.sum()))
         assert port.chain_select_fetch_sum(sel, fet, lo, hi, threads) == exp
         assert ref.chain_select_fetch_sum(sel, fet, lo, hi, threads) == exp
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 30_000])
+def test_print_int_result(port, ref, rng, n):
+    """print (query.c:245-304), INT branch.  Values stay <= 9 characters so the reference's
+    11-bytes-per-tuple buffer (query.c:253) is not overrun."""
+    v = rng.integers(-9_999_999, 99_999_999, n).astype(np.int32)
+    text = port.print_i32(v)
+    assert text == ref.print_i32(v)
+    assert text == "\n".join(str(int(x)) for x in v).encode()

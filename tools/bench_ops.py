@@ -2,6 +2,7 @@
 """Per-operator timings at the BASELINE.json config sizes (development tool; bench.py is
 the contract).  python tools/bench_ops.py [shared|index|join|load|all] [--scale 1.0]"""
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -174,6 +175,42 @@ def bench_load(eng, scale):
             "cpu_port_s": cpu_s, "cpu_port_text_gbs": len(text) / cpu_s / 1e9}
 
 
+def bench_print(eng, scale):
+    """print of a long INT result.  Device formatting + text download
+    against download + the reference's sprintf loop (the oracle's restatement of
+    query.c:262-269; the reference itself corrupts its heap on wide values, A8)."""
+    import time as _t
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle
+    n = int(50_000_000 * scale)
+    d = eng.synth_uniform(n, 5, 0, -500_000, 1_000_000)
+    nb = C.c_int64(0)
+
+    def kernels():
+        eng._ck(eng.lib.adb_format_i32_count(d.i32(), n, C.byref(nb)))
+        t = eng.alloc(nb.value)
+        eng._ck(eng.lib.adb_format_i32_emit(t.void()))
+        t.free()
+    med_k, _ = timed(eng, kernels, reps=5, warm=2)
+    t0 = _t.perf_counter()
+    text = eng.format_i32(d, n)
+    e2e_s = _t.perf_counter() - t0
+    t0 = _t.perf_counter()
+    text = eng.format_i32(d, n)
+    e2e_s = min(e2e_s, _t.perf_counter() - t0)
+    m = min(n, 5_000_000)
+    host = d.to_host(m)
+    t0 = _t.perf_counter()
+    ref = oracle.port().print_i32(host)
+    cpu_s = (_t.perf_counter() - t0) * n / m
+    ok = text[:len(ref)] == ref if m < n else text == ref
+    d.free()
+    return {"values": n, "text_bytes": len(text), "parity_prefix": bool(ok), "device_format_ms": med_k,
+            "device_format_gvalues_per_s": n / (med_k * 1e-3) / 1e9,
+            "print_to_host_text_ms": e2e_s * 1e3, "cpu_port_ms_extrapolated": cpu_s * 1e3,
+            "cpu_sample_values": m}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -191,6 +228,8 @@ def main():
         res["join"] = bench_join(eng, a.scale, ((1.0, 1.0),))
     if a.what in ("join", "all"):
         res["join"] = bench_join(eng, a.scale)
+    if a.what in ("print", "all"):
+        res["print"] = bench_print(eng, a.scale)
     if a.what in ("load", "all"):
         res["load"] = bench_load(eng, a.scale)
     print(json.dumps(res, indent=1))
