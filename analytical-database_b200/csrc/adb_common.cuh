@@ -43,6 +43,31 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------
+// The chain is a string of short kernels on one stream (0.31 ms + 0.13 ms per shard); a
+// kernel launched with launch_pdl() may be scheduled while its predecessor drains and must
+// call pdl_wait() before it reads or overwrites anything the predecessor touches.  Work that
+// depends on nothing earlier (the first column tile of the predicate pass) goes before the
+// wait.  pdl_launch_dependents() lets the successor's CTAs take the slots this grid frees.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                              cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- warp primitives ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
 #pragma unroll
@@ -85,6 +110,48 @@ __device__ __forceinline__ bool in_range(int32_t v, const Range &r) {
     return v >= r.lo && v <= r.hi_incl;
 }
 
+// ---- aggregate exchange over NVLink peer memory (peer_agg.cu, and the epilogue of the fused
+// chain kernel) ------------------------------------------------------------------------------
+// One 32-byte record per (bank, source rank) in every rank's mailbox; box[r] is rank r's
+// mailbox as mapped into this process (cudaIpcOpenMemHandle; box[rank] is the local
+// allocation itself).
+constexpr int kMaxPeers = ADB_MAX_PEERS;
+struct PeerRecord {
+    int64_t sum, count;
+    int32_t min, max;
+    uint32_t epoch, pad;
+};
+struct PeerBoxes {
+    PeerRecord *box[kMaxPeers];
+};
+constexpr size_t kPeerBoxBytes = sizeof(PeerRecord) * 2 * kMaxPeers;
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;      // 2 s
+
+// What a kernel needs to finish an aggregate across ranks: world == 0 disables it.
+struct PeerExchange {
+    const PeerBoxes *boxes;       // in DEVICE memory: an array inside a kernel parameter would be
+                                  // copied to every thread's local memory as soon as it is indexed
+    int32_t rank, world;
+    uint32_t epoch;
+    const adb_agg *parts;         // this rank's shard partials, all folded in before the exchange
+    int32_t k;
+    adb_agg *final_out;           // table-wide aggregate, identical on every rank
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---- aggregate accumulator + the block -> grid fold shared by aggregate_kernel and the
 // fused chain kernel --------------------------------------------------------------------------
 struct AggAcc {
@@ -103,12 +170,67 @@ struct AggAcc {
     }
 };
 
+// One full warp, converged.  Folds this rank's k shard partials, stores the result into every
+// rank's mailbox (payload, then the epoch with st.release.sys), acquire-spins on its own
+// mailbox until every rank's record of this epoch has arrived, folds them in rank order and
+// writes the table-wide aggregate (count = -1 if a peer did not arrive within 2 s).  Two
+// banks suffice: a peer can only start epoch e+2 after it received this rank's e+1 record,
+// which is sent after this rank has finished reading bank e.
+__device__ __forceinline__ void peer_exchange_warp(const PeerExchange &px, int lane) {
+    AggAcc g{0, INT32_MAX, INT32_MIN};
+    int64_t cnt = 0;
+    for (int i = lane; i < px.k; i += kWarp) {
+        const volatile adb_agg *p = px.parts + i;           // just written by this grid: no .nc path
+        g.sum += p->sum;
+        cnt += p->count;
+        g.mn = min(g.mn, p->min);
+        g.mx = max(g.mx, p->max);
+    }
+    g.sum = warp_sum_i64(g.sum);
+    cnt = warp_sum_i64(cnt);
+    g.mn = warp_min_i32(g.mn);
+    g.mx = warp_max_i32(g.mx);
+    const uint32_t bank = px.epoch & 1u;
+    if (lane < px.world) {
+        PeerRecord *dst = px.boxes->box[lane] + bank * kMaxPeers + px.rank;
+        volatile PeerRecord *v = dst;
+        v->sum = g.sum;
+        v->count = cnt;
+        v->min = g.mn;
+        v->max = g.mx;
+        st_release_sys(&dst->epoch, px.epoch);
+    }
+    AggAcc f{0, INT32_MAX, INT32_MIN};
+    int64_t fc = 0;
+    bool ok = true;
+    if (lane < px.world) {
+        PeerRecord *src = px.boxes->box[px.rank] + bank * kMaxPeers + lane;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&src->epoch) != px.epoch) {
+            if (global_ns() - t0 > kPeerTimeoutNs) { ok = false; break; }
+            __nanosleep(32);
+        }
+        const volatile PeerRecord *v = src;
+        f.sum = v->sum;
+        fc = v->count;
+        f.mn = v->min;
+        f.mx = v->max;
+    }
+    ok = __all_sync(kFull, ok);
+    f.sum = warp_sum_i64(f.sum);
+    fc = warp_sum_i64(fc);
+    f.mn = warp_min_i32(f.mn);
+    f.mx = warp_max_i32(f.mx);
+    if (lane == 0) *px.final_out = ok ? adb_agg{f.sum, fc, f.mn, f.mx} : adb_agg{0, -1, INT32_MAX, INT32_MIN};
+}
+
 // Every thread of every CTA calls this once with its private accumulator and its share of
 // the tuple count.  Warp shuffles -> one partial per CTA in `scratch` -> the last CTA to
 // arrive (ticket) folds all partials in a fixed order and writes *out.  The ticket re-arms
-// itself, so back-to-back launches on one stream need no reset.
+// itself, so back-to-back launches on one stream need no reset.  Returns true in (every thread
+// of) that last CTA, which may go on to exchange the aggregate with the peers.
 template <int THREADS>
-__device__ __forceinline__ void agg_grid_fold(AggAcc acc, int64_t cnt, adb_agg *__restrict__ out,
+__device__ __forceinline__ bool agg_grid_fold(AggAcc acc, int64_t cnt, adb_agg *__restrict__ out,
                                               adb_agg *scratch, unsigned int *ticket) {
     constexpr int W = THREADS / kWarp;
     __shared__ int64_t s_sum[W], s_cnt[W];
@@ -137,7 +259,7 @@ __device__ __forceinline__ void agg_grid_fold(AggAcc acc, int64_t cnt, adb_agg *
         }
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     __threadfence();
     AggAcc g{0, INT32_MAX, INT32_MIN};
     int64_t gc = 0;
@@ -167,6 +289,7 @@ __device__ __forceinline__ void agg_grid_fold(AggAcc acc, int64_t cnt, adb_agg *
         *out = adb_agg{f.sum, fc, f.mn, f.mx};
         *ticket = 0;                                    // re-arm for the next launch
     }
+    return true;
 }
 
 // splitmix64 finaliser: the counter-based generator behind adb_synth_uniform
@@ -200,6 +323,7 @@ struct SelectArgs {
     int32_t *val_out;
     adb_agg *agg_out, *agg_scratch;
     unsigned int *agg_ticket;
+    PeerExchange px;              // world != 0: the chain kernel finishes with the cross-rank exchange
 };
 int launch_select(const SelectArgs &a, cudaStream_t s);
 // two-phase form: mask + per-chunk counts (+ total into a.d_count), then expand into a.out
@@ -221,22 +345,8 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
 int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
                           uint32_t span, int sm_count, cudaStream_t s);
 constexpr int kAggMaxBlocks = 148 * 8;
+int launch_agg_combine_allreduce(const PeerExchange &px, cudaStream_t s);
 
-// Aggregate exchange over NVLink peer memory (peer_agg.cu).  One 32-byte record per
-// (bank, source rank) in every rank's mailbox; box[r] is rank r's mailbox as mapped into this
-// process (cudaIpcOpenMemHandle; box[rank] is the local allocation itself).
-constexpr int kMaxPeers = ADB_MAX_PEERS;
-struct PeerRecord {
-    int64_t sum, count;
-    int32_t min, max;
-    uint32_t epoch, pad;
-};
-struct PeerBoxes {
-    PeerRecord *box[kMaxPeers];
-};
-constexpr size_t kPeerBoxBytes = sizeof(PeerRecord) * 2 * kMaxPeers;
-int launch_agg_combine_allreduce(const adb_agg *parts, int32_t k, const PeerBoxes &boxes, int32_t rank,
-                                 int32_t world, uint32_t epoch, adb_agg *out, cudaStream_t s);
 
 // Batched shared scan (shared_scan.cu).  All pointers are device addresses.
 struct SharedScanPlan {

@@ -106,6 +106,7 @@ struct Engine {
     // aggregate exchange over peer memory (adb_peer_*): own mailbox + the peers' mappings
     adb::PeerRecord *peer_box = nullptr;
     adb::PeerBoxes peer_boxes{};
+    adb::PeerBoxes *peer_boxes_dev = nullptr;     // the same table in device memory (kernels index it)
     int32_t peer_world = 0, peer_rank = -1;
     bool peer_connected = false;
     uint32_t peer_epoch = 0;
@@ -187,6 +188,8 @@ void peer_close() {
     for (int r = 0; r < g.peer_world; ++r)
         if (r != g.peer_rank && g.peer_boxes.box[r]) cudaIpcCloseMemHandle(g.peer_boxes.box[r]);
     if (g.peer_box) cudaFree(g.peer_box);
+    if (g.peer_boxes_dev) cudaFree(g.peer_boxes_dev);
+    g.peer_boxes_dev = nullptr;
     cudaGetLastError();
     g.peer_box = nullptr;
     g.peer_boxes = adb::PeerBoxes{};
@@ -640,6 +643,8 @@ adb_status adb_peer_connect(const unsigned char *handles) {
         }
         g.peer_boxes.box[r] = static_cast<adb::PeerRecord *>(p);
     }
+    CU(cudaMalloc(&g.peer_boxes_dev, sizeof(adb::PeerBoxes)));
+    CU(cudaMemcpy(g.peer_boxes_dev, &g.peer_boxes, sizeof(adb::PeerBoxes), cudaMemcpyHostToDevice));
     g.peer_connected = true;
     g.peer_epoch = 0;
     return ADB_OK;
@@ -651,8 +656,8 @@ adb_status adb_agg_combine_allreduce(const adb_agg *d_parts, int32_t k, adb_agg 
     if (k < 0 || !d_out || (k > 0 && !d_parts))
         return fail(ADB_ERR_INVALID, "adb_agg_combine_allreduce: bad arguments");
     const uint32_t epoch = ++g.peer_epoch;
-    const int k_ = adb::launch_agg_combine_allreduce(d_parts, k, g.peer_boxes, g.peer_rank, g.peer_world,
-                                                     epoch, d_out, g.stream);
+    const int k_ = adb::launch_agg_combine_allreduce(
+        adb::PeerExchange{g.peer_boxes_dev, g.peer_rank, g.peer_world, epoch, d_parts, k, d_out}, g.stream);
     if (adb_status s = after_launch("agg_combine_allreduce", k_)) return s;
     if (h_out) {
         CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
@@ -695,10 +700,10 @@ adb_status adb_add(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const 
 adb_status adb_sub(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
                    int32_t *d_out) { return ewise(d_a, d_b, n_max, d_n, d_out, true); }
 
-adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d_fetch_col,
-                                      int64_t n, const int32_t *lo, const int32_t *hi,
-                                      int32_t *d_pos_out, int32_t *d_val_out,
-                                      int64_t *d_count, adb_agg *d_agg) {
+static adb_status chain_impl(const int32_t *d_sel_col, const int32_t *d_fetch_col,
+                             int64_t n, const int32_t *lo, const int32_t *hi,
+                             int32_t *d_pos_out, int32_t *d_val_out,
+                             int64_t *d_count, adb_agg *d_agg, const adb::PeerExchange *px) {
     adb::SelectArgs a;
     if (!d_count || !d_agg || (n > 0 && (!d_pos_out || !d_val_out || !d_fetch_col))) {
         NEED_UP();
@@ -708,6 +713,7 @@ adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d
     a.base_pos = 0; a.out = d_pos_out;
     a.fetch_col = d_fetch_col; a.val_out = d_val_out;
     a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
+    if (px) a.px = *px;
     // two launches: predicate pass -> bitmap, then expansion with the gather and the
     // aggregates fused in (positions and values are still materialised)
     const int32_t mb = g.chain_mark_base;
@@ -722,7 +728,30 @@ adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d
     k_ += adb::launch_select_expand(a, g.stream);
     if (adb_status s = after_launch("chain", k_)) return s;
     if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, n, d_count, 0, d_val_out)) return s;
-    return adb_aggregate(d_val_out, n, d_count, d_agg, nullptr);
+    if (adb_status s = adb_aggregate(d_val_out, n, d_count, d_agg, nullptr)) return s;
+    if (!px) return ADB_OK;
+    return after_launch("chain exchange", adb::launch_agg_combine_allreduce(*px, g.stream));
+}
+
+adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d_fetch_col,
+                                      int64_t n, const int32_t *lo, const int32_t *hi,
+                                      int32_t *d_pos_out, int32_t *d_val_out,
+                                      int64_t *d_count, adb_agg *d_agg) {
+    return chain_impl(d_sel_col, d_fetch_col, n, lo, hi, d_pos_out, d_val_out, d_count, d_agg, nullptr);
+}
+
+adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col, const int32_t *d_fetch_col,
+                                               int64_t n, const int32_t *lo, const int32_t *hi,
+                                               int32_t *d_pos_out, int32_t *d_val_out, int64_t *d_count,
+                                               adb_agg *d_parts, int32_t k, adb_agg *d_out) {
+    NEED_UP();
+    if (!g.peer_connected) return fail(ADB_ERR_INVALID, "adb_chain_select_fetch_agg_exchange: adb_peer_connect first");
+    if (k < 1 || !d_parts || !d_out) return fail(ADB_ERR_INVALID, "adb_chain_select_fetch_agg_exchange: bad arguments");
+    const adb::PeerExchange px{g.peer_boxes_dev, g.peer_rank, g.peer_world, g.peer_epoch + 1, d_parts, k, d_out};
+    const adb_status s = chain_impl(d_sel_col, d_fetch_col, n, lo, hi, d_pos_out, d_val_out, d_count,
+                                    d_parts + (k - 1), &px);
+    if (s == ADB_OK) ++g.peer_epoch;          // the exchange was enqueued: every rank advances together
+    return s;
 }
 
 // ---- batched shared scan -------------------------------------------------------------------

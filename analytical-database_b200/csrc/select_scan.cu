@@ -93,9 +93,11 @@ mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, ui
             uint32_t *__restrict__ counts) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t chunk = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+    pdl_launch_dependents();
     if (chunk >= num_chunks) return;
     uint32_t n = n_host;
     if (d_n) {
+        pdl_wait();                                          // the length comes from an earlier kernel
         const long long dn = *d_n;
         n = dn < (long long)n_host ? (uint32_t)(dn < 0 ? 0 : dn) : n_host;
     }
@@ -114,6 +116,9 @@ mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, ui
     if (full) {
         int4 cur[SEL_VEC];
         load_tile(cur, val, row_begin, lane);
+        // the column itself is never written by the operators of a chain: its first tile is
+        // requested while the previous kernel (which still reads the bitmap) drains
+        pdl_wait();
         for (uint32_t t = 0; t < full; ++t) {
             int4 nxt[SEL_VEC];
             if (t + 1 < full) load_tile(nxt, val, row_begin + (t + 1) * SEL_WTILE, lane);
@@ -126,6 +131,7 @@ mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, ui
             }
         }
     }
+    pdl_wait();
     for (uint32_t t = full; t < tiles; ++t) {            // ragged tail / unaligned view / past n
         const uint32_t row0 = row_begin + t * SEL_WTILE;
         const uint32_t nib = row0 < n ? tile_nibbles_guarded(val, row0, lane, n, rg) : 0u;
@@ -149,13 +155,31 @@ struct ChainArgs {
     adb_agg *agg_out, *agg_scratch;
     unsigned int *agg_ticket;
 };
+// EXCH: the chain kernel of a rank's last shard also carries the cross-rank exchange.  A
+// separate parameter type and instantiation, so the single-GPU kernel is compiled exactly as
+// before (r01o: growing ChainArgs itself cost the fused kernel 0.131 -> 0.180 ms).
+struct ChainArgsX {
+    ChainArgs c;
+    PeerExchange px;
+};
+// Out of line on purpose: inlined, the exchange (system-scope loads, a spin loop) changed the
+// register allocation and scheduling of the whole kernel (48 -> 40 registers, 0.131 -> 0.186 ms).
+__device__ __noinline__ void chain_exchange(PeerExchange px, int lane) { peer_exchange_warp(px, lane); }
 
-template <bool PAIRS, bool FETCH>
+template <bool EXCH> struct ChainOf { using type = ChainArgs; };
+template <> struct ChainOf<true> { using type = ChainArgsX; };
+__device__ __forceinline__ const ChainArgs &chain_of(const ChainArgs &a) { return a; }
+__device__ __forceinline__ const ChainArgs &chain_of(const ChainArgsX &a) { return a.c; }
+
+template <bool PAIRS, bool FETCH, bool EXCH = false>
 __global__ void __launch_bounds__(SEL_THREADS)
 expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
               uint32_t chunk_rows, uint32_t num_chunks, const int32_t *__restrict__ pos_in,
               int32_t base_pos, int32_t *__restrict__ out, int64_t *__restrict__ d_count,
-              ChainArgs ch) {
+              const typename ChainOf<EXCH>::type chx) {
+    const ChainArgs &ch = chain_of(chx);
+    pdl_launch_dependents();
+    pdl_wait();                                              // bitmap + counts come from mask_kernel
     __shared__ uint32_t s_red[SEL_WARPS];
     __shared__ int32_t s_stage[SEL_WARPS][kWarp * 32 * EXP_WORDS / 4];   // 1024 positions per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -286,9 +310,19 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
             out_off += step_total;
         }
     }
-    if (FETCH)
-        agg_grid_fold<SEL_THREADS>(acc, lane == 0 && chunk < num_chunks ? (int64_t)my_count : 0,
-                                   ch.agg_out, ch.agg_scratch, ch.agg_ticket);
+    if (FETCH) {
+        const bool last = agg_grid_fold<SEL_THREADS>(acc, lane == 0 && chunk < num_chunks ? (int64_t)my_count : 0,
+                                                     ch.agg_out, ch.agg_scratch, ch.agg_ticket);
+        // multi-GPU: the CTA that completed this shard's aggregate folds the rank's partials and
+        // exchanges them with every peer over NVLink (agg_out is one of px.parts: publish it first)
+        if constexpr (EXCH) {
+            if (last) {
+                __threadfence();
+                __syncthreads();
+                if (warp == 0) chain_exchange(chx.px, (int)lane);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,8 +372,8 @@ int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s) {
         return 0;
     }
     const SelectGeom g = select_geom(a.n, a.sm_count);
-    mask_kernel<<<g.grid, SEL_THREADS, 0, s>>>(a.val, a.d_n, a.n, a.range, g.chunk_rows,
-                                               g.num_chunks, a.mask, a.counts);
+    launch_pdl(mask_kernel, g.grid, SEL_THREADS, 0, s, a.val, a.d_n, a.n, a.range, g.chunk_rows,
+               g.num_chunks, a.mask, a.counts);
     if (!with_total) return 1;
     count_total_kernel<<<1, 1024, 0, s>>>(a.counts, g.num_chunks, a.d_count);
     return 2;
@@ -364,9 +398,13 @@ int launch_select_expand(const SelectArgs &a, cudaStream_t s) {
 int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s) {
     const SelectGeom g = select_geom(a.n ? a.n : 1, a.sm_count);
     if (a.n == 0 || (int)g.grid > kAggMaxBlocks) return -1;          // caller falls back to 3 launches
-    expand_kernel<false, true><<<g.grid, SEL_THREADS, 0, s>>>(
-        a.mask, a.counts, g.chunk_rows, g.num_chunks, nullptr, a.base_pos, a.out, a.d_count,
-        ChainArgs{a.fetch_col, a.val_out, a.agg_out, a.agg_scratch, a.agg_ticket});
+    const ChainArgs c{a.fetch_col, a.val_out, a.agg_out, a.agg_scratch, a.agg_ticket};
+    if (a.px.world)
+        launch_pdl(expand_kernel<false, true, true>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts, g.chunk_rows,
+                   g.num_chunks, (const int32_t *)nullptr, a.base_pos, a.out, a.d_count, ChainArgsX{c, a.px});
+    else
+        launch_pdl(expand_kernel<false, true, false>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts, g.chunk_rows,
+                   g.num_chunks, (const int32_t *)nullptr, a.base_pos, a.out, a.d_count, c);
     return 1;
 }
 

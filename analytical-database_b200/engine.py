@@ -137,6 +137,8 @@ class Engine:
         "adb_peer_connect": (C.c_int32, [C.c_char_p]),
         "adb_agg_combine_allreduce": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_peer_destroy": (C.c_int32, []),
+        "adb_chain_select_fetch_agg_exchange": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P,
+                                                            C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct)]),
         "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_sub": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
         "adb_chain_select_fetch_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P, C.POINTER(_AggStruct)]),

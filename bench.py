@@ -177,6 +177,10 @@ def run_reference(args):
     return 0
 
 
+def lib_early(eng):
+    return eng.lib
+
+
 def workload_config(args, rows_per_step):
     return {
         "workload": "BASELINE config 5: 4B-row multi-column int32 table row-partitioned "
@@ -213,6 +217,10 @@ def run_engine(args):
 
     if dist is not None and args.exchange == "peer":
         eng.peer_setup(dist)                    # map every rank's aggregate mailbox (NVLink P2P)
+    if dist is None and args.exchange_self:     # debug: the exchange kernel variant at world size 1
+        hbuf = C.create_string_buffer(64)
+        eng._ck(lib_early(eng).adb_peer_create(1, 0, hbuf))
+        eng._ck(lib_early(eng).adb_peer_connect(hbuf.raw))
 
     lo, hi = predicate(args.selectivity)
     shard_rows = TOTAL_ROWS // N_SHARDS
@@ -238,21 +246,28 @@ def run_engine(args):
     AggP = eng.agg_ptr
 
     def step(mark_base=None):
+        fused_exchange = (dist is not None and args.exchange == "peer") or (dist is None and args.exchange_self)
         for i, (c1, c2) in enumerate(cols):
             pos, val, cnt = res[i]
             if mark_base is not None:
                 eng._ck(lib.adb_chain_marks(mark_base + 3 * i))
             # predicate pass + expansion with the gather and the aggregates fused in; the
             # position list and the fetched vector are still materialised (pos, val)
-            eng._ck(lib.adb_chain_select_fetch_agg(c1.i32(), c2.i32(), shard_rows, C.byref(blo),
-                                                   C.byref(bhi), pos.i32(), val.i32(), cnt.i64(),
-                                                   AggP(parts, i)))
-        if dist is None:
+            if fused_exchange and i == len(cols) - 1:
+                # the rank's last shard: the CTA that completes its aggregate also folds the
+                # earlier shards' partials and swaps the result with every peer over NVLink
+                # peer memory, inside the same kernel (csrc/peer_agg.cu, adb_common.cuh)
+                eng._ck(lib.adb_chain_select_fetch_agg_exchange(
+                    c1.i32(), c2.i32(), shard_rows, C.byref(blo), C.byref(bhi), pos.i32(), val.i32(),
+                    cnt.i64(), AggP(parts), len(cols), AggP(combined)))
+            else:
+                eng._ck(lib.adb_chain_select_fetch_agg(c1.i32(), c2.i32(), shard_rows, C.byref(blo),
+                                                       C.byref(bhi), pos.i32(), val.i32(), cnt.i64(),
+                                                       AggP(parts, i)))
+        if fused_exchange:
+            pass
+        elif dist is None:
             eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
-        elif args.exchange == "peer":
-            # fold this rank's shard partials and swap them with every peer inside one
-            # kernel, over NVLink peer memory (csrc/peer_agg.cu)
-            eng._ck(lib.adb_agg_combine_allreduce(AggP(parts), len(cols), AggP(combined), None))
         else:
             eng._ck(lib.adb_agg_combine(AggP(parts), len(cols), AggP(combined), None))
             eng._ck(lib.adb_agg_export(AggP(combined), C.c_void_p(t_sum.data_ptr()),
@@ -268,8 +283,14 @@ def run_engine(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    # CUDA events between the chain's two launches give the live per-kernel times for the
+    # roofline object, but an event record between two kernels also keeps the second one from
+    # being scheduled while the first drains (programmatic dependent launch), so only every
+    # fourth timed step carries them
     marks_per_step = 3 * len(cols)
-    timed_marks = args.steps * marks_per_step <= 8000
+    MARK_EVERY = 4
+    marked_steps = [k for k in range(args.steps) if k % MARK_EVERY == 0]
+    timed_marks = len(marked_steps) * marks_per_step <= 8000
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -278,7 +299,7 @@ def run_engine(args):
     barrier()
     e0.record(stream)
     for k in range(args.steps):
-        step(k * marks_per_step if timed_marks else None)
+        step((k // MARK_EVERY) * marks_per_step if timed_marks and k % MARK_EVERY == 0 else None)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -309,7 +330,7 @@ def run_engine(args):
     hits_local = [int(r[2].to_host(1, np.int64)[0]) for r in res]
     mask_ms, fused_ms = [], []
     if timed_marks:
-        for k in range(args.steps):
+        for k in range(len(marked_steps)):
             for i in range(len(cols)):
                 b = k * marks_per_step + 3 * i
                 mask_ms.append(eng.mark_elapsed(b, b + 1))
@@ -333,11 +354,11 @@ def run_engine(args):
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "share_of_step": float(np.sum(mask_ms) / ms_total),
+                    "share_of_step": float(np.mean(mask_ms) * len(cols) / ms_step),
                     "second_kernel": {
                         "kernel": "adb::expand_kernel<false,true> (bitmap -> positions, gather, "
                                   "sum/min/max fused)",
-                        "avg_launch_ms": f_ms, "share_of_step": float(np.sum(fused_ms) / ms_total),
+                        "avg_launch_ms": f_ms, "share_of_step": float(f_ms * len(cols) / ms_step),
                         "algorithmic_bytes_per_launch": 16.0 * h_avg,
                         "achieved": 16.0 * h_avg / (f_ms * 1e-3) / 1e9,
                         "line_granular_bytes_per_launch": 128.0 * h_avg + 8.0 * h_avg + shard_rows / 8.0,
@@ -363,7 +384,7 @@ def run_engine(args):
         }
         if world > 1:
             line["config"]["aggregate_exchange"] = (
-                "adb_agg_combine_allreduce: local fold + exchange in one kernel over NVLink peer memory"
+                "adb_chain_select_fetch_agg_exchange: the chain kernel of the rank's last shard folds the partials and exchanges them over NVLink peer memory (no separate launch, no NCCL call)"
                 if args.exchange == "peer" else "adb_agg_export + 2 NCCL all-reduces")
 
     # ---- selectivity sweep on one shard (SURVEY.md 8d lists 0.1 %, 1 %, 10 %, 50 %) -----------
@@ -680,6 +701,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: aggregate exchange through the engine's peer-memory kernel or NCCL")
+    ap.add_argument("--exchange-self", action="store_true",
+                    help="debug (N = 1): run the last shard through the exchange-carrying chain kernel")
     ap.add_argument("--ops", action="store_true",
                     help="also time shared scan / index / join at the BASELINE config sizes")
     args = ap.parse_args()

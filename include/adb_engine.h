@@ -181,6 +181,16 @@ ADB_API adb_status adb_peer_create(int32_t world, int32_t rank, unsigned char *h
 ADB_API adb_status adb_peer_connect(const unsigned char *handles);
 ADB_API adb_status adb_agg_combine_allreduce(const adb_agg *d_parts, int32_t k, adb_agg *d_out,
                                              adb_agg *h_out);
+/* The north-star chain of this rank's LAST shard of a step with the exchange fused in: the
+ * shard's partial goes to d_parts[k-1] (earlier shards of the step filled d_parts[0..k-1)
+ * through adb_chain_select_fetch_agg), and the CTA that completes it folds all k partials and
+ * exchanges them with every peer in the same kernel: no launch and no collective call is left
+ * between the last gather and the table-wide result in d_out.  Collective. */
+ADB_API adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col, const int32_t *d_fetch_col,
+                                                       int64_t n, const int32_t *lo, const int32_t *hi,
+                                                       int32_t *d_pos_out, int32_t *d_val_out,
+                                                       int64_t *d_count, adb_agg *d_parts, int32_t k,
+                                                       adb_agg *d_out);
 ADB_API adb_status adb_peer_destroy(void);
 
 /* ---- element-wise add / sub -- replace add / sub, src/query.c:356-390 (int32, wraps) */

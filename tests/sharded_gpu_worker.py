@@ -40,6 +40,28 @@ def main():
     ops.connect_peers(dist)
     res["agg_peer"] = [t.aggregate(f) for _ in range(5)]      # one kernel over NVLink peer memory
     res["agg_peer_empty"] = t.aggregate(f[:0])
+    # the chain with the exchange fused into its last kernel: this rank's rows as two shards
+    import ctypes as C
+    from analytical_database_b200.engine import _AggStruct
+    rows = e - b
+    half = rows // 2
+    c1, c2 = t.cols["c1"], t.cols["c2"]
+    pos, val = ops.empty(rows), ops.empty(rows)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    parts = torch.zeros(3 * 2, dtype=torch.int64, device=dev)          # 2 x adb_agg (24 bytes each)
+    agg_out = torch.zeros(3, dtype=torch.int64, device=dev)
+    P = lambda x, ty=C.c_int32, off=0: C.cast(C.c_void_p(x.data_ptr() + off), C.POINTER(ty))
+    lo, hi = C.c_int32(-n // 20), C.c_int32(n // 10)
+    res["agg_fused"] = []
+    for _ in range(3):
+        eng._ck(eng.lib.adb_chain_select_fetch_agg(P(c1), P(c2), half, C.byref(lo), C.byref(hi), P(pos), P(val),
+                                                   P(cnt, C.c_int64), P(parts, _AggStruct)))
+        eng._ck(eng.lib.adb_chain_select_fetch_agg_exchange(
+            P(c1, off=4 * half), P(c2, off=4 * half), rows - half, C.byref(lo), C.byref(hi), P(pos), P(val),
+            P(cnt, C.c_int64), P(parts, _AggStruct), 2, P(agg_out, _AggStruct)))
+        torch.cuda.synchronize()
+        h = _AggStruct.from_buffer_copy(agg_out.cpu().numpy().tobytes())
+        res["agg_fused"].append({"sum": h.sum, "count": h.count, "min": h.min, "max": h.max})
     res["pos"] = t.gather_global(s.local, s.base).cpu().numpy()
     res["off"] = (s.offset, s.total, s.local.numel())
     lows = [-100, 0, n // 4, 7]

@@ -81,6 +81,8 @@ def test_nccl_shards_equal_one_shard(port, tmp_path):
     assert (a["sum"], a["count"], a["min"], a["max"], a["avg"]) == \
         (port.sum(vals), pos.size, port.min(vals), port.max(vals), port.avg(vals))
     assert all(x == a for x in res["agg_peer"])           # peer-memory exchange == NCCL exchange
+    for x in res["agg_fused"]:                              # chain kernel with the exchange as its epilogue
+        assert (x["sum"], x["count"], x["min"], x["max"]) == (a["sum"], a["count"], a["min"], a["max"])
     e = res["agg_peer_empty"]
     assert (e["sum"], e["count"]) == (0, 0) and e["avg"] != e["avg"]
     exp = port.shared_select(tab["c1"], [-100, 0, n // 4, 7], [100, n // 16, n // 4 + n // 50, 3])
