@@ -355,7 +355,19 @@ struct SharedScanPlan {
     const uint8_t *cov_q;      // covering query ids, ascending inside an interval
     uint32_t m;
     uint32_t q_count;
+    // host-built lookup tables over d = v - lo, d in [0, span):
+    const uint16_t *lut;       // kSsLut + 1 entries: bounds below the edge of bucket d >> lut_shift
+                               // (bit 15: no query reaches into the bucket)
+    const uint32_t *bits;      // kSsBits bits: bucket d >> bit_shift is touched by some query
+    uint32_t lut_shift, bit_shift;
+    int32_t lo;                // bounds[0]
+    uint32_t span;             // bounds[m-1] - bounds[0]
+    // query q covers the contiguous interval ids q_first[q] .. q_last[q] (first >= 1; first >
+    // last for an empty query): its hit count is a difference of interval-count prefix sums
+    const uint16_t *q_first, *q_last;
 };
+constexpr uint32_t kSsLut = 1024;
+constexpr uint32_t kSsBits = 1u << 16;
 struct SharedScanGeom {
     uint32_t chunk_rows, num_chunks, grid;
 };

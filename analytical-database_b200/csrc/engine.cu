@@ -758,7 +758,11 @@ adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col, const i
 constexpr size_t kSsBoundsBytes = 4 * 2 * ADB_MAX_BATCH;                 // 1200
 constexpr size_t kSsOffBytes = 2 * (2 * ADB_MAX_BATCH + 2);              // 604 -> padded to 640
 constexpr size_t kSsCovBytes = 2 * ADB_MAX_BATCH * ADB_MAX_BATCH;        // 45000
-constexpr size_t kSsPlanBytes = kSsBoundsBytes + 640 + kSsCovBytes;
+constexpr size_t kSsLutOff = kSsBoundsBytes + 640 + ((kSsCovBytes + 15) / 16) * 16;
+constexpr size_t kSsLutBytes = ((2 * (adb::kSsLut + 1) + 15) / 16) * 16;
+constexpr size_t kSsBitsOff = kSsLutOff + kSsLutBytes;
+constexpr size_t kSsQOff = kSsBitsOff + adb::kSsBits / 8;            // q_first | q_last, uint16 each
+constexpr size_t kSsPlanBytes = kSsQOff + 2 * 2 * ((ADB_MAX_BATCH + 7) / 8) * 8;
 constexpr size_t kSsMaxChunks = 8192;
 
 adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
@@ -794,16 +798,68 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
     }
     if (m >= 1) off[m + 1] = (uint16_t)cov.size();
     if (m == 0) off[1] = 0;
-    if (m) CU(cudaMemcpyAsync(g.ss_plan_mem, bounds, m * sizeof(int32_t), cudaMemcpyHostToDevice, g.stream));
-    CU(cudaMemcpyAsync(g.ss_plan_mem + kSsBoundsBytes, off.data(), off.size() * sizeof(uint16_t),
-                       cudaMemcpyHostToDevice, g.stream));
-    if (!cov.empty())
-        CU(cudaMemcpyAsync(g.ss_plan_mem + kSsBoundsBytes + 640, cov.data(), cov.size(),
-                           cudaMemcpyHostToDevice, g.stream));
-    CU(cudaStreamSynchronize(g.stream));                    // host vectors go out of scope
+    // one packed upload: bounds | cov_off | cov_q.  The source is pageable, so the call returns
+    // once the bytes sit in the driver's staging memory: no synchronisation needed before the
+    // host vector goes out of scope.
+    uint32_t lut_shift = 0, bit_shift = 0, span = 0;
+    {
+        std::vector<unsigned char> plan(kSsPlanBytes, 0);
+        if (m) memcpy(plan.data(), bounds, m * sizeof(int32_t));
+        memcpy(plan.data() + kSsBoundsBytes, off.data(), off.size() * sizeof(uint16_t));
+        if (!cov.empty()) memcpy(plan.data() + kSsBoundsBytes + 640, cov.data(), cov.size());
+        // value -> interval tables over d = v - bounds[0] in [0, span)
+        uint16_t *lut = reinterpret_cast<uint16_t *>(plan.data() + kSsLutOff);
+        uint32_t *bits = reinterpret_cast<uint32_t *>(plan.data() + kSsBitsOff);
+        if (m) {
+            const uint32_t ulo = (uint32_t)bounds[0];
+            span = (uint32_t)bounds[m - 1] - ulo;
+            while ((span >> lut_shift) >= adb::kSsLut) ++lut_shift;
+            while ((span >> bit_shift) >= adb::kSsBits) ++bit_shift;
+            // lut[k] = number of bounds strictly below the lower edge of bucket k
+            uint32_t a = 0;
+            for (uint32_t k = 0; k <= adb::kSsLut; ++k) {
+                const uint64_t edge = (uint64_t)k << lut_shift;
+                while (a < m && (uint64_t)((uint32_t)bounds[a] - ulo) < edge) ++a;
+                lut[k] = (uint16_t)a;
+            }
+            // interval ids reachable from bucket k: lut[k] .. lut[k+1]; none covered -> bit 15
+            std::vector<uint16_t> flagged(adb::kSsLut);
+            for (uint32_t k = 0; k < adb::kSsLut; ++k) {
+                bool covered = false;
+                for (uint32_t i = lut[k]; i <= lut[k + 1] && !covered; ++i) covered = off[i + 1] != off[i];
+                flagged[k] = covered ? lut[k] : (uint16_t)(lut[k] | 0x8000u);
+            }
+            memcpy(lut, flagged.data(), sizeof(uint16_t) * adb::kSsLut);
+            // fine bitmap: every bucket a covered interval [bounds[k-1], bounds[k]) reaches into
+            for (uint32_t k = 1; k < m; ++k) {
+                if (off[k + 1] == off[k]) continue;
+                const uint32_t t0 = ((uint32_t)bounds[k - 1] - ulo) >> bit_shift;
+                const uint32_t t1 = ((uint32_t)bounds[k] - 1u - ulo) >> bit_shift;
+                for (uint32_t t = t0; t <= t1; ++t) bits[t >> 5] |= 1u << (t & 31);
+            }
+        }
+        // interval id k = [bounds[k-1], bounds[k]): query q = [low, high) covers ids
+        // (index of low) + 1 .. (index of high)
+        uint16_t *qf = reinterpret_cast<uint16_t *>(plan.data() + kSsQOff);
+        uint16_t *ql = qf + ((ADB_MAX_BATCH + 7) / 8) * 8;
+        for (int32_t q = 0; q < q_count; ++q) {
+            qf[q] = 1;
+            ql[q] = 0;
+            if (lows[q] < highs[q]) {
+                qf[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, lows[q]) - bounds + 1);
+                ql[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, highs[q]) - bounds);
+            }
+        }
+        CU(cudaMemcpyAsync(g.ss_plan_mem, plan.data(), plan.size(), cudaMemcpyHostToDevice, g.stream));
+    }
     g.ss_plan = adb::SharedScanPlan{reinterpret_cast<const int32_t *>(g.ss_plan_mem),
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsBoundsBytes),
-                                    g.ss_plan_mem + kSsBoundsBytes + 640, m, (uint32_t)q_count};
+                                    g.ss_plan_mem + kSsBoundsBytes + 640, m, (uint32_t)q_count,
+                                    reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsLutOff),
+                                    reinterpret_cast<const uint32_t *>(g.ss_plan_mem + kSsBitsOff),
+                                    lut_shift, bit_shift, m ? bounds[0] : 0, span,
+                                    reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff),
+                                    reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff) + ((ADB_MAX_BATCH + 7) / 8) * 8};
     if (n == 0) {
         for (int32_t q = 0; q < q_count; ++q) if (h_counts) h_counts[q] = 0;
         g.ss_geom = adb::SharedScanGeom{0, 0, 0};
@@ -837,8 +893,7 @@ adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity) 
     g.ss_ready = false;
     if (g.ss_geom.num_chunks == 0) return ADB_OK;
     CU(cudaMemcpyAsync(g.ss_outs, d_out_ptrs, sizeof(int32_t *) * g.ss_plan.q_count,
-                       cudaMemcpyHostToDevice, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+                       cudaMemcpyHostToDevice, g.stream));      // pageable source: staged before return
     const int k_ = adb::launch_shared_emit(g.ss_hits, g.ss_chunk_hits, g.ss_plan, g.ss_geom, g.ss_counts,
                                            g.ss_outs, capacity, g.stream);
     return after_launch("shared_emit", k_);

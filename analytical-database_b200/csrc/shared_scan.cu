@@ -8,10 +8,10 @@
 //   host       the <= 2Q distinct bounds cut the value domain into elementary intervals;
 //              every interval knows the (few) queries that cover it (a CSR list, query
 //              ids ascending);
-//   classify   one streaming pass: a 1024-entry shared-memory table dismisses rows no query
-//              wants with one read; candidate rows are compacted per warp and resolved
-//              densely (exact interval, per-warp-chunk per-query counters, one packed
-//              {interval, row} entry in the chunk's hit list);
+//   classify   one streaming pass: a 64 K-bucket bitmap in shared memory dismisses rows no
+//              query wants with one bit test; candidate rows are compacted per warp and
+//              resolved densely (exact interval, per-warp-chunk per-query counters, one
+//              packed {interval, row} entry in the chunk's hit list);
 //   offsets    one CTA per query scans its row of the [query][chunk] count matrix;
 //   emit       each warp walks its chunk's hit list and queues (query, row) pairs in row
 //              order; 32 pairs at a time are ranked per query (one ballot per
@@ -37,7 +37,8 @@ constexpr int SS_QUEUE = 256;                     // (query, row) pairs parked p
 // [bounds[0], bounds[m-1]) gives the id at the lower edge of v's bucket; a short forward walk
 // (or a binary search inside the bucket when many bounds crowd into it) finishes the job --
 // one subtraction, one shift and two or three shared-memory reads for typical batches,
-// against log2(2Q) dependent probes for a plain binary search.
+// against log2(2Q) dependent probes for a plain binary search.  The table is built once on
+// the host (engine.cu) and copied into shared memory by every CTA.
 struct SsLookup {
     const int32_t *bounds;
     const uint16_t *lut;                          // SS_LUT + 1 entries
@@ -64,79 +65,84 @@ __device__ __forceinline__ uint32_t interval_of(const SsLookup &L, int32_t v) {
     return lo;
 }
 
-// Every CTA rebuilds the table from the bounds (m <= 300: a few hundred instructions).  A
-// bucket none of whose intervals is covered by a query gets bit 15: its rows are classified
-// as interval 0 (= no hit) after a single table read -- most rows of a selective batch.
-__device__ __forceinline__ SsLookup build_lookup(const SharedScanPlan &plan, int32_t *s_bounds,
-                                                 uint16_t *s_lut, const uint16_t *s_off) {
-    for (uint32_t i = threadIdx.x; i < plan.m; i += SS_THREADS) s_bounds[i] = plan.bounds[i];
-    __syncthreads();
-    SsLookup L{s_bounds, s_lut, plan.m, 0u, 0, 0};
-    if (plan.m) {
-        L.lo = s_bounds[0];
-        L.hi = s_bounds[plan.m - 1];
-        const uint32_t span = (uint32_t)L.hi - (uint32_t)L.lo;
-        while ((span >> L.shift) >= (uint32_t)SS_LUT) ++L.shift;
-        for (uint32_t k = threadIdx.x; k <= (uint32_t)SS_LUT; k += SS_THREADS) {
-            // number of bounds <= lo + (k << shift) - 1, i.e. strictly below the bucket's edge,
-            // plus those equal to the edge are found by the forward walk
-            const uint64_t edge = (uint64_t)k << L.shift;
-            uint32_t a = 0, b = plan.m;
-            while (a < b) {
-                const uint32_t mid = (a + b) >> 1;
-                if ((uint64_t)((uint32_t)s_bounds[mid] - (uint32_t)L.lo) < edge) a = mid + 1; else b = mid;
-            }
-            s_lut[k] = (uint16_t)a;
-        }
-        __syncthreads();
-        uint16_t flagged[(SS_LUT + SS_THREADS - 1) / SS_THREADS];
-        for (uint32_t k = threadIdx.x, t = 0; k < (uint32_t)SS_LUT; k += SS_THREADS, ++t) {
-            bool covered = false;                  // ids reachable from bucket k: lut[k] .. lut[k+1]
-            for (uint32_t i = s_lut[k]; i <= s_lut[k + 1] && !covered; ++i) covered = s_off[i + 1] != s_off[i];
-            flagged[t] = covered ? s_lut[k] : (uint16_t)(s_lut[k] | 0x8000u);
-        }
-        __syncthreads();
-        for (uint32_t k = threadIdx.x, t = 0; k < (uint32_t)SS_LUT; k += SS_THREADS, ++t) s_lut[k] = flagged[t];
-    }
-    __syncthreads();
-    return L;
-}
-
 // Classify + count.  The common case of a selective batch is a row no query wants: it is
-// dismissed branch-free with one table read (bit 15 of the bucket entry).  The few rows that
-// may hit are compacted, in row order, into a per-warp work list and then resolved with all
-// lanes busy: exact interval, per-query counters, and -- if at least one query covers the
-// interval -- one packed {interval, row} entry appended to the chunk's hit list in global
-// memory.  The emit pass reads that list instead of the column.
-constexpr int SS_WORK = SS_WTILE;                 // work-list entries per warp: one tile's worth
+// dismissed branch-free with one bit test in a 64 K-bucket bitmap over the value domain
+// (8 KB of shared memory; a bucket is set when some query reaches into it, so what survives
+// is the hits plus the rows in the two edge buckets of every query -- r01l's 1024-bucket
+// table let twice as many rows through as really hit).  Survivors are compacted, in row
+// order, into a per-warp work list that is only resolved when it cannot take another 128
+// rows, so the expensive part always runs on full warps: exact interval, per-query
+// counters, and -- if at least one query covers the interval -- one packed
+// {interval, row} entry appended to the chunk's hit list in global memory.  The emit pass
+// reads that list instead of the column.
+constexpr int SS_WORK = SS_WTILE;                 // work-list entries per warp
+constexpr int SS_BITWORDS = kSsBits / 32;         // 2048
+static_assert(SS_LUT == (int)kSsLut, "host and device agree on the table size");
+
+struct SsShared {                                  // carved out of dynamic shared memory
+    uint32_t bits[SS_BITWORDS + 4];                // [SS_BITWORDS] stays 0: where values past the last bound land
+    uint2 work[SS_WARPS][SS_WORK];
+    uint32_t cnt[SS_WARPS][SS_BMAX + 4];           // hits per INTERVAL id (0 .. m), per warp
+    int32_t bounds[SS_BMAX];
+    uint16_t lut[SS_LUT + 2];
+    uint16_t off[SS_BMAX + 2];
+};
+
+// resolve work[0 .. wcount): all lanes busy except in the last batch
+__device__ __forceinline__ uint32_t ss_resolve(const SsLookup &L, const uint16_t *s_off, const uint2 *work,
+                                               uint32_t wcount, uint32_t *my_cnt,
+                                               uint32_t *__restrict__ my_hits, uint32_t nhits,
+                                               uint32_t lane, uint32_t lt) {
+    for (uint32_t base = 0; base < wcount; base += kWarp) {
+        const bool live = base + lane < wcount;
+        uint32_t id = 0, rel = 0, b = 0, e = 0;
+        if (live) {
+            const uint2 w = work[base + lane];
+            rel = w.y;
+            id = interval_of(L, (int32_t)w.x);
+            b = s_off[id];
+            e = s_off[id + 1];
+        }
+        // hits are counted per interval here; a query covers a contiguous run of intervals, so
+        // its count is a difference of two prefix sums, taken once per chunk
+        const uint32_t m = __ballot_sync(kFull, e > b);
+        if (e > b) {
+            atomicAdd(&my_cnt[id], 1u);
+            my_hits[nhits + __popc(m & lt)] = (id << 23) | rel;           // rel < 2^23, id <= 300
+        }
+        nhits += __popc(m);
+    }
+    return nhits;
+}
 
 __global__ void __launch_bounds__(SS_THREADS)
 ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan plan,
                    uint32_t chunk_rows, uint32_t num_chunks, uint32_t *__restrict__ hitlist,
                    uint32_t *__restrict__ chunk_hits, uint32_t *__restrict__ counts /* [q][num_chunks] */) {
-    __shared__ int32_t s_bounds[SS_BMAX];
-    __shared__ uint16_t s_lut[SS_LUT + 1];
-    __shared__ uint16_t s_off[SS_BMAX + 2];
-    __shared__ uint32_t s_cnt[SS_WARPS][SS_QMAX];
-    __shared__ uint2 s_work[SS_WARPS][SS_WORK];
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    SsShared &S = *reinterpret_cast<SsShared *>(ss_smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < plan.m + 2; i += SS_THREADS) s_off[i] = plan.cov_off[i];
-    for (uint32_t i = threadIdx.x; i < SS_WARPS * SS_QMAX; i += SS_THREADS) (&s_cnt[0][0])[i] = 0;
+    for (uint32_t i = threadIdx.x; i < SS_BITWORDS / 4; i += SS_THREADS)
+        reinterpret_cast<uint4 *>(S.bits)[i] = reinterpret_cast<const uint4 *>(plan.bits)[i];
+    for (uint32_t i = threadIdx.x; i < SS_LUT + 1; i += SS_THREADS) S.lut[i] = plan.lut[i];
+    for (uint32_t i = threadIdx.x; i < plan.m; i += SS_THREADS) S.bounds[i] = plan.bounds[i];
+    for (uint32_t i = threadIdx.x; i < plan.m + 2; i += SS_THREADS) S.off[i] = plan.cov_off[i];
+    for (uint32_t i = threadIdx.x; i < SS_WARPS * (SS_BMAX + 4); i += SS_THREADS) (&S.cnt[0][0])[i] = 0;
+    if (threadIdx.x < 4) S.bits[SS_BITWORDS + threadIdx.x] = 0;
     __syncthreads();
-    const SsLookup L = build_lookup(plan, s_bounds, s_lut, s_off);
+    const SsLookup L{S.bounds, S.lut, plan.m, plan.lut_shift, plan.lo, (int32_t)((uint32_t)plan.lo + plan.span)};
     const uint32_t chunk = blockIdx.x * SS_WARPS + warp;
     if (chunk >= num_chunks) return;
     const uint32_t row_begin = chunk * chunk_rows;
     const uint32_t tiles = chunk_rows / SS_WTILE;
     const bool aligned = (reinterpret_cast<uintptr_t>(val) & 15u) == 0;
-    uint32_t *my_cnt = s_cnt[warp];
-    uint2 *work = s_work[warp];
+    uint32_t *my_cnt = S.cnt[warp];
+    uint2 *work = S.work[warp];
+    const uint32_t *bits = S.bits;
     uint32_t *__restrict__ my_hits = hitlist + (size_t)chunk * chunk_rows;
-    const uint8_t *__restrict__ cov_q = plan.cov_q;
-    const uint32_t ulo = (uint32_t)L.lo;
-    const uint32_t span = L.m ? (uint32_t)L.hi - ulo : 0u;      // values in [lo, hi) can hit
+    const uint32_t ulo = (uint32_t)plan.lo, bsh = plan.bit_shift;
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t nhits = 0;                                         // uniform across the warp
+    uint32_t nhits = 0, wcount = 0;                             // uniform across the warp
 
     for (uint32_t t = 0; t < tiles; ++t) {
         const uint32_t row0 = row_begin + t * SS_WTILE;
@@ -161,21 +167,28 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
                     v[4 * j + k] = ok ? ld_stream(val + r) : 0;
                 }
         }
-        uint32_t wcount = 0;                                     // uniform
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t need = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t d = (uint32_t)v[4 * j + k] - ulo;
-                const uint32_t e = d < span ? (uint32_t)s_lut[d >> L.shift] : 0x8000u;
-                need |= (e & 0x8000u) ? 0u : 1u << k;
+                // bucket of d = v - lo, saturated at kSsBits: everything at or past the last
+                // bound (and, by wrap-around, everything below the first) reads the zero word
+                const uint32_t tb = min(((uint32_t)v[4 * j + k] - ulo) >> bsh, kSsBits);
+                const uint32_t w = bits[tb >> 5];
+                need |= (__funnelshift_r(w, 0u, tb) & 1u) << k;           // shift count taken mod 32
             }
             need &= okmask >> (4 * j);
             const uint32_t c = __popc(need);
             const uint32_t incl = warp_incl_scan(c, lane);
             const uint32_t tot = __shfl_sync(kFull, incl, 31);
             if (tot == 0) continue;
+            if (wcount + tot > (uint32_t)SS_WORK) {            // no room for this group: resolve first
+                __syncwarp();
+                nhits = ss_resolve(L, S.off, work, wcount, my_cnt, my_hits, nhits, lane, lt);
+                wcount = 0;
+                __syncwarp();
+            }
             uint32_t slot = wcount + incl - c;
             const uint32_t rel0 = t * SS_WTILE + j * 128 + lane * 4;     // row within the chunk
 #pragma unroll
@@ -183,29 +196,28 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
                 if (need & (1u << k)) work[slot++] = make_uint2((uint32_t)v[4 * j + k], rel0 + k);
             wcount += tot;
         }
-        if (wcount == 0) continue;
+    }
+    if (wcount) {
         __syncwarp();
-        for (uint32_t base = 0; base < wcount; base += kWarp) {
-            const bool live = base + lane < wcount;
-            uint32_t id = 0, rel = 0, b = 0, e = 0;
-            if (live) {
-                const uint2 w = work[base + lane];
-                rel = w.y;
-                id = interval_of(L, (int32_t)w.x);
-                b = s_off[id];
-                e = s_off[id + 1];
-            }
-            for (uint32_t c = b; c < e; ++c) atomicAdd(&my_cnt[cov_q[c]], 1u);
-            const uint32_t m = __ballot_sync(kFull, e > b);
-            if (e > b) my_hits[nhits + __popc(m & lt)] = (id << 23) | rel;   // rel < 2^23, id <= 300
-            nhits += __popc(m);
-        }
-        __syncwarp();
+        nhits = ss_resolve(L, S.off, work, wcount, my_cnt, my_hits, nhits, lane, lt);
     }
     if (lane == 0) chunk_hits[chunk] = nhits;
     __syncwarp();
-    for (uint32_t q = lane; q < plan.q_count; q += kWarp)
-        counts[(size_t)q * num_chunks + chunk] = my_cnt[q];
+    // inclusive prefix over the interval counters (ids 0 .. m), in place
+    uint32_t carry = 0;
+    for (uint32_t i0 = 0; i0 <= plan.m; i0 += kWarp) {
+        const uint32_t i = i0 + lane;
+        const uint32_t x = i <= plan.m ? my_cnt[i] : 0u;
+        const uint32_t incl = warp_incl_scan(x, lane) + carry;
+        if (i <= plan.m) my_cnt[i] = incl;
+        carry = __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
+    // query q covers intervals first[q] .. last[q] (ids; empty when first > last)
+    for (uint32_t q = lane; q < plan.q_count; q += kWarp) {
+        const uint32_t a = plan.q_first[q], b = plan.q_last[q];
+        counts[(size_t)q * num_chunks + chunk] = a <= b ? my_cnt[b] - my_cnt[a - 1] : 0u;
+    }
 }
 
 // One CTA per query: exclusive scan of its counts row in place, total to totals[q].
@@ -352,8 +364,13 @@ SharedScanGeom shared_scan_geom(uint32_t n, int sm_count) {
 int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan &plan,
                            const SharedScanGeom &g, uint32_t *hitlist, uint32_t *chunk_hits,
                            uint32_t *counts, int64_t *totals, cudaStream_t s) {
-    ss_classify_kernel<<<g.grid, SS_THREADS, 0, s>>>(val, n, plan, g.chunk_rows, g.num_chunks,
-                                                     hitlist, chunk_hits, counts);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ss_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsShared));
+        attr_set = true;
+    }
+    ss_classify_kernel<<<g.grid, SS_THREADS, sizeof(SsShared), s>>>(val, n, plan, g.chunk_rows, g.num_chunks,
+                                                                    hitlist, chunk_hits, counts);
     ss_offsets_kernel<<<plan.q_count, 1024, 0, s>>>(counts, g.num_chunks, totals);
     return 2;
 }
