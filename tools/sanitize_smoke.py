@@ -74,6 +74,37 @@ def main():
     counts = (C.c_int64 * 8)()
     eng._ck(eng.lib.adb_route_pairs(d[0].i32(), d[1].i32(), 20_000, 8, ov.i32(), op.i32(), counts))
     assert sum(counts) == 20_000
+    # a skewed join: one heavy key overflows the shared-memory table (global-slot path)
+    k3 = np.where(rng.random(12_000) < 0.6, 7, rng.integers(1, 500, 12_000)).astype(np.int32)
+    q3 = np.arange(12_000, dtype=np.int32)
+    d3 = [eng.upload(x) for x in (k3, q3)]
+    o1, o2, m = eng.join(d3[0], d3[1], 12_000, d[2], d[3], 9_000)
+    e1, e2 = port.hash_join(k3, q3, k2, q2)
+    assert m == e1.size and np.array_equal(o1.to_host(m), e1) and np.array_equal(o2.to_host(m), e2)
+    # bulk load + result text
+    text = ("h\n" + "\n".join(",".join(str(int(x)) for x in r) for r in rng.integers(-10**6, 10**6, (3001, 3))) +
+            "\n 7,abc\n\n9223372036854775808,-5,+3,99").encode()
+    cols, rows = eng.csv_load(text, 3)
+    exp = port.csv_parse(text, 3)
+    assert rows == exp.shape[1]
+    for c, x in zip(cols, exp):
+        assert np.array_equal(c.to_host(rows), x)
+    assert eng.format_i32(cols[0], rows) == port.print_i32(exp[0])
+    # the exchange-carrying chain kernel and the stand-alone exchange, world size 1
+    hbuf = C.create_string_buffer(64)
+    eng._ck(eng.lib.adb_peer_create(1, 0, hbuf))
+    eng._ck(eng.lib.adb_peer_connect(hbuf.raw))
+    dout = eng.alloc(64)
+    for _ in range(3):
+        eng._ck(eng.lib.adb_chain_select_fetch_agg_exchange(da.i32(), db.i32(), n, C.byref(blo), C.byref(bhi),
+                                                            pos.i32(), val.i32(), dcnt.i64(), eng.agg_ptr(dagg), 1,
+                                                            eng.agg_ptr(dout)))
+        g2 = eng.read_agg(dout)
+        assert (g2.sum, g2.count, g2.min, g2.max) == (g.sum, g.count, g.min, g.max)
+    eng._ck(eng.lib.adb_agg_combine_allreduce(eng.agg_ptr(dagg), 1, eng.agg_ptr(dout), None))
+    g2 = eng.read_agg(dout)
+    assert (g2.sum, g2.count) == (g.sum, g.count)
+    eng._ck(eng.lib.adb_peer_destroy())
     eng.sync()
     print("sanitize_smoke ok:", eng.launch_count(), "launches")
     eng.close()
