@@ -419,8 +419,6 @@ int launch_fmt_emit(const int32_t *val, int64_t n, const uint32_t *block_off, un
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s);
 int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff, cudaStream_t s);
-uint32_t hj_smem_tuples();
-uint32_t hj_smem_slots();
 // toff: num_parts + 1 slot offsets (capacity of partition p = toff[p+1] - toff[p], 0 or a
 // power of two); table: toff[num_parts] 16-byte slots
 int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,

@@ -756,7 +756,7 @@ adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col, const i
 
 // ---- batched shared scan -------------------------------------------------------------------
 constexpr size_t kSsBoundsBytes = 4 * 2 * ADB_MAX_BATCH;                 // 1200
-constexpr size_t kSsOffBytes = 2 * (2 * ADB_MAX_BATCH + 2);              // 604 -> padded to 640
+// cov_off: 2 * (2 * ADB_MAX_BATCH + 2) = 604 bytes, padded to 640
 constexpr size_t kSsCovBytes = 2 * ADB_MAX_BATCH * ADB_MAX_BATCH;        // 45000
 constexpr size_t kSsLutOff = kSsBoundsBytes + 640 + ((kSsCovBytes + 15) / 16) * 16;
 constexpr size_t kSsLutBytes = ((2 * (adb::kSsLut + 1) + 15) / 16) * 16;

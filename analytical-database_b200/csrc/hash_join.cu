@@ -28,7 +28,6 @@ namespace adb {
 
 constexpr int HJ_THREADS = 256;
 constexpr uint32_t HJ_SLOTS = 4096;                    // shared-memory table slots
-constexpr uint32_t HJ_SMEM_TUPLES = 3072;              // largest build partition it holds (75 %)
 constexpr uint32_t kHashMul = 0x9E3779B1u;
 
 __device__ __forceinline__ uint32_t hj_pid(uint32_t key, uint32_t part_bits) {
@@ -120,7 +119,7 @@ __device__ __forceinline__ uint32_t hj_mix(uint32_t tag) {
     return (uint32_t)(((unsigned long long)tag * 0x9E3779B97F4A7C15ull) >> 29);
 }
 
-// One CTA per partition.  Partitions of up to HJ_SMEM_TUPLES build rows (capacity <= HJ_SLOTS)
+// One CTA per partition.  Partitions whose slot range is at most HJ_SLOTS (<= 3276 build rows)
 // build in shared memory in ONE phase -- every build row claims / finds its key's slot and
 // adds 1 to the size, the group leader (first row of the run of equal keys) adds its offset
 // in the same atomic -- and stream the finished table out.  Larger partitions (heavy skew)
@@ -263,9 +262,6 @@ int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long l
     hj_geometry_kernel<<<1, 1024, 0, s>>>(off1, num_parts, toff);
     return 1;
 }
-
-uint32_t hj_smem_tuples() { return HJ_SMEM_TUPLES; }
-uint32_t hj_smem_slots() { return HJ_SLOTS; }
 
 int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,
                           const unsigned long long *toff, uint32_t num_parts, uint32_t part_bits,

@@ -177,10 +177,6 @@ def run_reference(args):
     return 0
 
 
-def lib_early(eng):
-    return eng.lib
-
-
 def workload_config(args, rows_per_step):
     return {
         "workload": "BASELINE config 5: 4B-row multi-column int32 table row-partitioned "
@@ -219,8 +215,8 @@ def run_engine(args):
         eng.peer_setup(dist)                    # map every rank's aggregate mailbox (NVLink P2P)
     if dist is None and args.exchange_self:     # debug: the exchange kernel variant at world size 1
         hbuf = C.create_string_buffer(64)
-        eng._ck(lib_early(eng).adb_peer_create(1, 0, hbuf))
-        eng._ck(lib_early(eng).adb_peer_connect(hbuf.raw))
+        eng._ck(eng.lib.adb_peer_create(1, 0, hbuf))
+        eng._ck(eng.lib.adb_peer_connect(hbuf.raw))
 
     lo, hi = predicate(args.selectivity)
     shard_rows = TOTAL_ROWS // N_SHARDS
@@ -610,7 +606,8 @@ def measure_join_sharded(eng, dist, rank, world, local):
 
 def measure_ops(args):
     """The other BASELINE.json configs on one GPU, bounded: batched shared scan (config 2),
-    index range select + fetch (config 3), hash join with prefilters (config 4)."""
+    index range select + fetch (config 3), hash join with prefilters (config 4); plus the two
+    callers next to the path: bulk CSV load and print of a long result."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_ops
     import analytical_database_b200 as adb
@@ -620,6 +617,8 @@ def measure_ops(args):
         out["shared_scan_100q_100M"] = bench_ops.bench_shared(eng, 1.0)
         out["index_500M"] = bench_ops.bench_index(eng, 1.0)
         out["hash_join_100Mx100M"] = bench_ops.bench_join(eng, 1.0)
+        out["csv_load_4M_rows"] = bench_ops.bench_load(eng, 1.0)
+        out["print_50M_values"] = bench_ops.bench_print(eng, 1.0)
     except Exception as e:                                        # the headline line must survive
         out["error"] = repr(e)
     return out
