@@ -124,7 +124,16 @@ struct PeerRecord {
 struct PeerBoxes {
     PeerRecord *box[kMaxPeers];
 };
-constexpr size_t kPeerBoxBytes = sizeof(PeerRecord) * 2 * kMaxPeers;
+// The whole mailbox: the aggregate records first (box[r] points here), then the control words
+// of the join's pair exchange (peer_exchange.cu): every rank's per-destination pair counts
+// and two rows of epoch flags.
+struct PeerCtl {
+    PeerRecord agg[2][kMaxPeers];
+    uint32_t jcnt[2][kMaxPeers][kMaxPeers];          // [bank][source rank][destination rank]
+    uint32_t jcnt_epoch[2][kMaxPeers];               // [bank][source]: its count row has landed
+    uint32_t jdone_epoch[2][kMaxPeers];              // [bank][source]: its pairs have landed
+};
+constexpr size_t kPeerBoxBytes = sizeof(PeerCtl);
 constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;      // 2 s
 
 // What a kernel needs to finish an aggregate across ranks: world == 0 disables it.
@@ -347,6 +356,20 @@ int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_
 constexpr int kAggMaxBlocks = 148 * 8;
 int launch_agg_combine_allreduce(const PeerExchange &px, cudaStream_t s);
 
+// Pair exchange of the sharded hash join over NVLink peer memory (peer_exchange.cu + the
+// REMOTE flavour of the radix scatter): counts all-gather -> every rank scatters its routed
+// pairs straight into the destination ranks' receive buffers -> done flags.
+struct PairExchange {
+    const PeerBoxes *boxes;       // device table of the peers' mailboxes
+    int32_t rank, world;
+    uint32_t epoch;
+    unsigned long long cap;       // pairs a receive region holds
+};
+// status[0]: 0 ok, 1 a receive region would overflow, 2 a peer did not arrive
+int launch_jx_counts(const PairExchange &x, const uint32_t *my_totals, uint32_t *base_out,
+                     int64_t *recv_total_out, uint32_t *status, cudaStream_t s);
+int launch_jx_done(const PairExchange &x, uint32_t *status, cudaStream_t s);
+
 
 // Batched shared scan (shared_scan.cu).  All pointers are device addresses.
 struct SharedScanPlan {
@@ -392,6 +415,15 @@ RadixGeom radix_geom(uint32_t n, int sm_count);
 int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
                       uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
                       uint32_t *base, int sm_count, cudaStream_t s);
+// The same pass split in two for the peer exchange: histogram + per-tile offsets + totals, then
+// a scatter whose bucket d is written into peer_base[d] + key_off / pay_off (uint32 units) at
+// the offsets `base` holds (skipped when *abort_flag != 0).
+int launch_radix_hist(const uint32_t *keys_in, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
+                      int sm_count, cudaStream_t s);
+int launch_radix_scatter_remote(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t n, RadixPass p,
+                                const uint32_t *hist, const uint32_t *base, uint32_t *const *peer_base,
+                                unsigned long long key_off, unsigned long long pay_off,
+                                const uint32_t *abort_flag, int sm_count, cudaStream_t s);
 uint32_t scan_ctas(uint32_t n, int sm_count);
 // in_stride: distance (in uint32) between consecutive inputs (2 reads the .y of a uint2 array)
 int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out, uint32_t n,

@@ -110,6 +110,16 @@ struct Engine {
     int32_t peer_world = 0, peer_rank = -1;
     bool peer_connected = false;
     uint32_t peer_epoch = 0;
+    // pair exchange of the sharded join (adb_peer_join_*): my receive buffer (2 sides x
+    // {values, positions} x jx_cap ints), the peers' mapped buffers, a device table of them
+    int32_t *jx_recv = nullptr;
+    unsigned long long jx_cap = 0;
+    uint32_t *jx_peer_host[ADB_MAX_PEERS] = {};
+    uint32_t **jx_peer_dev = nullptr;
+    bool jx_connected = false;
+    uint32_t jx_epoch = 0;
+    uint32_t *jx_status = nullptr;          // device: 0 ok, 1 overflow, 2 timeout
+    int64_t *jx_total = nullptr;            // device: pairs this rank receives
     int64_t launches = 0;
     int32_t chain_mark_base = -1;       // adb_chain_marks(): slots for the next chain call
 } g;
@@ -184,7 +194,26 @@ adb_status ensure_select_scratch(uint32_t n) {
     return ADB_OK;
 }
 
+void jx_close() {
+    for (int r = 0; r < g.peer_world; ++r)
+        if (r != g.peer_rank && g.jx_peer_host[r]) cudaIpcCloseMemHandle(g.jx_peer_host[r]);
+    if (g.jx_recv) cudaFree(g.jx_recv);
+    if (g.jx_peer_dev) cudaFree(g.jx_peer_dev);
+    if (g.jx_status) cudaFree(g.jx_status);
+    if (g.jx_total) cudaFree(g.jx_total);
+    cudaGetLastError();
+    g.jx_recv = nullptr;
+    g.jx_cap = 0;
+    for (auto &p : g.jx_peer_host) p = nullptr;
+    g.jx_peer_dev = nullptr;
+    g.jx_connected = false;
+    g.jx_epoch = 0;
+    g.jx_status = nullptr;
+    g.jx_total = nullptr;
+}
+
 void peer_close() {
+    jx_close();
     for (int r = 0; r < g.peer_world; ++r)
         if (r != g.peer_rank && g.peer_boxes.box[r]) cudaIpcCloseMemHandle(g.peer_boxes.box[r]);
     if (g.peer_box) cudaFree(g.peer_box);
@@ -665,6 +694,107 @@ adb_status adb_agg_combine_allreduce(const adb_agg *d_parts, int32_t k, adb_agg 
         if (h_out->count < 0)
             return fail(ADB_ERR_CUDA, "adb_agg_combine_allreduce: a peer did not arrive within 2 s (epoch %u)", epoch);
     }
+    return ADB_OK;
+}
+
+// ---- pair exchange of the sharded join over peer memory ---------------------------------------
+static adb_status ensure_radix_scratch(uint32_t n);          // defined with the radix helpers below
+adb_status adb_peer_join_create(int64_t cap_pairs, unsigned char *handle_out) {
+    NEED_UP();
+    if (!g.peer_connected) return fail(ADB_ERR_INVALID, "adb_peer_join_create: adb_peer_connect first");
+    if (cap_pairs < 1 || cap_pairs >= ((int64_t)1 << 31) || !handle_out)
+        return fail(ADB_ERR_INVALID, "adb_peer_join_create: capacity %lld outside [1, 2^31)", (long long)cap_pairs);
+    CU(cudaStreamSynchronize(g.stream));
+    jx_close();
+    const unsigned long long cap = ((unsigned long long)cap_pairs + 63) & ~63ull;     // regions stay 256-byte aligned
+    cudaError_t e = cudaMalloc(&g.jx_recv, cap * 4 * sizeof(int32_t));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join receive buffer (%llu pairs x 4 regions): %s", cap, cudaGetErrorString(e)); }
+    CU(cudaMalloc(&g.jx_peer_dev, sizeof(uint32_t *) * ADB_MAX_PEERS));
+    CU(cudaMalloc(&g.jx_status, 4 * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.jx_total, 2 * sizeof(int64_t)));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, g.jx_recv));
+    memcpy(handle_out, &h, sizeof h);
+    g.jx_cap = cap;
+    g.jx_peer_host[g.peer_rank] = reinterpret_cast<uint32_t *>(g.jx_recv);
+    return ADB_OK;
+}
+
+adb_status adb_peer_join_connect(const unsigned char *handles) {
+    NEED_UP();
+    if (!g.jx_recv || !handles) return fail(ADB_ERR_INVALID, "adb_peer_join_connect: adb_peer_join_create first");
+    for (int r = 0; r < g.peer_world; ++r) {
+        if (r == g.peer_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * ADB_PEER_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ADB_ERR_CUDA, "adb_peer_join_connect: cannot map rank %d's receive buffer: %s", r, cudaGetErrorString(e));
+        }
+        g.jx_peer_host[r] = static_cast<uint32_t *>(p);
+    }
+    CU(cudaMemcpy(g.jx_peer_dev, g.jx_peer_host, sizeof(uint32_t *) * ADB_MAX_PEERS, cudaMemcpyHostToDevice));
+    g.jx_connected = true;
+    g.jx_epoch = 0;
+    return ADB_OK;
+}
+
+adb_status adb_peer_exchange_pairs(int32_t side, const int32_t *d_val, const int32_t *d_pos, int64_t n,
+                                   int64_t *h_recv_count, const int32_t **d_recv_val,
+                                   const int32_t **d_recv_pos) {
+    NEED_UP();
+    if (!g.jx_connected) return fail(ADB_ERR_INVALID, "adb_peer_exchange_pairs: adb_peer_join_connect first");
+    if (adb_status s = check_len(n, "adb_peer_exchange_pairs")) return s;
+    if (side < 0 || side > 1 || !h_recv_count || !d_recv_val || !d_recv_pos || (n > 0 && (!d_val || !d_pos)))
+        return fail(ADB_ERR_INVALID, "adb_peer_exchange_pairs: bad arguments");
+    const int world = g.peer_world;
+    if (world & (world - 1)) return fail(ADB_ERR_INVALID, "adb_peer_exchange_pairs: world size %d is not a power of two", world);
+    int bits = 0;
+    while ((1 << bits) < world) ++bits;
+    if (adb_status s = ensure_radix_scratch((uint32_t)(n ? n : 1))) return s;
+    const adb::RadixPass pass{32 - bits, bits, 2};            // the routing hash of adb_route_pairs
+    const adb::PairExchange x{g.peer_boxes_dev, g.peer_rank, world, ++g.jx_epoch, g.jx_cap};
+    const unsigned long long key_off = (unsigned long long)(2 * side) * g.jx_cap;
+    const unsigned long long pay_off = (unsigned long long)(2 * side + 1) * g.jx_cap;
+    int k_ = 0;
+    if (world == 1) {
+        // no routing digit: every pair stays here (still through the flags: one code path)
+        CU(cudaMemsetAsync(g.rx_totals, 0, sizeof(uint32_t) * 256, g.stream));
+        const uint32_t n32 = (uint32_t)n;
+        CU(cudaMemcpyAsync(g.rx_totals, &n32, sizeof n32, cudaMemcpyHostToDevice, g.stream));
+    } else {
+        k_ += adb::launch_radix_hist(reinterpret_cast<const uint32_t *>(d_val), (uint32_t)n, pass, g.rx_hist,
+                                     g.rx_totals, g.sm_count, g.stream);
+    }
+    k_ += adb::launch_jx_counts(x, g.rx_totals, g.rx_base, g.jx_total, g.jx_status, g.stream);
+    if (world == 1) {
+        if (n) {
+            CU(cudaMemcpyAsync(g.jx_recv + key_off, d_val, (size_t)n * 4, cudaMemcpyDeviceToDevice, g.stream));
+            CU(cudaMemcpyAsync(g.jx_recv + pay_off, d_pos, (size_t)n * 4, cudaMemcpyDeviceToDevice, g.stream));
+        }
+    } else {
+        k_ += adb::launch_radix_scatter_remote(reinterpret_cast<const uint32_t *>(d_val),
+                                               reinterpret_cast<const uint32_t *>(d_pos), (uint32_t)n, pass,
+                                               g.rx_hist, g.rx_base, g.jx_peer_dev, key_off, pay_off,
+                                               g.jx_status, g.sm_count, g.stream);
+    }
+    k_ += adb::launch_jx_done(x, g.jx_status, g.stream);
+    if (adb_status s = after_launch("peer_exchange_pairs", k_)) return s;
+    int64_t total = 0;
+    uint32_t status = 0;
+    CU(cudaMemcpyAsync(&total, g.jx_total, sizeof total, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(&status, g.jx_status, sizeof status, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if (status == 1)
+        return fail(ADB_ERR_NOMEM, "adb_peer_exchange_pairs: a rank would receive more than the %llu pairs its region "
+                    "holds (this rank: %lld); reserve more with adb_peer_join_create", g.jx_cap, (long long)total);
+    if (status == 2) return fail(ADB_ERR_CUDA, "adb_peer_exchange_pairs: a peer did not arrive within 2 s (epoch %u)", x.epoch);
+    *h_recv_count = total;
+    *d_recv_val = g.jx_recv + key_off;
+    *d_recv_pos = g.jx_recv + pay_off;
     return ADB_OK;
 }
 

@@ -90,11 +90,18 @@ constexpr int RX_TILE = RX_THREADS * RX_KPT;             // 4096 rows
 // (r01k tried finding the peers through a per-warp shared-memory table -- atomicOr of the
 // lane bit, sync, read back, leader clears -- instead of one ballot per digit bit: 20.4 ms
 // against 19.6 ms for the 500 M-key sort, so the ballots stayed.)
+// REMOTE: bucket d is a destination rank and is written into that rank's receive buffer over
+// NVLink (peer_base[d] + key_off / pay_off) instead of one local output array; `base` then
+// holds the offset of this rank's piece inside every destination buffer.  The run-contiguous
+// write-out is what makes the remote stores full 128-byte transactions.
+template <bool REMOTE>
 __global__ void __launch_bounds__(RX_THREADS)
 rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
                   uint32_t rows_per_cta, RadixPass p, const uint32_t *__restrict__ hist,
                   const uint32_t *__restrict__ base, uint32_t *__restrict__ keys_out,
-                  uint32_t *__restrict__ pay_out) {
+                  uint32_t *__restrict__ pay_out, uint32_t *const *__restrict__ peer_base,
+                  unsigned long long key_off, unsigned long long pay_off,
+                  const uint32_t *__restrict__ abort_flag) {
     __shared__ uint32_t s_key[RX_TILE];
     __shared__ uint32_t s_pay[RX_TILE];
     __shared__ uint32_t s_wcnt[RX_WARPS][RX_BUCKETS];      // per-warp digit counts -> prefix over warps
@@ -102,7 +109,12 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
     __shared__ uint32_t s_tbase[RX_BUCKETS];               // first tile slot of every digit
     __shared__ uint32_t s_gofs[RX_BUCKETS];                // global address = s_gofs[d] + tile slot
     __shared__ uint32_t s_ws[RX_WARPS];
+    __shared__ uint32_t *s_peer[REMOTE ? kMaxPeers : 1];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (REMOTE) {
+        if (*abort_flag) return;                            // a receive region would overflow
+        if (threadIdx.x < (1u << p.bits)) s_peer[threadIdx.x] = peer_base[threadIdx.x];
+    }
     s_off[threadIdx.x] = base[threadIdx.x] + hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
     const uint32_t begin = blockIdx.x * rows_per_cta;
     const uint32_t end = min(n, begin + rows_per_cta);
@@ -180,9 +192,16 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
         const uint32_t count = min((uint32_t)RX_TILE, end - tile);
         for (uint32_t slot = threadIdx.x; slot < count; slot += RX_THREADS) {
             const uint32_t k = s_key[slot];
-            const uint32_t dst = s_gofs[rx_digit(k, p)] + slot;
-            keys_out[dst] = k;
-            pay_out[dst] = s_pay[slot];
+            const uint32_t d = rx_digit(k, p);
+            const uint32_t dst = s_gofs[d] + slot;
+            if (REMOTE) {
+                uint32_t *pb = s_peer[d];
+                pb[key_off + dst] = k;
+                pb[pay_off + dst] = s_pay[slot];
+            } else {
+                keys_out[dst] = k;
+                pay_out[dst] = s_pay[slot];
+            }
         }
         __syncthreads();
     }
@@ -210,9 +229,32 @@ int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t 
     rx_hist_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
     rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
     rx_bucket_base_kernel<<<1, RX_BUCKETS, 0, s>>>(totals, base);
-    rx_scatter_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, pay_in, n, g.rows_per_cta, p, hist, base,
-                                                    keys_out, pay_out);
+    rx_scatter_kernel<false><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, pay_in, n, g.rows_per_cta, p, hist, base,
+                                                           keys_out, pay_out, nullptr, 0, 0, nullptr);
     return 4;
+}
+
+int launch_radix_hist(const uint32_t *keys_in, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
+                      int sm_count, cudaStream_t s) {
+    if (n == 0) {
+        cudaMemsetAsync(totals, 0, sizeof(uint32_t) * RX_BUCKETS, s);
+        return 0;
+    }
+    const RadixGeom g = radix_geom(n, sm_count);
+    rx_hist_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+    rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
+    return 2;
+}
+
+int launch_radix_scatter_remote(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t n, RadixPass p,
+                                const uint32_t *hist, const uint32_t *base, uint32_t *const *peer_base,
+                                unsigned long long key_off, unsigned long long pay_off,
+                                const uint32_t *abort_flag, int sm_count, cudaStream_t s) {
+    if (n == 0) return 0;
+    const RadixGeom g = radix_geom(n, sm_count);
+    rx_scatter_kernel<true><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, pay_in, n, g.rows_per_cta, p, hist, base,
+                                                          nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
+    return 1;
 }
 
 // ---- generic exclusive scan: out[i] = sum(in[0..i)), *total = sum(in[0..n)) -------------------

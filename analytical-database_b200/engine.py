@@ -137,6 +137,10 @@ class Engine:
         "adb_peer_connect": (C.c_int32, [C.c_char_p]),
         "adb_agg_combine_allreduce": (C.c_int32, [C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
         "adb_peer_destroy": (C.c_int32, []),
+        "adb_peer_join_create": (C.c_int32, [C.c_int64, C.c_char_p]),
+        "adb_peer_join_connect": (C.c_int32, [C.c_char_p]),
+        "adb_peer_exchange_pairs": (C.c_int32, [C.c_int32, _I32P, _I32P, C.c_int64, _I64P,
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
         "adb_chain_select_fetch_agg_exchange": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I64P,
                                                             C.POINTER(_AggStruct), C.c_int32, C.POINTER(_AggStruct)]),
         "adb_add": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P]),
@@ -192,6 +196,21 @@ class Engine:
         dist.all_gather_into_tensor(allh, t)
         self._ck(self.lib.adb_peer_connect(bytes(allh.cpu().numpy().tobytes())))
         dist.barrier()                                   # every mailbox is mapped everywhere
+
+    def peer_join_setup(self, dist, cap_pairs: int) -> None:
+        """Reserve this rank's receive buffer for the join's pair exchange (cap_pairs pairs per
+        side) and map every peer's (adb_peer_join_create -> all-gather of the handles ->
+        adb_peer_join_connect).  Needs peer_setup first."""
+        import torch
+        world = dist.get_world_size()
+        mine = C.create_string_buffer(64)
+        self._ck(self.lib.adb_peer_join_create(int(cap_pairs), mine))
+        dev = torch.device("cuda", self.device)
+        t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(dev)
+        allh = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, t)
+        self._ck(self.lib.adb_peer_join_connect(bytes(allh.cpu().numpy().tobytes())))
+        dist.barrier()
 
     def alloc(self, nbytes: int) -> DevBuf:
         return DevBuf(self, nbytes)

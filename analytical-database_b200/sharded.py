@@ -13,9 +13,12 @@ no data-path collective.  `torch.distributed` is plumbing only:
 * position lists stay shard-resident as (shard base row, local int32 positions); an all-gather
                  of the hit counts gives every shard its offset in the concatenated list, which
                  is only materialised for print / verification;
-* hash join      both (value, position) pair lists are hash-routed by value
-                 (``adb_route_pairs``), exchanged with an all-to-all-v, and joined locally;
-                 equal keys always meet on one rank, output pairs carry global positions.
+* hash join      both (value, position) pair lists are hash-routed by value and joined
+                 locally; equal keys always meet on one rank, output pairs carry global
+                 positions.  The exchange is either the routing kernel itself writing every
+                 destination's run into that rank's receive region over NVLink peer memory
+                 (``adb_peer_exchange_pairs``, after ``connect_peers(dist, join_cap_pairs)``) or
+                 ``adb_route_pairs`` + an NCCL all-to-all-v.
 
 The local operators come from an ``ops`` object: ``EngineOps`` (below) drives the CUDA engine
 through its C-ABI on torch CUDA tensors; the CPU tests pass an oracle-backed stand-in to check
@@ -89,11 +92,38 @@ class EngineOps:
         self.eng._ck(self.lib.adb_agg_export(aggp, C.c_void_p(sc.data_ptr()), C.c_void_p(mm.data_ptr())))
         return sc, mm
 
-    def connect_peers(self, dist):
+    def connect_peers(self, dist, join_cap_pairs: int = 0):
         """Map the peers' aggregate mailboxes (Engine.peer_setup): aggregates then take the
-        one-kernel NVLink exchange instead of two NCCL all-reduces."""
+        one-kernel NVLink exchange instead of two NCCL all-reduces.  With join_cap_pairs, also
+        reserve and map the receive buffers of the join's pair exchange
+        (Engine.peer_join_setup): hash joins then push their routed pairs straight into the
+        destination ranks' memory instead of going through six NCCL all-to-alls."""
         self.eng.peer_setup(dist)
         self.peers = True
+        if join_cap_pairs:
+            self.eng.peer_join_setup(dist, join_cap_pairs)
+            self.peer_join = True
+
+    def exchange_pairs_peer(self, side: int, val, pos):
+        """adb_peer_exchange_pairs: this rank's share of the routed pairs as views of its
+        receive regions (valid until the next exchange of the same side), or None when the
+        receive buffers are not mapped."""
+        if not getattr(self, "peer_join", False):
+            return None
+        cnt = C.c_int64(0)
+        rv, rp = C.c_void_p(), C.c_void_p()
+        self.eng._ck(self.lib.adb_peer_exchange_pairs(side, self._p(val), self._p(pos), val.numel(),
+                                                      C.byref(cnt), C.byref(rv), C.byref(rp)))
+        return self._view(rv.value, cnt.value), self._view(rp.value, cnt.value)
+
+    def _view(self, ptr: int, n: int):
+        if n == 0:
+            return self.empty(0)
+
+        class _Dev:                                   # the CUDA array interface of a raw region
+            __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False),
+                                        "version": 3, "strides": None}
+        return torch.as_tensor(_Dev(), device=self.device)
 
     def aggregate_fused(self, vals):
         """Local reduction + exchange with every peer inside adb_agg_combine_allreduce; returns
@@ -257,11 +287,17 @@ class ShardedTable:
         return torch.cat([buf[r * cap:r * cap + sizes[r]] for r in range(self.world)])
 
     # ---- hash join: route -> all-to-all-v -> local build + probe ----------------------------
-    def exchange_pairs(self, val: torch.Tensor, pos: torch.Tensor):
+    def exchange_pairs(self, val: torch.Tensor, pos: torch.Tensor, side: int = 0):
         """Hash-route a (value, global position) pair list; returns this rank's share, the
-        pieces ordered by source rank and in source order inside a piece."""
+        pieces ordered by source rank and in source order inside a piece.  `side` names the
+        receive region when the exchange runs over peer memory (both inputs of a join must
+        be resident at once)."""
         if self.dist is None:
             return val, pos
+        if hasattr(self.ops, "exchange_pairs_peer"):
+            got = self.ops.exchange_pairs_peer(side, val, pos)
+            if got is not None:
+                return got
         vo, po, counts = self.ops.route_pairs(val, pos, self.world)
         send = torch.tensor(counts, dtype=torch.int64, device=self.ops.device)
         recv = torch.zeros_like(send)
@@ -277,6 +313,6 @@ class ShardedTable:
         """Equi-join of two sharded pair lists (hash_join, query.c:652-696).  Positions must be
         global and fit int32 (the reference's own limit).  Returns this rank's (pos1, pos2)
         pairs; the union over ranks is the reference's result as a set of pairs."""
-        a_v, a_p = self.exchange_pairs(v1, p1)
-        b_v, b_p = self.exchange_pairs(v2, p2)
+        a_v, a_p = self.exchange_pairs(v1, p1, 0)
+        b_v, b_p = self.exchange_pairs(v2, p2, 1)
         return self.ops.hash_join(a_v, a_p, b_v, b_p)

@@ -560,8 +560,9 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
 
 def measure_join_sharded(eng, dist, rank, world, local):
     """BASELINE config 4: hash join of two 100 M-row tables with selective prefilters, both
-    row-range sharded over the ranks, pairs hash-routed by key (adb_route_pairs), exchanged
-    with NCCL all-to-all-v, joined locally.  Returns tuples/s over all ranks (max time)."""
+    row-range sharded over the ranks, pairs hash-routed by key and pushed into the destination
+    ranks' memory over NVLink (adb_peer_exchange_pairs), joined locally; the NCCL all-to-all-v
+    exchange is timed next to it.  Returns tuples/s over all ranks (max time)."""
     import torch
     from analytical_database_b200.sharded import EngineOps, ShardedTable, shard_range
     dev = torch.device("cuda", local)
@@ -578,10 +579,10 @@ def measure_join_sharded(eng, dist, rank, world, local):
         return t
     t1 = ShardedTable(ops, {"k": col(11, 1, n), "f": col(13, 0, 1000)}, n, dist)
     t2 = ShardedTable(ops, {"k": col(12, 1, n), "f": col(14, 0, 1000)}, n, dist)
-    for s1, s2 in ((0.8, 0.15), (1.0, 1.0)):
-        p1, p2 = t1.select("f", None, int(1000 * s1)), t2.select("f", None, int(1000 * s2))
-        v1, v2 = t1.fetch("k", p1), t2.fetch("k", p2)
-        g1, g2 = p1.local + p1.base, p2.local + p2.base        # global positions (< 2^31)
+    # receive regions of the peer-memory pair exchange: 30 % head room over an even split
+    ops.connect_peers(dist, join_cap_pairs=int(1.3 * n / world) + (1 << 16))
+
+    def timed_join(v1, g1, v2, g2):
         ms = []
         for it in range(4):
             torch.cuda.synchronize()
@@ -596,11 +597,25 @@ def measure_join_sharded(eng, dist, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         m = torch.tensor([o1.numel()], dtype=torch.int64, device=dev)
         dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        return float(t.item()), int(m.item())
+
+    for s1, s2 in ((0.8, 0.15), (1.0, 1.0)):
+        p1, p2 = t1.select("f", None, int(1000 * s1)), t2.select("f", None, int(1000 * s2))
+        v1, v2 = t1.fetch("k", p1), t2.fetch("k", p2)
+        g1, g2 = p1.local + p1.base, p2.local + p2.base        # global positions (< 2^31)
         tup = p1.total + p2.total
-        out[f"prefilter_{s1}_{s2}"] = {"build": p1.total, "probe": p2.total, "matches": int(m.item()),
-                                       "ms": float(t.item()), "tuples_per_s": tup / (float(t.item()) * 1e-3),
-                                       "world": world,
-                                       "includes": "routing kernel, 2 x (count + 2 payload) all-to-all, local join"}
+        ops.peer_join = True
+        ms_peer, m_peer = timed_join(v1, g1, v2, g2)
+        ops.peer_join = False
+        ms_nccl, m_nccl = timed_join(v1, g1, v2, g2)
+        ops.peer_join = True
+        out[f"prefilter_{s1}_{s2}"] = {
+            "build": p1.total, "probe": p2.total, "matches": m_peer, "matches_equal": m_peer == m_nccl,
+            "ms": ms_peer, "tuples_per_s": tup / (ms_peer * 1e-3), "world": world,
+            "includes": "adb_peer_exchange_pairs for both sides (counts all-gather, routing scatter into the "
+                        "destination ranks' memory over NVLink, done flags) + local join",
+            "nccl_exchange": {"ms": ms_nccl, "tuples_per_s": tup / (ms_nccl * 1e-3),
+                              "includes": "adb_route_pairs, 2 x (count + 2 payload) NCCL all-to-all, local join"}}
     return out
 
 

@@ -191,6 +191,23 @@ ADB_API adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col,
                                                        int32_t *d_pos_out, int32_t *d_val_out,
                                                        int64_t *d_count, adb_agg *d_parts, int32_t k,
                                                        adb_agg *d_out);
+/* Pair exchange of the sharded hash join ("hash-partition both (key, pos)
+ * lists by key to G GPUs ... all-to-all-v") over NVLink peer memory.  After adb_peer_connect:
+ * every rank reserves a receive buffer (adb_peer_join_create: cap_pairs pairs per side), the
+ * 64-byte handles are all-gathered by the host plumbing, every rank calls
+ * adb_peer_join_connect.  adb_peer_exchange_pairs(side, ...) then routes this rank's
+ * (value, position) pairs by the routing hash of adb_route_pairs and writes every
+ * destination's run straight into that rank's receive region: the pieces land ordered by
+ * source rank and in source order inside a piece -- the layout of an all-to-all-v.  On
+ * return (*h_recv_count pairs at *d_recv_val / *d_recv_pos, valid until the next exchange
+ * of the same side) every source's pairs have landed.  side is 0 or 1, so both inputs of a
+ * join can be resident at once.  Collective; world must be a power of two.
+ * ADB_ERR_NOMEM when some rank would receive more than cap_pairs (no rank writes anything). */
+ADB_API adb_status adb_peer_join_create(int64_t cap_pairs, unsigned char *handle_out);
+ADB_API adb_status adb_peer_join_connect(const unsigned char *handles);
+ADB_API adb_status adb_peer_exchange_pairs(int32_t side, const int32_t *d_val, const int32_t *d_pos, int64_t n,
+                                           int64_t *h_recv_count, const int32_t **d_recv_val,
+                                           const int32_t **d_recv_pos);
 ADB_API adb_status adb_peer_destroy(void);
 
 /* ---- element-wise add / sub -- replace add / sub, src/query.c:356-390 (int32, wraps) */

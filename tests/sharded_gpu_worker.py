@@ -78,6 +78,29 @@ def main():
     o1, o2 = t.hash_join(v1, p1, v2, p2)
     res["join"] = np.stack([t.gather_global(o1).cpu().numpy(), t.gather_global(o2).cpu().numpy()], 1)
     res["join_local"] = o1.numel()
+    # the same join with the pair exchange over peer memory (three times: banks, buffer reuse)
+    ops.connect_peers(dist, join_cap_pairs=n)
+    res["join_peer"] = []
+    for _ in range(3):
+        q1, q2 = t.hash_join(v1, p1, v2, p2)
+        res["join_peer"].append(np.stack([t.gather_global(q1).cpu().numpy(), t.gather_global(q2).cpu().numpy()], 1))
+    # and the exchange alone against the NCCL all-to-all-v: identical pieces in identical order
+    ops.peer_join = False
+    nv, npos = t.exchange_pairs(v2, p2)
+    ops.peer_join = True
+    pv, ppos = t.exchange_pairs(v2, p2, 1)
+    ok = torch.tensor([int(torch.equal(nv, pv) and torch.equal(npos, ppos))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)                 # on every rank
+    res["xchg_equal"] = bool(ok.item())
+    # a receive region that is too small fails on every rank alike, and the next exchange works
+    ops.connect_peers(dist, join_cap_pairs=64)
+    try:
+        t.exchange_pairs(v1, p1, 0)
+        res["overflow"] = "no error"
+    except Exception as ex:                                   # EngineError: ADB_ERR_NOMEM
+        res["overflow"] = str(ex)
+    small = t.exchange_pairs(v1[:8], p1[:8], 0)
+    res["after_overflow"] = int(t.gather_global(small[0]).numel())
     res["launches"] = eng.launch_count()
     if rank == 0:
         torch.save(res, out)

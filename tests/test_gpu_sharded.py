@@ -98,3 +98,7 @@ def test_nccl_shards_equal_one_shard(port, tmp_path):
         return x[np.lexsort((x[:, 0], x[:, 1]))]
     assert res["join"].shape == expj.shape and np.array_equal(canon(res["join"]), canon(expj))
     assert 0 < res["join_local"] < expj.shape[0] and res["launches"] > 20
+    for got in res["join_peer"]:                           # pair exchange over NVLink peer memory
+        assert got.shape == expj.shape and np.array_equal(canon(got), canon(expj))
+    assert res["xchg_equal"]                               # same pieces, same order as the all-to-all-v
+    assert "reserve more" in res["overflow"] and res["after_overflow"] == 8 * world
