@@ -39,6 +39,7 @@ struct Engine {
     int64_t idx_pending_n = -1;         // >= 0 between adb_select_index_count and _emit
     adb::SelectArgs sel_pending{};      // valid between adb_select_*_count and adb_select_emit
     bool sel_ready = false;
+    uint64_t sel_generation = 0;        // bumped by every select_prepare (adb_select_generation)
     int64_t *scratch_count = nullptr;   // device int64 for callers that pass no d_count
     // batched shared scan state (count phase -> emit phase)
     unsigned char *ss_plan_mem = nullptr;   // bounds | cov_off | cov_q
@@ -535,6 +536,7 @@ static adb_status select_prepare(const char *what, const int32_t *d_val, const i
                                  const int32_t *hi, int64_t *d_count, adb::SelectArgs *a) {
     NEED_UP();
     g.sel_ready = false;
+    ++g.sel_generation;
     if (adb_status s = check_len(n_max, what)) return s;
     if (n_max > 0 && !d_val) return fail(ADB_ERR_INVALID, "%s: NULL device pointer", what);
     *a = adb::SelectArgs{};
@@ -598,6 +600,41 @@ adb_status adb_select_emit(const int32_t *d_pos_in, int32_t base_pos, int32_t *d
     a.pos_in = d_pos_in; a.base_pos = base_pos; a.out = d_pos_out;
     a.d_count = g.scratch_count;                    // expand rewrites the same total
     return after_launch("select_emit", adb::launch_select_expand(a, g.stream));
+}
+
+uint64_t adb_select_generation(void) { return g.sel_generation; }
+
+// Deferred emit of a select whose consumers turned out to be fetch + aggregate: the fused
+// second kernel of the chain, after the host has read the count.
+adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_out, int32_t *d_val_out,
+                                     adb_agg *d_agg, adb_agg *h_agg) {
+    NEED_UP();
+    if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: no pending adb_select_count");
+    if (g.sel_pending.pos_in || g.sel_pending.d_n)
+        return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: the pending select is not over a base column");
+    if (!d_agg || (g.sel_pending.n > 0 && (!d_fetch_col || !d_pos_out || !d_val_out)))
+        return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: NULL device pointer");
+    g.sel_ready = false;
+    adb::SelectArgs a = g.sel_pending;
+    int64_t *d_count = a.d_count;                   // written by the count phase
+    a.base_pos = 0; a.out = d_pos_out;
+    a.d_count = g.scratch_count;                    // the expansion rewrites the same total
+    a.fetch_col = d_fetch_col; a.val_out = d_val_out;
+    a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
+    const int f_ = adb::launch_select_expand_fetch_agg(a, g.stream);
+    if (f_ > 0) {
+        if (adb_status s = after_launch("select_emit_fetch_agg", f_)) return s;
+    } else {
+        // empty column (or a grid larger than the fold scratch): the three-operator form
+        if (adb_status s = after_launch("select_emit_fetch_agg", adb::launch_select_expand(a, g.stream))) return s;
+        if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, a.n, d_count, 0, d_val_out)) return s;
+        if (adb_status s = adb_aggregate(d_val_out, a.n, d_count, d_agg, nullptr)) return s;
+    }
+    if (h_agg) {
+        CU(cudaMemcpyAsync(h_agg, d_agg, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+    }
+    return ADB_OK;
 }
 
 adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,

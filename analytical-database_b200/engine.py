@@ -122,6 +122,8 @@ class Engine:
         "adb_select_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, _I32P, _I32P, _I32P, _I64P, _I64P]),
         "adb_select_count": (C.c_int32, [_I32P, C.c_int64, _I64P, _I32P, _I32P, _I64P, _I64P]),
         "adb_select_emit": (C.c_int32, [_I32P, C.c_int32, _I32P]),
+        "adb_select_emit_fetch_agg": (C.c_int32, [_I32P, _I32P, _I32P, C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
+        "adb_select_generation": (C.c_uint64, []),
         "adb_select_index_count": (C.c_int32, [C.c_void_p, C.c_int32, _I32P, _I32P, _I64P, _I64P]),
         "adb_select_index_emit": (C.c_int32, [C.c_void_p, _I32P]),
         "adb_fetch": (C.c_int32, [_I32P, _I32P, C.c_int64, _I64P, C.c_int32, _I32P]),
@@ -327,6 +329,22 @@ class Engine:
         out = self.alloc_i32(h.value)
         self._ck(self.lib.adb_select_emit(pos_in.i32() if pos_in else None, base, out.i32()))
         return out, int(h.value)
+
+    def select_fetch_agg_deferred(self, sel_col: DevBuf, fetch_col: DevBuf, n: int, lo=None, hi=None):
+        """adb_select_count, host reads the count, then positions + gather + aggregates in one
+        kernel (adb_select_emit_fetch_agg): (pos DevBuf, val DevBuf, count, Agg)."""
+        (plo, _a), (phi, _b) = _bound(lo), _bound(hi)
+        h = C.c_int64(-1)
+        self._ck(self.lib.adb_select_count(sel_col.i32(), n, None, plo, phi, None, C.byref(h)))
+        gen = int(self.lib.adb_select_generation())
+        pos, val = self.alloc_i32(h.value), self.alloc_i32(h.value)
+        d_out = self.alloc(C.sizeof(_AggStruct))
+        a = _AggStruct()
+        assert int(self.lib.adb_select_generation()) == gen
+        self._ck(self.lib.adb_select_emit_fetch_agg(fetch_col.i32(), pos.i32(), val.i32(),
+                                                    C.cast(d_out.void(), C.POINTER(_AggStruct)), C.byref(a)))
+        d_out.free()
+        return pos, val, int(h.value), Agg(a.sum, a.count, a.min, a.max)
 
     def fetch(self, col: DevBuf, pos: DevBuf, n_max: int, d_n: DevBuf | None = None, base: int = 0,
               out: DevBuf | None = None) -> DevBuf:

@@ -70,7 +70,7 @@ typedef struct DevResult {
 #define SLOT_TOMB ((void *)1)
 
 static struct {
-    int up, failed, mirror;
+    int up, failed, mirror, lazy;
     DevColumn *cols;
     int ncols, capcols;
     DevResult *slots;           /* open addressing on payload address */
@@ -130,6 +130,74 @@ static void op_ok(Status *st) {
         }                                                         \
     } while (0)
 
+/* ---- deferred select -------------------------------------------------
+ * select_column over an un-indexed column returns as soon as the hit count is known: the
+ * predicate pass has left its bitmap in the engine's scratch, the position buffer is
+ * allocated, its contents are not written yet.  If the next thing that happens to the handle
+ * is fetch_column and then an aggregate of that fetch -- the s=select / f=fetch / a=sum(f)
+ * pattern of src/server.c:137-290 -- the aggregate call resolves all three with the chain's
+ * fused second kernel (positions + gather + sum/min/max in one pass over the bitmap).  Any
+ * other use of either handle, any other select, a column invalidation or a release first
+ * writes what is pending (flush_pending), so the handles are indistinguishable from eager
+ * ones to the unchanged plumbing.  At most one select is pending at a time.
+ * ADB_SHIM_EAGER=1 (or the mirror mode) turns the deferral off. */
+static struct {
+    int active;
+    const void *sel_payload;        /* registry key of the select handle */
+    int32_t *sel_d;                 /* its position buffer, h entries */
+    size_t h;
+    const int32_t *d_col;           /* what was scanned, to redo the count if another user of */
+    size_t rows;                    /* the engine overwrote the bitmap in the meantime        */
+    int has_lo, has_hi, lo, hi;
+    uint64_t generation;            /* adb_select_generation() right after the count */
+    const void *fetch_payload;      /* fetch_column of that select, values not written yet */
+    int32_t *fetch_d;
+    const int32_t *d_fetch_col;
+} P;
+
+static int pending_recount(void) {
+    if (adb_select_generation() == P.generation) return 0;
+    int64_t h = -1;
+    if (adb_select_count(P.d_col, (int64_t)P.rows, NULL, P.has_lo ? &P.lo : NULL,
+                         P.has_hi ? &P.hi : NULL, NULL, &h) != ADB_OK) {
+        set_err("deferred select: %s", adb_last_error());
+        return -1;
+    }
+    if ((size_t)h != P.h) {
+        set_err("deferred select: the column changed under a pending select (%zu hits, now %lld)",
+                P.h, (long long)h);
+        return -1;
+    }
+    return 0;
+}
+
+/* Write whatever is pending; afterwards every handle is an ordinary device result. */
+static int flush_pending(void) {
+    if (!P.active) return 0;
+    P.active = 0;
+    if (pending_recount()) return -1;
+    adb_status s = P.fetch_payload
+        ? adb_select_emit_fetch_agg(P.d_fetch_col, P.sel_d, P.fetch_d, S.d_agg, NULL)
+        : adb_select_emit(NULL, 0, P.sel_d);
+    if (s != ADB_OK) {
+        set_err("deferred select: %s", adb_last_error());
+        return -1;
+    }
+    return 0;
+}
+
+/* The plumbing is about to free (or has freed) this payload. */
+static void pending_payload_gone(const void *payload) {
+    if (!P.active) return;
+    if (payload == P.fetch_payload) {           /* nobody can read those values any more */
+        P.fetch_payload = NULL;
+        P.fetch_d = NULL;
+    } else if (payload == P.sel_payload) {
+        if (P.fetch_payload) flush_pending();   /* the fetch still needs the selected rows */
+        else P.active = 0;
+    }
+}
+
 /* ---- engine lifecycle ------------------------------------------------------------------ */
 int adb_host_init(int device) {
     if (S.up) return 0;
@@ -146,6 +214,8 @@ int adb_host_init(int device) {
     S.d_agg = (adb_agg *)p;
     const char *m = getenv("ADB_SHIM_MIRROR");
     S.mirror = m && m[0] && m[0] != '0';
+    const char *eager = getenv("ADB_SHIM_EAGER");
+    S.lazy = !S.mirror && !(eager && eager[0] && eager[0] != '0');
     S.up = 1;
     S.failed = 0;
     return 0;
@@ -158,6 +228,7 @@ static int ensure_up(void) {
 }
 
 static void dev_column_drop(DevColumn *c) {
+    if (P.active && c->d_data && (c->d_data == P.d_col || c->d_data == P.d_fetch_col)) flush_pending();
     if (c->ix) adb_index_destroy(c->ix);
     if (c->d_ix_values) adb_free(c->d_ix_values);
     if (c->d_ix_positions) adb_free(c->d_ix_positions);
@@ -170,6 +241,7 @@ static void dev_column_drop(DevColumn *c) {
 void adb_host_shutdown(void) {
     if (!S.up) return;
     lock();
+    P.active = 0;
     for (size_t i = 0; i < S.nslots; ++i)
         if (S.slots[i].payload != SLOT_EMPTY && S.slots[i].payload != SLOT_TOMB)
             adb_free(S.slots[i].d_ptr);
@@ -360,6 +432,7 @@ static int32_t *registry_take(const void *payload) {
 
 void adb_host_payload_freed(void *payload) {
     if (S.nlive <= 0 || !payload) return;
+    pending_payload_gone(payload);
     int32_t *d = registry_take(payload);
     if (d) adb_free(d);
 }
@@ -394,6 +467,7 @@ static Result *new_dev_result(int32_t *d_ptr, size_t tuples) {
      * plumbing without telling us -- reclaim its HBM now. */
     DevResult *stale = registry_find(payload);
     if (stale) {
+        pending_payload_gone(payload);
         adb_free(stale->d_ptr);
         stale->d_ptr = d_ptr;
         stale->tuples = tuples;
@@ -450,6 +524,7 @@ static int stage(const Result *r, Staged *out) {
         set_err("result of %zu tuples exceeds the int position domain (src/query.c:40-43)", r->num_tuples);
         return -1;
     }
+    if (flush_pending()) return -1;             /* an operand is about to be read */
     lock();
     DevResult *e = registry_find(r->payload);
     int32_t *d = e ? e->d_ptr : NULL;
@@ -486,6 +561,7 @@ static void unstage(Staged *s) {
 int adb_host_result_to_host(const Result *result, void *dst) {
     if (!result) return -1;
     if (result->num_tuples == 0) return 0;
+    if (flush_pending()) return -1;
     lock();
     DevResult *e = registry_find(result->payload);
     int32_t *d = e ? e->d_ptr : NULL;
@@ -545,13 +621,29 @@ Result *select_column(Column *column, int *low, int *high, Status *ret_status) {
         return select_index_path(column, c, low, high, ret_status);
     int64_t h = 0;
     int32_t *out = NULL;
+    if (flush_pending()) goto fail;                 /* this select takes over the bitmap */
     CK(adb_select_count(c->d_data, (int64_t)c->rows, NULL, low, high, NULL, &h));
     out = alloc_i32((size_t)h);
     if (!out) goto fail;
-    CK(adb_select_emit(NULL, 0, out));
+    const int defer = S.lazy && h > 0;
+    if (!defer) CK(adb_select_emit(NULL, 0, out));
     {
         Result *r = new_dev_result(out, (size_t)h);
         if (!r) return op_fail(ret_status, "select_column");
+        if (defer) {                                /* positions are written by whoever needs them first */
+            memset(&P, 0, sizeof P);
+            P.sel_payload = r->payload;
+            P.sel_d = out;
+            P.h = (size_t)h;
+            P.d_col = c->d_data;
+            P.rows = c->rows;
+            P.has_lo = low != NULL;
+            P.has_hi = high != NULL;
+            P.lo = low ? *low : 0;
+            P.hi = high ? *high : 0;
+            P.generation = adb_select_generation();
+            P.active = 1;
+        }
         op_ok(ret_status);
         return r;
     }
@@ -608,7 +700,7 @@ Result **shared_select(SelectOperator *operators, int query_count, Column *colum
         goto fail;
     }
     DevColumn *c = dev_column(column);
-    if (!c) goto fail;
+    if (!c || flush_pending()) goto fail;
     results = calloc((size_t)query_count, sizeof *results);
     outs = calloc((size_t)query_count, sizeof *outs);
     lows = malloc(sizeof *lows * (size_t)query_count);
@@ -661,7 +753,30 @@ Result *fetch_column(Column *column, Result *position_result, Status *ret_status
     int32_t *out = NULL;
     if (ensure_up()) goto fail;
     DevColumn *c = dev_column(column);
-    if (!c || stage(position_result, &p)) goto fail;
+    if (!c) goto fail;
+    /* fetch of the pending select: nothing is launched yet -- the values are written together
+     * with the positions, by the aggregate that usually follows or by the first other reader */
+    if (P.active && position_result && position_result->payload == P.sel_payload && !P.fetch_payload &&
+        position_result->num_tuples == P.h && c->rows >= P.rows) {
+        out = alloc_i32(P.h);
+        if (!out) goto fail;
+        Result *r = new_dev_result(out, P.h);
+        if (!r) return op_fail(ret_status, "fetch_column");
+        if (P.active) {                             /* (new_dev_result may have flushed) */
+            P.fetch_payload = r->payload;
+            P.fetch_d = out;
+            P.d_fetch_col = c->d_data;
+        } else if (adb_fetch(c->d_data, P.sel_d, (int64_t)P.h, NULL, 0, out) != ADB_OK) {
+            set_err("adb_fetch: %s", adb_last_error());
+            adb_host_result_release(r);
+            free(r->payload);
+            free(r);
+            return op_fail(ret_status, "fetch_column");
+        }
+        op_ok(ret_status);
+        return r;
+    }
+    if (stage(position_result, &p)) goto fail;
     const size_t n = position_result->num_tuples;
     out = alloc_i32(n);
     if (!out) goto fail;
@@ -682,7 +797,19 @@ fail:
 /* ---- aggregates ------------------------------------------------------------------------------ */
 static int aggregate_result(const Result *r, adb_agg *h) {
     Staged v = {0};
-    if (ensure_up() || stage(r, &v)) return -1;
+    if (ensure_up()) return -1;
+    /* aggregate of the pending fetch of the pending select: the chain's fused second kernel
+     * writes both handles and the aggregate in one pass */
+    if (P.active && r && P.fetch_payload && r->payload == P.fetch_payload && r->num_tuples == P.h &&
+        adb_select_generation() == P.generation) {
+        P.active = 0;
+        if (adb_select_emit_fetch_agg(P.d_fetch_col, P.sel_d, P.fetch_d, S.d_agg, h) != ADB_OK) {
+            set_err("adb_select_emit_fetch_agg: %s", adb_last_error());
+            return -1;
+        }
+        return 0;
+    }
+    if (stage(r, &v)) return -1;
     adb_status s = adb_aggregate(v.d, (int64_t)r->num_tuples, NULL, S.d_agg, h);
     if (s != ADB_OK) set_err("adb_aggregate: %s", adb_last_error());
     unstage(&v);
@@ -891,6 +1018,7 @@ char *print(Result **results, int result_num, Status *ret_status) {
     t_err[0] = '\0';
     Text t = {0};
     void *host = NULL;
+    if (flush_pending()) return op_fail(ret_status, "print");
     if (text_room(&t, 16)) goto oom;
     t.s[0] = '\0';
     for (int i = 0; i < result_num; ++i) {

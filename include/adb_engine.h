@@ -129,6 +129,21 @@ typedef struct adb_agg {
 } adb_agg;
 ADB_API adb_status adb_aggregate(const int32_t *d_val, int64_t n_max, const int64_t *d_n,
                          adb_agg *d_out, adb_agg *h_out);
+/* Emit phase of a pending adb_select_count over a base column with fetch_column and the
+ * aggregates fused in (a select whose only consumers so far are a fetch
+ * and an aggregate is resolved when the aggregate is asked for): one kernel writes the
+ * positions, d_val_out[i] = d_fetch_col[d_pos_out[i]] and the {sum, count, min, max} of those
+ * values -- the second kernel of adb_chain_select_fetch_agg, with the host having read the hit
+ * count in between to size both lists.  d_agg is a device adb_agg; h_agg optional
+ * (synchronises). */
+ADB_API adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_out,
+                                             int32_t *d_val_out, adb_agg *d_agg,
+                                             adb_agg *h_agg);
+/* Serial number of the select whose bitmap sits in the engine's scratch: it changes whenever
+ * any select (of any form) starts.  A caller that defers adb_select_emit compares it with
+ * the value it read right after its adb_select_count to learn whether the count is still
+ * pending. */
+ADB_API uint64_t adb_select_generation(void);
 /* Combine `k` device partials (one per shard) into d_out[0] on the device. */
 ADB_API adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, adb_agg *h_out);
 

@@ -229,3 +229,149 @@ def test_payload_registry_reclaims_on_address_reuse(api):
         query_api._libc.free(s.contents.payload)                       # plumbing-style free, no hook
         query_api._libc.free(C.cast(s, C.c_void_p))
     assert api.lib.adb_host_live_device_results() <= base + 3
+
+
+# ---- deferred select: every order in which the plumbing can touch the
+# handles of s=select / f=fetch / a=agg(f) gives the eager answer ---------------------------
+def _chain_inputs(rng, n):
+    c1, _c2, _c3, c4 = table(rng, n)
+    return c1, c4, -n // 6, n // 5
+
+
+@pytest.mark.parametrize("n", [33, 4097, 300_001])
+@pytest.mark.parametrize("agg", ["sum", "average", "min", "max"])
+def test_deferred_chain_resolves_in_the_aggregate(api, cpu, rng, n, agg):
+    c1, c4, lo, hi = _chain_inputs(rng, n)
+    col1, col4 = api.column(c1), api.column(c4)
+    epos = cpu.select_scan(c1, lo, hi)
+    evals = cpu.fetch(c4, epos)
+    s = api.select_column(col1, lo, hi)
+    assert s.contents.num_tuples == epos.size            # known before anything is written
+    f = api.fetch_column(col4, s)
+    assert f.contents.num_tuples == epos.size
+    a = api.sum_result(f) if agg == "sum" else api.unary(agg, f)
+    got = api.tuples(a)[0]
+    if agg == "sum":
+        assert int(got) == cpu.sum(evals)
+    elif agg == "average":
+        assert got.tobytes() == np.float64(cpu.avg(evals)).tobytes()
+    else:
+        assert int(got) == getattr(cpu, agg)(evals)
+    # the handles the aggregate resolved on the way are the eager ones
+    assert np.array_equal(api.tuples(s), epos)
+    assert np.array_equal(api.tuples(f), evals)
+    # and stay usable: a second aggregate, a second fetch, a select over the pair
+    assert int(api.tuples(api.unary("max", f))[0]) == cpu.max(evals)
+    f2 = api.fetch_column(col1, s)
+    assert np.array_equal(api.tuples(f2), cpu.fetch(c1, epos))
+    s2 = api.select_result(f2, s, 0, None)
+    assert np.array_equal(api.tuples(s2), cpu.select_result(cpu.fetch(c1, epos), epos, 0, None))
+    for r in (s, f, a, f2, s2):
+        api.drop(r)
+
+
+def test_deferred_handles_under_every_other_first_use(api, cpu, rng):
+    n = 70_001
+    c1, c4, lo, hi = _chain_inputs(rng, n)
+    col1, col4 = api.column(c1), api.column(c4)
+    epos = cpu.select_scan(c1, lo, hi)
+    evals = cpu.fetch(c4, epos)
+    live0 = api.lib.adb_host_live_device_results()
+
+    # the select is read first
+    s = api.select_column(col1, lo, hi)
+    assert np.array_equal(api.tuples(s), epos)
+    api.drop(s)
+    # the fetch is read first
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    assert np.array_equal(api.tuples(f), evals)
+    assert np.array_equal(api.tuples(s), epos)
+    api.drop(s), api.drop(f)
+    # the select is released while the fetch is pending (s is re-bound, client_context.c:31-45)
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    api.drop(s)
+    a = api.sum_result(f)
+    assert int(api.tuples(a)[0]) == cpu.sum(evals)
+    assert np.array_equal(api.tuples(f), evals)
+    api.drop(f), api.drop(a)
+    # the fetch is released while pending, the select lives on
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    api.drop(f)
+    assert np.array_equal(api.tuples(s), epos)
+    api.drop(s)
+    # both released untouched
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    api.drop(f), api.drop(s)
+    # another select takes the bitmap over
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    t = api.select_column(col4, None, I32MAX - 5000)
+    a = api.unary("min", f)
+    assert int(api.tuples(a)[0]) == cpu.min(evals)
+    assert np.array_equal(api.tuples(t), cpu.select_scan(c4, None, I32MAX - 5000))
+    assert np.array_equal(api.tuples(s), epos)
+    for r in (s, f, t, a):
+        api.drop(r)
+    # two fetches of one pending select, print, add, a batch and a join in between
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    g = api.fetch_column(col1, s)
+    d = api.binary("sub", f, g)
+    assert np.array_equal(api.tuples(d), (evals.astype(np.int64) - cpu.fetch(c1, epos)).astype(np.int32))
+    for r in (s, f, g, d):
+        api.drop(r)
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    assert api.print(f) == "\n".join(str(int(v)) for v in evals)
+    api.drop(s), api.drop(f)
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    batch = api.shared_select(col1, [lo, 0], [hi, 10])
+    assert np.array_equal(api.tuples(batch[0]), epos)
+    a = api.sum_result(f)
+    assert int(api.tuples(a)[0]) == cpu.sum(evals)
+    for r in (s, f, a, *batch):
+        api.drop(r)
+    # the column is invalidated (insert_row re-mmaps it, db_manager.c:178-186) while pending
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    api.lib.adb_host_column_invalidate(C.byref(col4))
+    api.lib.adb_host_column_invalidate(C.byref(col1))
+    a = api.sum_result(f)
+    assert int(api.tuples(a)[0]) == cpu.sum(evals)
+    assert np.array_equal(api.tuples(s), epos)
+    for r in (s, f, a):
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == live0
+
+
+def test_deferred_select_survives_a_foreign_engine_select(api, cpu, rng):
+    """Another user of the engine in the same process overwrites the pending bitmap: the
+    shim notices (adb_select_generation) and re-runs the predicate pass."""
+    import analytical_database_b200 as adb
+    n = 50_021
+    c1, c4, lo, hi = _chain_inputs(rng, n)
+    col1, col4 = api.column(c1), api.column(c4)
+    epos = cpu.select_scan(c1, lo, hi)
+    evals = cpu.fetch(c4, epos)
+    eng = adb.Engine(0)
+    other = eng.upload(np.arange(1000, dtype=np.int32))
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    pos, cnt = eng.select_exact(other, 1000, 10, 20)
+    assert cnt == 10
+    a = api.sum_result(f)
+    assert int(api.tuples(a)[0]) == cpu.sum(evals)
+    assert np.array_equal(api.tuples(s), epos) and np.array_equal(api.tuples(f), evals)
+    for r in (s, f, a):
+        api.drop(r)
+    # the engine-level deferred form agrees with the fused chain
+    d1, d4 = eng.upload(c1), eng.upload(c4)
+    p_, v_, h_, agg = eng.select_fetch_agg_deferred(d1, d4, n, lo, hi)
+    assert h_ == epos.size and agg.sum == cpu.sum(evals) and agg.count == epos.size
+    assert agg.min == cpu.min(evals) and agg.max == cpu.max(evals)
+    assert np.array_equal(p_.to_host(h_), epos) and np.array_equal(v_.to_host(h_), evals)
