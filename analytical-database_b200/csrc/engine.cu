@@ -39,7 +39,11 @@ struct Engine {
     int64_t idx_pending_n = -1;         // >= 0 between adb_select_index_count and _emit
     adb::SelectArgs sel_pending{};      // valid between adb_select_*_count and adb_select_emit
     bool sel_ready = false;
-    uint64_t sel_generation = 0;        // bumped by every select_prepare (adb_select_generation)
+    uint64_t sel_generation = 0;
+    // small results travel to the host through a mapped pinned mailbox (read_back)
+    unsigned long long *mbox = nullptr;  // kMboxWords payload words, then the flag word
+    unsigned long long *mbox_dev = nullptr;
+    unsigned long long mbox_seq = 0;        // bumped by every select_prepare (adb_select_generation)
     int64_t *scratch_count = nullptr;   // device int64 for callers that pass no d_count
     // batched shared scan state (count phase -> emit phase)
     unsigned char *ss_plan_mem = nullptr;   // bounds | cov_off | cov_q
@@ -153,6 +157,52 @@ adb_status after_launch(const char *what, int launches) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ADB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
     g.launches += launches;
+    return ADB_OK;
+}
+
+// ---- small device -> host results -----------------------------------------------------------
+// Every operator of the drop-in API ends by handing a count or an aggregate to the host
+// (Result.num_tuples is a plain struct field, src/include/cs165_api.h:179-183).
+// cudaMemcpyAsync into pageable memory + cudaStreamSynchronize costs ~20 us of host latency per
+// call; here a one-warp kernel at the end of the stream stores the words into mapped pinned
+// host memory, then a sequence number, and the host spins on that word.  The stream is polled
+// now and then so that a faulted kernel surfaces as an error instead of a hang.
+constexpr uint32_t kMboxWords = 256;                  // 2 KB: 150 batch counts fit
+__global__ void publish_kernel(const unsigned long long *__restrict__ src, uint32_t words,
+                               volatile unsigned long long *dst, unsigned long long seq) {
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) dst[kMboxWords] = seq;
+}
+
+static adb_status read_back(void *h_dst, const void *d_src, size_t bytes) {
+    if (bytes == 0) return ADB_OK;
+    if (!g.mbox || bytes > kMboxWords * 8 || (bytes & 7u) || (reinterpret_cast<uintptr_t>(d_src) & 7u)) {
+        CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+        return ADB_OK;
+    }
+    const unsigned long long seq = ++g.mbox_seq;
+    publish_kernel<<<1, 64, 0, g.stream>>>(static_cast<const unsigned long long *>(d_src), (uint32_t)(bytes / 8),
+                                           g.mbox_dev, seq);
+    if (adb_status s = after_launch("publish", 1)) return s;
+    const volatile unsigned long long *flag = g.mbox + kMboxWords;
+    for (uint32_t spins = 1;; ++spins) {
+        if (__atomic_load_n(const_cast<const unsigned long long *>(flag), __ATOMIC_ACQUIRE) == seq) break;
+        if ((spins & 0xFFFu) == 0) {
+            const cudaError_t e = cudaStreamQuery(g.stream);
+            if (e == cudaSuccess) {
+                if (__atomic_load_n(const_cast<const unsigned long long *>(flag), __ATOMIC_ACQUIRE) == seq) break;
+                return fail(ADB_ERR_CUDA, "result mailbox: the stream drained without publishing");
+            }
+            if (e != cudaErrorNotReady) return fail(ADB_ERR_CUDA, "result mailbox: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    memcpy(h_dst, g.mbox, bytes);
     return ADB_OK;
 }
 
@@ -361,6 +411,22 @@ adb_status adb_init(int device_ordinal) {
         if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
         cudaGetLastError();
     }
+    if (!getenv("ADB_NO_MAILBOX")) {
+        void *mb = nullptr;
+        if (cudaHostAlloc(&mb, (kMboxWords + 8) * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+            memset(mb, 0, (kMboxWords + 8) * sizeof(unsigned long long));
+            void *dv = nullptr;
+            if (cudaHostGetDevicePointer(&dv, mb, 0) == cudaSuccess) {
+                g.mbox = static_cast<unsigned long long *>(mb);
+                g.mbox_dev = static_cast<unsigned long long *>(dv);
+            } else {
+                cudaGetLastError();
+                cudaFreeHost(mb);
+            }
+        } else {
+            cudaGetLastError();                 // readbacks fall back to cudaMemcpyAsync
+        }
+    }
     CU(cudaMalloc(&g.agg_scratch, sizeof(adb_agg) * adb::kAggMaxBlocks));
     CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int)));
     CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int)));
@@ -401,6 +467,7 @@ adb_status adb_shutdown(void) {
     cudaFree(g.csv.total);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
+    if (g.mbox) cudaFreeHost(g.mbox);
     peer_close();
     for (int l = 0; l < g.stage_lanes; ++l) {
         for (int b = 0; b < 2; ++b) { cudaFreeHost(g.stage[l].buf[b]); cudaEventDestroy(g.stage[l].ev[b]); }
@@ -526,9 +593,7 @@ adb_status adb_chain_marks(int32_t base_slot) {
 // ---- operators ---------------------------------------------------------------------------
 static adb_status finish_count(int64_t *d_count, int64_t *h_count) {
     if (!h_count) return ADB_OK;
-    CU(cudaMemcpyAsync(h_count, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    return ADB_OK;
+    return read_back(h_count, d_count, sizeof(int64_t));
 }
 
 static adb_status select_prepare(const char *what, const int32_t *d_val, const int32_t *d_pos,
@@ -631,8 +696,7 @@ adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_
         if (adb_status s = adb_aggregate(d_val_out, a.n, d_count, d_agg, nullptr)) return s;
     }
     if (h_agg) {
-        CU(cudaMemcpyAsync(h_agg, d_agg, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
-        CU(cudaStreamSynchronize(g.stream));
+        if (adb_status s = read_back(h_agg, d_agg, sizeof(adb_agg))) return s;
     }
     return ADB_OK;
 }
@@ -655,8 +719,7 @@ adb_status adb_aggregate(const int32_t *d_val, int64_t n_max, const int64_t *d_n
     const int k_ = adb::launch_aggregate(d_val, n_max, d_n, d_out, g.agg_scratch, g.agg_ticket, g.sm_count, g.stream);
     if (adb_status s = after_launch("aggregate", k_)) return s;
     if (h_out) {
-        CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
-        CU(cudaStreamSynchronize(g.stream));
+        if (adb_status s = read_back(h_out, d_out, sizeof(adb_agg))) return s;
     }
     return ADB_OK;
 }
@@ -667,8 +730,7 @@ adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, ad
     const int k_ = adb::launch_agg_combine(d_parts, k, d_out, g.stream);
     if (adb_status s = after_launch("agg_combine", k_)) return s;
     if (h_out) {
-        CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
-        CU(cudaStreamSynchronize(g.stream));
+        if (adb_status s = read_back(h_out, d_out, sizeof(adb_agg))) return s;
     }
     return ADB_OK;
 }
@@ -726,8 +788,7 @@ adb_status adb_agg_combine_allreduce(const adb_agg *d_parts, int32_t k, adb_agg 
         adb::PeerExchange{g.peer_boxes_dev, g.peer_rank, g.peer_world, epoch, d_parts, k, d_out}, g.stream);
     if (adb_status s = after_launch("agg_combine_allreduce", k_)) return s;
     if (h_out) {
-        CU(cudaMemcpyAsync(h_out, d_out, sizeof(adb_agg), cudaMemcpyDeviceToHost, g.stream));
-        CU(cudaStreamSynchronize(g.stream));
+        if (adb_status s = read_back(h_out, d_out, sizeof(adb_agg))) return s;
         if (h_out->count < 0)
             return fail(ADB_ERR_CUDA, "adb_agg_combine_allreduce: a peer did not arrive within 2 s (epoch %u)", epoch);
     }
@@ -1046,8 +1107,7 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
                                                g.ss_chunk_hits, g.ss_counts, g.ss_totals, g.stream);
     if (adb_status s = after_launch("shared_classify", k_)) return s;
     if (h_counts) {
-        CU(cudaMemcpyAsync(h_counts, g.ss_totals, sizeof(int64_t) * q_count, cudaMemcpyDeviceToHost, g.stream));
-        CU(cudaStreamSynchronize(g.stream));
+        if (adb_status s = read_back(h_counts, g.ss_totals, sizeof(int64_t) * q_count)) return s;
     }
     g.ss_ready = true;
     return ADB_OK;
@@ -1412,8 +1472,7 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     launches += adb::launch_hj_bounds(bk, nb, part_bits, num_parts, off1, g.stream);
     launches += adb::launch_hj_geometry(off1, num_parts, toff, g.stream);
     unsigned long long slots = 0;
-    CU(cudaMemcpyAsync(&slots, toff + num_parts, sizeof slots, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+    if (adb_status s = read_back(&slots, toff + num_parts, sizeof slots)) return s;
     if (slots > g.hj_table_slots) {
         if (g.hj_table) CU(cudaFree(g.hj_table));
         g.hj_table = nullptr;
@@ -1436,8 +1495,7 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     tr.lap("probe");
     // 5. output offsets in probe-row order
     launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
-    CU(cudaMemcpyAsync(&j.matches, tot, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+    if (adb_status s = read_back(&j.matches, tot, sizeof(int64_t))) return s;
     tr.lap("output offsets");
     if (adb_status s = after_launch("join_count", launches)) return s;
     if (j.matches >= (int64_t)1 << 31) {

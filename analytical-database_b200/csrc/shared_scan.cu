@@ -167,35 +167,46 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
                     v[4 * j + k] = ok ? ld_stream(val + r) : 0;
                 }
         }
+        // survivors of the whole tile are ranked with ONE warp scan: the four 128-row groups'
+        // counts (<= 128 each) ride in the four bytes of one word
+        uint32_t need[4], packed = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint32_t need = 0;
+            uint32_t nd = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 // bucket of d = v - lo, saturated at kSsBits: everything at or past the last
                 // bound (and, by wrap-around, everything below the first) reads the zero word
                 const uint32_t tb = min(((uint32_t)v[4 * j + k] - ulo) >> bsh, kSsBits);
                 const uint32_t w = bits[tb >> 5];
-                need |= (__funnelshift_r(w, 0u, tb) & 1u) << k;           // shift count taken mod 32
+                nd |= (__funnelshift_r(w, 0u, tb) & 1u) << k;             // shift count taken mod 32
             }
-            need &= okmask >> (4 * j);
-            const uint32_t c = __popc(need);
-            const uint32_t incl = warp_incl_scan(c, lane);
-            const uint32_t tot = __shfl_sync(kFull, incl, 31);
-            if (tot == 0) continue;
-            if (wcount + tot > (uint32_t)SS_WORK) {            // no room for this group: resolve first
-                __syncwarp();
-                nhits = ss_resolve(L, S.off, work, wcount, my_cnt, my_hits, nhits, lane, lt);
-                wcount = 0;
-                __syncwarp();
-            }
-            uint32_t slot = wcount + incl - c;
+            nd &= okmask >> (4 * j);
+            need[j] = nd;
+            packed |= (uint32_t)__popc(nd) << (8 * j);
+        }
+        const uint32_t incl = warp_incl_scan(packed, lane);
+        const uint32_t totp = __shfl_sync(kFull, incl, 31);
+        if (totp == 0) continue;
+        const uint32_t tot = __dp4a(totp, 0x01010101u, 0u);        // sum of the four group totals, <= 512
+        if (wcount + tot > (uint32_t)SS_WORK) {                    // no room for this tile: resolve first
+            __syncwarp();
+            nhits = ss_resolve(L, S.off, work, wcount, my_cnt, my_hits, nhits, lane, lt);
+            wcount = 0;
+            __syncwarp();
+        }
+        const uint32_t excl = incl - packed;
+        uint32_t gbase = wcount;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t slot = gbase + ((excl >> (8 * j)) & 0xFFu);
             const uint32_t rel0 = t * SS_WTILE + j * 128 + lane * 4;     // row within the chunk
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (need & (1u << k)) work[slot++] = make_uint2((uint32_t)v[4 * j + k], rel0 + k);
-            wcount += tot;
+                if (need[j] & (1u << k)) work[slot++] = make_uint2((uint32_t)v[4 * j + k], rel0 + k);
+            gbase += (totp >> (8 * j)) & 0xFFu;
         }
+        wcount += tot;
     }
     if (wcount) {
         __syncwarp();
@@ -378,6 +389,15 @@ ss_emit_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict_
     }
     if (avail) ss_drain(queue, head, avail, lane, run, row_begin, outs, capacity);
 }
+
+// r01v-y, tried and dropped: a lane-independent emit (every lane owns a contiguous slice of the
+// chunk's hit list, counts per query into its own cell of a [query][lane] matrix in shared
+// memory, prefixes over the lanes, second walk writes at base[q] + prefix++).  It needs 35 M warp
+// instructions against the 59 M of the ballot form above and was slower in every variant tried
+// (4-byte loads 158 us, 16-byte loads 140 us, fire-and-forget shared atomics + prefetch 146 us,
+// against 110 us): the per-lane walk of the list is a chain of dependent L2 / DRAM loads at
+// 25 % occupancy (ncu r01x: issue active 26 %, 6.6 warps per issue waiting on global loads),
+// where the ballot form reads the list coalesced, one line per 32 hits.
 
 // ---- launch -------------------------------------------------------------------------------------
 SharedScanGeom shared_scan_geom(uint32_t n, int sm_count) {
