@@ -411,8 +411,10 @@ def run_engine(args):
             sv.free()
         line["selectivity_sweep"] = sweep
 
+    # second half of BASELINE.json's metric: hash-join tuples/s (config 4).  N > 1: both tables
+    # row-range sharded, pairs hash-routed to their owners, joined locally.
     join_sharded = None
-    if world > 1 and args.ops:
+    if world > 1 and not args.no_join:
         join_sharded = measure_join_sharded(eng, dist, rank, world, local)
 
     # ---- e2e and cpu_baseline (rank 0; the CPU leg only at N = 1) ----------------------------
@@ -422,13 +424,18 @@ def run_engine(args):
         line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = measure_cpu(args, eng, cols, res, shard_rows, lo, hi)
-        if world == 1 and args.ops:
+        if world == 1 and (args.ops or not args.no_join):
             for c1, c2 in cols[1:]:
                 c1.free()
                 c2.free()
+        if world == 1 and not args.no_join and not args.ops:
+            line["hash_join"] = measure_join_single(args)
+        if world == 1 and args.ops:
             line["ops"] = measure_ops(args)
-        if world > 1 and args.ops:
-            line["ops"] = {"hash_join_sharded": join_sharded}
+            if "hash_join_100Mx100M" in line["ops"]:
+                line["hash_join"] = join_summary(line["ops"]["hash_join_100Mx100M"], 1)
+        if world > 1 and join_sharded is not None:
+            line["hash_join"] = join_summary(join_sharded, world)
         emit(line)
     barrier()
     if dist is not None:
@@ -619,6 +626,32 @@ def measure_join_sharded(eng, dist, rank, world, local):
     return out
 
 
+def join_summary(cases: dict, world: int) -> dict:
+    """The `hash_join` object of the JSON line: tuples/s = (build + probe tuples) / time."""
+    out = {"metric": "hash-join tuples/sec", "unit": "tuples/s", "n_gpus": world,
+           "workload": "BASELINE config 4: 100M x 100M int32 key columns (uniform in [1, 100M]), prefilter "
+                       "select(f, null, x) on each side, hash join of the (value, position) pair lists"
+                       + (", pairs hash-partitioned across the ranks over NVLink" if world > 1 else ""),
+           "cases": cases}
+    full = cases.get("prefilter_1.0_1.0")
+    if full:
+        out["value"] = full["tuples_per_s"]
+        out["ms"] = full["ms"]
+    return out
+
+
+def measure_join_single(args):
+    """BASELINE config 4 on one GPU (adb_hash_join_count + adb_join_emit), two prefilter cases."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_ops
+    import analytical_database_b200 as adb
+    eng = adb.Engine(int(os.environ.get("LOCAL_RANK", "0")))     # same library instance
+    try:
+        return join_summary(bench_ops.bench_join(eng, 1.0, cases=((0.8, 0.15), (1.0, 1.0))), 1)
+    except Exception as e:                                        # the headline line must survive
+        return {"error": repr(e)}
+
+
 def measure_ops(args):
     """The other BASELINE.json configs on one GPU, bounded: batched shared scan (config 2),
     index range select + fetch (config 3), hash join with prefilters (config 4); plus the two
@@ -713,6 +746,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-join", action="store_true", help="skip the hash-join measurement (config 4)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: aggregate exchange through the engine's peer-memory kernel or NCCL")
     ap.add_argument("--exchange-self", action="store_true",
