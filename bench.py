@@ -497,6 +497,8 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
             api.drop(h_)
         return total, hits
 
+    h_pair = torch.zeros(2, dtype=torch.int64).pin_memory()
+
     def step():
         tot = hits = 0
         for (a, b) in hcols:
@@ -504,9 +506,13 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
             tot += t_
             hits += h_
         if dist is not None:
-            t_sum[0], t_sum[1] = tot, hits
+            # the ranks' host-side sums meet in one all-reduce: one pinned H2D copy down, one
+            # D2H copy back (element-wise tensor writes and .item() cost a launch + sync each)
+            h_pair[0], h_pair[1] = tot, hits
+            t_sum.copy_(h_pair, non_blocking=True)
             dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
-            tot, hits = int(t_sum[0].item()), int(t_sum[1].item())
+            h_pair.copy_(t_sum)
+            tot, hits = int(h_pair[0]), int(h_pair[1])
         return tot, hits
 
     steps = max(3, min(args.steps, 10))
@@ -528,8 +534,8 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
         dt = float(t.item())
     rows_step = shard_rows * len(cols) * max(world, 1)
     out = {"value": rows_step * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": 0,
-           "d2h_bytes_per_step": (8 + 24) * len(cols),
+           "h2d_bytes_per_step": 16 if dist is not None else 0,
+           "d2h_bytes_per_step": (8 + 24) * len(cols) + (16 if dist is not None else 0),
            "ms_per_step": 1e3 * dt / steps, "steps": steps,
            "api": "select_column -> fetch_column -> sum of include/adb_query_api.h "
                   "(libadb_query.so = host/query_shim.c), one call chain per shard",
