@@ -25,6 +25,23 @@ __device__ __forceinline__ int32_t ld_stream(const int32_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
+// Random accesses (gathers over position lists, hash-table probes): a miss of a plain load
+// brings a whole 128-byte line in from DRAM on this part whatever the cache operator or
+// cudaLimitMaxL2FetchGranularity says (profiles/r01c_gather_probe.md); the .L2::64B prefetch-size
+// qualifier (SASS LDG.E.LTC64B) halves that to 64 bytes per miss (r01z: 5 M sparse hits
+// 660 -> 340 MB of DRAM reads, 103 -> 82 us).
+__device__ __forceinline__ int32_t ld_gather(const int32_t *p) {
+    int32_t r;
+    asm volatile("ld.global.nc.L2::64B.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_gather(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void st_stream(int4 *p, const int4 &v) {
     asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
                  "r"(v.y), "r"(v.z), "r"(v.w)

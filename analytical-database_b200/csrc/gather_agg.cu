@@ -34,24 +34,24 @@ fetch_kernel(const int32_t *__restrict__ col, const int32_t *__restrict__ pos, i
         for (; i + stride < nvec; i += 2 * stride) {
             const int4 p0 = ld_stream(pos4 + i), p1 = ld_stream(pos4 + i + stride);
             int4 v0, v1;
-            v0.x = __ldg(col + (p0.x - base)); v0.y = __ldg(col + (p0.y - base));
-            v0.z = __ldg(col + (p0.z - base)); v0.w = __ldg(col + (p0.w - base));
-            v1.x = __ldg(col + (p1.x - base)); v1.y = __ldg(col + (p1.y - base));
-            v1.z = __ldg(col + (p1.z - base)); v1.w = __ldg(col + (p1.w - base));
+            v0.x = ld_gather(col + (p0.x - base)); v0.y = ld_gather(col + (p0.y - base));
+            v0.z = ld_gather(col + (p0.z - base)); v0.w = ld_gather(col + (p0.w - base));
+            v1.x = ld_gather(col + (p1.x - base)); v1.y = ld_gather(col + (p1.y - base));
+            v1.z = ld_gather(col + (p1.z - base)); v1.w = ld_gather(col + (p1.w - base));
             out4[i] = v0;
             out4[i + stride] = v1;
         }
         for (; i < nvec; i += stride) {
             const int4 p0 = ld_stream(pos4 + i);
             int4 v0;
-            v0.x = __ldg(col + (p0.x - base)); v0.y = __ldg(col + (p0.y - base));
-            v0.z = __ldg(col + (p0.z - base)); v0.w = __ldg(col + (p0.w - base));
+            v0.x = ld_gather(col + (p0.x - base)); v0.y = ld_gather(col + (p0.y - base));
+            v0.z = ld_gather(col + (p0.z - base)); v0.w = ld_gather(col + (p0.w - base));
             out4[i] = v0;
         }
         for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
-            out[t] = __ldg(col + (pos[t] - base));
+            out[t] = ld_gather(col + (pos[t] - base));
     } else {
-        for (; i < n; i += stride) out[i] = __ldg(col + (pos[i] - base));
+        for (; i < n; i += stride) out[i] = ld_gather(col + (pos[i] - base));
     }
 }
 

@@ -183,7 +183,7 @@ hj_table_build_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
 }
 
 // Probe side in its original row order: one random 16-byte slot read per row (linear probing
-// almost always ends inside the same 128-byte line), results stored coalesced.
+// almost always ends inside the same 64-byte half line, which is what a miss fetches: ld_gather), results stored coalesced.
 __global__ void __launch_bounds__(HJ_THREADS)
 hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe,
                 const unsigned long long *__restrict__ toff, uint32_t part_bits,
@@ -199,7 +199,7 @@ hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe,
             const unsigned long long mask = cap - 1;
             unsigned long long s = hj_mix(tag) & mask;
             while (true) {
-                const uint4 sl = __ldg(table + t0 + s);
+                const uint4 sl = ld_gather(table + t0 + s);
                 if (sl.x == tag) { r = make_uint2(sl.y, sl.z); break; }
                 if (sl.x == 0u) break;
                 s = (s + 1) & mask;
@@ -232,7 +232,7 @@ hj_expand_kernel(const uint2 *__restrict__ gc_by_j,
             out_probe[off] = pp;
         } else if (cnt && cnt <= 8) {
             for (uint32_t r = 0; r < cnt; ++r) {
-                out_build[off + r] = build_pos_sorted[gs + r];
+                out_build[off + r] = ld_gather(build_pos_sorted + gs + r);
                 out_probe[off + r] = pp;
             }
         }

@@ -240,9 +240,9 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
                         const uint32_t b = __ffs(bits) - 1;
                         bits &= bits - 1;
                         const uint32_t row = row0 + q * 32 + b;
-                        out[out_off + r] = PAIRS ? pos_in[row] : (int32_t)row + base_pos;
+                        out[out_off + r] = PAIRS ? ld_gather(pos_in + row) : (int32_t)row + base_pos;
                         if (FETCH) {
-                            const int32_t v = __ldg(fcol + row);
+                            const int32_t v = ld_gather(fcol + row);
                             vout[out_off + r] = v;
                             acc.add(v);
                         }
@@ -263,7 +263,7 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
                             bits &= bits - 1;
                             if (rr >= done && rr < lim) {
                                 const uint32_t row = row0 + q * 32 + b;
-                                stage[rr - done] = (PAIRS && !FETCH) ? pos_in[row] : (int32_t)row;
+                                stage[rr - done] = (PAIRS && !FETCH) ? ld_gather(pos_in + row) : (int32_t)row;
                             }
                             ++rr;
                         }
@@ -285,8 +285,8 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
                             }
 #pragma unroll
                             for (int k = 0; k < GB; ++k) {
-                                v[k] = row[k] >= 0 ? __ldg(fcol + row[k]) : 0;
-                                p[k] = PAIRS ? (row[k] >= 0 ? __ldg(pos_in + row[k]) : 0) : row[k] + base_pos;
+                                v[k] = row[k] >= 0 ? ld_gather(fcol + row[k]) : 0;
+                                p[k] = PAIRS ? (row[k] >= 0 ? ld_gather(pos_in + row[k]) : 0) : row[k] + base_pos;
                             }
 #pragma unroll
                             for (int k = 0; k < GB; ++k)

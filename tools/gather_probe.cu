@@ -16,6 +16,16 @@ template <> __device__ __forceinline__ int ld<4>(const int* p) { int r; asm vola
 template <> __device__ __forceinline__ int ld<5>(const int* p) { int r; asm volatile("ld.global.nc.L1::evict_last.s32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
 template <> __device__ __forceinline__ int ld<6>(const int* p) { int r; asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
 
+template <> __device__ __forceinline__ int ld<7>(const int* p) { int r; asm volatile("ld.global.L2::64B.s32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
+template <> __device__ __forceinline__ int ld<8>(const int* p) { int r; asm volatile("ld.global.nc.L1::no_allocate.L2::64B.s32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
+template <> __device__ __forceinline__ int ld<9>(const int* p) {
+    int r; unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol)); return r; }
+template <> __device__ __forceinline__ int ld<10>(const int* p) { int r; asm volatile("ld.global.nc.L1::no_allocate.L2::256B.s32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
+template <> __device__ __forceinline__ int ld<11>(const int* p) {     // 1-byte load of the wanted word's low byte
+    unsigned r; asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(r) : "l"(p)); return (int)r; }
+
 template <int V>
 __global__ void __launch_bounds__(256) gather(const int* __restrict__ col, const int* __restrict__ pos, long n, int* __restrict__ out) {
     long stride = (long)gridDim.x * blockDim.x;
@@ -47,5 +57,10 @@ int main(int argc, char** argv) {
     run<4>("ld.global.lu",col,pos,h,out);
     run<5>("nc.L1::evict_last",col,pos,h,out);
     run<6>("ld.volatile",col,pos,h,out);
+    run<7>("ld.global.L2::64B",col,pos,h,out);
+    run<8>("nc.no_allocate.L2::64B",col,pos,h,out);
+    run<9>("nc.no_allocate.L2 evict_first hint",col,pos,h,out);
+    run<10>("nc.no_allocate.L2::256B",col,pos,h,out);
+    run<11>("nc.no_allocate.u8",col,pos,h,out);
     return 0;
 }
