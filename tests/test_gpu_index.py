@@ -114,3 +114,67 @@ def test_large_tree_levels(eng, port, rng):
             assert np.array_equal(np.sort(got), spos.to_host(sh))
             spos.free()
     eng.index_destroy(ix)
+
+
+def _view(eng, buf, offset_elems):
+    from analytical_database_b200.engine import DevBuf
+    v = DevBuf.__new__(DevBuf)
+    v.eng, v.nbytes, v.ptr = eng, 0, buf.ptr + 4 * offset_elems
+    return v
+
+
+def test_full_size_index_properties(eng):
+    """BASELINE config 3 at its full size: a 500 M-row column -- the index build and both range
+    lookups, checked through size-independent properties (the oracle's quicksort needs
+    minutes there): sortedness, permutation, value/position pairing, agreement of the index
+    path with the scan path on counts and on the fetched values, B+-tree = sorted array."""
+    n = 500_000_000
+    key = eng.synth_uniform(n, 7, 0, 0, (1 << 31) - 1)
+    pay = eng.synth_uniform(n, 8, 0, 0, 10000)
+    vals, poss = eng.index_sort(key, n)
+    # (1) values ascending: min(v[i+1] - v[i]) >= 0 (no wrap: values are in [0, 2^31))
+    d = eng.aggregate(eng.ewise(_view(eng, vals, 1), vals, n - 1, True), n - 1)
+    assert d.min >= 0
+    # (2) pairing: values[i] == key[positions[i]] for every i
+    f = eng.fetch(key, poss, n)
+    z = eng.aggregate(eng.ewise(f, vals, n, True), n)
+    assert z.min == 0 and z.max == 0
+    f.free()
+    # (3) positions are a permutation of 0 .. n-1: right sum, and -- sorted once more -- strictly
+    #     ascending from 0 to n-1
+    ps = eng.aggregate(poss, n)
+    assert ps.sum == n * (n - 1) // 2 and ps.min == 0 and ps.max == n - 1
+    sp, _ = eng.index_sort(poss, n)
+    dd = eng.aggregate(eng.ewise(_view(eng, sp, 1), sp, n - 1, True), n - 1)
+    assert dd.min == 1 and dd.max == 1
+    sp.free(); _.free()
+    # (4) stability (the order adb_index_sort documents): inside a run of equal values the
+    #     positions ascend.  Equal neighbours have v[i+1] - v[i] == 0; there p[i+1] - p[i] > 0.
+    #     Checked on a 4 M-entry window on the host.
+    w = 4_000_000
+    hv, hp = vals.to_host(w, offset_bytes=4 * 123_456_789), poss.to_host(w, offset_bytes=4 * 123_456_789)
+    eq = hv[1:] == hv[:-1]
+    assert np.all(hp[1:][eq] > hp[:-1][eq])
+    # (5) range lookups against the scan path
+    ix = eng.index_create(vals, poss, n, with_btree=True)
+    vmin = int(vals.to_host(1)[0])
+    for lo, width in [(max(vmin, 1000), (1 << 31) // 5000), (1 << 29, (1 << 31) // 100), (1 << 30, (1 << 31) // 10)]:
+        hi = lo + width
+        ps_, hs = eng.select_index_exact(ix, lo, hi, use_btree=False)
+        pb_, hb = eng.select_index_exact(ix, lo, hi, use_btree=True)
+        scan_pos, scan_h = eng.select_exact(key, n, lo, hi)
+        assert hs == hb == scan_h
+        same = eng.aggregate(eng.ewise(ps_, pb_, hs, True), hs)
+        assert same.min == 0 and same.max == 0                       # B+-tree == sorted array
+        fk = eng.aggregate(eng.fetch(key, ps_, hs), hs)
+        assert lo <= fk.min and fk.max < hi                          # every emitted row qualifies
+        # the same set of rows as the scan: equal position sums and equal payload aggregates
+        a_ix, a_sc = eng.aggregate(ps_, hs), eng.aggregate(scan_pos, hs)
+        assert (a_ix.sum, a_ix.min, a_ix.max) == (a_sc.sum, a_sc.min, a_sc.max)
+        p_ix, p_sc = eng.aggregate(eng.fetch(pay, ps_, hs), hs), eng.aggregate(eng.fetch(pay, scan_pos, hs), hs)
+        assert (p_ix.sum, p_ix.min, p_ix.max) == (p_sc.sum, p_sc.min, p_sc.max)
+        for b in (ps_, pb_, scan_pos):
+            b.free()
+    eng.index_destroy(ix)
+    for b in (key, pay, vals, poss):
+        b.free()

@@ -125,3 +125,40 @@ def test_index_sort(eng, port, rng, n):
         dv, dp = eng.index_sort(col, n)
         ev, ep = port.index_sort(data)
         assert np.array_equal(dv.to_host(n), ev) and np.array_equal(dp.to_host(n), ep.astype(np.int32))
+
+
+def test_full_size_join_properties(eng):
+    """BASELINE config 4 at its full size on one GPU: 100 M x 100 M rows, prefilters at 80 % and
+    15 %, hash join of the (value, position) pair lists.  The oracle's multimap needs minutes
+    there, so: the pair count equals sum_k count1(k) * count2(k) from host histograms of the
+    very keys the GPU joined; every pair joins equal keys; the output is probe-major (probe
+    positions non-decreasing, query.c:669-681) and inside one probe row the build positions
+    keep the build side's order (insertion order of the multimap, multimap.c:74-90)."""
+    n = 100_000_000
+    k1, k2 = eng.synth_uniform(n, 11, 0, 1, n), eng.synth_uniform(n, 12, 0, 1, n)
+    f1, f2 = eng.synth_uniform(n, 13, 0, 0, 1000), eng.synth_uniform(n, 14, 0, 0, 1000)
+    p1, c1 = eng.select_exact(f1, n, None, 800)
+    p2, c2 = eng.select_exact(f2, n, None, 150)
+    v1, v2 = eng.fetch(k1, p1, c1), eng.fetch(k2, p2, c2)
+    assert c1 > c2                                            # parse.c:798-813: larger side builds
+    o1, o2, m = eng.join(v1, p1, c1, v2, p2, c2)
+    h1 = np.bincount(v1.to_host(c1), minlength=n + 1)
+    hv2 = v2.to_host(c2)
+    assert m == int(h1[hv2].sum())                            # sum_k count1(k) * count2(k)
+    # equal keys on both sides of every pair
+    z = eng.aggregate(eng.ewise(eng.fetch(k1, o1, m), eng.fetch(k2, o2, m), m, True), m)
+    assert z.min == 0 and z.max == 0
+    # every output position passed its side's prefilter
+    a1, a2 = eng.aggregate(eng.fetch(f1, o1, m), m), eng.aggregate(eng.fetch(f2, o2, m), m)
+    assert a1.max < 800 and a2.max < 150
+    # probe-major order; ties (one probe row, several build rows) in build order
+    ho1, ho2 = o1.to_host(m), o2.to_host(m)
+    assert np.all(ho2[1:] >= ho2[:-1])
+    tie = ho2[1:] == ho2[:-1]
+    assert tie.any() and np.all(ho1[1:][tie] > ho1[:-1][tie])
+    # per probe row the group size is the build side's count of its key
+    rows, cnt = np.unique(ho2, return_counts=True)
+    hp2 = p2.to_host(c2)
+    keys_of_rows = hv2[np.searchsorted(hp2, rows)]
+    assert np.array_equal(cnt, h1[keys_of_rows])
+    assert rows.size == int((h1[hv2] > 0).sum())
