@@ -357,10 +357,11 @@ def run_engine(args):
                         "avg_launch_ms": f_ms, "share_of_step": float(f_ms * len(cols) / ms_step),
                         "algorithmic_bytes_per_launch": 16.0 * h_avg,
                         "achieved": 16.0 * h_avg / (f_ms * 1e-3) / 1e9,
-                        "line_granular_bytes_per_launch": 128.0 * h_avg + 8.0 * h_avg + shard_rows / 8.0,
-                        "note": "a sparse gather moves one 128-byte line per hit on this part "
-                                "(profiles/r01c_gather_probe.md), so the kernel is DRAM-bound at "
-                                "about 8x its algorithmic bytes"}}
+                        "miss_granular_bytes_per_launch": 64.0 * h_avg + 8.0 * h_avg + shard_rows / 8.0,
+                        "note": "a sparse gather moves 64 bytes per hit with ld.global.nc.L2::64B "
+                                "(128 with a plain load; profiles/r01c_gather_probe.md): the kernel's "
+                                "DRAM traffic is about 5x its algorithmic bytes, and at 5 M random "
+                                "reads per launch it runs at the DRAM random-access rate"}}
     chain_bytes = 4.0 * rows_step + 20.0 * g_cnt
     chain_gbs = chain_bytes / (ms_step * 1e-3) / 1e9
 

@@ -32,7 +32,8 @@ def main():
     d = json.load(open(os.path.join(g, f"{tag}_bench_n1.json")))
     rf = d["roofline"]
     a_ms, b_ms = rf["avg_launch_ms"], rf["second_kernel"]["avg_launch_ms"]
-    m, e = agg["mask_kernel"], agg["expand_kernel<0, 1>"]
+    m = agg["mask_kernel"]
+    e = next(v for k, v in agg.items() if k.startswith("expand_kernel<0, 1"))
     mu, eu = m[1] / 1e3 / m[0], e[1] / 1e3 / e[0]
     out = [f"# {tag}: the north-star chain as shipped (2 launches per shard), ncu --set full, one 500 M-row shard, 1 % selectivity", "",
            "Command: `ncu --set full --clock-control none --import-source on -k regex:\"mask_kernel|expand_kernel\" -s 4 -c 2 "
@@ -42,7 +43,7 @@ def main():
            "--no-sweep`).  Both come from `tools/run_round_checks.sh`; this file from `tools/profile_chain_summary.py`.", "",
            md, "",
            "Launch list (all launches of the bench command, cold-cache serialised times; it also contains the e2e leg's "
-           "three-operator selects):", "", "| kernel | launches | total ms | avg us |", "|---|---|---|---|"]
+           "operator calls: with the deferred select these are the same two kernels plus count_total / publish):", "", "| kernel | launches | total ms | avg us |", "|---|---|---|---|"]
     for k, (n, t) in agg.items():
         out.append(f"| {k} | {n} | {t / 1e6:.3f} | {t / 1e3 / n:.1f} |")
     out += ["", f"Per shard of the device-resident step: mask_kernel {mu:.1f} us + fused expansion {eu:.1f} us under ncu = "
