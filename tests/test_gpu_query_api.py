@@ -375,3 +375,97 @@ def test_deferred_select_survives_a_foreign_engine_select(api, cpu, rng):
     assert h_ == epos.size and agg.sum == cpu.sum(evals) and agg.count == epos.size
     assert agg.min == cpu.min(evals) and agg.max == cpu.max(evals)
     assert np.array_equal(p_.to_host(h_), epos) and np.array_equal(v_.to_host(h_), evals)
+
+
+def test_random_walk_over_the_operator_api(api, cpu):
+    """A seeded random sequence of 600 operator calls over a pool of handles, every observable
+    value compared with a numpy model built from the oracle: whatever order the plumbing uses,
+    re-binds and releases handles in (client_context.c:31-45,76-90), deferred or not."""
+    rng = np.random.default_rng(2026)
+    n = 60_000
+    data = [rng.integers(-n // 2, n // 2, n).astype(np.int32) for _ in range(3)]
+    cols = [api.column(d) for d in data]
+    live0 = api.lib.adb_host_live_device_results()
+    pos, val = [], []                      # (handle, model array) pools
+
+    def bounds():
+        a, b = sorted(int(x) for x in rng.integers(-n // 2 - 10, n // 2 + 10, 2))
+        return [(a, b), (None, b), (a, None), (a, a + int(rng.integers(0, 50)))][int(rng.integers(0, 4))]
+
+    def check(h, model):
+        assert h.contents.num_tuples == model.size
+        assert np.array_equal(api.tuples(h), model)
+
+    for step in range(600):
+        op = int(rng.integers(0, 12))
+        if op <= 1 or not pos:                                   # select over a base column
+            c = int(rng.integers(0, 3))
+            lo, hi = bounds()
+            pos.append((api.select_column(cols[c], lo, hi), cpu.select_scan(data[c], lo, hi)))
+        elif op <= 3:                                            # fetch through some position list
+            c = int(rng.integers(0, 3))
+            h, m = pos[int(rng.integers(0, len(pos)))]
+            val.append((api.fetch_column(cols[c], h), cpu.fetch(data[c], m), h, m))
+        elif op == 4 and val:                                    # aggregate
+            h, m, _, _ = val[int(rng.integers(0, len(val)))]
+            if m.size:
+                name = ["sum", "average", "min", "max"][int(rng.integers(0, 4))]
+                r = api.sum_result(h) if name == "sum" else api.unary(name, h)
+                got = api.tuples(r)[0]
+                if name == "average":
+                    assert got.tobytes() == np.float64(cpu.avg(m)).tobytes()
+                else:
+                    assert int(got) == {"sum": cpu.sum, "min": cpu.min, "max": cpu.max}[name](m)
+                api.drop(r)
+        elif op == 5 and val:                                    # read a value vector
+            h, m, _, _ = val[int(rng.integers(0, len(val)))]
+            check(h, m)
+        elif op == 6:                                            # read a position list
+            h, m = pos[int(rng.integers(0, len(pos)))]
+            check(h, m)
+        elif op == 7 and val:                                    # select over (values, their positions)
+            h, m, ph, pm = val[int(rng.integers(0, len(val)))]
+            if any(ph is p for p, _ in pos):                     # the position list is still bound
+                lo, hi = bounds()
+                pos.append((api.select_result(h, ph, lo, hi), cpu.select_result(m, pm, lo, hi)))
+        elif op == 8 and len(val) >= 2:                          # add / sub of equally long vectors
+            i, j = rng.integers(0, len(val), 2)
+            (h1, m1, _, _), (h2, m2, _, _) = val[int(i)], val[int(j)]
+            if m1.size == m2.size:
+                sub = bool(rng.integers(0, 2))
+                r = api.binary("sub" if sub else "add", h1, h2)
+                exp = (m1.astype(np.int64) - m2 if sub else m1.astype(np.int64) + m2).astype(np.int32)
+                check(r, exp)
+                api.drop(r)
+        elif op == 9 and val:                                    # release a value vector
+            h, _, _, _ = val.pop(int(rng.integers(0, len(val))))
+            api.drop(h)
+        elif op == 10 and len(pos) > 1:                          # release a position list
+            h, _ = pos.pop(int(rng.integers(0, len(pos))))
+            api.drop(h)
+        elif op == 11:
+            which = int(rng.integers(0, 3))
+            if which == 0:                                       # insert_row re-mmaps: db_manager.c:178-186
+                api.lib.adb_host_column_invalidate(C.byref(cols[int(rng.integers(0, 3))]))
+            elif which == 1 and val:                             # print of a short vector
+                h, m, _, _ = val[int(rng.integers(0, len(val)))]
+                if 0 < m.size <= 5000:
+                    assert api.print(h) == "\n".join(str(int(v)) for v in m)
+            else:                                                # a small batch in between
+                c = int(rng.integers(0, 3))
+                lows, highs = [-100, 5, 2000], [300, 6, 2100]
+                res = api.shared_select(cols[c], lows, highs)
+                for r, lo, hi in zip(res, lows, highs):
+                    check(r, cpu.select_scan(data[c], lo, hi))
+                    api.drop(r)
+        if len(pos) > 12:
+            api.drop(pos.pop(0)[0])
+        if len(val) > 12:
+            api.drop(val.pop(0)[0])
+    for h, m, _, _ in val:
+        check(h, m)
+        api.drop(h)
+    for h, m in pos:
+        check(h, m)
+        api.drop(h)
+    assert api.lib.adb_host_live_device_results() == live0
