@@ -44,6 +44,10 @@ def main():
     g = eng.read_agg(dagg)
     assert g.count == e.size and g.sum == port.sum(port.fetch(b, e))
     assert np.array_equal(val.to_host(e.size), port.fetch(b, e))
+    # deferred emit (count, host sizes both lists, positions + gather + aggregates in one kernel)
+    dp, dv, dh, dg = eng.select_fetch_agg_deferred(da, db, n, -2000, 3000)
+    assert dh == e.size and (dg.sum, dg.count, dg.min, dg.max) == (g.sum, g.count, g.min, g.max)
+    assert np.array_equal(dp.to_host(dh), e) and np.array_equal(dv.to_host(dh), port.fetch(b, e))
     # shared scan: sparse, dense and nested batches
     for lows, highs in [(rng.integers(-5000, 4000, 40), None), (np.arange(0, 150), 1000 - np.arange(0, 150))]:
         lows = lows.astype(np.int32)
