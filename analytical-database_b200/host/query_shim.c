@@ -36,6 +36,7 @@
 #define _GNU_SOURCE
 #endif
 #include <limits.h>
+#include <malloc.h>
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -214,6 +215,15 @@ int adb_host_init(int device) {
     S.d_agg = (adb_agg *)p;
     const char *m = getenv("ADB_SHIM_MIRROR");
     S.mirror = m && m[0] && m[0] != '0';
+    /* Result payloads are plain malloc blocks of 4 * num_tuples bytes that nobody writes
+     * (the plumbing only frees them): above glibc's mmap threshold every handle costs an
+     * mmap + munmap pair (~10 us for a 20 MB list).  Serve them from the heap instead (up to 32 MB) and
+     * keep the freed space.  ADB_SHIM_NO_MALLOPT=1 leaves the process's malloc policy alone. */
+    const char *nm = getenv("ADB_SHIM_NO_MALLOPT");
+    if (!(nm && nm[0] && nm[0] != '0')) {
+        mallopt(M_MMAP_THRESHOLD, 32 << 20);         /* glibc's ceiling on 64-bit */
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    }
     const char *eager = getenv("ADB_SHIM_EAGER");
     S.lazy = !S.mirror && !(eager && eager[0] && eager[0] != '0');
     S.up = 1;
