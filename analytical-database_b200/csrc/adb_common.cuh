@@ -405,6 +405,12 @@ struct SharedScanPlan {
     // query q covers the contiguous interval ids q_first[q] .. q_last[q] (first >= 1; first >
     // last for an empty query): its hit count is a difference of interval-count prefix sums
     const uint16_t *q_first, *q_last;
+    // pair lists: when no value is covered by more than a few queries the classify pass lists
+    // one {query, row} entry per (row, covering query) pair -- list_rows = chunk_rows * deepest
+    // cover entries per chunk -- and the emit pass never looks an interval up; 0 = the chunk
+    // lists hold one {interval, row} entry per hit row (heavily overlapping batches)
+    uint32_t pair_depth;
+    const uint32_t *cov4;      // per interval id: its covering queries by colour, one byte each, 0xFF = none
 };
 constexpr uint32_t kSsLut = 1024;
 constexpr uint32_t kSsBits = 1u << 16;

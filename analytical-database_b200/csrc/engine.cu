@@ -990,7 +990,8 @@ constexpr size_t kSsLutOff = kSsBoundsBytes + 640 + ((kSsCovBytes + 15) / 16) * 
 constexpr size_t kSsLutBytes = ((2 * (adb::kSsLut + 1) + 15) / 16) * 16;
 constexpr size_t kSsBitsOff = kSsLutOff + kSsLutBytes;
 constexpr size_t kSsQOff = kSsBitsOff + adb::kSsBits / 8;            // q_first | q_last, uint16 each
-constexpr size_t kSsPlanBytes = kSsQOff + 2 * 2 * ((ADB_MAX_BATCH + 7) / 8) * 8;
+constexpr size_t kSsCov4Off = kSsQOff + 2 * 2 * ((ADB_MAX_BATCH + 7) / 8) * 8;   // 4 query ids per interval id
+constexpr size_t kSsPlanBytes = kSsCov4Off + 4 * (2 * ADB_MAX_BATCH + 8);
 constexpr size_t kSsMaxChunks = 8192;
 
 adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
@@ -1026,6 +1027,8 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
     }
     if (m >= 1) off[m + 1] = (uint16_t)cov.size();
     if (m == 0) off[1] = 0;
+    uint32_t deepest = 1;                                   // most queries covering one value
+    for (uint32_t k = 1; k < m; ++k) deepest = std::max<uint32_t>(deepest, (uint32_t)(off[k + 1] - off[k]));
     // one packed upload: bounds | cov_off | cov_q.  The source is pageable, so the call returns
     // once the bytes sit in the driver's staging memory: no synchronisation needed before the
     // host vector goes out of scope.
@@ -1078,6 +1081,40 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
                 ql[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, highs[q]) - bounds);
             }
         }
+        // Pair lists (<= 4 queries deep): the queries are coloured so that overlapping ones get
+        // different colours -- they are intervals, so going through them by lower bound and
+        // taking the lowest colour no still-open query holds needs exactly `deepest` colours --
+        // and every interval id lists its covering queries BY COLOUR (0xFF = none).  The
+        // classify pass then emits a batch's pairs colour by colour: a query lives in one
+        // colour, so its pairs stay in row order, which is all the emit pass needs.
+        uint32_t *cov4 = reinterpret_cast<uint32_t *>(plan.data() + kSsCov4Off);
+        for (uint32_t k = 0; k <= m + 1 && k < 2 * ADB_MAX_BATCH + 8; ++k) cov4[k] = 0xFFFFFFFFu;
+        if (deepest <= 4) {
+            std::vector<int32_t> order;
+            for (int32_t q = 0; q < q_count; ++q) if (lows[q] < highs[q]) order.push_back(q);
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                return lows[a] != lows[b] ? lows[a] < lows[b] : a < b; });
+            int32_t open_high[4];
+            bool open_used[4] = {false, false, false, false};
+            std::vector<uint8_t> colour((size_t)q_count, 0);
+            for (int32_t q : order) {
+                int c = -1;
+                for (int k = 0; k < 4; ++k) {
+                    if (open_used[k] && open_high[k] <= lows[q]) open_used[k] = false;     // closed before q opens
+                    if (c < 0 && !open_used[k]) c = k;
+                }
+                if (c < 0) { deepest = 5; break; }               // cannot happen for depth <= 4; stay safe
+                open_used[c] = true;
+                open_high[c] = highs[q];
+                colour[(size_t)q] = (uint8_t)c;
+            }
+            if (deepest <= 4)
+                for (uint32_t k = 1; k < m; ++k)
+                    for (uint32_t c = off[k]; c < off[k + 1]; ++c) {
+                        const uint32_t q = cov[c], sh = 8u * colour[q];
+                        cov4[k] = (cov4[k] & ~(0xFFu << sh)) | (q << sh);
+                    }
+        }
         CU(cudaMemcpyAsync(g.ss_plan_mem, plan.data(), plan.size(), cudaMemcpyHostToDevice, g.stream));
     }
     g.ss_plan = adb::SharedScanPlan{reinterpret_cast<const int32_t *>(g.ss_plan_mem),
@@ -1087,7 +1124,8 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
                                     reinterpret_cast<const uint32_t *>(g.ss_plan_mem + kSsBitsOff),
                                     lut_shift, bit_shift, m ? bounds[0] : 0, span,
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff),
-                                    reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff) + ((ADB_MAX_BATCH + 7) / 8) * 8};
+                                    reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff) + ((ADB_MAX_BATCH + 7) / 8) * 8,
+                                    0u, reinterpret_cast<const uint32_t *>(g.ss_plan_mem + kSsCov4Off)};
     if (n == 0) {
         for (int32_t q = 0; q < q_count; ++q) if (h_counts) h_counts[q] = 0;
         g.ss_geom = adb::SharedScanGeom{0, 0, 0};
@@ -1096,7 +1134,12 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
     }
     g.ss_geom = adb::shared_scan_geom((uint32_t)n, g.sm_count);
     if (g.ss_geom.num_chunks > kSsMaxChunks) return fail(ADB_ERR_INVALID, "shared scan: chunk table overflow");
-    const size_t rows = (size_t)g.ss_geom.num_chunks * g.ss_geom.chunk_rows;
+    // pair lists while they stay small: <= 4 queries deep and <= 4 GB of scratch
+    size_t rows = (size_t)g.ss_geom.num_chunks * g.ss_geom.chunk_rows;
+    if (deepest <= 4 && rows * deepest * sizeof(uint32_t) <= ((size_t)4 << 30) && !getenv("ADB_SS_INTERVAL_LISTS")) {
+        g.ss_plan.pair_depth = deepest;
+        rows *= deepest;
+    }
     if (rows > g.ss_hits_rows) {
         if (g.ss_hits) { CU(cudaStreamSynchronize(g.stream)); CU(cudaFree(g.ss_hits)); g.ss_hits = nullptr; g.ss_hits_rows = 0; }
         cudaError_t e = cudaMalloc(&g.ss_hits, (rows + rows / 8 + 4096) * sizeof(uint32_t));

@@ -10,14 +10,18 @@
 //              ids ascending);
 //   classify   one streaming pass: a 64 K-bucket bitmap in shared memory dismisses rows no
 //              query wants with one bit test; candidate rows are compacted per warp and
-//              resolved densely (exact interval, per-warp-chunk per-query counters, one
-//              packed {interval, row} entry in the chunk's hit list);
+//              resolved densely (exact interval, per-warp-chunk per-interval counters) into
+//              the chunk's hit list;
 //   offsets    one CTA per query scans its row of the [query][chunk] count matrix;
-//   emit       each warp walks its chunk's hit list and queues (query, row) pairs in row
-//              order; 32 pairs at a time are ranked per query (one ballot per
-//              query-id bit) and appended at that query's running offset.  Every list
-//              therefore comes out ascending, as the reference's memcpy-concatenated
-//              thread slices do (query.c:563-574).
+//   emit       each warp turns its chunk's hit list into the queries' position lists.  Every
+//              list comes out ascending, as the reference's memcpy-concatenated thread
+//              slices do (query.c:563-574).
+//
+// The hit lists come in two forms.  While no value is wanted by more than four queries (the
+// usual batch) they hold one {query, row} entry per (row, query) pair and the emit pass sorts
+// them by query, tile by tile, in shared memory (ss_emit_sorted_kernel).  Heavily overlapping
+// batches list one {interval, row} entry per hit row and the emit pass expands each row's
+// cover list through a small pair queue (ss_emit_kernel).
 //
 // has_low / has_high are ignored and all queries share one column, exactly as
 // query.c:474 and server.c:376 do.
@@ -85,36 +89,50 @@ struct SsShared {                                  // carved out of dynamic shar
     uint32_t cnt[SS_WARPS][SS_BMAX + 4];           // hits per INTERVAL id (0 .. m), per warp
     int32_t bounds[SS_BMAX];
     uint16_t lut[SS_LUT + 2];
-    uint16_t off[SS_BMAX + 2];
+    uint32_t pack[SS_BMAX + 2];                    // per interval id: pair lists -- its covering queries by colour, one
+                                                   // byte each, 0xFF = none; interval lists -- 0 = covered, ~0 = not
 };
 
-// resolve work[0 .. wcount): all lanes busy except in the last batch
-__device__ __forceinline__ uint32_t ss_resolve(const SsLookup &L, const uint16_t *s_off, const uint2 *work,
-                                               uint32_t wcount, uint32_t *my_cnt,
+// resolve work[0 .. wcount): all lanes busy except in the last batch.
+// PAIRS: one {query, row} entry per (row, covering query) pair, written colour by colour: the
+// host coloured the queries so that overlapping ones differ, a query therefore lives in one
+// colour and its entries stay in row order -- all the emit pass needs -- and a batch costs
+// one ballot-compaction per colour instead of a scan plus a loop over each row's cover list.
+// Otherwise one {interval, row} entry per hit row.
+template <bool PAIRS>
+__device__ __forceinline__ uint32_t ss_resolve(const SsLookup &L, const uint32_t *s_pack, uint32_t depth,
+                                               const uint2 *work, uint32_t wcount, uint32_t *my_cnt,
                                                uint32_t *__restrict__ my_hits, uint32_t nhits,
                                                uint32_t lane, uint32_t lt) {
     for (uint32_t base = 0; base < wcount; base += kWarp) {
         const bool live = base + lane < wcount;
-        uint32_t id = 0, rel = 0, b = 0, e = 0;
+        uint32_t id = 0, rel = 0, p = 0xFFFFFFFFu;
         if (live) {
             const uint2 w = work[base + lane];
             rel = w.y;
             id = interval_of(L, (int32_t)w.x);
-            b = s_off[id];
-            e = s_off[id + 1];
+            p = s_pack[id];
         }
         // hits are counted per interval here; a query covers a contiguous run of intervals, so
         // its count is a difference of two prefix sums, taken once per chunk
-        const uint32_t m = __ballot_sync(kFull, e > b);
-        if (e > b) {
-            atomicAdd(&my_cnt[id], 1u);
-            my_hits[nhits + __popc(m & lt)] = (id << 23) | rel;           // rel < 2^23, id <= 300
+        if (p != 0xFFFFFFFFu) atomicAdd(&my_cnt[id], 1u);
+        if (!PAIRS) {
+            const uint32_t m = __ballot_sync(kFull, p != 0xFFFFFFFFu);
+            if (p != 0xFFFFFFFFu) my_hits[nhits + __popc(m & lt)] = (id << 23) | rel;   // rel < 2^23, id <= 300
+            nhits += __popc(m);
+        } else {
+            for (uint32_t c = 0; c < depth; ++c) {
+                const uint32_t q = (p >> (8 * c)) & 0xFFu;
+                const uint32_t m = __ballot_sync(kFull, q != 0xFFu);
+                if (q != 0xFFu) my_hits[nhits + __popc(m & lt)] = (q << 23) | rel;
+                nhits += __popc(m);
+            }
         }
-        nhits += __popc(m);
     }
     return nhits;
 }
 
+template <bool PAIRS>
 __global__ void __launch_bounds__(SS_THREADS)
 ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan plan,
                    uint32_t chunk_rows, uint32_t num_chunks, uint32_t *__restrict__ hitlist,
@@ -126,7 +144,8 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
         reinterpret_cast<uint4 *>(S.bits)[i] = reinterpret_cast<const uint4 *>(plan.bits)[i];
     for (uint32_t i = threadIdx.x; i < SS_LUT + 1; i += SS_THREADS) S.lut[i] = plan.lut[i];
     for (uint32_t i = threadIdx.x; i < plan.m; i += SS_THREADS) S.bounds[i] = plan.bounds[i];
-    for (uint32_t i = threadIdx.x; i < plan.m + 2; i += SS_THREADS) S.off[i] = plan.cov_off[i];
+    for (uint32_t i = threadIdx.x; i <= plan.m; i += SS_THREADS)
+        S.pack[i] = PAIRS ? plan.cov4[i] : (plan.cov_off[i + 1] > plan.cov_off[i] ? 0u : 0xFFFFFFFFu);
     for (uint32_t i = threadIdx.x; i < SS_WARPS * (SS_BMAX + 4); i += SS_THREADS) (&S.cnt[0][0])[i] = 0;
     if (threadIdx.x < 4) S.bits[SS_BITWORDS + threadIdx.x] = 0;
     __syncthreads();
@@ -139,7 +158,7 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
     uint32_t *my_cnt = S.cnt[warp];
     uint2 *work = S.work[warp];
     const uint32_t *bits = S.bits;
-    uint32_t *__restrict__ my_hits = hitlist + (size_t)chunk * chunk_rows;
+    uint32_t *__restrict__ my_hits = hitlist + (size_t)chunk * chunk_rows * (PAIRS ? plan.pair_depth : 1u);
     const uint32_t ulo = (uint32_t)plan.lo, bsh = plan.bit_shift;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t nhits = 0, wcount = 0;                             // uniform across the warp
@@ -191,7 +210,7 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
         const uint32_t tot = __dp4a(totp, 0x01010101u, 0u);        // sum of the four group totals, <= 512
         if (wcount + tot > (uint32_t)SS_WORK) {                    // no room for this tile: resolve first
             __syncwarp();
-            nhits = ss_resolve(L, S.off, work, wcount, my_cnt, my_hits, nhits, lane, lt);
+            nhits = ss_resolve<PAIRS>(L, S.pack, plan.pair_depth, work, wcount, my_cnt, my_hits, nhits, lane, lt);
             wcount = 0;
             __syncwarp();
         }
@@ -210,7 +229,7 @@ ss_classify_kernel(const int32_t *__restrict__ val, uint32_t n, SharedScanPlan p
     }
     if (wcount) {
         __syncwarp();
-        nhits = ss_resolve(L, S.off, work, wcount, my_cnt, my_hits, nhits, lane, lt);
+        nhits = ss_resolve<PAIRS>(L, S.pack, plan.pair_depth, work, wcount, my_cnt, my_hits, nhits, lane, lt);
     }
     if (lane == 0) chunk_hits[chunk] = nhits;
     __syncwarp();
@@ -390,6 +409,99 @@ ss_emit_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict_
     if (avail) ss_drain(queue, head, avail, lane, run, row_begin, outs, capacity);
 }
 
+// Emit over pair lists (SharedScanPlan::pair_depth > 0), sorted tile by tile (r01zg).  Every
+// entry names its query, so no interval lookup and no pair queue.  r01zf tried the plain form
+// first -- rank 32 entries with the ballots, store each at its query's cursor -- and ncu put a
+// third of the stall samples on that store: 32 lanes, ~28 different queries, one LSU pass per
+// touched sector, ten million of them, with every shared-memory access of the SM queueing
+// behind (90-97 us).  Here a warp first sorts 1024 entries of its chunk's list by query inside
+// shared memory (count, prefix over the queries, stable ranked scatter: the ballots rank, the
+// scattered writes hit shared-memory banks instead of L2 sectors) and then writes the tile out
+// in sorted order: 32 consecutive lanes cover three or four queries' runs, i.e. a handful of
+// sectors per store instead of twenty-eight (72 us; the queue emit over interval lists: 105).
+constexpr int SO_TILE = 1024;
+constexpr int SO_QPAD = ((SS_QMAX + 31) / 32) * 32;          // 160
+
+__global__ void __launch_bounds__(SS_THREADS)
+ss_emit_sorted_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict__ chunk_hits,
+                      uint32_t q_count, uint32_t chunk_rows, uint32_t list_rows, uint32_t num_chunks,
+                      const uint32_t *__restrict__ offsets /* [q][num_chunks] */,
+                      int32_t *const *__restrict__ outs, int64_t capacity) {
+    __shared__ uint32_t s_tile[SS_WARPS][SO_TILE];
+    __shared__ uint32_t s_run[SS_WARPS][SO_QPAD];            // next free slot of every query's list
+    __shared__ uint16_t s_toff[SS_WARPS][SO_QPAD];           // first tile slot of every query (< 1024)
+    __shared__ uint32_t s_cur[SS_WARPS][SO_QPAD];            // counts, then scatter cursors
+    __shared__ int32_t *s_out[SS_QMAX];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t q = threadIdx.x; q < q_count; q += SS_THREADS) s_out[q] = outs[q];
+    __syncthreads();
+    const uint32_t chunk = blockIdx.x * SS_WARPS + warp;
+    if (chunk >= num_chunks) return;
+    const uint32_t nh = chunk_hits[chunk];
+    if (nh == 0) return;
+    uint32_t *tile = s_tile[warp], *run = s_run[warp], *cur = s_cur[warp];
+    uint16_t *toff = s_toff[warp];
+    for (uint32_t q = lane; q < SO_QPAD; q += kWarp)
+        run[q] = q < q_count ? offsets[(size_t)q * num_chunks + chunk] : 0u;
+    const uint32_t row_begin = chunk * chunk_rows;
+    const uint32_t *__restrict__ list = hitlist + (size_t)chunk * list_rows;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t q_pad = ((q_count + kWarp - 1) / kWarp) * kWarp;
+    for (uint32_t t0 = 0; t0 < nh; t0 += SO_TILE) {
+        const uint32_t tn = min((uint32_t)SO_TILE, nh - t0);
+        for (uint32_t q = lane; q < q_pad; q += kWarp) cur[q] = 0;
+        __syncwarp();
+        // (a) entries per query
+        for (uint32_t i = lane; i < tn; i += kWarp) atomicAdd(&cur[list[t0 + i] >> 23], 1u);
+        __syncwarp();
+        // (b) exclusive prefix over the queries -> first tile slot; the counts become cursors
+        uint32_t carry = 0;
+        for (uint32_t q0 = 0; q0 < q_pad; q0 += kWarp) {
+            const uint32_t c = cur[q0 + lane];
+            const uint32_t incl = warp_incl_scan(c, lane) + carry;
+            toff[q0 + lane] = (uint16_t)(incl - c);
+            cur[q0 + lane] = incl - c;
+            carry = __shfl_sync(kFull, incl, 31);
+        }
+        __syncwarp();
+        // (c) stable scatter into the tile: batches in list order, lanes of one query ranked in
+        //     lane order behind that query's cursor
+        uint32_t nxt = lane < tn ? list[t0 + lane] : 0u;
+        for (uint32_t i0 = 0; i0 < tn; i0 += kWarp) {
+            const uint32_t x = nxt;
+            const bool live = i0 + lane < tn;
+            if (i0 + kWarp + lane < tn) nxt = list[t0 + i0 + kWarp + lane];
+            const uint32_t q = live ? x >> 23 : 0u;
+            uint32_t peers = __ballot_sync(kFull, live);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (q >> b) & 1u;
+                const uint32_t vote = __ballot_sync(kFull, bit);
+                peers &= bit ? vote : ~vote;
+            }
+            uint32_t old = 0;
+            if (live) old = cur[q];
+            __syncwarp();
+            if (live) {
+                const uint32_t r = __popc(peers & lt);
+                if (r == 0) cur[q] = old + __popc(peers);
+                tile[old + r] = x;
+            }
+            __syncwarp();
+        }
+        // (d) write the tile out in sorted order
+        for (uint32_t sl = lane; sl < tn; sl += kWarp) {
+            const uint32_t x = tile[sl], q = x >> 23;
+            const int64_t o = (int64_t)run[q] + (sl - toff[q]);
+            if (o < capacity) s_out[q][o] = (int32_t)(row_begin + (x & 0x7FFFFFu));
+        }
+        __syncwarp();
+        // (e) advance the lists: cursor - first slot = entries of this tile
+        for (uint32_t q = lane; q < q_pad; q += kWarp) run[q] += cur[q] - toff[q];
+        __syncwarp();
+    }
+}
+
 // r01v-y, tried and dropped: a lane-independent emit (every lane owns a contiguous slice of the
 // chunk's hit list, counts per query into its own cell of a [query][lane] matrix in shared
 // memory, prefixes over the lanes, second walk writes at base[q] + prefix++).  It needs 35 M warp
@@ -417,11 +529,16 @@ int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan 
                            uint32_t *counts, int64_t *totals, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(ss_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsShared));
+        cudaFuncSetAttribute(ss_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsShared));
+        cudaFuncSetAttribute(ss_classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsShared));
         attr_set = true;
     }
-    ss_classify_kernel<<<g.grid, SS_THREADS, sizeof(SsShared), s>>>(val, n, plan, g.chunk_rows, g.num_chunks,
-                                                                    hitlist, chunk_hits, counts);
+    if (plan.pair_depth)
+        ss_classify_kernel<true><<<g.grid, SS_THREADS, sizeof(SsShared), s>>>(val, n, plan, g.chunk_rows, g.num_chunks,
+                                                                              hitlist, chunk_hits, counts);
+    else
+        ss_classify_kernel<false><<<g.grid, SS_THREADS, sizeof(SsShared), s>>>(val, n, plan, g.chunk_rows, g.num_chunks,
+                                                                               hitlist, chunk_hits, counts);
     ss_offsets_kernel<<<plan.q_count, 1024, 0, s>>>(counts, g.num_chunks, totals);
     return 2;
 }
@@ -429,8 +546,13 @@ int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan 
 int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
                        const SharedScanPlan &plan, const SharedScanGeom &g, const uint32_t *offsets,
                        int32_t *const *outs, int64_t capacity, cudaStream_t s) {
-    ss_emit_kernel<<<g.grid, SS_THREADS, 0, s>>>(hitlist, chunk_hits, plan, g.chunk_rows,
-                                                 g.num_chunks, offsets, outs, capacity);
+    if (plan.pair_depth)
+        ss_emit_sorted_kernel<<<g.grid, SS_THREADS, 0, s>>>(hitlist, chunk_hits, plan.q_count, g.chunk_rows,
+                                                            g.chunk_rows * plan.pair_depth, g.num_chunks, offsets,
+                                                            outs, capacity);
+    else
+        ss_emit_kernel<<<g.grid, SS_THREADS, 0, s>>>(hitlist, chunk_hits, plan, g.chunk_rows,
+                                                     g.num_chunks, offsets, outs, capacity);
     return 1;
 }
 

@@ -17,6 +17,18 @@ def eng():
     e.close()
 
 
+@pytest.fixture(autouse=True, params=["pair lists", "interval lists"])
+def list_form(request, monkeypatch):
+    """Both hit-list forms of the batched scan (shared_scan.cu): batches at most four queries
+    deep take pair lists unless ADB_SS_INTERVAL_LISTS is set; deeper ones always take interval
+    lists."""
+    if request.param == "interval lists":
+        monkeypatch.setenv("ADB_SS_INTERVAL_LISTS", "1")
+    else:
+        monkeypatch.delenv("ADB_SS_INTERVAL_LISTS", raising=False)
+    return request.param
+
+
 def check(eng, port, data, lows, highs, ref=None):
     col = eng.upload(data)
     got = eng.shared_select(col, data.size, lows, highs)
@@ -54,6 +66,21 @@ def test_random_batches(eng, port, ref, rng, n, q):
         lows[2], highs[2] = 50, 10        # inverted -> empty
         lows[3], highs[3] = lows[0], highs[0]   # duplicate query
     check(eng, port, data, lows, highs, ref if n >= 30000 else None)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5])
+def test_cover_depths(eng, port, rng, depth):
+    """Batches exactly `depth` queries deep: staggered ranges, each overlapping its depth - 1
+    successors (1 = disjoint); 4 is the deepest batch that takes pair lists.  More than one
+    1024-entry tile per chunk (dense hits), ties on the bounds, duplicates of a query."""
+    n, q = 300_000, 60
+    data = rng.integers(0, 6000, n).astype(np.int32)
+    lows = (np.arange(q) * 100).astype(np.int32)
+    highs = (lows + 100 * depth).astype(np.int32)
+    check(eng, port, data, lows, highs)
+    if depth >= 2:                                           # the same depth out of identical queries
+        lows2 = np.repeat(lows[::depth], depth)[:q].astype(np.int32)
+        check(eng, port, data, lows2, (lows2 + 100).astype(np.int32))
 
 
 def test_negative_and_extreme_values(eng, port, rng):
