@@ -39,11 +39,11 @@ struct Engine {
     int64_t idx_pending_n = -1;         // >= 0 between adb_select_index_count and _emit
     adb::SelectArgs sel_pending{};      // valid between adb_select_*_count and adb_select_emit
     bool sel_ready = false;
-    uint64_t sel_generation = 0;
+    uint64_t sel_generation = 0;        // bumped by every select_prepare (adb_select_generation)
     // small results travel to the host through a mapped pinned mailbox (read_back)
     unsigned long long *mbox = nullptr;  // kMboxWords payload words, then the flag word
     unsigned long long *mbox_dev = nullptr;
-    unsigned long long mbox_seq = 0;        // bumped by every select_prepare (adb_select_generation)
+    unsigned long long mbox_seq = 0;
     int64_t *scratch_count = nullptr;   // device int64 for callers that pass no d_count
     // batched shared scan state (count phase -> emit phase)
     unsigned char *ss_plan_mem = nullptr;   // bounds | cov_off | cov_q
@@ -659,6 +659,7 @@ adb_status adb_select_emit(const int32_t *d_pos_in, int32_t base_pos, int32_t *d
     NEED_UP();
     if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit: no pending adb_select_count");
     g.sel_ready = false;
+    ++g.sel_generation;                             // the pending count is consumed
     adb::SelectArgs a = g.sel_pending;
     if (a.n == 0) return ADB_OK;
     if (!d_pos_out) return fail(ADB_ERR_INVALID, "adb_select_emit: NULL output");
@@ -680,6 +681,7 @@ adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_
     if (!d_agg || (g.sel_pending.n > 0 && (!d_fetch_col || !d_pos_out || !d_val_out)))
         return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: NULL device pointer");
     g.sel_ready = false;
+    ++g.sel_generation;                             // the pending count is consumed
     adb::SelectArgs a = g.sel_pending;
     int64_t *d_count = a.d_count;                   // written by the count phase
     a.base_pos = 0; a.out = d_pos_out;

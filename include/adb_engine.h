@@ -140,9 +140,9 @@ ADB_API adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t
                                              int32_t *d_val_out, adb_agg *d_agg,
                                              adb_agg *h_agg);
 /* Serial number of the select whose bitmap sits in the engine's scratch: it changes whenever
- * any select (of any form) starts.  A caller that defers adb_select_emit compares it with
- * the value it read right after its adb_select_count to learn whether the count is still
- * pending. */
+ * any select (of any form) starts and whenever a pending count is consumed by an emit.  A
+ * caller that defers adb_select_emit compares it with the value it read right after its
+ * adb_select_count to learn whether the count is still pending. */
 ADB_API uint64_t adb_select_generation(void);
 /* Combine `k` device partials (one per shard) into d_out[0] on the device. */
 ADB_API adb_status adb_agg_combine(const adb_agg *d_parts, int32_t k, adb_agg *d_out, adb_agg *h_out);

@@ -369,6 +369,17 @@ def test_deferred_select_survives_a_foreign_engine_select(api, cpu, rng):
     assert np.array_equal(api.tuples(s), epos) and np.array_equal(api.tuples(f), evals)
     for r in (s, f, a):
         api.drop(r)
+    # ... or consumes the pending count outright (an emit without a count of its own)
+    s = api.select_column(col1, lo, hi)
+    f = api.fetch_column(col4, s)
+    stolen = eng.alloc_i32(epos.size)
+    eng._ck(eng.lib.adb_select_emit(None, 0, stolen.i32()))
+    assert np.array_equal(stolen.to_host(epos.size), epos)
+    a = api.unary("max", f)
+    assert int(api.tuples(a)[0]) == cpu.max(evals)
+    assert np.array_equal(api.tuples(s), epos) and np.array_equal(api.tuples(f), evals)
+    for r in (s, f, a):
+        api.drop(r)
     # the engine-level deferred form agrees with the fused chain
     d1, d4 = eng.upload(c1), eng.upload(c4)
     p_, v_, h_, agg = eng.select_fetch_agg_deferred(d1, d4, n, lo, hi)
