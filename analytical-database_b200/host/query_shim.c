@@ -811,7 +811,7 @@ static int aggregate_result(const Result *r, adb_agg *h) {
     /* aggregate of the pending fetch of the pending select: the chain's fused second kernel
      * writes both handles and the aggregate in one pass */
     if (P.active && r && P.fetch_payload && r->payload == P.fetch_payload && r->num_tuples == P.h &&
-        adb_select_generation() == P.generation) {
+        r->data_type == INT && adb_select_generation() == P.generation) {
         P.active = 0;
         if (adb_select_emit_fetch_agg(P.d_fetch_col, P.sel_d, P.fetch_d, S.d_agg, h) != ADB_OK) {
             set_err("adb_select_emit_fetch_agg: %s", adb_last_error());
@@ -835,6 +835,9 @@ static Result *scalar_result(DataType t, const void *value, size_t width, Status
         set_err("out of host memory");
         return op_fail(st, what);
     }
+    /* malloc handed out an address we still hold a device result for: the plumbing freed that
+     * payload without telling us (no release hook, no interposer) -- it is dead, drop it */
+    adb_host_payload_freed(p);
     memcpy(p, value, width);
     r->num_tuples = 1;
     r->data_type = t;

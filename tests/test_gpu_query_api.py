@@ -229,6 +229,27 @@ def test_payload_registry_reclaims_on_address_reuse(api):
         query_api._libc.free(s.contents.payload)                       # plumbing-style free, no hook
         query_api._libc.free(C.cast(s, C.c_void_p))
     assert api.lib.adb_host_live_device_results() <= base + 3
+    # the same with a deferred select + fetch pending behind the freed payloads: the next chain
+    # is still answered correctly, whatever addresses malloc recycles
+    data = np.arange(50_000, dtype=np.int32)
+    for i in range(20):
+        lo, hi = 100 + i, 5000 + 3 * i
+        s = api.select_column(col, lo, hi)
+        f = api.fetch_column(col, s)
+        if i % 2:
+            a = api.sum_result(f)
+            assert int(api.tuples(a)[0]) == int(data[lo:hi].sum())
+            api.drop(a)
+        for h in (f, s) if i % 3 else (s, f):
+            query_api._libc.free(h.contents.payload)
+            query_api._libc.free(C.cast(h, C.c_void_p))
+    s = api.select_column(col, 7, 9000)
+    f = api.fetch_column(col, s)
+    a = api.unary("max", f)
+    assert int(api.tuples(a)[0]) == 8999 and np.array_equal(api.tuples(s), np.arange(7, 9000))
+    for h in (s, f, a):
+        api.drop(h)
+    assert api.lib.adb_host_live_device_results() <= base + 6
 
 
 # ---- deferred select: every order in which the plumbing can touch the
