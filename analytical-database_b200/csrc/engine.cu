@@ -996,22 +996,15 @@ constexpr size_t kSsCov4Off = kSsQOff + 2 * 2 * ((ADB_MAX_BATCH + 7) / 8) * 8;  
 constexpr size_t kSsPlanBytes = kSsCov4Off + 4 * (2 * ADB_MAX_BATCH + 8);
 constexpr size_t kSsMaxChunks = 8192;
 
-adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
-                                   const int32_t *highs, int32_t q_count, int64_t *h_counts) {
-    NEED_UP();
-    g.ss_ready = false;
-    if (adb_status s = check_len(n, "adb_shared_select_count")) return s;
-    if (q_count < 1 || q_count > ADB_MAX_BATCH)
-        return fail(ADB_ERR_INVALID, "adb_shared_select_count: q_count %d outside [1, %d] (server.c:366-371 chunks "
-                    "batches to 150)", q_count, ADB_MAX_BATCH);
-    if (!lows || !highs || (n > 0 && !d_col)) return fail(ADB_ERR_INVALID, "adb_shared_select_count: NULL pointer");
-    if (!g.ss_plan_mem) {
-        CU(cudaMalloc(&g.ss_plan_mem, kSsPlanBytes));
-        CU(cudaMalloc(&g.ss_counts, sizeof(uint32_t) * ADB_MAX_BATCH * kSsMaxChunks));
-        CU(cudaMalloc(&g.ss_totals, sizeof(int64_t) * ADB_MAX_BATCH));
-        CU(cudaMalloc(&g.ss_outs, sizeof(int32_t *) * ADB_MAX_BATCH));
-        CU(cudaMalloc(&g.ss_chunk_hits, sizeof(uint32_t) * kSsMaxChunks));
-    }
+// The host half of the batched scan: everything the kernels look up, in one packed buffer
+// (bounds | cov_off | cov_q | lut | bits | q_first/q_last | cov4).  Pure host code: also
+// reachable without a device through adb_shared_select_plan (tests).
+struct SsHostPlan {
+    std::vector<unsigned char> bytes;
+    uint32_t m = 0, lut_shift = 0, bit_shift = 0, span = 0, deepest = 1;
+    int32_t lo = 0;
+};
+static void ss_build_plan(const int32_t *lows, const int32_t *highs, int32_t q_count, SsHostPlan *hp) {
     // ---- plan: elementary intervals and their covering queries ------------------------------
     int32_t bounds[2 * ADB_MAX_BATCH];
     uint32_t m = 0;
@@ -1031,12 +1024,11 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
     if (m == 0) off[1] = 0;
     uint32_t deepest = 1;                                   // most queries covering one value
     for (uint32_t k = 1; k < m; ++k) deepest = std::max<uint32_t>(deepest, (uint32_t)(off[k + 1] - off[k]));
-    // one packed upload: bounds | cov_off | cov_q.  The source is pageable, so the call returns
-    // once the bytes sit in the driver's staging memory: no synchronisation needed before the
-    // host vector goes out of scope.
+    // packed: bounds | cov_off | cov_q, then the lookup tables
     uint32_t lut_shift = 0, bit_shift = 0, span = 0;
     {
-        std::vector<unsigned char> plan(kSsPlanBytes, 0);
+        std::vector<unsigned char> &plan = hp->bytes;
+        plan.assign(kSsPlanBytes, 0);
         if (m) memcpy(plan.data(), bounds, m * sizeof(int32_t));
         memcpy(plan.data() + kSsBoundsBytes, off.data(), off.size() * sizeof(uint16_t));
         if (!cov.empty()) memcpy(plan.data() + kSsBoundsBytes + 640, cov.data(), cov.size());
@@ -1117,14 +1109,39 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
                         cov4[k] = (cov4[k] & ~(0xFFu << sh)) | (q << sh);
                     }
         }
-        CU(cudaMemcpyAsync(g.ss_plan_mem, plan.data(), plan.size(), cudaMemcpyHostToDevice, g.stream));
     }
+    hp->m = m; hp->lut_shift = lut_shift; hp->bit_shift = bit_shift; hp->span = span;
+    hp->deepest = deepest; hp->lo = m ? bounds[0] : 0;
+}
+
+adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
+                                   const int32_t *highs, int32_t q_count, int64_t *h_counts) {
+    NEED_UP();
+    g.ss_ready = false;
+    if (adb_status s = check_len(n, "adb_shared_select_count")) return s;
+    if (q_count < 1 || q_count > ADB_MAX_BATCH)
+        return fail(ADB_ERR_INVALID, "adb_shared_select_count: q_count %d outside [1, %d] (server.c:366-371 chunks "
+                    "batches to 150)", q_count, ADB_MAX_BATCH);
+    if (!lows || !highs || (n > 0 && !d_col)) return fail(ADB_ERR_INVALID, "adb_shared_select_count: NULL pointer");
+    if (!g.ss_plan_mem) {
+        CU(cudaMalloc(&g.ss_plan_mem, kSsPlanBytes));
+        CU(cudaMalloc(&g.ss_counts, sizeof(uint32_t) * ADB_MAX_BATCH * kSsMaxChunks));
+        CU(cudaMalloc(&g.ss_totals, sizeof(int64_t) * ADB_MAX_BATCH));
+        CU(cudaMalloc(&g.ss_outs, sizeof(int32_t *) * ADB_MAX_BATCH));
+        CU(cudaMalloc(&g.ss_chunk_hits, sizeof(uint32_t) * kSsMaxChunks));
+    }
+    SsHostPlan hp;
+    ss_build_plan(lows, highs, q_count, &hp);
+    // one packed upload.  The source is pageable, so the call returns once the bytes sit in the
+    // driver's staging memory: no synchronisation needed before the host vector goes out of scope.
+    CU(cudaMemcpyAsync(g.ss_plan_mem, hp.bytes.data(), hp.bytes.size(), cudaMemcpyHostToDevice, g.stream));
+    const uint32_t m = hp.m, lut_shift = hp.lut_shift, bit_shift = hp.bit_shift, span = hp.span, deepest = hp.deepest;
     g.ss_plan = adb::SharedScanPlan{reinterpret_cast<const int32_t *>(g.ss_plan_mem),
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsBoundsBytes),
                                     g.ss_plan_mem + kSsBoundsBytes + 640, m, (uint32_t)q_count,
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsLutOff),
                                     reinterpret_cast<const uint32_t *>(g.ss_plan_mem + kSsBitsOff),
-                                    lut_shift, bit_shift, m ? bounds[0] : 0, span,
+                                    lut_shift, bit_shift, hp.lo, span,
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff),
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsQOff) + ((ADB_MAX_BATCH + 7) / 8) * 8,
                                     0u, reinterpret_cast<const uint32_t *>(g.ss_plan_mem + kSsCov4Off)};
@@ -1169,6 +1186,26 @@ adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity) 
     const int k_ = adb::launch_shared_emit(g.ss_hits, g.ss_chunk_hits, g.ss_plan, g.ss_geom, g.ss_counts,
                                            g.ss_outs, capacity, g.stream);
     return after_launch("shared_emit", k_);
+}
+
+// Host-only: the plan adb_shared_select_count would upload for this batch (no device needed).
+adb_status adb_shared_select_plan(const int32_t *lows, const int32_t *highs, int32_t q_count,
+                                  unsigned char *plan_out, size_t capacity, uint32_t *meta_out) {
+    if (q_count < 1 || q_count > ADB_MAX_BATCH || !lows || !highs || !meta_out)
+        return fail(ADB_ERR_INVALID, "adb_shared_select_plan: bad arguments");
+    SsHostPlan hp;
+    ss_build_plan(lows, highs, q_count, &hp);
+    const uint32_t meta[16] = {(uint32_t)hp.bytes.size(), hp.m, hp.lut_shift, hp.bit_shift, hp.span,
+                               (uint32_t)hp.lo, hp.deepest, (uint32_t)kSsBoundsBytes,
+                               (uint32_t)(kSsBoundsBytes + 640), (uint32_t)kSsLutOff, (uint32_t)kSsBitsOff,
+                               (uint32_t)kSsQOff, (uint32_t)kSsCov4Off, adb::kSsLut, adb::kSsBits,
+                               (uint32_t)(((ADB_MAX_BATCH + 7) / 8) * 8)};
+    memcpy(meta_out, meta, sizeof meta);
+    if (plan_out) {
+        if (capacity < hp.bytes.size()) return fail(ADB_ERR_INVALID, "adb_shared_select_plan: buffer too small");
+        memcpy(plan_out, hp.bytes.data(), hp.bytes.size());
+    }
+    return ADB_OK;
 }
 
 adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *lows,

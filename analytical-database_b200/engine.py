@@ -151,6 +151,7 @@ class Engine:
         "adb_shared_select_count": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I64P]),
         "adb_shared_select_emit": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int64]),
         "adb_shared_select": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I32P, C.c_int64, _I64P]),
+        "adb_shared_select_plan": (C.c_int32, [_I32P, _I32P, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]),
         "adb_index_create": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
         "adb_index_destroy": (C.c_int32, [C.c_void_p]),
         "adb_select_index": (C.c_int32, [C.c_void_p, C.c_int32, _I32P, _I32P, _I32P, _I64P, _I64P]),

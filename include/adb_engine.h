@@ -258,6 +258,20 @@ ADB_API adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int3
                                      const int32_t *highs, int32_t q_count, int32_t *d_pos_out,
                                      int64_t stride, int64_t *h_counts);
 
+/* Host-only (no device, no adb_init): the lookup tables adb_shared_select_count would upload
+ * for this batch, for inspection and tests.  plan_out may be NULL to size the buffer.
+ * meta_out[16] = {bytes, m (distinct bounds), lut_shift, bit_shift, span, lo (bounds[0]),
+ * deepest cover, then the byte offsets of cov_off, cov_q, lut, bits, q_first/q_last, cov4,
+ * then the lut and bitmap sizes and the q_first -> q_last stride}.  Layout: bounds[m] int32
+ * ascending; interval id k = number of bounds <= v (0 and m lie outside every query);
+ * cov_off[m+2] uint16 + cov_q[] uint8: the queries covering interval k, ascending; lut /
+ * bits: value -> interval tables over d = v - lo (shared_scan.cu); q_first/q_last uint16:
+ * the interval ids query q covers; cov4[m+1] uint32: for batches at most four queries deep,
+ * interval k's covering queries one byte per colour (0xFF = none), overlapping queries in
+ * different colours. */
+ADB_API adb_status adb_shared_select_plan(const int32_t *lows, const int32_t *highs, int32_t q_count,
+                                          unsigned char *plan_out, size_t capacity, uint32_t *meta_out);
+
 /* ---- sorted index and B+-tree range select -- replace select_column_sorted_index +
  * binary_search, src/query.c:143-198 (and the stub src/btree.c, whose only defined
  * behaviour is "same as sorted", query.c:205-217).
