@@ -472,13 +472,16 @@ static Result *new_dev_result(int32_t *d_ptr, size_t tuples) {
             return NULL;
         }
     }
-    lock();
     /* malloc returned an address we still hold a buffer for: that payload was freed by the
-     * plumbing without telling us -- reclaim its HBM now. */
+     * plumbing without telling us -- reclaim its HBM now.  No engine call is made with the
+     * registry lock held (with the free() interposer other threads' frees wait on it). */
+    if (P.active && (payload == P.sel_payload || payload == P.fetch_payload))
+        pending_payload_gone(payload);          /* may still need the dead handle's buffer */
+    int32_t *dead = NULL;
+    lock();
     DevResult *stale = registry_find(payload);
     if (stale) {
-        pending_payload_gone(payload);
-        adb_free(stale->d_ptr);
+        dead = stale->d_ptr;
         stale->d_ptr = d_ptr;
         stale->tuples = tuples;
     } else {
@@ -500,6 +503,7 @@ static Result *new_dev_result(int32_t *d_ptr, size_t tuples) {
         ++S.nlive;
     }
     unlock();
+    if (dead) adb_free(dead);
     r->num_tuples = tuples;
     r->data_type = INT;
     r->payload = payload;
