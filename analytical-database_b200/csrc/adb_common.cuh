@@ -337,6 +337,7 @@ struct SelectArgs {
     const int32_t *pos_in;    // paired positions (select_pairs) or nullptr
     const int64_t *d_n;       // optional device-side length
     uint32_t n;               // host-side length / upper bound (< 2^31)
+    bool stable_val;          // val is a base column: no kernel ever writes it (early first-tile request)
     Range range;
     int32_t base_pos;
     int32_t *out;
@@ -361,6 +362,13 @@ constexpr uint32_t kMaxSelectChunks = 1u << 16;
 
 int launch_fetch(const int32_t *col, const int32_t *pos, int64_t n_max, const int64_t *d_n,
                   int32_t base_pos, int32_t *out, int sm_count, cudaStream_t s);
+// a column row-range sharded over several contexts / devices: shard k holds rows
+// [k * shard_rows, (k + 1) * shard_rows); remote shards are peer-mapped
+struct ShardTable {
+    const int32_t *ptr[kMaxPeers];
+};
+int launch_fetch_sharded(const ShardTable &t, int n_shards, uint32_t shard_rows, const int32_t *pos,
+                         int64_t n_max, const int64_t *d_n, int32_t *out, int sm_count, cudaStream_t s);
 int launch_aggregate(const int32_t *v, int64_t n_max, const int64_t *d_n, adb_agg *out,
                       adb_agg *scratch, unsigned int *ticket, int sm_count, cudaStream_t s);
 int launch_agg_combine(const adb_agg *parts, int32_t k, adb_agg *out, cudaStream_t s);
@@ -370,6 +378,7 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
                   int32_t *out, bool subtract, int sm_count, cudaStream_t s);
 int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
                           uint32_t span, int sm_count, cudaStream_t s);
+int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s);
 constexpr int kAggMaxBlocks = 148 * 8;
 int launch_agg_combine_allreduce(const PeerExchange &px, cudaStream_t s);
 
@@ -423,7 +432,7 @@ int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan 
                            uint32_t *counts, int64_t *totals, cudaStream_t s);
 int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
                        const SharedScanPlan &plan, const SharedScanGeom &g, const uint32_t *offsets,
-                       int32_t *const *outs, int64_t capacity, cudaStream_t s);
+                       int32_t *const *outs, int64_t capacity, uint32_t base_pos, cudaStream_t s);
 
 // Stable radix partition passes + generic exclusive scan (radix.cu).
 struct RadixPass {
@@ -494,8 +503,12 @@ struct BTreeView {
 };
 int launch_btree_level(const int32_t *below, int64_t below_len, int32_t *level, int64_t level_len,
                        int sm_count, cudaStream_t s);
+// plain_range: `values` is one slice of a range-partitioned index -- the slice answers
+// positions[lb(low) .. lb(high)) and the caller applies the reference's low == high quirk to
+// the whole index (it depends on the total count and on the smallest key of all slices)
 int launch_index_bounds(const int32_t *values, int64_t n, const BTreeView *tree, const int32_t *lo,
-                        const int32_t *hi, int64_t *bounds, int64_t *d_count, cudaStream_t s);
+                        const int32_t *hi, bool plain_range, int64_t *bounds, int64_t *d_count,
+                        cudaStream_t s);
 int launch_index_emit(const int32_t *positions, int64_t n, const int64_t *bounds, int32_t *out,
                       int sm_count, cudaStream_t s);
 

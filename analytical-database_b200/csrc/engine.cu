@@ -22,6 +22,7 @@ thread_local std::string g_err;
 
 struct Engine {
     bool up = false;
+    int32_t ctx_index = 0;
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -56,6 +57,7 @@ struct Engine {
     adb::SharedScanPlan ss_plan{};
     adb::SharedScanGeom ss_geom{};
     bool ss_ready = false;
+    int32_t ss_base_pos = 0;            // added to every emitted row (shard base)
     // radix / join scratch
     uint32_t *rx_hist = nullptr, *rx_totals = nullptr, *rx_base = nullptr;
     size_t rx_hist_elems = 0;
@@ -127,7 +129,15 @@ struct Engine {
     int64_t *jx_total = nullptr;            // device: pairs this rank receives
     int64_t launches = 0;
     int32_t chain_mark_base = -1;       // adb_chain_marks(): slots for the next chain call
-} g;
+    bool peer_local = false;            // mailboxes mapped by peer access inside one process (no IPC handles)
+};
+
+// One context per GPU of the box (several may share a device: a 1-GPU box then runs the
+// multi-shard host path unchanged).  Every entry point works on the calling THREAD's current
+// context (adb_ctx_select); a context is only ever driven by one thread at a time.
+Engine g_ctx[ADB_MAX_CONTEXTS];
+thread_local int g_cur = 0;
+#define g (g_ctx[g_cur])
 
 
 adb_status fail(adb_status code, const char *fmt, ...) {
@@ -247,7 +257,7 @@ adb_status ensure_select_scratch(uint32_t n) {
 
 void jx_close() {
     for (int r = 0; r < g.peer_world; ++r)
-        if (r != g.peer_rank && g.jx_peer_host[r]) cudaIpcCloseMemHandle(g.jx_peer_host[r]);
+        if (r != g.peer_rank && g.jx_peer_host[r] && !g.peer_local) cudaIpcCloseMemHandle(g.jx_peer_host[r]);
     if (g.jx_recv) cudaFree(g.jx_recv);
     if (g.jx_peer_dev) cudaFree(g.jx_peer_dev);
     if (g.jx_status) cudaFree(g.jx_status);
@@ -266,7 +276,7 @@ void jx_close() {
 void peer_close() {
     jx_close();
     for (int r = 0; r < g.peer_world; ++r)
-        if (r != g.peer_rank && g.peer_boxes.box[r]) cudaIpcCloseMemHandle(g.peer_boxes.box[r]);
+        if (r != g.peer_rank && g.peer_boxes.box[r] && !g.peer_local) cudaIpcCloseMemHandle(g.peer_boxes.box[r]);
     if (g.peer_box) cudaFree(g.peer_box);
     if (g.peer_boxes_dev) cudaFree(g.peer_boxes_dev);
     g.peer_boxes_dev = nullptr;
@@ -277,6 +287,7 @@ void peer_close() {
     g.peer_rank = -1;
     g.peer_connected = false;
     g.peer_epoch = 0;
+    g.peer_local = false;
 }
 
 // ---- large host <-> device copies of pageable memory ----------------------------------------
@@ -321,11 +332,12 @@ adb_status staged_copy(void *d, void *h, size_t bytes, bool up) {
     const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
     const int lanes = g.stage_lanes;
     std::atomic<int> err{(int)cudaSuccess};
+    Engine &E = g;                                  // the helper threads have their own current context
     auto work = [&](int l) {
-        auto &L = g.stage[l];
-        cudaSetDevice(g.device);
+        auto &L = E.stage[l];
+        cudaSetDevice(E.device);
         auto ck = [&](cudaError_t e) { if (e != cudaSuccess) { int ok = (int)cudaSuccess; err.compare_exchange_strong(ok, (int)e); } };
-        ck(cudaStreamWaitEvent(L.st, g.stage_ready, 0));
+        ck(cudaStreamWaitEvent(L.st, E.stage_ready, 0));
         char *dp = static_cast<char *>(d), *hp = static_cast<char *>(h);
         if (up) {
             int b = 0;
@@ -375,6 +387,28 @@ const char *adb_last_error(void) { return g_err.c_str(); }
 const char *adb_version(void) { return "adb_b200 0.1 (sm_100a)"; }
 int adb_sm_count(void) { return g.sm_count; }
 int64_t adb_launch_count(void) { return g.launches; }
+int64_t adb_launch_count_all(void) {
+    int64_t t = 0;
+    for (const Engine &e : g_ctx) t += e.up ? e.launches : 0;
+    return t;
+}
+
+int32_t adb_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+int32_t adb_ctx_current(void) { return g_cur; }
+adb_status adb_ctx_select(int32_t ctx) {
+    if (ctx < 0 || ctx >= ADB_MAX_CONTEXTS) return fail(ADB_ERR_INVALID, "adb_ctx_select: context %d outside [0, %d)", ctx, ADB_MAX_CONTEXTS);
+    g_cur = ctx;
+    if (g.up) CU(cudaSetDevice(g.device));
+    return ADB_OK;
+}
+adb_status adb_ctx_init(int32_t ctx, int device_ordinal) {
+    if (adb_status s = adb_ctx_select(ctx)) return s;
+    return adb_init(device_ordinal);
+}
 
 adb_status adb_init(int device_ordinal) {
     if (g.up) return ADB_OK;
@@ -431,11 +465,24 @@ adb_status adb_init(int device_ordinal) {
     CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int)));
     CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int)));
     g.launches = 0;
+    g.ctx_index = g_cur;
     g.up = true;
     return ADB_OK;
 }
 
+static adb_status shutdown_current();
+// Shuts down every context of the process (the hook is called once, from shutdown_server()).
 adb_status adb_shutdown(void) {
+    const int keep = g_cur;
+    // first quiesce every stream: a context's kernels may still touch a peer's mailbox
+    for (int c = 0; c < ADB_MAX_CONTEXTS; ++c)
+        if (g_ctx[c].up) { cudaSetDevice(g_ctx[c].device); cudaStreamSynchronize(g_ctx[c].stream); }
+    for (int c = 0; c < ADB_MAX_CONTEXTS; ++c) { g_cur = c; shutdown_current(); }
+    g_cur = keep;
+    return ADB_OK;
+}
+
+static adb_status shutdown_current() {
     if (!g.up) return ADB_OK;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
@@ -596,9 +643,13 @@ static adb_status finish_count(int64_t *d_count, int64_t *h_count) {
     return read_back(h_count, d_count, sizeof(int64_t));
 }
 
+// stable_val: d_val is a base column -- no operator ever writes it, so the predicate pass may
+// request its first tile while the previous kernel on the stream is still draining (any other
+// input may be that kernel's output and must wait for it: ADVICE r1, select_scan.cu).
 static adb_status select_prepare(const char *what, const int32_t *d_val, const int32_t *d_pos,
                                  int64_t n_max, const int64_t *d_n, const int32_t *lo,
-                                 const int32_t *hi, int64_t *d_count, adb::SelectArgs *a) {
+                                 const int32_t *hi, int64_t *d_count, adb::SelectArgs *a,
+                                 bool stable_val = false) {
     NEED_UP();
     g.sel_ready = false;
     ++g.sel_generation;
@@ -606,6 +657,7 @@ static adb_status select_prepare(const char *what, const int32_t *d_val, const i
     if (n_max > 0 && !d_val) return fail(ADB_ERR_INVALID, "%s: NULL device pointer", what);
     *a = adb::SelectArgs{};
     a->val = d_val; a->pos_in = d_pos; a->d_n = d_n; a->n = (uint32_t)n_max;
+    a->stable_val = stable_val;
     fold_range(lo, hi, &a->range);
     a->d_count = d_count ? d_count : g.scratch_count;
     if (adb_status s = ensure_select_scratch(a->n)) return s;
@@ -621,7 +673,7 @@ adb_status adb_select_scan(const int32_t *d_col, int64_t n, const int32_t *lo, c
         NEED_UP();
         return fail(ADB_ERR_INVALID, "adb_select_scan: NULL device pointer");
     }
-    if (adb_status s = select_prepare("adb_select_scan", d_col, nullptr, n, nullptr, lo, hi, d_count, &a)) return s;
+    if (adb_status s = select_prepare("adb_select_scan", d_col, nullptr, n, nullptr, lo, hi, d_count, &a, true)) return s;
     a.base_pos = base_pos; a.out = d_pos_out;
     if (adb_status s = after_launch("select_scan", adb::launch_select(a, g.stream))) return s;
     return finish_count(d_count, h_count);
@@ -655,6 +707,21 @@ adb_status adb_select_count(const int32_t *d_val, int64_t n_max, const int64_t *
     return finish_count(a.d_count, h_count);
 }
 
+// Count phase over rows [base_pos, base_pos + n) of a BASE column (shard): as adb_select_count,
+// plus the two things only a base column allows -- the early first-tile request (see
+// select_prepare) and a pending select that adb_select_emit_fetch_agg* can resolve, emitting
+// base_pos + row.
+adb_status adb_select_count_base(const int32_t *d_col, int64_t n, const int32_t *lo, const int32_t *hi,
+                                 int32_t base_pos, int64_t *d_count, int64_t *h_count) {
+    adb::SelectArgs a;
+    if (adb_status s = select_prepare("adb_select_count_base", d_col, nullptr, n, nullptr, lo, hi, d_count, &a, true)) return s;
+    if (adb_status s = after_launch("select_count", adb::launch_select_mask(a, true, g.stream))) return s;
+    a.base_pos = base_pos;
+    g.sel_pending = a;
+    g.sel_ready = true;
+    return finish_count(a.d_count, h_count);
+}
+
 adb_status adb_select_emit(const int32_t *d_pos_in, int32_t base_pos, int32_t *d_pos_out) {
     NEED_UP();
     if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit: no pending adb_select_count");
@@ -672,8 +739,8 @@ uint64_t adb_select_generation(void) { return g.sel_generation; }
 
 // Deferred emit of a select whose consumers turned out to be fetch + aggregate: the fused
 // second kernel of the chain, after the host has read the count.
-adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_out, int32_t *d_val_out,
-                                     adb_agg *d_agg, adb_agg *h_agg) {
+static adb_status emit_fetch_agg_impl(const int32_t *d_fetch_col, int32_t *d_pos_out, int32_t *d_val_out,
+                                      adb_agg *d_agg, adb_agg *h_agg, const adb::PeerExchange *px) {
     NEED_UP();
     if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: no pending adb_select_count");
     if (g.sel_pending.pos_in || g.sel_pending.d_n)
@@ -684,23 +751,50 @@ adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_
     ++g.sel_generation;                             // the pending count is consumed
     adb::SelectArgs a = g.sel_pending;
     int64_t *d_count = a.d_count;                   // written by the count phase
-    a.base_pos = 0; a.out = d_pos_out;
+    a.out = d_pos_out;                              // base_pos: what the count phase recorded
     a.d_count = g.scratch_count;                    // the expansion rewrites the same total
     a.fetch_col = d_fetch_col; a.val_out = d_val_out;
     a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
+    if (px) a.px = *px;
     const int f_ = adb::launch_select_expand_fetch_agg(a, g.stream);
     if (f_ > 0) {
         if (adb_status s = after_launch("select_emit_fetch_agg", f_)) return s;
     } else {
         // empty column (or a grid larger than the fold scratch): the three-operator form
         if (adb_status s = after_launch("select_emit_fetch_agg", adb::launch_select_expand(a, g.stream))) return s;
-        if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, a.n, d_count, 0, d_val_out)) return s;
+        if (adb_status s = adb_fetch(d_fetch_col, d_pos_out, a.n, d_count, a.base_pos, d_val_out)) return s;
         if (adb_status s = adb_aggregate(d_val_out, a.n, d_count, d_agg, nullptr)) return s;
+        if (px)
+            if (adb_status s = after_launch("chain exchange", adb::launch_agg_combine_allreduce(*px, g.stream))) return s;
     }
     if (h_agg) {
-        if (adb_status s = read_back(h_agg, d_agg, sizeof(adb_agg))) return s;
+        if (adb_status s = read_back(h_agg, px ? px->final_out : d_agg, sizeof(adb_agg))) return s;
+        if (px && h_agg->count < 0)
+            return fail(ADB_ERR_CUDA, "aggregate exchange: a peer did not arrive within 2 s (epoch %u)", px->epoch);
     }
     return ADB_OK;
+}
+
+adb_status adb_select_emit_fetch_agg(const int32_t *d_fetch_col, int32_t *d_pos_out, int32_t *d_val_out,
+                                     adb_agg *d_agg, adb_agg *h_agg) {
+    return emit_fetch_agg_impl(d_fetch_col, d_pos_out, d_val_out, d_agg, h_agg, nullptr);
+}
+
+// The deferred emit with the cross-context exchange riding in the same kernel: this context's
+// partial goes to d_part, the table-wide aggregate to d_out (and h_out) on every context.
+// Collective over the contexts / ranks of adb_peer_connect*.
+adb_status adb_select_emit_fetch_agg_exchange(const int32_t *d_fetch_col, int32_t *d_pos_out,
+                                              int32_t *d_val_out, adb_agg *d_part, adb_agg *d_out,
+                                              adb_agg *h_out) {
+    NEED_UP();
+    if (!g.peer_connected) return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg_exchange: adb_peer_connect first");
+    if (!d_part || !d_out) return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg_exchange: NULL device pointer");
+    const adb::PeerExchange px{g.peer_boxes_dev, g.peer_rank, g.peer_world, g.peer_epoch + 1, d_part, 1, d_out};
+    // the epoch advances as soon as the arguments are accepted: every context must take part
+    // in every exchange, so a context that fails below has desynchronised the group anyway
+    if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg_exchange: no pending adb_select_count_base");
+    ++g.peer_epoch;
+    return emit_fetch_agg_impl(d_fetch_col, d_pos_out, d_val_out, d_part, h_out, &px);
 }
 
 adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
@@ -711,6 +805,24 @@ adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
     if (!d_col || !d_pos || !d_val_out) return fail(ADB_ERR_INVALID, "adb_fetch: NULL device pointer");
     const int k_ = adb::launch_fetch(d_col, d_pos, n_max, d_n, base_pos, d_val_out, g.sm_count, g.stream);
     return after_launch("fetch", k_);
+}
+
+// fetch over a column that is row-range sharded across contexts: position p lives in shard
+// p / shard_rows at row p % shard_rows; remote shards are read over NVLink peer memory
+// (adb_peer_connect_local has enabled the access).
+adb_status adb_fetch_sharded(const int32_t *const *d_shards, int32_t n_shards, int64_t shard_rows,
+                             const int32_t *d_pos, int64_t n_max, const int64_t *d_n, int32_t *d_val_out) {
+    NEED_UP();
+    if (adb_status s = check_len(n_max, "adb_fetch_sharded")) return s;
+    if (n_shards < 1 || n_shards > ADB_MAX_PEERS || shard_rows < 1 || shard_rows >= ((int64_t)1 << 31) || !d_shards)
+        return fail(ADB_ERR_INVALID, "adb_fetch_sharded: %d shards of %lld rows", n_shards, (long long)shard_rows);
+    if (n_max == 0) return ADB_OK;
+    if (!d_pos || !d_val_out) return fail(ADB_ERR_INVALID, "adb_fetch_sharded: NULL device pointer");
+    adb::ShardTable t{};
+    for (int i = 0; i < n_shards; ++i) t.ptr[i] = d_shards[i];
+    const int k_ = adb::launch_fetch_sharded(t, n_shards, (uint32_t)shard_rows, d_pos, n_max, d_n, d_val_out,
+                                             g.sm_count, g.stream);
+    return after_launch("fetch_sharded", k_);
 }
 
 adb_status adb_aggregate(const int32_t *d_val, int64_t n_max, const int64_t *d_n,
@@ -860,6 +972,9 @@ adb_status adb_peer_exchange_pairs(int32_t side, const int32_t *d_val, const int
     const unsigned long long key_off = (unsigned long long)(2 * side) * g.jx_cap;
     const unsigned long long pay_off = (unsigned long long)(2 * side + 1) * g.jx_cap;
     int k_ = 0;
+    if (world == 1 && (unsigned long long)n > g.jx_cap)
+        return fail(ADB_ERR_NOMEM, "adb_peer_exchange_pairs: %lld pairs do not fit the %llu-pair receive region; "
+                    "reserve more with adb_peer_join_create", (long long)n, g.jx_cap);
     if (world == 1) {
         // no routing digit: every pair stays here (still through the flags: one code path)
         CU(cudaMemsetAsync(g.rx_totals, 0, sizeof(uint32_t) * 256, g.stream));
@@ -895,6 +1010,158 @@ adb_status adb_peer_exchange_pairs(int32_t side, const int32_t *d_val, const int
     *h_recv_count = total;
     *d_recv_val = g.jx_recv + key_off;
     *d_recv_pos = g.jx_recv + pay_off;
+    return ADB_OK;
+}
+
+// ---- the same exchange group inside ONE process: contexts 0 .. world-1 are the ranks --------
+// Peer access (cudaDeviceEnablePeerAccess + access to the stream-ordered pools) instead of IPC
+// handles; contexts that share a device simply see each other's allocations.
+static adb_status enable_peer_access(int world) {
+    for (int i = 0; i < world; ++i) {
+        const int di = g_ctx[i].device;
+        CU(cudaSetDevice(di));
+        for (int j = 0; j < world; ++j) {
+            const int dj = g_ctx[j].device;
+            if (di == dj) continue;
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, di, dj));
+            if (!can) return fail(ADB_ERR_CUDA, "device %d cannot access device %d's memory (NVLink / PCIe peer access is required)", di, dj);
+            cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else CU(e);
+            // buffers of device dj's stream-ordered pool (columns, results) readable / writable from di
+            cudaMemPool_t pool;
+            CU(cudaDeviceGetDefaultMemPool(&pool, dj));
+            cudaMemAccessDesc desc{};
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = di;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            CU(cudaMemPoolSetAccess(pool, &desc, 1));
+        }
+    }
+    return ADB_OK;
+}
+
+adb_status adb_peer_connect_local(int32_t world) {
+    if (world < 1 || world > ADB_MAX_PEERS || world > ADB_MAX_CONTEXTS)
+        return fail(ADB_ERR_INVALID, "adb_peer_connect_local: world %d (max %d)", world, ADB_MAX_PEERS);
+    for (int r = 0; r < world; ++r)
+        if (!g_ctx[r].up) return fail(ADB_ERR_NOT_INITIALISED, "adb_peer_connect_local: context %d is not initialised", r);
+    const int keep = g_cur;
+    adb_status rc = enable_peer_access(world);
+    for (int r = 0; r < world && rc == ADB_OK; ++r) {
+        g_cur = r;
+        auto one = [&]() -> adb_status {
+            CU(cudaSetDevice(g.device));
+            CU(cudaStreamSynchronize(g.stream));
+            peer_close();
+            CU(cudaMalloc(&g.peer_box, adb::kPeerBoxBytes));
+            CU(cudaMemset(g.peer_box, 0, adb::kPeerBoxBytes));
+            CU(cudaDeviceSynchronize());
+            return ADB_OK;
+        };
+        rc = one();
+    }
+    for (int r = 0; r < world && rc == ADB_OK; ++r) {
+        g_cur = r;
+        auto one = [&]() -> adb_status {
+            CU(cudaSetDevice(g.device));
+            for (int q = 0; q < world; ++q) g.peer_boxes.box[q] = g_ctx[q].peer_box;
+            g.peer_world = world;
+            g.peer_rank = r;
+            g.peer_local = true;
+            CU(cudaMalloc(&g.peer_boxes_dev, sizeof(adb::PeerBoxes)));
+            CU(cudaMemcpy(g.peer_boxes_dev, &g.peer_boxes, sizeof(adb::PeerBoxes), cudaMemcpyHostToDevice));
+            g.peer_connected = true;
+            g.peer_epoch = 0;
+            return ADB_OK;
+        };
+        rc = one();
+    }
+    g_cur = keep;
+    if (g.up) cudaSetDevice(g.device);
+    return rc;
+}
+
+adb_status adb_peer_join_connect_local(int64_t cap_pairs) {
+    const int world = g.peer_world;
+    if (!g.peer_connected || !g.peer_local) return fail(ADB_ERR_INVALID, "adb_peer_join_connect_local: adb_peer_connect_local first");
+    if (cap_pairs < 1 || cap_pairs >= ((int64_t)1 << 31))
+        return fail(ADB_ERR_INVALID, "adb_peer_join_connect_local: capacity %lld outside [1, 2^31)", (long long)cap_pairs);
+    const unsigned long long cap = ((unsigned long long)cap_pairs + 63) & ~63ull;
+    const int keep = g_cur;
+    adb_status rc = ADB_OK;
+    for (int r = 0; r < world && rc == ADB_OK; ++r) {
+        g_cur = r;
+        auto one = [&]() -> adb_status {
+            CU(cudaSetDevice(g.device));
+            CU(cudaStreamSynchronize(g.stream));
+            jx_close();
+            cudaError_t e = cudaMalloc(&g.jx_recv, cap * 4 * sizeof(int32_t));
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join receive buffer (%llu pairs x 4 regions): %s", cap, cudaGetErrorString(e)); }
+            CU(cudaMalloc(&g.jx_peer_dev, sizeof(uint32_t *) * ADB_MAX_PEERS));
+            CU(cudaMalloc(&g.jx_status, 4 * sizeof(uint32_t)));
+            CU(cudaMalloc(&g.jx_total, 2 * sizeof(int64_t)));
+            g.jx_cap = cap;
+            return ADB_OK;
+        };
+        rc = one();
+    }
+    for (int r = 0; r < world && rc == ADB_OK; ++r) {
+        g_cur = r;
+        auto one = [&]() -> adb_status {
+            CU(cudaSetDevice(g.device));
+            for (int q = 0; q < world; ++q) g.jx_peer_host[q] = reinterpret_cast<uint32_t *>(g_ctx[q].jx_recv);
+            CU(cudaMemcpy(g.jx_peer_dev, g.jx_peer_host, sizeof(uint32_t *) * ADB_MAX_PEERS, cudaMemcpyHostToDevice));
+            g.jx_connected = true;
+            g.jx_epoch = 0;
+            return ADB_OK;
+        };
+        rc = one();
+    }
+    g_cur = keep;
+    if (g.up) cudaSetDevice(g.device);
+    return rc;
+}
+
+// Copy between contexts (peer DMA when the devices differ), ordered on the CURRENT context's
+// stream after everything already enqueued on the source context's stream.
+adb_status adb_copy_from_ctx(void *d_dst, int32_t src_ctx, const void *d_src, size_t bytes) {
+    NEED_UP();
+    if (src_ctx < 0 || src_ctx >= ADB_MAX_CONTEXTS || !g_ctx[src_ctx].up)
+        return fail(ADB_ERR_INVALID, "adb_copy_from_ctx: context %d is not initialised", src_ctx);
+    if (bytes == 0) return ADB_OK;
+    if (!d_dst || !d_src) return fail(ADB_ERR_INVALID, "adb_copy_from_ctx: NULL pointer");
+    Engine &src = g_ctx[src_ctx];
+    if (&src != &g) {
+        // the source bytes are produced on the source context's stream
+        cudaEvent_t ev;
+        CU(cudaSetDevice(src.device));
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, src.stream));
+        CU(cudaSetDevice(g.device));
+        CU(cudaStreamWaitEvent(g.stream, ev, 0));
+        CU(cudaEventDestroy(ev));                  // released once the wait has consumed it
+    }
+    if (src.device == g.device) CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g.stream));
+    else CU(cudaMemcpyPeerAsync(d_dst, g.device, d_src, src.device, bytes, g.stream));
+    return ADB_OK;
+}
+
+// The current context's stream waits for everything enqueued so far on `other_ctx`'s stream.
+adb_status adb_ctx_wait(int32_t other_ctx) {
+    NEED_UP();
+    if (other_ctx < 0 || other_ctx >= ADB_MAX_CONTEXTS || !g_ctx[other_ctx].up)
+        return fail(ADB_ERR_INVALID, "adb_ctx_wait: context %d is not initialised", other_ctx);
+    Engine &o = g_ctx[other_ctx];
+    if (&o == &g) return ADB_OK;
+    cudaEvent_t ev;
+    CU(cudaSetDevice(o.device));
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, o.stream));
+    CU(cudaSetDevice(g.device));
+    CU(cudaStreamWaitEvent(g.stream, ev, 0));
+    CU(cudaEventDestroy(ev));
     return ADB_OK;
 }
 
@@ -939,7 +1206,7 @@ static adb_status chain_impl(const int32_t *d_sel_col, const int32_t *d_fetch_co
         NEED_UP();
         return fail(ADB_ERR_INVALID, "adb_chain_select_fetch_agg: NULL device pointer");
     }
-    if (adb_status s = select_prepare("adb_chain_select_fetch_agg", d_sel_col, nullptr, n, nullptr, lo, hi, d_count, &a)) return s;
+    if (adb_status s = select_prepare("adb_chain_select_fetch_agg", d_sel_col, nullptr, n, nullptr, lo, hi, d_count, &a, true)) return s;
     a.base_pos = 0; a.out = d_pos_out;
     a.fetch_col = d_fetch_col; a.val_out = d_val_out;
     a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
@@ -1131,8 +1398,23 @@ static void ss_build_plan(const int32_t *lows, const int32_t *highs, int32_t q_c
     hp->deepest = deepest; hp->lo = m ? bounds[0] : 0;
 }
 
+static adb_status shared_select_count_impl(const int32_t *d_col, int64_t n, const int32_t *lows,
+                                           const int32_t *highs, int32_t q_count, int64_t *h_counts);
 adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
                                    const int32_t *highs, int32_t q_count, int64_t *h_counts) {
+    NEED_UP();
+    g.ss_base_pos = 0;
+    return shared_select_count_impl(d_col, n, lows, highs, q_count, h_counts);
+}
+// over rows [base_pos, base_pos + n) of a column (shard): the emit phase writes base_pos + row
+adb_status adb_shared_select_count_base(const int32_t *d_col, int64_t n, int32_t base_pos, const int32_t *lows,
+                                        const int32_t *highs, int32_t q_count, int64_t *h_counts) {
+    NEED_UP();
+    g.ss_base_pos = base_pos;
+    return shared_select_count_impl(d_col, n, lows, highs, q_count, h_counts);
+}
+static adb_status shared_select_count_impl(const int32_t *d_col, int64_t n, const int32_t *lows,
+                                           const int32_t *highs, int32_t q_count, int64_t *h_counts) {
     NEED_UP();
     g.ss_ready = false;
     if (adb_status s = check_len(n, "adb_shared_select_count")) return s;
@@ -1201,7 +1483,7 @@ adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity) 
     CU(cudaMemcpyAsync(g.ss_outs, d_out_ptrs, sizeof(int32_t *) * g.ss_plan.q_count,
                        cudaMemcpyHostToDevice, g.stream));      // pageable source: staged before return
     const int k_ = adb::launch_shared_emit(g.ss_hits, g.ss_chunk_hits, g.ss_plan, g.ss_geom, g.ss_counts,
-                                           g.ss_outs, capacity, g.stream);
+                                           g.ss_outs, capacity, (uint32_t)g.ss_base_pos, g.stream);
     return after_launch("shared_emit", k_);
 }
 
@@ -1642,6 +1924,7 @@ struct adb_index {
     int64_t n;
     int32_t *tree_mem;
     adb::BTreeView tree;
+    bool slice = false;
 };
 
 adb_status adb_index_create(const int32_t *d_values, const int32_t *d_positions, int64_t n,
@@ -1650,7 +1933,7 @@ adb_status adb_index_create(const int32_t *d_values, const int32_t *d_positions,
     if (adb_status s = check_len(n, "adb_index_create")) return s;
     if (!out || (n > 0 && (!d_values || !d_positions)))
         return fail(ADB_ERR_INVALID, "adb_index_create: NULL pointer");
-    adb_index *ix = new adb_index{d_values, d_positions, n, nullptr, adb::BTreeView{}};
+    adb_index *ix = new adb_index{d_values, d_positions, n, nullptr, adb::BTreeView{}, false};
     if (with_btree && n > 32) {
         int64_t lens[adb::kBTreeMaxDepth], total = 0;
         int depth = 0;
@@ -1684,6 +1967,16 @@ adb_status adb_index_create(const int32_t *d_values, const int32_t *d_positions,
     return ADB_OK;
 }
 
+// `ix` is one slice of an index that is range-partitioned (by index order) over several
+// contexts: it answers positions[lb(low) .. lb(high)) of its slice, and the caller applies the
+// reference's low == high quirk (query.c:181-188) to the whole index -- it depends on the total
+// count and on the smallest key of all slices.
+adb_status adb_index_set_slice(adb_index *ix, int32_t is_slice) {
+    if (!ix) return fail(ADB_ERR_INVALID, "adb_index_set_slice: NULL index");
+    ix->slice = is_slice != 0;
+    return ADB_OK;
+}
+
 adb_status adb_index_destroy(adb_index *ix) {
     NEED_UP();
     if (!ix) return ADB_OK;
@@ -1701,7 +1994,7 @@ adb_status adb_select_index_count(const adb_index *ix, int32_t use_btree, const 
     int64_t *dc = d_count ? d_count : g.scratch_count;
     const int k_ = adb::launch_index_bounds(ix->values, ix->n,
                                             use_btree && ix->tree.depth > 0 ? &ix->tree : nullptr,
-                                            lo, hi, g.idx_bounds, dc, g.stream);
+                                            lo, hi, ix->slice, g.idx_bounds, dc, g.stream);
     if (adb_status s = after_launch("index_bounds", k_)) return s;
     g.idx_pending_n = ix->n;
     return finish_count(dc, h_count);
@@ -1727,6 +2020,16 @@ adb_status adb_select_index(const adb_index *ix, int32_t use_btree, const int32_
     if (adb_status s = adb_select_index_count(ix, use_btree, lo, hi, d_count, nullptr)) return s;
     if (adb_status s = adb_select_index_emit(ix, d_pos_out)) return s;
     return finish_count(d_count, h_count);
+}
+
+// ColumnIndex.positions are size_t on the host (src/include/cs165_api.h:65-68) and truncated to
+// int when emitted (src/query.c:187): upload the 8-byte array as it is and narrow it here.
+adb_status adb_narrow_u64_to_i32(const void *d_src_u64, int64_t n, int32_t *d_dst) {
+    NEED_UP();
+    if (n < 0 || (n > 0 && (!d_src_u64 || !d_dst))) return fail(ADB_ERR_INVALID, "adb_narrow_u64_to_i32: bad arguments");
+    if (n == 0) return ADB_OK;
+    const int k_ = adb::launch_narrow_u64(static_cast<const unsigned long long *>(d_src_u64), n, d_dst, g.sm_count, g.stream);
+    return after_launch("narrow_u64", k_);
 }
 
 adb_status adb_synth_uniform(int32_t *d_out, int64_t n, uint64_t seed, uint64_t first_row,

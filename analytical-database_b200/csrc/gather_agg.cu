@@ -55,6 +55,34 @@ fetch_kernel(const int32_t *__restrict__ col, const int32_t *__restrict__ pos, i
     }
 }
 
+// ---- fetch over a sharded column: out[i] = shard[pos[i] / shard_rows][pos[i] % shard_rows] --------
+// The shard table travels as a kernel parameter and is copied to shared memory once per CTA (a
+// dynamically indexed parameter array would be spilled to every thread's local memory).  Remote
+// shards are read straight over NVLink (peer loads bypass the local L2).
+__global__ void __launch_bounds__(STREAM_THREADS)
+fetch_sharded_kernel(const ShardTable t, int n_shards, uint32_t shard_rows, const int32_t *__restrict__ pos,
+                     int64_t n_max, const int64_t *__restrict__ d_n, int32_t *__restrict__ out) {
+    __shared__ const int32_t *s_ptr[kMaxPeers];
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < kMaxPeers; ++k) s_ptr[k] = t.ptr[k];
+    __syncthreads();
+    const int64_t n = resolve_n(n_max, d_n);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto one = [&](int32_t p) {
+        const uint32_t k = (uint32_t)p / shard_rows;
+        return ld_gather(s_ptr[k < (uint32_t)n_shards ? k : 0] + ((uint32_t)p - k * shard_rows));
+    };
+    for (; i + 3 * stride < n; i += 4 * stride) {          // four independent gathers in flight
+        const int32_t p0 = ld_stream(pos + i), p1 = ld_stream(pos + i + stride);
+        const int32_t p2 = ld_stream(pos + i + 2 * stride), p3 = ld_stream(pos + i + 3 * stride);
+        const int32_t v0 = one(p0), v1 = one(p1), v2 = one(p2), v3 = one(p3);
+        out[i] = v0; out[i + stride] = v1; out[i + 2 * stride] = v2; out[i + 3 * stride] = v3;
+    }
+    for (; i < n; i += stride) out[i] = one(ld_stream(pos + i));
+}
+
 // ---- aggregate: {sum (int64), min, max, count} in one pass --------------------------------
 __global__ void __launch_bounds__(STREAM_THREADS)
 aggregate_kernel(const int32_t *__restrict__ v, int64_t n_max, const int64_t *__restrict__ d_n,
@@ -167,6 +195,14 @@ synth_uniform_kernel(int32_t *__restrict__ out, int64_t n, uint64_t seed, uint64
     }
 }
 
+// ---- size_t positions -> int32 (index upload) ----------------------------------------------------
+__global__ void __launch_bounds__(STREAM_THREADS)
+narrow_u64_kernel(const unsigned long long *__restrict__ src, int64_t n, int32_t *__restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = (int32_t)src[i];
+}
+
 // ---- launchers ------------------------------------------------------------------------------
 static int stream_grid(int64_t work_items, int sm_count, int per_sm) {
     const int64_t want = (work_items + STREAM_THREADS - 1) / STREAM_THREADS;
@@ -179,6 +215,14 @@ int launch_fetch(const int32_t *col, const int32_t *pos, int64_t n_max, const in
     if (n_max <= 0) return 0;
     fetch_kernel<<<stream_grid(n_max / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(
         col, pos, n_max, d_n, base_pos, out);
+    return 1;
+}
+
+int launch_fetch_sharded(const ShardTable &t, int n_shards, uint32_t shard_rows, const int32_t *pos,
+                         int64_t n_max, const int64_t *d_n, int32_t *out, int sm_count, cudaStream_t s) {
+    if (n_max <= 0) return 0;
+    fetch_sharded_kernel<<<stream_grid(n_max / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(
+        t, n_shards, shard_rows, pos, n_max, d_n, out);
     return 1;
 }
 
@@ -203,6 +247,12 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
         ewise_kernel<true><<<grid, STREAM_THREADS, 0, s>>>(a, b, n_max, d_n, out);
     else
         ewise_kernel<false><<<grid, STREAM_THREADS, 0, s>>>(a, b, n_max, d_n, out);
+    return 1;
+}
+
+int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s) {
+    if (n <= 0) return 0;
+    narrow_u64_kernel<<<stream_grid(n / 2 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(src, n, dst);
     return 1;
 }
 

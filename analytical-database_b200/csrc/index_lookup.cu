@@ -73,6 +73,7 @@ __device__ int64_t lb_btree(const int32_t *__restrict__ leaves, int64_t n, const
 struct IndexQuery {
     int32_t low, high;
     int32_t has_low, has_high;
+    int32_t plain_range;                     // a slice of a range-partitioned index: no quirk here
 };
 
 // One warp resolves the query and publishes {first, count}; *d_count mirrors count.
@@ -92,7 +93,8 @@ __global__ void index_bounds_kernel(const int32_t *__restrict__ values, int64_t 
     }
     if (lane != 0) return;
     int64_t count = lbh > lbl ? lbh - lbl : 0;
-    const bool defined = n > 0 && q.has_low && q.has_high && q.low >= values[0] && q.high >= values[0];
+    const bool defined = !q.plain_range && n > 0 && q.has_low && q.has_high && q.low >= values[0] &&
+                         q.high >= values[0];
     if (defined) {
         if (q.low > q.high) count = 0;
         else if (lbh < n && values[lbh] == q.high && count == 0) count = 1;   // query.c:181-188
@@ -113,8 +115,9 @@ index_emit_kernel(const int32_t *__restrict__ positions, const int64_t *__restri
 }
 
 int launch_index_bounds(const int32_t *values, int64_t n, const BTreeView *tree, const int32_t *lo,
-                        const int32_t *hi, int64_t *bounds, int64_t *d_count, cudaStream_t s) {
-    IndexQuery q{lo ? *lo : 0, hi ? *hi : 0, lo != nullptr, hi != nullptr};
+                        const int32_t *hi, bool plain_range, int64_t *bounds, int64_t *d_count,
+                        cudaStream_t s) {
+    IndexQuery q{lo ? *lo : 0, hi ? *hi : 0, lo != nullptr, hi != nullptr, plain_range};
     BTreeView view{};
     if (tree) view = *tree;
     index_bounds_kernel<<<1, kWarp, 0, s>>>(values, n, view, tree != nullptr && view.depth > 0, q,

@@ -90,11 +90,14 @@ __device__ __forceinline__ void store_mask_words(uint32_t nib, uint32_t lane,
 __global__ void __launch_bounds__(SEL_THREADS)
 mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, uint32_t n_host,
             Range rg, uint32_t chunk_rows, uint32_t num_chunks, uint32_t *__restrict__ mask,
-            uint32_t *__restrict__ counts) {
+            uint32_t *__restrict__ counts, bool stable_val) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t chunk = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
     pdl_launch_dependents();
     if (chunk >= num_chunks) return;
+    // Anything but a base column may be the output of the kernel this one was launched behind
+    // (select_result over a just-fetched vector): wait for it before the first load.
+    if (!stable_val) pdl_wait();
     uint32_t n = n_host;
     if (d_n) {
         pdl_wait();                                          // the length comes from an earlier kernel
@@ -116,8 +119,8 @@ mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, ui
     if (full) {
         int4 cur[SEL_VEC];
         load_tile(cur, val, row_begin, lane);
-        // the column itself is never written by the operators of a chain: its first tile is
-        // requested while the previous kernel (which still reads the bitmap) drains
+        // a base column is never written by an operator: its first tile is requested while the
+        // previous kernel (which still reads the bitmap) drains
         pdl_wait();
         for (uint32_t t = 0; t < full; ++t) {
             int4 nxt[SEL_VEC];
@@ -373,7 +376,7 @@ int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s) {
     }
     const SelectGeom g = select_geom(a.n, a.sm_count);
     launch_pdl(mask_kernel, g.grid, SEL_THREADS, 0, s, a.val, a.d_n, a.n, a.range, g.chunk_rows,
-               g.num_chunks, a.mask, a.counts);
+               g.num_chunks, a.mask, a.counts, a.stable_val);
     if (!with_total) return 1;
     count_total_kernel<<<1, 1024, 0, s>>>(a.counts, g.num_chunks, a.d_count);
     return 2;

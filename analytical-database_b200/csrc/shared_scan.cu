@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(SS_THREADS)
 ss_emit_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict__ chunk_hits,
                SharedScanPlan plan, uint32_t chunk_rows, uint32_t num_chunks,
                const uint32_t *__restrict__ offsets /* [q][num_chunks] */,
-               int32_t *const *__restrict__ outs, int64_t capacity) {
+               int32_t *const *__restrict__ outs, int64_t capacity, uint32_t base_pos) {
     __shared__ uint16_t s_off[SS_BMAX + 2];
     __shared__ uint32_t s_run[SS_WARPS][SS_QMAX];
     __shared__ uint32_t s_queue[SS_WARPS][SS_QUEUE];
@@ -327,7 +327,7 @@ ss_emit_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict_
     for (uint32_t q = lane; q < plan.q_count; q += kWarp)
         run[q] = offsets[(size_t)q * num_chunks + chunk];
     __syncwarp();
-    const uint32_t row_begin = chunk * chunk_rows;
+    const uint32_t row_begin = chunk * chunk_rows + base_pos;      // only ever added to emitted rows
     const uint32_t *__restrict__ list = hitlist + (size_t)chunk * chunk_rows;
     const uint8_t *__restrict__ cov_q = plan.cov_q;
     uint32_t head = 0, avail = 0;                          // queue state, uniform across the warp
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(SS_THREADS)
 ss_emit_sorted_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict__ chunk_hits,
                       uint32_t q_count, uint32_t chunk_rows, uint32_t list_rows, uint32_t num_chunks,
                       const uint32_t *__restrict__ offsets /* [q][num_chunks] */,
-                      int32_t *const *__restrict__ outs, int64_t capacity) {
+                      int32_t *const *__restrict__ outs, int64_t capacity, uint32_t base_pos) {
     __shared__ uint32_t s_tile[SS_WARPS][SO_TILE];
     __shared__ uint32_t s_run[SS_WARPS][SO_QPAD];            // next free slot of every query's list
     __shared__ uint16_t s_toff[SS_WARPS][SO_QPAD];           // first tile slot of every query (< 1024)
@@ -443,7 +443,7 @@ ss_emit_sorted_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__re
     uint16_t *toff = s_toff[warp];
     for (uint32_t q = lane; q < SO_QPAD; q += kWarp)
         run[q] = q < q_count ? offsets[(size_t)q * num_chunks + chunk] : 0u;
-    const uint32_t row_begin = chunk * chunk_rows;
+    const uint32_t row_begin = chunk * chunk_rows + base_pos;      // only ever added to emitted rows
     const uint32_t *__restrict__ list = hitlist + (size_t)chunk * list_rows;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t q_pad = ((q_count + kWarp - 1) / kWarp) * kWarp;
@@ -545,14 +545,14 @@ int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan 
 
 int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
                        const SharedScanPlan &plan, const SharedScanGeom &g, const uint32_t *offsets,
-                       int32_t *const *outs, int64_t capacity, cudaStream_t s) {
+                       int32_t *const *outs, int64_t capacity, uint32_t base_pos, cudaStream_t s) {
     if (plan.pair_depth)
         ss_emit_sorted_kernel<<<g.grid, SS_THREADS, 0, s>>>(hitlist, chunk_hits, plan.q_count, g.chunk_rows,
                                                             g.chunk_rows * plan.pair_depth, g.num_chunks, offsets,
-                                                            outs, capacity);
+                                                            outs, capacity, base_pos);
     else
         ss_emit_kernel<<<g.grid, SS_THREADS, 0, s>>>(hitlist, chunk_hits, plan, g.chunk_rows,
-                                                     g.num_chunks, offsets, outs, capacity);
+                                                     g.num_chunks, offsets, outs, capacity, base_pos);
     return 1;
 }
 

@@ -161,6 +161,23 @@ class Engine:
         "adb_join_emit": (C.c_int32, [_I32P, _I32P]),
         "adb_route_pairs": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int32, _I32P, _I32P, _I64P]),
         "adb_synth_uniform": (C.c_int32, [_I32P, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32]),
+        # several contexts in one process (one per GPU) + in-process peer exchange
+        "adb_device_count": (C.c_int32, []),
+        "adb_ctx_init": (C.c_int32, [C.c_int32, C.c_int]),
+        "adb_ctx_select": (C.c_int32, [C.c_int32]),
+        "adb_ctx_current": (C.c_int32, []),
+        "adb_ctx_wait": (C.c_int32, [C.c_int32]),
+        "adb_copy_from_ctx": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
+        "adb_launch_count_all": (C.c_int64, []),
+        "adb_peer_connect_local": (C.c_int32, [C.c_int32]),
+        "adb_peer_join_connect_local": (C.c_int32, [C.c_int64]),
+        "adb_select_count_base": (C.c_int32, [_I32P, C.c_int64, _I32P, _I32P, C.c_int32, _I64P, _I64P]),
+        "adb_select_emit_fetch_agg_exchange": (C.c_int32, [_I32P, _I32P, _I32P, C.POINTER(_AggStruct),
+                                                           C.POINTER(_AggStruct), C.POINTER(_AggStruct)]),
+        "adb_fetch_sharded": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, _I32P, C.c_int64, _I64P, _I32P]),
+        "adb_shared_select_count_base": (C.c_int32, [_I32P, C.c_int64, C.c_int32, _I32P, _I32P, C.c_int32, _I64P]),
+        "adb_index_set_slice": (C.c_int32, [C.c_void_p, C.c_int32]),
+        "adb_narrow_u64_to_i32": (C.c_int32, [C.c_void_p, C.c_int64, _I32P]),
     }
 
     def __init__(self, device: int = 0):

@@ -7,6 +7,29 @@
  * engine cannot start, every operator sets ret_status->code = ERROR and returns NULL,
  * which the dispatcher turns into a "Failed ..." reply (src/server.c:171-174).
  *
+ * One process, G GPUs (adb_host_init_multi(G) or ADB_GPUS=G; G = 1 by default)
+ *   The reference server is one process serving one client (src/server.c:616-656), so the
+ *   multi-GPU path lives here, behind the unchanged operator API: one engine context per GPU
+ *   (adb_ctx_*), one host thread per context (the calling thread drives context 0), peer
+ *   access between all devices.
+ *   base columns    row-range sharded: shard g holds rows [g*S, (g+1)*S) of the column in the
+ *                   HBM of GPU g (S = rows per shard, the same for every column of a table, so
+ *                   the columns of a table are co-partitioned).
+ *   results         a position list / value vector is the concatenation, in shard order, of
+ *                   G device buffers; positions are GLOBAL row numbers, so the concatenation
+ *                   is exactly the reference's list.  A list produced by a scan select is
+ *                   "row-aligned" (shard g's entries name rows of shard g): fetch, the fused
+ *                   chain and select_result then run shard-local with no data movement.
+ *                   Any other list (index order, join output, host arrays) is fetched with
+ *                   peer loads over NVLink (adb_fetch_sharded).
+ *   aggregates      per-shard partial + one exchange step over peer memory, fused into the
+ *                   kernel that produces the partial (adb_select_emit_fetch_agg_exchange /
+ *                   adb_agg_combine_allreduce); the host reads context 0's copy.
+ *   indexes         range-partitioned BY INDEX ORDER: slice g holds entries [b_g, b_{g+1}) of
+ *                   the sorted (values, positions) arrays, equal keys never straddle a
+ *                   boundary.  Every slice answers the range lookup; the concatenation in
+ *                   slice order is the reference's value-ordered list, bit for bit.
+ *
  * Where things live
  *   base columns    Column.data stays the host mmap the catalog owns; the first operator
  *                   that touches a column uploads it to HBM (int32 array) and the copy is
@@ -20,7 +43,7 @@
  *                   plumbing may free() it (src/client_context.c:35,82) and may read
  *                   num_tuples ints from it (the dispatcher's no-op log loop,
  *                   src/server.c:177-181); a registry maps that address to the device
- *                   buffer.  The block's bytes are NOT the tuples unless ADB_SHIM_MIRROR=1
+ *                   buffers.  The block's bytes are NOT the tuples unless ADB_SHIM_MIRROR=1
  *                   (then every result is also copied back to the host).  Scalars
  *                   (sum / avg / min / max) are ordinary host values, as in the reference.
  *   reclaiming HBM  adb_host_result_release() (two-line patch), the free() interposer
@@ -47,24 +70,38 @@
 #include "adb_engine.h"
 #include "adb_query_api.h"
 
+#define MAXG ADB_MAX_PEERS
+
 /* ---- state ----------------------------------------------------------------------------- */
 typedef struct DevColumn {
     const Column *key;
     const int *host_data;
     size_t rows;
-    int32_t *d_data;
-    int adopted;                /* d_data belongs to the caller (adb_host_column_adopt) */
-    /* index */
+    size_t shard_rows;          /* S: shard g = rows [g*S, min(rows, (g+1)*S)) */
+    int32_t *d_data[MAXG];
+    int adopted;                /* d_data belongs to the caller (adb_host_column_adopt*) */
+    /* index: slice g = entries [ix_begin[g], ix_begin[g+1]) of the sorted arrays */
     const int *host_ix_values;
     size_t ix_rows;
-    int32_t *d_ix_values, *d_ix_positions;
-    adb_index *ix;
+    size_t ix_begin[MAXG + 1];
+    int32_t *d_ix_values[MAXG], *d_ix_positions[MAXG];
+    adb_index *ix[MAXG];
+    int ix_min;                 /* smallest key of the whole index */
 } DevColumn;
+
+/* several results carved out of one allocation per context (shared_select) */
+typedef struct Slab {
+    int32_t *base[MAXG];
+    long refs;
+} Slab;
 
 typedef struct DevResult {
     void *payload;              /* key: the host block handed out as Result.payload */
-    int32_t *d_ptr;
-    size_t tuples;
+    int32_t *d_ptr[MAXG];
+    size_t tuples[MAXG];
+    size_t total;
+    size_t aligned;             /* S > 0: shard g's entries are positions inside rows [g*S, (g+1)*S) */
+    Slab *slab;                 /* NULL: the buffers are this result's own */
 } DevResult;
 
 #define SLOT_EMPTY ((void *)0)
@@ -72,12 +109,14 @@ typedef struct DevResult {
 
 static struct {
     int up, failed, mirror, lazy;
+    int G;                      /* contexts = shards */
+    size_t shard_min_rows;
     DevColumn *cols;
     int ncols, capcols;
     DevResult *slots;           /* open addressing on payload address */
     size_t nslots, nused;       /* nused counts live + tombstones */
     volatile long nlive;
-    adb_agg *d_agg;
+    adb_agg *d_part[MAXG], *d_out[MAXG];
     pthread_mutex_t mu;
     int mu_ready;
 } S;
@@ -86,6 +125,7 @@ static __thread char t_err[384];
 
 const char *adb_host_last_error(void) { return t_err; }
 long adb_host_live_device_results(void) { return S.nlive; }
+int adb_host_gpus(void) { return S.up ? S.G : 0; }
 
 static void set_err(const char *fmt, ...) {
     va_list ap;
@@ -123,68 +163,218 @@ static void op_ok(Status *st) {
         st->error_message = NULL;
     }
 }
-#define CK(call)                                                  \
-    do {                                                          \
-        if ((call) != ADB_OK) {                                   \
-            set_err("%s: %s", #call, adb_last_error());           \
-            goto fail;                                            \
-        }                                                         \
+
+/* ---- one host thread per context ---------------------------------------------------------
+ * An operator is a function run once per shard: the calling thread runs shard 0 (it stays on
+ * context 0), worker g runs shard g on context g.  Workers spin for the next job for a while
+ * (operators of one query arrive microseconds apart), then sleep on a condition variable. */
+typedef void (*shard_fn)(int g, void *arg);
+typedef struct ShardErr {
+    char msg[MAXG][256];
+    int failed[MAXG];
+} ShardErr;
+
+static struct {
+    pthread_t th[MAXG];
+    int started;
+    volatile unsigned long seq;
+    shard_fn fn;
+    void *arg;
+    struct { volatile unsigned long v; char pad[56]; } done[MAXG];
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    volatile int sleepers, quit;
+    long spin_limit;
+} W;
+
+static inline void cpu_relax(void) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+
+static void *worker_main(void *p) {
+    const int g = (int)(intptr_t)p;
+    adb_ctx_select(g);
+    unsigned long seen = 0;
+    for (;;) {
+        long spins = 0;
+        unsigned long s;
+        while ((s = __atomic_load_n(&W.seq, __ATOMIC_ACQUIRE)) == seen && !W.quit) {
+            if (++spins > W.spin_limit) {
+                pthread_mutex_lock(&W.mu);
+                __atomic_add_fetch(&W.sleepers, 1, __ATOMIC_SEQ_CST);
+                while (__atomic_load_n(&W.seq, __ATOMIC_SEQ_CST) == seen && !W.quit)
+                    pthread_cond_wait(&W.cv, &W.mu);
+                __atomic_sub_fetch(&W.sleepers, 1, __ATOMIC_SEQ_CST);
+                pthread_mutex_unlock(&W.mu);
+                spins = 0;
+            } else {
+                cpu_relax();
+            }
+        }
+        if (W.quit) break;
+        seen = s;
+        W.fn(g, W.arg);
+        __atomic_store_n(&W.done[g].v, s, __ATOMIC_RELEASE);
+    }
+    return NULL;
+}
+
+static void run_shards(shard_fn fn, void *arg) {
+    if (S.G == 1) {
+        fn(0, arg);
+        return;
+    }
+    W.fn = fn;
+    W.arg = arg;
+    const unsigned long s = __atomic_add_fetch(&W.seq, 1, __ATOMIC_SEQ_CST);
+    if (__atomic_load_n(&W.sleepers, __ATOMIC_SEQ_CST) > 0) {
+        pthread_mutex_lock(&W.mu);
+        pthread_cond_broadcast(&W.cv);
+        pthread_mutex_unlock(&W.mu);
+    }
+    fn(0, arg);
+    for (int g = 1; g < S.G; ++g)
+        while (__atomic_load_n(&W.done[g].v, __ATOMIC_ACQUIRE) != s) cpu_relax();
+}
+
+static int workers_start(void) {
+    if (S.G == 1 || W.started) return 0;
+    pthread_mutex_init(&W.mu, NULL);
+    pthread_cond_init(&W.cv, NULL);
+    W.quit = 0;
+    W.seq = 0;
+    const char *sp = getenv("ADB_SHIM_SPIN");
+    W.spin_limit = sp ? atol(sp) : 200000;          /* ~ a millisecond or two of pause loops */
+    for (int g = 1; g < S.G; ++g) {
+        W.done[g].v = 0;
+        if (pthread_create(&W.th[g], NULL, worker_main, (void *)(intptr_t)g)) {
+            set_err("cannot start the host thread of GPU %d", g);
+            return -1;
+        }
+    }
+    W.started = 1;
+    return 0;
+}
+static void workers_stop(void) {
+    if (!W.started) return;
+    pthread_mutex_lock(&W.mu);
+    W.quit = 1;
+    pthread_cond_broadcast(&W.cv);
+    pthread_mutex_unlock(&W.mu);
+    for (int g = 1; g < S.G; ++g) pthread_join(W.th[g], NULL);
+    W.started = 0;
+}
+
+/* per-shard failure -> the caller's t_err (first failing shard) */
+static void shard_fail(ShardErr *e, int g, const char *what) {
+    e->failed[g] = 1;
+    snprintf(e->msg[g], sizeof e->msg[g], "%s (GPU %d): %s", what, g, adb_last_error());
+}
+static int shard_errs(const ShardErr *e) {
+    for (int g = 0; g < S.G; ++g)
+        if (e->failed[g]) {
+            set_err("%s", e->msg[g]);
+            return -1;
+        }
+    return 0;
+}
+#define SCK(call)                                   \
+    do {                                            \
+        if ((call) != ADB_OK) {                     \
+            shard_fail(&a->err, g, #call);          \
+            return;                                 \
+        }                                           \
     } while (0)
+
+/* Main-thread engine calls on another context (cheap bookkeeping: allocations, frees). */
+static void on_ctx(int g) {
+    if (S.G > 1) adb_ctx_select(g);
+}
+static void free_on(int g, void *d) {
+    if (!d) return;
+    on_ctx(g);
+    adb_free(d);
+    on_ctx(0);
+}
+
+/* rows of shard g of a list of `rows` rows cut every S rows */
+static size_t shard_len(size_t rows, size_t S_, int g) {
+    const size_t b = (size_t)g * S_;
+    if (b >= rows) return 0;
+    return rows - b < S_ ? rows - b : S_;
+}
 
 /* ---- deferred select -------------------------------------------------
  * select_column over an un-indexed column returns as soon as the hit count is known: the
- * predicate pass has left its bitmap in the engine's scratch, the position buffer is
- * allocated, its contents are not written yet.  If the next thing that happens to the handle
- * is fetch_column and then an aggregate of that fetch -- the s=select / f=fetch / a=sum(f)
- * pattern of src/server.c:137-290 -- the aggregate call resolves all three with the chain's
- * fused second kernel (positions + gather + sum/min/max in one pass over the bitmap).  Any
- * other use of either handle, any other select, a column invalidation or a release first
- * writes what is pending (flush_pending), so the handles are indistinguishable from eager
- * ones to the unchanged plumbing.  At most one select is pending at a time.
- * ADB_SHIM_EAGER=1 (or the mirror mode) turns the deferral off. */
+ * predicate pass has left its bitmap in the engine's scratch (one per context), the position
+ * buffers are allocated, their contents are not written yet.  If the next thing that happens
+ * to the handle is fetch_column and then an aggregate of that fetch -- the s=select / f=fetch /
+ * a=sum(f) pattern of src/server.c:137-290 -- the aggregate call resolves all three with the
+ * chain's fused second kernel (positions + gather + sum/min/max in one pass over the bitmap,
+ * and with G > 1 the cross-GPU exchange in the same kernel).  Any other use of either handle,
+ * any other select, a column invalidation or a release first writes what is pending
+ * (flush_pending), so the handles are indistinguishable from eager ones to the unchanged
+ * plumbing.  At most one select is pending at a time.  ADB_SHIM_EAGER=1 (or the mirror mode)
+ * turns the deferral off. */
 static struct {
     int active;
     const void *sel_payload;        /* registry key of the select handle */
-    int32_t *sel_d;                 /* its position buffer, h entries */
-    size_t h;
-    const int32_t *d_col;           /* what was scanned, to redo the count if another user of */
-    size_t rows;                    /* the engine overwrote the bitmap in the meantime        */
+    int32_t *sel_d[MAXG];           /* its position buffers, h[g] entries */
+    size_t h[MAXG];
+    const int32_t *d_col[MAXG];     /* what was scanned, to redo the count if another user of */
+    size_t rows[MAXG];              /* the engine overwrote the bitmap in the meantime        */
+    size_t shard_rows;
     int has_lo, has_hi, lo, hi;
-    uint64_t generation;            /* adb_select_generation() right after the count */
+    uint64_t generation[MAXG];      /* adb_select_generation() right after the count */
     const void *fetch_payload;      /* fetch_column of that select, values not written yet */
-    int32_t *fetch_d;
-    const int32_t *d_fetch_col;
+    int32_t *fetch_d[MAXG];
+    const int32_t *d_fetch_col[MAXG];
 } P;
 
-static int pending_recount(void) {
-    if (adb_select_generation() == P.generation) return 0;
+typedef struct FlushJob {
+    ShardErr err;
+} FlushJob;
+
+static int32_t shard_base(int g, size_t shard_rows) { return (int32_t)((size_t)g * shard_rows); }
+
+/* runs on context g: redo the predicate pass if the bitmap is gone */
+static int pending_recount_shard(int g, ShardErr *e) {
+    if (adb_select_generation() == P.generation[g]) return 0;
     int64_t h = -1;
-    if (adb_select_count(P.d_col, (int64_t)P.rows, NULL, P.has_lo ? &P.lo : NULL,
-                         P.has_hi ? &P.hi : NULL, NULL, &h) != ADB_OK) {
-        set_err("deferred select: %s", adb_last_error());
+    if (adb_select_count_base(P.d_col[g], (int64_t)P.rows[g], P.has_lo ? &P.lo : NULL,
+                              P.has_hi ? &P.hi : NULL, shard_base(g, P.shard_rows), NULL, &h) != ADB_OK) {
+        shard_fail(e, g, "deferred select");
         return -1;
     }
-    if ((size_t)h != P.h) {
-        set_err("deferred select: the column changed under a pending select (%zu hits, now %lld)",
-                P.h, (long long)h);
+    if ((size_t)h != P.h[g]) {
+        e->failed[g] = 1;
+        snprintf(e->msg[g], sizeof e->msg[g],
+                 "deferred select: the column changed under a pending select (%zu hits, now %lld)",
+                 P.h[g], (long long)h);
         return -1;
     }
     return 0;
+}
+
+static void flush_shard(int g, void *arg) {
+    FlushJob *a = arg;
+    if (pending_recount_shard(g, &a->err)) return;
+    if (P.fetch_payload)
+        SCK(adb_select_emit_fetch_agg(P.d_fetch_col[g], P.sel_d[g], P.fetch_d[g], S.d_part[g], NULL));
+    else
+        SCK(adb_select_emit(NULL, shard_base(g, P.shard_rows), P.sel_d[g]));
 }
 
 /* Write whatever is pending; afterwards every handle is an ordinary device result. */
 static int flush_pending(void) {
     if (!P.active) return 0;
     P.active = 0;
-    if (pending_recount()) return -1;
-    adb_status s = P.fetch_payload
-        ? adb_select_emit_fetch_agg(P.d_fetch_col, P.sel_d, P.fetch_d, S.d_agg, NULL)
-        : adb_select_emit(NULL, 0, P.sel_d);
-    if (s != ADB_OK) {
-        set_err("deferred select: %s", adb_last_error());
-        return -1;
-    }
-    return 0;
+    FlushJob job;
+    memset(&job, 0, sizeof job);
+    run_shards(flush_shard, &job);
+    return shard_errs(&job.err);
 }
 
 /* The plumbing is about to free (or has freed) this payload. */
@@ -192,7 +382,6 @@ static void pending_payload_gone(const void *payload) {
     if (!P.active) return;
     if (payload == P.fetch_payload) {           /* nobody can read those values any more */
         P.fetch_payload = NULL;
-        P.fetch_d = NULL;
     } else if (payload == P.sel_payload) {
         if (P.fetch_payload) flush_pending();   /* the fetch still needs the selected rows */
         else P.active = 0;
@@ -200,19 +389,42 @@ static void pending_payload_gone(const void *payload) {
 }
 
 /* ---- engine lifecycle ------------------------------------------------------------------ */
-int adb_host_init(int device) {
+static int host_init(int first_device, int gpus) {
     if (S.up) return 0;
-    if (adb_init(device) != ADB_OK) {
-        set_err("adb_init(%d): %s", device, adb_last_error());
+    if (gpus < 1 || gpus > MAXG) {
+        set_err("adb_host_init_multi: %d GPUs outside [1, %d]", gpus, MAXG);
+        return -1;
+    }
+    const int ndev = adb_device_count();
+    for (int g = 0; g < gpus; ++g) {
+        /* fewer devices than contexts: contexts share devices (a 1-GPU box runs the same path) */
+        const int dev = ndev > 0 ? (first_device + g) % ndev : first_device + g;
+        if (adb_ctx_init(g, dev) != ADB_OK) {
+            set_err("adb_init(device %d): %s", dev, adb_last_error());
+            S.failed = 1;
+            adb_ctx_select(0);
+            return -1;
+        }
+    }
+    adb_ctx_select(0);
+    if (gpus > 1 && adb_peer_connect_local(gpus) != ADB_OK) {
+        set_err("adb_peer_connect_local(%d): %s", gpus, adb_last_error());
         S.failed = 1;
         return -1;
     }
-    void *p = NULL;
-    if (adb_alloc(&p, sizeof(adb_agg)) != ADB_OK) {
-        set_err("adb_alloc: %s", adb_last_error());
-        return -1;
+    S.G = gpus;
+    for (int g = 0; g < gpus; ++g) {
+        void *p = NULL, *q = NULL;
+        on_ctx(g);
+        if (adb_alloc(&p, sizeof(adb_agg)) != ADB_OK || adb_alloc(&q, sizeof(adb_agg)) != ADB_OK) {
+            set_err("adb_alloc: %s", adb_last_error());
+            on_ctx(0);
+            return -1;
+        }
+        S.d_part[g] = p;
+        S.d_out[g] = q;
     }
-    S.d_agg = (adb_agg *)p;
+    on_ctx(0);
     const char *m = getenv("ADB_SHIM_MIRROR");
     S.mirror = m && m[0] && m[0] != '0';
     /* Result payloads are plain malloc blocks of 4 * num_tuples bytes that nobody writes
@@ -226,26 +438,81 @@ int adb_host_init(int device) {
     }
     const char *eager = getenv("ADB_SHIM_EAGER");
     S.lazy = !S.mirror && !(eager && eager[0] && eager[0] != '0');
+    const char *mn = getenv("ADB_SHARD_MIN_ROWS");
+    S.shard_min_rows = mn ? (size_t)atol(mn) : 32;
+    if (S.shard_min_rows < 1) S.shard_min_rows = 1;
+    if (workers_start()) return -1;
     S.up = 1;
     S.failed = 0;
     return 0;
 }
 
+int adb_host_init(int device) { return host_init(device, 1); }
+int adb_host_init_multi(int gpus) {
+    const char *d = getenv("ADB_DEVICE");
+    return host_init(d ? atoi(d) : 0, gpus);
+}
+
 static int ensure_up(void) {
     if (S.up) return 0;
     const char *d = getenv("ADB_DEVICE");
-    return adb_host_init(d ? atoi(d) : 0);
+    const char *n = getenv("ADB_GPUS");
+    return host_init(d ? atoi(d) : 0, n && atoi(n) > 0 ? atoi(n) : 1);
+}
+
+static void dev_index_drop(DevColumn *c) {
+    for (int g = 0; g < S.G; ++g) {
+        if (!c->ix[g] && !c->d_ix_values[g] && !c->d_ix_positions[g]) continue;
+        on_ctx(g);
+        if (c->ix[g]) adb_index_destroy(c->ix[g]);
+        if (c->d_ix_values[g]) adb_free(c->d_ix_values[g]);
+        if (c->d_ix_positions[g]) adb_free(c->d_ix_positions[g]);
+        c->ix[g] = NULL;
+        c->d_ix_values[g] = c->d_ix_positions[g] = NULL;
+    }
+    on_ctx(0);
+    c->host_ix_values = NULL;
+    c->ix_rows = 0;
+}
+
+/* kernels of any context may still be reading a buffer that is about to go back to its pool
+ * (peer gathers read other contexts' column shards) */
+static void sync_all(void) {
+    if (S.G == 1) return;
+    for (int g = 0; g < S.G; ++g) {
+        on_ctx(g);
+        adb_sync();
+    }
+    on_ctx(0);
 }
 
 static void dev_column_drop(DevColumn *c) {
-    if (P.active && c->d_data && (c->d_data == P.d_col || c->d_data == P.d_fetch_col)) flush_pending();
-    if (c->ix) adb_index_destroy(c->ix);
-    if (c->d_ix_values) adb_free(c->d_ix_values);
-    if (c->d_ix_positions) adb_free(c->d_ix_positions);
-    if (c->d_data && !c->adopted) adb_free(c->d_data);
+    if (c->d_data[0] || c->ix[0]) sync_all();
+    if (P.active)
+        for (int g = 0; g < S.G; ++g)
+            if (c->d_data[g] && (c->d_data[g] == P.d_col[g] || c->d_data[g] == P.d_fetch_col[g])) {
+                flush_pending();
+                break;
+            }
+    dev_index_drop(c);
+    if (!c->adopted)
+        for (int g = 0; g < S.G; ++g) free_on(g, c->d_data[g]);
     const Column *key = c->key;
     memset(c, 0, sizeof *c);
     c->key = key;
+}
+
+static void result_buffers_free(DevResult *r) {
+    if (r->slab) {
+        if (--r->slab->refs == 0) {
+            for (int g = 0; g < S.G; ++g) free_on(g, r->slab->base[g]);
+            free(r->slab);
+        }
+    } else {
+        for (int g = 0; g < S.G; ++g) free_on(g, r->d_ptr[g]);
+    }
+    memset(r->d_ptr, 0, sizeof r->d_ptr);
+    r->slab = NULL;
 }
 
 void adb_host_shutdown(void) {
@@ -254,7 +521,7 @@ void adb_host_shutdown(void) {
     P.active = 0;
     for (size_t i = 0; i < S.nslots; ++i)
         if (S.slots[i].payload != SLOT_EMPTY && S.slots[i].payload != SLOT_TOMB)
-            adb_free(S.slots[i].d_ptr);
+            result_buffers_free(&S.slots[i]);
     DevResult *old = S.slots;
     S.slots = NULL;
     S.nslots = S.nused = 0;
@@ -263,13 +530,18 @@ void adb_host_shutdown(void) {
     DevColumn *oldc = S.cols;
     S.cols = NULL;
     S.ncols = S.capcols = 0;
-    adb_free(S.d_agg);
-    S.d_agg = NULL;
+    for (int g = 0; g < S.G; ++g) {
+        free_on(g, S.d_part[g]);
+        free_on(g, S.d_out[g]);
+        S.d_part[g] = S.d_out[g] = NULL;
+    }
+    workers_stop();
     S.up = 0;
     unlock();
     free(old);
     free(oldc);
     adb_shutdown();
+    S.G = 0;
 }
 
 /* ---- base columns ----------------------------------------------------------------------- */
@@ -304,21 +576,48 @@ static DevColumn *dev_column_slot(Column *column) {
     return c;
 }
 
+/* rows per shard: an even split, rounded up to 32 rows so that every shard but the last is a
+ * whole number of bitmap words; never below ADB_SHARD_MIN_ROWS */
+static size_t shard_rows_for(size_t rows) {
+    size_t s = (rows + (size_t)S.G - 1) / (size_t)S.G;
+    if (s < S.shard_min_rows) s = S.shard_min_rows;
+    s = (s + 31) & ~(size_t)31;
+    return s ? s : 32;
+}
+
+typedef struct UploadJob {
+    ShardErr err;
+    DevColumn *c;
+    const int *host;
+} UploadJob;
+static void upload_shard(int g, void *arg) {
+    UploadJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t n = shard_len(c->rows, c->shard_rows, g);
+    void *p = NULL;
+    SCK(adb_alloc(&p, 4 * n));
+    c->d_data[g] = p;
+    if (n) SCK(adb_upload(p, a->host + (size_t)g * c->shard_rows, 4 * n));
+}
+
 static DevColumn *dev_column(Column *column) {
     DevColumn *c = dev_column_slot(column);
     if (!c) return NULL;
-    if (c->d_data && c->host_data == column->data && c->rows == column->row_count) return c;
+    if (c->d_data[0] && c->host_data == column->data && c->rows == column->row_count) return c;
     dev_column_drop(c);
-    void *p = NULL;
-    if (adb_alloc(&p, 4 * column->row_count) != ADB_OK ||
-        adb_upload(p, column->data, 4 * column->row_count) != ADB_OK) {
-        set_err("column upload: %s", adb_last_error());
-        if (p) adb_free(p);
+    c->rows = column->row_count;
+    c->shard_rows = shard_rows_for(c->rows);
+    UploadJob job;
+    memset(&job, 0, sizeof job);
+    job.c = c;
+    job.host = column->data;
+    run_shards(upload_shard, &job);
+    if (shard_errs(&job.err)) {
+        for (int g = 0; g < S.G; ++g) free_on(g, c->d_data[g]);
+        memset(c->d_data, 0, sizeof c->d_data);
         return NULL;
     }
-    c->d_data = p;
     c->host_data = column->data;
-    c->rows = column->row_count;
     return c;
 }
 
@@ -328,18 +627,37 @@ int adb_host_column_upload(Column *column) {
 }
 
 /* The column's rows are already in HBM (a GPU-side loader put them there: SURVEY.md 8f
- * rank 1).  The shim uses d_data as is until the column's data pointer or row_count
- * changes; the buffer stays the caller's. */
-int adb_host_column_adopt(Column *column, const void *d_data) {
+ * rank 1).  The shim uses the buffers as they are until the column's data pointer or
+ * row_count changes; they stay the caller's.  adb_host_column_adopt: one buffer on context 0
+ * (G = 1).  adb_host_column_adopt_shards: d_shards[g] holds rows [g*shard_rows, (g+1)*shard_rows)
+ * on context g; shard_rows must be a multiple of 32. */
+int adb_host_column_adopt_shards(Column *column, const void *const *d_shards, size_t shard_rows) {
     if (ensure_up()) return -1;
     DevColumn *c = dev_column_slot(column);
-    if (!c || !d_data) return -1;
+    if (!c || !d_shards || shard_rows == 0 || (shard_rows & 31) ||
+        shard_rows * (size_t)S.G < column->row_count) {
+        set_err("adb_host_column_adopt_shards: %d shards of %zu rows cannot hold %zu rows (shard_rows must be "
+                "a multiple of 32)", S.G, shard_rows, column ? column->row_count : 0);
+        return -1;
+    }
     dev_column_drop(c);
-    c->d_data = (int32_t *)d_data;
+    for (int g = 0; g < S.G; ++g) c->d_data[g] = (int32_t *)d_shards[g];
     c->adopted = 1;
     c->host_data = column->data;
     c->rows = column->row_count;
+    c->shard_rows = shard_rows;
     return 0;
+}
+int adb_host_column_adopt(Column *column, const void *d_data) {
+    if (ensure_up()) return -1;
+    if (S.G != 1 || !column) {
+        set_err("adb_host_column_adopt: one buffer per GPU is needed with %d GPUs (adb_host_column_adopt_shards)", S.G);
+        return -1;
+    }
+    const void *one[1] = {d_data};
+    if (!d_data) return -1;
+    size_t sr = (column->row_count + 31) & ~(size_t)31;
+    return adb_host_column_adopt_shards(column, one, sr ? sr : 32);
 }
 
 void adb_host_column_invalidate(Column *column) {
@@ -347,45 +665,82 @@ void adb_host_column_invalidate(Column *column) {
         if (S.cols[i].key == column) dev_column_drop(&S.cols[i]);
 }
 
-/* Upload the ColumnIndex the reference built (src/index.c:89-101,119-146).  Its positions
- * are size_t on the host and are truncated to int when emitted (src/query.c:187), so the
- * device copy is int32. */
+/* Upload the ColumnIndex the reference built (src/index.c:89-101,119-146), cut into G slices
+ * by index order.  Its positions are size_t on the host and are truncated to int when emitted
+ * (src/query.c:187), so the device copy is int32 (narrowed on the device). */
+typedef struct IndexJob {
+    ShardErr err;
+    DevColumn *c;
+    Column *column;
+} IndexJob;
+static void index_shard(int g, void *arg) {
+    IndexJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t b = c->ix_begin[g], n = c->ix_begin[g + 1] - b;
+    void *dv = NULL, *dp = NULL, *d64 = NULL;
+    SCK(adb_alloc(&dv, 4 * n));
+    c->d_ix_values[g] = dv;
+    SCK(adb_alloc(&dp, 4 * n));
+    c->d_ix_positions[g] = dp;
+    if (n) {
+        SCK(adb_upload(dv, a->column->index->values + b, 4 * n));
+        SCK(adb_alloc(&d64, 8 * n));
+        if (adb_upload(d64, a->column->index->positions + b, 8 * n) != ADB_OK ||
+            adb_narrow_u64_to_i32(d64, (int64_t)n, dp) != ADB_OK) {
+            shard_fail(&a->err, g, "index upload");
+            adb_free(d64);
+            return;
+        }
+        adb_free(d64);
+    }
+    SCK(adb_index_create(dv, dp, (int64_t)n, /*with_btree=*/!a->column->sorted, &c->ix[g]));
+    if (S.G > 1) SCK(adb_index_set_slice(c->ix[g], 1));
+}
+
 static int dev_index(DevColumn *c, Column *column) {
     if (!column->index || !column->index->values || !column->index->positions) {
         set_err("column '%s' is flagged clustered/has_index but carries no ColumnIndex", column->name);
         return -1;
     }
-    if (c->ix && c->host_ix_values == column->index->values && c->ix_rows == column->row_count) return 0;
-    if (c->ix) adb_index_destroy(c->ix);
-    if (c->d_ix_values) adb_free(c->d_ix_values);
-    if (c->d_ix_positions) adb_free(c->d_ix_positions);
-    c->ix = NULL;
-    c->d_ix_values = c->d_ix_positions = NULL;
+    if (c->ix[0] && c->host_ix_values == column->index->values && c->ix_rows == column->row_count) return 0;
+    dev_index_drop(c);
     const size_t n = column->row_count;
-    int32_t *pos32 = malloc(n ? 4 * n : 4);
-    if (!pos32) {
-        set_err("out of host memory");
+    const int *v = column->index->values;
+    /* slice boundaries: an even split by index order, moved forward to the end of a run of
+     * equal keys (a run inside one slice keeps every slice's lookup independent) */
+    const size_t per = (n + (size_t)S.G - 1) / (size_t)S.G;
+    c->ix_begin[0] = 0;
+    for (int g = 1; g <= S.G; ++g) {
+        size_t b = (size_t)g * per;
+        if (b >= n || g == S.G) {
+            b = n;
+        } else {
+            if (b < c->ix_begin[g - 1]) b = c->ix_begin[g - 1];
+            if (b > 0 && b < n && v[b] == v[b - 1]) {       /* upper bound of the run of v[b-1] */
+                size_t lo = b, hi = n;
+                const int key = v[b - 1];
+                while (lo < hi) {
+                    const size_t mid = lo + (hi - lo) / 2;
+                    if (v[mid] <= key) lo = mid + 1; else hi = mid;
+                }
+                b = lo;
+            }
+        }
+        c->ix_begin[g] = b;
+    }
+    c->ix_min = n ? v[0] : 0;
+    IndexJob job;
+    memset(&job, 0, sizeof job);
+    job.c = c;
+    job.column = column;
+    run_shards(index_shard, &job);
+    if (shard_errs(&job.err)) {
+        dev_index_drop(c);
         return -1;
     }
-    for (size_t i = 0; i < n; ++i) pos32[i] = (int32_t)column->index->positions[i];
-    void *dv = NULL, *dp = NULL;
-    int rc = -1;
-    if (adb_alloc(&dv, 4 * n) == ADB_OK && adb_alloc(&dp, 4 * n) == ADB_OK &&
-        adb_upload(dv, column->index->values, 4 * n) == ADB_OK &&
-        adb_upload(dp, pos32, 4 * n) == ADB_OK &&
-        adb_index_create(dv, dp, (int64_t)n, /*with_btree=*/!column->sorted, &c->ix) == ADB_OK) {
-        c->d_ix_values = dv;
-        c->d_ix_positions = dp;
-        c->host_ix_values = column->index->values;
-        c->ix_rows = n;
-        rc = 0;
-    } else {
-        set_err("index upload: %s", adb_last_error());
-        if (dv) adb_free(dv);
-        if (dp) adb_free(dp);
-    }
-    free(pos32);
-    return rc;
+    c->host_ix_values = column->index->values;
+    c->ix_rows = n;
+    return 0;
 }
 
 /* ---- device-resident results ------------------------------------------------------------- */
@@ -425,71 +780,104 @@ static int registry_grow(void) {
     return 0;
 }
 
-/* Detach the device buffer registered under `payload` (if any) and return it. */
-static int32_t *registry_take(const void *payload) {
-    int32_t *d = NULL;
+/* Detach the device buffers registered under `payload` (if any); returns 1 and fills *out. */
+static int registry_take(const void *payload, DevResult *out) {
+    int found = 0;
     lock();
     DevResult *r = registry_find(payload);
     if (r) {
-        d = r->d_ptr;
+        *out = *r;
+        memset(r, 0, sizeof *r);
         r->payload = SLOT_TOMB;
-        r->d_ptr = NULL;
         --S.nlive;
+        found = 1;
     }
     unlock();
-    return d;
+    return found;
 }
 
 void adb_host_payload_freed(void *payload) {
     if (S.nlive <= 0 || !payload) return;
     pending_payload_gone(payload);
-    int32_t *d = registry_take(payload);
-    if (d) adb_free(d);
+    DevResult dead;
+    if (registry_take(payload, &dead)) result_buffers_free(&dead);
 }
 
 void adb_host_result_release(Result *result) {
     if (result) adb_host_payload_freed(result->payload);
 }
 
-/* Wrap a device buffer of `tuples` int32 as a Result the plumbing can own. */
-static Result *new_dev_result(int32_t *d_ptr, size_t tuples) {
+/* What new_dev_result wraps: G device buffers (this call takes ownership). */
+typedef struct Shards {
+    int32_t *d[MAXG];
+    size_t n[MAXG];
+    size_t aligned;
+    Slab *slab;
+} Shards;
+
+static void shards_free(Shards *s) {
+    if (s->slab) return;                            /* the slab's owner frees it */
+    for (int g = 0; g < S.G; ++g) {
+        free_on(g, s->d[g]);
+        s->d[g] = NULL;
+    }
+}
+
+static int download_shards(void *dst, int32_t *const d[], const size_t n[]) {
+    size_t off = 0;
+    int rc = 0;
+    for (int g = 0; g < S.G; ++g) {
+        if (!n[g]) continue;
+        on_ctx(g);
+        if (adb_download((char *)dst + 4 * off, d[g], 4 * n[g]) != ADB_OK) {
+            set_err("adb_download: %s", adb_last_error());
+            rc = -1;
+            break;
+        }
+        off += n[g];
+    }
+    on_ctx(0);
+    return rc;
+}
+
+/* Wrap G device buffers as a Result the plumbing can own. */
+static Result *new_dev_result(Shards *sh) {
+    size_t tuples = 0;
+    for (int g = 0; g < S.G; ++g) tuples += sh->n[g];
     Result *r = malloc(sizeof *r);
     size_t bytes = 4 * tuples < 16 ? 16 : 4 * tuples;
     void *payload = malloc(bytes);
     if (!r || !payload) {
         free(r);
         free(payload);
-        adb_free(d_ptr);
+        shards_free(sh);
         set_err("out of host memory for a %zu-tuple result", tuples);
         return NULL;
     }
-    if (S.mirror) {
-        if (tuples && adb_download(payload, d_ptr, 4 * tuples) != ADB_OK) {
-            set_err("result mirror: %s", adb_last_error());
-            free(r);
-            free(payload);
-            adb_free(d_ptr);
-            return NULL;
-        }
+    if (S.mirror && tuples && download_shards(payload, sh->d, sh->n)) {
+        free(r);
+        free(payload);
+        shards_free(sh);
+        return NULL;
     }
-    /* malloc returned an address we still hold a buffer for: that payload was freed by the
+    /* malloc returned an address we still hold buffers for: that payload was freed by the
      * plumbing without telling us -- reclaim its HBM now.  No engine call is made with the
      * registry lock held (with the free() interposer other threads' frees wait on it). */
     if (P.active && (payload == P.sel_payload || payload == P.fetch_payload))
-        pending_payload_gone(payload);          /* may still need the dead handle's buffer */
-    int32_t *dead = NULL;
+        pending_payload_gone(payload);          /* may still need the dead handle's buffers */
+    DevResult dead;
+    int have_dead = 0;
     lock();
-    DevResult *stale = registry_find(payload);
-    if (stale) {
-        dead = stale->d_ptr;
-        stale->d_ptr = d_ptr;
-        stale->tuples = tuples;
+    DevResult *e = registry_find(payload);
+    if (e) {
+        dead = *e;
+        have_dead = 1;
     } else {
         if (4 * (S.nused + 1) > 3 * S.nslots && registry_grow()) {
             unlock();
             free(r);
             free(payload);
-            adb_free(d_ptr);
+            shards_free(sh);
             set_err("out of host memory");
             return NULL;
         }
@@ -497,39 +885,102 @@ static Result *new_dev_result(int32_t *d_ptr, size_t tuples) {
         while (S.slots[j].payload != SLOT_EMPTY && S.slots[j].payload != SLOT_TOMB)
             j = (j + 1) & (S.nslots - 1);
         if (S.slots[j].payload == SLOT_EMPTY) ++S.nused;
-        S.slots[j].payload = payload;
-        S.slots[j].d_ptr = d_ptr;
-        S.slots[j].tuples = tuples;
+        e = &S.slots[j];
         ++S.nlive;
     }
+    memset(e, 0, sizeof *e);
+    e->payload = payload;
+    for (int g = 0; g < S.G; ++g) {
+        e->d_ptr[g] = sh->d[g];
+        e->tuples[g] = sh->n[g];
+    }
+    e->total = tuples;
+    e->aligned = sh->aligned;
+    e->slab = sh->slab;
     unlock();
-    if (dead) adb_free(dead);
+    if (have_dead) result_buffers_free(&dead);
     r->num_tuples = tuples;
     r->data_type = INT;
     r->payload = payload;
     return r;
 }
 
-static int32_t *alloc_i32(size_t n) {
-    void *p = NULL;
-    if (adb_alloc(&p, 4 * n) != ADB_OK) {
-        set_err("adb_alloc(%zu): %s", 4 * n, adb_last_error());
-        return NULL;
-    }
-    return p;
+static void drop_result(Result *r) {
+    if (!r) return;
+    adb_host_result_release(r);
+    free(r->payload);
+    free(r);
 }
 
-/* An operator input: the device buffer behind a Result.  A Result whose payload is not in
+/* An operator input: the device buffers behind a Result.  A Result whose payload is not in
  * the registry is an ordinary host array (built by a test or by foreign code); it is staged
- * into a temporary device buffer that the caller releases with unstage(). */
+ * into temporary device buffers that the caller releases with unstage().  `like` (optional):
+ * the split the operand must have -- a device result cut differently is re-cut with peer
+ * copies, a host array is uploaded that way. */
 typedef struct Staged {
-    int32_t *d;
+    int32_t *d[MAXG];
+    size_t n[MAXG];
+    size_t total, aligned;
     int temp;
 } Staged;
 
-static int stage(const Result *r, Staged *out) {
-    out->d = NULL;
-    out->temp = 0;
+static void unstage(Staged *s) {
+    if (s->temp)
+        for (int g = 0; g < S.G; ++g) free_on(g, s->d[g]);   /* stream-ordered: safe right after the launch */
+    memset(s, 0, sizeof *s);
+}
+
+static int same_split(const size_t a[], const size_t b[]) {
+    for (int g = 0; g < S.G; ++g)
+        if (a[g] != b[g]) return 0;
+    return 1;
+}
+
+/* dst (context g, `want[g]` entries each) <- the list whose shards are src/have, re-cut */
+static int recut(int32_t *const src[], const size_t have[], const size_t want[], int32_t *dst[]) {
+    size_t src_begin[MAXG + 1];
+    src_begin[0] = 0;
+    for (int s = 0; s < S.G; ++s) src_begin[s + 1] = src_begin[s] + have[s];
+    size_t dst_begin = 0;
+    int rc = 0;
+    for (int g = 0; g < S.G && !rc; ++g) {
+        void *p = NULL;
+        on_ctx(g);
+        if (adb_alloc(&p, 4 * want[g]) != ADB_OK) {
+            set_err("adb_alloc(%zu): %s", 4 * want[g], adb_last_error());
+            rc = -1;
+            break;
+        }
+        dst[g] = p;
+        const size_t b = dst_begin, e = dst_begin + want[g];
+        for (int s = 0; s < S.G; ++s) {
+            const size_t lo = b > src_begin[s] ? b : src_begin[s];
+            const size_t hi = e < src_begin[s + 1] ? e : src_begin[s + 1];
+            if (lo >= hi) continue;
+            if (adb_copy_from_ctx(dst[g] + (lo - b), s, src[s] + (lo - src_begin[s]), 4 * (hi - lo)) != ADB_OK) {
+                set_err("adb_copy_from_ctx: %s", adb_last_error());
+                rc = -1;
+                break;
+            }
+        }
+        dst_begin = e;
+    }
+    /* The copies run on each destination context's own stream -- the stream its consumer runs
+     * on -- but the SOURCE buffers belong to other contexts' pools and may be released as soon as
+     * the operator returns: wait for the copies here (a rare path: operands cut differently). */
+    for (int g = 0; g < S.G; ++g) {
+        on_ctx(g);
+        if (adb_sync() != ADB_OK && !rc) {
+            set_err("adb_sync: %s", adb_last_error());
+            rc = -1;
+        }
+    }
+    on_ctx(0);
+    return rc;
+}
+
+static int stage(const Result *r, const size_t *like, Staged *out) {
+    memset(out, 0, sizeof *out);
     if (!r) {
         set_err("NULL result operand");
         return -1;
@@ -541,35 +992,67 @@ static int stage(const Result *r, Staged *out) {
     if (flush_pending()) return -1;             /* an operand is about to be read */
     lock();
     DevResult *e = registry_find(r->payload);
-    int32_t *d = e ? e->d_ptr : NULL;
-    size_t have = e ? e->tuples : 0;
+    DevResult dv;
+    if (e) dv = *e;
     unlock();
-    if (d) {
-        if (have < r->num_tuples) {
-            set_err("result claims %zu tuples but its device buffer holds %zu", r->num_tuples, have);
+    out->total = r->num_tuples;
+    if (e) {
+        if (dv.total < r->num_tuples) {
+            set_err("result claims %zu tuples but its device buffers hold %zu", r->num_tuples, dv.total);
             return -1;
         }
-        out->d = d;
+        size_t have[MAXG];
+        memcpy(have, dv.tuples, sizeof have);
+        if (dv.total > r->num_tuples) {         /* a caller shortened the list: drop the tail */
+            size_t left = r->num_tuples;
+            for (int g = 0; g < S.G; ++g) {
+                have[g] = have[g] < left ? have[g] : left;
+                left -= have[g];
+            }
+        }
+        if (!like || same_split(have, like)) {
+            for (int g = 0; g < S.G; ++g) {
+                out->d[g] = dv.d_ptr[g];
+                out->n[g] = have[g];
+            }
+            out->aligned = dv.aligned;
+            return 0;
+        }
+        out->temp = 1;
+        memcpy(out->n, like, sizeof(size_t) * (size_t)S.G);
+        if (recut(dv.d_ptr, have, like, out->d)) {
+            unstage(out);
+            return -1;
+        }
         return 0;
     }
     if (r->num_tuples && !r->payload) {
         set_err("result operand has no payload");
         return -1;
     }
-    out->d = alloc_i32(r->num_tuples);
-    if (!out->d) return -1;
+    /* host array: upload, cut like the partner or evenly */
     out->temp = 1;
-    if (r->num_tuples && adb_upload(out->d, r->payload, 4 * r->num_tuples) != ADB_OK) {
-        set_err("operand upload: %s", adb_last_error());
-        adb_free(out->d);
-        out->d = NULL;
-        return -1;
+    const size_t per = (r->num_tuples + (size_t)S.G - 1) / (size_t)S.G;
+    size_t off = 0;
+    int rc = 0;
+    for (int g = 0; g < S.G; ++g) {
+        const size_t n = like ? like[g] : shard_len(r->num_tuples, per ? per : 1, g);
+        void *p = NULL;
+        on_ctx(g);
+        if (adb_alloc(&p, 4 * n) != ADB_OK ||
+            (n && adb_upload(p, (const char *)r->payload + 4 * off, 4 * n) != ADB_OK)) {
+            set_err("operand upload: %s", adb_last_error());
+            if (p) adb_free(p);
+            rc = -1;
+            break;
+        }
+        out->d[g] = p;
+        out->n[g] = n;
+        off += n;
     }
-    return 0;
-}
-static void unstage(Staged *s) {
-    if (s->temp && s->d) adb_free(s->d);   /* stream-ordered: safe right after the launch */
-    s->d = NULL;
+    on_ctx(0);
+    if (rc) unstage(out);
+    return rc;
 }
 
 int adb_host_result_to_host(const Result *result, void *dst) {
@@ -578,17 +1061,36 @@ int adb_host_result_to_host(const Result *result, void *dst) {
     if (flush_pending()) return -1;
     lock();
     DevResult *e = registry_find(result->payload);
-    int32_t *d = e ? e->d_ptr : NULL;
+    DevResult dv;
+    if (e) dv = *e;
     unlock();
-    if (!d) {                               /* scalar or foreign host payload */
+    if (!e) {                               /* scalar or foreign host payload */
         size_t w = result->data_type == INT || result->data_type == FLOAT ? 4 : 8;
         memcpy(dst, result->payload, w * result->num_tuples);
         return 0;
     }
-    if (adb_download(dst, d, 4 * result->num_tuples) != ADB_OK) {
-        set_err("adb_download: %s", adb_last_error());
-        return -1;
+    size_t have[MAXG], left = result->num_tuples;
+    for (int g = 0; g < S.G; ++g) {
+        have[g] = dv.tuples[g] < left ? dv.tuples[g] : left;
+        left -= have[g];
     }
+    return download_shards(dst, dv.d_ptr, have);
+}
+
+/* allocate n[g] ints on every context (main thread) */
+static int alloc_shards(Shards *sh) {
+    for (int g = 0; g < S.G; ++g) {
+        void *p = NULL;
+        on_ctx(g);
+        if (adb_alloc(&p, 4 * sh->n[g]) != ADB_OK) {
+            set_err("adb_alloc(%zu): %s", 4 * sh->n[g], adb_last_error());
+            on_ctx(0);
+            shards_free(sh);
+            return -1;
+        }
+        sh->d[g] = p;
+    }
+    on_ctx(0);
     return 0;
 }
 
@@ -603,25 +1105,94 @@ bool should_use_index(Column *column, int low, int high) {
 
 void log_result(Result *result) { (void)result; }        /* src/query.c:26-28: returns at once */
 
-/* select_column_sorted_index (src/query.c:165-198) through the uploaded index. */
-static Result *select_index_path(Column *column, DevColumn *c, int *low, int *high, Status *st) {
+typedef struct SelectJob {
+    ShardErr err;
+    DevColumn *c;
+    int *low, *high;
+    int use_btree, defer;
+    Shards out;
+    uint64_t generation[MAXG];
+} SelectJob;
+
+/* select_column_sorted_index (src/query.c:165-198) through the uploaded index slices. */
+static void select_index_shard(int g, void *arg) {
+    SelectJob *a = arg;
+    DevColumn *c = a->c;
     int64_t h = 0;
-    int32_t *out = NULL;
+    SCK(adb_select_index_count(c->ix[g], a->use_btree, a->low, a->high, NULL, &h));
+    void *p = NULL;
+    SCK(adb_alloc(&p, 4 * (size_t)h));
+    a->out.d[g] = p;
+    a->out.n[g] = (size_t)h;
+    SCK(adb_select_index_emit(c->ix[g], p));
+}
+
+static Result *select_index_path(Column *column, DevColumn *c, int *low, int *high, Status *st) {
     if (dev_index(c, column)) return op_fail(st, "select_column");
-    const int use_btree = !column->sorted;             /* create_index(... sorted=false) = btree */
-    CK(adb_select_index_count(c->ix, use_btree, low, high, NULL, &h));
-    out = alloc_i32((size_t)h);
-    if (!out) goto fail;
-    CK(adb_select_index_emit(c->ix, out));
+    SelectJob job;
+    memset(&job, 0, sizeof job);
+    job.c = c;
+    job.low = low;
+    job.high = high;
+    job.use_btree = !column->sorted;                 /* create_index(... sorted=false) = btree */
+    run_shards(select_index_shard, &job);
+    if (shard_errs(&job.err)) goto fail;
+    if (S.G > 1) {
+        /* the slices answered positions[lb(low) .. lb(high)); the reference's low == high quirk
+         * (query.c:181-188; closed form in index_lookup.cu) belongs to the whole index: in the
+         * defined domain, an empty range whose upper bound is a key yields the first tuple
+         * carrying that key */
+        size_t total = 0;
+        for (int g = 0; g < S.G; ++g) total += job.out.n[g];
+        if (total == 0 && c->ix_rows > 0 && low && high && *low <= *high && *low >= c->ix_min) {
+            SelectJob q2;
+            memset(&q2, 0, sizeof q2);
+            int lo2 = *high, hi2 = *high == INT_MAX ? 0 : *high + 1;
+            q2.c = c;
+            q2.low = &lo2;
+            q2.high = *high == INT_MAX ? NULL : &hi2;
+            q2.use_btree = job.use_btree;
+            run_shards(select_index_shard, &q2);
+            if (shard_errs(&q2.err)) {
+                shards_free(&q2.out);
+                goto fail;
+            }
+            int first = -1;
+            for (int g = 0; g < S.G; ++g)
+                if (q2.out.n[g] && first < 0) first = g;
+            if (first >= 0) {                       /* keep the first tuple only */
+                shards_free(&job.out);
+                job.out = q2.out;
+                for (int g = 0; g < S.G; ++g) job.out.n[g] = g == first ? 1 : 0;
+            } else {
+                shards_free(&q2.out);
+            }
+        }
+    }
+    job.out.aligned = 0;                            /* index order: positions anywhere */
     {
-        Result *r = new_dev_result(out, (size_t)h);
+        Result *r = new_dev_result(&job.out);
         if (!r) return op_fail(st, "select_column");
         op_ok(st);
         return r;
     }
 fail:
-    if (out) adb_free(out);
+    shards_free(&job.out);
     return op_fail(st, "select_column");
+}
+
+static void select_scan_shard(int g, void *arg) {
+    SelectJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t n = shard_len(c->rows, c->shard_rows, g);
+    int64_t h = 0;
+    SCK(adb_select_count_base(c->d_data[g], (int64_t)n, a->low, a->high, shard_base(g, c->shard_rows), NULL, &h));
+    a->generation[g] = adb_select_generation();
+    void *p = NULL;
+    SCK(adb_alloc(&p, 4 * (size_t)h));
+    a->out.d[g] = p;
+    a->out.n[g] = (size_t)h;
+    if (!a->defer) SCK(adb_select_emit(NULL, shard_base(g, c->shard_rows), p));
 }
 
 /* src/query.c:203-220: clustered or indexed columns go through the index, others scan. */
@@ -633,79 +1204,148 @@ Result *select_column(Column *column, int *low, int *high, Status *ret_status) {
     if (column->clustered ||
         (column->has_index && should_use_index(column, low ? *low : 0, high ? *high : 0)))
         return select_index_path(column, c, low, high, ret_status);
-    int64_t h = 0;
-    int32_t *out = NULL;
-    if (flush_pending()) goto fail;                 /* this select takes over the bitmap */
-    CK(adb_select_count(c->d_data, (int64_t)c->rows, NULL, low, high, NULL, &h));
-    out = alloc_i32((size_t)h);
-    if (!out) goto fail;
-    const int defer = S.lazy && h > 0;
-    if (!defer) CK(adb_select_emit(NULL, 0, out));
+    SelectJob job;
+    memset(&job, 0, sizeof job);
+    if (flush_pending()) goto fail;                 /* this select takes over the bitmaps */
+    job.c = c;
+    job.low = low;
+    job.high = high;
+    job.defer = S.lazy;
+    run_shards(select_scan_shard, &job);
+    if (shard_errs(&job.err)) goto fail;
+    job.out.aligned = c->shard_rows;
     {
-        Result *r = new_dev_result(out, (size_t)h);
+        size_t total = 0;
+        for (int g = 0; g < S.G; ++g) total += job.out.n[g];
+        Shards keep = job.out;
+        Result *r = new_dev_result(&job.out);
         if (!r) return op_fail(ret_status, "select_column");
-        if (defer) {                                /* positions are written by whoever needs them first */
+        if (job.defer && total > 0) {               /* positions are written by whoever needs them first */
             memset(&P, 0, sizeof P);
             P.sel_payload = r->payload;
-            P.sel_d = out;
-            P.h = (size_t)h;
-            P.d_col = c->d_data;
-            P.rows = c->rows;
+            for (int g = 0; g < S.G; ++g) {
+                P.sel_d[g] = keep.d[g];
+                P.h[g] = keep.n[g];
+                P.d_col[g] = c->d_data[g];
+                P.rows[g] = shard_len(c->rows, c->shard_rows, g);
+                P.generation[g] = job.generation[g];
+            }
+            P.shard_rows = c->shard_rows;
             P.has_lo = low != NULL;
             P.has_hi = high != NULL;
             P.lo = low ? *low : 0;
             P.hi = high ? *high : 0;
-            P.generation = adb_select_generation();
             P.active = 1;
         }
         op_ok(ret_status);
         return r;
     }
 fail:
-    if (out) adb_free(out);
+    shards_free(&job.out);
     return op_fail(ret_status, "select_column");
 }
 
 /* src/query.c:38-86: predicate over a fetched value vector, emits the paired positions. */
+typedef struct PairsJob {
+    ShardErr err;
+    Staged *v, *p;
+    int *low, *high;
+    Shards out;
+} PairsJob;
+static void select_pairs_shard(int g, void *arg) {
+    PairsJob *a = arg;
+    int64_t h = 0;
+    SCK(adb_select_count(a->v->d[g], (int64_t)a->v->n[g], NULL, a->low, a->high, NULL, &h));
+    void *p = NULL;
+    SCK(adb_alloc(&p, 4 * (size_t)h));
+    a->out.d[g] = p;
+    a->out.n[g] = (size_t)h;
+    SCK(adb_select_emit(a->p->d[g], 0, p));
+}
+
 Result *select_result(Result *column, Result *position, int *low_pointer, int *high_pointer,
                       Status *ret_status) {
     t_err[0] = '\0';
-    Staged v = {0}, p = {0};
-    int32_t *out = NULL;
-    int64_t h = 0;
-    if (ensure_up() || stage(column, &v) || stage(position, &p)) goto fail;
-    if (position->num_tuples < column->num_tuples) {
-        set_err("select: %zu values but only %zu positions", column->num_tuples, position->num_tuples);
+    Staged v, p;
+    memset(&v, 0, sizeof v);
+    memset(&p, 0, sizeof p);
+    PairsJob job;
+    memset(&job, 0, sizeof job);
+    if (ensure_up() || stage(column, NULL, &v)) goto fail;
+    if (!position || position->num_tuples < column->num_tuples) {
+        set_err("select: %zu values but only %zu positions", column->num_tuples,
+                position ? position->num_tuples : (size_t)0);
         goto fail;
     }
-    CK(adb_select_count(v.d, (int64_t)column->num_tuples, NULL, low_pointer, high_pointer, NULL, &h));
-    out = alloc_i32((size_t)h);
-    if (!out) goto fail;
-    CK(adb_select_emit(p.d, 0, out));
+    {
+        /* the positions are cut like the values (a longer list: the extra tail is ignored, as
+         * the reference's loop over column->num_tuples does) */
+        Result head = *position;
+        head.num_tuples = column->num_tuples;
+        if (stage(&head, v.n, &p)) goto fail;
+    }
+    job.v = &v;
+    job.p = &p;
+    job.low = low_pointer;
+    job.high = high_pointer;
+    run_shards(select_pairs_shard, &job);
+    if (shard_errs(&job.err)) goto fail;
+    job.out.aligned = p.aligned;
     unstage(&v);
     unstage(&p);
     {
-        Result *r = new_dev_result(out, (size_t)h);
+        Result *r = new_dev_result(&job.out);
         if (!r) return op_fail(ret_status, "select_result");
         op_ok(ret_status);
         return r;
     }
 fail:
-    if (out) adb_free(out);
+    shards_free(&job.out);
     unstage(&v);
     unstage(&p);
     return op_fail(ret_status, "select_result");
 }
 
 /* src/query.c:450-583: query_count range selects in one pass; reads .low/.high only and
- * ignores has_low/has_high and indexes, exactly as query.c:474 does. */
+ * ignores has_low/has_high and indexes, exactly as query.c:474 does.  Per context ONE slab holds
+ * all the batch's position lists (one allocation instead of query_count); every Result is a
+ * view into it and the slab goes back to the pool when the last of them is released. */
+typedef struct SharedJob {
+    ShardErr err;
+    DevColumn *c;
+    int q_count;
+    int32_t *lows, *highs;
+    int64_t counts[MAXG][ADB_MAX_BATCH];
+    size_t off[MAXG][ADB_MAX_BATCH];
+    int32_t *slab[MAXG];
+} SharedJob;
+static void shared_shard(int g, void *arg) {
+    SharedJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t n = shard_len(c->rows, c->shard_rows, g);
+    SCK(adb_shared_select_count_base(c->d_data[g], (int64_t)n, shard_base(g, c->shard_rows), a->lows, a->highs,
+                                     a->q_count, a->counts[g]));
+    size_t total = 0;
+    int64_t cap = 1;
+    for (int q = 0; q < a->q_count; ++q) {
+        a->off[g][q] = total;
+        total += ((size_t)a->counts[g][q] + 3) & ~(size_t)3;         /* every list 16-byte aligned */
+        if (a->counts[g][q] > cap) cap = a->counts[g][q];
+    }
+    void *p = NULL;
+    SCK(adb_alloc(&p, 4 * total));
+    a->slab[g] = p;
+    int32_t *outs[ADB_MAX_BATCH];
+    for (int q = 0; q < a->q_count; ++q) outs[q] = a->slab[g] + a->off[g][q];
+    SCK(adb_shared_select_emit(outs, cap));
+}
+
 Result **shared_select(SelectOperator *operators, int query_count, Column *column,
                        Status *ret_status) {
     t_err[0] = '\0';
     Result **results = NULL;
-    int32_t **outs = NULL;
-    int32_t *lows = NULL, *highs = NULL;
-    int64_t *counts = NULL;
+    SharedJob *job = NULL;
+    Slab *slab = NULL;
     int made = 0;
     if (ensure_up()) goto fail;
     if (query_count < 1 || query_count > ADB_MAX_BATCH || !operators) {
@@ -716,118 +1356,226 @@ Result **shared_select(SelectOperator *operators, int query_count, Column *colum
     DevColumn *c = dev_column(column);
     if (!c || flush_pending()) goto fail;
     results = calloc((size_t)query_count, sizeof *results);
-    outs = calloc((size_t)query_count, sizeof *outs);
-    lows = malloc(sizeof *lows * (size_t)query_count);
-    highs = malloc(sizeof *highs * (size_t)query_count);
-    counts = malloc(sizeof *counts * (size_t)query_count);
-    if (!results || !outs || !lows || !highs || !counts) {
+    job = calloc(1, sizeof *job);
+    slab = calloc(1, sizeof *slab);
+    if (job) {
+        job->lows = malloc(sizeof(int32_t) * (size_t)query_count);
+        job->highs = malloc(sizeof(int32_t) * (size_t)query_count);
+    }
+    if (!results || !job || !slab || !job->lows || !job->highs) {
         set_err("out of host memory");
         goto fail;
     }
     for (int q = 0; q < query_count; ++q) {
-        lows[q] = operators[q].low;
-        highs[q] = operators[q].high;
+        job->lows[q] = operators[q].low;
+        job->highs[q] = operators[q].high;
     }
-    CK(adb_shared_select_count(c->d_data, (int64_t)c->rows, lows, highs, query_count, counts));
-    int64_t cap = 1;
-    for (int q = 0; q < query_count; ++q) {
-        outs[q] = alloc_i32((size_t)counts[q]);
-        if (!outs[q]) goto fail;
-        if (counts[q] > cap) cap = counts[q];
+    job->c = c;
+    job->q_count = query_count;
+    run_shards(shared_shard, job);
+    if (shard_errs(&job->err)) {
+        for (int g = 0; g < S.G; ++g) free_on(g, job->slab[g]);
+        goto fail;
     }
-    CK(adb_shared_select_emit(outs, cap));
+    for (int g = 0; g < S.G; ++g) slab->base[g] = job->slab[g];
+    slab->refs = query_count;
     for (int q = 0; q < query_count; ++q) {
-        int32_t *d = outs[q];
-        outs[q] = NULL;                             /* ownership moves into the Result */
-        results[q] = new_dev_result(d, (size_t)counts[q]);
-        if (!results[q]) goto fail;
+        Shards sh;
+        memset(&sh, 0, sizeof sh);
+        for (int g = 0; g < S.G; ++g) {
+            sh.d[g] = job->slab[g] + job->off[g][q];
+            sh.n[g] = (size_t)job->counts[g][q];
+        }
+        sh.aligned = c->shard_rows;
+        sh.slab = slab;
+        results[q] = new_dev_result(&sh);
+        if (!results[q]) {
+            /* the views not handed out yet give their references back */
+            slab->refs -= query_count - q;
+            if (slab->refs == 0) {
+                for (int g = 0; g < S.G; ++g) free_on(g, slab->base[g]);
+                free(slab);
+            }
+            slab = NULL;
+            goto fail;
+        }
         made = q + 1;
     }
-    free(outs); free(lows); free(highs); free(counts);
+    free(job->lows);
+    free(job->highs);
+    free(job);
     op_ok(ret_status);
     return results;
 fail:
-    for (int q = 0; q < made; ++q) {
-        adb_host_result_release(results[q]);
-        free(results[q]->payload);
-        free(results[q]);
+    for (int q = 0; q < made; ++q) drop_result(results[q]);
+    if (made == 0) free(slab);
+    free(results);
+    if (job) {
+        free(job->lows);
+        free(job->highs);
+        free(job);
     }
-    if (outs)
-        for (int q = 0; q < query_count; ++q)
-            if (outs[q]) adb_free(outs[q]);
-    free(results); free(outs); free(lows); free(highs); free(counts);
     return op_fail(ret_status, "shared_select");
 }
 
 /* ---- fetch --------------------------------------------------------------------------------- */
 /* src/query.c:223-243: values[i] = column->data[position[i]]. */
+typedef struct FetchJob {
+    ShardErr err;
+    DevColumn *c;
+    Staged *p;
+    Shards out;
+} FetchJob;
+static void fetch_shard(int g, void *arg) {
+    FetchJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t n = a->p->n[g];
+    void *out = NULL;
+    SCK(adb_alloc(&out, 4 * n));
+    a->out.d[g] = out;
+    a->out.n[g] = n;
+    if (!n) return;
+    if (S.G == 1 || (a->p->aligned && a->p->aligned == c->shard_rows))
+        SCK(adb_fetch(c->d_data[g], a->p->d[g], (int64_t)n, NULL, shard_base(g, c->shard_rows), out));
+    else
+        SCK(adb_fetch_sharded((const int32_t *const *)c->d_data, S.G, (int64_t)c->shard_rows, a->p->d[g],
+                              (int64_t)n, NULL, out));
+}
+
 Result *fetch_column(Column *column, Result *position_result, Status *ret_status) {
     t_err[0] = '\0';
-    Staged p = {0};
-    int32_t *out = NULL;
+    Staged p;
+    memset(&p, 0, sizeof p);
+    FetchJob job;
+    memset(&job, 0, sizeof job);
     if (ensure_up()) goto fail;
     DevColumn *c = dev_column(column);
     if (!c) goto fail;
     /* fetch of the pending select: nothing is launched yet -- the values are written together
      * with the positions, by the aggregate that usually follows or by the first other reader */
     if (P.active && position_result && position_result->payload == P.sel_payload && !P.fetch_payload &&
-        position_result->num_tuples == P.h && c->rows >= P.rows) {
-        out = alloc_i32(P.h);
-        if (!out) goto fail;
-        Result *r = new_dev_result(out, P.h);
-        if (!r) return op_fail(ret_status, "fetch_column");
-        if (P.active) {                             /* (new_dev_result may have flushed) */
-            P.fetch_payload = r->payload;
-            P.fetch_d = out;
-            P.d_fetch_col = c->d_data;
-        } else if (adb_fetch(c->d_data, P.sel_d, (int64_t)P.h, NULL, 0, out) != ADB_OK) {
-            set_err("adb_fetch: %s", adb_last_error());
-            adb_host_result_release(r);
-            free(r->payload);
-            free(r);
-            return op_fail(ret_status, "fetch_column");
+        c->shard_rows == P.shard_rows) {
+        size_t total = 0;
+        int fits = 1;
+        for (int g = 0; g < S.G; ++g) {
+            total += P.h[g];
+            if (shard_len(c->rows, c->shard_rows, g) < P.rows[g]) fits = 0;
         }
-        op_ok(ret_status);
-        return r;
+        if (fits && position_result->num_tuples == total) {
+            Shards sh;
+            memset(&sh, 0, sizeof sh);
+            memcpy(sh.n, P.h, sizeof sh.n);
+            if (alloc_shards(&sh)) goto fail;
+            Shards keep = sh;
+            Result *r = new_dev_result(&sh);
+            if (!r) return op_fail(ret_status, "fetch_column");
+            if (P.active) {                         /* (new_dev_result may have flushed) */
+                P.fetch_payload = r->payload;
+                for (int g = 0; g < S.G; ++g) {
+                    P.fetch_d[g] = keep.d[g];
+                    P.d_fetch_col[g] = c->d_data[g];
+                }
+                op_ok(ret_status);
+                return r;
+            }
+            drop_result(r);                         /* rare: take the ordinary path below */
+        }
     }
-    if (stage(position_result, &p)) goto fail;
-    const size_t n = position_result->num_tuples;
-    out = alloc_i32(n);
-    if (!out) goto fail;
-    CK(adb_fetch(c->d_data, p.d, (int64_t)n, NULL, 0, out));
+    if (stage(position_result, NULL, &p)) goto fail;
+    job.c = c;
+    job.p = &p;
+    run_shards(fetch_shard, &job);
+    if (shard_errs(&job.err)) goto fail;
+    job.out.aligned = p.aligned;                    /* values pair with their positions shard by shard */
     unstage(&p);
     {
-        Result *r = new_dev_result(out, n);
+        Result *r = new_dev_result(&job.out);
         if (!r) return op_fail(ret_status, "fetch_column");
         op_ok(ret_status);
         return r;
     }
 fail:
-    if (out) adb_free(out);
+    shards_free(&job.out);
     unstage(&p);
     return op_fail(ret_status, "fetch_column");
 }
 
 /* ---- aggregates ------------------------------------------------------------------------------ */
+typedef struct AggJob {
+    ShardErr err;
+    int32_t *const *d;
+    const size_t *n;
+    int fused;                   /* resolve the pending select + fetch in the same kernel */
+    adb_agg h;
+} AggJob;
+static void agg_shard(int g, void *arg) {
+    AggJob *a = arg;
+    adb_agg *h = g == 0 ? &a->h : NULL;
+    if (a->fused) {
+        if (S.G == 1)
+            SCK(adb_select_emit_fetch_agg(P.d_fetch_col[g], P.sel_d[g], P.fetch_d[g], S.d_part[g], h));
+        else
+            SCK(adb_select_emit_fetch_agg_exchange(P.d_fetch_col[g], P.sel_d[g], P.fetch_d[g], S.d_part[g],
+                                                   S.d_out[g], h));
+        return;
+    }
+    if (S.G == 1) {
+        SCK(adb_aggregate(a->d[g], (int64_t)a->n[g], NULL, S.d_part[g], h));
+    } else {
+        SCK(adb_aggregate(a->d[g], (int64_t)a->n[g], NULL, S.d_part[g], NULL));
+        SCK(adb_agg_combine_allreduce(S.d_part[g], 1, S.d_out[g], h));
+    }
+}
+
+static int aggregate_shards(int32_t *const d[], const size_t n[], adb_agg *h) {
+    AggJob job;
+    memset(&job, 0, sizeof job);
+    job.d = d;
+    job.n = n;
+    run_shards(agg_shard, &job);
+    if (shard_errs(&job.err)) return -1;
+    *h = job.h;
+    return 0;
+}
+
 static int aggregate_result(const Result *r, adb_agg *h) {
-    Staged v = {0};
+    Staged v;
+    memset(&v, 0, sizeof v);
     if (ensure_up()) return -1;
     /* aggregate of the pending fetch of the pending select: the chain's fused second kernel
      * writes both handles and the aggregate in one pass */
-    if (P.active && r && P.fetch_payload && r->payload == P.fetch_payload && r->num_tuples == P.h &&
-        r->data_type == INT && adb_select_generation() == P.generation) {
-        P.active = 0;
-        if (adb_select_emit_fetch_agg(P.d_fetch_col, P.sel_d, P.fetch_d, S.d_agg, h) != ADB_OK) {
-            set_err("adb_select_emit_fetch_agg: %s", adb_last_error());
-            return -1;
+    if (P.active && r && P.fetch_payload && r->payload == P.fetch_payload && r->data_type == INT) {
+        size_t total = 0;
+        for (int g = 0; g < S.G; ++g) total += P.h[g];
+        if (r->num_tuples == total) {
+            /* every context must still hold its bitmap: a context that lost it redoes the count
+             * first (flush path), after which the ordinary aggregate below runs */
+            int intact = 1;
+            if (S.G == 1) {
+                intact = adb_select_generation() == P.generation[0];
+            } else {
+                for (int g = 0; g < S.G && intact; ++g) {
+                    on_ctx(g);
+                    intact = adb_select_generation() == P.generation[g];
+                }
+                on_ctx(0);
+            }
+            if (intact) {
+                AggJob job;
+                memset(&job, 0, sizeof job);
+                job.fused = 1;
+                P.active = 0;
+                run_shards(agg_shard, &job);
+                if (shard_errs(&job.err)) return -1;
+                *h = job.h;
+                return 0;
+            }
         }
-        return 0;
     }
-    if (stage(r, &v)) return -1;
-    adb_status s = adb_aggregate(v.d, (int64_t)r->num_tuples, NULL, S.d_agg, h);
-    if (s != ADB_OK) set_err("adb_aggregate: %s", adb_last_error());
+    if (stage(r, NULL, &v)) return -1;
+    int rc = aggregate_shards(v.d, v.n, h);
     unstage(&v);
-    return s == ADB_OK ? 0 : -1;
+    return rc;
 }
 
 static Result *scalar_result(DataType t, const void *value, size_t width, Status *st, const char *what) {
@@ -875,10 +1623,9 @@ Result *sum(GeneralizedColumn *column, Status *ret_status) {
         if (ensure_up()) return op_fail(ret_status, "sum");
         DevColumn *c = dev_column(column->column_pointer.column);
         if (!c) return op_fail(ret_status, "sum");
-        if (adb_aggregate(c->d_data, (int64_t)c->rows, NULL, S.d_agg, &a) != ADB_OK) {
-            set_err("adb_aggregate: %s", adb_last_error());
-            return op_fail(ret_status, "sum");
-        }
+        size_t n[MAXG];
+        for (int g = 0; g < S.G; ++g) n[g] = shard_len(c->rows, c->shard_rows, g);
+        if (aggregate_shards(c->d_data, n, &a)) return op_fail(ret_status, "sum");
     }
     long s = (long)a.sum;
     return scalar_result(LONG, &s, sizeof s, ret_status, "sum");
@@ -904,30 +1651,55 @@ Result *max(Result *column, Status *ret_status) {
 /* ---- add / sub -------------------------------------------------------------------------------- */
 /* src/query.c:356-390: length is column_one's; the reference does not check column_two's
  * length (it would read out of bounds) -- here a shorter column_two is an ERROR. */
+typedef struct EwiseJob {
+    ShardErr err;
+    Staged *a, *b;
+    int subtract;
+    Shards out;
+} EwiseJob;
+static void ewise_shard(int g, void *arg) {
+    EwiseJob *a = arg;
+    const size_t n = a->a->n[g];
+    void *out = NULL;
+    SCK(adb_alloc(&out, 4 * n));
+    a->out.d[g] = out;
+    a->out.n[g] = n;
+    SCK((a->subtract ? adb_sub : adb_add)(a->a->d[g], a->b->d[g], (int64_t)n, NULL, out));
+}
 static Result *ewise(Result *one, Result *two, int subtract, Status *st) {
     t_err[0] = '\0';
     const char *what = subtract ? "sub" : "add";
-    Staged a = {0}, b = {0};
-    int32_t *out = NULL;
-    if (ensure_up() || stage(one, &a) || stage(two, &b)) goto fail;
-    if (two->num_tuples < one->num_tuples) {
-        set_err("%s: operands of %zu and %zu tuples", what, one->num_tuples, two->num_tuples);
+    Staged a, b;
+    memset(&a, 0, sizeof a);
+    memset(&b, 0, sizeof b);
+    EwiseJob job;
+    memset(&job, 0, sizeof job);
+    if (ensure_up() || stage(one, NULL, &a)) goto fail;
+    if (!two || two->num_tuples < one->num_tuples) {
+        set_err("%s: operands of %zu and %zu tuples", what, one->num_tuples, two ? two->num_tuples : (size_t)0);
         goto fail;
     }
-    const size_t n = one->num_tuples;
-    out = alloc_i32(n);
-    if (!out) goto fail;
-    CK((subtract ? adb_sub : adb_add)(a.d, b.d, (int64_t)n, NULL, out));
+    {
+        Result head = *two;
+        head.num_tuples = one->num_tuples;
+        if (stage(&head, a.n, &b)) goto fail;
+    }
+    job.a = &a;
+    job.b = &b;
+    job.subtract = subtract;
+    run_shards(ewise_shard, &job);
+    if (shard_errs(&job.err)) goto fail;
+    job.out.aligned = a.aligned;
     unstage(&a);
     unstage(&b);
     {
-        Result *r = new_dev_result(out, n);
+        Result *r = new_dev_result(&job.out);
         if (!r) return op_fail(st, what);
         op_ok(st);
         return r;
     }
 fail:
-    if (out) adb_free(out);
+    shards_free(&job.out);
     unstage(&a);
     unstage(&b);
     return op_fail(st, what);
@@ -942,42 +1714,85 @@ Result *sub(Result *column_one, Result *column_two, Status *ret_status) {
 /* ---- joins --------------------------------------------------------------------------------------- */
 /* src/query.c:585-696.  results[0] lists side-one positions, results[1] side-two positions;
  * hash join is probe-major over side two, nested-loop outer-major over side one.  The
- * caller frees the two-element array (src/server.c:432). */
+ * caller frees the two-element array (src/server.c:432).
+ * G > 1: the four operands are brought to context 0 over peer copies and joined there (the
+ * output order of the reference is global -- probe-major -- so the result is one list);
+ * the sharded form of the join (hash-partitioned over the GPUs, adb_peer_exchange_pairs) is
+ * measured through the C-ABI by bench.py. */
 static Result **join(Result *v1, Result *p1, Result *v2, Result *p2, int nested, Status *st) {
     t_err[0] = '\0';
     const char *what = nested ? "nested_loop_join" : "hash_join";
-    Staged a = {0}, b = {0}, c = {0}, d = {0};
+    Staged a, b, c, d;
+    memset(&a, 0, sizeof a); memset(&b, 0, sizeof b); memset(&c, 0, sizeof c); memset(&d, 0, sizeof d);
     int32_t *o1 = NULL, *o2 = NULL;
     Result **results = NULL;
     int64_t m = 0;
-    if (ensure_up() || stage(v1, &a) || stage(p1, &b) || stage(v2, &c) || stage(p2, &d)) goto fail;
+    size_t all1[MAXG] = {0}, all2[MAXG] = {0};
+    if (ensure_up() || !v1 || !p1 || !v2 || !p2) goto fail;
     if (p1->num_tuples < v1->num_tuples || p2->num_tuples < v2->num_tuples) {
         set_err("%s: fewer positions than values", what);
         goto fail;
     }
-    CK((nested ? adb_nested_loop_join_count : adb_hash_join_count)(
-        a.d, b.d, (int64_t)v1->num_tuples, c.d, d.d, (int64_t)v2->num_tuples, &m));
-    o1 = alloc_i32((size_t)m);
-    o2 = alloc_i32((size_t)m);
-    if (!o1 || !o2) goto fail;
-    CK(adb_join_emit(o1, o2));
+    all1[0] = v1->num_tuples;
+    all2[0] = v2->num_tuples;
+    {
+        Result h1 = *p1, h2 = *p2;
+        h1.num_tuples = v1->num_tuples;
+        h2.num_tuples = v2->num_tuples;
+        if (stage(v1, all1, &a) || stage(&h1, all1, &b) || stage(v2, all2, &c) || stage(&h2, all2, &d)) goto fail;
+    }
+    if ((nested ? adb_nested_loop_join_count : adb_hash_join_count)(
+            a.d[0], b.d[0], (int64_t)v1->num_tuples, c.d[0], d.d[0], (int64_t)v2->num_tuples, &m) != ADB_OK) {
+        set_err("%s: %s", what, adb_last_error());
+        goto fail;
+    }
+    {
+        void *x = NULL, *y = NULL;
+        if (adb_alloc(&x, 4 * (size_t)m) != ADB_OK || adb_alloc(&y, 4 * (size_t)m) != ADB_OK) {
+            set_err("adb_alloc: %s", adb_last_error());
+            if (x) adb_free(x);
+            goto fail;
+        }
+        o1 = x;
+        o2 = y;
+    }
+    if (adb_join_emit(o1, o2) != ADB_OK) {
+        set_err("adb_join_emit: %s", adb_last_error());
+        goto fail;
+    }
     unstage(&a); unstage(&b); unstage(&c); unstage(&d);
     results = malloc(2 * sizeof *results);
     if (!results) {
         set_err("out of host memory");
         goto fail;
     }
-    results[0] = new_dev_result(o1, (size_t)m);
-    o1 = NULL;
-    results[1] = results[0] ? new_dev_result(o2, (size_t)m) : NULL;
-    if (results[0]) o2 = NULL;
-    if (!results[0] || !results[1]) {
-        if (results[0]) {
-            adb_host_result_release(results[0]);
-            free(results[0]->payload);
-            free(results[0]);
+    {
+        Shards s1, s2;
+        memset(&s1, 0, sizeof s1);
+        memset(&s2, 0, sizeof s2);
+        s1.n[0] = s2.n[0] = (size_t)m;
+        s1.d[0] = o1;
+        s2.d[0] = o2;
+        for (int g = 1; g < S.G; ++g) {             /* the other contexts hold empty pieces */
+            void *x = NULL, *y = NULL;
+            on_ctx(g);
+            adb_alloc(&x, 0);
+            adb_alloc(&y, 0);
+            s1.d[g] = x;
+            s2.d[g] = y;
         }
-        goto fail;
+        on_ctx(0);
+        o1 = o2 = NULL;
+        results[0] = new_dev_result(&s1);
+        if (!results[0]) {
+            shards_free(&s2);
+            goto fail;
+        }
+        results[1] = new_dev_result(&s2);
+        if (!results[1]) {
+            drop_result(results[0]);
+            goto fail;
+        }
     }
     op_ok(st);
     return results;
@@ -1025,6 +1840,31 @@ static void text_i64(Text *t, long long v) {          /* "%d" / "%ld" without th
     while (k) t->s[t->len++] = buf[--k];
 }
 
+/* device-side "%d\n%d..." of every shard, concatenated */
+typedef struct FormatJob {
+    ShardErr err;
+    int32_t *const *d;
+    const size_t *n;
+    int64_t bytes[MAXG];
+    void *d_text[MAXG];
+    char *dst[MAXG];
+    int phase;
+} FormatJob;
+static void format_shard(int g, void *arg) {
+    FormatJob *a = arg;
+    if (!a->n[g]) return;
+    if (a->phase == 0) {
+        SCK(adb_format_i32_count(a->d[g], (int64_t)a->n[g], &a->bytes[g]));
+        SCK(adb_alloc(&a->d_text[g], (size_t)a->bytes[g]));
+        SCK(adb_format_i32_emit(a->d_text[g]));
+    } else {
+        adb_status s = adb_download(a->dst[g], a->d_text[g], (size_t)a->bytes[g]);
+        adb_free(a->d_text[g]);
+        a->d_text[g] = NULL;
+        if (s != ADB_OK) shard_fail(&a->err, g, "adb_download");
+    }
+}
+
 /* src/query.c:245-304: results are rendered one after another (column-major), values of a
  * result separated by '\n', results separated by ','; ints "%d", longs "%ld", floats and
  * doubles "%.2f".  Device-resident payloads are copied to the host first.  The reference
@@ -1051,21 +1891,45 @@ char *print(Result **results, int result_num, Status *ret_status) {
              * the integers, crosses PCIe and no sprintf runs */
             lock();
             DevResult *e = registry_find(r->payload);
-            const int32_t *d = e ? e->d_ptr : NULL;
+            DevResult dv;
+            if (e) dv = *e;
             unlock();
-            if (d) {
-                int64_t bytes = 0;
-                void *d_text = NULL;
-                if (adb_format_i32_count(d, (int64_t)n, &bytes) != ADB_OK) goto dev_fail;
-                if (text_room(&t, (size_t)bytes)) goto oom;
-                if (adb_alloc(&d_text, (size_t)bytes) != ADB_OK) goto dev_fail;
-                if (adb_format_i32_emit(d_text) != ADB_OK ||
-                    adb_download(t.s + t.len, d_text, (size_t)bytes) != ADB_OK) {
-                    adb_free(d_text);
-                    goto dev_fail;
+            if (e && dv.total >= n) {
+                size_t have[MAXG], left = n;
+                for (int g = 0; g < S.G; ++g) {
+                    have[g] = dv.tuples[g] < left ? dv.tuples[g] : left;
+                    left -= have[g];
                 }
-                adb_free(d_text);
-                t.len += (size_t)bytes;
+                FormatJob job;
+                memset(&job, 0, sizeof job);
+                job.d = dv.d_ptr;
+                job.n = have;
+                run_shards(format_shard, &job);
+                size_t bytes = 0;
+                int pieces = 0;
+                for (int g = 0; g < S.G; ++g)
+                    if (have[g]) { bytes += (size_t)job.bytes[g]; ++pieces; }
+                bytes += pieces ? (size_t)pieces - 1 : 0;            /* '\n' between the shards' texts */
+                int bad = shard_errs(&job.err);
+                if (!bad && text_room(&t, bytes)) bad = 2;
+                if (!bad) {
+                    size_t off = t.len;
+                    int seen = 0;
+                    for (int g = 0; g < S.G; ++g) {
+                        if (!have[g]) continue;
+                        if (seen++) t.s[off++] = '\n';
+                        job.dst[g] = t.s + off;
+                        off += (size_t)job.bytes[g];
+                    }
+                    job.phase = 1;
+                    run_shards(format_shard, &job);
+                    bad = shard_errs(&job.err);
+                    if (!bad) t.len += bytes;
+                } else {
+                    for (int g = 0; g < S.G; ++g) free_on(g, job.d_text[g]);
+                }
+                if (bad == 2) goto oom;
+                if (bad) goto dev_fail;
                 continue;
             }
         }
@@ -1091,7 +1955,6 @@ char *print(Result **results, int result_num, Status *ret_status) {
     op_ok(ret_status);
     return t.s;
 dev_fail:
-    set_err("print: %s", adb_last_error());
     free(t.s);
     return op_fail(ret_status, "print");
 oom:

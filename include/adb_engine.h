@@ -52,6 +52,23 @@ enum {
 /* ---- lifecycle (no reference equivalent; SURVEY.md section 8b "new hooks") ---------- */
 ADB_API adb_status adb_init(int device_ordinal);      /* call from main(), src/server.c:616 */
 ADB_API adb_status adb_shutdown(void);                /* call from shutdown_server(), src/server.c:40 */
+/* Several engine contexts in one process -- one per GPU of the box (north_star: "columns are
+ * row-range partitioned across the 8 B200s of one box"; the reference server is ONE process,
+ * src/server.c:616-656, so its operator API can only reach several GPUs from inside it).
+ * Every entry point of this header works on the calling THREAD's current context (context 0
+ * until adb_ctx_select is called); adb_init() initialises the current context.  Contexts may
+ * share a device, so the multi-shard host path also runs on a 1-GPU box.  A context must only
+ * be driven by one thread at a time.  adb_shutdown() shuts down every context. */
+#define ADB_MAX_CONTEXTS 16
+ADB_API int32_t adb_device_count(void);
+ADB_API adb_status adb_ctx_init(int32_t ctx, int device_ordinal);   /* select + adb_init */
+ADB_API adb_status adb_ctx_select(int32_t ctx);
+ADB_API int32_t adb_ctx_current(void);
+/* the current context's stream waits for everything enqueued so far on other_ctx's stream */
+ADB_API adb_status adb_ctx_wait(int32_t other_ctx);
+/* copy into the current context from a buffer of src_ctx (peer DMA across devices), ordered
+ * after src_ctx's stream */
+ADB_API adb_status adb_copy_from_ctx(void *d_dst, int32_t src_ctx, const void *d_src, size_t bytes);
 ADB_API const char *adb_last_error(void);
 ADB_API const char *adb_version(void);
 ADB_API int adb_sm_count(void);
@@ -83,6 +100,7 @@ ADB_API adb_status adb_mark_elapsed(int32_t from_slot, int32_t to_slot, float *m
 ADB_API adb_status adb_chain_marks(int32_t base_slot);
 /* number of engine kernels launched since adb_init (bench.py's gpu_launches) */
 ADB_API int64_t adb_launch_count(void);
+ADB_API int64_t adb_launch_count_all(void);           /* summed over every context */
 
 /* ---- range select over a base column -- replaces select_column_scan, src/query.c:92-137
  * d_pos_out must hold n int32 (the reference mallocs row_count ints, query.c:94).
@@ -110,11 +128,24 @@ ADB_API adb_status adb_select_count(const int32_t *d_val, int64_t n_max, const i
                             const int32_t *lo, const int32_t *hi, int64_t *d_count,
                             int64_t *h_count);
 ADB_API adb_status adb_select_emit(const int32_t *d_pos_in, int32_t base_pos, int32_t *d_pos_out);
+/* Count phase over rows [base_pos, base_pos + n) of a BASE column (shard).  A base column is
+ * never written by an operator, so the predicate pass may request its first tile while the
+ * previous kernel on the stream is still draining (adb_select_count cannot: its input may be
+ * that kernel's output), and the pending select can be resolved by adb_select_emit_fetch_agg*,
+ * which then emit base_pos + row. */
+ADB_API adb_status adb_select_count_base(const int32_t *d_col, int64_t n, const int32_t *lo, const int32_t *hi,
+                                 int32_t base_pos, int64_t *d_count, int64_t *h_count);
 
 /* ---- fetch (gather) -- replaces fetch_column, src/query.c:223-243
  * d_val_out[i] = d_col[d_pos[i] - base_pos], i < n (n from d_n when non-NULL). */
 ADB_API adb_status adb_fetch(const int32_t *d_col, const int32_t *d_pos, int64_t n_max,
                      const int64_t *d_n, int32_t base_pos, int32_t *d_val_out);
+/* fetch over a column that is row-range sharded across contexts: d_shards is a
+ * HOST array of n_shards device pointers, shard k holding rows [k * shard_rows, (k+1) *
+ * shard_rows); d_pos holds global positions in any order.  Remote shards are read over NVLink
+ * peer memory (adb_peer_connect_local enables the access). */
+ADB_API adb_status adb_fetch_sharded(const int32_t *const *d_shards, int32_t n_shards, int64_t shard_rows,
+                             const int32_t *d_pos, int64_t n_max, const int64_t *d_n, int32_t *d_val_out);
 
 /* ---- aggregates -- replace sum / average / min / max, src/query.c:306-437
  * One pass produces all three partials; sum is int64 (query.c:326-327).  Empty input:
@@ -224,6 +255,19 @@ ADB_API adb_status adb_peer_exchange_pairs(int32_t side, const int32_t *d_val, c
                                            int64_t *h_recv_count, const int32_t **d_recv_val,
                                            const int32_t **d_recv_pos);
 ADB_API adb_status adb_peer_destroy(void);
+/* The same exchange group inside ONE process: contexts 0 .. world-1 become ranks 0 .. world-1.
+ * Mailboxes and receive regions are reached through peer access (cudaDeviceEnablePeerAccess,
+ * plus access to the peers' stream-ordered pools so that columns and results can be read
+ * across devices) instead of IPC handles.  Call from one thread while no other thread drives
+ * a context. */
+ADB_API adb_status adb_peer_connect_local(int32_t world);
+ADB_API adb_status adb_peer_join_connect_local(int64_t cap_pairs);
+/* adb_select_emit_fetch_agg with the exchange riding in the same kernel (the deferred form of
+ * adb_chain_select_fetch_agg_exchange): this context's partial goes to d_part, the table-wide
+ * aggregate to d_out (h_out optional) on every context.  Collective. */
+ADB_API adb_status adb_select_emit_fetch_agg_exchange(const int32_t *d_fetch_col, int32_t *d_pos_out,
+                                              int32_t *d_val_out, adb_agg *d_part, adb_agg *d_out,
+                                              adb_agg *h_out);
 
 /* ---- element-wise add / sub -- replace add / sub, src/query.c:356-390 (int32, wraps) */
 ADB_API adb_status adb_add(const int32_t *d_a, const int32_t *d_b, int64_t n_max, const int64_t *d_n,
@@ -254,6 +298,11 @@ ADB_API adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const in
 ADB_API adb_status adb_shared_select_count(const int32_t *d_col, int64_t n, const int32_t *lows,
                                            const int32_t *highs, int32_t q_count, int64_t *h_counts);
 ADB_API adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity);
+/* count phase over rows [base_pos, base_pos + n) of a column (shard): the emit phase then
+ * writes base_pos + row (global positions of a row-range sharded column) */
+ADB_API adb_status adb_shared_select_count_base(const int32_t *d_col, int64_t n, int32_t base_pos,
+                                                const int32_t *lows, const int32_t *highs, int32_t q_count,
+                                                int64_t *h_counts);
 ADB_API adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *lows,
                                      const int32_t *highs, int32_t q_count, int32_t *d_pos_out,
                                      int64_t stride, int64_t *h_counts);
@@ -287,6 +336,10 @@ typedef struct adb_index adb_index;
 ADB_API adb_status adb_index_create(const int32_t *d_values, const int32_t *d_positions, int64_t n,
                                     int32_t with_btree, adb_index **out);
 ADB_API adb_status adb_index_destroy(adb_index *ix);
+/* `ix` is one slice of an index range-partitioned (by index order) over several contexts: it
+ * answers positions[lb(low) .. lb(high)) of its slice; the caller applies the low == high quirk
+ * of query.c:181-188 to the whole index. */
+ADB_API adb_status adb_index_set_slice(adb_index *ix, int32_t is_slice);
 ADB_API adb_status adb_select_index(const adb_index *ix, int32_t use_btree, const int32_t *lo,
                                     const int32_t *hi, int32_t *d_pos_out, int64_t *d_count,
                                     int64_t *h_count);
@@ -303,6 +356,9 @@ ADB_API adb_status adb_select_index_emit(const adb_index *ix, int32_t *d_pos_out
  * permutes the sibling columns with adb_fetch(sibling, positions) (index.c:105-135). */
 ADB_API adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_values_out,
                                   int32_t *d_positions_out);
+/* ColumnIndex.positions are size_t on the host (src/include/cs165_api.h:65-68) and truncated
+ * to int when emitted (src/query.c:187): d_dst[i] = (int32_t) d_src_u64[i]. */
+ADB_API adb_status adb_narrow_u64_to_i32(const void *d_src_u64, int64_t n, int32_t *d_dst);
 
 /* ---- joins -- replace hash_join + multimap (src/query.c:652-696, src/multimap.c) and
  * nested_loop_join (src/query.c:585-650).  Inputs are two (value, position) pair lists;

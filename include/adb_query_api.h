@@ -143,9 +143,19 @@ bool should_use_index(Column *column, int low, int high);
 extern "C" {
 #endif
 int adb_host_init(int device);                    /* call from main(), src/server.c:616 */
+/* One process, `gpus` GPUs (SURVEY.md 8b `engine_init(int ngpus)`): every column is row-range
+ * sharded over the GPUs, every operator of this header fans out over them and still returns
+ * ONE Result (see the head of host/query_shim.c).  Devices ADB_DEVICE .. ADB_DEVICE+gpus-1,
+ * wrapping around when the box has fewer (contexts then share a device).  Without an explicit
+ * call the shim initialises itself on first use with ADB_GPUS (default 1) GPUs. */
+int adb_host_init_multi(int gpus);
+int adb_host_gpus(void);                          /* 0 before initialisation */
 void adb_host_shutdown(void);                     /* call from shutdown_server(), src/server.c:40 */
 int adb_host_column_upload(Column *column);       /* after load_db + build_index, src/server.c:120-125 */
 int adb_host_column_adopt(Column *column, const void *d_data);   /* rows already in HBM (GPU-side load) */
+/* the same with several GPUs: d_shards[g] (on GPU g) holds rows [g*shard_rows, (g+1)*shard_rows),
+ * shard_rows a multiple of 32 */
+int adb_host_column_adopt_shards(Column *column, const void *const *d_shards, size_t shard_rows);
 void adb_host_column_invalidate(Column *column);  /* after insert_row, src/server.c:250 */
 /* Device-resident results: Result.payload of a position list / value vector is a small
  * malloc'd descriptor, so the plumbing's free(payload) (src/client_context.c:35,82) stays

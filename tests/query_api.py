@@ -69,6 +69,9 @@ OPERATORS = {
 }
 HOOKS = {
     "adb_host_init": (C.c_int, [C.c_int]),
+    "adb_host_init_multi": (C.c_int, [C.c_int]),
+    "adb_host_gpus": (C.c_int, []),
+    "adb_host_column_adopt_shards": (C.c_int, [C.POINTER(Column), C.POINTER(C.c_void_p), C.c_size_t]),
     "adb_host_shutdown": (None, []),
     "adb_host_column_upload": (C.c_int, [C.POINTER(Column)]),
     "adb_host_column_adopt": (C.c_int, [C.POINTER(Column), C.c_void_p]),

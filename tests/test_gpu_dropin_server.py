@@ -23,8 +23,8 @@ def mismatches(ref, b200):
     return [t for t in TESTS if t not in REFERENCE_OUTPUT_UNDEFINED and b200[t] != ref[t]]
 
 
-@pytest.fixture(scope="module")
-def outputs():
+@pytest.fixture(scope="module", params=["1", "3"], ids=["1gpu", "3gpus"])
+def outputs(request):
     """Both pairs replay the suite.  The unmodified client reads a reply with a single recv
     (client.c:127), so a replay can come out truncated on either side for
     reasons that have nothing to do with the operators (seen once in about ten replays during
@@ -33,7 +33,9 @@ def outputs():
     with tempfile.TemporaryDirectory(prefix="adb_ref_") as w1, tempfile.TemporaryDirectory(prefix="adb_b200_") as w2:
         for attempt in range(3):
             ref = H.ServerPair("ref", w1).run_suite(TESTS)
-            b200 = H.ServerPair("b200", w2).run_suite(TESTS)
+            # ADB_GPUS: the unmodified server process drives that many engine contexts (one per
+            # GPU; they share the device on a 1-GPU box), every column sharded over them
+            b200 = H.ServerPair("b200", w2, env={"ADB_GPUS": request.param}).run_suite(TESTS)
             bad = mismatches(ref, b200)
             if not bad:
                 break

@@ -13,10 +13,18 @@ pytestmark = pytest.mark.gpu
 I32MAX = 2**31 - 1
 
 
-@pytest.fixture(scope="module")
-def api():
+@pytest.fixture(scope="module", params=[1, 2, 3], ids=["1gpu", "2gpus", "3gpus"])
+def api(request):
+    """The whole module runs three times: on one GPU, and with every column row-range sharded
+    over 2 and 3 engine contexts driven from ONE process (host/query_shim.c, adb_host_init_multi).
+    On a 1-GPU box the contexts share the device -- same host code, same kernels, same peer
+    exchange, the mailboxes simply live in one HBM."""
     a = Api()
-    assert a.lib.adb_host_init(0) == 0, a.lib.adb_host_last_error()
+    if request.param == 1:
+        assert a.lib.adb_host_init(0) == 0, a.lib.adb_host_last_error()
+    else:
+        assert a.lib.adb_host_init_multi(request.param) == 0, a.lib.adb_host_last_error()
+    assert a.lib.adb_host_gpus() == request.param
     yield a
     a.lib.adb_host_shutdown()
 
@@ -501,3 +509,120 @@ def test_random_walk_over_the_operator_api(api, cpu):
         check(h, m)
         api.drop(h)
     assert api.lib.adb_host_live_device_results() == live0
+
+
+# ---- one process, several GPUs: the cases only a sharded layout has ---------------------------
+def test_sharded_lists_that_are_not_row_aligned(api, cpu, rng):
+    """Position lists in index order, from a join, or built by foreign code name rows of any
+    shard: fetch goes through peer loads (adb_fetch_sharded) and must still be the reference's
+    gather, element for element."""
+    n = 100_003
+    data = rng.integers(0, 5000, n).astype(np.int32)
+    other = rng.integers(-10**6, 10**6, n).astype(np.int32)
+    values, positions = cpu.index_sort(data)
+    col = api.column(data, index=(values, positions), sorted_=True)
+    ocol = api.column(other)
+    s = api.select_column(col, 1000, 1200)
+    exp, undefined = cpu.select_sorted_index(values, positions, 1000, 1200)
+    assert not undefined and np.array_equal(api.tuples(s), exp)
+    f = api.fetch_column(ocol, s)
+    assert np.array_equal(api.tuples(f), other[exp])
+    a = api.sum_result(f)
+    assert int(api.tuples(a)[0]) == int(other[exp].astype(np.int64).sum())
+    s2 = api.select_result(f, s, 0, None)
+    assert np.array_equal(api.tuples(s2), cpu.select_result(other[exp], exp, 0, None))
+    # a host-built list in no order at all
+    perm = rng.permutation(n)[:7777].astype(np.int32)
+    hp = api.host_result(perm)
+    f2 = api.fetch_column(ocol, C.pointer(hp))
+    assert np.array_equal(api.tuples(f2), other[perm])
+    # operands cut differently: f (cut like the index slices) + f3 (cut like the rows)
+    rows = api.select_column(ocol, None, None)
+    f3 = api.fetch_column(ocol, rows)
+    short = api.host_result(np.arange(exp.size, dtype=np.int32))
+    d = api.binary("add", f, C.pointer(short))
+    assert np.array_equal(api.tuples(d), (other[exp].astype(np.int64) + np.arange(exp.size)).astype(np.int32))
+    d2 = api.binary("sub", f, f3)                     # f3 is longer: its head is used (query.c:361)
+    assert np.array_equal(api.tuples(d2), (other[exp].astype(np.int64) - other[:exp.size]).astype(np.int32))
+    for r in (s, f, a, s2, f2, rows, f3, d, d2):
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 65, 200])
+def test_columns_shorter_than_the_shard_grid(api, cpu, rng, n):
+    """Fewer rows than shards x 32: trailing shards are empty and every operator still agrees."""
+    c1 = rng.integers(-50, 50, n).astype(np.int32)
+    c2 = rng.integers(-1000, 1000, n).astype(np.int32)
+    col1, col2 = api.column(c1), api.column(c2)
+    for lo, hi in [(None, None), (-10, 10), (49, None), (7, 7)]:
+        s = api.select_column(col1, lo, hi)
+        epos = cpu.select_scan(c1, lo, hi)
+        f = api.fetch_column(col2, s)
+        a = api.sum_result(f)
+        assert int(api.tuples(a)[0]) == cpu.sum(cpu.fetch(c2, epos))
+        assert np.array_equal(api.tuples(s), epos) and np.array_equal(api.tuples(f), cpu.fetch(c2, epos))
+        if epos.size:
+            mx = api.unary("max", f)
+            assert int(api.tuples(mx)[0]) == cpu.max(cpu.fetch(c2, epos))
+            api.drop(mx)
+        for r in (s, f, a):
+            api.drop(r)
+    tot = api.sum_column(col2)
+    assert int(api.tuples(tot)[0]) == cpu.sum_column(c2)
+    api.drop(tot)
+    res = api.shared_select(col1, [-5, 0, 60], [5, 1, 70])
+    for r, (lo, hi) in zip(res, [(-5, 5), (0, 1), (60, 70)]):
+        assert np.array_equal(api.tuples(r), cpu.select_scan(c1, lo, hi))
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == 0
+
+
+def test_index_quirk_across_slices(api, cpu, rng):
+    """low == high on a key (query.c:181-188) and bounds around slice boundaries of the
+    range-partitioned index: runs of equal keys never straddle a slice, and the quirk is decided
+    for the whole index, not per slice."""
+    n = 9_000
+    data = np.repeat(np.arange(0, 90, dtype=np.int32), 100)            # 90 runs of 100 equal keys
+    rng.shuffle(data)
+    values, positions = cpu.index_sort(data)
+    col = api.column(data, index=(values, positions), sorted_=True)
+    cases = [(k, k) for k in (0, 29, 30, 44, 45, 59, 60, 89)] + [(29, 31), (44, 46), (0, 90), (30, 30), (88, 200)]
+    for lo, hi in cases:
+        s = api.select_column(col, lo, hi)
+        exp, undefined = cpu.select_sorted_index(values, positions, lo, hi)
+        assert not undefined
+        assert np.array_equal(api.tuples(s), exp), (lo, hi)
+        api.drop(s)
+
+
+def test_long_print_across_shards(api, rng):
+    n = 50_000
+    data = rng.integers(-2**31, 2**31 - 1, n, dtype=np.int64).astype(np.int32)
+    col = api.column(data)
+    s = api.select_column(col, None, None)
+    f = api.fetch_column(col, s)
+    assert api.print(f) == "\n".join(str(int(v)) for v in data)
+    api.drop(s), api.drop(f)
+
+
+def test_join_of_sharded_operands(api, cpu, rng):
+    n1, n2 = 70_000, 50_000
+    k1 = rng.integers(1, 30_000, n1).astype(np.int32)
+    k2 = rng.integers(1, 30_000, n2).astype(np.int32)
+    f1 = rng.integers(0, 100, n1).astype(np.int32)
+    f2 = rng.integers(0, 100, n2).astype(np.int32)
+    ck1, ck2, cf1, cf2 = (api.column(x) for x in (k1, k2, f1, f2))
+    p1, p2 = api.select_column(cf1, None, 80), api.select_column(cf2, None, 15)   # milestone4.py:332-339
+    v1, v2 = api.fetch_column(ck1, p1), api.fetch_column(ck2, p2)
+    o1, o2 = api.join("hash_join", v1, p1, v2, p2)
+    e_p1, e_p2 = cpu.select_scan(f1, None, 80), cpu.select_scan(f2, None, 15)
+    e1, e2 = cpu.hash_join(k1[e_p1], e_p1, k2[e_p2], e_p2)
+    assert np.array_equal(api.tuples(o1), e1) and np.array_equal(api.tuples(o2), e2)
+    g1 = api.fetch_column(cf1, o1)                     # join output feeds a fetch (tests 32-37)
+    assert np.array_equal(api.tuples(g1), f1[e1])
+    a = api.unary("average", g1)
+    assert api.tuples(a)[0].tobytes() == np.float64(cpu.avg(f1[e1])).tobytes()
+    for r in (p1, p2, v1, v2, o1, o2, g1, a):
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == 0
