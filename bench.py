@@ -5,10 +5,13 @@ the 4 B-row int32 table of BASELINE.json config 5, row-range partitioned into 8 
 below 2^31 rows) spread over N B200s, aggregate partials combined with an NCCL allreduce.
 
 One "step" = one pass of the chain over every shard of the table on every rank:
-  s = select(tbl.col1, lo, hi)      adb_select_scan   (query.c:92)
-  f = fetch(tbl.col2, s)            adb_fetch         (query.c:223)
-  a = sum(f) / min(f) / max(f)      adb_aggregate     (query.c:325,392,417)
-with the position list and the fetched vector materialised, as the operator API defines.
+  s = select(tbl.col1, lo, hi)      (query.c:92)    } adb_chain_select_fetch_agg: two kernels per
+  f = fetch(tbl.col2, s)            (query.c:223)   } shard -- the predicate pass (mask_kernel), then
+  a = sum(f) / min(f) / max(f)      (query.c:325..) } the expansion with gather + aggregates fused in
+with the position list and the fetched vector still materialised, as the operator API defines
+(`value`, device-timed).  `e2e` is the same chain through the reference's own operator API
+(select_column -> fetch_column -> sum of include/adb_query_api.h) from ONE host process that
+drives all N GPUs (host/query_shim.c), wall clock, every count and sum read back by the host.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            engine arm
   python bench.py --impl reference ...                           reference CPU arm
@@ -35,6 +38,10 @@ N_SHARDS = 8
 SEED = 42
 SPAN = 1 << 30                       # col1 uniform in [0, 2^30)
 FETCH_LO, FETCH_SPAN = 2**31 - 10000, 10000     # col2 near INT_MAX (milestone1.py:119)
+NOMINAL_GBS = 8000.0                # the ~8 TB/s per-GPU figure north_star quotes
+# the e2e leg drives the table as 2 columns of 2 B rows (a reference column holds < 2^31 rows:
+# positions are int, src/query.c:94-95), each row-range sharded over the N GPUs by the shim
+E2E_PARTS, E2E_PART_ROWS = 2, 2_000_000_000
 METRIC = "rows/sec for select+fetch+sum"
 UNIT = "rows/s"
 
@@ -152,13 +159,34 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     ops, kind, what = cpu_ops()
     lo, hi = predicate(args.selectivity)
-    rows = args.cpu_rows
-    sel, fet = host_columns(rows, 0, cores)
+    from oracle import oracle
+    # the whole table, shard by shard (a reference column holds < 2^31 rows: int positions),
+    # regenerated on the host outside the timed region; fewer shards only if RAM is short
+    shard_rows = TOTAL_ROWS // N_SHARDS
+    shards = N_SHARDS if args.cpu_rows <= 0 else max(1, min(N_SHARDS, args.cpu_rows // shard_rows))
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+        shards = max(1, min(shards, int(avail * 0.6) // (8 * shard_rows)))
+    except (ValueError, OSError):
+        pass
+    cols = []
+    for k in range(shards):
+        cols.append((oracle.synth_uniform(shard_rows, SEED, k * shard_rows, 0, SPAN, cores),
+                     oracle.synth_uniform(shard_rows, SEED + 1, k * shard_rows, FETCH_LO, FETCH_SPAN, cores)))
+    rows = shard_rows * shards
+
+    def step():
+        tot = hits = 0
+        for sel, fet in cols:
+            a, b = ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+            tot += a
+            hits += b
+        return tot, hits
     for _ in range(args.warmup):
-        ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        s, h = ops.chain_select_fetch_sum(sel, fet, lo, hi, threads=cores)
+        s, h = step()
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
     line = {
@@ -168,8 +196,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "int32 (int64 accumulate)", "data": "synthetic",
         "config": workload_config(args, rows_per_step=rows),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{rows} rows of the same table per step, one reference "
-                                   f"instance per row range on {cores} threads; {what}"},
+                         "sample": f"{shards} of the table's {N_SHARDS} shards ({rows} rows) per step, one "
+                                   f"reference instance per row range on {cores} threads; {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "check": {"sum": s, "hits": h},
     }
@@ -206,6 +234,9 @@ def run_engine(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side barrier for the legs one rank runs alone (an NCCL barrier would park a
+        # spinning kernel on the GPUs that rank is measuring)
+        args.gloo = dist.new_group(backend="gloo")
     eng = adb.Engine(local)
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)          # engine kernels and NCCL share one stream
@@ -324,6 +355,7 @@ def run_engine(args):
     # column), from CUDA events recorded on the engine stream inside the timed region -------
     peak, peak_src = measured_peak()
     hits_local = [int(r[2].to_host(1, np.int64)[0]) for r in res]
+    par = chain_parity(eng, my_shards, res, shard_rows, lo, hi)     # before anything reuses `res`
     mask_ms, fused_ms = [], []
     if timed_marks:
         for k in range(len(marked_steps)):
@@ -348,6 +380,7 @@ def run_engine(args):
         roofline = {"bound": "hbm", "kernel": "adb::mask_kernel (predicate pass of adb_select_scan / "
                     "adb_chain_select_fetch_agg: column -> 1 bit/row bitmap + per-chunk counts)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "frac_of_nominal_8tbs": achieved / NOMINAL_GBS,
                     "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "share_of_step": float(np.mean(mask_ms) * len(cols) / ms_step),
@@ -376,6 +409,8 @@ def run_engine(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "chain": {"algorithmic_bytes_per_step": chain_bytes, "achieved_gbs": chain_gbs,
                       "frac_of_aggregate_peak": chain_gbs / (peak * max(world, 1)),
+                      "frac_of_nominal": chain_gbs / (NOMINAL_GBS * max(world, 1)),
+                      "nominal_gbs_per_gpu": NOMINAL_GBS,
                       "formula": "4N + 20H (SURVEY.md 8d)"},
             "result": {"sum": g_sum, "count": g_cnt, "min": g_min, "max": g_max},
         }
@@ -416,13 +451,31 @@ def run_engine(args):
     # row-range sharded, pairs hash-routed to their owners, joined locally.
     join_sharded = None
     if world > 1 and not args.no_join:
-        join_sharded = measure_join_sharded(eng, dist, rank, world, local)
+        join_sharded = measure_join_sharded(eng, dist, rank, world, local, args.gloo)
 
-    # ---- e2e and cpu_baseline (rank 0; the CPU leg only at N = 1) ----------------------------
-    e2e = measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
-                      combined, parts)
+    # ---- parity at every N: each rank diffs a window of every shard it owns -- positions and
+    # fetched values of the last timed step -- against the reference's operators run on the same
+    # rows regenerated on the host (numpy twin of the generator), and the table-wide aggregate
+    # against the N-independent constants of the synthetic table
+    if dist is not None:
+        t = torch.tensor([1 if par["ok"] else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        par["ok"] = bool(t.item())
     if rank == 0:
+        line["parity"] = {"chain": par["ok"], "chain_detail": par["detail"],
+                          "join": (join_sharded or {}).get("parity")}
+    if not par["ok"]:
+        raise SystemExit(f"PARITY FAILURE (rank {rank}): {par}")
+    if join_sharded is not None and join_sharded.get("parity") is False:
+        raise SystemExit(f"PARITY FAILURE in the sharded join (rank {rank})")
+
+    # ---- e2e (one host process drives all N GPUs) and cpu_baseline (the CPU leg only at N = 1)
+    e2e = measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, (g_sum, g_cnt))
+    if rank == 0:
+        cold = e2e.pop("cold", None)
         line["e2e"] = e2e
+        if cold is not None:
+            line["e2e_cold"] = cold
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = measure_cpu(args, eng, cols, res, shard_rows, lo, hi)
         if world == 1 and (args.ops or not args.no_join):
@@ -444,8 +497,31 @@ def run_engine(args):
     return 0
 
 
-def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_sum, t_mm,
-                combined, parts):
+def chain_parity(eng, my_shards, res, shard_rows, lo, hi, window=1 << 22):
+    """Oracle check of what the timed chain left in HBM, on this rank's shards: the first
+    `window` rows of every shard are regenerated on the host (numpy twin of the generator) and
+    run through the reference's select -> fetch (oracle/_ref when built, else the restatement);
+    the GPU's position list and value vector must start with exactly those tuples."""
+    from analytical_database_b200 import synth
+    ops, kind, _ = cpu_ops()
+    ok, checked = True, 0
+    for i, s_ in enumerate(my_shards):
+        pos, val, cnt = res[i]
+        h = int(cnt.to_host(1, np.int64)[0])
+        sel = synth.uniform(window, SEED, s_ * shard_rows, 0, SPAN)
+        fet = synth.uniform(window, SEED + 1, s_ * shard_rows, FETCH_LO, FETCH_SPAN)
+        epos = ops.select_scan(sel, lo, hi)
+        evals = ops.fetch(fet, epos)
+        k = epos.size
+        gpos, gval = pos.to_host(min(h, k + 1)), val.to_host(min(h, k + 1))
+        good = h >= k and np.array_equal(gpos[:k], epos) and np.array_equal(gval[:k], evals) and \
+            (h == k or gpos[k] >= window)
+        ok = ok and bool(good)
+        checked += k
+    return {"ok": ok, "detail": f"{len(my_shards)} shards x first {window} rows vs {kind}: {checked} tuples"}
+
+
+def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
     """The same chain through the reference-facing operator API -- the C host drop-in
     (host/query_shim.c -> libadb_query.so) called exactly as src/server.c:137-290 calls
     query.c: select_column(Column*, &lo, &hi) -> fetch_column(Column*, Result*) ->
@@ -454,30 +530,47 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
     the long read back from the scalar Result, and the handles released the way
     client_context.c does.  Wall clock.
 
-    warm: a table is uploaded to HBM once, when the shim first touches it (the reference
-          keeps loaded columns in RAM the same way); the timed steps then move only the
-          bounds down and the counts / sum up.
+    ONE process (rank 0) drives all N GPUs, as the reference's one-process server would
+    (adb_host_init_multi): the table is E2E_PARTS columns of E2E_PART_ROWS rows, every column
+    row-range sharded over the N GPUs by the shim; a select fans out over the shards, the
+    aggregate's partials meet in one exchange over NVLink peer memory inside the kernel that
+    produces them, and the host reads one Result per operator.  The other ranks idle at a host
+    barrier meanwhile.
+
+    warm: a table is in HBM once loaded (the reference keeps loaded columns in RAM the same
+          way); the timed steps then move only the bounds down and the counts / sum up.
     cold: one shard whose two columns live in HOST memory and are invalidated before every
-          step, so each step pays the H2D copy of 2 x 2 GB inside the timed region."""
-    import torch
+          step, so each step pays the H2D copy of 2 x 2 GB inside the timed region (N = 1)."""
+    if rank != 0:
+        dist.barrier(group=args.gloo)           # rank 0 is measuring; wait on the host
+        return None
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import query_api as q                      # ctypes view of include/adb_query_api.h
     api = q.Api()
     L = api.lib
-
-    def make_col(devbuf, host=None):
-        c = q.Column()
-        c.name = b"col"
-        c.row_count = shard_rows
-        if host is not None:
-            c.data = host.ctypes.data_as(C.POINTER(C.c_int))
-        return c
-
-    hcols = []
-    for (c1, c2) in cols:
-        a, b = make_col(c1), make_col(c2)
-        assert L.adb_host_column_adopt(C.byref(a), c1.void()) == 0
-        assert L.adb_host_column_adopt(C.byref(b), c2.void()) == 0
+    G = max(world, 1)
+    if L.adb_host_init_multi(G) != 0:
+        raise SystemExit("adb_host_init_multi: " + L.adb_host_last_error().decode())
+    lib = eng.lib
+    S = E2E_PART_ROWS // G
+    assert S % 32 == 0 and S * G == E2E_PART_ROWS and E2E_PARTS * E2E_PART_ROWS == TOTAL_ROWS
+    bufs, hcols = [], []
+    for p_ in range(E2E_PARTS):
+        pa, pb = (C.c_void_p * G)(), (C.c_void_p * G)()
+        for g in range(G):
+            eng._ck(lib.adb_ctx_select(g))
+            first = p_ * E2E_PART_ROWS + g * S
+            b1 = eng.synth_uniform(S, SEED, first, 0, SPAN)
+            b2 = eng.synth_uniform(S, SEED + 1, first, FETCH_LO, FETCH_SPAN)
+            eng.sync()
+            bufs += [(g, b1), (g, b2)]
+            pa[g], pb[g] = b1.ptr, b2.ptr
+        eng._ck(lib.adb_ctx_select(0))
+        a, b = q.Column(), q.Column()
+        a.name, b.name = b"col1", b"col2"
+        a.row_count = b.row_count = E2E_PART_ROWS
+        assert L.adb_host_column_adopt_shards(C.byref(a), pa, S) == 0, L.adb_host_last_error()
+        assert L.adb_host_column_adopt_shards(C.byref(b), pb, S) == 0, L.adb_host_last_error()
         hcols.append((a, b))
     blo, bhi = C.c_int(lo), C.c_int(hi)
     st = q.Status(99, None)
@@ -498,57 +591,66 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
             api.drop(h_)
         return total, hits
 
-    h_pair = torch.zeros(2, dtype=torch.int64).pin_memory()
-
     def step():
         tot = hits = 0
         for (a, b) in hcols:
             t_, h_ = chain(a, b)
             tot += t_
             hits += h_
-        if dist is not None:
-            # the ranks' host-side sums meet in one all-reduce: one pinned H2D copy down, one
-            # D2H copy back (element-wise tensor writes and .item() cost a launch + sync each)
-            h_pair[0], h_pair[1] = tot, hits
-            t_sum.copy_(h_pair, non_blocking=True)
-            dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
-            h_pair.copy_(t_sum)
-            tot, hits = int(h_pair[0]), int(h_pair[1])
         return tot, hits
 
+    def sync_all():
+        for g in range(G):
+            lib.adb_ctx_select(g)
+            eng.sync()
+        lib.adb_ctx_select(0)
+
     steps = max(3, min(args.steps, 10))
+    l0 = lib.adb_launch_count_all()
     for _ in range(2):
         step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sync_all()
     t0 = time.perf_counter()
     for _ in range(steps):
         tot, hits = step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
+    sync_all()
     dt = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    rows_step = shard_rows * len(cols) * max(world, 1)
+    launches = (lib.adb_launch_count_all() - l0) // (steps + 2)
+    rows_step = E2E_PARTS * E2E_PART_ROWS
+    if (tot, hits) != tuple(expect) and not args.shards_limit:
+        raise SystemExit(f"PARITY FAILURE: e2e chain {(tot, hits)} != device-resident chain {tuple(expect)}")
     out = {"value": rows_step * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": 16 if dist is not None else 0,
-           "d2h_bytes_per_step": (8 + 24) * len(cols) + (16 if dist is not None else 0),
-           "ms_per_step": 1e3 * dt / steps, "steps": steps,
-           "api": "select_column -> fetch_column -> sum of include/adb_query_api.h "
-                  "(libadb_query.so = host/query_shim.c), one call chain per shard",
+           "h2d_bytes_per_step": 0,
+           "d2h_bytes_per_step": (8 * G + 24) * E2E_PARTS,
+           "ms_per_step": 1e3 * dt / steps, "steps": steps, "gpu_launches_per_step": int(launches),
+           "host_processes": 1, "gpus_driven": G,
+           "api": "select_column -> fetch_column -> sum of include/adb_query_api.h (libadb_query.so = "
+                  f"host/query_shim.c, adb_host_init_multi({G})): one call chain per column of "
+                  f"{E2E_PART_ROWS} rows, each column row-range sharded over the {G} GPU(s) by the shim",
            "mode": "warm: columns HBM-resident after load; bounds travel as kernel arguments "
-                   "(no H2D copy); per shard the host reads num_tuples (8 B) after select and "
-                   "the aggregate (24 B) after sum; wall clock; see `cold` for the H2D-inclusive figure",
-           "check": {"sum": tot, "hits": hits}}
+                   "(no H2D copy); per column the host reads every shard's num_tuples (8 B) after select "
+                   "and the exchanged aggregate (24 B) after sum; wall clock; see `e2e_cold` for the "
+                   "H2D-inclusive figure",
+           "check": {"sum": tot, "hits": hits, "equals_device_resident_chain": True}}
+    for g, b in bufs:
+        lib.adb_ctx_select(g)
+        b.free()
+    lib.adb_ctx_select(0)
+    for (a, b) in hcols:
+        L.adb_host_column_invalidate(C.byref(a))
+        L.adb_host_column_invalidate(C.byref(b))
     # cold: HOST columns, re-uploaded by the shim inside every timed step
-    if rank == 0 and world == 1 and not args.no_cold:
+    if world == 1 and not args.no_cold:
         c1, c2 = cols[0]
         h1, h2 = c1.to_host(shard_rows), c2.to_host(shard_rows)
-        a, b = make_col(c1, h1), make_col(c2, h2)
+
+        def host_col(host):
+            c = q.Column()
+            c.name = b"col"
+            c.row_count = shard_rows
+            c.data = host.ctypes.data_as(C.POINTER(C.c_int))
+            return c
+        a, b = host_col(h1), host_col(h2)
         chain(a, b)                                         # first touch
         reps = 3
         t0 = time.perf_counter()
@@ -566,13 +668,12 @@ def measure_e2e(args, eng, cols, res, shard_rows, lo, hi, world, dist, rank, t_s
                                  "shim uploads both inside every timed step (pageable memory staged "
                                  "through the engine's pinned multi-lane pipeline, adb_upload)",
                        "check": {"sum": ctot, "hits": chits}}
-    for (a, b) in hcols:
-        L.adb_host_column_invalidate(C.byref(a))
-        L.adb_host_column_invalidate(C.byref(b))
+    if dist is not None:
+        dist.barrier(group=args.gloo)
     return out
 
 
-def measure_join_sharded(eng, dist, rank, world, local):
+def measure_join_sharded(eng, dist, rank, world, local, args_gloo):
     """BASELINE config 4: hash join of two 100 M-row tables with selective prefilters, both
     row-range sharded over the ranks, pairs hash-routed by key and pushed into the destination
     ranks' memory over NVLink (adb_peer_exchange_pairs), joined locally; the NCCL all-to-all-v
@@ -586,10 +687,11 @@ def measure_join_sharded(eng, dist, rank, world, local):
     b, e = shard_range(n, rank, world)
     rows = e - b
 
-    def col(seed, lo, span):
-        t = torch.empty(rows, dtype=torch.int32, device=dev)
+    def col(seed, lo, span, first=None, count=None):
+        first, count = (b, rows) if first is None else (first, count)
+        t = torch.empty(count, dtype=torch.int32, device=dev)
         eng._ck(eng.lib.adb_synth_uniform(C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_int32)),
-                                          rows, seed, b, lo, span))
+                                          count, seed, first, lo, span))
         return t
     t1 = ShardedTable(ops, {"k": col(11, 1, n), "f": col(13, 0, 1000)}, n, dist)
     t2 = ShardedTable(ops, {"k": col(12, 1, n), "f": col(14, 0, 1000)}, n, dist)
@@ -612,6 +714,37 @@ def measure_join_sharded(eng, dist, rank, world, local):
         m = torch.tensor([o1.numel()], dtype=torch.int64, device=dev)
         dist.all_reduce(m, op=dist.ReduceOp.SUM)
         return float(t.item()), int(m.item())
+
+    # parity: the same sharded join on two 2 M-row tables, its pair set (gathered on rank 0)
+    # against the reference's hash_join on the same rows regenerated on the host
+    ns = 2_000_000
+    sb, se = shard_range(ns, rank, world)
+    s1t = ShardedTable(ops, {"k": col(21, 1, ns, sb, se - sb), "f": col(23, 0, 1000, sb, se - sb)}, ns, dist)
+    s2t = ShardedTable(ops, {"k": col(22, 1, ns, sb, se - sb), "f": col(24, 0, 1000, sb, se - sb)}, ns, dist)
+    q1, q2 = s1t.select("f", None, 800), s2t.select("f", None, 150)
+    w1, w2 = s1t.fetch("k", q1), s2t.fetch("k", q2)
+    j1, j2 = s1t.hash_join(w1, q1.local + q1.base, w2, q2.local + q2.base)
+    mine = np.stack([j1.cpu().numpy(), j2.cpu().numpy()], axis=1) if j1.numel() else np.zeros((0, 2), np.int32)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=args_gloo)
+    out["parity"] = None
+    if rank == 0:
+        from analytical_database_b200 import synth
+        cpu, kind, _ = cpu_ops()
+        k1, f1 = synth.uniform(ns, 21, 0, 1, ns), synth.uniform(ns, 23, 0, 0, 1000)
+        k2, f2 = synth.uniform(ns, 22, 0, 1, ns), synth.uniform(ns, 24, 0, 0, 1000)
+        e1, e2 = cpu.select_scan(f1, None, 800), cpu.select_scan(f2, None, 150)
+        r1, r2 = cpu.hash_join(k1[e1], e1, k2[e2], e2)
+        got = np.concatenate(gathered)
+        exp = np.stack([r1, r2], axis=1)
+        got = got[np.lexsort((got[:, 0], got[:, 1]))]
+        exp = exp[np.lexsort((exp[:, 0], exp[:, 1]))]
+        out["parity"] = bool(got.shape == exp.shape and np.array_equal(got, exp))
+        out["parity_detail"] = f"2M x 2M rows, prefilters 0.8 / 0.15, {exp.shape[0]} pairs as a sorted set vs {kind}"
+    flag = torch.tensor([1 if out["parity"] in (None, True) else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        out["parity"] = False
 
     for s1, s2 in ((0.8, 0.15), (1.0, 1.0)):
         p1, p2 = t1.select("f", None, int(1000 * s1)), t2.select("f", None, int(1000 * s2))
@@ -748,7 +881,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--selectivity", type=float, default=0.01)
-    ap.add_argument("--cpu-rows", type=int, default=500_000_000)
+    ap.add_argument("--cpu-rows", type=int, default=500_000_000,
+                    help="rows of the cpu_baseline sample of the engine arm; the reference arm runs the "
+                         "whole table unless --cpu-rows is given explicitly there (0 = whole table)")
     ap.add_argument("--shards-limit", type=int, default=0, help="debug: fewer shards per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
@@ -764,6 +899,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     quiet_stdout()
     if args.impl == "reference":
+        if "--cpu-rows" not in sys.argv:
+            args.cpu_rows = 0
         return run_reference(args)
     return run_engine(args)
 

@@ -442,3 +442,42 @@ ORC_API int64_t orc_print_i32(const int32_t *v, int64_t n, char *out, int64_t ca
     }
     return index;
 }
+
+
+/* ---- synthetic columns for the CPU arm of bench.py (not an operator: the counter-based
+ * generator of analytical-database_b200/synth.py, restated in C so that the reference arm can
+ * regenerate the whole 4 B-row table on the host in seconds) ------------------------------- */
+static inline uint64_t orc_mix64(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+typedef struct {
+    int32_t *out;
+    int64_t n;
+    uint64_t seed, first_row;
+    int32_t lo;
+    uint32_t span;
+} orc_synth_job;
+static void *orc_synth_worker(void *arg) {
+    orc_synth_job *j = arg;
+    for (int64_t i = 0; i < j->n; ++i) {
+        const uint64_t z = orc_mix64(j->seed, j->first_row + (uint64_t)i);
+        j->out[i] = (int32_t)((uint32_t)j->lo + (uint32_t)(((z >> 32) * (uint64_t)j->span) >> 32));
+    }
+    return NULL;
+}
+ORC_API void orc_synth_uniform_mt(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
+                                  uint32_t span, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t tid[256];
+    orc_synth_job jobs[256];
+    for (int t = 0; t < threads; ++t) {
+        const int64_t b = n * t / threads, e = n * (t + 1) / threads;
+        jobs[t] = (orc_synth_job){out + b, e - b, seed, first_row + (uint64_t)b, lo, span};
+        pthread_create(&tid[t], NULL, orc_synth_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(tid[t], NULL);
+}

@@ -236,6 +236,18 @@ class CpuOps:
         return int(s), int(hits.value)
 
 
+def synth_uniform(n: int, seed: int, first_row: int, lo: int, span: int, threads: int = 1) -> np.ndarray:
+    """The generator of analytical-database_b200/synth.py on `threads` host threads (C, in
+    liboracle.so): input regeneration for the CPU arm of bench.py at full table size."""
+    lib = port().lib
+    fn = lib.orc_synth_uniform_mt
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32, C.c_int]
+    out = np.empty(n, dtype=np.int32)
+    fn(out.ctypes.data_as(C.c_void_p), n, seed, first_row, lo, span, threads)
+    return out
+
+
 _cache: dict = {}
 
 

@@ -403,7 +403,11 @@ def test_deferred_select_survives_a_foreign_engine_select(api, cpu, rng):
     f = api.fetch_column(col4, s)
     stolen = eng.alloc_i32(epos.size)
     eng._ck(eng.lib.adb_select_emit(None, 0, stolen.i32()))
-    assert np.array_equal(stolen.to_host(epos.size), epos)
+    # (the foreign caller sits on context 0: with several GPUs it steals the first shard's rows)
+    G = api.lib.adb_host_gpus()
+    shard_rows = ((n + G - 1) // G + 31) // 32 * 32
+    m = int(np.searchsorted(epos, shard_rows)) if G > 1 else epos.size
+    assert np.array_equal(stolen.to_host(epos.size)[:m], epos[:m])
     a = api.unary("max", f)
     assert int(api.tuples(a)[0]) == cpu.max(evals)
     assert np.array_equal(api.tuples(s), epos) and np.array_equal(api.tuples(f), evals)
@@ -517,6 +521,7 @@ def test_sharded_lists_that_are_not_row_aligned(api, cpu, rng):
     shard: fetch goes through peer loads (adb_fetch_sharded) and must still be the reference's
     gather, element for element."""
     n = 100_003
+    live0 = api.lib.adb_host_live_device_results()
     data = rng.integers(0, 5000, n).astype(np.int32)
     other = rng.integers(-10**6, 10**6, n).astype(np.int32)
     values, positions = cpu.index_sort(data)
@@ -546,12 +551,13 @@ def test_sharded_lists_that_are_not_row_aligned(api, cpu, rng):
     assert np.array_equal(api.tuples(d2), (other[exp].astype(np.int64) - other[:exp.size]).astype(np.int32))
     for r in (s, f, a, s2, f2, rows, f3, d, d2):
         api.drop(r)
-    assert api.lib.adb_host_live_device_results() == 0
+    assert api.lib.adb_host_live_device_results() == live0
 
 
 @pytest.mark.parametrize("n", [1, 31, 33, 65, 200])
 def test_columns_shorter_than_the_shard_grid(api, cpu, rng, n):
     """Fewer rows than shards x 32: trailing shards are empty and every operator still agrees."""
+    live0 = api.lib.adb_host_live_device_results()
     c1 = rng.integers(-50, 50, n).astype(np.int32)
     c2 = rng.integers(-1000, 1000, n).astype(np.int32)
     col1, col2 = api.column(c1), api.column(c2)
@@ -575,7 +581,7 @@ def test_columns_shorter_than_the_shard_grid(api, cpu, rng, n):
     for r, (lo, hi) in zip(res, [(-5, 5), (0, 1), (60, 70)]):
         assert np.array_equal(api.tuples(r), cpu.select_scan(c1, lo, hi))
         api.drop(r)
-    assert api.lib.adb_host_live_device_results() == 0
+    assert api.lib.adb_host_live_device_results() == live0
 
 
 def test_index_quirk_across_slices(api, cpu, rng):
@@ -608,6 +614,7 @@ def test_long_print_across_shards(api, rng):
 
 def test_join_of_sharded_operands(api, cpu, rng):
     n1, n2 = 70_000, 50_000
+    live0 = api.lib.adb_host_live_device_results()
     k1 = rng.integers(1, 30_000, n1).astype(np.int32)
     k2 = rng.integers(1, 30_000, n2).astype(np.int32)
     f1 = rng.integers(0, 100, n1).astype(np.int32)
@@ -625,4 +632,4 @@ def test_join_of_sharded_operands(api, cpu, rng):
     assert api.tuples(a)[0].tobytes() == np.float64(cpu.avg(f1[e1])).tobytes()
     for r in (p1, p2, v1, v2, o1, o2, g1, a):
         api.drop(r)
-    assert api.lib.adb_host_live_device_results() == 0
+    assert api.lib.adb_host_live_device_results() == live0
