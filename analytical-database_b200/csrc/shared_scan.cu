@@ -527,7 +527,11 @@ SharedScanGeom shared_scan_geom(uint32_t n, int sm_count) {
 int launch_shared_classify(const int32_t *val, uint32_t n, const SharedScanPlan &plan,
                            const SharedScanGeom &g, uint32_t *hitlist, uint32_t *chunk_hits,
                            uint32_t *counts, int64_t *totals, cudaStream_t s) {
-    static bool attr_set = false;
+    // function attributes are per device: one flag per device the engine has launched on
+    static bool attr_set_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &attr_set = attr_set_dev[dev & 63];
     if (!attr_set) {
         cudaFuncSetAttribute(ss_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsShared));
         cudaFuncSetAttribute(ss_classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsShared));

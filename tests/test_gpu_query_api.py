@@ -512,7 +512,9 @@ def test_random_walk_over_the_operator_api(api, cpu):
     for h, m in pos:
         check(h, m)
         api.drop(h)
-    assert api.lib.adb_host_live_device_results() == live0
+    # (<=: entries an earlier test leaked on purpose -- payloads freed behind the shim's back --
+    # may have been reclaimed meanwhile, when malloc handed their addresses out again)
+    assert api.lib.adb_host_live_device_results() <= live0
 
 
 # ---- one process, several GPUs: the cases only a sharded layout has ---------------------------
