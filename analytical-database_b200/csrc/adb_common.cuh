@@ -379,6 +379,11 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
 int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
                           uint32_t span, int sm_count, cudaStream_t s);
 int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s);
+int launch_iota(int32_t *out, int64_t n, int32_t first, int sm_count, cudaStream_t s);
+int launch_widen_i32(const int32_t *src, int64_t n, unsigned long long *dst, int sm_count, cudaStream_t s);
+// counts: 128 uint64 (zeroed by the launcher)
+int launch_histogram(const int32_t *v, int64_t n, int32_t vmin, int32_t bin_size, unsigned long long *counts,
+                     int sm_count, cudaStream_t s);
 constexpr int kAggMaxBlocks = 148 * 8;
 int launch_agg_combine_allreduce(const PeerExchange &px, cudaStream_t s);
 

@@ -2032,6 +2032,38 @@ adb_status adb_narrow_u64_to_i32(const void *d_src_u64, int64_t n, int32_t *d_ds
     return after_launch("narrow_u64", k_);
 }
 
+adb_status adb_iota_i32(int32_t *d_out, int64_t n, int32_t first) {
+    NEED_UP();
+    if (adb_status s = check_len(n, "adb_iota_i32")) return s;
+    if (n > 0 && !d_out) return fail(ADB_ERR_INVALID, "adb_iota_i32: NULL output");
+    return after_launch("iota", adb::launch_iota(d_out, n, first, g.sm_count, g.stream));
+}
+
+// d_dst[i] = (size_t) d_src[i]; d_src == NULL: d_dst[i] = i (identity positions of a clustered index)
+adb_status adb_widen_i32_to_u64(const int32_t *d_src, int64_t n, void *d_dst_u64) {
+    NEED_UP();
+    if (n < 0 || (n > 0 && !d_dst_u64)) return fail(ADB_ERR_INVALID, "adb_widen_i32_to_u64: bad arguments");
+    if (n == 0) return ADB_OK;
+    const int k_ = adb::launch_widen_i32(d_src, n, static_cast<unsigned long long *>(d_dst_u64), g.sm_count, g.stream);
+    return after_launch("widen_i32", k_);
+}
+
+// build_histogram, src/index.c:63-84: h_counts[b] = rows with (v - vmin) / bin_size == b, b < 100.
+adb_status adb_histogram_i32(const int32_t *d_val, int64_t n, int32_t vmin, int32_t bin_size, uint64_t *h_counts) {
+    NEED_UP();
+    if (adb_status s = check_len(n, "adb_histogram_i32")) return s;
+    if (bin_size <= 0 || !h_counts || (n > 0 && !d_val)) return fail(ADB_ERR_INVALID, "adb_histogram_i32: bad arguments");
+    void *d = nullptr;
+    if (adb_status s = adb_alloc(&d, 128 * sizeof(unsigned long long))) return s;
+    const int k_ = adb::launch_histogram(d_val, n, vmin, bin_size, static_cast<unsigned long long *>(d), g.sm_count, g.stream);
+    adb_status rc = after_launch("histogram", k_);
+    unsigned long long host[128];
+    if (rc == ADB_OK) rc = adb_download(host, d, sizeof host);
+    adb_free(d);
+    if (rc == ADB_OK) for (int b = 0; b < 100; ++b) h_counts[b] = host[b];
+    return rc;
+}
+
 adb_status adb_synth_uniform(int32_t *d_out, int64_t n, uint64_t seed, uint64_t first_row,
                              int32_t lo, uint32_t span) {
     NEED_UP();

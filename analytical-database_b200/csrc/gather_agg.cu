@@ -203,6 +203,40 @@ narrow_u64_kernel(const unsigned long long *__restrict__ src, int64_t n, int32_t
         dst[i] = (int32_t)src[i];
 }
 
+// int32 -> size_t (what ColumnIndex.positions holds on the host, cs165_api.h:65-68); with
+// iota the source is the row number itself (a clustered index keeps identity positions,
+// index.c:89-101,119-135)
+__global__ void __launch_bounds__(STREAM_THREADS)
+widen_i32_kernel(const int32_t *__restrict__ src, int64_t n, unsigned long long *__restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = src ? (unsigned long long)(uint32_t)src[i] : (unsigned long long)i;
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+iota_kernel(int32_t *__restrict__ out, int64_t n, int32_t first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = first + (int32_t)i;
+}
+
+// ---- the 100-bin histogram of build_histogram (src/index.c:63-84): bin = (v - min) / bin_size ----
+constexpr int HIST_BINS = 128;                           // the reference keeps BIN_NUM = 100
+__global__ void __launch_bounds__(STREAM_THREADS)
+histogram_kernel(const int32_t *__restrict__ v, int64_t n, int32_t vmin, int32_t bin_size,
+                 unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int s_c[HIST_BINS];
+    if (threadIdx.x < HIST_BINS) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // the reference computes this in int: (data - min) wraps like its subtraction does
+        const int32_t bin = (int32_t)((uint32_t)ld_stream(v + i) - (uint32_t)vmin) / bin_size;
+        if (bin >= 0 && bin < HIST_BINS) atomicAdd(&s_c[bin], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < HIST_BINS && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+
 // ---- launchers ------------------------------------------------------------------------------
 static int stream_grid(int64_t work_items, int sm_count, int per_sm) {
     const int64_t want = (work_items + STREAM_THREADS - 1) / STREAM_THREADS;
@@ -253,6 +287,26 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
 int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s) {
     if (n <= 0) return 0;
     narrow_u64_kernel<<<stream_grid(n / 2 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(src, n, dst);
+    return 1;
+}
+
+int launch_widen_i32(const int32_t *src, int64_t n, unsigned long long *dst, int sm_count, cudaStream_t s) {
+    if (n <= 0) return 0;
+    widen_i32_kernel<<<stream_grid(n / 2 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(src, n, dst);
+    return 1;
+}
+
+int launch_iota(int32_t *out, int64_t n, int32_t first, int sm_count, cudaStream_t s) {
+    if (n <= 0) return 0;
+    iota_kernel<<<stream_grid(n / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(out, n, first);
+    return 1;
+}
+
+int launch_histogram(const int32_t *v, int64_t n, int32_t vmin, int32_t bin_size, unsigned long long *counts,
+                     int sm_count, cudaStream_t s) {
+    cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * HIST_BINS, s);
+    if (n <= 0) return 0;
+    histogram_kernel<<<stream_grid(n / 8 + 1, sm_count, 4), STREAM_THREADS, 0, s>>>(v, n, vmin, bin_size, counts);
     return 1;
 }
 

@@ -178,6 +178,9 @@ class Engine:
         "adb_shared_select_count_base": (C.c_int32, [_I32P, C.c_int64, C.c_int32, _I32P, _I32P, C.c_int32, _I64P]),
         "adb_index_set_slice": (C.c_int32, [C.c_void_p, C.c_int32]),
         "adb_narrow_u64_to_i32": (C.c_int32, [C.c_void_p, C.c_int64, _I32P]),
+        "adb_widen_i32_to_u64": (C.c_int32, [_I32P, C.c_int64, C.c_void_p]),
+        "adb_iota_i32": (C.c_int32, [_I32P, C.c_int64, C.c_int32]),
+        "adb_histogram_i32": (C.c_int32, [_I32P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     }
 
     def __init__(self, device: int = 0):

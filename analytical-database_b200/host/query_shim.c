@@ -697,6 +697,7 @@ static void index_shard(int g, void *arg) {
     if (S.G > 1) SCK(adb_index_set_slice(c->ix[g], 1));
 }
 
+static int slice_bounds(DevColumn *c, const int *v, size_t n);
 static int dev_index(DevColumn *c, Column *column) {
     if (!column->index || !column->index->values || !column->index->positions) {
         set_err("column '%s' is flagged clustered/has_index but carries no ColumnIndex", column->name);
@@ -706,8 +707,37 @@ static int dev_index(DevColumn *c, Column *column) {
     dev_index_drop(c);
     const size_t n = column->row_count;
     const int *v = column->index->values;
-    /* slice boundaries: an even split by index order, moved forward to the end of a run of
-     * equal keys (a run inside one slice keeps every slice's lookup independent) */
+    slice_bounds(c, v, n);
+    IndexJob job;
+    memset(&job, 0, sizeof job);
+    job.c = c;
+    job.column = column;
+    run_shards(index_shard, &job);
+    if (shard_errs(&job.err)) {
+        dev_index_drop(c);
+        return -1;
+    }
+    c->host_ix_values = column->index->values;
+    c->ix_rows = n;
+    return 0;
+}
+
+/* ---- index build on the engine (src/index.c:25-178) --------------------------------------------
+ * build_unclustered_index: (values ascending, positions) of the column; build_clustered_index:
+ * the same sort on a COPY, every other column of the table permuted into that order, the
+ * indexed column's own data and its index->positions (identity) left untouched.
+ * Here the sort is the engine's stable LSD radix sort (adb_index_sort): ties come out in
+ * ascending row order where the reference's unstable quicksort leaves another order
+ *  -- identical whenever the keys are unique.  The host arrays the catalog owns
+ * (ColumnIndex.values / .positions, the siblings' data) are filled from the device, because the
+ * unchanged plumbing persists them at shutdown (src/db_manager.c:396-397); the device-side
+ * index slices are installed directly, so the first select re-uploads nothing.
+ *
+ * cols[0 .. n_cols) are the table's columns in declaration order, `which` the indexed one
+ * (its sorted / clustered flags say what to build).  The sort itself runs on context 0 (a
+ * global sort; SURVEY.md 8e: "clustered index build: does not shard"); the sibling permutation
+ * is one peer gather per GPU. */
+static int slice_bounds(DevColumn *c, const int *v, size_t n) {
     const size_t per = (n + (size_t)S.G - 1) / (size_t)S.G;
     c->ix_begin[0] = 0;
     for (int g = 1; g <= S.G; ++g) {
@@ -729,17 +759,214 @@ static int dev_index(DevColumn *c, Column *column) {
         c->ix_begin[g] = b;
     }
     c->ix_min = n ? v[0] : 0;
-    IndexJob job;
-    memset(&job, 0, sizeof job);
-    job.c = c;
-    job.column = column;
-    run_shards(index_shard, &job);
-    if (shard_errs(&job.err)) {
-        dev_index_drop(c);
+    return 0;
+}
+
+typedef struct PermuteJob {
+    ShardErr err;
+    DevColumn *sib;
+    const int32_t *order0;      /* sorted positions, on context 0 */
+    int *host_out;
+    int32_t *fresh[MAXG];
+} PermuteJob;
+static void permute_shard(int g, void *arg) {
+    PermuteJob *a = arg;
+    DevColumn *c = a->sib;
+    const size_t n = shard_len(c->rows, c->shard_rows, g);
+    void *ord = NULL, *out = NULL;
+    SCK(adb_alloc(&out, 4 * n));
+    a->fresh[g] = out;
+    if (!n) return;
+    SCK(adb_alloc(&ord, 4 * n));
+    if (adb_copy_from_ctx(ord, 0, a->order0 + (size_t)g * c->shard_rows, 4 * n) != ADB_OK ||
+        (S.G == 1 ? adb_fetch(c->d_data[0], ord, (int64_t)n, NULL, 0, out)
+                  : adb_fetch_sharded((const int32_t *const *)c->d_data, S.G, (int64_t)c->shard_rows, ord,
+                                      (int64_t)n, NULL, out)) != ADB_OK ||
+        adb_download(a->host_out + (size_t)g * c->shard_rows, out, 4 * n) != ADB_OK)
+        shard_fail(&a->err, g, "clustered index: sibling permutation");
+    adb_free(ord);
+}
+
+typedef struct SliceJob {
+    ShardErr err;
+    DevColumn *c;
+    const int32_t *vals0, *poss0;       /* on context 0; poss0 NULL = identity */
+    int with_btree;
+} SliceJob;
+static void slice_shard(int g, void *arg) {
+    SliceJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t b = c->ix_begin[g], n = c->ix_begin[g + 1] - b;
+    void *dv = NULL, *dp = NULL;
+    SCK(adb_alloc(&dv, 4 * n));
+    c->d_ix_values[g] = dv;
+    SCK(adb_alloc(&dp, 4 * n));
+    c->d_ix_positions[g] = dp;
+    SCK(adb_copy_from_ctx(dv, 0, a->vals0 + b, 4 * n));
+    if (a->poss0) SCK(adb_copy_from_ctx(dp, 0, a->poss0 + b, 4 * n));
+    else SCK(adb_iota_i32(dp, (int64_t)n, (int32_t)b));
+    SCK(adb_index_create(dv, dp, (int64_t)n, a->with_btree, &c->ix[g]));
+    if (S.G > 1) SCK(adb_index_set_slice(c->ix[g], 1));
+    SCK(adb_sync());                    /* the sort buffers on context 0 are released next */
+}
+
+int adb_host_index_build(Column **cols, int n_cols, int which) {
+    t_err[0] = '\0';
+    if (ensure_up()) return -1;
+    if (!cols || which < 0 || which >= n_cols || !cols[which]) {
+        set_err("adb_host_index_build: bad arguments");
         return -1;
     }
+    Column *column = cols[which];
+    const size_t n = column->row_count;
+    if (flush_pending()) return -1;
+    DevColumn *c = dev_column(column);
+    if (!c) return -1;
+    int rc = -1;
+    int32_t *all = NULL, *vals = NULL, *poss = NULL;
+    void *wide = NULL;
+    ColumnIndex *ix = NULL;
+    int own_all = 0;
+    /* the whole column on context 0 */
+    if (S.G == 1) {
+        all = c->d_data[0];
+    } else {
+        void *p = NULL;
+        if (adb_alloc(&p, 4 * n) != ADB_OK) goto dev_fail;
+        all = p;
+        own_all = 1;
+        for (int g = 0; g < S.G; ++g) {
+            const size_t len = shard_len(c->rows, c->shard_rows, g);
+            if (len && adb_copy_from_ctx(all + (size_t)g * c->shard_rows, g, c->d_data[g], 4 * len) != ADB_OK)
+                goto dev_fail;
+        }
+    }
+    {
+        void *p = NULL, *q = NULL;
+        if (adb_alloc(&p, 4 * n) != ADB_OK || adb_alloc(&q, 4 * n) != ADB_OK) {
+            if (p) adb_free(p);
+            goto dev_fail;
+        }
+        vals = p;
+        poss = q;
+    }
+    if (adb_index_sort(all, (int64_t)n, vals, poss) != ADB_OK) goto dev_fail;
+    /* the catalog's host copy (plain malloc: release_index frees it, db_manager.c:614-626) */
+    ix = malloc(sizeof *ix);
+    if (ix) {
+        ix->values = malloc(n ? n * sizeof(int) : 1);
+        ix->positions = malloc(n ? n * sizeof(size_t) : 1);
+    }
+    if (!ix || !ix->values || !ix->positions) {
+        set_err("out of host memory for the index of %zu rows", n);
+        goto fail;
+    }
+    if (n) {
+        if (adb_alloc(&wide, 8 * n) != ADB_OK) goto dev_fail;
+        if (adb_download(ix->values, vals, 4 * n) != ADB_OK ||
+            adb_widen_i32_to_u64(column->clustered ? NULL : poss, (int64_t)n, wide) != ADB_OK ||
+            adb_download(ix->positions, wide, 8 * n) != ADB_OK)
+            goto dev_fail;
+        adb_free(wide);
+        wide = NULL;
+    }
+    if (column->clustered) {
+        /* every OTHER column (by name, index.c:128-133) moves into index order */
+        for (int j = 0; j < n_cols; ++j) {
+            Column *sib = cols[j];
+            if (!sib || strcmp(sib->name, column->name) == 0) continue;
+            if (sib->row_count != n) {
+                set_err("clustered index: column '%s' has %zu rows, '%s' has %zu", sib->name, sib->row_count,
+                        column->name, n);
+                goto fail;
+            }
+            DevColumn *dc = dev_column(sib);
+            c = dev_column_slot(column);            /* the registry may have moved */
+            if (!dc || !c) goto fail;
+            if (dc->adopted) {
+                set_err("clustered index: column '%s' lives in caller-owned device memory", sib->name);
+                goto fail;
+            }
+            PermuteJob job;
+            memset(&job, 0, sizeof job);
+            job.sib = dc;
+            job.order0 = poss;
+            job.host_out = sib->data;               /* in place: the mmap is the catalog's truth */
+            run_shards(permute_shard, &job);
+            if (shard_errs(&job.err)) {
+                for (int g = 0; g < S.G; ++g) free_on(g, job.fresh[g]);
+                goto fail;
+            }
+            sync_all();                             /* every gather has read the old shards */
+            for (int g = 0; g < S.G; ++g) {
+                free_on(g, dc->d_data[g]);
+                dc->d_data[g] = job.fresh[g];
+            }
+        }
+    }
+    /* device-side index slices, cut by index order */
+    dev_index_drop(c);
+    slice_bounds(c, ix->values, n);
+    {
+        SliceJob job;
+        memset(&job, 0, sizeof job);
+        job.c = c;
+        job.vals0 = vals;
+        job.poss0 = column->clustered ? NULL : poss;
+        job.with_btree = !column->sorted;
+        run_shards(slice_shard, &job);
+        if (shard_errs(&job.err)) {
+            dev_index_drop(c);
+            goto fail;
+        }
+    }
+    column->index = ix;
+    ix = NULL;
     c->host_ix_values = column->index->values;
     c->ix_rows = n;
+    rc = 0;
+    goto done;
+dev_fail:
+    set_err("index build: %s", adb_last_error());
+fail:
+    if (ix) {
+        free(ix->values);
+        free(ix->positions);
+        free(ix);
+    }
+done:
+    if (wide) adb_free(wide);
+    if (vals) adb_free(vals);
+    if (poss) adb_free(poss);
+    if (own_all && all) adb_free(all);
+    return rc;
+}
+
+/* build_histogram (src/index.c:63-84) on the device: counts[b] for the 100 bins of width
+ * (max - min) / 99 starting at column->min.  Returns -1 when the bin width is 0 (the reference
+ * divides by it). */
+int adb_host_column_histogram(Column *column, int bin_size, unsigned long counts[100]) {
+    t_err[0] = '\0';
+    if (ensure_up() || !column || !counts) return -1;
+    if (bin_size <= 0) {
+        set_err("histogram: bin width %d (the reference divides by it, index.c:77)", bin_size);
+        return -1;
+    }
+    DevColumn *c = dev_column(column);
+    if (!c) return -1;
+    memset(counts, 0, 100 * sizeof counts[0]);
+    for (int g = 0; g < S.G; ++g) {
+        uint64_t part[100];
+        const size_t len = shard_len(c->rows, c->shard_rows, g);
+        on_ctx(g);
+        if (adb_histogram_i32(c->d_data[g], (int64_t)len, column->min, bin_size, part) != ADB_OK) {
+            set_err("histogram: %s", adb_last_error());
+            on_ctx(0);
+            return -1;
+        }
+        for (int b = 0; b < 100; ++b) counts[b] += part[b];
+    }
+    on_ctx(0);
     return 0;
 }
 
@@ -1095,13 +1322,12 @@ static int alloc_shards(Shards *sh) {
 }
 
 /* ---- selects ------------------------------------------------------------------------------ */
-#ifndef ADB_WITH_REFERENCE_HEADERS
-/* src/index.c:180-185: the cost model is the constant `true`. */
+/* src/index.c:180-185: the cost model is the constant `true` (the drop-in links
+ * host/index_shim.c in place of index.c, so the definition lives here in both builds). */
 bool should_use_index(Column *column, int low, int high) {
     (void)column; (void)low; (void)high;
     return true;
 }
-#endif
 
 void log_result(Result *result) { (void)result; }        /* src/query.c:26-28: returns at once */
 

@@ -359,6 +359,16 @@ ADB_API adb_status adb_index_sort(const int32_t *d_col, int64_t n, int32_t *d_va
 /* ColumnIndex.positions are size_t on the host (src/include/cs165_api.h:65-68) and truncated
  * to int when emitted (src/query.c:187): d_dst[i] = (int32_t) d_src_u64[i]. */
 ADB_API adb_status adb_narrow_u64_to_i32(const void *d_src_u64, int64_t n, int32_t *d_dst);
+/* the other direction, for handing a device-built index back to the host catalog:
+ * d_dst_u64[i] = (size_t) d_src[i]; d_src == NULL writes the identity (the positions of a
+ * clustered index stay 0..n-1, src/index.c:89-101,119-135) */
+ADB_API adb_status adb_widen_i32_to_u64(const int32_t *d_src, int64_t n, void *d_dst_u64);
+/* d_out[i] = first + i (identity positions: init_column_index, src/index.c:89-101) */
+ADB_API adb_status adb_iota_i32(int32_t *d_out, int64_t n, int32_t first);
+/* build_histogram, src/index.c:63-84: h_counts[b] (b < 100) = rows with (v - vmin) / bin_size == b;
+ * bins past 99 (the reference writes out of bounds there) are dropped */
+ADB_API adb_status adb_histogram_i32(const int32_t *d_val, int64_t n, int32_t vmin, int32_t bin_size,
+                                     uint64_t *h_counts);
 
 /* ---- joins -- replace hash_join + multimap (src/query.c:652-696, src/multimap.c) and
  * nested_loop_join (src/query.c:585-650).  Inputs are two (value, position) pair lists;

@@ -157,6 +157,16 @@ int adb_host_column_adopt(Column *column, const void *d_data);   /* rows already
  * shard_rows a multiple of 32 */
 int adb_host_column_adopt_shards(Column *column, const void *const *d_shards, size_t shard_rows);
 void adb_host_column_invalidate(Column *column);  /* after insert_row, src/server.c:250 */
+/* Index build on the engine -- what build_unclustered_index / build_clustered_index do
+ * (src/index.c:105-146): cols[0 .. n_cols) are the table's columns in declaration order,
+ * cols[which] the indexed one (its sorted / clustered flags say what to build).  Fills
+ * cols[which]->index (plain malloc, as init_column_index does), permutes the siblings' host data
+ * in place for a clustered index, and installs the device-side index.  Ties come out in
+ * ascending row order (stable radix sort; the reference's quicksort leaves another order,
+ * SURVEY.md A3 -- identical for unique keys).  host/index_shim.c builds build_index(Db*) on it. */
+int adb_host_index_build(Column **cols, int n_cols, int which);
+/* build_histogram's counts (src/index.c:63-84) computed on the device */
+int adb_host_column_histogram(Column *column, int bin_size, unsigned long counts[100]);
 /* Device-resident results: Result.payload of a position list / value vector is a small
  * malloc'd descriptor, so the plumbing's free(payload) (src/client_context.c:35,82) stays
  * valid; the HBM buffer behind it is returned to the engine by adb_host_result_release()

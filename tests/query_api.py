@@ -76,6 +76,8 @@ HOOKS = {
     "adb_host_column_upload": (C.c_int, [C.POINTER(Column)]),
     "adb_host_column_adopt": (C.c_int, [C.POINTER(Column), C.c_void_p]),
     "adb_host_column_invalidate": (None, [C.POINTER(Column)]),
+    "adb_host_index_build": (C.c_int, [C.POINTER(C.POINTER(Column)), C.c_int, C.c_int]),
+    "adb_host_column_histogram": (C.c_int, [C.POINTER(Column), C.c_int, C.POINTER(C.c_ulong)]),
     "adb_host_result_release": (None, [RP]),
     "adb_host_payload_freed": (None, [C.c_void_p]),
     "adb_host_result_to_host": (C.c_int, [RP, C.c_void_p]),
@@ -122,6 +124,35 @@ class Api:
             col.index = C.pointer(ix)
             self._keep += [v, p, ix]
         return col
+
+    def table(self, arrays, flags=None):
+        """A table's columns in declaration order (writable host arrays: a clustered index build
+        permutes sibling data in place).  flags[j] = (sorted, clustered) for an indexed column."""
+        cols = []
+        for j, a in enumerate(arrays):
+            a = np.array(a, dtype=np.int32, copy=True)
+            col = Column()
+            col.name = b"col%d" % (j + 1)
+            col.data = a.ctypes.data_as(C.POINTER(C.c_int))
+            col.row_count = a.size
+            if a.size:
+                col.min, col.max = int(a.min()), int(a.max())
+            if flags and flags.get(j):
+                col.sorted, col.clustered = flags[j]
+                col.has_index = True
+            self._keep.append(a)
+            cols.append((col, a))
+        return cols
+
+    def build_index(self, cols, which):
+        arr = (C.POINTER(Column) * len(cols))(*[C.pointer(c) for c, _ in cols])
+        if self.lib.adb_host_index_build(arr, len(cols), which) != 0:
+            raise RuntimeError("adb_host_index_build: " + self.lib.adb_host_last_error().decode())
+        col = cols[which][0]
+        n = col.row_count
+        ix = col.index.contents
+        return (np.ctypeslib.as_array(ix.values, shape=(n,)).copy() if n else np.zeros(0, np.int32),
+                np.ctypeslib.as_array(ix.positions, shape=(n,)).copy() if n else np.zeros(0, np.uint64))
 
     def host_result(self, values) -> Result:
         """A Result whose payload is an ordinary host int array (as the reference builds)."""

@@ -19,11 +19,41 @@ REFERENCE_OUTPUT_UNDEFINED = {14}
 TESTS = range(1, 38)
 
 
+# Tests that print position / value lists in INDEX order (milestone 3).  With the index built
+# on the engine (stable radix sort) the order inside a run of equal keys is ascending row order,
+# with the reference's unstable quicksort it is whatever the partition steps left (SURVEY.md
+# A3): those replies are compared the way the reference's own verifier compares them when exact
+# match fails -- as sorted lines (infra_scripts/verify_output_standalone.sh:41-47).  With
+# ADB_INDEX_BUILD=reference (the reference's index.c builds, the shim uploads) every reply is
+# byte-identical.
+INDEX_ORDERED = set(range(18, 32))
+MODE = {"index": "engine"}
+
+
+def same(t, a, b):
+    if a == b:
+        return True
+    if MODE["index"] == "engine" and t in INDEX_ORDERED:
+        return sorted(a.splitlines()) == sorted(b.splitlines())
+    return False
+
+
+def tie_order_garbage(t, ref_out):
+    """Tests 25 and 27: the reference's own answer fails its .exp (an unclustered
+    index built before a later column's clustered index keeps pre-permutation positions).  WHICH
+    wrong rows it then reads depends on how its quicksort ordered equal keys of the clustered
+    column, so with an engine-built (stable) index the drop-in reads other wrong rows.  Compared
+    byte for byte only under ADB_INDEX_BUILD=reference."""
+    return MODE["index"] == "engine" and t in INDEX_ORDERED and H.verdict(ref_out, H.exp_text(t)) == "fail"
+
+
 def mismatches(ref, b200):
-    return [t for t in TESTS if t not in REFERENCE_OUTPUT_UNDEFINED and b200[t] != ref[t]]
+    return [t for t in TESTS if t not in REFERENCE_OUTPUT_UNDEFINED and not tie_order_garbage(t, ref[t])
+            and not same(t, b200[t], ref[t])]
 
 
-@pytest.fixture(scope="module", params=["1", "3"], ids=["1gpu", "3gpus"])
+@pytest.fixture(scope="module", params=[("1", "reference"), ("1", "engine"), ("3", "engine")],
+                ids=["1gpu-reference_index", "1gpu-engine_index", "3gpus-engine_index"])
 def outputs(request):
     """Both pairs replay the suite.  The unmodified client reads a reply with a single recv
     (client.c:127), so a replay can come out truncated on either side for
@@ -35,7 +65,9 @@ def outputs(request):
             ref = H.ServerPair("ref", w1).run_suite(TESTS)
             # ADB_GPUS: the unmodified server process drives that many engine contexts (one per
             # GPU; they share the device on a 1-GPU box), every column sharded over them
-            b200 = H.ServerPair("b200", w2, env={"ADB_GPUS": request.param}).run_suite(TESTS)
+            MODE["index"] = request.param[1]
+            b200 = H.ServerPair("b200", w2, env={"ADB_GPUS": request.param[0],
+                                                 "ADB_INDEX_BUILD": request.param[1]}).run_suite(TESTS)
             bad = mismatches(ref, b200)
             if not bad:
                 break
@@ -57,7 +89,10 @@ def test_drop_in_matches_the_golden_expectations(outputs):
     for t in TESTS:
         vr, vb = H.verdict(ref[t], H.exp_text(t)), H.verdict(b200[t], H.exp_text(t))
         if vr != "fail":
-            assert vb == vr, (t, vr, vb)
+            if MODE["index"] == "engine" and t in INDEX_ORDERED:
+                assert vb != "fail", (t, vr, vb)            # tie order may turn "exact" into "sorted"
+            else:
+                assert vb == vr, (t, vr, vb)
     # test 14: every select is empty; the drop-in prints nothing where the reference prints
     # uninitialised bytes, which is what the .exp expects
     assert H.verdict(b200[14], H.exp_text(14)) == "exact"
