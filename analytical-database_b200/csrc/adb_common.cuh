@@ -356,7 +356,14 @@ int launch_select(const SelectArgs &a, cudaStream_t s);
 // two-phase form: mask + per-chunk counts (+ total into a.d_count), then expand into a.out
 int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s);
 int launch_select_expand(const SelectArgs &a, cudaStream_t s);
-int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s);
+int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s);     // a.out == a.val_out == NULL: aggregate only
+int launch_scan_gather_agg(const SelectArgs &a, cudaStream_t s);
+// sliced, overlapped form of mask + expand_fetch_agg (select_scan.cu); agg_scratch must hold
+// slices * ceil(chunks_per_slice / 8) partials, agg_ticket `slices` zeroed counters;
+// returns -1 when the geometry does not fit (caller uses the unsliced chain)
+int launch_chain_sliced(const SelectArgs &a, uint32_t slices, uint32_t chunks_per_slice, adb_agg *slice_parts,
+                        cudaStream_t main_s, cudaStream_t side_s, cudaEvent_t *mask_done, uint32_t *slices_used);
+constexpr int kChainMaxSlices = 16;
 size_t select_mask_words(uint32_t n, int sm_count);
 constexpr uint32_t kMaxSelectChunks = 1u << 16;
 
@@ -379,6 +386,8 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
 int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
                           uint32_t span, int sm_count, cudaStream_t s);
 int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s);
+int launch_synth_affine(int32_t *out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add, uint64_t modulus,
+                        int sm_count, cudaStream_t s);
 int launch_iota(int32_t *out, int64_t n, int32_t first, int sm_count, cudaStream_t s);
 int launch_widen_i32(const int32_t *src, int64_t n, unsigned long long *dst, int sm_count, cudaStream_t s);
 // counts: 128 uint64 (zeroed by the launcher)

@@ -130,6 +130,12 @@ struct Engine {
     int64_t launches = 0;
     int32_t chain_mark_base = -1;       // adb_chain_marks(): slots for the next chain call
     bool peer_local = false;            // mailboxes mapped by peer access inside one process (no IPC handles)
+    // sliced chain (launch_chain_sliced): a higher-priority side stream for the expansions
+    cudaStream_t side = nullptr;
+    cudaEvent_t slice_ev[adb::kChainMaxSlices] = {};
+    cudaEvent_t side_done = nullptr;
+    adb_agg *slice_parts = nullptr;
+    int chain_slices = 0, chain_cps_div = 2;        // ADB_CHAIN_SLICES (0 = by size), ADB_CHAIN_CPS_DIV
 };
 
 // One context per GPU of the box (several may share a device: a 1-GPU box then runs the
@@ -461,9 +467,19 @@ adb_status adb_init(int device_ordinal) {
             cudaGetLastError();                 // readbacks fall back to cudaMemcpyAsync
         }
     }
-    CU(cudaMalloc(&g.agg_scratch, sizeof(adb_agg) * adb::kAggMaxBlocks));
-    CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int)));
-    CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int)));
+    CU(cudaMalloc(&g.agg_scratch, sizeof(adb_agg) * adb::kAggMaxBlocks * adb::kChainMaxSlices));
+    CU(cudaMalloc(&g.agg_ticket, sizeof(unsigned int) * (adb::kChainMaxSlices + 1)));
+    CU(cudaMemset(g.agg_ticket, 0, sizeof(unsigned int) * (adb::kChainMaxSlices + 1)));
+    {
+        int lo_prio = 0, hi_prio = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CU(cudaStreamCreateWithPriority(&g.side, cudaStreamNonBlocking, hi_prio));
+        for (cudaEvent_t &e : g.slice_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&g.side_done, cudaEventDisableTiming));
+        CU(cudaMalloc(&g.slice_parts, sizeof(adb_agg) * adb::kChainMaxSlices));
+        if (const char *e = getenv("ADB_CHAIN_SLICES")) g.chain_slices = atoi(e);
+        if (const char *e = getenv("ADB_CHAIN_CPS_DIV")) g.chain_cps_div = atoi(e) > 0 ? atoi(e) : 1;
+    }
     g.launches = 0;
     g.ctx_index = g_cur;
     g.up = true;
@@ -514,6 +530,10 @@ static adb_status shutdown_current() {
     cudaFree(g.csv.total);
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
+    cudaFree(g.slice_parts);
+    if (g.side) { cudaStreamSynchronize(g.side); cudaStreamDestroy(g.side); }
+    for (cudaEvent_t &e : g.slice_ev) if (e) cudaEventDestroy(e);
+    if (g.side_done) cudaEventDestroy(g.side_done);
     if (g.mbox) cudaFreeHost(g.mbox);
     peer_close();
     for (int l = 0; l < g.stage_lanes; ++l) {
@@ -626,6 +646,17 @@ adb_status adb_mark_elapsed(int32_t from_slot, int32_t to_slot, float *ms) {
         return fail(ADB_ERR_INVALID, "adb_mark_elapsed: unrecorded or invalid slot");
     CU(cudaEventSynchronize(g.marks[to_slot]));
     CU(cudaEventElapsedTime(ms, g.marks[from_slot], g.marks[to_slot]));
+    return ADB_OK;
+}
+
+// slices: row slices per adb_chain_select_fetch_agg call (0 = by size: 4 from 2^26 rows, else 1);
+// cps_div: every slice's grid fills 1/cps_div of the machine (the rest is the other kernel's)
+adb_status adb_chain_config(int32_t slices, int32_t cps_div) {
+    NEED_UP();
+    if (slices < 0 || slices > adb::kChainMaxSlices || cps_div < 1 || cps_div > 8)
+        return fail(ADB_ERR_INVALID, "adb_chain_config: slices in [0, %d], cps_div in [1, 8]", adb::kChainMaxSlices);
+    g.chain_slices = slices;
+    g.chain_cps_div = cps_div;
     return ADB_OK;
 }
 
@@ -745,10 +776,15 @@ static adb_status emit_fetch_agg_impl(const int32_t *d_fetch_col, int32_t *d_pos
     if (!g.sel_ready) return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: no pending adb_select_count");
     if (g.sel_pending.pos_in || g.sel_pending.d_n)
         return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: the pending select is not over a base column");
-    if (!d_agg || (g.sel_pending.n > 0 && (!d_fetch_col || !d_pos_out || !d_val_out)))
+    // both outputs NULL: aggregate only -- nothing is materialised and the pending select stays
+    // pending (the bitmap is only read), so a later emit can still write the handles
+    const bool nostore = !d_pos_out && !d_val_out;
+    if (!d_agg || (g.sel_pending.n > 0 && (!d_fetch_col || (!nostore && (!d_pos_out || !d_val_out)))))
         return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: NULL device pointer");
-    g.sel_ready = false;
-    ++g.sel_generation;                             // the pending count is consumed
+    if (!nostore) {
+        g.sel_ready = false;
+        ++g.sel_generation;                         // the pending count is consumed
+    }
     adb::SelectArgs a = g.sel_pending;
     int64_t *d_count = a.d_count;                   // written by the count phase
     a.out = d_pos_out;                              // base_pos: what the count phase recorded
@@ -759,6 +795,8 @@ static adb_status emit_fetch_agg_impl(const int32_t *d_fetch_col, int32_t *d_pos
     const int f_ = adb::launch_select_expand_fetch_agg(a, g.stream);
     if (f_ > 0) {
         if (adb_status s = after_launch("select_emit_fetch_agg", f_)) return s;
+    } else if (nostore && a.n > 0) {
+        return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: a select over %u rows cannot be aggregated unmaterialised", a.n);
     } else {
         // empty column (or a grid larger than the fold scratch): the three-operator form
         if (adb_status s = after_launch("select_emit_fetch_agg", adb::launch_select_expand(a, g.stream))) return s;
@@ -1215,6 +1253,28 @@ static adb_status chain_impl(const int32_t *d_sel_col, const int32_t *d_fetch_co
     // aggregates fused in (positions and values are still materialised)
     const int32_t mb = g.chain_mark_base;
     g.chain_mark_base = -1;
+    // Large shards: cut into row slices so that the predicate pass of slice k+1 overlaps the
+    // expansion + gather + aggregate of slice k (launch_chain_sliced).  Not when per-kernel
+    // marks were asked for (they need the two kernels back to back on one stream) and not for
+    // the exchange-carrying form.
+    // (r02: measured on 500 M-row shards, 0.415 ms sliced 4 x 1/2 against 0.418 ms plain -- the
+    // gather alone already moves 3.7 TB/s of 64-byte sectors, there is little idle bandwidth to
+    // fill; profiles/r02_chain_slices.md.  Kept selectable, off by default.)
+    uint32_t slices = g.chain_slices > 0 ? (uint32_t)g.chain_slices : 1u;
+    if (slices > (uint32_t)adb::kChainMaxSlices) slices = adb::kChainMaxSlices;
+    if (slices > 1 && mb < 0 && !px) {
+        const uint32_t wave = (uint32_t)g.sm_count * 8u * 8u;
+        uint32_t cps = wave / (uint32_t)g.chain_cps_div;
+        if (cps * slices > adb::kMaxSelectChunks) cps = adb::kMaxSelectChunks / slices;
+        uint32_t used = 0;
+        const int l_ = adb::launch_chain_sliced(a, slices, cps, g.slice_parts, g.stream, g.side, g.slice_ev, &used);
+        if (l_ > 0) {
+            int c_ = adb::launch_agg_combine(g.slice_parts, (int32_t)used, d_agg, g.side);
+            CU(cudaEventRecord(g.side_done, g.side));
+            CU(cudaStreamWaitEvent(g.stream, g.side_done, 0));
+            return after_launch("chain (sliced)", l_ + c_);
+        }
+    }
     if (mb >= 0) adb_mark(mb);
     int k_ = adb::launch_select_mask(a, false, g.stream);
     if (mb >= 0) adb_mark(mb + 1);
@@ -1235,6 +1295,31 @@ adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const int32_t *d
                                       int32_t *d_pos_out, int32_t *d_val_out,
                                       int64_t *d_count, adb_agg *d_agg) {
     return chain_impl(d_sel_col, d_fetch_col, n, lo, hi, d_pos_out, d_val_out, d_count, d_agg, nullptr);
+}
+
+// The chain with NEITHER handle materialised: one kernel scans the select
+// column and gathers + folds the fetch column at every hit -- 4N + 4H bytes, no bitmap, no lists.
+adb_status adb_chain_select_agg(const int32_t *d_sel_col, const int32_t *d_fetch_col, int64_t n,
+                                const int32_t *lo, const int32_t *hi, int64_t *d_count, adb_agg *d_agg,
+                                adb_agg *h_agg) {
+    adb::SelectArgs a;
+    if (!d_count || !d_agg || (n > 0 && !d_fetch_col)) {
+        NEED_UP();
+        return fail(ADB_ERR_INVALID, "adb_chain_select_agg: NULL device pointer");
+    }
+    if (adb_status s = select_prepare("adb_chain_select_agg", d_sel_col, nullptr, n, nullptr, lo, hi, d_count, &a, true)) return s;
+    a.fetch_col = d_fetch_col;
+    a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
+    const int f_ = adb::launch_scan_gather_agg(a, g.stream);
+    if (f_ > 0) {
+        if (adb_status s = after_launch("chain (unmaterialised)", f_)) return s;
+    } else {
+        // empty column: the aggregate of nothing
+        CU(cudaMemsetAsync(d_count, 0, sizeof(int64_t), g.stream));
+        if (adb_status s = adb_aggregate(d_sel_col, 0, nullptr, d_agg, nullptr)) return s;
+    }
+    if (h_agg) return read_back(h_agg, d_agg, sizeof(adb_agg));
+    return ADB_OK;
 }
 
 adb_status adb_chain_select_fetch_agg_exchange(const int32_t *d_sel_col, const int32_t *d_fetch_col,
@@ -2030,6 +2115,14 @@ adb_status adb_narrow_u64_to_i32(const void *d_src_u64, int64_t n, int32_t *d_ds
     if (n == 0) return ADB_OK;
     const int k_ = adb::launch_narrow_u64(static_cast<const unsigned long long *>(d_src_u64), n, d_dst, g.sm_count, g.stream);
     return after_launch("narrow_u64", k_);
+}
+
+adb_status adb_synth_affine(int32_t *d_out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add,
+                            uint64_t modulus) {
+    NEED_UP();
+    if (n < 0 || (n > 0 && !d_out) || modulus == 0 || modulus > ((uint64_t)1 << 31) || mul >= modulus || add >= modulus)
+        return fail(ADB_ERR_INVALID, "adb_synth_affine: bad arguments");
+    return after_launch("synth_affine", adb::launch_synth_affine(d_out, n, first_row, mul, add, modulus, g.sm_count, g.stream));
 }
 
 adb_status adb_iota_i32(int32_t *d_out, int64_t n, int32_t first) {

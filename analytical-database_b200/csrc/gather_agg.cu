@@ -237,6 +237,16 @@ histogram_kernel(const int32_t *__restrict__ v, int64_t n, int32_t vmin, int32_t
     if (threadIdx.x < HIST_BINS && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
 }
 
+// out[i] = ((first_row + i) * mul + add) mod modulus: with gcd(mul, modulus) = 1 a permutation of
+// 0 .. modulus-1 (the unique-key column of BASELINE config 3)
+__global__ void __launch_bounds__(STREAM_THREADS)
+synth_affine_kernel(int32_t *__restrict__ out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add,
+                    uint64_t modulus) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int32_t)(((first_row + (uint64_t)i) * mul + add) % modulus);
+}
+
 // ---- launchers ------------------------------------------------------------------------------
 static int stream_grid(int64_t work_items, int sm_count, int per_sm) {
     const int64_t want = (work_items + STREAM_THREADS - 1) / STREAM_THREADS;
@@ -281,6 +291,13 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
         ewise_kernel<true><<<grid, STREAM_THREADS, 0, s>>>(a, b, n_max, d_n, out);
     else
         ewise_kernel<false><<<grid, STREAM_THREADS, 0, s>>>(a, b, n_max, d_n, out);
+    return 1;
+}
+
+int launch_synth_affine(int32_t *out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add, uint64_t modulus,
+                        int sm_count, cudaStream_t s) {
+    if (n <= 0) return 0;
+    synth_affine_kernel<<<stream_grid(n / 4 + 1, sm_count, 16), STREAM_THREADS, 0, s>>>(out, n, first_row, mul, add, modulus);
     return 1;
 }
 

@@ -180,6 +180,10 @@ class Engine:
         "adb_narrow_u64_to_i32": (C.c_int32, [C.c_void_p, C.c_int64, _I32P]),
         "adb_widen_i32_to_u64": (C.c_int32, [_I32P, C.c_int64, C.c_void_p]),
         "adb_iota_i32": (C.c_int32, [_I32P, C.c_int64, C.c_int32]),
+        "adb_chain_config": (C.c_int32, [C.c_int32, C.c_int32]),
+        "adb_chain_select_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I64P, C.POINTER(_AggStruct),
+                                             C.POINTER(_AggStruct)]),
+        "adb_synth_affine": (C.c_int32, [_I32P, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
         "adb_histogram_i32": (C.c_int32, [_I32P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     }
 

@@ -299,6 +299,24 @@ static void free_on(int g, void *d) {
     on_ctx(0);
 }
 
+/* release one buffer per context: each context's thread frees its own */
+typedef struct FreeJob {
+    int32_t *d[MAXG];
+} FreeJob;
+static void free_shard(int g, void *arg) {
+    FreeJob *a = arg;
+    if (a->d[g]) adb_free(a->d[g]);
+}
+static void free_shards(int32_t *const d[]) {
+    FreeJob job;
+    int any = 0;
+    for (int g = 0; g < MAXG; ++g) {
+        job.d[g] = g < S.G ? d[g] : NULL;
+        any |= job.d[g] != NULL;
+    }
+    if (any) run_shards(free_shard, &job);
+}
+
 /* rows of shard g of a list of `rows` rows cut every S rows */
 static size_t shard_len(size_t rows, size_t S_, int g) {
     const size_t b = (size_t)g * S_;
@@ -306,86 +324,174 @@ static size_t shard_len(size_t rows, size_t S_, int g) {
     return rows - b < S_ ? rows - b : S_;
 }
 
-/* ---- deferred select -------------------------------------------------
+/* ---- lazy handles ----------------------------------------------------
  * select_column over an un-indexed column returns as soon as the hit count is known: the
  * predicate pass has left its bitmap in the engine's scratch (one per context), the position
- * buffers are allocated, their contents are not written yet.  If the next thing that happens
- * to the handle is fetch_column and then an aggregate of that fetch -- the s=select / f=fetch /
- * a=sum(f) pattern of src/server.c:137-290 -- the aggregate call resolves all three with the
- * chain's fused second kernel (positions + gather + sum/min/max in one pass over the bitmap,
- * and with G > 1 the cross-GPU exchange in the same kernel).  Any other use of either handle,
- * any other select, a column invalidation or a release first writes what is pending
- * (flush_pending), so the handles are indistinguishable from eager ones to the unchanged
- * plumbing.  At most one select is pending at a time.  ADB_SHIM_EAGER=1 (or the mirror mode)
- * turns the deferral off. */
-static struct {
+ * buffers are allocated, their contents are NOT written.  fetch_column of that handle
+ * launches nothing either.  An aggregate of that fetch -- the s=select / f=fetch / a=sum(f)
+ * pattern of src/server.c:137-290 -- gathers and folds the hit rows straight from the bitmap
+ * without writing the positions or the values (and with G > 1 exchanges the partials over
+ * NVLink in the same kernel): the chain costs 4N + 4H bytes instead of 4N + 20H.  A handle is
+ * written only when somebody reads it: print, a second fetch, add / sub, a join,
+ * select_result, a second aggregate, a foreign reader (adb_host_result_to_host), or the
+ * invalidation of a column it depends on.  The record of the newest select (P) still has its
+ * bitmap and is written from it; when the next select takes the bitmap over, the record is
+ * demoted to a recipe (R: column, bounds, fetch column, buffers) and writing it re-runs the
+ * predicate pass.  A handle that is released unread is never written at all.  To the unchanged
+ * plumbing the handles are indistinguishable from eager ones.  ADB_SHIM_EAGER=1 (or the mirror
+ * mode) turns all of this off. */
+typedef struct Lazy {
     int active;
-    const void *sel_payload;        /* registry key of the select handle */
-    int32_t *sel_d[MAXG];           /* its position buffers, h[g] entries */
-    size_t h[MAXG];
-    const int32_t *d_col[MAXG];     /* what was scanned, to redo the count if another user of */
-    size_t rows[MAXG];              /* the engine overwrote the bitmap in the meantime        */
-    size_t shard_rows;
-    int has_lo, has_hi, lo, hi;
-    uint64_t generation[MAXG];      /* adb_select_generation() right after the count */
+    const void *sel_payload;        /* registry key of the select handle; NULL once it was released */
     const void *fetch_payload;      /* fetch_column of that select, values not written yet */
+    int32_t *sel_d[MAXG];           /* position buffers, h[g] entries */
     int32_t *fetch_d[MAXG];
+    int owns_sel;                   /* the select handle is gone: its buffers belong to this record */
+    size_t h[MAXG];
+    const int32_t *d_col[MAXG];     /* what was scanned, to redo the predicate pass */
+    size_t rows[MAXG];
+    size_t shard_rows;
     const int32_t *d_fetch_col[MAXG];
-} P;
+    int has_lo, has_hi, lo, hi;
+    uint64_t generation[MAXG];      /* adb_select_generation() right after the count (P only) */
+    int aggregated;                 /* an aggregate has been answered without writing the handles */
+} Lazy;
+static Lazy P;                      /* the newest select: its bitmaps sit in the engines' scratch */
+static Lazy *R;                     /* older unwritten selects: recipes */
+static int nR, capR;
 
-typedef struct FlushJob {
+typedef struct LazyJob {
     ShardErr err;
-} FlushJob;
+    Lazy *z;
+    int have_bitmap;
+} LazyJob;
 
 static int32_t shard_base(int g, size_t shard_rows) { return (int32_t)((size_t)g * shard_rows); }
 
-/* runs on context g: redo the predicate pass if the bitmap is gone */
-static int pending_recount_shard(int g, ShardErr *e) {
-    if (adb_select_generation() == P.generation[g]) return 0;
+/* runs on context g: redo the predicate pass unless this record's bitmap is still in scratch */
+static int lazy_recount_shard(Lazy *z, int have_bitmap, int g, ShardErr *e) {
+    if (have_bitmap && adb_select_generation() == z->generation[g]) return 0;
     int64_t h = -1;
-    if (adb_select_count_base(P.d_col[g], (int64_t)P.rows[g], P.has_lo ? &P.lo : NULL,
-                              P.has_hi ? &P.hi : NULL, shard_base(g, P.shard_rows), NULL, &h) != ADB_OK) {
-        shard_fail(e, g, "deferred select");
+    if (adb_select_count_base(z->d_col[g], (int64_t)z->rows[g], z->has_lo ? &z->lo : NULL,
+                              z->has_hi ? &z->hi : NULL, shard_base(g, z->shard_rows), NULL, &h) != ADB_OK) {
+        shard_fail(e, g, "lazy select");
         return -1;
     }
-    if ((size_t)h != P.h[g]) {
+    if ((size_t)h != z->h[g]) {
         e->failed[g] = 1;
         snprintf(e->msg[g], sizeof e->msg[g],
-                 "deferred select: the column changed under a pending select (%zu hits, now %lld)",
-                 P.h[g], (long long)h);
+                 "lazy select: the column changed under an unwritten select (%zu hits, now %lld)",
+                 z->h[g], (long long)h);
         return -1;
     }
+    z->generation[g] = adb_select_generation();
     return 0;
 }
 
-static void flush_shard(int g, void *arg) {
-    FlushJob *a = arg;
-    if (pending_recount_shard(g, &a->err)) return;
-    if (P.fetch_payload)
-        SCK(adb_select_emit_fetch_agg(P.d_fetch_col[g], P.sel_d[g], P.fetch_d[g], S.d_part[g], NULL));
+static void lazy_write_shard(int g, void *arg) {
+    LazyJob *a = arg;
+    Lazy *z = a->z;
+    if (lazy_recount_shard(z, a->have_bitmap, g, &a->err)) return;
+    if (z->fetch_payload)
+        SCK(adb_select_emit_fetch_agg(z->d_fetch_col[g], z->sel_d[g], z->fetch_d[g], S.d_part[g], NULL));
     else
-        SCK(adb_select_emit(NULL, shard_base(g, P.shard_rows), P.sel_d[g]));
+        SCK(adb_select_emit(NULL, shard_base(g, z->shard_rows), z->sel_d[g]));
 }
 
-/* Write whatever is pending; afterwards every handle is an ordinary device result. */
-static int flush_pending(void) {
-    if (!P.active) return 0;
-    P.active = 0;
-    FlushJob job;
-    memset(&job, 0, sizeof job);
-    run_shards(flush_shard, &job);
-    return shard_errs(&job.err);
-}
-
-/* The plumbing is about to free (or has freed) this payload. */
-static void pending_payload_gone(const void *payload) {
-    if (!P.active) return;
-    if (payload == P.fetch_payload) {           /* nobody can read those values any more */
-        P.fetch_payload = NULL;
-    } else if (payload == P.sel_payload) {
-        if (P.fetch_payload) flush_pending();   /* the fetch still needs the selected rows */
-        else P.active = 0;
+static void lazy_done(Lazy *z) {
+    if (z->owns_sel) free_shards(z->sel_d);
+    z->owns_sel = 0;
+    z->active = 0;
+    if (z != &P) {                               /* a recipe: close the gap */
+        const int k = (int)(z - R);
+        R[k] = R[nR - 1];
+        --nR;
     }
+}
+
+/* Write the handles of one record; afterwards they are ordinary device results. */
+static int lazy_write(Lazy *z) {
+    if (!z->active) return 0;
+    int rc = 0;
+    if (z->sel_payload || z->fetch_payload) {
+        LazyJob job;
+        memset(&job, 0, sizeof job);
+        job.z = z;
+        job.have_bitmap = z == &P;
+        run_shards(lazy_write_shard, &job);
+        rc = shard_errs(&job.err);
+    }
+    lazy_done(z);
+    return rc;
+}
+
+static Lazy *lazy_find(const void *payload) {
+    if (!payload) return NULL;
+    if (P.active && (payload == P.sel_payload || payload == P.fetch_payload)) return &P;
+    for (int k = 0; k < nR; ++k)
+        if (payload == R[k].sel_payload || payload == R[k].fetch_payload) return &R[k];
+    return NULL;
+}
+
+/* `payload` is about to be read: write its handle if it is still unwritten */
+static int resolve_payload(const void *payload) {
+    if (!P.active && nR == 0) return 0;
+    Lazy *z = lazy_find(payload);
+    return z ? lazy_write(z) : 0;
+}
+
+/* a new select is about to take the bitmaps over: P becomes a recipe (no GPU work) */
+static int demote_pending(void) {
+    if (!P.active) return 0;
+    if (!P.sel_payload && !P.fetch_payload) {
+        lazy_done(&P);
+        return 0;
+    }
+    if (nR == capR) {
+        const int cap = capR ? 2 * capR : 8;
+        Lazy *n = realloc(R, (size_t)cap * sizeof *n);
+        if (!n) return lazy_write(&P);          /* out of host memory: write it now instead */
+        R = n;
+        capR = cap;
+    }
+    R[nR++] = P;
+    P.active = 0;
+    P.owns_sel = 0;
+    return 0;
+}
+
+/* The plumbing is about to free (or has freed) this payload.  Returns 1 when the handle's
+ * device buffers must NOT be released: an unwritten fetch still needs the select's position
+ * buffers as scratch should it ever be written -- they now belong to the record. */
+static int pending_payload_gone(const void *payload) {
+    if (!P.active && nR == 0) return 0;
+    Lazy *z = lazy_find(payload);
+    if (!z) return 0;
+    if (payload == z->fetch_payload) {           /* nobody can read those values any more */
+        z->fetch_payload = NULL;
+        if (!z->sel_payload) lazy_done(z);
+        return 0;
+    }
+    if (z->fetch_payload) {                      /* the select goes, its unwritten fetch stays */
+        z->sel_payload = NULL;
+        z->owns_sel = 1;
+        return 1;
+    }
+    lazy_done(z);
+    return 0;
+}
+
+/* a column's device copy is about to go: write every handle that would have to re-read it */
+static void lazy_column_gone(int32_t *const d_data[]) {
+    for (int pass = 0; pass < 2; ++pass)
+        for (int k = pass ? nR - 1 : 0; k >= 0; --k) {
+            Lazy *z = pass ? &R[k] : &P;
+            if (!z->active) continue;
+            int uses = 0;
+            for (int g = 0; g < S.G; ++g)
+                if (d_data[g] && (d_data[g] == z->d_col[g] || d_data[g] == z->d_fetch_col[g])) uses = 1;
+            if (uses) lazy_write(z);
+        }
 }
 
 /* ---- engine lifecycle ------------------------------------------------------------------ */
@@ -488,12 +594,7 @@ static void sync_all(void) {
 
 static void dev_column_drop(DevColumn *c) {
     if (c->d_data[0] || c->ix[0]) sync_all();
-    if (P.active)
-        for (int g = 0; g < S.G; ++g)
-            if (c->d_data[g] && (c->d_data[g] == P.d_col[g] || c->d_data[g] == P.d_fetch_col[g])) {
-                flush_pending();
-                break;
-            }
+    if (P.active || nR) lazy_column_gone(c->d_data);
     dev_index_drop(c);
     if (!c->adopted)
         for (int g = 0; g < S.G; ++g) free_on(g, c->d_data[g]);
@@ -509,7 +610,7 @@ static void result_buffers_free(DevResult *r) {
             free(r->slab);
         }
     } else {
-        for (int g = 0; g < S.G; ++g) free_on(g, r->d_ptr[g]);
+        free_shards(r->d_ptr);
     }
     memset(r->d_ptr, 0, sizeof r->d_ptr);
     r->slab = NULL;
@@ -518,7 +619,11 @@ static void result_buffers_free(DevResult *r) {
 void adb_host_shutdown(void) {
     if (!S.up) return;
     lock();
-    P.active = 0;
+    if (P.active) lazy_done(&P);
+    while (nR) lazy_done(&R[nR - 1]);
+    free(R);
+    R = NULL;
+    capR = 0;
     for (size_t i = 0; i < S.nslots; ++i)
         if (S.slots[i].payload != SLOT_EMPTY && S.slots[i].payload != SLOT_TOMB)
             result_buffers_free(&S.slots[i]);
@@ -819,7 +924,6 @@ int adb_host_index_build(Column **cols, int n_cols, int which) {
     }
     Column *column = cols[which];
     const size_t n = column->row_count;
-    if (flush_pending()) return -1;
     DevColumn *c = dev_column(column);
     if (!c) return -1;
     int rc = -1;
@@ -898,6 +1002,7 @@ int adb_host_index_build(Column **cols, int n_cols, int which) {
                 goto fail;
             }
             sync_all();                             /* every gather has read the old shards */
+            if (P.active || nR) lazy_column_gone(dc->d_data);
             for (int g = 0; g < S.G; ++g) {
                 free_on(g, dc->d_data[g]);
                 dc->d_data[g] = job.fresh[g];
@@ -1025,13 +1130,26 @@ static int registry_take(const void *payload, DevResult *out) {
 
 void adb_host_payload_freed(void *payload) {
     if (S.nlive <= 0 || !payload) return;
-    pending_payload_gone(payload);
+    const int keep = pending_payload_gone(payload);
     DevResult dead;
-    if (registry_take(payload, &dead)) result_buffers_free(&dead);
+    if (registry_take(payload, &dead) && !keep) result_buffers_free(&dead);
 }
 
 void adb_host_result_release(Result *result) {
     if (result) adb_host_payload_freed(result->payload);
+}
+
+/* What update_result / free_client_context do with a handle's old value (src/client_context.c:
+ * 31-45,76-90) plus the release hook, for a batch of Results: release the device buffers, free
+ * the payload, free the Result.  For hosts (and harnesses) that drop many handles at once. */
+void adb_host_results_drop(Result **results, int n) {
+    for (int i = 0; i < n; ++i) {
+        Result *r = results ? results[i] : NULL;
+        if (!r) continue;
+        adb_host_payload_freed(r->payload);
+        free(r->payload);
+        free(r);
+    }
 }
 
 /* What new_dev_result wraps: G device buffers (this call takes ownership). */
@@ -1044,10 +1162,8 @@ typedef struct Shards {
 
 static void shards_free(Shards *s) {
     if (s->slab) return;                            /* the slab's owner frees it */
-    for (int g = 0; g < S.G; ++g) {
-        free_on(g, s->d[g]);
-        s->d[g] = NULL;
-    }
+    free_shards(s->d);
+    memset(s->d, 0, sizeof s->d);
 }
 
 static int download_shards(void *dst, int32_t *const d[], const size_t n[]) {
@@ -1090,8 +1206,7 @@ static Result *new_dev_result(Shards *sh) {
     /* malloc returned an address we still hold buffers for: that payload was freed by the
      * plumbing without telling us -- reclaim its HBM now.  No engine call is made with the
      * registry lock held (with the free() interposer other threads' frees wait on it). */
-    if (P.active && (payload == P.sel_payload || payload == P.fetch_payload))
-        pending_payload_gone(payload);          /* may still need the dead handle's buffers */
+    const int keep_dead = pending_payload_gone(payload);    /* an unwritten fetch may keep the dead select's buffers */
     DevResult dead;
     int have_dead = 0;
     lock();
@@ -1125,7 +1240,7 @@ static Result *new_dev_result(Shards *sh) {
     e->aligned = sh->aligned;
     e->slab = sh->slab;
     unlock();
-    if (have_dead) result_buffers_free(&dead);
+    if (have_dead && !keep_dead) result_buffers_free(&dead);
     r->num_tuples = tuples;
     r->data_type = INT;
     r->payload = payload;
@@ -1152,8 +1267,7 @@ typedef struct Staged {
 } Staged;
 
 static void unstage(Staged *s) {
-    if (s->temp)
-        for (int g = 0; g < S.G; ++g) free_on(g, s->d[g]);   /* stream-ordered: safe right after the launch */
+    if (s->temp) free_shards(s->d);                 /* stream-ordered: safe right after the launch */
     memset(s, 0, sizeof *s);
 }
 
@@ -1216,7 +1330,7 @@ static int stage(const Result *r, const size_t *like, Staged *out) {
         set_err("result of %zu tuples exceeds the int position domain (src/query.c:40-43)", r->num_tuples);
         return -1;
     }
-    if (flush_pending()) return -1;             /* an operand is about to be read */
+    if (resolve_payload(r->payload)) return -1; /* an operand is about to be read: write it if unwritten */
     lock();
     DevResult *e = registry_find(r->payload);
     DevResult dv;
@@ -1285,7 +1399,7 @@ static int stage(const Result *r, const size_t *like, Staged *out) {
 int adb_host_result_to_host(const Result *result, void *dst) {
     if (!result) return -1;
     if (result->num_tuples == 0) return 0;
-    if (flush_pending()) return -1;
+    if (resolve_payload(result->payload)) return -1;
     lock();
     DevResult *e = registry_find(result->payload);
     DevResult dv;
@@ -1304,20 +1418,26 @@ int adb_host_result_to_host(const Result *result, void *dst) {
     return download_shards(dst, dv.d_ptr, have);
 }
 
-/* allocate n[g] ints on every context (main thread) */
+/* allocate n[g] ints on every context (each context's thread allocates its own) */
+typedef struct AllocJob {
+    ShardErr err;
+    Shards *sh;
+} AllocJob;
+static void alloc_shard(int g, void *arg) {
+    AllocJob *a = arg;
+    void *p = NULL;
+    SCK(adb_alloc(&p, 4 * a->sh->n[g]));
+    a->sh->d[g] = p;
+}
 static int alloc_shards(Shards *sh) {
-    for (int g = 0; g < S.G; ++g) {
-        void *p = NULL;
-        on_ctx(g);
-        if (adb_alloc(&p, 4 * sh->n[g]) != ADB_OK) {
-            set_err("adb_alloc(%zu): %s", 4 * sh->n[g], adb_last_error());
-            on_ctx(0);
-            shards_free(sh);
-            return -1;
-        }
-        sh->d[g] = p;
+    AllocJob job;
+    memset(&job, 0, sizeof job);
+    job.sh = sh;
+    run_shards(alloc_shard, &job);
+    if (shard_errs(&job.err)) {
+        shards_free(sh);
+        return -1;
     }
-    on_ctx(0);
     return 0;
 }
 
@@ -1432,7 +1552,7 @@ Result *select_column(Column *column, int *low, int *high, Status *ret_status) {
         return select_index_path(column, c, low, high, ret_status);
     SelectJob job;
     memset(&job, 0, sizeof job);
-    if (flush_pending()) goto fail;                 /* this select takes over the bitmaps */
+    if (demote_pending()) goto fail;                /* this select takes the bitmaps over */
     job.c = c;
     job.low = low;
     job.high = high;
@@ -1580,7 +1700,7 @@ Result **shared_select(SelectOperator *operators, int query_count, Column *colum
         goto fail;
     }
     DevColumn *c = dev_column(column);
-    if (!c || flush_pending()) goto fail;
+    if (!c) goto fail;                              /* (the batched scan has its own scratch: P stays) */
     results = calloc((size_t)query_count, sizeof *results);
     job = calloc(1, sizeof *job);
     slab = calloc(1, sizeof *slab);
@@ -1738,11 +1858,15 @@ static void agg_shard(int g, void *arg) {
     AggJob *a = arg;
     adb_agg *h = g == 0 ? &a->h : NULL;
     if (a->fused) {
+        /* the newest select's bitmap: gather + fold its hit rows, unwritten (fused == 1) or
+         * writing both handles on the way (fused == 2); a context whose bitmap was overwritten
+         * meanwhile redoes its predicate pass first */
+        if (lazy_recount_shard(&P, 1, g, &a->err)) return;
+        int32_t *pos = a->fused == 2 ? P.sel_d[g] : NULL, *val = a->fused == 2 ? P.fetch_d[g] : NULL;
         if (S.G == 1)
-            SCK(adb_select_emit_fetch_agg(P.d_fetch_col[g], P.sel_d[g], P.fetch_d[g], S.d_part[g], h));
+            SCK(adb_select_emit_fetch_agg(P.d_fetch_col[g], pos, val, S.d_part[g], h));
         else
-            SCK(adb_select_emit_fetch_agg_exchange(P.d_fetch_col[g], P.sel_d[g], P.fetch_d[g], S.d_part[g],
-                                                   S.d_out[g], h));
+            SCK(adb_select_emit_fetch_agg_exchange(P.d_fetch_col[g], pos, val, S.d_part[g], S.d_out[g], h));
         return;
     }
     if (S.G == 1) {
@@ -1768,34 +1892,23 @@ static int aggregate_result(const Result *r, adb_agg *h) {
     Staged v;
     memset(&v, 0, sizeof v);
     if (ensure_up()) return -1;
-    /* aggregate of the pending fetch of the pending select: the chain's fused second kernel
-     * writes both handles and the aggregate in one pass */
+    /* aggregate of the unwritten fetch of the newest select: the hit rows are gathered and
+     * folded straight from the bitmap.  The first aggregate writes nothing (4N + 4H bytes for the
+     * chain); a second one on the same handle writes both handles on the way -- whoever asks
+     * twice will probably ask again. */
     if (P.active && r && P.fetch_payload && r->payload == P.fetch_payload && r->data_type == INT) {
         size_t total = 0;
         for (int g = 0; g < S.G; ++g) total += P.h[g];
         if (r->num_tuples == total) {
-            /* every context must still hold its bitmap: a context that lost it redoes the count
-             * first (flush path), after which the ordinary aggregate below runs */
-            int intact = 1;
-            if (S.G == 1) {
-                intact = adb_select_generation() == P.generation[0];
-            } else {
-                for (int g = 0; g < S.G && intact; ++g) {
-                    on_ctx(g);
-                    intact = adb_select_generation() == P.generation[g];
-                }
-                on_ctx(0);
-            }
-            if (intact) {
-                AggJob job;
-                memset(&job, 0, sizeof job);
-                job.fused = 1;
-                P.active = 0;
-                run_shards(agg_shard, &job);
-                if (shard_errs(&job.err)) return -1;
-                *h = job.h;
-                return 0;
-            }
+            AggJob job;
+            memset(&job, 0, sizeof job);
+            job.fused = P.aggregated ? 2 : 1;
+            run_shards(agg_shard, &job);
+            if (job.fused == 2) lazy_done(&P);
+            else P.aggregated = 1;
+            if (shard_errs(&job.err)) return -1;
+            *h = job.h;
+            return 0;
         }
     }
     if (stage(r, NULL, &v)) return -1;
@@ -2101,7 +2214,8 @@ char *print(Result **results, int result_num, Status *ret_status) {
     t_err[0] = '\0';
     Text t = {0};
     void *host = NULL;
-    if (flush_pending()) return op_fail(ret_status, "print");
+    for (int i = 0; i < result_num; ++i)
+        if (results[i] && resolve_payload(results[i]->payload)) return op_fail(ret_status, "print");
     if (text_room(&t, 16)) goto oom;
     t.s[0] = '\0';
     for (int i = 0; i < result_num; ++i) {

@@ -473,6 +473,8 @@ def run_engine(args):
     e2e = measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, (g_sum, g_cnt))
     if rank == 0:
         cold = e2e.pop("cold", None)
+        for k_, v_ in (e2e.pop("configs", None) or {}).items():
+            line[k_] = v_
         line["e2e"] = e2e
         if cold is not None:
             line["e2e_cold"] = cold
@@ -587,9 +589,11 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
             raise SystemExit("fetch/sum: " + L.adb_host_last_error().decode())
         total = C.cast(r_.contents.payload, C.POINTER(C.c_long))[0]
         hits = s_.contents.num_tuples
-        for h_ in (s_, f_, r_):
-            api.drop(h_)
+        trio[0], trio[1], trio[2] = s_, f_, r_
+        L.adb_host_results_drop(trio, 3)        # what free_client_context does per handle
         return total, hits
+
+    trio = (q.RP * 3)()
 
     def step():
         tot = hits = 0
@@ -632,13 +636,20 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
                    "and the exchanged aggregate (24 B) after sum; wall clock; see `e2e_cold` for the "
                    "H2D-inclusive figure",
            "check": {"sum": tot, "hits": hits, "equals_device_resident_chain": True}}
+    for (a, b) in hcols:
+        L.adb_host_column_invalidate(C.byref(a))
+        L.adb_host_column_invalidate(C.byref(b))
     for g, b in bufs:
         lib.adb_ctx_select(g)
         b.free()
     lib.adb_ctx_select(0)
-    for (a, b) in hcols:
-        L.adb_host_column_invalidate(C.byref(a))
-        L.adb_host_column_invalidate(C.byref(b))
+    # BASELINE configs 2 and 3 through the same operator API and the same G GPUs
+    if not args.no_configs:
+        try:
+            out["configs"] = {"config2_shared_scan": api_shared_scan(eng, api, q, G, sync_all),
+                              "config3_index": api_index(eng, api, q, G, sync_all)}
+        except Exception as e:                              # the headline line must survive
+            out["configs"] = {"error": repr(e)}
     # cold: HOST columns, re-uploaded by the shim inside every timed step
     if world == 1 and not args.no_cold:
         c1, c2 = cols[0]
@@ -670,6 +681,203 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
                        "check": {"sum": ctot, "hits": chits}}
     if dist is not None:
         dist.barrier(group=args.gloo)
+    return out
+
+
+def adopt_sharded(eng, api, q, G, rows, fill, name, **flags):
+    """A Column of `rows` rows whose shards are generated on the GPUs (fill(g, first_row, count) ->
+    DevBuf on the current context) and adopted by the shim (no host copy)."""
+    lib, L = eng.lib, api.lib
+    S = ((rows + G - 1) // G + 31) // 32 * 32
+    ptrs, bufs = (C.c_void_p * G)(), []
+    for g in range(G):
+        eng._ck(lib.adb_ctx_select(g))
+        cnt = max(0, min(S, rows - g * S))
+        b = fill(g, g * S, max(cnt, 1))
+        eng.sync()
+        bufs.append((g, b))
+        ptrs[g] = b.ptr
+    eng._ck(lib.adb_ctx_select(0))
+    col = q.Column()
+    col.name = name
+    col.row_count = rows
+    for k, v in flags.items():
+        setattr(col, k, v)
+    assert L.adb_host_column_adopt_shards(C.byref(col), ptrs, S) == 0, L.adb_host_last_error()
+    return col, bufs
+
+
+def free_sharded(eng, api, col, bufs):
+    api.lib.adb_host_column_invalidate(C.byref(col))
+    for g, b in bufs:
+        eng.lib.adb_ctx_select(g)
+        b.free()
+    eng.lib.adb_ctx_select(0)
+
+
+def api_shared_scan(eng, api, q, G, sync_all, n=100_000_000, nq=100):
+    """BASELINE config 2: 100 concurrent range selects over a 100 M-row column in one
+    shared_select call of the operator API (query.h:36; the dispatcher's batch_execute,
+    server.c:366-393), the column row-range sharded over the G GPUs."""
+    from analytical_database_b200 import synth
+    L = api.lib
+    peak, _ = measured_peak()
+    col, bufs = adopt_sharded(eng, api, q, G, n, lambda g, first, cnt: eng.synth_uniform(cnt, SEED, first, 0, n), b"c2")
+    rng = np.random.default_rng(SEED)
+    lows = rng.integers(0, n - n // 1000, nq).astype(np.int32)
+    highs = (lows + n // 1000).astype(np.int32)
+    ops = (q.SelectOperator * nq)()
+    for k in range(nq):
+        ops[k].low, ops[k].high, ops[k].has_low, ops[k].has_high = int(lows[k]), int(highs[k]), 1, 1
+    st = q.Status(99, None)
+
+    def run(keep=False):
+        res = L.shared_select(ops, nq, C.byref(col), C.byref(st))
+        if st.code != q.OK or not res:
+            raise RuntimeError("shared_select: " + L.adb_host_last_error().decode())
+        if not keep:                            # timed form: the batch's handles go the way
+            L.adb_host_results_drop(res, nq)    # free_client_context releases them
+            q._libc.free(C.cast(res, C.c_void_p))
+            return None, None
+        hs = [res[k].contents.num_tuples for k in range(nq)]
+        handles = [C.pointer(res[k].contents) for k in range(nq)]
+        q._libc.free(C.cast(res, C.c_void_p))
+        if keep:
+            return hs, handles
+        for h_ in handles:
+            api.drop(h_)
+        return hs, None
+    for _ in range(2):
+        run()
+    sync_all()
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run()
+    sync_all()
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    # oracle window: the first 4 M rows regenerated on the host, ten of the queries
+    hs, handles = run(keep=True)
+    cpu, kind, _ = cpu_ops()
+    W = 1 << 22
+    win = synth.uniform(W, SEED, 0, 0, n)
+    ok = True
+    for k in range(0, nq, 10):
+        exp = cpu.select_scan(win, int(lows[k]), int(highs[k]))
+        got = api.tuples(handles[k])
+        ok = ok and got.size >= exp.size and np.array_equal(got[:exp.size], exp) and \
+            (got.size == exp.size or got[exp.size] >= W) and bool(np.all(np.diff(got) > 0))
+    for h_ in handles:
+        api.drop(h_)
+    free_sharded(eng, api, col, bufs)
+    alg = 4.0 * n + 4.0 * sum(hs)
+    if not ok:
+        raise SystemExit("PARITY FAILURE: shared_select window differs from the reference")
+    return {"rows": n, "queries": nq, "hits": int(sum(hs)), "ms": ms, "gpus": G,
+            "rows_per_s": n / (ms * 1e-3), "pred_evals_per_s": n * nq / (ms * 1e-3),
+            "algorithmic_bytes": alg, "formula": "4N + 4*sum(H_q)", "alg_gbs": alg / (ms * 1e-3) / 1e9,
+            "frac_of_peak": alg / (ms * 1e-3) / 1e9 / (peak * G),
+            "frac_of_nominal": alg / (ms * 1e-3) / 1e9 / (NOMINAL_GBS * G),
+            "through": "shared_select of include/adb_query_api.h: one slab per GPU, one Result per query; "
+                       "wall clock incl. the host reading all counts",
+            "parity": f"first {W} rows x 10 queries vs {kind} + ascending order of every checked list"}
+
+
+def api_index(eng, api, q, G, sync_all, n=500_000_000):
+    """BASELINE config 3: index build + range select + fetch over 500 M rows through the operator
+    API.  The indexed key is a permutation of 0..n-1 (unique keys: any correct sort equals the
+    reference's), (row * mul + add) mod n, so the oracle is a closed form: the
+    row holding key v is inv(mul) * (v - add) mod n -- checked against the reference's own index
+    build in tests/test_gpu_index_build.py."""
+    from analytical_database_b200 import synth
+    L, lib = api.lib, eng.lib
+    peak, _ = measured_peak()
+    mul, add = 387_420_489, 123_456_789              # 3^18: coprime with n = 2^8 * 5^9 * ...
+    import math
+    assert math.gcd(mul, n) == 1
+    inv = pow(mul, -1, n)
+
+    def fill_key(g, first, cnt):
+        b = eng.alloc_i32(cnt)
+        eng._ck(lib.adb_synth_affine(b.i32(), cnt, first, mul, add, n))
+        return b
+    key, kb = adopt_sharded(eng, api, q, G, n, fill_key, b"key", has_index=True, sorted=False, clustered=False)
+    pay, pb = adopt_sharded(eng, api, q, G, n, lambda g, first, cnt: eng.synth_uniform(cnt, 8, first, 0, 10000), b"pay")
+    arr = (C.POINTER(q.Column) * 2)(C.pointer(key), C.pointer(pay))
+    sync_all()
+    t0 = time.perf_counter()
+    if L.adb_host_index_build(arr, 2, 0) != 0:
+        raise RuntimeError("adb_host_index_build: " + L.adb_host_last_error().decode())
+    build_s = time.perf_counter() - t0
+    out = {"rows": n, "gpus": G, "index": "btree, unclustered (B+-tree descent + sorted-array slices, "
+           "range-partitioned by index order over the GPUs)",
+           "build_s_incl_host_copy": build_s,
+           "build_note": "adb_host_index_build: engine radix sort + 6 GB of (values, size_t positions) copied "
+                         "back into the catalog's host arrays, which the unchanged plumbing persists"}
+    hv = np.ctypeslib.as_array(key.index.contents.values, shape=(n,))
+    hp = np.ctypeslib.as_array(key.index.contents.positions, shape=(n,))
+    ok = bool(np.array_equal(hv[:1 << 20], np.arange(1 << 20, dtype=np.int32)))
+    vs = np.arange(n - (1 << 20), n, dtype=np.int64)
+    ok = ok and bool(np.array_equal(hp[n - (1 << 20):], ((vs - add) % n * inv % n).astype(np.uint64)))
+    st = q.Status(99, None)
+    cases = {}
+    for sel in (0.0002, 0.01, 0.1):
+        lo = n // 7
+        hi = lo + int(n * sel)
+        blo, bhi = C.c_int(lo), C.c_int(hi)
+
+        def run(keep=False):
+            s_ = L.select_column(C.byref(key), C.byref(blo), C.byref(bhi), C.byref(st))
+            if st.code != q.OK:
+                raise RuntimeError("select_column: " + L.adb_host_last_error().decode())
+            f_ = L.fetch_column(C.byref(pay), s_, C.byref(st))
+            if st.code != q.OK:
+                raise RuntimeError("fetch_column: " + L.adb_host_last_error().decode())
+            h = s_.contents.num_tuples
+            if keep:
+                return h, s_, f_
+            api.drop(s_)
+            api.drop(f_)
+            return h, None, None
+        for _ in range(2):
+            run()
+        sync_all()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            h, _, _ = run()
+        sync_all()
+        ms = 1e3 * (time.perf_counter() - t0) / reps
+        # oracle: the first and last 2^20 tuples of the value-ordered result
+        h, s_, f_ = run(keep=True)
+        gpos, gval = api.tuples(s_), api.tuples(f_)
+        W = min(h, 1 << 20)
+        for a0 in (0, h - W):
+            vs = np.arange(lo + a0, lo + a0 + W, dtype=np.int64)
+            epos = ((vs - add) % n * inv % n).astype(np.int32)
+            z = synth.mix64(8, epos.astype(np.uint64))
+            evals = (((z >> np.uint64(32)) * np.uint64(10000)) >> np.uint64(32)).astype(np.int32)
+            ok = ok and h == hi - lo and bool(np.array_equal(gpos[a0:a0 + W], epos)) and \
+                bool(np.array_equal(gval[a0:a0 + W], evals))
+        api.drop(s_)
+        api.drop(f_)
+        alg = 8.0 * h + 12.0 * h
+        cases[f"sel_{sel}"] = {"hits": int(h), "ms": ms, "algorithmic_bytes": alg,
+                               "formula": "select 4H (int32 index positions) + 4H out, fetch 12H",
+                               "alg_gbs": alg / (ms * 1e-3) / 1e9,
+                               "frac_of_peak": alg / (ms * 1e-3) / 1e9 / (peak * G),
+                               "gathers_per_s": h / (ms * 1e-3)}
+    out["cases"] = cases
+    out["parity"] = "index arrays + first/last 2^20 tuples of every result (positions and fetched values) vs the closed form of the permutation"
+    ix = key.index.contents
+    q._libc.free(C.cast(ix.values, C.c_void_p))
+    q._libc.free(C.cast(ix.positions, C.c_void_p))
+    q._libc.free(C.cast(key.index, C.c_void_p))
+    key.index = None
+    free_sharded(eng, api, key, kb)
+    free_sharded(eng, api, pay, pb)
+    if not ok:
+        raise SystemExit("PARITY FAILURE: index select / fetch differs from the closed-form oracle")
     return out
 
 
@@ -888,6 +1096,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip BASELINE configs 2 (shared scan) and 3 (index) through the operator API")
     ap.add_argument("--no-join", action="store_true", help="skip the hash-join measurement (config 4)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: aggregate exchange through the engine's peer-memory kernel or NCCL")

@@ -283,6 +283,21 @@ ADB_API adb_status adb_chain_select_fetch_agg(const int32_t *d_sel_col, const in
                                       int64_t n, const int32_t *lo, const int32_t *hi,
                                       int32_t *d_pos_out, int32_t *d_val_out,
                                       int64_t *d_count, adb_agg *d_agg);
+/* The chain with NEITHER handle materialised ("select -> fetch -> sum
+ * without materialising s / f ... cuts the chain from 4N + 20H to 4N + 4H bytes"): one kernel
+ * scans d_sel_col and gathers + folds d_fetch_col at every hit.  d_count and d_agg are device
+ * outputs, h_agg optional (synchronises).  Likewise adb_select_emit_fetch_agg[_exchange] with
+ * d_pos_out == d_val_out == NULL aggregates the pending select's hits without writing them and
+ * leaves the select pending. */
+ADB_API adb_status adb_chain_select_agg(const int32_t *d_sel_col, const int32_t *d_fetch_col, int64_t n,
+                                const int32_t *lo, const int32_t *hi, int64_t *d_count, adb_agg *d_agg,
+                                adb_agg *h_agg);
+/* How adb_chain_select_fetch_agg cuts a shard into row slices whose predicate pass (slice k+1)
+ * overlaps the expansion + gather + aggregate of slice k on a second, higher-priority stream:
+ * slices = 0 or 1 is the plain two-kernel chain (the default: measured, slicing gains nothing);
+ * cps_div: each slice's grids fill 1/cps_div of the resident CTA slots.  Results are identical
+ * for every setting (the chunks are numbered through the whole shard). */
+ADB_API adb_status adb_chain_config(int32_t slices, int32_t cps_div);
 
 /* ---- batched shared scan -- replaces shared_select + select_task, src/query.c:450-583
  * One pass over d_col evaluates q_count (<= ADB_MAX_BATCH, the dispatcher's chunk,
@@ -401,6 +416,12 @@ ADB_API adb_status adb_route_pairs(const int32_t *d_val, const int32_t *d_pos, i
  * analytical-database_b200/synth.py produces with numpy. */
 ADB_API adb_status adb_synth_uniform(int32_t *d_out, int64_t n, uint64_t seed, uint64_t first_row,
                              int32_t lo, uint32_t span);
+/* d_out[i] = ((first_row + i) * mul + add) mod modulus (mul, add < modulus <= 2^31): with
+ * gcd(mul, modulus) = 1 a permutation of 0 .. modulus-1 -- the unique-key indexed column of
+ * BASELINE config 3 (the reference's own M3 experiment uses a random permutation,
+ * project_tests/experiment_scripts/data_generation.py:216-218). */
+ADB_API adb_status adb_synth_affine(int32_t *d_out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add,
+                            uint64_t modulus);
 
 #ifdef __cplusplus
 }

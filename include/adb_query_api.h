@@ -174,6 +174,9 @@ int adb_host_column_histogram(Column *column, int bin_size, unsigned long counts
  * in host/free_interpose.c. */
 void adb_host_result_release(Result *result);
 void adb_host_payload_freed(void *payload);       /* what the interposer calls */
+/* release + free(payload) + free(Result) for n Results at once (what free_client_context does
+ * per handle, src/client_context.c:76-90, with the release hook applied) */
+void adb_host_results_drop(Result **results, int n);
 /* Copy a result's tuples to host memory (what print does); returns 0 on success. */
 int adb_host_result_to_host(const Result *result, void *dst);
 const char *adb_host_last_error(void);

@@ -80,6 +80,7 @@ HOOKS = {
     "adb_host_column_histogram": (C.c_int, [C.POINTER(Column), C.c_int, C.POINTER(C.c_ulong)]),
     "adb_host_result_release": (None, [RP]),
     "adb_host_payload_freed": (None, [C.c_void_p]),
+    "adb_host_results_drop": (None, [RPP, C.c_int]),
     "adb_host_result_to_host": (C.c_int, [RP, C.c_void_p]),
     "adb_host_last_error": (C.c_char_p, []),
     "adb_host_live_device_results": (C.c_long, []),

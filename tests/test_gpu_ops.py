@@ -138,11 +138,16 @@ def test_add_sub_wrap(eng, port, rng, n):
     assert np.array_equal(eng.ewise(da, db, n, True).to_host(n), port.sub(a, b))
 
 
+@pytest.mark.parametrize("slices,cps_div", [(1, 2), (2, 1), (3, 2), (7, 4), (16, 2)],
+                         ids=["plain", "2slices", "3slices", "7slices", "16slices"])
 @pytest.mark.parametrize("n", [0, 1, 513, 4097, 1_000_003])
-def test_chain_matches_oracle_and_reference(eng, port, rng, n):
+def test_chain_matches_oracle_and_reference(eng, port, rng, n, slices, cps_div):
     """s=select(col1,lo,hi); f=fetch(col2,s); a=sum(f)/min/max/avg -- the north-star chain
-    (predicate pass + expansion with the gather and the aggregates fused in)."""
+    (predicate pass + expansion with the gather and the aggregates fused in), plain and cut into
+    row slices whose predicate pass overlaps the previous slice's expansion (adb_chain_config):
+    every setting must give the same positions, values and aggregates."""
     import ctypes as C
+    eng._ck(eng.lib.adb_chain_config(slices, cps_div))
     from oracle import oracle
     ref = oracle.reference("O2")
     sel = rng.integers(-n // 2 - 1, n // 2 + 1, n).astype(np.int32)
@@ -174,6 +179,50 @@ def test_chain_matches_oracle_and_reference(eng, port, rng, n):
         if h:
             assert agg.min == port.min(exp_val) and agg.max == port.max(exp_val)
             assert agg.avg == port.avg(exp_val)
+    eng._ck(eng.lib.adb_chain_config(0, 2))
+
+
+@pytest.mark.parametrize("n", [0, 1, 513, 4097, 1_000_003])
+def test_unmaterialised_chain_matches_oracle(eng, port, rng, n):
+    """adb_chain_select_agg: select -> fetch -> sum/min/max in ONE kernel with neither handle
+    materialised (SURVEY.md 8f rank 3, 4N + 4H bytes), and the aggregate-only form of the deferred
+    emit (adb_select_emit_fetch_agg with NULL outputs), against the oracle's chain."""
+    import ctypes as C
+    from analytical_database_b200.engine import _AggStruct
+    sel = rng.integers(-n // 2 - 1, n // 2 + 1, n).astype(np.int32)
+    if n > 100000:
+        sel[200000:260000] = 7
+    fet = rng.integers(I32MAX - 10000, I32MAX, n, dtype=np.int64).astype(np.int32)
+    ds, df = eng.upload(sel), eng.upload(fet)
+    dcnt, dagg = eng.alloc(8), eng.alloc(64)
+    for lo, hi in [(None, None), (-100, 5000), (0, None), (None, -490000), (5, 5), (7, 8)]:
+        blo = C.c_int32(lo) if lo is not None else None
+        bhi = C.c_int32(hi) if hi is not None else None
+        plo = C.byref(blo) if blo is not None else None
+        phi = C.byref(bhi) if bhi is not None else None
+        hagg = _AggStruct()
+        eng._ck(eng.lib.adb_chain_select_agg(ds.i32(), df.i32(), n, plo, phi, dcnt.i64(), eng.agg_ptr(dagg),
+                                             C.byref(hagg)))
+        exp_pos = port.select_scan(sel, lo, hi)
+        exp_val = port.fetch(fet, exp_pos)
+        h = int(dcnt.to_host(1, np.int64)[0])
+        assert h == exp_pos.size and hagg.count == h and hagg.sum == port.sum(exp_val)
+        if h:
+            assert hagg.min == port.min(exp_val) and hagg.max == port.max(exp_val)
+        # the deferred form: count, aggregate unwritten, aggregate again, then write
+        hc = C.c_int64(0)
+        eng._ck(eng.lib.adb_select_count_base(ds.i32(), n, plo, phi, 0, None, C.byref(hc)))
+        gen = eng.lib.adb_select_generation()
+        for _ in range(2):
+            h2 = _AggStruct()
+            eng._ck(eng.lib.adb_select_emit_fetch_agg(df.i32(), None, None, eng.agg_ptr(dagg), C.byref(h2)))
+            assert (h2.sum, h2.count) == (hagg.sum, h) and eng.lib.adb_select_generation() == gen
+        pos, val = eng.alloc_i32(max(h, 1)), eng.alloc_i32(max(h, 1))
+        h3 = _AggStruct()
+        eng._ck(eng.lib.adb_select_emit_fetch_agg(df.i32(), pos.i32(), val.i32(), eng.agg_ptr(dagg), C.byref(h3)))
+        assert (h3.sum, h3.count) == (hagg.sum, h)
+        assert np.array_equal(pos.to_host(h), exp_pos) and np.array_equal(val.to_host(h), exp_val)
+        pos.free(), val.free()
 
 
 def test_synth_twin(eng):

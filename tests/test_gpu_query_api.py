@@ -517,6 +517,82 @@ def test_random_walk_over_the_operator_api(api, cpu):
     assert api.lib.adb_host_live_device_results() <= live0
 
 
+def test_lazy_handles_are_written_only_when_read(api, cpu, rng):
+    """s=select / f=fetch / a=sum(f) answers the aggregate without writing s
+    or f (4N + 4H bytes); the handles are written when -- and only when -- somebody reads them,
+    also after later selects have taken the bitmap over (recipes re-run the predicate pass)."""
+    import analytical_database_b200 as adb
+    eng = adb.Engine(0)                                   # same library: launch counters
+    n = 200_003
+    c1, c4, lo, hi = _chain_inputs(rng, n)
+    col1, col4 = api.column(c1), api.column(c4)
+    api.lib.adb_host_column_upload(C.byref(col1)), api.lib.adb_host_column_upload(C.byref(col4))
+    epos = cpu.select_scan(c1, lo, hi)
+    evals = cpu.fetch(c4, epos)
+    G = api.lib.adb_host_gpus()
+    live0 = api.lib.adb_host_live_device_results()
+
+    def chain(lo_, hi_):
+        s_ = api.select_column(col1, lo_, hi_)
+        f_ = api.fetch_column(col4, s_)
+        a_ = api.sum_result(f_)
+        return s_, f_, a_
+    # (1) released unread: per GPU the predicate pass (mask, total, publish) and ONE gather+fold
+    # kernel (+ publish on GPU 0) -- no expansion writes, no fetch kernel, no aggregate kernel
+    l0 = eng.lib.adb_launch_count_all()
+    s, f, a = chain(lo, hi)
+    assert int(api.tuples(a)[0]) == cpu.sum(evals)
+    launches = eng.lib.adb_launch_count_all() - l0
+    assert launches <= 4 * G + 1, launches
+    for r in (s, f, a):                                   # select first: the fetch stays unwritten
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == live0
+    # (2) several chains in a row, all handles alive (the server's handles live until the client
+    # disconnects): nothing is written until the end, then everything is read back in any order
+    kept = []
+    for k in range(5):
+        lo_k, hi_k = lo + 37 * k, hi - 11 * k
+        s, f, a = chain(lo_k, hi_k)
+        ep = cpu.select_scan(c1, lo_k, hi_k)
+        assert int(api.tuples(a)[0]) == cpu.sum(cpu.fetch(c4, ep))
+        kept.append((s, f, a, ep))
+    for k in (3, 0, 4, 1, 2):
+        s, f, a, ep = kept[k]
+        if k % 2:
+            assert np.array_equal(api.tuples(f), cpu.fetch(c4, ep))
+            assert np.array_equal(api.tuples(s), ep)
+        else:
+            assert np.array_equal(api.tuples(s), ep)
+            mx = api.unary("max", f)                      # an aggregate of a demoted handle
+            assert int(api.tuples(mx)[0]) == cpu.max(cpu.fetch(c4, ep))
+            assert np.array_equal(api.tuples(f), cpu.fetch(c4, ep))
+            api.drop(mx)
+    for s, f, a, _ in kept:
+        for r in (f, s, a):
+            api.drop(r)
+    # (3) second aggregate on the same handle writes on the way; a third reads the written vector
+    s, f, a = chain(lo, hi)
+    av = api.unary("average", f)
+    assert api.tuples(av)[0].tobytes() == np.float64(cpu.avg(evals)).tobytes()
+    mn = api.unary("min", f)
+    assert int(api.tuples(mn)[0]) == cpu.min(evals)
+    assert np.array_equal(api.tuples(s), epos) and np.array_equal(api.tuples(f), evals)
+    for r in (s, f, a, av, mn):
+        api.drop(r)
+    # (4) the select is released, its unwritten fetch lives on through two more selects and a
+    # column invalidation, and is then read
+    s, f, a = chain(lo, hi)
+    api.drop(s)
+    t1 = api.select_column(col4, None, I32MAX - 9000)
+    t2 = api.select_column(col1, 0, 5)
+    api.lib.adb_host_column_invalidate(C.byref(col4))
+    assert np.array_equal(api.tuples(f), evals)
+    assert np.array_equal(api.tuples(t1), cpu.select_scan(c4, None, I32MAX - 9000))
+    for r in (f, a, t1, t2):
+        api.drop(r)
+    assert api.lib.adb_host_live_device_results() == live0
+
+
 # ---- one process, several GPUs: the cases only a sharded layout has ---------------------------
 def test_sharded_lists_that_are_not_row_aligned(api, cpu, rng):
     """Position lists in index order, from a join, or built by foreign code name rows of any
