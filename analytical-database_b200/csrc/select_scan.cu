@@ -174,10 +174,7 @@ template <> struct ChainOf<true> { using type = ChainArgsX; };
 __device__ __forceinline__ const ChainArgs &chain_of(const ChainArgs &a) { return a; }
 __device__ __forceinline__ const ChainArgs &chain_of(const ChainArgsX &a) { return a.c; }
 
-// STORE = false: the aggregate-only form: the hit rows are gathered and
-// folded but neither the position list nor the value vector is written -- the handles stay
-// unmaterialised, the bitmap stays where it is for whoever reads them later.
-template <bool PAIRS, bool FETCH, bool EXCH = false, bool STORE = true>
+template <bool PAIRS, bool FETCH, bool EXCH = false>
 __global__ void __launch_bounds__(SEL_THREADS)
 expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
               uint32_t chunk_rows, uint32_t num_chunks, const int32_t *__restrict__ pos_in,
@@ -210,7 +207,7 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
         if (w == warp) my_count = c;
     }
     const uint32_t chunk = first_chunk + warp;
-    if (STORE && chunk == num_chunks - 1 && lane == 0) *d_count = (int64_t)base + my_count;
+    if (chunk == num_chunks - 1 && lane == 0) *d_count = (int64_t)base + my_count;
     const bool active = chunk < chunk_end && my_count != 0;
     if (!FETCH && !active) return;
 
@@ -297,11 +294,9 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
 #pragma unroll
                             for (int k = 0; k < GB; ++k)
                                 if (row[k] >= 0) {
-                                    if (STORE) {
-                                        const uint32_t o = out_off + done + i0 + k * kWarp + lane;
-                                        out[o] = p[k];
-                                        vout[o] = v[k];
-                                    }
+                                    const uint32_t o = out_off + done + i0 + k * kWarp + lane;
+                                    out[o] = p[k];
+                                    vout[o] = v[k];
                                     acc.add(v[k]);
                                 }
                         }
@@ -329,6 +324,61 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
                 __syncthreads();
                 if (warp == 0) chain_exchange(chx.px, (int)lane);
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// bitmap_gather_agg_kernel: the aggregate-only resolution of a pending select (SURVEY.md 8f rank
+// 3).  No ranking, no staging, no stores: order does not matter to sum / min / max, so every
+// lane walks its own bitmap words and gathers + folds the fetch column at each set bit.  A
+// lane's gathers are serialised by their round trip, the 9472 warps' are not.  The bitmap is
+// only read: the select stays pending for whoever wants its handles written later.
+// ------------------------------------------------------------------------------------------
+template <bool EXCH>
+__global__ void __launch_bounds__(SEL_THREADS)
+bitmap_gather_agg_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
+                         uint32_t chunk_rows, uint32_t num_chunks, const typename ChainOf<EXCH>::type chx) {
+    const ChainArgs &ch = chain_of(chx);
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * SEL_WARPS + warp;
+    const int32_t *__restrict__ fcol = ch.fetch_col;
+    AggAcc acc{0, INT32_MAX, INT32_MIN};
+    uint32_t my_count = 0;
+    if (chunk < num_chunks) my_count = counts[chunk];
+    if (my_count) {
+        const uint32_t row_begin = chunk * chunk_rows;
+        const uint32_t nwords = chunk_rows / 32;                // a multiple of 16
+        const uint32_t *__restrict__ words = mask + row_begin / 32;
+        // four words per lane and step (rows 32 apart per lane: neighbouring lanes' hits share sectors)
+        for (uint32_t w0 = 0; w0 < nwords; w0 += 4 * kWarp) {
+            uint32_t m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w = w0 + k * kWarp + lane;
+                m[k] = w < nwords ? words[w] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t bits = m[k];
+                const uint32_t row0 = row_begin + (w0 + k * kWarp + lane) * 32;
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    acc.add(ld_gather(fcol + row0 + b));
+                }
+            }
+        }
+    }
+    const bool last = agg_grid_fold<SEL_THREADS>(acc, lane == 0 ? (int64_t)my_count : 0, ch.agg_out, ch.agg_scratch,
+                                                 ch.agg_ticket);
+    if constexpr (EXCH) {
+        if (last) {
+            __threadfence();
+            __syncthreads();
+            if (warp == 0) chain_exchange(chx.px, (int)lane);
         }
     }
 }
@@ -472,13 +522,11 @@ int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s) {
     const ChainArgs c{a.fetch_col, a.val_out, a.agg_out, a.agg_scratch, a.agg_ticket};
     if (!a.out && !a.val_out) {                     // aggregate only: nothing is materialised
         if (a.px.world)
-            launch_pdl(expand_kernel<false, true, true, false>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts,
-                       g.chunk_rows, g.num_chunks, (const int32_t *)nullptr, a.base_pos, (int32_t *)nullptr,
-                       a.d_count, ChainArgsX{c, a.px}, 0u, g.num_chunks);
+            launch_pdl(bitmap_gather_agg_kernel<true>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts, g.chunk_rows,
+                       g.num_chunks, ChainArgsX{c, a.px});
         else
-            launch_pdl(expand_kernel<false, true, false, false>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts,
-                       g.chunk_rows, g.num_chunks, (const int32_t *)nullptr, a.base_pos, (int32_t *)nullptr,
-                       a.d_count, c, 0u, g.num_chunks);
+            launch_pdl(bitmap_gather_agg_kernel<false>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts, g.chunk_rows,
+                       g.num_chunks, c);
         return 1;
     }
     if (a.px.world)

@@ -419,6 +419,56 @@ def run_engine(args):
                 "adb_chain_select_fetch_agg_exchange: the chain kernel of the rank's last shard folds the partials and exchanges them over NVLink peer memory (no separate launch, no NCCL call)"
                 if args.exchange == "peer" else "adb_agg_export + 2 NCCL all-reduces")
 
+    # ---- the same chain with NEITHER handle materialised (4N + 4H bytes):
+    # one kernel per shard scans col1 and gathers + folds col2 at every hit; the partials meet in
+    # the same exchange.  This is what the operator API runs when s and f are never read (e2e).
+    lazy = None
+    if not args.no_lazy:
+        lz_parts = eng.alloc(AGG_BYTES * max(len(my_shards), 1))
+        lz_out = eng.alloc(AGG_BYTES)
+
+        def lazy_step():
+            for i, (c1, c2) in enumerate(cols):
+                eng._ck(lib.adb_chain_select_agg(c1.i32(), c2.i32(), shard_rows, C.byref(blo), C.byref(bhi),
+                                                 res[i][2].i64(), AggP(lz_parts, i), None))
+            if dist is not None and args.exchange == "peer":
+                eng._ck(lib.adb_agg_combine_allreduce(AggP(lz_parts), len(cols), AggP(lz_out), None))
+            else:
+                eng._ck(lib.adb_agg_combine(AggP(lz_parts), len(cols), AggP(lz_out), None))
+        for _ in range(3):
+            lazy_step()
+        barrier()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record(stream)
+        for _ in range(args.steps):
+            lazy_step()
+        z1.record(stream)
+        barrier()
+        lz_ms = z0.elapsed_time(z1) / args.steps
+        la = eng.read_agg(lz_out)
+        lz_sum, lz_cnt = la.sum, la.count
+        if dist is not None:
+            t = torch.tensor([lz_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lz_ms = float(t.item())
+            if args.exchange != "peer":
+                t2 = torch.tensor([lz_sum, lz_cnt], dtype=torch.int64, device="cuda")
+                dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+                lz_sum, lz_cnt = int(t2[0].item()), int(t2[1].item())
+        if (lz_sum, lz_cnt) != (g_sum, g_cnt) and not args.shards_limit:
+            raise SystemExit(f"PARITY FAILURE: unmaterialised chain {(lz_sum, lz_cnt)} != materialised {(g_sum, g_cnt)}")
+        lz_bytes = 4.0 * rows_step + 4.0 * g_cnt
+        lz_gbs = lz_bytes / (lz_ms * 1e-3) / 1e9
+        lazy = {"value": rows_step / (lz_ms * 1e-3), "unit": UNIT, "ms_per_step": lz_ms,
+                "algorithmic_bytes_per_step": lz_bytes, "formula": "4N + 4H (SURVEY.md 8f rank 3)",
+                "achieved_gbs": lz_gbs, "frac_of_aggregate_peak": lz_gbs / (peak * max(world, 1)),
+                "frac_of_nominal": lz_gbs / (NOMINAL_GBS * max(world, 1)),
+                "kernel": "adb::scan_gather_agg_kernel (adb_chain_select_agg): predicate pass with the gather "
+                          "and the aggregates fused in, nothing written",
+                "equals_materialised_chain": True}
+        if rank == 0:
+            line["chain_unmaterialised"] = lazy
+
     # ---- selectivity sweep on one shard (SURVEY.md 8d lists 0.1 %, 1 %, 10 %, 50 %) -----------
     if rank == 0 and not args.no_sweep:
         sweep = {}
@@ -631,6 +681,9 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
            "api": "select_column -> fetch_column -> sum of include/adb_query_api.h (libadb_query.so = "
                   f"host/query_shim.c, adb_host_init_multi({G})): one call chain per column of "
                   f"{E2E_PART_ROWS} rows, each column row-range sharded over the {G} GPU(s) by the shim",
+           "bytes_model": "4N + 4H: s and f are lazy handles (host/query_shim.c) -- the aggregate gathers and folds "
+                          "the hit rows straight from the select's bitmap and neither list is written, because "
+                          "the harness, like a client that only prints the sum, never reads them",
            "mode": "warm: columns HBM-resident after load; bounds travel as kernel arguments "
                    "(no H2D copy); per column the host reads every shard's num_tuples (8 B) after select "
                    "and the exchanged aggregate (24 B) after sum; wall clock; see `e2e_cold` for the "
@@ -1096,6 +1149,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-lazy", action="store_true", help="skip the unmaterialised (4N + 4H) chain")
     ap.add_argument("--no-configs", action="store_true",
                     help="skip BASELINE configs 2 (shared scan) and 3 (index) through the operator API")
     ap.add_argument("--no-join", action="store_true", help="skip the hash-join measurement (config 4)")
