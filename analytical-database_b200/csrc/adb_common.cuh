@@ -351,7 +351,20 @@ struct SelectArgs {
     adb_agg *agg_out, *agg_scratch;
     unsigned int *agg_ticket;
     PeerExchange px;              // world != 0: the chain kernel finishes with the cross-rank exchange
+    // Small results go to the host through a mapped pinned mailbox (engine.cu read_back).  When
+    // pub is set, the kernel that produces the count / the aggregate stores it there itself
+    // (payload words, fence, then the sequence number at pub[kMboxWords]) and no separate
+    // publish kernel is launched.
+    unsigned long long *pub;
+    unsigned long long pub_seq;
 };
+constexpr uint32_t kMboxWords = 256;                  // 2 KB: 150 batch counts fit
+__device__ __forceinline__ void mbox_publish(volatile unsigned long long *pub, unsigned long long seq,
+                                             const unsigned long long *words, int n) {
+    for (int i = 0; i < n; ++i) pub[i] = words[i];
+    __threadfence_system();
+    pub[kMboxWords] = seq;
+}
 int launch_select(const SelectArgs &a, cudaStream_t s);
 // two-phase form: mask + per-chunk counts (+ total into a.d_count), then expand into a.out
 int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s);

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 
 #include "adb_common.cuh"
 
@@ -136,6 +137,17 @@ struct Engine {
     cudaEvent_t side_done = nullptr;
     adb_agg *slice_parts = nullptr;
     int chain_slices = 0, chain_cps_div = 2;        // ADB_CHAIN_SLICES (0 = by size), ADB_CHAIN_CPS_DIV
+    // Front cache of adb_alloc / adb_free.  Result buffers of one query shape come and go in
+    // the same few sizes; cudaMallocAsync / cudaFreeAsync cost 5-10 us each (r02h: 14 + 2 x 18 us
+    // per select -> fetch -> sum chain on 8 GPUs), a hit here is host bookkeeping.  Blocks keep
+    // the stream-ordered semantics of the pool: they are only ever reused on this context's
+    // stream.  live: block -> its size class.
+    struct CachedBlock { void *p; size_t bytes; };
+    static constexpr int kCacheSlots = 64;
+    CachedBlock cache[kCacheSlots];
+    int cache_n = 0;
+    size_t cache_bytes = 0, cache_cap = (size_t)16 << 30;
+    std::unordered_map<void *, size_t> *live = nullptr;
 };
 
 // One context per GPU of the box (several may share a device: a 1-GPU box then runs the
@@ -183,7 +195,7 @@ adb_status after_launch(const char *what, int launches) {
 // call; here a one-warp kernel at the end of the stream stores the words into mapped pinned
 // host memory, then a sequence number, and the host spins on that word.  The stream is polled
 // now and then so that a faulted kernel surfaces as an error instead of a hang.
-constexpr uint32_t kMboxWords = 256;                  // 2 KB: 150 batch counts fit
+using adb::kMboxWords;
 __global__ void publish_kernel(const unsigned long long *__restrict__ src, uint32_t words,
                                volatile unsigned long long *dst, unsigned long long seq) {
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
@@ -192,6 +204,7 @@ __global__ void publish_kernel(const unsigned long long *__restrict__ src, uint3
     if (threadIdx.x == 0) dst[kMboxWords] = seq;
 }
 
+static adb_status mbox_wait(unsigned long long seq, void *h_dst, size_t bytes);
 static adb_status read_back(void *h_dst, const void *d_src, size_t bytes) {
     if (bytes == 0) return ADB_OK;
     if (!g.mbox || bytes > kMboxWords * 8 || (bytes & 7u) || (reinterpret_cast<uintptr_t>(d_src) & 7u)) {
@@ -203,6 +216,11 @@ static adb_status read_back(void *h_dst, const void *d_src, size_t bytes) {
     publish_kernel<<<1, 64, 0, g.stream>>>(static_cast<const unsigned long long *>(d_src), (uint32_t)(bytes / 8),
                                            g.mbox_dev, seq);
     if (adb_status s = after_launch("publish", 1)) return s;
+    return mbox_wait(seq, h_dst, bytes);
+}
+
+// Spin until the kernel that carries sequence number `seq` has stored its words into the mailbox.
+static adb_status mbox_wait(unsigned long long seq, void *h_dst, size_t bytes) {
     const volatile unsigned long long *flag = g.mbox + kMboxWords;
     for (uint32_t spins = 1;; ++spins) {
         if (__atomic_load_n(const_cast<const unsigned long long *>(flag), __ATOMIC_ACQUIRE) == seq) break;
@@ -482,11 +500,16 @@ adb_status adb_init(int device_ordinal) {
     }
     g.launches = 0;
     g.ctx_index = g_cur;
+    g.live = new std::unordered_map<void *, size_t>();
+    g.cache_n = 0;
+    g.cache_bytes = 0;
+    if (const char *e = getenv("ADB_ALLOC_CACHE_MB")) g.cache_cap = (size_t)atol(e) << 20;
     g.up = true;
     return ADB_OK;
 }
 
 static adb_status shutdown_current();
+static void cache_flush(Engine &E);
 // Shuts down every context of the process (the hook is called once, from shutdown_server()).
 adb_status adb_shutdown(void) {
     const int keep = g_cur;
@@ -501,6 +524,9 @@ adb_status adb_shutdown(void) {
 static adb_status shutdown_current() {
     if (!g.up) return ADB_OK;
     cudaSetDevice(g.device);
+    cache_flush(g);
+    delete g.live;
+    g.live = nullptr;
     cudaStreamSynchronize(g.stream);
     cudaFree(g.sel_mask);
     cudaFree(g.sel_counts);
@@ -561,21 +587,101 @@ adb_status adb_set_stream(void *cuda_stream) {
     return ADB_OK;
 }
 
+// size classes: 256-byte steps up to 64 KB, then eight steps per power of two (<= 12.5 % slack)
+static size_t alloc_class(size_t bytes) {
+    if (bytes < 16) bytes = 16;
+    if (bytes <= (64u << 10)) return (bytes + 255) & ~(size_t)255;
+    size_t p2 = (size_t)1 << 16;
+    while (p2 < bytes) p2 <<= 1;                       // smallest power of two >= bytes
+    const size_t step = p2 >> 4;                       // 1/8 of the power of two below
+    return (bytes + step - 1) / step * step;
+}
+static void *cache_take(Engine &E, size_t cls) {
+    for (int i = 0; i < E.cache_n; ++i)
+        if (E.cache[i].bytes == cls) {
+            void *p = E.cache[i].p;
+            E.cache[i] = E.cache[--E.cache_n];
+            E.cache_bytes -= cls;
+            return p;
+        }
+    return nullptr;
+}
+// give every cached block back to the pool (before shutdown, or when the device runs short)
+static void cache_flush(Engine &E) {
+    for (int i = 0; i < E.cache_n; ++i) cudaFreeAsync(E.cache[i].p, E.stream);
+    E.cache_n = 0;
+    E.cache_bytes = 0;
+    cudaGetLastError();
+}
+
 adb_status adb_alloc(void **d_ptr, size_t bytes) {
     NEED_UP();
     if (!d_ptr) return fail(ADB_ERR_INVALID, "adb_alloc: NULL out pointer");
-    cudaError_t e = cudaMallocAsync(d_ptr, bytes ? bytes : 16, g.stream);
+    const size_t cls = alloc_class(bytes);
+    if (void *p = cache_take(g, cls)) {
+        (*g.live)[p] = cls;
+        *d_ptr = p;
+        return ADB_OK;
+    }
+    cudaError_t e = cudaMallocAsync(d_ptr, cls, g.stream);
+    if (e == cudaErrorMemoryAllocation && g.cache_n) {          // short of memory: drop the cache, once more
+        cudaGetLastError();
+        cache_flush(g);
+        cudaStreamSynchronize(g.stream);
+        e = cudaMallocAsync(d_ptr, cls, g.stream);
+    }
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
         return fail(ADB_ERR_NOMEM, "adb_alloc: out of device memory for %zu bytes", bytes);
     }
     CU(e);
+    (*g.live)[*d_ptr] = cls;
     return ADB_OK;
 }
 adb_status adb_free(void *d_ptr) {
     NEED_UP();
-    if (d_ptr) CU(cudaFreeAsync(d_ptr, g.stream));
+    if (!d_ptr) return ADB_OK;
+    auto it = g.live->find(d_ptr);
+    if (it == g.live->end()) {                      // not one of ours (or freed twice): let the runtime judge
+        CU(cudaFreeAsync(d_ptr, g.stream));
+        return ADB_OK;
+    }
+    const size_t cls = it->second;
+    g.live->erase(it);
+    if (g.cache_n < Engine::kCacheSlots && g.cache_bytes + cls <= g.cache_cap) {
+        g.cache[g.cache_n++] = Engine::CachedBlock{d_ptr, cls};
+        g.cache_bytes += cls;
+        return ADB_OK;
+    }
+    CU(cudaFreeAsync(d_ptr, g.stream));
     return ADB_OK;
+}
+// The same on context `ctx` from ANOTHER thread's point of view: served only when it needs no
+// CUDA call (a cache hit / room in the cache), so the caller neither switches devices nor wakes
+// the context's own thread.  ADB_ERR_INVALID-free protocol: returns 1 when served, 0 when the
+// caller must go through adb_alloc / adb_free on that context.  The context must be idle.
+int32_t adb_alloc_cached_on(int32_t ctx, void **d_ptr, size_t bytes) {
+    if (ctx < 0 || ctx >= ADB_MAX_CONTEXTS || !g_ctx[ctx].up || !d_ptr) return 0;
+    Engine &E = g_ctx[ctx];
+    const size_t cls = alloc_class(bytes);
+    void *p = cache_take(E, cls);
+    if (!p) return 0;
+    (*E.live)[p] = cls;
+    *d_ptr = p;
+    return 1;
+}
+int32_t adb_free_cached_on(int32_t ctx, void *d_ptr) {
+    if (ctx < 0 || ctx >= ADB_MAX_CONTEXTS || !g_ctx[ctx].up) return 0;
+    if (!d_ptr) return 1;
+    Engine &E = g_ctx[ctx];
+    auto it = E.live->find(d_ptr);
+    if (it == E.live->end()) return 0;
+    const size_t cls = it->second;
+    if (E.cache_n >= Engine::kCacheSlots || E.cache_bytes + cls > E.cache_cap) return 0;
+    E.live->erase(it);
+    E.cache[E.cache_n++] = Engine::CachedBlock{d_ptr, cls};
+    E.cache_bytes += cls;
+    return 1;
 }
 adb_status adb_upload_async(void *d_dst, const void *h_src, size_t bytes) {
     NEED_UP();
@@ -746,10 +852,16 @@ adb_status adb_select_count_base(const int32_t *d_col, int64_t n, const int32_t 
                                  int32_t base_pos, int64_t *d_count, int64_t *h_count) {
     adb::SelectArgs a;
     if (adb_status s = select_prepare("adb_select_count_base", d_col, nullptr, n, nullptr, lo, hi, d_count, &a, true)) return s;
+    // the host wants the count: the kernel that totals it also hands it over (no publish launch)
+    const bool fused_pub = h_count && g.mbox && a.n > 0;
+    if (fused_pub) { a.pub = g.mbox_dev; a.pub_seq = ++g.mbox_seq; }
     if (adb_status s = after_launch("select_count", adb::launch_select_mask(a, true, g.stream))) return s;
+    const unsigned long long seq = a.pub_seq;
+    a.pub = nullptr; a.pub_seq = 0;
     a.base_pos = base_pos;
     g.sel_pending = a;
     g.sel_ready = true;
+    if (fused_pub) return mbox_wait(seq, h_count, sizeof(int64_t));
     return finish_count(a.d_count, h_count);
 }
 
@@ -792,9 +904,22 @@ static adb_status emit_fetch_agg_impl(const int32_t *d_fetch_col, int32_t *d_pos
     a.fetch_col = d_fetch_col; a.val_out = d_val_out;
     a.agg_out = d_agg; a.agg_scratch = g.agg_scratch; a.agg_ticket = g.agg_ticket;
     if (px) a.px = *px;
+    const bool fused_pub = nostore && h_agg && g.mbox && a.n > 0;
+    if (fused_pub) { a.pub = g.mbox_dev; a.pub_seq = ++g.mbox_seq; }
     const int f_ = adb::launch_select_expand_fetch_agg(a, g.stream);
     if (f_ > 0) {
         if (adb_status s = after_launch("select_emit_fetch_agg", f_)) return s;
+        if (fused_pub) {
+            unsigned long long w[3];
+            if (adb_status s = mbox_wait(a.pub_seq, w, sizeof w)) return s;
+            h_agg->sum = (int64_t)w[0];
+            h_agg->count = (int64_t)w[1];
+            h_agg->min = (int32_t)(uint32_t)w[2];
+            h_agg->max = (int32_t)(uint32_t)(w[2] >> 32);
+            if (px && h_agg->count < 0)
+                return fail(ADB_ERR_CUDA, "aggregate exchange: a peer did not arrive within 2 s (epoch %u)", px->epoch);
+            return ADB_OK;
+        }
     } else if (nostore && a.n > 0) {
         return fail(ADB_ERR_INVALID, "adb_select_emit_fetch_agg: a select over %u rows cannot be aggregated unmaterialised", a.n);
     } else {

@@ -338,7 +338,8 @@ expand_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ co
 template <bool EXCH>
 __global__ void __launch_bounds__(SEL_THREADS)
 bitmap_gather_agg_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ counts,
-                         uint32_t chunk_rows, uint32_t num_chunks, const typename ChainOf<EXCH>::type chx) {
+                         uint32_t chunk_rows, uint32_t num_chunks, const typename ChainOf<EXCH>::type chx,
+                         unsigned long long *pub, unsigned long long pub_seq) {
     const ChainArgs &ch = chain_of(chx);
     pdl_launch_dependents();
     pdl_wait();
@@ -352,34 +353,61 @@ bitmap_gather_agg_kernel(const uint32_t *__restrict__ mask, const uint32_t *__re
         const uint32_t row_begin = chunk * chunk_rows;
         const uint32_t nwords = chunk_rows / 32;                // a multiple of 16
         const uint32_t *__restrict__ words = mask + row_begin / 32;
-        // four words per lane and step (rows 32 apart per lane: neighbouring lanes' hits share sectors)
-        for (uint32_t w0 = 0; w0 < nwords; w0 += 4 * kWarp) {
-            uint32_t m[4];
+        // BG words per lane and step.  A lane's gathers would be serialised by their round trip
+        // if it walked one word after the other; instead every round takes the next hit of EACH
+        // of the lane's words, so up to BG independent gathers are in flight per lane.
+        constexpr int BG = 8;
+        for (uint32_t w0 = 0; w0 < nwords; w0 += BG * kWarp) {
+            uint32_t m[BG];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < BG; ++k) {
                 const uint32_t w = w0 + k * kWarp + lane;
                 m[k] = w < nwords ? words[w] : 0u;
             }
+            const uint32_t row0 = row_begin + (w0 + lane) * 32;
+            uint32_t any = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t bits = m[k];
-                const uint32_t row0 = row_begin + (w0 + k * kWarp + lane) * 32;
-                while (bits) {
-                    const uint32_t b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    acc.add(ld_gather(fcol + row0 + b));
+            for (int k = 0; k < BG; ++k) any |= m[k];
+            while (any) {
+                int32_t v[BG];
+                uint32_t has = 0;
+#pragma unroll
+                for (int k = 0; k < BG; ++k) {
+                    v[k] = 0;
+                    if (m[k]) {
+                        const uint32_t b = __ffs(m[k]) - 1;
+                        m[k] &= m[k] - 1;
+                        v[k] = ld_gather(fcol + row0 + k * (kWarp * 32) + b);
+                        has |= 1u << k;
+                    }
+                }
+                any = 0;
+#pragma unroll
+                for (int k = 0; k < BG; ++k) {
+                    if (has & (1u << k)) acc.add(v[k]);
+                    any |= m[k];
                 }
             }
         }
     }
     const bool last = agg_grid_fold<SEL_THREADS>(acc, lane == 0 ? (int64_t)my_count : 0, ch.agg_out, ch.agg_scratch,
                                                  ch.agg_ticket);
+    if (!last) return;
     if constexpr (EXCH) {
-        if (last) {
-            __threadfence();
-            __syncthreads();
-            if (warp == 0) chain_exchange(chx.px, (int)lane);
-        }
+        __threadfence();
+        __syncthreads();
+        if (warp == 0) chain_exchange(chx.px, (int)lane);
+        __syncwarp();
+    }
+    // the host is waiting for the aggregate: hand it over from here (no publish kernel)
+    if (pub && threadIdx.x == 0) {
+        const volatile adb_agg *r = ch.agg_out;
+        if constexpr (EXCH) r = chx.px.final_out;
+        unsigned long long w[3];
+        w[0] = (unsigned long long)r->sum;
+        w[1] = (unsigned long long)r->count;
+        w[2] = (unsigned long long)(uint32_t)r->min | ((unsigned long long)(uint32_t)r->max << 32);
+        mbox_publish(pub, pub_seq, w, 3);
     }
 }
 
@@ -473,7 +501,7 @@ size_t select_mask_words(uint32_t n, int sm_count) {
 // two-phase form: the caller sizes the position list before expand_kernel runs).
 __global__ void __launch_bounds__(1024)
 count_total_kernel(const uint32_t *__restrict__ counts, uint32_t num_chunks,
-                   int64_t *__restrict__ d_count) {
+                   int64_t *__restrict__ d_count, unsigned long long *pub, unsigned long long pub_seq) {
     __shared__ unsigned long long s_w[32];
     unsigned long long acc = 0;
     for (uint32_t i = threadIdx.x; i < num_chunks; i += 1024) acc += counts[i];
@@ -484,6 +512,7 @@ count_total_kernel(const uint32_t *__restrict__ counts, uint32_t num_chunks,
         unsigned long long t = 0;
         for (int w = 0; w < 32; ++w) t += s_w[w];
         *d_count = (int64_t)t;
+        if (pub) mbox_publish(pub, pub_seq, &t, 1);         // the host is waiting for this count
     }
 }
 
@@ -496,7 +525,7 @@ int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s) {
     launch_pdl(mask_kernel, g.grid, SEL_THREADS, 0, s, a.val, a.d_n, a.n, a.range, g.chunk_rows,
                g.num_chunks, a.mask, a.counts, a.stable_val, 0u);
     if (!with_total) return 1;
-    count_total_kernel<<<1, 1024, 0, s>>>(a.counts, g.num_chunks, a.d_count);
+    count_total_kernel<<<1, 1024, 0, s>>>(a.counts, g.num_chunks, a.d_count, a.pub, a.pub_seq);
     return 2;
 }
 
@@ -523,10 +552,10 @@ int launch_select_expand_fetch_agg(const SelectArgs &a, cudaStream_t s) {
     if (!a.out && !a.val_out) {                     // aggregate only: nothing is materialised
         if (a.px.world)
             launch_pdl(bitmap_gather_agg_kernel<true>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts, g.chunk_rows,
-                       g.num_chunks, ChainArgsX{c, a.px});
+                       g.num_chunks, ChainArgsX{c, a.px}, a.pub, a.pub_seq);
         else
             launch_pdl(bitmap_gather_agg_kernel<false>, g.grid, SEL_THREADS, 0, s, a.mask, a.counts, g.chunk_rows,
-                       g.num_chunks, c);
+                       g.num_chunks, c, a.pub, a.pub_seq);
         return 1;
     }
     if (a.px.world)

@@ -164,6 +164,39 @@ static void op_ok(Status *st) {
     }
 }
 
+/* ---- optional host-side profile (ADB_SHIM_PROFILE=1): wall time per phase, printed by
+ * adb_host_shutdown / adb_host_profile_dump ------------------------------------------------- */
+#include <time.h>
+enum { PF_SELECT, PF_SELECT_JOB, PF_FETCH, PF_FETCH_JOB, PF_AGG, PF_AGG_JOB, PF_NEWRESULT, PF_RELEASE,
+       PF_FREE_JOB, PF_COUNT };
+static const char *const pf_names[PF_COUNT] = {"select_column", "  its shard job", "fetch_column", "  its shard job",
+                                               "aggregate", "  its shard job", "new_dev_result", "payload release",
+                                               "  free job"};
+static struct { int on; double t[PF_COUNT]; long n[PF_COUNT]; } PF;
+static inline double pf_now(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
+}
+#define PF_BEGIN(id) const double pf_t0_##id = PF.on ? pf_now() : 0.0
+#define PF_END(id)                                   \
+    do {                                             \
+        if (PF.on) {                                 \
+            PF.t[id] += pf_now() - pf_t0_##id;       \
+            ++PF.n[id];                              \
+        }                                            \
+    } while (0)
+void adb_host_profile_dump(void) {
+    if (!PF.on) return;
+    fprintf(stderr, "[adb shim profile] phase                 calls   total us    us/call\n");
+    for (int i = 0; i < PF_COUNT; ++i)
+        if (PF.n[i])
+            fprintf(stderr, "[adb shim profile] %-20s %7ld %10.0f %10.2f\n", pf_names[i], PF.n[i], PF.t[i],
+                    PF.t[i] / (double)PF.n[i]);
+    memset(PF.t, 0, sizeof PF.t);
+    memset(PF.n, 0, sizeof PF.n);
+}
+
 /* ---- one host thread per context ---------------------------------------------------------
  * An operator is a function run once per shard: the calling thread runs shard 0 (it stays on
  * context 0), worker g runs shard g on context g.  Workers spin for the next job for a while
@@ -312,9 +345,16 @@ static void free_shards(int32_t *const d[]) {
     int any = 0;
     for (int g = 0; g < MAXG; ++g) {
         job.d[g] = g < S.G ? d[g] : NULL;
+        /* the engine's front cache takes the block back without a CUDA call (and without waking
+         * GPU g's thread) whenever it has room */
+        if (job.d[g] && adb_free_cached_on(g, job.d[g])) job.d[g] = NULL;
         any |= job.d[g] != NULL;
     }
-    if (any) run_shards(free_shard, &job);
+    if (any) {
+        PF_BEGIN(PF_FREE_JOB);
+        run_shards(free_shard, &job);
+        PF_END(PF_FREE_JOB);
+    }
 }
 
 /* rows of shard g of a list of `rows` rows cut every S rows */
@@ -539,9 +579,14 @@ static int host_init(int first_device, int gpus) {
      * keep the freed space.  ADB_SHIM_NO_MALLOPT=1 leaves the process's malloc policy alone. */
     const char *nm = getenv("ADB_SHIM_NO_MALLOPT");
     if (!(nm && nm[0] && nm[0] != '0')) {
-        mallopt(M_MMAP_THRESHOLD, 32 << 20);         /* glibc's ceiling on 64-bit */
-        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        /* no mmap'd blocks at all: a 20 M-tuple handle's 80 MB payload would otherwise cost an
+         * mmap + munmap pair per operator (the threshold cannot be raised past 32 MB) */
+        mallopt(M_MMAP_MAX, 0);
+        mallopt(M_TRIM_THRESHOLD, -1);               /* never give heap back */
+        mallopt(M_TOP_PAD, 256 << 20);
     }
+    const char *pf = getenv("ADB_SHIM_PROFILE");
+    PF.on = pf && pf[0] && pf[0] != '0';
     const char *eager = getenv("ADB_SHIM_EAGER");
     S.lazy = !S.mirror && !(eager && eager[0] && eager[0] != '0');
     const char *mn = getenv("ADB_SHARD_MIN_ROWS");
@@ -618,6 +663,7 @@ static void result_buffers_free(DevResult *r) {
 
 void adb_host_shutdown(void) {
     if (!S.up) return;
+    adb_host_profile_dump();
     lock();
     if (P.active) lazy_done(&P);
     while (nR) lazy_done(&R[nR - 1]);
@@ -1130,9 +1176,11 @@ static int registry_take(const void *payload, DevResult *out) {
 
 void adb_host_payload_freed(void *payload) {
     if (S.nlive <= 0 || !payload) return;
+    PF_BEGIN(PF_RELEASE);
     const int keep = pending_payload_gone(payload);
     DevResult dead;
     if (registry_take(payload, &dead) && !keep) result_buffers_free(&dead);
+    PF_END(PF_RELEASE);
 }
 
 void adb_host_result_release(Result *result) {
@@ -1184,7 +1232,14 @@ static int download_shards(void *dst, int32_t *const d[], const size_t n[]) {
 }
 
 /* Wrap G device buffers as a Result the plumbing can own. */
+static Result *new_dev_result_impl(Shards *sh);
 static Result *new_dev_result(Shards *sh) {
+    PF_BEGIN(PF_NEWRESULT);
+    Result *r = new_dev_result_impl(sh);
+    PF_END(PF_NEWRESULT);
+    return r;
+}
+static Result *new_dev_result_impl(Shards *sh) {
     size_t tuples = 0;
     for (int g = 0; g < S.G; ++g) tuples += sh->n[g];
     Result *r = malloc(sizeof *r);
@@ -1426,6 +1481,7 @@ typedef struct AllocJob {
 static void alloc_shard(int g, void *arg) {
     AllocJob *a = arg;
     void *p = NULL;
+    if (a->sh->d[g]) return;                        /* served from the cache already */
     SCK(adb_alloc(&p, 4 * a->sh->n[g]));
     a->sh->d[g] = p;
 }
@@ -1433,7 +1489,13 @@ static int alloc_shards(Shards *sh) {
     AllocJob job;
     memset(&job, 0, sizeof job);
     job.sh = sh;
-    run_shards(alloc_shard, &job);
+    int missing = 0;
+    for (int g = 0; g < S.G; ++g) {
+        void *p = NULL;
+        sh->d[g] = adb_alloc_cached_on(g, &p, 4 * sh->n[g]) ? p : NULL;
+        missing |= sh->d[g] == NULL;
+    }
+    if (missing) run_shards(alloc_shard, &job);
     if (shard_errs(&job.err)) {
         shards_free(sh);
         return -1;
@@ -1542,7 +1604,14 @@ static void select_scan_shard(int g, void *arg) {
 }
 
 /* src/query.c:203-220: clustered or indexed columns go through the index, others scan. */
+static Result *select_column_impl(Column *column, int *low, int *high, Status *ret_status);
 Result *select_column(Column *column, int *low, int *high, Status *ret_status) {
+    PF_BEGIN(PF_SELECT);
+    Result *r = select_column_impl(column, low, high, ret_status);
+    PF_END(PF_SELECT);
+    return r;
+}
+static Result *select_column_impl(Column *column, int *low, int *high, Status *ret_status) {
     t_err[0] = '\0';
     if (ensure_up()) return op_fail(ret_status, "select_column");
     DevColumn *c = dev_column(column);
@@ -1557,7 +1626,9 @@ Result *select_column(Column *column, int *low, int *high, Status *ret_status) {
     job.low = low;
     job.high = high;
     job.defer = S.lazy;
+    PF_BEGIN(PF_SELECT_JOB);
     run_shards(select_scan_shard, &job);
+    PF_END(PF_SELECT_JOB);
     if (shard_errs(&job.err)) goto fail;
     job.out.aligned = c->shard_rows;
     {
@@ -1788,7 +1859,14 @@ static void fetch_shard(int g, void *arg) {
                               (int64_t)n, NULL, out));
 }
 
+static Result *fetch_column_impl(Column *column, Result *position_result, Status *ret_status);
 Result *fetch_column(Column *column, Result *position_result, Status *ret_status) {
+    PF_BEGIN(PF_FETCH);
+    Result *r = fetch_column_impl(column, position_result, ret_status);
+    PF_END(PF_FETCH);
+    return r;
+}
+static Result *fetch_column_impl(Column *column, Result *position_result, Status *ret_status) {
     t_err[0] = '\0';
     Staged p;
     memset(&p, 0, sizeof p);
@@ -1811,7 +1889,10 @@ Result *fetch_column(Column *column, Result *position_result, Status *ret_status
             Shards sh;
             memset(&sh, 0, sizeof sh);
             memcpy(sh.n, P.h, sizeof sh.n);
-            if (alloc_shards(&sh)) goto fail;
+            PF_BEGIN(PF_FETCH_JOB);
+            const int arc = alloc_shards(&sh);
+            PF_END(PF_FETCH_JOB);
+            if (arc) goto fail;
             Shards keep = sh;
             Result *r = new_dev_result(&sh);
             if (!r) return op_fail(ret_status, "fetch_column");
@@ -1888,7 +1969,14 @@ static int aggregate_shards(int32_t *const d[], const size_t n[], adb_agg *h) {
     return 0;
 }
 
+static int aggregate_result_impl(const Result *r, adb_agg *h);
 static int aggregate_result(const Result *r, adb_agg *h) {
+    PF_BEGIN(PF_AGG);
+    const int rc = aggregate_result_impl(r, h);
+    PF_END(PF_AGG);
+    return rc;
+}
+static int aggregate_result_impl(const Result *r, adb_agg *h) {
     Staged v;
     memset(&v, 0, sizeof v);
     if (ensure_up()) return -1;
@@ -1903,7 +1991,9 @@ static int aggregate_result(const Result *r, adb_agg *h) {
             AggJob job;
             memset(&job, 0, sizeof job);
             job.fused = P.aggregated ? 2 : 1;
+            PF_BEGIN(PF_AGG_JOB);
             run_shards(agg_shard, &job);
+            PF_END(PF_AGG_JOB);
             if (job.fused == 2) lazy_done(&P);
             else P.aggregated = 1;
             if (shard_errs(&job.err)) return -1;

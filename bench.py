@@ -664,11 +664,13 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
     for _ in range(2):
         step()
     sync_all()
+    L.adb_host_profile_dump()                   # (ADB_SHIM_PROFILE=1: start the phase timers afresh)
     t0 = time.perf_counter()
     for _ in range(steps):
         tot, hits = step()
     sync_all()
     dt = time.perf_counter() - t0
+    L.adb_host_profile_dump()
     launches = (lib.adb_launch_count_all() - l0) // (steps + 2)
     rows_step = E2E_PARTS * E2E_PART_ROWS
     if (tot, hits) != tuple(expect) and not args.shards_limit:

@@ -76,6 +76,15 @@ ADB_API int adb_sm_count(void);
 /* ---- device memory and stream plumbing ----------------------------------------------- */
 ADB_API adb_status adb_alloc(void **d_ptr, size_t bytes);            /* stream-ordered pool */
 ADB_API adb_status adb_free(void *d_ptr);
+/* adb_alloc / adb_free keep a small front cache of freed blocks per context (size classes with
+ * <= 12.5 % slack; ADB_ALLOC_CACHE_MB caps it, default 16384): a hit is host bookkeeping where
+ * cudaMallocAsync / cudaFreeAsync cost microseconds.  Blocks keep the pool's stream-ordered
+ * semantics (reused on this context's stream only).  The *_cached_on forms serve context `ctx`
+ * from another thread when -- and only when -- no CUDA call is needed (return 1), so a host that
+ * drives several contexts releases and re-acquires result buffers without switching devices;
+ * on 0 the caller goes through adb_alloc / adb_free on that context.  The context must be idle. */
+ADB_API int32_t adb_alloc_cached_on(int32_t ctx, void **d_ptr, size_t bytes);
+ADB_API int32_t adb_free_cached_on(int32_t ctx, void *d_ptr);
 ADB_API adb_status adb_upload(void *d_dst, const void *h_src, size_t bytes);     /* H2D, synchronous */
 ADB_API adb_status adb_download(void *h_dst, const void *d_src, size_t bytes);   /* D2H, synchronous */
 ADB_API adb_status adb_upload_async(void *d_dst, const void *h_src, size_t bytes);

@@ -181,6 +181,7 @@ void adb_host_results_drop(Result **results, int n);
 int adb_host_result_to_host(const Result *result, void *dst);
 const char *adb_host_last_error(void);
 long adb_host_live_device_results(void);          /* diagnostics: descriptors not yet released */
+void adb_host_profile_dump(void);                 /* ADB_SHIM_PROFILE=1: wall time per host phase, to stderr */
 #ifdef __cplusplus
 }
 #endif

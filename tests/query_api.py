@@ -84,6 +84,7 @@ HOOKS = {
     "adb_host_result_to_host": (C.c_int, [RP, C.c_void_p]),
     "adb_host_last_error": (C.c_char_p, []),
     "adb_host_live_device_results": (C.c_long, []),
+    "adb_host_profile_dump": (None, []),
 }
 
 
