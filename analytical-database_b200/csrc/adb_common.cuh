@@ -329,6 +329,24 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) 
 }  // namespace adb
 
 // ---- engine-internal launch interface (engine.cu <-> kernel files) --------------------
+namespace adb {
+inline void preload_one(const void *kernel) {
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, kernel);
+    cudaGetLastError();
+}
+void preload_csv_load();
+void preload_format_text();
+void preload_gather_agg();
+void preload_hash_join();
+void preload_index_lookup();
+void preload_peer_agg();
+void preload_peer_exchange();
+void preload_radix();
+void preload_select_scan();
+void preload_shared_scan();
+}  // namespace adb
+
 // Every launch_* returns the number of kernels it enqueued (0 for an empty input).
 namespace adb {
 

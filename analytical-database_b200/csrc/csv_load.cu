@@ -188,4 +188,13 @@ int launch_csv_fixup(unsigned long long rows, uint32_t n_cols, int32_t *const *c
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_csv_load() {
+    preload_one(reinterpret_cast<const void *>(&csv_count_kernel));
+    preload_one(reinterpret_cast<const void *>(&csv_fixup_kernel));
+    preload_one(reinterpret_cast<const void *>(&csv_index_kernel));
+    preload_one(reinterpret_cast<const void *>(&csv_parse_kernel));
+}
+
 }  // namespace adb

@@ -436,6 +436,9 @@ adb_status adb_ctx_init(int32_t ctx, int device_ordinal) {
 
 adb_status adb_init(int device_ordinal) {
     if (g.up) return ADB_OK;
+    // (takes effect when this is the first CUDA call of the process; otherwise the preload_*
+    // calls below do the same for the engine's own kernels)
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -498,6 +501,11 @@ adb_status adb_init(int device_ordinal) {
         if (const char *e = getenv("ADB_CHAIN_SLICES")) g.chain_slices = atoi(e);
         if (const char *e = getenv("ADB_CHAIN_CPS_DIV")) g.chain_cps_div = atoi(e) > 0 ? atoi(e) : 1;
     }
+    // every kernel of the engine is loaded here, per device: see preload_* (adb_common.cuh)
+    adb::preload_csv_load(); adb::preload_format_text(); adb::preload_gather_agg(); adb::preload_hash_join();
+    adb::preload_index_lookup(); adb::preload_peer_agg(); adb::preload_peer_exchange(); adb::preload_radix();
+    adb::preload_select_scan(); adb::preload_shared_scan();
+    { cudaFuncAttributes attr; cudaFuncGetAttributes(&attr, publish_kernel); cudaGetLastError(); }
     g.launches = 0;
     g.ctx_index = g_cur;
     g.live = new std::unordered_map<void *, size_t>();

@@ -125,4 +125,11 @@ int launch_fmt_emit(const int32_t *val, int64_t n, const uint32_t *block_off, un
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_format_text() {
+    preload_one(reinterpret_cast<const void *>(&fmt_emit_kernel));
+    preload_one(reinterpret_cast<const void *>(&fmt_len_kernel));
+}
+
 }  // namespace adb

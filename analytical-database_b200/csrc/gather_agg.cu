@@ -335,4 +335,23 @@ int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_gather_agg() {
+    preload_one(reinterpret_cast<const void *>(&aggregate_kernel));
+    { auto *fp = &ewise_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &ewise_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    preload_one(reinterpret_cast<const void *>(&fetch_kernel));
+    preload_one(reinterpret_cast<const void *>(&fetch_sharded_kernel));
+    preload_one(reinterpret_cast<const void *>(&histogram_kernel));
+    preload_one(reinterpret_cast<const void *>(&iota_kernel));
+    preload_one(reinterpret_cast<const void *>(&narrow_u64_kernel));
+    preload_one(reinterpret_cast<const void *>(&synth_affine_kernel));
+    preload_one(reinterpret_cast<const void *>(&synth_uniform_kernel));
+    preload_one(reinterpret_cast<const void *>(&widen_i32_kernel));
+    preload_one(reinterpret_cast<const void *>(&agg_combine_kernel));
+    preload_one(reinterpret_cast<const void *>(&agg_export_kernel));
+    preload_one(reinterpret_cast<const void *>(&agg_import_kernel));
+}
+
 }  // namespace adb

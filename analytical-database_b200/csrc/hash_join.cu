@@ -290,4 +290,14 @@ int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_hash_join() {
+    preload_one(reinterpret_cast<const void *>(&hj_expand_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_geometry_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_probe_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_table_build_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_bounds_kernel));
+}
+
 }  // namespace adb

@@ -135,4 +135,12 @@ int launch_index_emit(const int32_t *positions, int64_t n, const int64_t *bounds
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_index_lookup() {
+    preload_one(reinterpret_cast<const void *>(&index_emit_kernel));
+    preload_one(reinterpret_cast<const void *>(&index_bounds_kernel));
+    preload_one(reinterpret_cast<const void *>(&btree_level_kernel));
+}
+
 }  // namespace adb

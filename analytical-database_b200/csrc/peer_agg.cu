@@ -38,4 +38,10 @@ int launch_agg_combine_allreduce(const PeerExchange &px, cudaStream_t s) {
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_peer_agg() {
+    preload_one(reinterpret_cast<const void *>(&agg_combine_allreduce_kernel));
+}
+
 }  // namespace adb

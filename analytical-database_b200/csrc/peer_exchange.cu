@@ -98,4 +98,11 @@ int launch_jx_done(const PairExchange &x, uint32_t *status, cudaStream_t s) {
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_peer_exchange() {
+    preload_one(reinterpret_cast<const void *>(&jx_counts_kernel));
+    preload_one(reinterpret_cast<const void *>(&jx_done_kernel));
+}
+
 }  // namespace adb

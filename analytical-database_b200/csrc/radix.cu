@@ -332,4 +332,16 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out,
     return 2;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_radix() {
+    preload_one(reinterpret_cast<const void *>(&rx_hist_kernel));
+    preload_one(reinterpret_cast<const void *>(&rx_row_scan_kernel));
+    preload_one(reinterpret_cast<const void *>(&rx_bucket_base_kernel));
+    { auto *fp = &rx_scatter_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    preload_one(reinterpret_cast<const void *>(&sc_chunk_scan_kernel));
+    preload_one(reinterpret_cast<const void *>(&sc_chunk_sum_kernel));
+}
+
 }  // namespace adb

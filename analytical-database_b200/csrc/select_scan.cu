@@ -619,4 +619,18 @@ int launch_select(const SelectArgs &a, cudaStream_t s) {
     return launch_select_mask(a, false, s) + launch_select_expand(a, s);
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_select_scan() {
+    { auto *fp = &bitmap_gather_agg_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &bitmap_gather_agg_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    preload_one(reinterpret_cast<const void *>(&count_total_kernel));
+    { auto *fp = &expand_kernel<true, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &expand_kernel<false, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &expand_kernel<false, true, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &expand_kernel<false, true, true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    preload_one(reinterpret_cast<const void *>(&mask_kernel));
+    preload_one(reinterpret_cast<const void *>(&scan_gather_agg_kernel));
+}
+
 }  // namespace adb

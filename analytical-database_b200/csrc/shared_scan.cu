@@ -560,4 +560,14 @@ int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
     return 1;
 }
 
+// Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
+// has to load code while another context's kernel spin-waits for this one can stall behind it.
+void preload_shared_scan() {
+    { auto *fp = &ss_classify_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &ss_classify_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    preload_one(reinterpret_cast<const void *>(&ss_emit_kernel));
+    preload_one(reinterpret_cast<const void *>(&ss_emit_sorted_kernel));
+    preload_one(reinterpret_cast<const void *>(&ss_offsets_kernel));
+}
+
 }  // namespace adb

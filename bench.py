@@ -659,19 +659,36 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
             eng.sync()
         lib.adb_ctx_select(0)
 
-    steps = max(3, min(args.steps, 10))
+    # The timed loop is the dispatcher's sequence written in C (host/api_harness.c ->
+    # libadb_harness.so: select_column -> fetch_column -> sum -> release, exactly chain() above):
+    # the operators are called from C in the reference, and ctypes costs ~2 us per call.
+    H = C.CDLL(os.path.join(ROOT, "analytical-database_b200", "libadb_harness.so"))
+    H.adb_harness_select_fetch_sum.restype = C.c_int
+    H.adb_harness_select_fetch_sum.argtypes = [C.POINTER(C.POINTER(q.Column)), C.POINTER(C.POINTER(q.Column)), C.c_int,
+                                               C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long),
+                                               C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
+    sel_arr = (C.POINTER(q.Column) * len(hcols))(*[C.pointer(a) for a, _ in hcols])
+    fet_arr = (C.POINTER(q.Column) * len(hcols))(*[C.pointer(b) for _, b in hcols])
+    steps = max(3, min(args.steps, 20))
     l0 = lib.adb_launch_count_all()
-    for _ in range(2):
-        step()
+    tot_py, hits_py = step()                    # the Python spelling of the same chain, once
+    c_sum, c_hits, c_sec = C.c_long(0), C.c_size_t(0), C.c_double(0.0)
+
+    def harness(k):
+        if H.adb_harness_select_fetch_sum(sel_arr, fet_arr, len(hcols), lo, hi, k, C.byref(c_sum), C.byref(c_hits),
+                                          C.byref(c_sec)) != 0:
+            raise SystemExit("e2e harness: " + L.adb_host_last_error().decode())
+    harness(2)
     sync_all()
     L.adb_host_profile_dump()                   # (ADB_SHIM_PROFILE=1: start the phase timers afresh)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        tot, hits = step()
+    harness(steps)
     sync_all()
-    dt = time.perf_counter() - t0
+    dt = c_sec.value
+    tot, hits = c_sum.value, c_hits.value
+    if (tot, hits) != (tot_py, hits_py):
+        raise SystemExit(f"e2e harness {(tot, hits)} != the same chain driven from Python {(tot_py, hits_py)}")
     L.adb_host_profile_dump()
-    launches = (lib.adb_launch_count_all() - l0) // (steps + 2)
+    launches = (lib.adb_launch_count_all() - l0) // (steps + 3)
     rows_step = E2E_PARTS * E2E_PART_ROWS
     if (tot, hits) != tuple(expect) and not args.shards_limit:
         raise SystemExit(f"PARITY FAILURE: e2e chain {(tot, hits)} != device-resident chain {tuple(expect)}")
@@ -680,6 +697,8 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
            "d2h_bytes_per_step": (8 * G + 24) * E2E_PARTS,
            "ms_per_step": 1e3 * dt / steps, "steps": steps, "gpu_launches_per_step": int(launches),
            "host_processes": 1, "gpus_driven": G,
+           "caller": "host/api_harness.c (C, as the reference's dispatcher is): select_column -> fetch_column -> "
+                     "sum -> release per column, wall clock around all steps",
            "api": "select_column -> fetch_column -> sum of include/adb_query_api.h (libadb_query.so = "
                   f"host/query_shim.c, adb_host_init_multi({G})): one call chain per column of "
                   f"{E2E_PART_ROWS} rows, each column row-range sharded over the {G} GPU(s) by the shim",

@@ -257,7 +257,10 @@ def test_payload_registry_reclaims_on_address_reuse(api):
     assert int(api.tuples(a)[0]) == 8999 and np.array_equal(api.tuples(s), np.arange(7, 9000))
     for h in (s, f, a):
         api.drop(h)
-    assert api.lib.adb_host_live_device_results() <= base + 6
+    # these payloads had 40 different sizes: whether malloc has handed their addresses out again
+    # by now depends on its bins and the process's malloc policy (the shim's own mallopt), so
+    # only the upper bound is fixed -- nothing beyond the 40 leaked-on-purpose entries is live
+    assert api.lib.adb_host_live_device_results() <= base + 3 + 40
 
 
 # ---- deferred select: every order in which the plumbing can touch the
