@@ -148,6 +148,14 @@ struct Engine {
     int cache_n = 0;
     size_t cache_bytes = 0, cache_cap = (size_t)16 << 30;
     std::unordered_map<void *, size_t> *live = nullptr;
+    // small host -> device blobs (batch plans, pointer tables) are staged through engine-owned
+    // pinned slots: a cudaMemcpyAsync from the caller's memory would read it after the call
+    // returned if that memory happened to be pinned
+    static constexpr int kBlobSlots = 4;
+    static constexpr size_t kBlobBytes = 64 << 10;
+    unsigned char *blob[kBlobSlots] = {};
+    cudaEvent_t blob_ev[kBlobSlots] = {};
+    int blob_next = 0;
 };
 
 // One context per GPU of the box (several may share a device: a 1-GPU box then runs the
@@ -237,6 +245,29 @@ static adb_status mbox_wait(unsigned long long seq, void *h_dst, size_t bytes) {
 #endif
     }
     memcpy(h_dst, g.mbox, bytes);
+    return ADB_OK;
+}
+
+// Asynchronous upload of a small blob whose source may go out of scope as soon as the caller
+// returns: through a ring of pinned slots (a slot is reused only after its copy has run).
+adb_status upload_blob(void *d_dst, const void *h_src, size_t bytes) {
+    if (bytes == 0) return ADB_OK;
+    if (bytes > Engine::kBlobBytes) {               // large: synchronous
+        CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+        return ADB_OK;
+    }
+    const int k = g.blob_next;
+    g.blob_next = (k + 1) % Engine::kBlobSlots;
+    if (!g.blob[k]) {
+        CU(cudaHostAlloc(reinterpret_cast<void **>(&g.blob[k]), Engine::kBlobBytes, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&g.blob_ev[k], cudaEventDisableTiming));
+    } else {
+        CU(cudaEventSynchronize(g.blob_ev[k]));
+    }
+    memcpy(g.blob[k], h_src, bytes);
+    CU(cudaMemcpyAsync(d_dst, g.blob[k], bytes, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaEventRecord(g.blob_ev[k], g.stream));
     return ADB_OK;
 }
 
@@ -565,6 +596,10 @@ static adb_status shutdown_current() {
     cudaFree(g.agg_scratch);
     cudaFree(g.agg_ticket);
     cudaFree(g.slice_parts);
+    for (int k = 0; k < Engine::kBlobSlots; ++k) {
+        if (g.blob[k]) cudaFreeHost(g.blob[k]);
+        if (g.blob_ev[k]) cudaEventDestroy(g.blob_ev[k]);
+    }
     if (g.side) { cudaStreamSynchronize(g.side); cudaStreamDestroy(g.side); }
     for (cudaEvent_t &e : g.slice_ev) if (e) cudaEventDestroy(e);
     if (g.side_done) cudaEventDestroy(g.side_done);
@@ -1150,7 +1185,7 @@ adb_status adb_peer_exchange_pairs(int32_t side, const int32_t *d_val, const int
         // no routing digit: every pair stays here (still through the flags: one code path)
         CU(cudaMemsetAsync(g.rx_totals, 0, sizeof(uint32_t) * 256, g.stream));
         const uint32_t n32 = (uint32_t)n;
-        CU(cudaMemcpyAsync(g.rx_totals, &n32, sizeof n32, cudaMemcpyHostToDevice, g.stream));
+        if (adb_status s = upload_blob(g.rx_totals, &n32, sizeof n32)) return s;
     } else {
         k_ += adb::launch_radix_hist(reinterpret_cast<const uint32_t *>(d_val), (uint32_t)n, pass, g.rx_hist,
                                      g.rx_totals, g.sm_count, g.stream);
@@ -1649,9 +1684,8 @@ static adb_status shared_select_count_impl(const int32_t *d_col, int64_t n, cons
     }
     SsHostPlan hp;
     ss_build_plan(lows, highs, q_count, &hp);
-    // one packed upload.  The source is pageable, so the call returns once the bytes sit in the
-    // driver's staging memory: no synchronisation needed before the host vector goes out of scope.
-    CU(cudaMemcpyAsync(g.ss_plan_mem, hp.bytes.data(), hp.bytes.size(), cudaMemcpyHostToDevice, g.stream));
+    // one packed upload, staged through a pinned slot (the host vector goes out of scope below)
+    if (adb_status s = upload_blob(g.ss_plan_mem, hp.bytes.data(), hp.bytes.size())) return s;
     const uint32_t m = hp.m, lut_shift = hp.lut_shift, bit_shift = hp.bit_shift, span = hp.span, deepest = hp.deepest;
     g.ss_plan = adb::SharedScanPlan{reinterpret_cast<const int32_t *>(g.ss_plan_mem),
                                     reinterpret_cast<const uint16_t *>(g.ss_plan_mem + kSsBoundsBytes),
@@ -1698,8 +1732,7 @@ adb_status adb_shared_select_emit(int32_t *const *d_out_ptrs, int64_t capacity) 
     if (!d_out_ptrs) return fail(ADB_ERR_INVALID, "adb_shared_select_emit: NULL pointer");
     g.ss_ready = false;
     if (g.ss_geom.num_chunks == 0) return ADB_OK;
-    CU(cudaMemcpyAsync(g.ss_outs, d_out_ptrs, sizeof(int32_t *) * g.ss_plan.q_count,
-                       cudaMemcpyHostToDevice, g.stream));      // pageable source: staged before return
+    if (adb_status s = upload_blob(g.ss_outs, d_out_ptrs, sizeof(int32_t *) * g.ss_plan.q_count)) return s;
     const int k_ = adb::launch_shared_emit(g.ss_hits, g.ss_chunk_hits, g.ss_plan, g.ss_geom, g.ss_counts,
                                            g.ss_outs, capacity, (uint32_t)g.ss_base_pos, g.stream);
     return after_launch("shared_emit", k_);
@@ -1945,7 +1978,7 @@ adb_status adb_csv_parse(int32_t n_cols, int32_t *const *d_cols) {
     for (int32_t i = 0; i < n_cols; ++i)
         if (!d_cols[i]) return fail(ADB_ERR_INVALID, "adb_csv_parse: column %d is NULL", i);
     if (adb_status s = csv_grow(&c.n_fields, &c.fields_cap, (size_t)c.rows)) return s;
-    CU(cudaMemcpyAsync(c.col_table, d_cols, sizeof(int32_t *) * n_cols, cudaMemcpyHostToDevice, g.stream));
+    if (adb_status s = upload_blob(c.col_table, d_cols, sizeof(int32_t *) * n_cols)) return s;
     CU(cudaMemsetAsync(c.flags, 0, 4 * sizeof(uint32_t), g.stream));
     int k_ = adb::launch_csv_parse(c.text, c.bytes, c.line_end, c.newlines, c.skip, c.rows, (uint32_t)n_cols,
                                    c.col_table, c.n_fields, c.flags, g.stream);
@@ -2044,7 +2077,9 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     int launches = 0;
     StageTrace tr;
     uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
-    while (part_bits < 16 && (nb >> part_bits) > 1024) ++part_bits;
+    // (up to 2^20 partitions: a 500 M-row build side still gets ~500-row partitions that fit the
+    // shared-memory table, instead of 2^16 oversized ones built slot by slot in global memory)
+    while (part_bits < 20 && (nb >> part_bits) > 1024) ++part_bits;
     const uint32_t num_parts = 1u << part_bits;
     const size_t pbytes = (size_t)(num_parts + 1) * 4;
     if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +

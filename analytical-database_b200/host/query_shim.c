@@ -1122,6 +1122,24 @@ int adb_host_column_histogram(Column *column, int bin_size, unsigned long counts
 }
 
 /* ---- device-resident results ------------------------------------------------------------- */
+/* Every payload block the shim hands out starts with a tag derived from its own address.  A
+ * registry hit is only trusted when the tag is still there: if the plumbing freed the payload
+ * behind the shim's back and malloc gave the address to somebody else (a foreign host Result),
+ * that somebody has written its own bytes over the tag.  Not in mirror mode, where
+ * the block holds the tuples themselves. */
+#define PAYLOAD_MAGIC 0xADB200C5EEDULL
+static uint64_t payload_tag(const void *payload) { return PAYLOAD_MAGIC ^ ((uint64_t)(uintptr_t)payload * 0x9E3779B97F4A7C15ULL); }
+static void payload_stamp(void *payload) {
+    if (!S.mirror) {
+        ((uint64_t *)payload)[0] = payload_tag(payload);
+        ((uint64_t *)payload)[1] = ~payload_tag(payload);
+    }
+}
+static int payload_is_ours(const void *payload) {
+    return S.mirror || (((const uint64_t *)payload)[0] == payload_tag(payload) &&
+                        ((const uint64_t *)payload)[1] == ~payload_tag(payload));
+}
+
 static size_t slot_of(const void *p, size_t nslots) {
     uint64_t x = (uint64_t)(uintptr_t)p;
     x ^= x >> 33;
@@ -1296,6 +1314,7 @@ static Result *new_dev_result_impl(Shards *sh) {
     e->slab = sh->slab;
     unlock();
     if (have_dead && !keep_dead) result_buffers_free(&dead);
+    payload_stamp(payload);
     r->num_tuples = tuples;
     r->data_type = INT;
     r->payload = payload;
@@ -1391,6 +1410,11 @@ static int stage(const Result *r, const size_t *like, Staged *out) {
     DevResult dv;
     if (e) dv = *e;
     unlock();
+    if (e && r->payload && !payload_is_ours(r->payload)) {
+        /* the address was recycled: the registered device buffers belong to a dead handle */
+        adb_host_payload_freed(r->payload);
+        e = NULL;
+    }
     out->total = r->num_tuples;
     if (e) {
         if (dv.total < r->num_tuples) {
@@ -1460,6 +1484,10 @@ int adb_host_result_to_host(const Result *result, void *dst) {
     DevResult dv;
     if (e) dv = *e;
     unlock();
+    if (e && result->data_type == INT && !payload_is_ours(result->payload)) {
+        adb_host_payload_freed(result->payload);        /* recycled address: see payload_stamp */
+        e = NULL;
+    }
     if (!e) {                               /* scalar or foreign host payload */
         size_t w = result->data_type == INT || result->data_type == FLOAT ? 4 : 8;
         memcpy(dst, result->payload, w * result->num_tuples);

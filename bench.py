@@ -350,6 +350,8 @@ def run_engine(args):
     else:
         a = eng.read_agg(combined)
         g_sum, g_cnt, g_min, g_max = a.sum, a.count, a.min, a.max
+        if g_cnt < 0:                               # the exchange gave up on a peer (2 s): not a result
+            raise SystemExit(f"rank {rank}: the aggregate exchange timed out waiting for a peer (count = -1)")
 
     # ---- roofline of the dominant kernel (mask_kernel: the predicate pass over the selected
     # column), from CUDA events recorded on the engine stream inside the timed region -------

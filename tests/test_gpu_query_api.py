@@ -520,6 +520,67 @@ def test_random_walk_over_the_operator_api(api, cpu):
     assert api.lib.adb_host_live_device_results() <= live0
 
 
+def test_recycled_payload_address_is_not_mistaken_for_a_device_result(api, rng):
+    """A payload freed behind the shim's back whose address malloc then gives to a foreign host
+    Result: the registry still knows the address, the tag the shim stamped into its own blocks is
+    gone, so the operand is read as the host array it is."""
+    import query_api
+    from query_api import Result, INT
+    libc = query_api._libc
+    libc.malloc.restype, libc.malloc.argtypes = C.c_void_p, [C.c_size_t]
+    n = 30_000
+    data = rng.integers(0, 1000, n).astype(np.int32)
+    col = api.column(data)
+    hit = False
+    for _ in range(50):
+        s = api.select_column(col, 0, 500)
+        m = s.contents.num_tuples
+        api.tuples(s)                                     # written, registered
+        addr = s.contents.payload
+        libc.free(addr)                                   # plumbing-style free, no hook
+        libc.free(C.cast(s, C.c_void_p))
+        p = libc.malloc(4 * m)                            # same size: usually the same address
+        foreign = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), shape=(m,))
+        foreign[:] = np.arange(m, dtype=np.int32)[::-1] % n
+        r = Result(m, INT, p)
+        f = api.fetch_column(col, C.pointer(r))
+        assert np.array_equal(api.tuples(f), data[foreign])
+        got = np.empty(m, np.int32)
+        assert api.lib.adb_host_result_to_host(C.byref(r), got.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(got, foreign)
+        api.drop(f)
+        hit = hit or p == addr
+        libc.free(p)
+    assert hit                                            # the scenario did occur
+
+
+def test_ten_thousand_exchanges(api, rng):
+    """The aggregate exchange's two-bank epoch protocol (adb_common.cuh: peer_exchange_warp) over
+    10 000 back-to-back rounds, alternating the fused and the stand-alone form: every round's
+    table-wide aggregate must be exact (a late or early peer record would corrupt a sum)."""
+    n = 40_000
+    data = rng.integers(-10**6, 10**6, n).astype(np.int32)
+    col = api.column(data)
+    total = int(data.astype(np.int64).sum())
+    s = api.select_column(col, None, 0)
+    f = api.fetch_column(col, s)
+    neg = int(data[data < 0].astype(np.int64).sum())
+    st = Status(99, None)
+    g1, g2 = GeneralizedColumn(1), GeneralizedColumn(RESULT)      # COLUMN, RESULT
+    g1.column_pointer.column = C.pointer(col)
+    g2.column_pointer.result = f
+    drop3 = (type(f) * 1)()
+    for k in range(5_000):
+        a = api.lib.sum(C.byref(g1), C.byref(st))
+        b = api.lib.sum(C.byref(g2), C.byref(st))
+        assert C.cast(a.contents.payload, C.POINTER(C.c_long))[0] == total, k
+        assert C.cast(b.contents.payload, C.POINTER(C.c_long))[0] == neg, k
+        for r in (a, b):
+            drop3[0] = r
+            api.lib.adb_host_results_drop(drop3, 1)
+    api.drop(s), api.drop(f)
+
+
 def test_lazy_handles_are_written_only_when_read(api, cpu, rng):
     """s=select / f=fetch / a=sum(f) answers the aggregate without writing s
     or f (4N + 4H bytes); the handles are written when -- and only when -- somebody reads them,
