@@ -539,6 +539,24 @@ int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
                      int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);
 
+// The join sharded over several contexts: the build side is hash-partitioned
+// over the owners (adb_peer_exchange_pairs' routing hash), every owner builds the tables of its
+// share, and every context probes ITS probe rows -- in their original order -- against the
+// owner of each key over NVLink peer memory.  Output pairs then come out probe-major per
+// context, and the contexts' outputs concatenated in shard order are the reference's list.
+struct JoinOwners {
+    const unsigned long long *toff[kMaxPeers];
+    const uint4 *table[kMaxPeers];
+    const int32_t *bpos[kMaxPeers];                  // build positions sorted by hash (multi-row groups)
+    uint32_t part_bits[kMaxPeers];
+    uint32_t route_bits;                             // owner = (key * 0x85EBCA6B) >> (32 - route_bits)
+};
+int launch_hj_probe_sharded(const uint32_t *pkeys, uint32_t n_probe, const JoinOwners &owners, uint2 *gc_by_j,
+                            int sm_count, cudaStream_t s);
+int launch_hj_expand_sharded(const uint2 *gc_by_j, const uint32_t *off_by_j, uint32_t n_probe,
+                             const uint32_t *pkeys, const JoinOwners &owners, const int32_t *probe_pos,
+                             int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);
+
 // Implicit fan-out-32 B+-tree over a sorted value array (index_lookup.cu).
 constexpr int kBTreeMaxDepth = 8;
 struct BTreeView {

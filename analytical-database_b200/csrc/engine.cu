@@ -72,6 +72,13 @@ struct Engine {
         int32_t *build_pos_sorted = nullptr;   // all three live in the arena
         const int32_t *probe_pos = nullptr;
         bool swapped = false;
+        // sharded form (adb_join_build / adb_join_probe_sharded): this context's tables, read by
+        // every context's probe; the probe keys and the owner table for the expansion
+        bool built = false, sharded = false;
+        uint32_t part_bits = 1;
+        const unsigned long long *toff = nullptr;
+        const uint32_t *probe_keys = nullptr;
+        adb::JoinOwners owners{};
     } join;
     // grow-only scratch arena for the sort / join temporaries: cudaMallocAsync of many
     // differently sized multi-hundred-MB blocks made the pool re-map memory on every join
@@ -2059,6 +2066,63 @@ struct StageTrace {
 
 // build = the side whose rows are grouped (the reference's column_one for hash_join);
 // probe = the side walked in row order.  Output pair k is (build position, probe position).
+//
+// join_build: steps 1-3 (sort on the hash, partition boundaries, one table per partition);
+// leaves {build_pos_sorted, toff, part_bits} in g.join and the tables in g.hj_table.  The arena
+// is reserved for the build AND for `np` probe rows' worth of {group, count} + offsets.
+static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, uint32_t np, int *launches,
+                             StageTrace &tr) {
+    uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
+    // (up to 2^20 partitions: a 500 M-row build side still gets ~500-row partitions that fit the
+    // shared-memory table, instead of 2^16 oversized ones built slot by slot in global memory)
+    while (part_bits < 20 && (nb >> part_bits) > 1024) ++part_bits;
+    const uint32_t num_parts = 1u << part_bits;
+    const size_t pbytes = (size_t)(num_parts + 1) * 4;
+    if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
+                                     arena_round((size_t)np * 4) + arena_round(pbytes) +
+                                     arena_round((size_t)(num_parts + 1) * 8) + 4096))
+        return s;
+    auto &j = g.join;
+    j.part_bits = part_bits;
+    uint32_t *off1 = ARENA_TAKE(uint32_t, num_parts + 1);
+    unsigned long long *toff = ARENA_TAKE(unsigned long long, num_parts + 1);
+    j.toff = toff;
+    if (nb == 0) {                             // an owner without build rows: every partition is empty
+        CU(cudaMemsetAsync(toff, 0, (size_t)(num_parts + 1) * 8, g.stream));
+        j.build_pos_sorted = nullptr;
+        return ADB_OK;
+    }
+    // 1. build side: full stable sort on the bijective hash; the payload carried through the
+    //    passes is the build position itself, so nothing is gathered afterwards
+    const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
+    uint32_t *bk = nullptr, *bi = nullptr;
+    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, nullptr, nullptr, &bk, &bi,
+                                 launches, reinterpret_cast<const uint32_t *>(bp))) return s;
+    j.build_pos_sorted = reinterpret_cast<int32_t *>(bi);
+    tr.lap("build sort");
+    // 2. partition boundaries -> table geometry: partition p gets a power-of-two slot range
+    //    holding its rows at <= 80 % load (<= 4096 slots: built in shared memory)
+    *launches += adb::launch_hj_bounds(bk, nb, part_bits, num_parts, off1, g.stream);
+    *launches += adb::launch_hj_geometry(off1, num_parts, toff, g.stream);
+    unsigned long long slots = 0;
+    if (adb_status s = read_back(&slots, toff + num_parts, sizeof slots)) return s;
+    if (slots > g.hj_table_slots) {
+        if (g.hj_table) CU(cudaFree(g.hj_table));
+        g.hj_table = nullptr;
+        g.hj_table_slots = 0;
+        const unsigned long long want = slots + slots / 8 + 4096;
+        cudaError_t e = cudaMalloc(&g.hj_table, want * 16);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join tables (%llu slots): %s", want, cudaGetErrorString(e)); }
+        g.hj_table_slots = want;
+    }
+    tr.lap("partition boundaries");
+    // 3. one table per partition
+    *launches += adb::launch_hj_table_build(bk, j.build_pos_sorted, off1, toff, num_parts, part_bits,
+                                            static_cast<uint4 *>(g.hj_table), g.stream);
+    tr.lap("per-partition tables");
+    return ADB_OK;
+}
+
 static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64, const int32_t *pv,
                              const int32_t *pp, int64_t np64, bool swapped, int64_t *h_matches) {
     NEED_UP();
@@ -2076,55 +2140,16 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     }
     int launches = 0;
     StageTrace tr;
-    uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
-    // (up to 2^20 partitions: a 500 M-row build side still gets ~500-row partitions that fit the
-    // shared-memory table, instead of 2^16 oversized ones built slot by slot in global memory)
-    while (part_bits < 20 && (nb >> part_bits) > 1024) ++part_bits;
-    const uint32_t num_parts = 1u << part_bits;
-    const size_t pbytes = (size_t)(num_parts + 1) * 4;
-    if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
-                                     arena_round((size_t)np * 4) + arena_round(pbytes) +
-                                     arena_round((size_t)(num_parts + 1) * 8) + 4096))
-        return s;
+    if (adb_status s = join_build(bv, bp, nb, np, &launches, tr)) return s;
     auto &j = g.join;
     j.swapped = swapped;
     j.n_probe = np;
     j.probe_pos = pp;
-    // 1. build side: full stable sort on the bijective hash; the payload carried through the
-    //    passes is the build position itself, so nothing is gathered afterwards
-    const adb::RadixPass sort4[4] = {{0, 8, 1}, {8, 8, 1}, {16, 8, 1}, {24, 8, 1}};
-    uint32_t *bk = nullptr, *bi = nullptr;
-    if (adb_status s = radix_run(reinterpret_cast<const uint32_t *>(bv), nb, sort4, 4, nullptr, nullptr, &bk, &bi,
-                                 &launches, reinterpret_cast<const uint32_t *>(bp))) return s;
-    j.build_pos_sorted = reinterpret_cast<int32_t *>(bi);
-    tr.lap("build sort");
-    // 2. partition boundaries -> table geometry: partition p gets a power-of-two slot range
-    //    holding its rows at <= 80 % load (<= 4096 slots: built in shared memory)
-    uint32_t *off1 = ARENA_TAKE(uint32_t, num_parts + 1);
-    unsigned long long *toff = ARENA_TAKE(unsigned long long, num_parts + 1);
     int64_t *tot = ARENA_TAKE(int64_t, 2);
-    launches += adb::launch_hj_bounds(bk, nb, part_bits, num_parts, off1, g.stream);
-    launches += adb::launch_hj_geometry(off1, num_parts, toff, g.stream);
-    unsigned long long slots = 0;
-    if (adb_status s = read_back(&slots, toff + num_parts, sizeof slots)) return s;
-    if (slots > g.hj_table_slots) {
-        if (g.hj_table) CU(cudaFree(g.hj_table));
-        g.hj_table = nullptr;
-        g.hj_table_slots = 0;
-        const unsigned long long want = slots + slots / 8 + 4096;
-        cudaError_t e = cudaMalloc(&g.hj_table, want * 16);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join tables (%llu slots): %s", want, cudaGetErrorString(e)); }
-        g.hj_table_slots = want;
-    }
-    tr.lap("partition boundaries");
-    // 3. one table per partition
-    launches += adb::launch_hj_table_build(bk, j.build_pos_sorted, off1, toff, num_parts, part_bits,
-                                           static_cast<uint4 *>(g.hj_table), g.stream);
-    tr.lap("per-partition tables");
     // 4. probe in row order
     j.gc_by_j = ARENA_TAKE(uint2, np);
     j.off_by_j = ARENA_TAKE(uint32_t, np);
-    launches += adb::launch_hj_probe(reinterpret_cast<const uint32_t *>(pv), np, toff, part_bits,
+    launches += adb::launch_hj_probe(reinterpret_cast<const uint32_t *>(pv), np, j.toff, j.part_bits,
                                      static_cast<const uint4 *>(g.hj_table), j.gc_by_j, g.sm_count, g.stream);
     tr.lap("probe");
     // 5. output offsets in probe-row order
@@ -2138,6 +2163,77 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
         return fail(ADB_ERR_INVALID, "join produces %lld pairs; the reference indexes its output with an int "
                     "(query.c:657) so the result must stay below 2^31", m);
     }
+    j.ready = true;
+    if (h_matches) *h_matches = j.matches;
+    return ADB_OK;
+}
+
+// ---- the join sharded over the contexts of one process ----------------------------
+// Every context calls adb_join_build on its share of the build side (what adb_peer_exchange_pairs
+// delivered), the host waits for all of them, then every context calls adb_join_probe_sharded
+// with ITS probe rows and adb_join_emit_sharded.  The probe rows keep their original order, so
+// the contexts' outputs concatenated in shard order are the reference's probe-major list.
+adb_status adb_join_build(const int32_t *d_v, const int32_t *d_p, int64_t n, int64_t probe_rows_hint) {
+    NEED_UP();
+    join_release();
+    if (adb_status s = check_len(n, "adb_join_build")) return s;
+    if (adb_status s = check_len(probe_rows_hint, "adb_join_build")) return s;
+    if (n > 0 && (!d_v || !d_p)) return fail(ADB_ERR_INVALID, "adb_join_build: NULL device pointer");
+    int launches = 0;
+    StageTrace tr;
+    if (adb_status s = ensure_radix_scratch((uint32_t)(n ? n : 1))) return s;
+    if (adb_status s = join_build(d_v, d_p, (uint32_t)n, (uint32_t)probe_rows_hint, &launches, tr)) return s;
+    if (adb_status s = after_launch("join_build", launches)) return s;
+    CU(cudaStreamSynchronize(g.stream));               // the other contexts' probes read these tables
+    g.join.built = true;
+    g.join.n_probe = (uint32_t)probe_rows_hint;
+    return ADB_OK;
+}
+
+adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np64,
+                                  int32_t swapped, int64_t *h_matches) {
+    NEED_UP();
+    auto &j = g.join;
+    if (!j.built) return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: no preceding adb_join_build on this context");
+    if (world < 1 || world > ADB_MAX_PEERS || (world & (world - 1)))
+        return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: world %d must be a power of two <= %d", world, ADB_MAX_PEERS);
+    if (adb_status s = check_len(np64, "adb_join_probe_sharded")) return s;
+    if ((uint32_t)np64 > j.n_probe) return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: more probe rows than adb_join_build reserved for");
+    if (np64 > 0 && (!d_pv || !d_pp)) return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: NULL device pointer");
+    const uint32_t np = (uint32_t)np64;
+    adb::JoinOwners o{};
+    for (int r = 0; r < world; ++r) {
+        const Engine &E = g_ctx[r];
+        if (!E.up || !E.join.built) return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: context %d has built no tables", r);
+        o.toff[r] = E.join.toff;
+        o.table[r] = static_cast<const uint4 *>(E.hj_table);
+        o.bpos[r] = E.join.build_pos_sorted;
+        o.part_bits[r] = E.join.part_bits;
+    }
+    while ((1 << o.route_bits) < world) ++o.route_bits;
+    j.owners = o;
+    j.sharded = true;
+    j.swapped = swapped != 0;
+    j.n_probe = np;
+    j.probe_pos = d_pp;
+    j.probe_keys = reinterpret_cast<const uint32_t *>(d_pv);
+    j.matches = 0;
+    if (np == 0) {
+        j.ready = true;
+        if (h_matches) *h_matches = 0;
+        return ADB_OK;
+    }
+    int launches = 0;
+    int64_t *tot = ARENA_TAKE(int64_t, 2);
+    j.gc_by_j = ARENA_TAKE(uint2, np);
+    j.off_by_j = ARENA_TAKE(uint32_t, np);
+    launches += adb::launch_hj_probe_sharded(j.probe_keys, np, o, j.gc_by_j, g.sm_count, g.stream);
+    launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
+    if (adb_status s = read_back(&j.matches, tot, sizeof(int64_t))) return s;
+    if (adb_status s = after_launch("join_probe_sharded", launches)) return s;
+    if (j.matches >= (int64_t)1 << 31)
+        return fail(ADB_ERR_INVALID, "join produces %lld pairs on one context; the result must stay below 2^31",
+                    (long long)j.matches);
     j.ready = true;
     if (h_matches) *h_matches = j.matches;
     return ADB_OK;
@@ -2162,9 +2258,20 @@ adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2) {
     if (j.matches > 0) {
         if (!d_out1 || !d_out2) return fail(ADB_ERR_INVALID, "adb_join_emit: NULL output");
         int32_t *ob = j.swapped ? d_out2 : d_out1, *op = j.swapped ? d_out1 : d_out2;
-        const int k_ = adb::launch_hj_expand(j.gc_by_j, j.off_by_j, j.n_probe,
-                                             j.build_pos_sorted, j.probe_pos, ob, op, g.sm_count, g.stream);
+        const int k_ = j.sharded
+            ? adb::launch_hj_expand_sharded(j.gc_by_j, j.off_by_j, j.n_probe, j.probe_keys, j.owners, j.probe_pos,
+                                            ob, op, g.sm_count, g.stream)
+            : adb::launch_hj_expand(j.gc_by_j, j.off_by_j, j.n_probe, j.build_pos_sorted, j.probe_pos, ob, op,
+                                    g.sm_count, g.stream);
         rc = after_launch("join_expand", k_);
+    }
+    if (j.sharded) {
+        // the other contexts' expansions may still be reading this context's tables and sorted
+        // build positions: they stay until the next join on this context (the host waits for
+        // every context's emit before it starts one)
+        j.ready = false;
+        if (rc == ADB_OK) CU(cudaStreamSynchronize(g.stream));
+        return rc;
     }
     join_release();
     return rc;

@@ -251,6 +251,105 @@ hj_expand_kernel(const uint2 *__restrict__ gc_by_j,
     }
 }
 
+// ---- the same two kernels when the tables live on several contexts ------------------------------
+// The owner table travels as a kernel parameter and is copied to shared memory once per CTA.
+struct HjOwnersShared {
+    const unsigned long long *toff[kMaxPeers];
+    const uint4 *table[kMaxPeers];
+    const int32_t *bpos[kMaxPeers];
+    uint32_t part_bits[kMaxPeers];
+};
+__device__ __forceinline__ void hj_load_owners(const JoinOwners &o, HjOwnersShared &s) {
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < kMaxPeers; ++k) {
+            s.toff[k] = o.toff[k];
+            s.table[k] = o.table[k];
+            s.bpos[k] = o.bpos[k];
+            s.part_bits[k] = o.part_bits[k];
+        }
+    __syncthreads();
+}
+__device__ __forceinline__ uint32_t hj_owner(uint32_t key, uint32_t route_bits) {
+    return route_bits ? (key * 0x85EBCA6Bu) >> (32 - route_bits) : 0u;
+}
+
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_probe_sharded_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe, const JoinOwners owners,
+                        uint2 *__restrict__ gc_by_j) {
+    __shared__ HjOwnersShared so;
+    hj_load_owners(owners, so);
+    const uint32_t stride = gridDim.x * HJ_THREADS;
+    for (uint32_t j = blockIdx.x * HJ_THREADS + threadIdx.x; j < n_probe; j += stride) {
+        const uint32_t k = (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(pkeys) + j);
+        const uint32_t w = hj_owner(k, owners.route_bits);
+        const uint32_t part_bits = so.part_bits[w];
+        const unsigned long long *__restrict__ toff = so.toff[w];
+        const uint32_t p = hj_pid(k, part_bits);
+        const unsigned long long t0 = toff[p], cap = toff[p + 1] - t0;      // (peer loads when w is remote)
+        uint2 r = make_uint2(0u, 0u);
+        if (cap) {
+            const uint4 *__restrict__ table = so.table[w];
+            const uint32_t tag = hj_tag(k, part_bits);
+            const unsigned long long mask = cap - 1;
+            unsigned long long s = hj_mix(tag) & mask;
+            while (true) {
+                const uint4 sl = ld_gather(table + t0 + s);
+                if (sl.x == tag) { r = make_uint2(sl.y, sl.z); break; }
+                if (sl.x == 0u) break;
+                s = (s + 1) & mask;
+            }
+        }
+        gc_by_j[j] = r;
+    }
+}
+
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_expand_sharded_kernel(const uint2 *__restrict__ gc_by_j, const uint32_t *__restrict__ off_by_j,
+                         uint32_t n_probe, const uint32_t *__restrict__ pkeys, const JoinOwners owners,
+                         const int32_t *__restrict__ probe_pos, int32_t *__restrict__ out_build,
+                         int32_t *__restrict__ out_probe) {
+    __shared__ HjOwnersShared so;
+    hj_load_owners(owners, so);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (HJ_THREADS / kWarp);
+    const uint32_t warp_id = blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5);
+    for (uint32_t j0 = warp_id * kWarp; j0 < n_probe; j0 += warps * kWarp) {
+        const uint32_t j = j0 + lane;
+        uint32_t cnt = 0, gs = 0, off = 0, w = 0;
+        int32_t pp = 0;
+        if (j < n_probe) {
+            const uint2 gc = gc_by_j[j];
+            cnt = gc.y;
+            if (cnt) { gs = gc.x; off = off_by_j[j]; pp = probe_pos[j]; }
+            if (cnt > 1) w = hj_owner(pkeys[j], owners.route_bits);      // whose sorted build list holds the group
+        }
+        if (cnt == 1) {                                  // gs already is the build position
+            out_build[off] = (int32_t)gs;
+            out_probe[off] = pp;
+        } else if (cnt && cnt <= 8) {
+            const int32_t *__restrict__ bp = so.bpos[w];
+            for (uint32_t r = 0; r < cnt; ++r) {
+                out_build[off + r] = bp[gs + r];
+                out_probe[off + r] = pp;
+            }
+        }
+        uint32_t longs = __ballot_sync(kFull, cnt > 8);
+        while (longs) {
+            const int src = __ffs(longs) - 1;
+            longs &= longs - 1;
+            const uint32_t c = __shfl_sync(kFull, cnt, src), g = __shfl_sync(kFull, gs, src);
+            const uint32_t o = __shfl_sync(kFull, off, src), ww = __shfl_sync(kFull, w, src);
+            const int32_t q = __shfl_sync(kFull, pp, src);
+            const int32_t *__restrict__ bp = so.bpos[ww];
+            for (uint32_t r = lane; r < c; r += kWarp) {
+                out_build[o + r] = bp[g + r];
+                out_probe[o + r] = q;
+            }
+        }
+    }
+}
+
 // ---- launchers --------------------------------------------------------------------------------------
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s) {
@@ -290,9 +389,31 @@ int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
     return 1;
 }
 
+int launch_hj_probe_sharded(const uint32_t *pkeys, uint32_t n_probe, const JoinOwners &owners, uint2 *gc_by_j,
+                            int sm_count, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
+    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
+    hj_probe_sharded_kernel<<<blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, owners, gc_by_j);
+    return 1;
+}
+
+int launch_hj_expand_sharded(const uint2 *gc_by_j, const uint32_t *off_by_j, uint32_t n_probe,
+                             const uint32_t *pkeys, const JoinOwners &owners, const int32_t *probe_pos,
+                             int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
+    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
+    hj_expand_sharded_kernel<<<blocks, HJ_THREADS, 0, s>>>(gc_by_j, off_by_j, n_probe, pkeys, owners, probe_pos,
+                                                           out_build, out_probe);
+    return 1;
+}
+
 // Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
 // has to load code while another context's kernel spin-waits for this one can stall behind it.
 void preload_hash_join() {
+    preload_one(reinterpret_cast<const void *>(&hj_probe_sharded_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_expand_sharded_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_expand_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_geometry_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_probe_kernel));

@@ -181,6 +181,8 @@ class Engine:
         "adb_widen_i32_to_u64": (C.c_int32, [_I32P, C.c_int64, C.c_void_p]),
         "adb_iota_i32": (C.c_int32, [_I32P, C.c_int64, C.c_int32]),
         "adb_chain_config": (C.c_int32, [C.c_int32, C.c_int32]),
+        "adb_join_build": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int64]),
+        "adb_join_probe_sharded": (C.c_int32, [C.c_int32, _I32P, _I32P, C.c_int64, C.c_int32, _I64P]),
         "adb_alloc_cached_on": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p), C.c_size_t]),
         "adb_free_cached_on": (C.c_int32, [C.c_int32, C.c_void_p]),
         "adb_chain_select_agg": (C.c_int32, [_I32P, _I32P, C.c_int64, _I32P, _I32P, _I64P, C.POINTER(_AggStruct),

@@ -121,6 +121,7 @@ static struct {
     int mu_ready;
 } S;
 
+static size_t jx_cap_now;                           /* pairs a GPU's join receive region holds */
 static __thread char t_err[384];
 
 const char *adb_host_last_error(void) { return t_err; }
@@ -687,6 +688,7 @@ void adb_host_shutdown(void) {
         S.d_part[g] = S.d_out[g] = NULL;
     }
     workers_stop();
+    jx_cap_now = 0;
     S.up = 0;
     unlock();
     free(old);
@@ -2172,13 +2174,132 @@ Result *sub(Result *column_one, Result *column_two, Status *ret_status) {
 /* src/query.c:585-696.  results[0] lists side-one positions, results[1] side-two positions;
  * hash join is probe-major over side two, nested-loop outer-major over side one.  The
  * caller frees the two-element array (src/server.c:432).
- * G > 1: the four operands are brought to context 0 over peer copies and joined there (the
- * output order of the reference is global -- probe-major -- so the result is one list);
- * the sharded form of the join (hash-partitioned over the GPUs, adb_peer_exchange_pairs) is
- * measured through the C-ABI by bench.py. */
+ * A GPU count that is not a power of two (the exchange's routing takes hash bits): the four
+ * operands are brought to context 0 over peer copies and joined there. */
+/* G = 2, 4, 8, 16: the join itself is sharded.  The build side is hash-partitioned over the GPUs
+ * through peer memory (adb_peer_exchange_pairs), every GPU builds the tables of its keys, and
+ * every GPU probes ITS slice of the probe side, in its original order, reading a key's table
+ * from its owner over NVLink.  The slices' outputs concatenated in shard order are the
+ * reference's probe-major list, so nothing is gathered and nothing re-sorted. */
+typedef struct JoinJob {
+    ShardErr err;
+    Staged *bv, *bp, *pv, *pp;
+    int swapped, phase, overflow;
+    Shards o1, o2;
+} JoinJob;
+static void join_shard(int g, void *arg) {
+    JoinJob *a = arg;
+    if (a->phase == 0) {
+        int64_t rn = 0;
+        const int32_t *rv = NULL, *rp = NULL;
+        const adb_status s = adb_peer_exchange_pairs(0, a->bv->d[g], a->bp->d[g], (int64_t)a->bv->n[g], &rn, &rv, &rp);
+        if (s == ADB_ERR_NOMEM) {                   /* every GPU sees the same verdict: retry with more room */
+            a->overflow = 1;
+            return;
+        }
+        if (s != ADB_OK) {
+            shard_fail(&a->err, g, "adb_peer_exchange_pairs");
+            return;
+        }
+        SCK(adb_join_build(rv, rp, rn, (int64_t)a->pv->n[g]));
+        return;
+    }
+    int64_t m = 0;
+    SCK(adb_join_probe_sharded(S.G, a->pv->d[g], a->pp->d[g], (int64_t)a->pv->n[g], a->swapped, &m));
+    void *x = NULL, *y = NULL;
+    SCK(adb_alloc(&x, 4 * (size_t)m));
+    a->o1.d[g] = x;
+    SCK(adb_alloc(&y, 4 * (size_t)m));
+    a->o2.d[g] = y;
+    a->o1.n[g] = a->o2.n[g] = (size_t)m;
+    SCK(adb_join_emit(x, y));
+}
+
+static int ensure_join_exchange(size_t cap) {
+    if (cap <= jx_cap_now) return 0;
+    sync_all();
+    if (adb_peer_join_connect_local((int64_t)cap) != ADB_OK) {
+        set_err("adb_peer_join_connect_local(%zu): %s", cap, adb_last_error());
+        return -1;
+    }
+    jx_cap_now = cap;
+    return 0;
+}
+
+static Result **join_sharded(Result *v1, Result *p1, Result *v2, Result *p2, int nested, Status *st) {
+    const char *what = nested ? "nested_loop_join" : "hash_join";
+    Staged a, b, c, d;
+    memset(&a, 0, sizeof a); memset(&b, 0, sizeof b); memset(&c, 0, sizeof c); memset(&d, 0, sizeof d);
+    JoinJob job;
+    memset(&job, 0, sizeof job);
+    Result **results = NULL;
+    {
+        Result h1 = *p1, h2 = *p2;
+        h1.num_tuples = v1->num_tuples;
+        h2.num_tuples = v2->num_tuples;
+        if (stage(v1, NULL, &a) || stage(&h1, a.n, &b) || stage(v2, NULL, &c) || stage(&h2, c.n, &d)) goto fail;
+    }
+    /* hash join: side one is grouped (build), side two walked in order (probe); nested-loop
+     * join is outer-major over side one: side one probes (src/query.c:597-611,669-681) */
+    job.bv = nested ? &c : &a;
+    job.bp = nested ? &d : &b;
+    job.pv = nested ? &a : &c;
+    job.pp = nested ? &b : &d;
+    job.swapped = nested;
+    const size_t nb = job.bv->total;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        /* head room of 50 % over an even split; a skewed key set gets the whole side's worth */
+        if (ensure_join_exchange(attempt ? nb + 64 : nb / (size_t)S.G + nb / (2 * (size_t)S.G) + 65536)) goto fail;
+        job.phase = 0;
+        job.overflow = 0;
+        run_shards(join_shard, &job);
+        if (shard_errs(&job.err)) goto fail;
+        if (!job.overflow) break;
+        if (attempt) {
+            set_err("%s: the build side does not fit the exchange regions", what);
+            goto fail;
+        }
+    }
+    job.phase = 1;
+    run_shards(join_shard, &job);
+    if (shard_errs(&job.err)) goto fail;
+    unstage(&a); unstage(&b); unstage(&c); unstage(&d);
+    results = malloc(2 * sizeof *results);
+    if (!results) {
+        set_err("out of host memory");
+        goto fail;
+    }
+    results[0] = new_dev_result(&job.o1);
+    if (!results[0]) {
+        shards_free(&job.o2);
+        memset(&job.o1, 0, sizeof job.o1);
+        memset(&job.o2, 0, sizeof job.o2);
+        goto fail;
+    }
+    results[1] = new_dev_result(&job.o2);
+    if (!results[1]) {
+        drop_result(results[0]);
+        memset(&job.o1, 0, sizeof job.o1);
+        memset(&job.o2, 0, sizeof job.o2);
+        goto fail;
+    }
+    op_ok(st);
+    return results;
+fail:
+    shards_free(&job.o1);
+    shards_free(&job.o2);
+    unstage(&a); unstage(&b); unstage(&c); unstage(&d);
+    free(results);
+    return op_fail(st, what);
+}
+
 static Result **join(Result *v1, Result *p1, Result *v2, Result *p2, int nested, Status *st) {
     t_err[0] = '\0';
     const char *what = nested ? "nested_loop_join" : "hash_join";
+    if (ensure_up()) return op_fail(st, what);
+    if (S.G > 1 && (S.G & (S.G - 1)) == 0 && v1 && p1 && v2 && p2 && v1->num_tuples && v2->num_tuples &&
+        p1->num_tuples >= v1->num_tuples && p2->num_tuples >= v2->num_tuples)
+        return join_sharded(v1, p1, v2, p2, nested, st);
     Staged a, b, c, d;
     memset(&a, 0, sizeof a); memset(&b, 0, sizeof b); memset(&c, 0, sizeof c); memset(&d, 0, sizeof d);
     int32_t *o1 = NULL, *o2 = NULL;

@@ -502,7 +502,7 @@ def run_engine(args):
     # second half of BASELINE.json's metric: hash-join tuples/s (config 4).  N > 1: both tables
     # row-range sharded, pairs hash-routed to their owners, joined locally.
     join_sharded = None
-    if world > 1 and not args.no_join:
+    if world > 1 and args.join_torch:
         join_sharded = measure_join_sharded(eng, dist, rank, world, local, args.gloo)
 
     # ---- parity at every N: each rank diffs a window of every shard it owns -- positions and
@@ -527,6 +527,14 @@ def run_engine(args):
         cold = e2e.pop("cold", None)
         for k_, v_ in (e2e.pop("configs", None) or {}).items():
             line[k_] = v_
+        aj = e2e.pop("api_join", None)
+        if aj is not None and "error" not in aj:
+            line["hash_join"] = join_summary(aj, max(world, 1))
+            line["hash_join"]["through"] = "the operator API (host/query_shim.c), one host process"
+            if "parity" in line:
+                line["parity"]["join"] = aj.get("parity")
+        elif aj is not None:
+            line["hash_join"] = aj
         line["e2e"] = e2e
         if cold is not None:
             line["e2e_cold"] = cold
@@ -536,14 +544,14 @@ def run_engine(args):
             for c1, c2 in cols[1:]:
                 c1.free()
                 c2.free()
-        if world == 1 and not args.no_join and not args.ops:
-            line["hash_join"] = measure_join_single(args)
+        if world == 1 and args.join_torch and not args.ops:
+            line["hash_join_c_abi"] = measure_join_single(args)
         if world == 1 and args.ops:
             line["ops"] = measure_ops(args)
             if "hash_join_100Mx100M" in line["ops"]:
                 line["hash_join"] = join_summary(line["ops"]["hash_join_100Mx100M"], 1)
         if world > 1 and join_sharded is not None:
-            line["hash_join"] = join_summary(join_sharded, world)
+            line["hash_join_process_per_gpu"] = join_summary(join_sharded, world)
         emit(line)
     barrier()
     if dist is not None:
@@ -726,6 +734,11 @@ def measure_e2e(args, eng, cols, shard_rows, lo, hi, world, dist, rank, expect):
                               "config3_index": api_index(eng, api, q, G, sync_all)}
         except Exception as e:                              # the headline line must survive
             out["configs"] = {"error": repr(e)}
+    if not args.no_join:
+        try:
+            out["api_join"] = api_join(eng, api, q, G, sync_all)
+        except Exception as e:
+            out["api_join"] = {"error": repr(e)}
     # cold: HOST columns, re-uploaded by the shim inside every timed step
     if world == 1 and not args.no_cold:
         c1, c2 = cols[0]
@@ -957,6 +970,86 @@ def api_index(eng, api, q, G, sync_all, n=500_000_000):
     return out
 
 
+def api_join(eng, api, q, G, sync_all, n=100_000_000):
+    """BASELINE config 4 through the operator API: two 100 M-row tables (key uniform in [1, n],
+    filter column uniform in [0, 1000)), prefilter select(f, null, x) + fetch(k, .) on each side,
+    then hash_join(v1, p1, v2, p2) of the reference's query.h -- ONE call that, with G > 1,
+    hash-partitions the build side over the GPUs through peer memory and probes every GPU's slice
+    of the probe side in place (host/query_shim.c join_sharded).  Output order is the
+    reference's (probe-major), checked element for element on a 2 M-row instance."""
+    from analytical_database_b200 import synth
+    L = api.lib
+    cpu, kind, _ = cpu_ops()
+
+    def tables(rows, seeds):
+        cols, bufs = {}, []
+        for name, seed, lo, span in (("k1", seeds[0], 1, rows), ("f1", seeds[1], 0, 1000),
+                                     ("k2", seeds[2], 1, rows), ("f2", seeds[3], 0, 1000)):
+            c, b = adopt_sharded(eng, api, q, G, rows,
+                                 lambda g, first, cnt, s_=seed, l_=lo, sp_=span: eng.synth_uniform(cnt, s_, first, l_, sp_),
+                                 name.encode())
+            cols[name] = c
+            bufs.append((c, b))
+        return cols, bufs
+
+    def prefiltered(cols, x1, x2):
+        p1 = api.select_column(cols["f1"], None, x1)
+        p2 = api.select_column(cols["f2"], None, x2)
+        v1, v2 = api.fetch_column(cols["k1"], p1), api.fetch_column(cols["k2"], p2)
+        return v1, p1, v2, p2
+
+    # ---- parity: 2 M x 2 M rows, prefilters 0.8 / 0.15, pair lists element for element
+    ns = 2_000_000
+    cols, bufs = tables(ns, (21, 23, 22, 24))
+    v1, p1, v2, p2 = prefiltered(cols, 800, 150)
+    o1, o2 = api.join("hash_join", v1, p1, v2, p2)
+    k1, f1 = synth.uniform(ns, 21, 0, 1, ns), synth.uniform(ns, 23, 0, 0, 1000)
+    k2, f2 = synth.uniform(ns, 22, 0, 1, ns), synth.uniform(ns, 24, 0, 0, 1000)
+    e1, e2 = cpu.select_scan(f1, None, 800), cpu.select_scan(f2, None, 150)
+    r1, r2 = cpu.hash_join(k1[e1], e1, k2[e2], e2)
+    parity = bool(np.array_equal(api.tuples(o1), r1) and np.array_equal(api.tuples(o2), r2))
+    for h_ in (v1, p1, v2, p2, o1, o2):
+        api.drop(h_)
+    for c, b in bufs:
+        free_sharded(eng, api, c, b)
+    if not parity:
+        raise SystemExit("PARITY FAILURE: hash_join through the operator API differs from the reference's pair lists")
+    # ---- timing at full size
+    cols, bufs = tables(n, (11, 13, 12, 14))
+    cases = {"parity": True,
+             "parity_detail": f"2M x 2M rows, prefilters 0.8 / 0.15, {r1.size} pairs element for element "
+                              f"(probe-major order) vs {kind}"}
+    for s1, s2 in ((0.8, 0.15), (1.0, 1.0)):
+        v1, p1, v2, p2 = prefiltered(cols, int(1000 * s1), int(1000 * s2))
+        api.tuples(v1)[:1], api.tuples(v2)[:1]             # the lazy handles are written before the clock starts
+        ms = []
+        for it in range(4):
+            sync_all()
+            t0 = time.perf_counter()
+            o1, o2 = api.join("hash_join", v1, p1, v2, p2)
+            sync_all()
+            ms.append(1e3 * (time.perf_counter() - t0))
+            m = o1.contents.num_tuples
+            api.drop(o1)
+            api.drop(o2)
+        best = min(ms[1:])
+        nb, np_ = v1.contents.num_tuples, v2.contents.num_tuples
+        cases[f"prefilter_{s1}_{s2}"] = {
+            "build": int(nb), "probe": int(np_), "matches": int(m), "ms": best, "world": G,
+            "tuples_per_s": (nb + np_) / (best * 1e-3),
+            "algorithmic_bytes": 8.0 * (nb + np_) + 8.0 * m, "formula": "8(B+P) + 8M (SURVEY.md 8d)",
+            "alg_gbs": (8.0 * (nb + np_) + 8.0 * m) / (best * 1e-3) / 1e9,
+            "includes": "hash_join of include/adb_query_api.h, wall clock: "
+                        + ("build-side exchange over NVLink peer memory, per-GPU tables, probe in place with "
+                           "peer table reads, output sized and written" if G > 1 else
+                           "sort + tables + probe + offsets + expansion on one GPU")}
+        for h_ in (v1, p1, v2, p2):
+            api.drop(h_)
+    for c, b in bufs:
+        free_sharded(eng, api, c, b)
+    return cases
+
+
 def measure_join_sharded(eng, dist, rank, world, local, args_gloo):
     """BASELINE config 4: hash join of two 100 M-row tables with selective prefilters, both
     row-range sharded over the ranks, pairs hash-routed by key and pushed into the destination
@@ -1176,6 +1269,9 @@ def main():
     ap.add_argument("--no-configs", action="store_true",
                     help="skip BASELINE configs 2 (shared scan) and 3 (index) through the operator API")
     ap.add_argument("--no-join", action="store_true", help="skip the hash-join measurement (config 4)")
+    ap.add_argument("--join-torch", action="store_true",
+                    help="also time the process-per-GPU join of analytical-database_b200/sharded.py (peer exchange "
+                         "vs NCCL all-to-all-v; round-1 form) and the single-GPU C-ABI join")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: aggregate exchange through the engine's peer-memory kernel or NCCL")
     ap.add_argument("--exchange-self", action="store_true",

@@ -410,6 +410,23 @@ ADB_API adb_status adb_nested_loop_join_count(const int32_t *d_v1, const int32_t
                                               const int32_t *d_v2, const int32_t *d_p2, int64_t n2,
                                               int64_t *h_matches);
 ADB_API adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2);
+/* The join sharded over the contexts of ONE process (SURVEY.md 8e "hash join: hash-partition both
+ * (key, pos) lists by key to G GPUs"), keeping the reference's output order:
+ *   1. every context routes its slice of the BUILD side to the keys' owners
+ *      (adb_peer_exchange_pairs, side 0: pieces land in source-rank order = insertion order);
+ *   2. every context calls adb_join_build on what it received (sort on the hash + one table per
+ *      partition, as steps 1-3 of adb_hash_join_count); probe_rows_hint = the probe rows this
+ *      context will bring (scratch is reserved for them).  Synchronises;
+ *   3. once EVERY context has built, each calls adb_join_probe_sharded with its own slice of the
+ *      PROBE side, in its original order: a key's table is read from its owner over NVLink peer
+ *      memory; *h_matches = this context's pair count;
+ *   4. adb_join_emit writes this context's pairs (multi-row groups read the owner's sorted build
+ *      positions over peer memory).  Synchronises.
+ * The contexts' outputs concatenated in context order are the reference's probe-major list.
+ * world = number of contexts, a power of two; swapped as in adb_nested_loop_join_count. */
+ADB_API adb_status adb_join_build(const int32_t *d_v, const int32_t *d_p, int64_t n, int64_t probe_rows_hint);
+ADB_API adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np,
+                                          int32_t swapped, int64_t *h_matches);
 
 /* ---- multi-GPU join exchange, send side (no reference equivalent: SURVEY.md 8e) ----------
  * Stable partition of a (value, position) pair list by destination rank = the top

@@ -52,8 +52,8 @@ def mismatches(ref, b200):
             and not same(t, b200[t], ref[t])]
 
 
-@pytest.fixture(scope="module", params=[("1", "reference"), ("1", "engine"), ("3", "engine")],
-                ids=["1gpu-reference_index", "1gpu-engine_index", "3gpus-engine_index"])
+@pytest.fixture(scope="module", params=[("1", "reference"), ("1", "engine"), ("3", "engine"), ("4", "engine")],
+                ids=["1gpu-reference_index", "1gpu-engine_index", "3gpus-engine_index", "4gpus-engine_index"])
 def outputs(request):
     """Both pairs replay the suite.  The unmodified client reads a reply with a single recv
     (client.c:127), so a replay can come out truncated on either side for

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 I32MAX = 2**31 - 1
 
 
-@pytest.fixture(scope="module", params=[1, 2, 3], ids=["1gpu", "2gpus", "3gpus"])
+@pytest.fixture(scope="module", params=[1, 2, 3, 4], ids=["1gpu", "2gpus", "3gpus", "4gpus"])
 def api(request):
     """The whole module runs three times: on one GPU, and with every column row-range sharded
     over 2 and 3 engine contexts driven from ONE process (host/query_shim.c, adb_host_init_multi).
@@ -774,4 +774,17 @@ def test_join_of_sharded_operands(api, cpu, rng):
     assert api.tuples(a)[0].tobytes() == np.float64(cpu.avg(f1[e1])).tobytes()
     for r in (p1, p2, v1, v2, o1, o2, g1, a):
         api.drop(r)
+    # heavy skew: a few hundred keys, groups of hundreds of rows spread over every GPU (the probing
+    # GPU reads the owner's sorted build positions over peer memory), both join kinds
+    s1, s2 = rng.integers(1, 300, 40_000).astype(np.int32), rng.integers(1, 400, 900).astype(np.int32)
+    q1, q2 = rng.permutation(40_000).astype(np.int32), rng.permutation(900).astype(np.int32)
+    R = [C.pointer(api.host_result(x)) for x in (s1, q1, s2, q2)]
+    for name in ("hash_join", "nested_loop_join"):
+        if name == "nested_loop_join":                       # quadratic in the oracle: smaller
+            R = [C.pointer(api.host_result(x)) for x in (s1[:3000], q1[:3000], s2, q2)]
+        o1, o2 = api.join(name, *R)
+        args = (s1, q1, s2, q2) if name == "hash_join" else (s1[:3000], q1[:3000], s2, q2)
+        e1, e2 = getattr(cpu, name)(*args)
+        assert np.array_equal(api.tuples(o1), e1) and np.array_equal(api.tuples(o2), e2), name
+        api.drop(o1), api.drop(o2)
     assert api.lib.adb_host_live_device_results() == live0
