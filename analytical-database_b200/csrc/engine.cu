@@ -87,6 +87,10 @@ struct Engine {
     // join tables: one open-addressing table per build partition, 16-byte slots (grow-only)
     void *hj_table = nullptr;
     unsigned long long hj_table_slots = 0;
+    // sharded join: local copies of the other contexts' partition -> slot-range tables (a probe
+    // then costs ONE remote read, the slot, instead of two dependent ones)
+    unsigned long long *toff_replica = nullptr;
+    size_t toff_replica_words = 0;
     // bulk CSV load state (adb_csv_index -> adb_csv_parse); scratch is grow-only
     struct CsvState {
         const unsigned char *text = nullptr;
@@ -590,6 +594,7 @@ static adb_status shutdown_current() {
     cudaFree(g.sc_sums);
     cudaFree(g.arena);
     cudaFree(g.hj_table);
+    cudaFree(g.toff_replica);
     cudaFree(g.fmt.block_len);
     cudaFree(g.fmt.block_off);
     cudaFree(g.fmt.total);
@@ -2202,10 +2207,20 @@ adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int3
     if (np64 > 0 && (!d_pv || !d_pp)) return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: NULL device pointer");
     const uint32_t np = (uint32_t)np64;
     adb::JoinOwners o{};
+    size_t replica_used = 0;
     for (int r = 0; r < world; ++r) {
         const Engine &E = g_ctx[r];
         if (!E.up || !E.join.built) return fail(ADB_ERR_INVALID, "adb_join_probe_sharded: context %d has built no tables", r);
         o.toff[r] = E.join.toff;
+        const size_t words = ((size_t)1 << E.join.part_bits) + 1;
+        if (&E != &g && np64 > 0 && replica_used + words <= g.toff_replica_words) {
+            // a local copy of the owner's (small) partition table: the probe's only remote read is the slot
+            unsigned long long *mine = g.toff_replica + replica_used;
+            if (E.device == g.device) CU(cudaMemcpyAsync(mine, E.join.toff, words * 8, cudaMemcpyDeviceToDevice, g.stream));
+            else CU(cudaMemcpyPeerAsync(mine, g.device, E.join.toff, E.device, words * 8, g.stream));
+            o.toff[r] = mine;
+            replica_used += words;
+        }
         o.table[r] = static_cast<const uint4 *>(E.hj_table);
         o.bpos[r] = E.join.build_pos_sorted;
         o.part_bits[r] = E.join.part_bits;
@@ -2227,15 +2242,63 @@ adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int3
     int64_t *tot = ARENA_TAKE(int64_t, 2);
     j.gc_by_j = ARENA_TAKE(uint2, np);
     j.off_by_j = ARENA_TAKE(uint32_t, np);
+    StageTrace tr;
     launches += adb::launch_hj_probe_sharded(j.probe_keys, np, o, j.gc_by_j, g.sm_count, g.stream);
+    tr.lap("probe (peer table reads)");
     launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
     if (adb_status s = read_back(&j.matches, tot, sizeof(int64_t))) return s;
+    tr.lap("output offsets");
     if (adb_status s = after_launch("join_probe_sharded", launches)) return s;
     if (j.matches >= (int64_t)1 << 31)
         return fail(ADB_ERR_INVALID, "join produces %lld pairs on one context; the result must stay below 2^31",
                     (long long)j.matches);
     j.ready = true;
     if (h_matches) *h_matches = j.matches;
+    return ADB_OK;
+}
+
+// Everything adb_peer_exchange_pairs / adb_join_build allocate, sized up front.  Device memory
+// management can wait for the device to go idle; a context that did that while a peer context
+// ON THE SAME DEVICE sits in the exchange's spin-wait for it would stall both (contexts sharing
+// a device is the 1-GPU test configuration).  Call on every context, wait for all, then start
+// the collective.
+adb_status adb_peer_exchange_reserve(int64_t send_pairs, int64_t build_pairs, int64_t probe_rows) {
+    NEED_UP();
+    if (adb_status s = check_len(send_pairs, "adb_peer_exchange_reserve")) return s;
+    if (adb_status s = check_len(build_pairs, "adb_peer_exchange_reserve")) return s;
+    if (adb_status s = check_len(probe_rows, "adb_peer_exchange_reserve")) return s;
+    const uint32_t big = (uint32_t)(send_pairs > build_pairs ? send_pairs : build_pairs);
+    if (adb_status s = ensure_radix_scratch(big ? big : 1)) return s;
+    const uint32_t nb = (uint32_t)build_pairs, np = (uint32_t)probe_rows;
+    uint32_t part_bits = 1;
+    while (part_bits < 20 && (nb >> part_bits) > 1024) ++part_bits;
+    const uint32_t num_parts = 1u << part_bits;
+    if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
+                                     arena_round((size_t)np * 4) + arena_round((size_t)(num_parts + 1) * 4) +
+                                     arena_round((size_t)(num_parts + 1) * 8) + 8192))
+        return s;
+    {
+        const size_t words = (size_t)ADB_MAX_PEERS * ((size_t)num_parts + 1);
+        if (words > g.toff_replica_words) {
+            CU(cudaStreamSynchronize(g.stream));
+            if (g.toff_replica) CU(cudaFree(g.toff_replica));
+            g.toff_replica = nullptr;
+            g.toff_replica_words = 0;
+            CU(cudaMalloc(&g.toff_replica, words * sizeof(unsigned long long)));
+            g.toff_replica_words = words;
+        }
+    }
+    // tables: <= 2.5 slots per build row (power-of-two capacity at <= 80 % load) + 16 per partition
+    const unsigned long long slots = (unsigned long long)nb * 5 / 2 + 16ull * num_parts + 4096;
+    if (slots > g.hj_table_slots) {
+        CU(cudaStreamSynchronize(g.stream));
+        if (g.hj_table) CU(cudaFree(g.hj_table));
+        g.hj_table = nullptr;
+        g.hj_table_slots = 0;
+        cudaError_t e = cudaMalloc(&g.hj_table, slots * 16);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ADB_ERR_NOMEM, "join tables (%llu slots): %s", slots, cudaGetErrorString(e)); }
+        g.hj_table_slots = slots;
+    }
     return ADB_OK;
 }
 
@@ -2266,6 +2329,8 @@ adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2) {
         rc = after_launch("join_expand", k_);
     }
     if (j.sharded) {
+        StageTrace tr;
+        tr.lap("expand (sharded)");
         // the other contexts' expansions may still be reading this context's tables and sorted
         // build positions: they stay until the next join on this context (the host waits for
         // every context's emit before it starts one)

@@ -182,6 +182,7 @@ class Engine:
         "adb_iota_i32": (C.c_int32, [_I32P, C.c_int64, C.c_int32]),
         "adb_chain_config": (C.c_int32, [C.c_int32, C.c_int32]),
         "adb_join_build": (C.c_int32, [_I32P, _I32P, C.c_int64, C.c_int64]),
+        "adb_peer_exchange_reserve": (C.c_int32, [C.c_int64, C.c_int64, C.c_int64]),
         "adb_join_probe_sharded": (C.c_int32, [C.c_int32, _I32P, _I32P, C.c_int64, C.c_int32, _I64P]),
         "adb_alloc_cached_on": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p), C.c_size_t]),
         "adb_free_cached_on": (C.c_int32, [C.c_int32, C.c_void_p]),

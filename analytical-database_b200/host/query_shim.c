@@ -2185,10 +2185,16 @@ typedef struct JoinJob {
     ShardErr err;
     Staged *bv, *bp, *pv, *pp;
     int swapped, phase, overflow;
+    size_t cap;                                     /* pairs a GPU can receive */
     Shards o1, o2;
 } JoinJob;
 static void join_shard(int g, void *arg) {
     JoinJob *a = arg;
+    if (a->phase == -1) {
+        /* all scratch sized before anybody starts the collective (see adb_peer_exchange_reserve) */
+        SCK(adb_peer_exchange_reserve((int64_t)a->bv->n[g], (int64_t)a->cap, (int64_t)a->pv->n[g]));
+        return;
+    }
     if (a->phase == 0) {
         int64_t rn = 0;
         const int32_t *rv = NULL, *rp = NULL;
@@ -2250,6 +2256,10 @@ static Result **join_sharded(Result *v1, Result *p1, Result *v2, Result *p2, int
     for (int attempt = 0; attempt < 2; ++attempt) {
         /* head room of 50 % over an even split; a skewed key set gets the whole side's worth */
         if (ensure_join_exchange(attempt ? nb + 64 : nb / (size_t)S.G + nb / (2 * (size_t)S.G) + 65536)) goto fail;
+        job.cap = jx_cap_now < nb ? jx_cap_now : nb;
+        job.phase = -1;
+        run_shards(join_shard, &job);
+        if (shard_errs(&job.err)) goto fail;
         job.phase = 0;
         job.overflow = 0;
         run_shards(join_shard, &job);

@@ -424,6 +424,11 @@ ADB_API adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2);
  *      positions over peer memory).  Synchronises.
  * The contexts' outputs concatenated in context order are the reference's probe-major list.
  * world = number of contexts, a power of two; swapped as in adb_nested_loop_join_count. */
+/* Sizes every scratch buffer steps 1-3 will need on this context (exchange of send_pairs pairs,
+ * build over up to build_pairs received pairs, probe_rows probe rows) BEFORE the collective
+ * starts: device memory management may wait for the device to go idle, which must not happen
+ * while a context sharing the device spin-waits for this one.  Every context, then a barrier. */
+ADB_API adb_status adb_peer_exchange_reserve(int64_t send_pairs, int64_t build_pairs, int64_t probe_rows);
 ADB_API adb_status adb_join_build(const int32_t *d_v, const int32_t *d_p, int64_t n, int64_t probe_rows_hint);
 ADB_API adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np,
                                           int32_t swapped, int64_t *h_matches);
