@@ -334,7 +334,9 @@ void jx_close() {
     for (auto &p : g.jx_peer_host) p = nullptr;
     g.jx_peer_dev = nullptr;
     g.jx_connected = false;
-    g.jx_epoch = 0;
+    // jx_epoch is NOT reset: the epoch words live in the aggregate mailbox, which outlives the
+    // receive regions -- a new connection that started over at epoch 1 would take the previous
+    // connection's count rows for its own (only peer_close, which frees the mailbox, resets it)
     g.jx_status = nullptr;
     g.jx_total = nullptr;
 }
@@ -353,6 +355,7 @@ void peer_close() {
     g.peer_rank = -1;
     g.peer_connected = false;
     g.peer_epoch = 0;
+    g.jx_epoch = 0;
     g.peer_local = false;
 }
 
@@ -1168,7 +1171,6 @@ adb_status adb_peer_join_connect(const unsigned char *handles) {
     }
     CU(cudaMemcpy(g.jx_peer_dev, g.jx_peer_host, sizeof(uint32_t *) * ADB_MAX_PEERS, cudaMemcpyHostToDevice));
     g.jx_connected = true;
-    g.jx_epoch = 0;
     return ADB_OK;
 }
 
@@ -1332,7 +1334,6 @@ adb_status adb_peer_join_connect_local(int64_t cap_pairs) {
             for (int q = 0; q < world; ++q) g.jx_peer_host[q] = reinterpret_cast<uint32_t *>(g_ctx[q].jx_recv);
             CU(cudaMemcpy(g.jx_peer_dev, g.jx_peer_host, sizeof(uint32_t *) * ADB_MAX_PEERS, cudaMemcpyHostToDevice));
             g.jx_connected = true;
-            g.jx_epoch = 0;
             return ADB_OK;
         };
         rc = one();

@@ -2223,6 +2223,9 @@ static void join_shard(int g, void *arg) {
 
 static int ensure_join_exchange(size_t cap) {
     if (cap <= jx_cap_now) return 0;
+    size_t p2 = (size_t)1 << 17;                    /* grow in powers of two: reconnecting is a device-wide affair */
+    while (p2 < cap) p2 <<= 1;
+    if (p2 < ((size_t)1 << 31)) cap = p2;
     sync_all();
     if (adb_peer_join_connect_local((int64_t)cap) != ADB_OK) {
         set_err("adb_peer_join_connect_local(%zu): %s", cap, adb_last_error());

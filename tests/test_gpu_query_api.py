@@ -520,6 +520,21 @@ def test_random_walk_over_the_operator_api(api, cpu):
     assert api.lib.adb_host_live_device_results() <= live0
 
 
+def test_joins_of_growing_size_reconnect_the_exchange(api, cpu, rng):
+    """Every join larger than the exchange's receive regions re-creates them; the epoch words of
+    the exchange protocol live in a mailbox that survives, so epochs must keep counting (r02: a
+    restart at epoch 1 took the previous connection's count rows for its own)."""
+    for n1, n2 in [(300, 40), (2000, 299), (150_000, 90_000), (400_000, 1000), (700, 650)]:
+        v1 = rng.integers(0, max(n2, 50), n1).astype(np.int32)
+        v2 = rng.permutation(n2).astype(np.int32)
+        p1, p2 = np.arange(n1, dtype=np.int32), np.arange(n2, dtype=np.int32)
+        R = [C.pointer(api.host_result(x)) for x in (v1, p1, v2, p2)]
+        o1, o2 = api.join("hash_join", *R)
+        e1, e2 = cpu.hash_join(v1, p1, v2, p2)
+        assert np.array_equal(api.tuples(o1), e1) and np.array_equal(api.tuples(o2), e2), (n1, n2)
+        api.drop(o1), api.drop(o2)
+
+
 def test_recycled_payload_address_is_not_mistaken_for_a_device_result(api, rng):
     """A payload freed behind the shim's back whose address malloc then gives to a foreign host
     Result: the registry still knows the address, the tag the shim stamped into its own blocks is
