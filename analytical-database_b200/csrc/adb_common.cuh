@@ -375,6 +375,7 @@ struct SelectArgs {
     // publish kernel is launched.
     unsigned long long *pub;
     unsigned long long pub_seq;
+    unsigned int *mask_ticket;    // set: the predicate kernel of a count phase totals the counts itself
 };
 constexpr uint32_t kMboxWords = 256;                  // 2 KB: 150 batch counts fit
 __device__ __forceinline__ void mbox_publish(volatile unsigned long long *pub, unsigned long long seq,

@@ -913,9 +913,10 @@ adb_status adb_select_count_base(const int32_t *d_col, int64_t n, const int32_t 
     // the host wants the count: the kernel that totals it also hands it over (no publish launch)
     const bool fused_pub = h_count && g.mbox && a.n > 0;
     if (fused_pub) { a.pub = g.mbox_dev; a.pub_seq = ++g.mbox_seq; }
+    a.mask_ticket = g.agg_ticket + adb::kChainMaxSlices;       // (a spare, zeroed counter next to the slices')
     if (adb_status s = after_launch("select_count", adb::launch_select_mask(a, true, g.stream))) return s;
     const unsigned long long seq = a.pub_seq;
-    a.pub = nullptr; a.pub_seq = 0;
+    a.pub = nullptr; a.pub_seq = 0; a.mask_ticket = nullptr;
     a.base_pos = base_pos;
     g.sel_pending = a;
     g.sel_ready = true;

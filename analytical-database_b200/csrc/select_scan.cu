@@ -87,10 +87,21 @@ __device__ __forceinline__ void store_mask_words(uint32_t nib, uint32_t lane,
     }
 }
 
+// TOTAL: the count phase of the two-phase select.  The last warp to finish (a ticket) also sums
+// the per-chunk counts into *d_count and, when the host is waiting for the count, hands it over
+// through the mailbox: no count kernel, no publish kernel behind the predicate pass.  A separate
+// instantiation, so the chain's kernel is compiled exactly as before.
+struct MaskTotal {
+    int64_t *d_count;
+    unsigned int *ticket;             // zeroed; re-armed by the last warp
+    unsigned long long *pub;          // mapped host mailbox or nullptr
+    unsigned long long pub_seq;
+};
+template <bool TOTAL>
 __global__ void __launch_bounds__(SEL_THREADS)
 mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, uint32_t n_host,
             Range rg, uint32_t chunk_rows, uint32_t num_chunks, uint32_t *__restrict__ mask,
-            uint32_t *__restrict__ counts, bool stable_val, uint32_t chunk_offset) {
+            uint32_t *__restrict__ counts, bool stable_val, uint32_t chunk_offset, MaskTotal tot) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t chunk = chunk_offset + blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
     pdl_launch_dependents();
@@ -143,6 +154,26 @@ mask_kernel(const int32_t *__restrict__ val, const int64_t *__restrict__ d_n, ui
     }
     hits = warp_sum(hits);
     if (lane == 0) counts[chunk] = hits;
+    if constexpr (TOTAL) {
+        // one ticket per warp-chunk; whoever draws the last one totals the counts (9472 words from
+        // L2) while every other warp has long retired
+        uint32_t done = 0;
+        if (lane == 0) {
+            __threadfence();
+            done = atomicAdd(tot.ticket, 1u);
+        }
+        done = __shfl_sync(kFull, done, 0);
+        if (done != num_chunks - 1) return;
+        __threadfence();
+        unsigned long long acc = 0;
+        for (uint32_t i = lane; i < num_chunks; i += kWarp) acc += *reinterpret_cast<volatile uint32_t *>(counts + i);
+        acc = (unsigned long long)warp_sum_i64((int64_t)acc);
+        if (lane == 0) {
+            *tot.d_count = (int64_t)acc;
+            *tot.ticket = 0;
+            if (tot.pub) mbox_publish(tot.pub, tot.pub_seq, &acc, 1);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -522,8 +553,14 @@ int launch_select_mask(const SelectArgs &a, bool with_total, cudaStream_t s) {
         return 0;
     }
     const SelectGeom g = select_geom(a.n, a.sm_count);
-    launch_pdl(mask_kernel, g.grid, SEL_THREADS, 0, s, a.val, a.d_n, a.n, a.range, g.chunk_rows,
-               g.num_chunks, a.mask, a.counts, a.stable_val, 0u);
+    if (with_total && a.mask_ticket) {
+        launch_pdl(mask_kernel<true>, g.grid, SEL_THREADS, 0, s, a.val, a.d_n, a.n, a.range, g.chunk_rows,
+                   g.num_chunks, a.mask, a.counts, a.stable_val, 0u,
+                   MaskTotal{a.d_count, a.mask_ticket, a.pub, a.pub_seq});
+        return 1;
+    }
+    launch_pdl(mask_kernel<false>, g.grid, SEL_THREADS, 0, s, a.val, a.d_n, a.n, a.range, g.chunk_rows,
+               g.num_chunks, a.mask, a.counts, a.stable_val, 0u, MaskTotal{});
     if (!with_total) return 1;
     count_total_kernel<<<1, 1024, 0, s>>>(a.counts, g.num_chunks, a.d_count, a.pub, a.pub_seq);
     return 2;
@@ -592,8 +629,8 @@ int launch_chain_sliced(const SelectArgs &a, uint32_t slices, uint32_t chunks_pe
         const uint32_t grid = (c1 - c0 + SEL_WARPS - 1) / SEL_WARPS;
         // mask: chunks [c0, c1) (the kernel's own bound is num_chunks; a CTA's spare warps past
         // c1 would redo the next slice's first chunks, so the bound passed is c1)
-        launch_pdl(mask_kernel, grid, SEL_THREADS, 0, main_s, a.val, a.d_n, a.n, a.range, g.chunk_rows, c1,
-                   a.mask, a.counts, a.stable_val, c0);
+        launch_pdl(mask_kernel<false>, grid, SEL_THREADS, 0, main_s, a.val, a.d_n, a.n, a.range, g.chunk_rows, c1,
+                   a.mask, a.counts, a.stable_val, c0, MaskTotal{});
         cudaEventRecord(mask_done[k], main_s);
         cudaStreamWaitEvent(side_s, mask_done[k], 0);
         const ChainArgs c{a.fetch_col, a.val_out, slice_parts + k, a.agg_scratch + (size_t)k * grid_cap, a.agg_ticket + k};
@@ -629,7 +666,8 @@ void preload_select_scan() {
     { auto *fp = &expand_kernel<false, false>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &expand_kernel<false, true, false>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &expand_kernel<false, true, true>; preload_one(reinterpret_cast<const void *>(fp)); }
-    preload_one(reinterpret_cast<const void *>(&mask_kernel));
+    { auto *fp = &mask_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &mask_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }
     preload_one(reinterpret_cast<const void *>(&scan_gather_agg_kernel));
 }
 
