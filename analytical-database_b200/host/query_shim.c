@@ -111,6 +111,7 @@ static struct {
     int up, failed, mirror, lazy;
     int G;                      /* contexts = shards */
     size_t shard_min_rows;
+    size_t rebalance_min;       /* index-ordered lists at least this long are re-cut evenly (ADB_REBALANCE_MIN) */
     DevColumn *cols;
     int ncols, capcols;
     DevResult *slots;           /* open addressing on payload address */
@@ -593,6 +594,8 @@ static int host_init(int first_device, int gpus) {
     const char *mn = getenv("ADB_SHARD_MIN_ROWS");
     S.shard_min_rows = mn ? (size_t)atol(mn) : 32;
     if (S.shard_min_rows < 1) S.shard_min_rows = 1;
+    const char *rb = getenv("ADB_REBALANCE_MIN");
+    S.rebalance_min = rb ? (size_t)atol(rb) : ((size_t)1 << 20);   /* shorter lists: the re-cut costs more than it saves */
     if (workers_start()) return -1;
     S.up = 1;
     S.failed = 0;
@@ -1608,6 +1611,29 @@ static Result *select_index_path(Column *column, DevColumn *c, int *low, int *hi
         }
     }
     job.out.aligned = 0;                            /* index order: positions anywhere */
+    if (S.G > 1) {
+        /* A range of a range-partitioned index lives in one or two slices, so one or two GPUs hold
+         * the whole (long) list and would do every later fetch / aggregate over it alone.  The
+         * list is the concatenation of the shards' buffers whatever the cut: re-cut it evenly over
+         * the GPUs with peer copies (order untouched). */
+        size_t total = 0, most = 0;
+        for (int g = 0; g < S.G; ++g) {
+            total += job.out.n[g];
+            if (job.out.n[g] > most) most = job.out.n[g];
+        }
+        if (total >= S.rebalance_min && most > 2 * (total / (size_t)S.G)) {
+            Shards even;
+            memset(&even, 0, sizeof even);
+            const size_t per = (total + (size_t)S.G - 1) / (size_t)S.G;
+            for (int g = 0; g < S.G; ++g) even.n[g] = shard_len(total, per, g);
+            if (recut(job.out.d, job.out.n, even.n, even.d)) {
+                shards_free(&even);
+                goto fail;
+            }
+            shards_free(&job.out);
+            job.out = even;
+        }
+    }
     {
         Result *r = new_dev_result(&job.out);
         if (!r) return op_fail(st, "select_column");

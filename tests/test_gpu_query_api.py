@@ -19,6 +19,8 @@ def api(request):
     over 2 and 3 engine contexts driven from ONE process (host/query_shim.c, adb_host_init_multi).
     On a 1-GPU box the contexts share the device -- same host code, same kernels, same peer
     exchange, the mailboxes simply live in one HBM."""
+    import os
+    os.environ["ADB_REBALANCE_MIN"] = "1000"      # index-ordered lists of the test sizes get re-cut too
     a = Api()
     if request.param == 1:
         assert a.lib.adb_host_init(0) == 0, a.lib.adb_host_last_error()
