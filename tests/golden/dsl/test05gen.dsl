@@ -1,7 +1,7 @@
 -- Summation
 --
--- SELECT SUM(col3) FROM tbl2 WHERE col1 >= -640 AND col1 < 960;
-s1=select(db1.tbl2.col1,-640,960)
+-- SELECT SUM(col3) FROM tbl2 WHERE col1 >= -4554 AND col1 < 3446;
+s1=select(db1.tbl2.col1,-4554,3446)
 f1=fetch(db1.tbl2.col3,s1)
 a1=sum(f1)
 print(a1)

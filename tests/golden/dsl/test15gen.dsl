@@ -8,16 +8,16 @@
 --
 --
 batch_queries()
-s0=select(db1.tbl3_batch.col4,1430,1490)
-s1=select(db1.tbl3_batch.col4,1432,1488)
-s2=select(db1.tbl3_batch.col4,1434,1486)
-s3=select(db1.tbl3_batch.col4,1436,1484)
-s4=select(db1.tbl3_batch.col4,1438,1482)
-s5=select(db1.tbl3_batch.col4,1440,1480)
-s6=select(db1.tbl3_batch.col4,1442,1478)
-s7=select(db1.tbl3_batch.col4,1444,1476)
-s8=select(db1.tbl3_batch.col4,1446,1474)
-s9=select(db1.tbl3_batch.col4,1448,1472)
+s0=select(db1.tbl3_batch.col4,6962,7022)
+s1=select(db1.tbl3_batch.col4,6964,7020)
+s2=select(db1.tbl3_batch.col4,6966,7018)
+s3=select(db1.tbl3_batch.col4,6968,7016)
+s4=select(db1.tbl3_batch.col4,6970,7014)
+s5=select(db1.tbl3_batch.col4,6972,7012)
+s6=select(db1.tbl3_batch.col4,6974,7010)
+s7=select(db1.tbl3_batch.col4,6976,7008)
+s8=select(db1.tbl3_batch.col4,6978,7006)
+s9=select(db1.tbl3_batch.col4,6980,7004)
 batch_execute()
 f0=fetch(db1.tbl3_batch.col1,s0)
 f1=fetch(db1.tbl3_batch.col1,s1)

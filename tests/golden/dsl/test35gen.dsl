@@ -1,11 +1,11 @@
 -- join test 2 - hash. Select + Join + aggregation
 -- Performs the join using hashing
 -- Query in SQL:
--- SELECT sum(tbl5_fact.col2), avg(tbl5_dim1.col1) FROM tbl5_fact,tbl5_dim1 WHERE tbl5_fact.col1=tbl5_dim1.col1 AND tbl5_fact.col2 < 60 AND tbl5_dim1.col3<60;
+-- SELECT sum(tbl5_fact.col2), avg(tbl5_dim1.col1) FROM tbl5_fact,tbl5_dim1 WHERE tbl5_fact.col1=tbl5_dim1.col1 AND tbl5_fact.col2 < 300 AND tbl5_dim1.col3<300;
 --
 --
-p1=select(db1.tbl5_fact.col2,null, 60)
-p2=select(db1.tbl5_dim1.col3,null, 60)
+p1=select(db1.tbl5_fact.col2,null, 300)
+p2=select(db1.tbl5_dim1.col3,null, 300)
 f1=fetch(db1.tbl5_fact.col1,p1)
 f2=fetch(db1.tbl5_dim1.col1,p2)
 t1,t2=join(f1,p1,f2,p2,hash)

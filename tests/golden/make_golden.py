@@ -15,8 +15,9 @@ time: DataFrame.to_csv(line_terminator=) -> lineterminato
 DataFrame.append -> pandas.concat.
 
 Usage (this container only -- /root/reference does not travel to the GPU box):
-    python tests/golden/make_golden.py [rows=2000] [seed=42]
-The committed fixtures were made with the defaults.
+    python tests/golden/make_golden.py [rows=10000] [seed=42]
+The committed fixtures were made with the defaults, which are the reference's own
+(project_tests/data_generation_scripts/gen_all_for_staff_use.sh:9-14: 10000 rows, seed 42).
 """
 import os
 import runpy
@@ -57,7 +58,7 @@ def run(script, argv):
 
 
 def main():
-    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 42
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF_GEN)

@@ -134,3 +134,73 @@ def test_histogram_counts(api, rng):
     bins = (data.astype(np.int64) - int(data.min())) // bin_size
     exp = np.bincount(bins[bins < 100], minlength=100)
     assert np.array_equal(np.array(counts[:], dtype=np.int64), exp)
+
+
+def test_config3_full_size_through_select_column(rng):
+    """BASELINE config 3 at full size through the operator API: 500 M rows, indexed key = a
+    permutation of 0..n-1 ((row * mul + add) mod n: unique keys, so every correct sort is the
+    reference's), payload uniform in [0, 10000).  Index build on the engine,
+    btree range select + fetch at 0.02 % and 1 %; oracle = the closed form of the permutation
+    (the row holding key v is inv(mul) * (v - add) mod n), which
+    test_unclustered_unique_keys_equal_the_reference_build pins to the reference's own index build
+    at sizes it can sort.  The same run on 2 engine contexts (sliced index, peer gathers)."""
+    import ctypes as C
+    import analytical_database_b200 as adb
+    from analytical_database_b200 import synth
+    import query_api as q
+    n, mul, add = 500_000_000, 387_420_489, 123_456_789
+    inv = pow(mul, -1, n)
+    for G in (1, 2):
+        api = Api()
+        assert api.lib.adb_host_init_multi(G) == 0, api.lib.adb_host_last_error()
+        eng = adb.Engine(0)
+        S = ((n + G - 1) // G + 31) // 32 * 32
+        cols = []
+        for name, fill in (("key", lambda first, cnt: _affine(eng, cnt, first, mul, add, n)),
+                           ("pay", lambda first, cnt: eng.synth_uniform(cnt, 8, first, 0, 10000))):
+            ptrs, bufs = (C.c_void_p * G)(), []
+            for g in range(G):
+                eng._ck(eng.lib.adb_ctx_select(g))
+                b = fill(g * S, max(1, min(S, n - g * S)))
+                eng.sync()
+                bufs.append(b)
+                ptrs[g] = b.ptr
+            eng._ck(eng.lib.adb_ctx_select(0))
+            c = q.Column()
+            c.name, c.row_count = name.encode(), n
+            if name == "key":
+                c.has_index, c.sorted, c.clustered = True, False, False
+            assert api.lib.adb_host_column_adopt_shards(C.byref(c), ptrs, S) == 0
+            cols.append((c, bufs))
+        (key, _), (pay, _) = cols
+        arr = (C.POINTER(q.Column) * 2)(C.pointer(key), C.pointer(pay))
+        assert api.lib.adb_host_index_build(arr, 2, 0) == 0, api.lib.adb_host_last_error()
+        hv = np.ctypeslib.as_array(key.index.contents.values, shape=(n,))
+        hp = np.ctypeslib.as_array(key.index.contents.positions, shape=(n,))
+        for a0 in (0, n // 3, n - (1 << 18)):                              # the catalog's host arrays
+            vs = np.arange(a0, a0 + (1 << 18), dtype=np.int64)
+            assert np.array_equal(hv[a0:a0 + (1 << 18)], vs.astype(np.int32))
+            assert np.array_equal(hp[a0:a0 + (1 << 18)], ((vs - add) % n * inv % n).astype(np.uint64))
+        for sel in (0.0002, 0.01):
+            lo = n // 7
+            hi = lo + int(n * sel)
+            s_ = api.select_column(key, lo, hi)
+            f_ = api.fetch_column(pay, s_)
+            assert s_.contents.num_tuples == hi - lo
+            gpos, gval = api.tuples(s_), api.tuples(f_)
+            vs = np.arange(lo, hi, dtype=np.int64)
+            epos = ((vs - add) % n * inv % n).astype(np.int32)
+            z = synth.mix64(8, epos.astype(np.uint64))
+            evals = (((z >> np.uint64(32)) * np.uint64(10000)) >> np.uint64(32)).astype(np.int32)
+            assert np.array_equal(gpos, epos) and np.array_equal(gval, evals), (G, sel)
+            api.drop(s_), api.drop(f_)
+        ix = key.index.contents
+        for ptr in (ix.values, ix.positions, key.index):
+            q._libc.free(C.cast(ptr, C.c_void_p))
+        api.lib.adb_host_shutdown()
+
+
+def _affine(eng, cnt, first, mul, add, n):
+    b = eng.alloc_i32(cnt)
+    eng._ck(eng.lib.adb_synth_affine(b.i32(), cnt, first, mul, add, n))
+    return b
