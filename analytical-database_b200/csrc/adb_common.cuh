@@ -418,6 +418,12 @@ int launch_ewise(const int32_t *a, const int32_t *b, int64_t n_max, const int64_
 int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_row, int32_t lo,
                           uint32_t span, int sm_count, cudaStream_t s);
 int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s);
+int launch_scatter_value(int32_t *col, int64_t n_rows, const int32_t *pos, int64_t n, int32_t base, int32_t value,
+                         int sm_count, cudaStream_t s);
+int launch_mark_rows(uint32_t *dead, int64_t n_rows, const int32_t *pos, int64_t n, int32_t base, int sm_count,
+                     cudaStream_t s);
+int launch_compact_rows(const int32_t *col, const uint32_t *dead, const uint32_t *dead_before, int64_t n_rows,
+                        int32_t *out, int sm_count, cudaStream_t s);
 int launch_synth_affine(int32_t *out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add, uint64_t modulus,
                         int sm_count, cudaStream_t s);
 int launch_iota(int32_t *out, int64_t n, int32_t first, int sm_count, cudaStream_t s);

@@ -84,6 +84,9 @@ struct Engine {
     // differently sized multi-hundred-MB blocks made the pool re-map memory on every join
     unsigned char *arena = nullptr;
     size_t arena_cap = 0, arena_used = 0;
+    // delete plan (adb_delete_rows_plan -> _apply): flags and prefix in the arena
+    uint32_t *del_dead = nullptr, *del_before = nullptr;
+    int64_t del_rows = -1;
     // join tables: one open-addressing table per build partition, 16-byte slots (grow-only)
     void *hj_table = nullptr;
     unsigned long long hj_table_slots = 0;
@@ -1810,6 +1813,7 @@ static size_t arena_round(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 // the arena before (a join waiting for its emit phase) is gone.
 static adb_status arena_reserve(size_t bytes) {
     g.join = Engine::JoinState{};
+    g.del_rows = -1;
     g.arena_used = 0;
     if (bytes <= g.arena_cap) return ADB_OK;
     CU(cudaStreamSynchronize(g.stream));
@@ -2457,6 +2461,53 @@ adb_status adb_narrow_u64_to_i32(const void *d_src_u64, int64_t n, int32_t *d_ds
     if (n == 0) return ADB_OK;
     const int k_ = adb::launch_narrow_u64(static_cast<const unsigned long long *>(d_src_u64), n, d_dst, g.sm_count, g.stream);
     return after_launch("narrow_u64", k_);
+}
+
+// ---- updates and deletes (milestone5.py:123-262) --------------------------------
+adb_status adb_update_rows(int32_t *d_col, int64_t n_rows, const int32_t *d_pos, int64_t n_pos, int32_t base_pos,
+                           int32_t value) {
+    NEED_UP();
+    if (adb_status s = check_len(n_pos, "adb_update_rows")) return s;
+    if (adb_status s = check_len(n_rows, "adb_update_rows")) return s;
+    if (n_pos > 0 && n_rows > 0 && (!d_col || !d_pos)) return fail(ADB_ERR_INVALID, "adb_update_rows: NULL device pointer");
+    return after_launch("update_rows", adb::launch_scatter_value(d_col, n_rows, d_pos, n_pos, base_pos, value,
+                                                                  g.sm_count, g.stream));
+}
+
+// Plan: which of n_rows rows die (positions d_pos[0 .. n_pos), duplicates allowed) and where the
+// survivors move.  *h_rows_left = rows left.  The plan lives in the engine's scratch arena until
+// the next sort / join / plan; adb_delete_rows_apply compacts one column with it.
+adb_status adb_delete_rows_plan(int64_t n_rows, const int32_t *d_pos, int64_t n_pos, int32_t base_pos,
+                                int64_t *h_rows_left) {
+    NEED_UP();
+    g.del_rows = -1;
+    if (adb_status s = check_len(n_rows, "adb_delete_rows_plan")) return s;
+    if (adb_status s = check_len(n_pos, "adb_delete_rows_plan")) return s;
+    if (!h_rows_left || (n_pos > 0 && !d_pos)) return fail(ADB_ERR_INVALID, "adb_delete_rows_plan: NULL pointer");
+    if (n_rows == 0) { *h_rows_left = 0; g.del_rows = 0; return ADB_OK; }
+    if (adb_status s = ensure_radix_scratch(1)) return s;
+    if (adb_status s = arena_reserve(2 * arena_round((size_t)n_rows * 4) + 4096)) return s;
+    g.del_dead = ARENA_TAKE(uint32_t, n_rows);
+    g.del_before = ARENA_TAKE(uint32_t, n_rows);
+    int64_t *tot = ARENA_TAKE(int64_t, 2);
+    CU(cudaMemsetAsync(g.del_dead, 0, (size_t)n_rows * 4, g.stream));
+    int k_ = adb::launch_mark_rows(g.del_dead, n_rows, d_pos, n_pos, base_pos, g.sm_count, g.stream);
+    k_ += adb::launch_exclusive_scan(g.del_dead, 1, g.del_before, (uint32_t)n_rows, g.sc_sums, tot, g.sm_count, g.stream);
+    if (adb_status s = after_launch("delete_rows_plan", k_)) return s;
+    int64_t dead = 0;
+    if (adb_status s = read_back(&dead, tot, sizeof dead)) return s;
+    g.del_rows = n_rows;
+    *h_rows_left = n_rows - dead;
+    return ADB_OK;
+}
+adb_status adb_delete_rows_apply(const int32_t *d_col, int32_t *d_col_out) {
+    NEED_UP();
+    if (g.del_rows < 0) return fail(ADB_ERR_INVALID, "adb_delete_rows_apply: no preceding adb_delete_rows_plan");
+    if (g.del_rows == 0) return ADB_OK;
+    if (!d_col || !d_col_out || d_col == d_col_out)
+        return fail(ADB_ERR_INVALID, "adb_delete_rows_apply: needs distinct input and output columns");
+    return after_launch("delete_rows_apply", adb::launch_compact_rows(d_col, g.del_dead, g.del_before, g.del_rows,
+                                                                      d_col_out, g.sm_count, g.stream));
 }
 
 adb_status adb_synth_affine(int32_t *d_out, int64_t n, uint64_t first_row, uint64_t mul, uint64_t add,

@@ -247,6 +247,38 @@ synth_affine_kernel(int32_t *__restrict__ out, int64_t n, uint64_t first_row, ui
         out[i] = (int32_t)(((first_row + (uint64_t)i) * mul + add) % modulus);
 }
 
+// ---- updates and deletes (milestone 5: relational_update / relational_delete,
+// project_tests/data_generation_scripts/milestone5.py:123-262; the reference's parser has no
+// branch for them, parse.c:876-960) ---------------------------------------------------------------
+// update: col[pos[i] - base] = value
+__global__ void __launch_bounds__(STREAM_THREADS)
+scatter_value_kernel(int32_t *__restrict__ col, int64_t n_rows, const int32_t *__restrict__ pos, int64_t n,
+                     int32_t base, int32_t value) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t r = (int64_t)ld_stream(pos + i) - base;       // rows of other shards are not this call's
+        if (r >= 0 && r < n_rows) col[r] = value;
+    }
+}
+// delete, step 1: dead[pos[i] - base] = 1 (dead was zeroed); rows outside [0, n_rows) are ignored
+__global__ void __launch_bounds__(STREAM_THREADS)
+mark_rows_kernel(uint32_t *__restrict__ dead, int64_t n_rows, const int32_t *__restrict__ pos, int64_t n,
+                 int32_t base) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t r = (int64_t)ld_stream(pos + i) - base;
+        if (r >= 0 && r < n_rows) dead[r] = 1u;
+    }
+}
+// delete, step 3: surviving row i moves to i - (dead rows before i); order is kept
+__global__ void __launch_bounds__(STREAM_THREADS)
+compact_rows_kernel(const int32_t *__restrict__ col, const uint32_t *__restrict__ dead,
+                    const uint32_t *__restrict__ dead_before, int64_t n_rows, int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += stride)
+        if (!dead[i]) out[i - dead_before[i]] = ld_stream(col + i);
+}
+
 // ---- launchers ------------------------------------------------------------------------------
 static int stream_grid(int64_t work_items, int sm_count, int per_sm) {
     const int64_t want = (work_items + STREAM_THREADS - 1) / STREAM_THREADS;
@@ -301,6 +333,26 @@ int launch_synth_affine(int32_t *out, int64_t n, uint64_t first_row, uint64_t mu
     return 1;
 }
 
+int launch_scatter_value(int32_t *col, int64_t n_rows, const int32_t *pos, int64_t n, int32_t base, int32_t value,
+                         int sm_count, cudaStream_t s) {
+    if (n <= 0 || n_rows <= 0) return 0;
+    scatter_value_kernel<<<stream_grid(n / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(col, n_rows, pos, n, base, value);
+    return 1;
+}
+int launch_mark_rows(uint32_t *dead, int64_t n_rows, const int32_t *pos, int64_t n, int32_t base, int sm_count,
+                     cudaStream_t s) {
+    if (n <= 0) return 0;
+    mark_rows_kernel<<<stream_grid(n / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(dead, n_rows, pos, n, base);
+    return 1;
+}
+int launch_compact_rows(const int32_t *col, const uint32_t *dead, const uint32_t *dead_before, int64_t n_rows,
+                        int32_t *out, int sm_count, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    compact_rows_kernel<<<stream_grid(n_rows / 4 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(col, dead, dead_before,
+                                                                                          n_rows, out);
+    return 1;
+}
+
 int launch_narrow_u64(const unsigned long long *src, int64_t n, int32_t *dst, int sm_count, cudaStream_t s) {
     if (n <= 0) return 0;
     narrow_u64_kernel<<<stream_grid(n / 2 + 1, sm_count, 8), STREAM_THREADS, 0, s>>>(src, n, dst);
@@ -338,6 +390,9 @@ int launch_synth_uniform(int32_t *out, int64_t n, uint64_t seed, uint64_t first_
 // Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
 // has to load code while another context's kernel spin-waits for this one can stall behind it.
 void preload_gather_agg() {
+    preload_one(reinterpret_cast<const void *>(&scatter_value_kernel));
+    preload_one(reinterpret_cast<const void *>(&mark_rows_kernel));
+    preload_one(reinterpret_cast<const void *>(&compact_rows_kernel));
     preload_one(reinterpret_cast<const void *>(&aggregate_kernel));
     { auto *fp = &ewise_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &ewise_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }

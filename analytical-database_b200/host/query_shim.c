@@ -1536,6 +1536,182 @@ static int alloc_shards(Shards *sh) {
     return 0;
 }
 
+/* ---- updates and deletes ------------------------------------------------
+ * relational_update(col, positions, value) and relational_delete(tbl, positions) of milestone 5
+ * (project_tests/data_generation_scripts/milestone5.py:123-262).  The reference's parser has no
+ * branch for them (src/parse.c:876-960) and query.c no function, so these are hooks a parser
+ * branch would call; the semantics are the generator's pandas model.  The host arrays
+ * (Column.data, the catalog's truth: they are what shutdown persists) are brought up to date
+ * from the device after every change.  Handles created before the change keep their values
+ * (unwritten ones are written first).  Indexes: an unclustered index of a changed column (update)
+ * or of any column of the table (delete) is rebuilt on the engine; a table with a CLUSTERED index
+ * is refused -- the reference's clustered layout has no defined update semantics. */
+typedef struct UpdateJob {
+    ShardErr err;
+    DevColumn *c;
+    int32_t *pos[MAXG];             /* the positions this context applies */
+    size_t n[MAXG];
+    int value;
+    int *host;
+} UpdateJob;
+static void update_shard(int g, void *arg) {
+    UpdateJob *a = arg;
+    DevColumn *c = a->c;
+    const size_t rows = shard_len(c->rows, c->shard_rows, g);
+    if (!rows) return;
+    SCK(adb_update_rows(c->d_data[g], (int64_t)rows, a->pos[g], (int64_t)a->n[g], shard_base(g, c->shard_rows), a->value));
+    SCK(adb_download(a->host + (size_t)g * c->shard_rows, c->d_data[g], 4 * rows));
+}
+
+static int table_has_clustered(Column **cols, int n_cols) {
+    for (int j = 0; j < n_cols; ++j)
+        if (cols[j] && cols[j]->clustered) return 1;
+    return 0;
+}
+static int rebuild_index(Column **cols, int n_cols, int j) {
+    Column *col = cols[j];
+    if (col->index) {                       /* plain mallocs of init_column_index / adb_host_index_build */
+        free(col->index->values);
+        free(col->index->positions);
+        free(col->index);
+        col->index = NULL;
+    }
+    return adb_host_index_build(cols, n_cols, j);
+}
+
+int adb_host_relational_update(Column **cols, int n_cols, int which, Result *positions, int value) {
+    t_err[0] = '\0';
+    if (ensure_up()) return -1;
+    if (!cols || which < 0 || which >= n_cols || !cols[which] || !positions) {
+        set_err("relational_update: bad arguments");
+        return -1;
+    }
+    if (table_has_clustered(cols, n_cols)) {
+        set_err("relational_update: the table has a clustered index (no defined update semantics, SURVEY.md A2)");
+        return -1;
+    }
+    Column *column = cols[which];
+    Staged p;
+    memset(&p, 0, sizeof p);
+    int32_t *all[MAXG] = {0};
+    int rc = -1;
+    DevColumn *c = dev_column(column);
+    if (!c || c->adopted || !column->data) {
+        if (c) set_err("relational_update: column '%s' has no host array to keep up to date", column->name);
+        return -1;
+    }
+    if (stage(positions, NULL, &p)) return -1;
+    c = dev_column_slot(column);
+    if (P.active || nR) lazy_column_gone(c->d_data);        /* handles that still have to read the old values */
+    UpdateJob job;
+    memset(&job, 0, sizeof job);
+    job.c = c;
+    job.value = value;
+    job.host = column->data;
+    if (S.G == 1 || (p.aligned && p.aligned == c->shard_rows)) {
+        for (int g = 0; g < S.G; ++g) {
+            job.pos[g] = p.d[g];
+            job.n[g] = p.n[g];
+        }
+    } else {
+        /* positions anywhere: every GPU gets the whole list and applies the rows it owns */
+        size_t allto[MAXG];
+        for (int g = 0; g < S.G; ++g) {
+            memset(allto, 0, sizeof allto);
+            allto[g] = p.total;
+            int32_t *tmp[MAXG] = {0};
+            if (recut(p.d, p.n, allto, tmp)) {
+                for (int k = 0; k < S.G; ++k) free_on(k, tmp[k]);
+                goto done;
+            }
+            all[g] = tmp[g];
+            for (int k = 0; k < S.G; ++k)
+                if (k != g) free_on(k, tmp[k]);
+            job.pos[g] = all[g];
+            job.n[g] = p.total;
+        }
+    }
+    run_shards(update_shard, &job);
+    if (shard_errs(&job.err)) goto done;
+    if (value < column->min) column->min = value;           /* insert_row keeps these (db_manager.c:193-194) */
+    if (value > column->max) column->max = value;
+    rc = 0;
+    if (column->has_index) rc = rebuild_index(cols, n_cols, which);
+done:
+    for (int g = 0; g < S.G; ++g) free_on(g, all[g]);
+    unstage(&p);
+    return rc;
+}
+
+int adb_host_relational_delete(Column **cols, int n_cols, Result *positions) {
+    t_err[0] = '\0';
+    if (ensure_up()) return -1;
+    if (!cols || n_cols < 1 || !positions) {
+        set_err("relational_delete: bad arguments");
+        return -1;
+    }
+    if (table_has_clustered(cols, n_cols)) {
+        set_err("relational_delete: the table has a clustered index (no defined delete semantics, SURVEY.md A2)");
+        return -1;
+    }
+    const size_t rows = cols[0] ? cols[0]->row_count : 0;
+    for (int j = 0; j < n_cols; ++j)
+        if (!cols[j] || cols[j]->row_count != rows || !cols[j]->data) {
+            set_err("relational_delete: the table's columns must be host-backed and equally long");
+            return -1;
+        }
+    Staged p;
+    memset(&p, 0, sizeof p);
+    size_t all0[MAXG] = {0};
+    all0[0] = positions->num_tuples;
+    if (stage(positions, all0, &p)) return -1;              /* the whole list on GPU 0 (a global compaction) */
+    int rc = -1;
+    int64_t left = -1;
+    void *gathered = NULL, *out = NULL;
+    if (adb_delete_rows_plan((int64_t)rows, p.d[0], (int64_t)p.total, 0, &left) != ADB_OK) {
+        set_err("relational_delete: %s", adb_last_error());
+        goto done;
+    }
+    if (adb_alloc(&out, 4 * (size_t)(left > 0 ? left : 1)) != ADB_OK ||
+        (S.G > 1 && adb_alloc(&gathered, 4 * (rows ? rows : 1)) != ADB_OK)) {
+        set_err("relational_delete: %s", adb_last_error());
+        goto done;
+    }
+    for (int j = 0; j < n_cols; ++j) {
+        DevColumn *c = dev_column(cols[j]);
+        if (!c) goto done;
+        if (P.active || nR) lazy_column_gone(c->d_data);    /* handles that still have to read the old rows */
+        const int32_t *src = c->d_data[0];
+        if (S.G > 1) {
+            for (int g = 0; g < S.G; ++g) {
+                const size_t len = shard_len(c->rows, c->shard_rows, g);
+                if (len && adb_copy_from_ctx((int32_t *)gathered + (size_t)g * c->shard_rows, g, c->d_data[g], 4 * len) != ADB_OK) {
+                    set_err("relational_delete: %s", adb_last_error());
+                    goto done;
+                }
+            }
+            src = gathered;
+        }
+        if (adb_delete_rows_apply(src, out) != ADB_OK ||
+            (left > 0 && adb_download(cols[j]->data, out, 4 * (size_t)left) != ADB_OK)) {
+            set_err("relational_delete: %s", adb_last_error());
+            goto done;
+        }
+    }
+    for (int j = 0; j < n_cols; ++j) {
+        adb_host_column_invalidate(cols[j]);                /* re-sharded at the next touch */
+        cols[j]->row_count = (size_t)left;
+    }
+    rc = 0;
+    for (int j = 0; j < n_cols && rc == 0; ++j)
+        if (cols[j]->has_index) rc = rebuild_index(cols, n_cols, j);
+done:
+    if (out) adb_free(out);
+    if (gathered) adb_free(gathered);
+    unstage(&p);
+    return rc;
+}
+
 /* ---- selects ------------------------------------------------------------------------------ */
 /* src/index.c:180-185: the cost model is the constant `true` (the drop-in links
  * host/index_shim.c in place of index.c, so the definition lives here in both builds). */

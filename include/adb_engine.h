@@ -394,6 +394,24 @@ ADB_API adb_status adb_iota_i32(int32_t *d_out, int64_t n, int32_t first);
 ADB_API adb_status adb_histogram_i32(const int32_t *d_val, int64_t n, int32_t vmin, int32_t bin_size,
                                      uint64_t *h_counts);
 
+/* ---- updates and deletes -- relational_update / relational_delete of
+ * milestone 5 (project_tests/data_generation_scripts/milestone5.py:123-262: `UPDATE tbl SET col =
+ * v WHERE ...` as u=select(...); relational_update(col, u, v), `DELETE FROM tbl WHERE ...` as
+ * d=select(...); relational_delete(tbl, d)).  The reference's parser has no branch for either
+ * (src/parse.c:876-960), so these have no reference function to replace; the semantics are the
+ * generator's pandas model: an update overwrites col[pos] for every listed position, a delete
+ * removes the listed rows from every column of the table, survivors keep their order.
+ *   adb_update_rows        d_col[d_pos[i] - base_pos] = value for the positions that fall into
+ *                          [base_pos, base_pos + n_rows) (a shard ignores the other shards' rows)
+ *   adb_delete_rows_plan   marks the rows of d_pos (duplicates allowed) among n_rows rows and
+ *                          computes where the survivors move; *h_rows_left = rows left
+ *   adb_delete_rows_apply  compacts one column with the plan (d_col_out != d_col, >= rows left) */
+ADB_API adb_status adb_update_rows(int32_t *d_col, int64_t n_rows, const int32_t *d_pos, int64_t n_pos,
+                                   int32_t base_pos, int32_t value);
+ADB_API adb_status adb_delete_rows_plan(int64_t n_rows, const int32_t *d_pos, int64_t n_pos, int32_t base_pos,
+                                        int64_t *h_rows_left);
+ADB_API adb_status adb_delete_rows_apply(const int32_t *d_col, int32_t *d_col_out);
+
 /* ---- joins -- replace hash_join + multimap (src/query.c:652-696, src/multimap.c) and
  * nested_loop_join (src/query.c:585-650).  Inputs are two (value, position) pair lists;
  * outputs two aligned position lists.  Order is the reference's: hash join probe-major

@@ -165,6 +165,14 @@ void adb_host_column_invalidate(Column *column);  /* after insert_row, src/serve
  * ascending row order (stable radix sort; the reference's quicksort leaves another order,
  * SURVEY.md A3 -- identical for unique keys).  host/index_shim.c builds build_index(Db*) on it. */
 int adb_host_index_build(Column **cols, int n_cols, int which);
+/* Updates and deletes of milestone 5: what a parser branch for
+ * `relational_update(db.tbl.col, positions, value)` / `relational_delete(db.tbl, positions)` would
+ * call (the reference's parser has none, src/parse.c:876-960; semantics =
+ * project_tests/data_generation_scripts/milestone5.py:123-262).  cols[0 .. n_cols) are the table's
+ * columns; the host arrays (Column.data, row_count) are brought up to date, unclustered indexes
+ * rebuilt on the engine; a table with a clustered index is refused.  0 on success. */
+int adb_host_relational_update(Column **cols, int n_cols, int which, Result *positions, int value);
+int adb_host_relational_delete(Column **cols, int n_cols, Result *positions);
 /* build_histogram's counts (src/index.c:63-84) computed on the device */
 int adb_host_column_histogram(Column *column, int bin_size, unsigned long counts[100]);
 /* Device-resident results: Result.payload of a position list / value vector is a small

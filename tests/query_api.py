@@ -77,6 +77,8 @@ HOOKS = {
     "adb_host_column_adopt": (C.c_int, [C.POINTER(Column), C.c_void_p]),
     "adb_host_column_invalidate": (None, [C.POINTER(Column)]),
     "adb_host_index_build": (C.c_int, [C.POINTER(C.POINTER(Column)), C.c_int, C.c_int]),
+    "adb_host_relational_update": (C.c_int, [C.POINTER(C.POINTER(Column)), C.c_int, C.c_int, RP, C.c_int]),
+    "adb_host_relational_delete": (C.c_int, [C.POINTER(C.POINTER(Column)), C.c_int, RP]),
     "adb_host_column_histogram": (C.c_int, [C.POINTER(Column), C.c_int, C.POINTER(C.c_ulong)]),
     "adb_host_result_release": (None, [RP]),
     "adb_host_payload_freed": (None, [C.c_void_p]),
