@@ -766,6 +766,30 @@ adb_status adb_download(void *h_dst, const void *d_src, size_t bytes) {
     adb_status s = adb_download_async(h_dst, d_src, bytes);
     return s ? s : adb_sync();
 }
+// Page-lock a host range the caller keeps uploading from (a loaded column is an mmap that
+// insert_row appends to, src/db_manager.c:164-199: every insert invalidates the HBM copy): from
+// registered memory adb_upload is one DMA at the link's rate instead of the staged copy through
+// pinned lanes.  Portable: every context's device sees it pinned.  Registration itself is slow
+// (it touches and locks every page), so it only pays for memory that is uploaded repeatedly.
+adb_status adb_host_register(void *h_ptr, size_t bytes) {
+    NEED_UP();
+    if (!h_ptr || !bytes) return fail(ADB_ERR_INVALID, "adb_host_register: empty range");
+    cudaError_t e = cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return ADB_OK; }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ADB_ERR_CUDA, "adb_host_register(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return ADB_OK;
+}
+adb_status adb_host_unregister(void *h_ptr) {
+    NEED_UP();
+    if (!h_ptr) return ADB_OK;
+    cudaError_t e = cudaHostUnregister(h_ptr);
+    if (e != cudaSuccess) cudaGetLastError();       // (not registered: nothing to undo)
+    return ADB_OK;
+}
+
 adb_status adb_memset(void *d_dst, int byte, size_t bytes) {
     NEED_UP();
     if (bytes) CU(cudaMemsetAsync(d_dst, byte, bytes, g.stream));

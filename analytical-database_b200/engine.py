@@ -112,6 +112,8 @@ class Engine:
         "adb_set_stream": (C.c_int32, [C.c_void_p]),
         "adb_host_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
         "adb_host_free": (C.c_int32, [C.c_void_p]),
+        "adb_host_register": (C.c_int32, [C.c_void_p, C.c_size_t]),
+        "adb_host_unregister": (C.c_int32, [C.c_void_p]),
         "adb_timer_start": (C.c_int32, []),
         "adb_timer_stop": (C.c_int32, [C.POINTER(C.c_float)]),
         "adb_launch_count": (C.c_int64, []),

@@ -71,6 +71,7 @@
 #include "adb_query_api.h"
 
 #define MAXG ADB_MAX_PEERS
+#define REGISTER_MIN_BYTES ((size_t)64 << 20)
 
 /* ---- state ----------------------------------------------------------------------------- */
 typedef struct DevColumn {
@@ -80,6 +81,9 @@ typedef struct DevColumn {
     size_t shard_rows;          /* S: shard g = rows [g*S, min(rows, (g+1)*S)) */
     int32_t *d_data[MAXG];
     int adopted;                /* d_data belongs to the caller (adb_host_column_adopt*) */
+    const int *uploaded_from;   /* host array of the last upload, and how often it was uploaded: */
+    size_t uploaded_bytes;      /* a large array uploaded a second time is page-locked (insert_row */
+    int uploads, registered;    /* invalidates the HBM copy again and again, db_manager.c:164-199)  */
     /* index: slice g = entries [ix_begin[g], ix_begin[g+1]) of the sorted arrays */
     const int *host_ix_values;
     size_t ix_rows;
@@ -110,6 +114,7 @@ typedef struct DevResult {
 static struct {
     int up, failed, mirror, lazy;
     int G;                      /* contexts = shards */
+    int register_uploads;       /* page-lock host columns that are uploaded repeatedly (ADB_SHIM_NO_REGISTER=1: never) */
     size_t shard_min_rows;
     size_t rebalance_min;       /* index-ordered lists at least this long are re-cut evenly (ADB_REBALANCE_MIN) */
     DevColumn *cols;
@@ -594,6 +599,8 @@ static int host_init(int first_device, int gpus) {
     const char *mn = getenv("ADB_SHARD_MIN_ROWS");
     S.shard_min_rows = mn ? (size_t)atol(mn) : 32;
     if (S.shard_min_rows < 1) S.shard_min_rows = 1;
+    const char *nr = getenv("ADB_SHIM_NO_REGISTER");
+    S.register_uploads = !(nr && nr[0] && nr[0] != '0');
     const char *rb = getenv("ADB_REBALANCE_MIN");
     S.rebalance_min = rb ? (size_t)atol(rb) : ((size_t)1 << 20);   /* shorter lists: the re-cut costs more than it saves */
     if (workers_start()) return -1;
@@ -648,8 +655,23 @@ static void dev_column_drop(DevColumn *c) {
     if (!c->adopted)
         for (int g = 0; g < S.G; ++g) free_on(g, c->d_data[g]);
     const Column *key = c->key;
+    const int *from = c->uploaded_from;             /* the upload history survives an invalidation */
+    const size_t fbytes = c->uploaded_bytes;
+    const int uploads = c->uploads, registered = c->registered;
     memset(c, 0, sizeof *c);
     c->key = key;
+    c->uploaded_from = from;
+    c->uploaded_bytes = fbytes;
+    c->uploads = uploads;
+    c->registered = registered;
+}
+
+static void column_unregister(DevColumn *c) {
+    if (c->registered) adb_host_unregister((void *)c->uploaded_from);
+    c->registered = 0;
+    c->uploads = 0;
+    c->uploaded_from = NULL;
+    c->uploaded_bytes = 0;
 }
 
 static void result_buffers_free(DevResult *r) {
@@ -681,7 +703,10 @@ void adb_host_shutdown(void) {
     S.slots = NULL;
     S.nslots = S.nused = 0;
     S.nlive = 0;
-    for (int i = 0; i < S.ncols; ++i) dev_column_drop(&S.cols[i]);
+    for (int i = 0; i < S.ncols; ++i) {
+        dev_column_drop(&S.cols[i]);
+        column_unregister(&S.cols[i]);
+    }
     DevColumn *oldc = S.cols;
     S.cols = NULL;
     S.ncols = S.capcols = 0;
@@ -763,6 +788,15 @@ static DevColumn *dev_column(Column *column) {
     dev_column_drop(c);
     c->rows = column->row_count;
     c->shard_rows = shard_rows_for(c->rows);
+    /* the same large array again (the column was invalidated, not re-mapped): page-lock it once,
+     * this and every later upload is then a single DMA per GPU at the link's rate */
+    if (c->uploaded_from != column->data || c->uploaded_bytes != 4 * column->row_count) {
+        column_unregister(c);
+        c->uploaded_from = column->data;
+        c->uploaded_bytes = 4 * column->row_count;
+    }
+    if (++c->uploads == 2 && !c->registered && c->uploaded_bytes >= REGISTER_MIN_BYTES && S.register_uploads)
+        c->registered = adb_host_register((void *)column->data, c->uploaded_bytes) == ADB_OK;
     UploadJob job;
     memset(&job, 0, sizeof job);
     job.c = c;
@@ -1199,6 +1233,13 @@ static int registry_take(const void *payload, DevResult *out) {
 
 void adb_host_payload_freed(void *payload) {
     if (S.nlive <= 0 || !payload) return;
+    /* With the free() interposer every free() of the process lands here, from any thread (the
+     * CUDA runtime's included): only an address the registry knows goes any further -- the lazy
+     * records below are the calling plumbing's (single-threaded) state. */
+    lock();
+    const int known = registry_find(payload) != NULL;
+    unlock();
+    if (!known) return;
     PF_BEGIN(PF_RELEASE);
     const int keep = pending_payload_gone(payload);
     DevResult dead;

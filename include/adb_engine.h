@@ -95,6 +95,10 @@ ADB_API void *adb_stream(void);                       /* the cudaStream_t operat
 ADB_API adb_status adb_set_stream(void *cuda_stream); /* adopt a caller's stream (NULL = legacy default) */
 ADB_API adb_status adb_host_alloc(void **h_ptr, size_t bytes);       /* pinned host memory */
 ADB_API adb_status adb_host_free(void *h_ptr);
+/* page-lock / unlock a host range that is uploaded from repeatedly (then adb_upload is one DMA at
+ * the link's rate instead of a staged copy); failures of the unlock are ignored */
+ADB_API adb_status adb_host_register(void *h_ptr, size_t bytes);
+ADB_API adb_status adb_host_unregister(void *h_ptr);
 /* CUDA-event stopwatch on the engine stream: start, run operators, stop -> milliseconds. */
 ADB_API adb_status adb_timer_start(void);
 ADB_API adb_status adb_timer_stop(float *ms);
