@@ -77,3 +77,34 @@ def test_patched_pair_prints_what_the_reference_pair_prints():
             finally:
                 pair.stop()
     assert outs["chunked"] == outs["ref"] and len(outs["ref"]) > 5000
+
+
+@pytest.mark.skipif(not os.environ.get("ADB_TEST_BIG_PRINT"), reason="set ADB_TEST_BIG_PRINT=1: 50 M rows, ~1 GB of text, minutes")
+def test_fifty_million_row_print_travels_end_to_end():
+    """a 50 M-row print through the patched reply path (550 MB of text in one
+    reply, formatted on the device, sent and received in pieces).  Slow (the reference's load_db
+    parses 50 M CSV lines with atoi, and the client's output is captured), so opt-in; the result of
+    the round's run is recorded in profiles/r02_print_50M.md."""
+    import time
+    rows = 50_000_000
+    rng = np.random.default_rng(50)
+    c1 = rng.integers(-2**31, 2**31 - 1, rows, dtype=np.int64).astype(np.int32)
+    with tempfile.TemporaryDirectory(prefix="adb_chunked_big_") as w:
+        csv = os.path.join(w, "t.csv")
+        with open(csv, "w") as f:
+            f.write("db1.tbl1.col1\n")
+            for b in range(0, rows, 1 << 22):
+                f.write("\n".join(map(str, c1[b:b + (1 << 22)].tolist())) + "\n")
+        pair = H.ServerPair("chunked", w)
+        try:
+            t0 = time.time()
+            pair.run_dsl(script(csv, 1, []), timeout=1800)
+            t_load = time.time() - t0
+            t0 = time.time()
+            out = pair.run_dsl("s1=select(db1.tbl1.col1,null,null)\nf1=fetch(db1.tbl1.col1,s1)\nprint(f1)\n", timeout=1800)
+            t_print = time.time() - t0
+        finally:
+            pair.stop()
+    got = np.fromstring(out, sep="\n", dtype=np.int64)
+    assert got.size == rows and np.array_equal(got.astype(np.int32), c1)
+    print(f"50M-row print: load {t_load:.1f} s, select+fetch+print round trip {t_print:.1f} s, reply {len(out)} bytes")
