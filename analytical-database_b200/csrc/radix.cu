@@ -22,21 +22,44 @@ constexpr int RX_THREADS = 256;
 constexpr int RX_WARPS = RX_THREADS / kWarp;
 constexpr int RX_BUCKETS = 256;
 
-__device__ __forceinline__ uint32_t rx_digit(uint32_t key, const RadixPass &p) {
-    const uint32_t f = p.hash == 1 ? key * 0x9E3779B1u : p.hash == 2 ? key * 0x85EBCA6Bu : key ^ 0x80000000u;
-    return (f >> p.shift) & ((1u << p.bits) - 1u);
-}
+// f(key) of RadixPass::hash; the digit is (f >> shift) & mask.  For the signed order (HASH 0)
+// the sign flip is folded into one constant xor-ed onto the extracted digit.
+template <int HASH>
+struct RxDigit {
+    uint32_t shift, mask, flip;
+    __host__ __device__ explicit RxDigit(const RadixPass &p)
+        : shift((uint32_t)p.shift), mask((1u << p.bits) - 1u),
+          flip(HASH == 0 ? ((0x80000000u >> p.shift) & ((1u << p.bits) - 1u)) : 0u) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t key) const {
+        if (HASH == 1) return ((key * 0x9E3779B1u) >> shift) & mask;
+        if (HASH == 2) return ((key * 0x85EBCA6Bu) >> shift) & mask;
+        return ((key >> shift) & mask) ^ flip;
+    }
+};
 
+template <int HASH>
 __global__ void __launch_bounds__(RX_THREADS)
 rx_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t rows_per_cta, RadixPass p,
                uint32_t *__restrict__ hist /* [bucket][gridDim.x] */) {
     __shared__ uint32_t s_h[RX_BUCKETS];
+    const RxDigit<HASH> digit(p);
     s_h[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t begin = blockIdx.x * rows_per_cta;
     const uint32_t end = min(n, begin + rows_per_cta);
-    for (uint32_t i = begin + threadIdx.x; i < end; i += RX_THREADS)
-        atomicAdd(&s_h[rx_digit(keys[i], p)], 1u);
+    if (end - begin == rows_per_cta && (reinterpret_cast<uintptr_t>(keys) & 15) == 0 && (rows_per_cta & 3) == 0) {
+        const int4 *k4 = reinterpret_cast<const int4 *>(keys + begin);
+        for (uint32_t i = threadIdx.x; i < rows_per_cta / 4; i += RX_THREADS) {
+            const int4 k = ld_stream(k4 + i);
+            atomicAdd(&s_h[digit((uint32_t)k.x)], 1u);
+            atomicAdd(&s_h[digit((uint32_t)k.y)], 1u);
+            atomicAdd(&s_h[digit((uint32_t)k.z)], 1u);
+            atomicAdd(&s_h[digit((uint32_t)k.w)], 1u);
+        }
+    } else {
+        for (uint32_t i = begin + threadIdx.x; i < end; i += RX_THREADS)
+            atomicAdd(&s_h[digit(keys[i])], 1u);
+    }
     __syncthreads();
     hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
 }
@@ -77,134 +100,204 @@ __global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals, uint3
     base[threadIdx.x] = wexcl + incl - x;
 }
 
-// Stable scatter, one 4096-row tile at a time.  Warp w of the CTA owns the contiguous rows
-// tile + w*512 .. +512 (row = ... + i*32 + lane), so ranking its keys round by round with
-// match_any gives every key its rank among the warp's equal digits in row order.  Per-digit
-// prefixes over the eight warps and over the 256 digits turn that into a slot in the
-// tile-sorted order; keys and payloads are parked there in shared memory and written out
-// slot by slot, so each digit's run leaves as one contiguous (coalesced) piece instead of
-// thirty-two 4-byte scatters per warp.
-constexpr int RX_KPT = 16;
-constexpr int RX_TILE = RX_THREADS * RX_KPT;             // 4096 rows
-
+// Stable scatter, one 4096-row tile per CTA.  Warp w owns the contiguous rows
+// tile + w*512 .. +512 (row = ... + i*32 + lane), so ranking its keys round by round gives
+// every key its rank among the warp's equal digits in row order.  Per-digit prefixes over the
+// eight warps and over the 256 digits turn that into a slot in the tile-sorted order; {key,
+// payload} pairs are parked there in shared memory and written out slot by slot, so each
+// digit's run leaves as one contiguous (coalesced) piece instead of thirty-two 4-byte scatters
+// per warp.
+//
+// r02t (ncu, 200 M pairs, profiles/r02t_radix_summary.md): the first version of this kernel
+// spent 159 warp instructions per 32 keys at 43 % issue utilisation and 37 % occupancy -- a
+// run-time loop over the digit's bits around each ballot (9 instructions per bit), the digit
+// recomputed with a run-time hash selector, the payload loaded after the ranking (38 % of the
+// stall samples).  This version: hash, digit width and tile fullness are template parameters
+// (4 instructions per bit, unrolled), the peer masks of all sixteen rounds are computed before
+// the dependent counter chain, the payload tile travels global -> shared with cp.async while the
+// ranking runs, pairs move through shared memory as 8-byte words, counters are 16-bit:
+// 56 KB of shared memory and <= 64 registers = 4 CTAs per SM.
+//
 // (r01k tried finding the peers through a per-warp shared-memory table -- atomicOr of the
 // lane bit, sync, read back, leader clears -- instead of one ballot per digit bit: 20.4 ms
-// against 19.6 ms for the 500 M-key sort, so the ballots stayed.)
+// against 19.6 ms for the 500 M-key sort, so the ballots stayed.  MATCH.ANY: r01f, XU pipe bound.)
 // REMOTE: bucket d is a destination rank and is written into that rank's receive buffer over
 // NVLink (peer_base[d] + key_off / pay_off) instead of one local output array; `base` then
 // holds the offset of this rank's piece inside every destination buffer.  The run-contiguous
 // write-out is what makes the remote stores full 128-byte transactions.
-template <bool REMOTE>
-__global__ void __launch_bounds__(RX_THREADS)
-rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
-                  uint32_t rows_per_cta, RadixPass p, const uint32_t *__restrict__ hist,
-                  const uint32_t *__restrict__ base, uint32_t *__restrict__ keys_out,
-                  uint32_t *__restrict__ pay_out, uint32_t *const *__restrict__ peer_base,
-                  unsigned long long key_off, unsigned long long pay_off,
-                  const uint32_t *__restrict__ abort_flag) {
-    __shared__ uint32_t s_key[RX_TILE];
-    __shared__ uint32_t s_pay[RX_TILE];
-    __shared__ uint32_t s_wcnt[RX_WARPS][RX_BUCKETS];      // per-warp digit counts -> prefix over warps
-    __shared__ uint32_t s_off[RX_BUCKETS];                 // next free global slot of every digit
-    __shared__ uint32_t s_tbase[RX_BUCKETS];               // first tile slot of every digit
-    __shared__ uint32_t s_gofs[RX_BUCKETS];                // global address = s_gofs[d] + tile slot
-    __shared__ uint32_t s_ws[RX_WARPS];
-    __shared__ uint32_t *s_peer[REMOTE ? kMaxPeers : 1];
+constexpr int RX_KPT = 16;
+constexpr int RX_TILE = RX_THREADS * RX_KPT;             // 4096 rows
+
+struct RxShared {
+    uint2 kv[RX_TILE];                                   // tile-sorted {key, payload}
+    uint32_t pay_in[RX_TILE];                            // the tile's payloads in row order (cp.async)
+    uint16_t wcnt[RX_WARPS][RX_BUCKETS];                 // per-warp digit counts -> first slot of (warp, digit)
+    uint32_t gofs[RX_BUCKETS];                           // global address = gofs[d] + tile slot
+    uint32_t ws[RX_WARPS];
+    uint32_t *peer[kMaxPeers];
+};
+
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// peers &= lanes whose digit agrees with mine in the bit `bitmask`.  Spelled out in PTX: from
+// the C form nvcc derives two predicates per bit (bit != 0 for the select, bit != 1 for the
+// vote) through a shift, an and and a compare -- six instructions where four do.
+__device__ __forceinline__ uint32_t rx_match_bit(uint32_t peers, uint32_t d, uint32_t bitmask) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, v;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+        "selp.b32 t, 0, 0xffffffff, p;\n\t"
+        "lop3.b32 %0, %0, v, t, 0x60;\n\t"
+        "}"
+        : "+r"(peers) : "r"(d), "r"(bitmask));
+    return peers;
+}
+
+template <int HASH, int BITS, bool REMOTE, bool FULL>
+__device__ __forceinline__ void rx_scatter_tile(RxShared &sh, const uint32_t *__restrict__ keys,
+                                                const uint32_t *__restrict__ pay, uint32_t tile, uint32_t end,
+                                                const RadixPass &p, uint32_t my_off, uint32_t *__restrict__ keys_out,
+                                                uint32_t *__restrict__ pay_out, unsigned long long key_off,
+                                                unsigned long long pay_off) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (REMOTE) {
-        if (*abort_flag) return;                            // a receive region would overflow
-        if (threadIdx.x < (1u << p.bits)) s_peer[threadIdx.x] = peer_base[threadIdx.x];
-    }
-    s_off[threadIdx.x] = base[threadIdx.x] + hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
-    const uint32_t begin = blockIdx.x * rows_per_cta;
-    const uint32_t end = min(n, begin + rows_per_cta);
+    const RxDigit<HASH> digit(p);
     const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t tile = begin; tile < end; tile += RX_TILE) {
+    const uint32_t wofs = warp * (kWarp * RX_KPT) + lane;  // row in tile of this lane's round-0 key
+    const uint32_t wrow = tile + wofs;
+    // the payload tile goes straight to shared memory while the keys are ranked
+    if (pay) {
+        if (FULL && (reinterpret_cast<uintptr_t>(pay) & 15) == 0) {
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; ++w) s_wcnt[w][threadIdx.x] = 0;
-        __syncthreads();
-        uint32_t key[RX_KPT];
-        uint32_t dr[RX_KPT];                               // digit | rank-in-warp << 8, ~0 = past the end
-        const uint32_t wrow = tile + warp * (kWarp * RX_KPT) + lane;
-        uint32_t *cnt = s_wcnt[warp];
-        // all sixteen loads are issued before the first rank round needs a key
+            for (int i = 0; i < RX_KPT / 4; ++i) {
+                const uint32_t q = (i * RX_THREADS + threadIdx.x) * 4;
+                cp_async_16(&sh.pay_in[q], pay + tile + q);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < RX_KPT; ++i) {
-            const uint32_t row = wrow + i * kWarp;
-            key[i] = row < end ? ld_stream(reinterpret_cast<const int32_t *>(keys) + row) : 0u;
+            for (int i = 0; i < RX_KPT; ++i)
+                if (FULL || wrow + i * kWarp < end) cp_async_4(&sh.pay_in[wofs + i * kWarp], pay + wrow + i * kWarp);
         }
+    }
+    uint32_t key[RX_KPT];
 #pragma unroll
-        for (int i = 0; i < RX_KPT; ++i) {
-            const uint32_t row = wrow + i * kWarp;
-            const bool live = row < end;
-            dr[i] = 0xFFFFFFFFu;
-            const uint32_t active = __ballot_sync(kFull, live);
-            uint32_t d = 0, peers = 0, before = 0;
-            if (live) d = rx_digit(key[i], p);
-            // lanes holding the same digit, one ballot per digit bit: MATCH.ANY runs on the
-            // XU pipe and saturated it at 16 rounds per tile (ncu r01f: xu 177 % of peak)
-            peers = active;
+    for (int i = 0; i < RX_KPT; ++i)
+        key[i] = (FULL || wrow + i * kWarp < end)
+                     ? (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(keys) + wrow + i * kWarp) : 0u;
+    {   // zero the per-warp counters: 4 KB = one 16-byte store per thread
+        reinterpret_cast<uint4 *>(&sh.wcnt[0][0])[threadIdx.x] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // 1a. lanes holding the same digit, one ballot per digit bit (MATCH.ANY runs on the XU pipe
+    //     and saturated it, ncu r01f).  dr = digit | rank among the round's equal digits << 8 |
+    //     size of that group << 16; 0xFFFFFFFF = past the end.
+    uint32_t dr[RX_KPT];
+#pragma unroll
+    for (int i = 0; i < RX_KPT; ++i) {
+        const bool live = FULL || wrow + i * kWarp < end;
+        const uint32_t d = digit(key[i]);
+        uint32_t peers = FULL ? kFull : __ballot_sync(kFull, live);
+        if (BITS > 0) {
+#pragma unroll
+            for (int b = 0; b < BITS; ++b) peers = rx_match_bit(peers, d, 1u << b);
+        } else {
             for (int b = 0; b < p.bits; ++b) {
-                const bool bit = (d >> b) & 1u;
+                const bool bit = (d & (1u << b)) != 0u;
                 const uint32_t vote = __ballot_sync(kFull, bit);
                 peers &= bit ? vote : ~vote;
             }
-            if (live) before = cnt[d];
-            __syncwarp();
-            if (live) {
-                const uint32_t r = __popc(peers & lt);
-                if (r == 0) cnt[d] = before + __popc(peers);
-                dr[i] = d | ((before + r) << 8);
-            }
-            __syncwarp();
         }
-        __syncthreads();
-        // digit `threadIdx.x`: exclusive prefix over the warps, then over the digits
-        uint32_t tot = 0;
+        dr[i] = live ? (d | ((uint32_t)__popc(peers & lt) << 8) | ((uint32_t)__popc(peers) << 16)) : 0xFFFFFFFFu;
+    }
+    // 1b. the dependent part: the warp's running count of every digit
+    uint16_t *cnt = sh.wcnt[warp];
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; ++w) {
-            const uint32_t c = s_wcnt[w][threadIdx.x];
-            s_wcnt[w][threadIdx.x] = tot;
-            tot += c;
-        }
+    for (int i = 0; i < RX_KPT; ++i) {
+        const bool live = FULL || dr[i] != 0xFFFFFFFFu;
+        const uint32_t d = dr[i] & 0xFFu, r = (dr[i] >> 8) & 0xFFu;
+        uint32_t before = 0;
+        if (live) before = cnt[d];
+        __syncwarp();
+        if (live && r == 0) cnt[d] = (uint16_t)(before + (dr[i] >> 16));
+        __syncwarp();
+        if (live) dr[i] = d | ((before + r) << 8);
+    }
+    __syncthreads();
+    // 2. digit `threadIdx.x`: exclusive prefix over the warps, then over the digits
+    {
+        uint32_t c[RX_WARPS], tot = 0;
+#pragma unroll
+        for (int w = 0; w < RX_WARPS; ++w) { c[w] = sh.wcnt[w][threadIdx.x]; tot += c[w]; }
         const uint32_t incl = warp_incl_scan(tot, lane);
-        if (lane == 31) s_ws[warp] = incl;
+        if (lane == 31) sh.ws[warp] = incl;
         __syncthreads();
         uint32_t wexcl = 0;
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; ++w) wexcl += (uint32_t)w < warp ? s_ws[w] : 0u;
-        const uint32_t tbase = wexcl + incl - tot;
-        s_tbase[threadIdx.x] = tbase;
-        s_gofs[threadIdx.x] = s_off[threadIdx.x] - tbase;   // modular: slot >= tbase for this digit
-        s_off[threadIdx.x] += tot;
-        __syncthreads();
+        for (int w = 0; w < RX_WARPS; ++w) wexcl += (uint32_t)w < warp ? sh.ws[w] : 0u;
+        const uint32_t tbase = wexcl + incl - tot;          // first tile slot of this digit
+        sh.gofs[threadIdx.x] = my_off - tbase;              // modular: slot >= tbase for this digit
+        uint32_t run = tbase;
 #pragma unroll
-        for (int i = 0; i < RX_KPT; ++i) {
-            if (dr[i] != 0xFFFFFFFFu) {
-                const uint32_t d = dr[i] & 0xFFu, r = dr[i] >> 8;
-                const uint32_t slot = s_tbase[d] + s_wcnt[warp][d] + r;
-                const uint32_t row = wrow + i * kWarp;
-                s_key[slot] = key[i];
-                s_pay[slot] = pay ? pay[row] : row;
-            }
-        }
-        __syncthreads();
-        const uint32_t count = min((uint32_t)RX_TILE, end - tile);
-        for (uint32_t slot = threadIdx.x; slot < count; slot += RX_THREADS) {
-            const uint32_t k = s_key[slot];
-            const uint32_t d = rx_digit(k, p);
-            const uint32_t dst = s_gofs[d] + slot;
-            if (REMOTE) {
-                uint32_t *pb = s_peer[d];
-                pb[key_off + dst] = k;
-                pb[pay_off + dst] = s_pay[slot];
-            } else {
-                keys_out[dst] = k;
-                pay_out[dst] = s_pay[slot];
-            }
-        }
-        __syncthreads();
+        for (int w = 0; w < RX_WARPS; ++w) { sh.wcnt[w][threadIdx.x] = (uint16_t)run; run += c[w]; }
     }
+    if (pay) cp_async_wait_all();
+    __syncthreads();
+    // 3. park the pairs in tile-sorted order
+#pragma unroll
+    for (int i = 0; i < RX_KPT; ++i) {
+        if (FULL || dr[i] != 0xFFFFFFFFu) {
+            const uint32_t d = dr[i] & 0xFFu, r = dr[i] >> 8;
+            const uint32_t slot = sh.wcnt[warp][d] + r;
+            sh.kv[slot] = make_uint2(key[i], pay ? sh.pay_in[wofs + i * kWarp] : wrow + i * kWarp);
+        }
+    }
+    __syncthreads();
+    // 4. write out, run by run
+    const uint32_t count = FULL ? (uint32_t)RX_TILE : end - tile;
+#pragma unroll 4
+    for (uint32_t slot = threadIdx.x; slot < count; slot += RX_THREADS) {
+        const uint2 kv = sh.kv[slot];
+        const uint32_t d = digit(kv.x);
+        const uint32_t dst = sh.gofs[d] + slot;
+        if (REMOTE) {
+            uint32_t *pb = sh.peer[d];
+            pb[key_off + dst] = kv.x;
+            pb[pay_off + dst] = kv.y;
+        } else {
+            keys_out[dst] = kv.x;
+            pay_out[dst] = kv.y;
+        }
+    }
+}
+
+template <int HASH, int BITS, bool REMOTE>
+__global__ void __launch_bounds__(RX_THREADS, 4)
+rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
+                  RadixPass p, const uint32_t *__restrict__ hist, const uint32_t *__restrict__ base,
+                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ pay_out,
+                  uint32_t *const *__restrict__ peer_base, unsigned long long key_off,
+                  unsigned long long pay_off, const uint32_t *__restrict__ abort_flag) {
+    extern __shared__ __align__(16) unsigned char rx_smem[];
+    RxShared &sh = *reinterpret_cast<RxShared *>(rx_smem);
+    if (REMOTE) {
+        if (*abort_flag) return;                            // a receive region would overflow
+        if (threadIdx.x < (1u << p.bits)) sh.peer[threadIdx.x] = peer_base[threadIdx.x];
+    }
+    // next free global slot of digit `threadIdx.x` for this tile
+    const uint32_t my_off = base[threadIdx.x] + hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    const uint32_t tile = blockIdx.x * RX_TILE;
+    if (tile + RX_TILE <= n)
+        rx_scatter_tile<HASH, BITS, REMOTE, true>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
+    else
+        rx_scatter_tile<HASH, BITS, REMOTE, false>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
 }
 
 // One CTA per 4096-row tile, launched in row order: the CTAs resident at any moment work on
@@ -220,17 +313,52 @@ RadixGeom radix_geom(uint32_t n, int sm_count) {
     return g;
 }
 
+template <class K>
+static void rx_allow_smem(K *kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RxShared));
+}
+// function attributes are per device: once per device the engine launches on
+static void rx_set_attributes() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done[dev & 63]) return;
+    rx_allow_smem(&rx_scatter_kernel<0, 8, false>);
+    rx_allow_smem(&rx_scatter_kernel<1, 8, false>);
+    rx_allow_smem(&rx_scatter_kernel<0, 0, false>);
+    rx_allow_smem(&rx_scatter_kernel<1, 0, false>);
+    rx_allow_smem(&rx_scatter_kernel<2, 0, false>);
+    rx_allow_smem(&rx_scatter_kernel<2, 0, true>);
+    done[dev & 63] = true;
+}
+
+static void launch_hist(const uint32_t *keys_in, uint32_t n, const RadixGeom &g, RadixPass p, uint32_t *hist,
+                        cudaStream_t s) {
+    if (p.hash == 1) rx_hist_kernel<1><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+    else if (p.hash == 2) rx_hist_kernel<2><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+    else rx_hist_kernel<0><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+}
+
 // scratch: hist = 256 * radix_geom(n).ctas uint32, totals = 256, base = 256
 int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
                       uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
                       uint32_t *base, int sm_count, cudaStream_t s) {
     if (n == 0) return 0;
+    rx_set_attributes();
     const RadixGeom g = radix_geom(n, sm_count);
-    rx_hist_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+    launch_hist(keys_in, n, g, p, hist, s);
     rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
     rx_bucket_base_kernel<<<1, RX_BUCKETS, 0, s>>>(totals, base);
-    rx_scatter_kernel<false><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, pay_in, n, g.rows_per_cta, p, hist, base,
-                                                           keys_out, pay_out, nullptr, 0, 0, nullptr);
+    const size_t sm = sizeof(RxShared);
+#define RX_LAUNCH(H, B)                                                                                       \
+    rx_scatter_kernel<H, B, false><<<g.ctas, RX_THREADS, sm, s>>>(keys_in, pay_in, n, p, hist, base, keys_out, \
+                                                                  pay_out, nullptr, 0, 0, nullptr)
+    if (p.hash == 0 && p.bits == 8) RX_LAUNCH(0, 8);
+    else if (p.hash == 1 && p.bits == 8) RX_LAUNCH(1, 8);
+    else if (p.hash == 0) RX_LAUNCH(0, 0);
+    else if (p.hash == 1) RX_LAUNCH(1, 0);
+    else RX_LAUNCH(2, 0);
+#undef RX_LAUNCH
     return 4;
 }
 
@@ -241,7 +369,7 @@ int launch_radix_hist(const uint32_t *keys_in, uint32_t n, RadixPass p, uint32_t
         return 0;
     }
     const RadixGeom g = radix_geom(n, sm_count);
-    rx_hist_kernel<<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+    launch_hist(keys_in, n, g, p, hist, s);
     rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
     return 2;
 }
@@ -251,9 +379,11 @@ int launch_radix_scatter_remote(const uint32_t *keys_in, const uint32_t *pay_in,
                                 unsigned long long key_off, unsigned long long pay_off,
                                 const uint32_t *abort_flag, int sm_count, cudaStream_t s) {
     if (n == 0) return 0;
+    if (p.hash != 2) return -1;                              // the routing hash is the only remote user
+    rx_set_attributes();
     const RadixGeom g = radix_geom(n, sm_count);
-    rx_scatter_kernel<true><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, pay_in, n, g.rows_per_cta, p, hist, base,
-                                                          nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
+    rx_scatter_kernel<2, 0, true><<<g.ctas, RX_THREADS, sizeof(RxShared), s>>>(
+        keys_in, pay_in, n, p, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
     return 1;
 }
 
@@ -335,13 +465,20 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t in_stride, uint32_t *out,
 // Load this file's kernels now (CUDA loads them lazily, on first launch): a first launch that
 // has to load code while another context's kernel spin-waits for this one can stall behind it.
 void preload_radix() {
-    preload_one(reinterpret_cast<const void *>(&rx_hist_kernel));
+    { auto *fp = &rx_hist_kernel<0>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_hist_kernel<1>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_hist_kernel<2>; preload_one(reinterpret_cast<const void *>(fp)); }
     preload_one(reinterpret_cast<const void *>(&rx_row_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&rx_bucket_base_kernel));
-    { auto *fp = &rx_scatter_kernel<true>; preload_one(reinterpret_cast<const void *>(fp)); }
-    { auto *fp = &rx_scatter_kernel<false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<0, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<1, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<0, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<1, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<2, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<2, 0, true>; preload_one(reinterpret_cast<const void *>(fp)); }
     preload_one(reinterpret_cast<const void *>(&sc_chunk_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&sc_chunk_sum_kernel));
+    rx_set_attributes();
 }
 
 }  // namespace adb
