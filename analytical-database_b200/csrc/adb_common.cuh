@@ -499,6 +499,15 @@ RadixGeom radix_geom(uint32_t n, int sm_count);
 int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
                       uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
                       uint32_t *base, int sm_count, cudaStream_t s);
+// The pass over consecutive segments of seg_tiles 4096-row tiles, each partitioned inside its own
+// row range; base[seg * 256 + d] = first output row of bucket d of segment seg (the join's
+// partitioned probe: segments = probe-row windows, buckets = table partitions).  totals and
+// base: 256 * radix_segments() words, hist: radix_hist_elems() words.
+uint32_t radix_segments(uint32_t n, uint32_t seg_tiles);
+size_t radix_hist_elems(uint32_t n, uint32_t seg_tiles);
+int launch_radix_pass_segmented(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
+                                uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t seg_tiles, uint32_t *hist,
+                                uint32_t *totals, uint32_t *base, int sm_count, cudaStream_t s);
 // The same pass split in two for the peer exchange: histogram + per-tile offsets + totals, then
 // a scatter whose bucket d is written into peer_base[d] + key_off / pay_off (uint32 units) at
 // the offsets `base` holds (skipped when *abort_flag != 0).
@@ -534,17 +543,37 @@ int launch_fmt_emit(const int32_t *val, int64_t n, const uint32_t *block_off, un
 // Hash join (hash_join.cu).
 int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint32_t num_parts,
                      uint32_t *off, cudaStream_t s);
-int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff, cudaStream_t s);
+// sums: scratch of (num_parts + 1023) / 1024 + 1 64-bit words
+int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff,
+                       unsigned long long *sums, cudaStream_t s);
 // toff: num_parts + 1 slot offsets (capacity of partition p = toff[p+1] - toff[p], 0 or a
 // power of two); table: toff[num_parts] 16-byte slots
 int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,
                           const unsigned long long *toff, uint32_t num_parts, uint32_t part_bits,
                           uint4 *table, cudaStream_t s);
-int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const unsigned long long *toff,
-                    uint32_t part_bits, const uint4 *table, uint2 *gc_by_j, int sm_count, cudaStream_t s);
-int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
+// Probe and expansion share one geometry: warp w of the grid owns the probe rows
+// [w * rows_per_warp, (w + 1) * rows_per_warp).  The probe leaves per-warp match counts, scanned
+// in place (warp_sums[w] = first output slot of warp w, *total = all matches).
+struct HjProbeGeom {
+    uint32_t blocks, warps, rows_per_warp;
+};
+HjProbeGeom hj_probe_geom(uint32_t n_probe, int sm_count);
+int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &pg, const unsigned long long *toff,
+                    uint32_t part_bits, const uint4 *table, uint2 *gc_by_j, unsigned long long *warp_sums,
+                    unsigned long long *total, cudaStream_t s);
+// Probe side partitioned for L2 locality (hash_join.cu): pkeys_part / row_part / cell_base come
+// from launch_radix_pass_segmented(probe keys, NULL, ..., RadixPass{24, 8, 1}, seg_tiles).
+HjProbeGeom hj_probe_geom_partitioned(uint32_t n_probe);   // one CTA per 4096 rows (its pg goes to the expansion too)
+// sub_start: (n_probe / 4096 + segs + 1) * 256 words; chunk_sums: pg.warps / 1024 + 2 64-bit words
+int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_part, const uint32_t *cell_base,
+                                uint32_t segs, uint32_t seg_rows, uint32_t n_probe, const HjProbeGeom &pg,
+                                const unsigned long long *toff, uint32_t part_bits, const uint4 *table,
+                                uint2 *res_part, uint32_t *sub_start, uint2 *gc_by_j,
+                                unsigned long long *warp_sums, unsigned long long *chunk_sums,
+                                unsigned long long *total, cudaStream_t s);
+int launch_hj_expand(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
-                     int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);
+                     int32_t *out_build, int32_t *out_probe, cudaStream_t s);
 
 // The join sharded over several contexts: the build side is hash-partitioned
 // over the owners (adb_peer_exchange_pairs' routing hash), every owner builds the tables of its
@@ -558,11 +587,12 @@ struct JoinOwners {
     uint32_t part_bits[kMaxPeers];
     uint32_t route_bits;                             // owner = (key * 0x85EBCA6B) >> (32 - route_bits)
 };
-int launch_hj_probe_sharded(const uint32_t *pkeys, uint32_t n_probe, const JoinOwners &owners, uint2 *gc_by_j,
-                            int sm_count, cudaStream_t s);
-int launch_hj_expand_sharded(const uint2 *gc_by_j, const uint32_t *off_by_j, uint32_t n_probe,
-                             const uint32_t *pkeys, const JoinOwners &owners, const int32_t *probe_pos,
-                             int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s);
+int launch_hj_probe_sharded(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &pg, const JoinOwners &owners,
+                            uint2 *gc_by_j, unsigned long long *warp_sums, unsigned long long *total,
+                            cudaStream_t s);
+int launch_hj_expand_sharded(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,
+                             uint32_t n_probe, const uint32_t *pkeys, const JoinOwners &owners,
+                             const int32_t *probe_pos, int32_t *out_build, int32_t *out_probe, cudaStream_t s);
 
 // Implicit fan-out-32 B+-tree over a sorted value array (index_lookup.cu).
 constexpr int kBTreeMaxDepth = 8;

@@ -68,7 +68,8 @@ struct Engine {
         uint32_t n_probe = 0;
         int64_t matches = 0;
         uint2 *gc_by_j = nullptr;           // {group start, match count} per probe row
-        uint32_t *off_by_j = nullptr;
+        unsigned long long *warp_base = nullptr;   // first output slot of every probing warp (pg.warps)
+        adb::HjProbeGeom pg{};
         int32_t *build_pos_sorted = nullptr;   // all three live in the arena
         const int32_t *probe_pos = nullptr;
         bool swapped = false;
@@ -1813,11 +1814,12 @@ adb_status adb_shared_select(const int32_t *d_col, int64_t n, const int32_t *low
 // ---- radix sort / partition helpers ---------------------------------------------------------
 static adb_status ensure_radix_scratch(uint32_t n) {
     if (!g.rx_totals) {
-        CU(cudaMalloc(&g.rx_totals, sizeof(uint32_t) * 256));
-        CU(cudaMalloc(&g.rx_base, sizeof(uint32_t) * 256));
+        CU(cudaMalloc(&g.rx_totals, sizeof(uint32_t) * 256 * 256));     // <= 256 segments (segmented pass)
+        CU(cudaMalloc(&g.rx_base, sizeof(uint32_t) * 256 * 256));
         CU(cudaMalloc(&g.sc_sums, sizeof(unsigned long long) * (size_t)(g.sm_count * 2 + 8)));
     }
-    const size_t need = 256 * (size_t)adb::radix_geom(n, g.sm_count).ctas;      // [bucket][tile]
+    // [segment][bucket][tiles per segment]: <= 256 segments, the last one padded
+    const size_t need = 256 * ((size_t)adb::radix_geom(n, g.sm_count).ctas + 256);
     if (need <= g.rx_hist_elems) return ADB_OK;
     CU(cudaStreamSynchronize(g.stream));
     if (g.rx_hist) CU(cudaFree(g.rx_hist));
@@ -2083,6 +2085,9 @@ adb_status adb_format_i32_emit(char *d_text) {
 
 // ---- hash join ------------------------------------------------------------------------------------
 static void join_release() { g.join = Engine::JoinState{}; }      // its buffers are arena memory
+// per-warp match counts of the probe (<= 8 warps x 8 CTAs x SMs), the geometry's chunk sums
+// (<= 2^20 partitions / 1024) and a few totals
+static constexpr size_t kJoinSmallScratch = 512 * 1024;
 
 // ADB_TRACE=1: synchronise after every stage of a join and print its wall-clock time.
 struct StageTrace {
@@ -2105,8 +2110,24 @@ struct StageTrace {
 // join_build: steps 1-3 (sort on the hash, partition boundaries, one table per partition);
 // leaves {build_pos_sorted, toff, part_bits} in g.join and the tables in g.hj_table.  The arena
 // is reserved for the build AND for `np` probe rows' worth of {group, count} + offsets.
+// Probe rows partitioned for L2 locality (hash_join.cu, P1-P3) when the tables will not fit L2
+// by a wide margin: ~21 bytes of table per build row against 126 MB.  ADB_JOIN_PROBE=direct /
+// partitioned overrides (tests run both forms on the same inputs).
+static bool join_probe_partitioned(uint32_t nb, uint32_t np) {
+    if (const char *e = getenv("ADB_JOIN_PROBE")) {
+        if (!strcmp(e, "direct")) return false;
+        if (!strcmp(e, "partitioned")) return np > 0;
+    }
+    return nb >= (6u << 20) && np >= (4u << 20);
+}
+static size_t join_partition_scratch(uint32_t np) {      // keys + row numbers + results in partition order,
+    return 2 * arena_round((size_t)np * 4) + arena_round((size_t)np * 8) +      // 8 piece sums per 4096 rows,
+           arena_round(((size_t)np / 4096 + 2) * 8 * 8) +                          // the cells' sub-window starts
+           arena_round(((size_t)np / 4096 + (size_t)np / (4096 * 256) + 520) * 256 * 4) + 4096;
+}
+
 static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, uint32_t np, int *launches,
-                             StageTrace &tr) {
+                             StageTrace &tr, bool part_scratch = false) {
     uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
     // (up to 2^20 partitions: a 500 M-row build side still gets ~500-row partitions that fit the
     // shared-memory table, instead of 2^16 oversized ones built slot by slot in global memory)
@@ -2114,8 +2135,8 @@ static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, 
     const uint32_t num_parts = 1u << part_bits;
     const size_t pbytes = (size_t)(num_parts + 1) * 4;
     if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
-                                     arena_round((size_t)np * 4) + arena_round(pbytes) +
-                                     arena_round((size_t)(num_parts + 1) * 8) + 4096))
+                                     arena_round(pbytes) + arena_round((size_t)(num_parts + 1) * 8) +
+                                     (part_scratch ? join_partition_scratch(np) : 0) + kJoinSmallScratch))
         return s;
     auto &j = g.join;
     j.part_bits = part_bits;
@@ -2138,7 +2159,8 @@ static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, 
     // 2. partition boundaries -> table geometry: partition p gets a power-of-two slot range
     //    holding its rows at <= 80 % load (<= 4096 slots: built in shared memory)
     *launches += adb::launch_hj_bounds(bk, nb, part_bits, num_parts, off1, g.stream);
-    *launches += adb::launch_hj_geometry(off1, num_parts, toff, g.stream);
+    *launches += adb::launch_hj_geometry(off1, num_parts, toff, ARENA_TAKE(unsigned long long, num_parts / 1024 + 2),
+                                         g.stream);
     unsigned long long slots = 0;
     if (adb_status s = read_back(&slots, toff + num_parts, sizeof slots)) return s;
     if (slots > g.hj_table_slots) {
@@ -2175,22 +2197,43 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     }
     int launches = 0;
     StageTrace tr;
-    if (adb_status s = join_build(bv, bp, nb, np, &launches, tr)) return s;
+    const bool partitioned = join_probe_partitioned(nb, np);
+    if (partitioned)
+        if (adb_status s = ensure_radix_scratch(np > nb ? np : nb)) return s;
+    if (adb_status s = join_build(bv, bp, nb, np, &launches, tr, partitioned)) return s;
     auto &j = g.join;
     j.swapped = swapped;
     j.n_probe = np;
     j.probe_pos = pp;
-    int64_t *tot = ARENA_TAKE(int64_t, 2);
-    // 4. probe in row order
+    unsigned long long *tot = ARENA_TAKE(unsigned long long, 2);
+    // 4. probe in row order; every warp leaves the matches of its piece, their scan = the
+    //    first output slot of every piece (the expansion computes the slots inside a piece)
+    j.pg = partitioned ? adb::hj_probe_geom_partitioned(np) : adb::hj_probe_geom(np, g.sm_count);
     j.gc_by_j = ARENA_TAKE(uint2, np);
-    j.off_by_j = ARENA_TAKE(uint32_t, np);
-    launches += adb::launch_hj_probe(reinterpret_cast<const uint32_t *>(pv), np, j.toff, j.part_bits,
-                                     static_cast<const uint4 *>(g.hj_table), j.gc_by_j, g.sm_count, g.stream);
-    tr.lap("probe");
-    // 5. output offsets in probe-row order
-    launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
+    j.warp_base = ARENA_TAKE(unsigned long long, j.pg.warps);
+    if (partitioned) {
+        // <= 256 windows of whole 4096-row tiles, each partitioned on the top 8 hash bits
+        const uint32_t tiles = (np + 4095) / 4096;
+        const uint32_t seg_tiles = (tiles + 255) / 256;
+        const uint32_t segs = adb::radix_segments(np, seg_tiles);
+        uint32_t *pk = ARENA_TAKE(uint32_t, np), *rows = ARENA_TAKE(uint32_t, np);
+        uint2 *res = ARENA_TAKE(uint2, np);
+        uint32_t *sub_start = ARENA_TAKE(uint32_t, ((size_t)segs * (seg_tiles + 1) + 1) * 256);
+        unsigned long long *chunk_sums = ARENA_TAKE(unsigned long long, j.pg.warps / 1024 + 2);
+        launches += adb::launch_radix_pass_segmented(reinterpret_cast<const uint32_t *>(pv), nullptr, pk, rows, np,
+                                                     adb::RadixPass{24, 8, 1}, seg_tiles, g.rx_hist, g.rx_totals,
+                                                     g.rx_base, g.sm_count, g.stream);
+        tr.lap("probe rows by window and table slice");
+        launches += adb::launch_hj_probe_partitioned(pk, rows, g.rx_base, segs, seg_tiles * 4096, np, j.pg, j.toff,
+                                                     j.part_bits, static_cast<const uint4 *>(g.hj_table), res,
+                                                     sub_start, j.gc_by_j, j.warp_base, chunk_sums, tot, g.stream);
+    } else {
+        launches += adb::launch_hj_probe(reinterpret_cast<const uint32_t *>(pv), np, j.pg, j.toff, j.part_bits,
+                                         static_cast<const uint4 *>(g.hj_table), j.gc_by_j, j.warp_base, tot,
+                                         g.stream);
+    }
     if (adb_status s = read_back(&j.matches, tot, sizeof(int64_t))) return s;
-    tr.lap("output offsets");
+    tr.lap(partitioned ? "probe slice by slice + back to row order" : "probe + piece offsets");
     if (adb_status s = after_launch("join_count", launches)) return s;
     if (j.matches >= (int64_t)1 << 31) {
         const long long m = j.matches;
@@ -2269,15 +2312,14 @@ adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int3
         return ADB_OK;
     }
     int launches = 0;
-    int64_t *tot = ARENA_TAKE(int64_t, 2);
+    unsigned long long *tot = ARENA_TAKE(unsigned long long, 2);
+    j.pg = adb::hj_probe_geom(np, g.sm_count);
     j.gc_by_j = ARENA_TAKE(uint2, np);
-    j.off_by_j = ARENA_TAKE(uint32_t, np);
+    j.warp_base = ARENA_TAKE(unsigned long long, j.pg.warps);
     StageTrace tr;
-    launches += adb::launch_hj_probe_sharded(j.probe_keys, np, o, j.gc_by_j, g.sm_count, g.stream);
-    tr.lap("probe (peer table reads)");
-    launches += adb::launch_exclusive_scan(&j.gc_by_j[0].y, 2, j.off_by_j, np, g.sc_sums, tot, g.sm_count, g.stream);
+    launches += adb::launch_hj_probe_sharded(j.probe_keys, np, j.pg, o, j.gc_by_j, j.warp_base, tot, g.stream);
     if (adb_status s = read_back(&j.matches, tot, sizeof(int64_t))) return s;
-    tr.lap("output offsets");
+    tr.lap("probe (peer table reads) + piece offsets");
     if (adb_status s = after_launch("join_probe_sharded", launches)) return s;
     if (j.matches >= (int64_t)1 << 31)
         return fail(ADB_ERR_INVALID, "join produces %lld pairs on one context; the result must stay below 2^31",
@@ -2304,8 +2346,8 @@ adb_status adb_peer_exchange_reserve(int64_t send_pairs, int64_t build_pairs, in
     while (part_bits < 20 && (nb >> part_bits) > 1024) ++part_bits;
     const uint32_t num_parts = 1u << part_bits;
     if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
-                                     arena_round((size_t)np * 4) + arena_round((size_t)(num_parts + 1) * 4) +
-                                     arena_round((size_t)(num_parts + 1) * 8) + 8192))
+                                     arena_round((size_t)(num_parts + 1) * 4) +
+                                     arena_round((size_t)(num_parts + 1) * 8) + kJoinSmallScratch))
         return s;
     {
         const size_t words = (size_t)ADB_MAX_PEERS * ((size_t)num_parts + 1);
@@ -2352,10 +2394,10 @@ adb_status adb_join_emit(int32_t *d_out1, int32_t *d_out2) {
         if (!d_out1 || !d_out2) return fail(ADB_ERR_INVALID, "adb_join_emit: NULL output");
         int32_t *ob = j.swapped ? d_out2 : d_out1, *op = j.swapped ? d_out1 : d_out2;
         const int k_ = j.sharded
-            ? adb::launch_hj_expand_sharded(j.gc_by_j, j.off_by_j, j.n_probe, j.probe_keys, j.owners, j.probe_pos,
-                                            ob, op, g.sm_count, g.stream)
-            : adb::launch_hj_expand(j.gc_by_j, j.off_by_j, j.n_probe, j.build_pos_sorted, j.probe_pos, ob, op,
-                                    g.sm_count, g.stream);
+            ? adb::launch_hj_expand_sharded(j.gc_by_j, j.warp_base, j.pg, j.n_probe, j.probe_keys, j.owners,
+                                            j.probe_pos, ob, op, g.stream)
+            : adb::launch_hj_expand(j.gc_by_j, j.warp_base, j.pg, j.n_probe, j.build_pos_sorted, j.probe_pos, ob, op,
+                                    g.stream);
         rc = after_launch("join_expand", k_);
     }
     if (j.sharded) {

@@ -51,41 +51,94 @@ __global__ void hj_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, 
 
 // ---- table geometry ------------------------------------------------------------------------------
 // Partition p gets a power-of-two slot range holding its rows at <= 80 % load (0 slots when it
-// is empty); toff = exclusive scan of the capacities, toff[num_parts] = total.  One CTA.
-__global__ void __launch_bounds__(1024)
-hj_geometry_kernel(const uint32_t *__restrict__ off1, uint32_t num_parts,
-                   unsigned long long *__restrict__ toff) {
-    __shared__ unsigned long long s_w[32];
+// is empty); toff = exclusive scan of the capacities, toff[num_parts] = total.  Three small
+// launches (r02u: one CTA walking 2^17-2^20 partitions 1024 at a time took 0.3 ms): every CTA
+// scans the capacities of 1024 partitions and leaves their sum, one CTA scans the sums, every
+// CTA adds its base.
+constexpr uint32_t HJ_GEOM_CHUNK = 1024;
+
+__device__ __forceinline__ unsigned long long hj_block_incl_scan_u64(unsigned long long x, unsigned long long *s_w,
+                                                                      unsigned long long *block_total) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long carry = 0;
-    for (uint32_t base = 0; base < num_parts; base += 1024) {
-        const uint32_t p = base + threadIdx.x;
-        unsigned long long cap = 0;
-        if (p < num_parts) {
-            const unsigned long long sz = off1[p + 1] - off1[p];
-            if (sz) {
-                cap = 16;
-                while (cap < sz + sz / 4 + 1) cap <<= 1;
-            }
-        }
-        unsigned long long incl = cap;
+    unsigned long long incl = x;
 #pragma unroll
-        for (int d = 1; d < kWarp; d <<= 1) {
-            const unsigned long long y = __shfl_up_sync(kFull, incl, d);
-            if (lane >= (uint32_t)d) incl += y;
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        unsigned long long wexcl = 0, tot = 0;
-        for (uint32_t w = 0; w < 32; ++w) {
-            if (w < warp) wexcl += s_w[w];
-            tot += s_w[w];
-        }
-        if (p < num_parts) toff[p] = carry + wexcl + incl - cap;
-        carry += tot;
-        __syncthreads();
+    for (int d = 1; d < kWarp; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(kFull, incl, d);
+        if (lane >= (uint32_t)d) incl += y;
     }
-    if (threadIdx.x == 0) toff[num_parts] = carry;
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long wexcl = 0, tot = 0;
+    for (uint32_t w = 0; w < blockDim.x / kWarp; ++w) {
+        if (w < warp) wexcl += s_w[w];
+        tot += s_w[w];
+    }
+    __syncthreads();
+    *block_total = tot;
+    return wexcl + incl;
+}
+
+__global__ void __launch_bounds__(HJ_GEOM_CHUNK)
+hj_geometry_local_kernel(const uint32_t *__restrict__ off1, uint32_t num_parts,
+                         unsigned long long *__restrict__ toff, unsigned long long *__restrict__ chunk_sums) {
+    __shared__ unsigned long long s_w[32];
+    const uint32_t p = blockIdx.x * HJ_GEOM_CHUNK + threadIdx.x;
+    unsigned long long cap = 0;
+    if (p < num_parts) {
+        const unsigned long long sz = off1[p + 1] - off1[p];
+        if (sz) {
+            cap = 16;
+            while (cap < sz + sz / 4 + 1) cap <<= 1;
+        }
+    }
+    unsigned long long tot;
+    const unsigned long long incl = hj_block_incl_scan_u64(cap, s_w, &tot);
+    if (p < num_parts) toff[p] = incl - cap;              // exclusive inside the chunk
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = tot;
+}
+
+// in-place exclusive scan of 64-bit sums by one CTA (a few thousand, or the partitioned probe's
+// 8 per 4096 rows: four per thread and step); the total goes to *total
+__global__ void __launch_bounds__(1024)
+hj_sums_scan_kernel(unsigned long long *__restrict__ sums, uint32_t n, unsigned long long *__restrict__ total) {
+    __shared__ unsigned long long s_w[32];
+    unsigned long long carry = 0;
+    for (uint32_t base = 0; base < n; base += 4096) {
+        const uint32_t i = base + threadIdx.x * 4;
+        unsigned long long x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = i + k < n ? sums[i + k] : 0ull;
+        unsigned long long tot;
+        const unsigned long long incl = hj_block_incl_scan_u64(x[0] + x[1] + x[2] + x[3], s_w, &tot);
+        unsigned long long run = carry + incl - (x[0] + x[1] + x[2] + x[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n) sums[i + k] = run;
+            run += x[k];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(HJ_GEOM_CHUNK)
+hj_geometry_add_kernel(unsigned long long *__restrict__ toff, uint32_t num_parts,
+                       const unsigned long long *__restrict__ chunk_base) {
+    const uint32_t p = blockIdx.x * HJ_GEOM_CHUNK + threadIdx.x;
+    if (p < num_parts) toff[p] += chunk_base[blockIdx.x];
+}
+
+// exclusive scan of n 64-bit sums in place, 1024 per CTA (the partitioned probe leaves 8 per 4096
+// rows: one CTA walking 195 K of them took 207 us, r02z)
+__global__ void __launch_bounds__(HJ_GEOM_CHUNK)
+hj_sums_local_kernel(unsigned long long *__restrict__ sums, uint32_t n, unsigned long long *__restrict__ chunk_sums) {
+    __shared__ unsigned long long s_w[32];
+    const uint32_t i = blockIdx.x * HJ_GEOM_CHUNK + threadIdx.x;
+    const unsigned long long x = i < n ? sums[i] : 0ull;
+    unsigned long long tot;
+    const unsigned long long incl = hj_block_incl_scan_u64(x, s_w, &tot);
+    if (i < n) sums[i] = incl - x;
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = tot;
 }
 
 // ---- per-partition tables ---------------------------------------------------------------------
@@ -105,11 +158,26 @@ hj_geometry_kernel(const uint32_t *__restrict__ off1, uint32_t num_parts,
 // partitioning passes, no scatter.
 struct HjSlot {                       // 16 bytes, read with one ld.global.v4
     uint32_t tag;                     // hj_tag(key), 0 = free
-    uint32_t val;                     // cnt == 1: build position; else group start
-    uint32_t cnt;                     // group size
+    uint32_t x, y;                    // what a probe of this key gets, see hj_matches()
     uint32_t pad;
 };
 static_assert(sizeof(HjSlot) == 16, "slot layout");
+
+// A probe row's result {x, y}:  y == 0: no match;  y == 1: one build row, x = its position;
+// y with bit 31 set: two build rows, x and y & 0x7FFFFFFF their positions in insertion order
+// (positions are row numbers < 2^31);  else: y >= 2 rows, x = start of the group in the sorted
+// build positions.  r02w: on uniform keys 26 % of the probe rows meet a group of two or more and
+// each of those cost the expansion a random read of the sorted build positions (1.7 GB of DRAM
+// lines per 100 M probes); pairs -- two thirds of them -- now travel inside the slot.
+__device__ __forceinline__ uint32_t hj_matches(uint32_t y) { return (y >> 31) ? 2u : y; }
+__device__ __forceinline__ uint2 hj_slot_value(uint32_t group_start, uint32_t size, const int32_t *__restrict__ bpos) {
+    if (size == 1) return make_uint2((uint32_t)bpos[group_start], 1u);
+    if (size == 2) {
+        const uint32_t p0 = (uint32_t)bpos[group_start], p1 = (uint32_t)bpos[group_start + 1];
+        if (!(p1 >> 31)) return make_uint2(p0, 0x80000000u | p1);
+    }
+    return make_uint2(group_start, size);
+}
 
 __device__ __forceinline__ uint32_t hj_tag(uint32_t key, uint32_t part_bits) {
     return (((key * kHashMul) << part_bits) >> part_bits) + 1u;       // part_bits >= 1: never wraps to 0
@@ -155,7 +223,8 @@ hj_table_build_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
         uint4 *__restrict__ out = table + t0;
         for (uint32_t s = threadIdx.x; s < cap; s += HJ_THREADS) {
             const uint32_t w = s_gc[s], c = w & 0xFFFFu, gs = b0 + (w >> 16);
-            out[s] = make_uint4(s_tag[s], c == 1 ? (uint32_t)bpos[gs] : gs, c, 0u);
+            const uint2 v = c ? hj_slot_value(gs, c, bpos) : make_uint2(0u, 0u);
+            out[s] = make_uint4(s_tag[s], v.x, v.y, 0u);
         }
         return;
     }
@@ -178,18 +247,42 @@ hj_table_build_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
         if (leader) T[4 * s + 1] = i;                    // only the leader writes this word
     }
     __syncthreads();
-    for (unsigned long long s = threadIdx.x; s < cap64; s += HJ_THREADS)
-        if (T[4 * s + 2] == 1u) T[4 * s + 1] = (uint32_t)bpos[T[4 * s + 1]];
+    for (unsigned long long s = threadIdx.x; s < cap64; s += HJ_THREADS) {
+        const uint32_t c = T[4 * s + 2];
+        if (c == 1u || c == 2u) {
+            const uint2 v = hj_slot_value(T[4 * s + 1], c, bpos);
+            T[4 * s + 1] = v.x;
+            T[4 * s + 2] = v.y;
+        }
+    }
 }
 
 // Probe side in its original row order: one random 16-byte slot read per row (linear probing
 // almost always ends inside the same 64-byte half line, which is what a miss fetches: ld_gather), results stored coalesced.
+// Every warp walks ONE contiguous piece of the probe side and leaves the number of matches it
+// found: the scan of those ~9 K sums is all the expansion needs to compute its output offsets
+// itself (r02u: the separate offsets pass over the 100 M counts cost 0.52 ms, and reading them
+// back in the expansion another 400 MB).
+__device__ __forceinline__ void hj_warp_range(uint32_t rows_per_warp, uint32_t n_probe, uint32_t *j0, uint32_t *j1) {
+    const unsigned long long w = blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5);
+    const unsigned long long b = w * rows_per_warp, e = b + rows_per_warp;
+    *j0 = (uint32_t)(b < n_probe ? b : n_probe);
+    *j1 = (uint32_t)(e < n_probe ? e : n_probe);
+}
+__device__ __forceinline__ void hj_warp_sum_out(unsigned long long acc, unsigned long long *__restrict__ warp_sums) {
+    acc = (unsigned long long)warp_sum_i64((int64_t)acc);
+    if ((threadIdx.x & 31) == 0) warp_sums[blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5)] = acc;
+}
+
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe,
+hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe, uint32_t rows_per_warp,
                 const unsigned long long *__restrict__ toff, uint32_t part_bits,
-                const uint4 *__restrict__ table, uint2 *__restrict__ gc_by_j) {
-    const uint32_t stride = gridDim.x * HJ_THREADS;
-    for (uint32_t j = blockIdx.x * HJ_THREADS + threadIdx.x; j < n_probe; j += stride) {
+                const uint4 *__restrict__ table, uint2 *__restrict__ gc_by_j,
+                unsigned long long *__restrict__ warp_sums) {
+    uint32_t j0, j1;
+    hj_warp_range(rows_per_warp, n_probe, &j0, &j1);
+    unsigned long long acc = 0;
+    for (uint32_t j = j0 + (threadIdx.x & 31); j < j1; j += kWarp) {
         const uint32_t k = (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(pkeys) + j);
         const uint32_t p = hj_pid(k, part_bits);
         const unsigned long long t0 = toff[p], cap = toff[p + 1] - t0;
@@ -206,49 +299,239 @@ hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe,
             }
         }
         gc_by_j[j] = r;
+        acc += hj_matches(r.y);
+    }
+    hj_warp_sum_out(acc, warp_sums);
+}
+
+// ---- the probe side partitioned for L2 locality ---------------------------------------------------
+// tools/random_read_probe.cu (r02v): 100 M random 16-byte reads of a 2 GB table run at 36 G/s
+// whatever the miss size -- the DRAM's random-access rate -- and at 145-165 G/s when consecutive
+// reads stay inside a 32 MB slice of it.  For a table well beyond L2 the probe therefore goes:
+//   P1  the probe rows, cut into <= 256 WINDOWS of consecutive rows, are partitioned window by
+//       window on the top 8 bits of the join hash (one segmented radix pass, payload = the row
+//       number): cell (w, p) = the rows of window w whose slots lie in 1/256 of the table;
+//   P2  the cells are probed partition-major -- p = 0: all windows, p = 1: all windows ... -- so
+//       the slice of the table in use stays in L2; results are stored where the row sits;
+//   P3  one linear pass takes {row number, result} back to probe order: consecutive entries
+//       belong to one window, i.e. to a 3 MB piece of the result array, so these scattered
+//       8-byte stores meet in L2 and leave it as full sectors (r01k's scatter straight from the
+//       partitions was a 32-byte read-modify-write in DRAM per row: 1.8 TB/s of traffic).
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_probe_cells_kernel(const uint32_t *__restrict__ pkeys_part, const uint32_t *__restrict__ cell_base,
+                      uint32_t segs, uint32_t seg_rows, uint32_t n_probe,
+                      const unsigned long long *__restrict__ toff, uint32_t part_bits,
+                      const uint4 *__restrict__ table, uint2 *__restrict__ res_part) {
+    const uint32_t p = blockIdx.x / segs, w = blockIdx.x - p * segs;
+    const uint32_t b = cell_base[w * 256 + p];
+    const unsigned long long seg_end = (unsigned long long)(w + 1) * seg_rows;
+    const uint32_t e = p < 255 ? cell_base[w * 256 + p + 1] : (uint32_t)(seg_end < n_probe ? seg_end : n_probe);
+    for (uint32_t i = b + threadIdx.x; i < e; i += HJ_THREADS) {
+        const uint32_t k = (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(pkeys_part) + i);
+        const uint32_t pid = hj_pid(k, part_bits);
+        const unsigned long long t0 = toff[pid], cap = toff[pid + 1] - t0;
+        uint2 r = make_uint2(0u, 0u);
+        if (cap) {
+            const uint32_t tag = hj_tag(k, part_bits);
+            const unsigned long long mask = cap - 1;
+            unsigned long long s = hj_mix(tag) & mask;
+            while (true) {
+                const uint4 sl = ld_gather(table + t0 + s);
+                if (sl.x == tag) { r = make_uint2(sl.y, sl.z); break; }
+                if (sl.x == 0u) break;
+                s = (s + 1) & mask;
+            }
+        }
+        res_part[i] = r;
     }
 }
 
-// ---- expand ---------------------------------------------------------------------------------------
+// P3.  r02y: scattering {row number -> result} entry by entry, even though consecutive entries
+// stay inside one 3 MB window of the result array, still cost a DRAM read-modify-write per
+// 8-byte store (3.9 GB read + 3.0 GB written for 100 M rows, 3.6 ms): partially written sectors
+// do not wait in L2 for their other rows.  So the rows are gathered instead: a CTA owns 4096
+// consecutive probe rows, finds their entries in each of the window's 256 cells (row numbers
+// ascend inside a cell: two binary searches per cell, ~16 entries each), parks the results in
+// shared memory by row and writes them out as whole lines.  Its eight warps are the expansion's
+// pieces (512 rows each): their match counts go to warp_sums.
+constexpr uint32_t HJ_SUB = 4096;
+constexpr uint32_t HJ_SUB_WARP = HJ_SUB / (HJ_THREADS / kWarp);
+
+__device__ __forceinline__ uint32_t hj_lower_bound(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t v) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// sub_start[(w * (subs + 1) + k) * 256 + p] = first entry of cell (w, p) whose row number is
+// >= w * seg_rows + k * 4096 (k = subs: the end of the cell).  One thread per search, all of them
+// in flight at once: done inside the gathering CTAs the 22 dependent loads per cell were most
+// of their 1.6 ms (r02z).
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_expand_kernel(const uint2 *__restrict__ gc_by_j,
-                 const uint32_t *__restrict__ off_by_j, uint32_t n_probe,
-                 const int32_t *__restrict__ build_pos_sorted, const int32_t *__restrict__ probe_pos,
-                 int32_t *__restrict__ out_build, int32_t *__restrict__ out_probe) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * (HJ_THREADS / kWarp);
-    const uint32_t warp_id = blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5);
-    for (uint32_t j0 = warp_id * kWarp; j0 < n_probe; j0 += warps * kWarp) {
-        const uint32_t j = j0 + lane;
-        uint32_t cnt = 0, gs = 0, off = 0;
-        int32_t pp = 0;
-        if (j < n_probe) {
-            const uint2 gc = gc_by_j[j];
-            cnt = gc.y;
-            if (cnt) { gs = gc.x; off = off_by_j[j]; pp = probe_pos[j]; }
-        }
-        if (cnt == 1) {                                  // gs already is the build position
-            out_build[off] = (int32_t)gs;
-            out_probe[off] = pp;
-        } else if (cnt && cnt <= 8) {
-            for (uint32_t r = 0; r < cnt; ++r) {
-                out_build[off + r] = ld_gather(build_pos_sorted + gs + r);
-                out_probe[off + r] = pp;
+hj_sub_bounds_kernel(const uint32_t *__restrict__ row_part, const uint32_t *__restrict__ cell_base,
+                     uint32_t segs, uint32_t seg_rows, uint32_t n_probe, uint32_t *__restrict__ sub_start) {
+    const uint32_t subs = seg_rows / HJ_SUB;
+    const unsigned long long gid = (unsigned long long)blockIdx.x * HJ_THREADS + threadIdx.x;
+    const uint32_t p = (uint32_t)(gid & 255u);
+    const uint32_t k = (uint32_t)((gid >> 8) % (subs + 1));
+    const uint32_t w = (uint32_t)((gid >> 8) / (subs + 1));
+    if (w >= segs) return;
+    const uint32_t b = cell_base[w * 256 + p];
+    const unsigned long long seg_end = (unsigned long long)(w + 1) * seg_rows;
+    const uint32_t e = p < 255 ? cell_base[w * 256 + p + 1] : (uint32_t)(seg_end < n_probe ? seg_end : n_probe);
+    const unsigned long long first_row = (unsigned long long)w * seg_rows + (unsigned long long)k * HJ_SUB;
+    sub_start[gid] = first_row >= n_probe ? e : hj_lower_bound(row_part, b, e, (uint32_t)first_row);
+}
+
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_unpartition_kernel(const uint32_t *__restrict__ row_part, const uint2 *__restrict__ res_part,
+                      const uint32_t *__restrict__ sub_start, uint32_t seg_rows, uint32_t n_probe,
+                      uint2 *__restrict__ gc_by_j, unsigned long long *__restrict__ warp_sums) {
+    __shared__ uint2 s_res[HJ_SUB];
+    __shared__ uint32_t s_lo[256], s_n[256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t j_lo = blockIdx.x * HJ_SUB;
+    const uint32_t j_hi = min(n_probe, j_lo + HJ_SUB);
+    const uint32_t subs = seg_rows / HJ_SUB;
+    const uint32_t w = blockIdx.x / subs, k = blockIdx.x - w * subs;
+    {
+        const size_t at = ((size_t)w * (subs + 1) + k) * 256 + threadIdx.x;
+        const uint32_t lo = sub_start[at], hi = sub_start[at + 256];
+        s_lo[threadIdx.x] = lo;
+        s_n[threadIdx.x] = hi - lo;
+    }
+    __syncthreads();
+    // warp `warp` gathers cells warp*32 .. +32, four cells' loads in flight at a time
+    constexpr int U = 4;
+    for (uint32_t c0 = warp * 32; c0 < warp * 32 + 32; c0 += U) {
+        uint32_t row[U];
+        int2 val[U];
+        bool more = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t cnt = s_n[c0 + u];
+            row[u] = 0xFFFFFFFFu;
+            if (lane < cnt) {
+                row[u] = row_part[s_lo[c0 + u] + lane];
+                val[u] = *reinterpret_cast<const int2 *>(res_part + s_lo[c0 + u] + lane);
             }
+            more |= cnt > kWarp;
         }
-        uint32_t longs = __ballot_sync(kFull, cnt > 8);
-        while (longs) {
-            const int src = __ffs(longs) - 1;
-            longs &= longs - 1;
-            const uint32_t c = __shfl_sync(kFull, cnt, src), g = __shfl_sync(kFull, gs, src);
-            const uint32_t o = __shfl_sync(kFull, off, src);
-            const int32_t q = __shfl_sync(kFull, pp, src);
-            for (uint32_t r = lane; r < c; r += kWarp) {
-                out_build[o + r] = build_pos_sorted[g + r];
-                out_probe[o + r] = q;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (row[u] != 0xFFFFFFFFu) s_res[row[u] - j_lo] = make_uint2((uint32_t)val[u].x, (uint32_t)val[u].y);
+        if (more) {                                          // a cell with more than 32 rows in here (skew)
+            for (int u = 0; u < U; ++u) {
+                const uint32_t lo = s_lo[c0 + u], cnt = s_n[c0 + u];
+                for (uint32_t q = kWarp + lane; q < cnt; q += kWarp) {
+                    const int2 t = *reinterpret_cast<const int2 *>(res_part + lo + q);
+                    s_res[row_part[lo + q] - j_lo] = make_uint2((uint32_t)t.x, (uint32_t)t.y);
+                }
             }
         }
     }
+    __syncthreads();
+    const uint32_t rows = j_hi - j_lo;
+    for (uint32_t r = threadIdx.x; r < rows; r += HJ_THREADS) gc_by_j[j_lo + r] = s_res[r];
+    uint32_t acc = 0;
+    for (uint32_t r = warp * HJ_SUB_WARP + lane; r < min(rows, (warp + 1) * HJ_SUB_WARP); r += kWarp)
+        acc += hj_matches(s_res[r].y);
+    acc = warp_sum(acc);
+    if (lane == 0) warp_sums[blockIdx.x * (HJ_THREADS / kWarp) + warp] = acc;
+}
+
+// ---- expand ---------------------------------------------------------------------------------------
+// A warp expands the piece of the probe side it probed: its first output slot comes from the
+// scan of the warps' match counts, the slots inside the piece from a running warp scan.  Four
+// 32-row steps are loaded at once (r02u: one step at a time kept 16 KB per SM in flight and
+// ran at 2.2 TB/s).
+constexpr int HJ_EXP_STEPS = 4;
+
+struct HjLocalBuild {
+    const int32_t *__restrict__ bpos;
+    __device__ __forceinline__ const int32_t *list(uint32_t) const { return bpos; }
+};
+
+template <class BuildLists, class OwnerOf>
+__device__ __forceinline__ void hj_expand_body(const uint2 *__restrict__ gc_by_j,
+                                               const unsigned long long *__restrict__ warp_base,
+                                               uint32_t rows_per_warp, uint32_t n_probe,
+                                               const BuildLists &lists, const OwnerOf &owner_of,
+                                               const int32_t *__restrict__ probe_pos,
+                                               int32_t *__restrict__ out_build, int32_t *__restrict__ out_probe) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t j0, j1;
+    hj_warp_range(rows_per_warp, n_probe, &j0, &j1);
+    if (j0 >= j1) return;
+    uint32_t running = (uint32_t)warp_base[blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5)];
+    for (uint32_t jb = j0; jb < j1; jb += kWarp * HJ_EXP_STEPS) {
+        uint2 gcv[HJ_EXP_STEPS];
+        int32_t ppv[HJ_EXP_STEPS];
+#pragma unroll
+        for (int u = 0; u < HJ_EXP_STEPS; ++u) {
+            const uint32_t j = jb + u * kWarp + lane;
+            gcv[u] = make_uint2(0u, 0u);
+            ppv[u] = 0;
+            if (j < j1) {
+                const int2 t = *reinterpret_cast<const int2 *>(gc_by_j + j);
+                gcv[u] = make_uint2((uint32_t)t.x, (uint32_t)t.y);
+                ppv[u] = ld_stream(probe_pos + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < HJ_EXP_STEPS; ++u) {
+            if (jb + u * kWarp >= j1) break;                 // warp-uniform
+            const bool pair = gcv[u].y >> 31;
+            const uint32_t cnt = hj_matches(gcv[u].y), gs = gcv[u].x;
+            const int32_t pp = ppv[u];
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            const uint32_t off = running + incl - cnt;
+            running += __shfl_sync(kFull, incl, 31);
+            if (cnt == 1) {                                  // gs already is the build position
+                out_build[off] = (int32_t)gs;
+                out_probe[off] = pp;
+            } else if (pair) {                               // both build positions came with the slot
+                out_build[off] = (int32_t)gs;
+                out_build[off + 1] = (int32_t)(gcv[u].y & 0x7FFFFFFFu);
+                out_probe[off] = pp;
+                out_probe[off + 1] = pp;
+            } else if (cnt && cnt <= 8) {
+                const int32_t *__restrict__ bp = lists.list(owner_of(jb + u * kWarp + lane));
+                for (uint32_t r = 0; r < cnt; ++r) {
+                    out_build[off + r] = ld_gather(bp + gs + r);
+                    out_probe[off + r] = pp;
+                }
+            }
+            uint32_t longs = __ballot_sync(kFull, cnt > 8);
+            while (longs) {
+                const int src = __ffs(longs) - 1;
+                longs &= longs - 1;
+                const uint32_t c = __shfl_sync(kFull, cnt, src), g = __shfl_sync(kFull, gs, src);
+                const uint32_t o = __shfl_sync(kFull, off, src);
+                const int32_t q = __shfl_sync(kFull, pp, src);
+                const int32_t *__restrict__ bp = lists.list(owner_of(jb + u * kWarp + src));
+                for (uint32_t r = lane; r < c; r += kWarp) {
+                    out_build[o + r] = bp[g + r];
+                    out_probe[o + r] = q;
+                }
+            }
+        }
+    }
+}
+
+struct HjNoOwner {
+    __device__ __forceinline__ uint32_t operator()(uint32_t) const { return 0u; }
+};
+
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_expand_kernel(const uint2 *__restrict__ gc_by_j, const unsigned long long *__restrict__ warp_base,
+                 uint32_t rows_per_warp, uint32_t n_probe,
+                 const int32_t *__restrict__ build_pos_sorted, const int32_t *__restrict__ probe_pos,
+                 int32_t *__restrict__ out_build, int32_t *__restrict__ out_probe) {
+    hj_expand_body(gc_by_j, warp_base, rows_per_warp, n_probe, HjLocalBuild{build_pos_sorted}, HjNoOwner{},
+                   probe_pos, out_build, out_probe);
 }
 
 // ---- the same two kernels when the tables live on several contexts ------------------------------
@@ -275,12 +558,15 @@ __device__ __forceinline__ uint32_t hj_owner(uint32_t key, uint32_t route_bits) 
 }
 
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_probe_sharded_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe, const JoinOwners owners,
-                        uint2 *__restrict__ gc_by_j) {
+hj_probe_sharded_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe, uint32_t rows_per_warp,
+                        const JoinOwners owners, uint2 *__restrict__ gc_by_j,
+                        unsigned long long *__restrict__ warp_sums) {
     __shared__ HjOwnersShared so;
     hj_load_owners(owners, so);
-    const uint32_t stride = gridDim.x * HJ_THREADS;
-    for (uint32_t j = blockIdx.x * HJ_THREADS + threadIdx.x; j < n_probe; j += stride) {
+    uint32_t j0, j1;
+    hj_warp_range(rows_per_warp, n_probe, &j0, &j1);
+    unsigned long long acc = 0;
+    for (uint32_t j = j0 + (threadIdx.x & 31); j < j1; j += kWarp) {
         const uint32_t k = (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(pkeys) + j);
         const uint32_t w = hj_owner(k, owners.route_bits);
         const uint32_t part_bits = so.part_bits[w];
@@ -301,53 +587,30 @@ hj_probe_sharded_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe, co
             }
         }
         gc_by_j[j] = r;
+        acc += hj_matches(r.y);
     }
+    hj_warp_sum_out(acc, warp_sums);
 }
 
+struct HjOwnerLists {
+    const HjOwnersShared *so;
+    __device__ __forceinline__ const int32_t *list(uint32_t w) const { return so->bpos[w]; }
+};
+struct HjOwnerOfRow {                                   // whose sorted build list holds row j's group
+    const uint32_t *__restrict__ pkeys;
+    uint32_t route_bits;
+    __device__ __forceinline__ uint32_t operator()(uint32_t j) const { return hj_owner(pkeys[j], route_bits); }
+};
+
 __global__ void __launch_bounds__(HJ_THREADS)
-hj_expand_sharded_kernel(const uint2 *__restrict__ gc_by_j, const uint32_t *__restrict__ off_by_j,
-                         uint32_t n_probe, const uint32_t *__restrict__ pkeys, const JoinOwners owners,
-                         const int32_t *__restrict__ probe_pos, int32_t *__restrict__ out_build,
-                         int32_t *__restrict__ out_probe) {
+hj_expand_sharded_kernel(const uint2 *__restrict__ gc_by_j, const unsigned long long *__restrict__ warp_base,
+                         uint32_t rows_per_warp, uint32_t n_probe, const uint32_t *__restrict__ pkeys,
+                         const JoinOwners owners, const int32_t *__restrict__ probe_pos,
+                         int32_t *__restrict__ out_build, int32_t *__restrict__ out_probe) {
     __shared__ HjOwnersShared so;
     hj_load_owners(owners, so);
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * (HJ_THREADS / kWarp);
-    const uint32_t warp_id = blockIdx.x * (HJ_THREADS / kWarp) + (threadIdx.x >> 5);
-    for (uint32_t j0 = warp_id * kWarp; j0 < n_probe; j0 += warps * kWarp) {
-        const uint32_t j = j0 + lane;
-        uint32_t cnt = 0, gs = 0, off = 0, w = 0;
-        int32_t pp = 0;
-        if (j < n_probe) {
-            const uint2 gc = gc_by_j[j];
-            cnt = gc.y;
-            if (cnt) { gs = gc.x; off = off_by_j[j]; pp = probe_pos[j]; }
-            if (cnt > 1) w = hj_owner(pkeys[j], owners.route_bits);      // whose sorted build list holds the group
-        }
-        if (cnt == 1) {                                  // gs already is the build position
-            out_build[off] = (int32_t)gs;
-            out_probe[off] = pp;
-        } else if (cnt && cnt <= 8) {
-            const int32_t *__restrict__ bp = so.bpos[w];
-            for (uint32_t r = 0; r < cnt; ++r) {
-                out_build[off + r] = bp[gs + r];
-                out_probe[off + r] = pp;
-            }
-        }
-        uint32_t longs = __ballot_sync(kFull, cnt > 8);
-        while (longs) {
-            const int src = __ffs(longs) - 1;
-            longs &= longs - 1;
-            const uint32_t c = __shfl_sync(kFull, cnt, src), g = __shfl_sync(kFull, gs, src);
-            const uint32_t o = __shfl_sync(kFull, off, src), ww = __shfl_sync(kFull, w, src);
-            const int32_t q = __shfl_sync(kFull, pp, src);
-            const int32_t *__restrict__ bp = so.bpos[ww];
-            for (uint32_t r = lane; r < c; r += kWarp) {
-                out_build[o + r] = bp[g + r];
-                out_probe[o + r] = q;
-            }
-        }
-    }
+    hj_expand_body(gc_by_j, warp_base, rows_per_warp, n_probe, HjOwnerLists{&so},
+                   HjOwnerOfRow{pkeys, owners.route_bits}, probe_pos, out_build, out_probe);
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
@@ -357,9 +620,14 @@ int launch_hj_bounds(const uint32_t *keys, uint32_t n, uint32_t part_bits, uint3
     return 1;
 }
 
-int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff, cudaStream_t s) {
-    hj_geometry_kernel<<<1, 1024, 0, s>>>(off1, num_parts, toff);
-    return 1;
+// sums: scratch of (num_parts + 1023) / 1024 + 1 64-bit words
+int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long long *toff,
+                       unsigned long long *sums, cudaStream_t s) {
+    const uint32_t chunks = (num_parts + HJ_GEOM_CHUNK - 1) / HJ_GEOM_CHUNK;
+    hj_geometry_local_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(off1, num_parts, toff, sums);
+    hj_sums_scan_kernel<<<1, 1024, 0, s>>>(sums, chunks, toff + num_parts);
+    hj_geometry_add_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(toff, num_parts, sums);
+    return 3;
 }
 
 int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,
@@ -369,43 +637,89 @@ int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint
     return 1;
 }
 
-int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const unsigned long long *toff,
-                    uint32_t part_bits, const uint4 *table, uint2 *gc_by_j, int sm_count, cudaStream_t s) {
-    if (n_probe == 0) return 0;
-    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
-    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
-    hj_probe_kernel<<<blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, toff, part_bits, table, gc_by_j);
-    return 1;
+HjProbeGeom hj_probe_geom(uint32_t n_probe, int sm_count) {
+    HjProbeGeom pg{};
+    pg.blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
+    if (pg.blocks > (uint32_t)sm_count * 8) pg.blocks = sm_count * 8;
+    if (pg.blocks == 0) pg.blocks = 1;
+    pg.warps = pg.blocks * (HJ_THREADS / kWarp);
+    pg.rows_per_warp = ((n_probe + pg.warps - 1) / pg.warps + kWarp - 1) / kWarp * kWarp;
+    if (pg.rows_per_warp == 0) pg.rows_per_warp = kWarp;
+    return pg;
 }
 
-int launch_hj_expand(const uint2 *gc_by_j, const uint32_t *off_by_j,
+// warp_sums: pg.warps 64-bit words; after the call warp_sums[w] = matches of the warps before w,
+// *total = all matches
+int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &pg, const unsigned long long *toff,
+                    uint32_t part_bits, const uint4 *table, uint2 *gc_by_j, unsigned long long *warp_sums,
+                    unsigned long long *total, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    hj_probe_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, pg.rows_per_warp, toff, part_bits, table,
+                                                     gc_by_j, warp_sums);
+    hj_sums_scan_kernel<<<1, 1024, 0, s>>>(warp_sums, pg.warps, total);
+    return 2;
+}
+
+// The partitioned form of launch_hj_probe (P2 + P3 above; P1 is launch_radix_pass_segmented with
+// RadixPass{24, 8, 1}, payload = row number): pkeys_part / row_part = its outputs, cell_base = its
+// `base`, res_part = n_probe scratch entries.
+// sub_start: (n_probe / 4096 + segs + 1) * 256 words; chunk_sums: pg.warps / 1024 + 2 64-bit words
+int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_part, const uint32_t *cell_base,
+                                uint32_t segs, uint32_t seg_rows, uint32_t n_probe, const HjProbeGeom &pg,
+                                const unsigned long long *toff, uint32_t part_bits, const uint4 *table,
+                                uint2 *res_part, uint32_t *sub_start, uint2 *gc_by_j,
+                                unsigned long long *warp_sums, unsigned long long *chunk_sums,
+                                unsigned long long *total, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    hj_probe_cells_kernel<<<segs * 256, HJ_THREADS, 0, s>>>(pkeys_part, cell_base, segs, seg_rows, n_probe, toff,
+                                                            part_bits, table, res_part);
+    const unsigned long long searches = (unsigned long long)segs * (seg_rows / HJ_SUB + 1) * 256;
+    hj_sub_bounds_kernel<<<(unsigned)((searches + HJ_THREADS - 1) / HJ_THREADS), HJ_THREADS, 0, s>>>(
+        row_part, cell_base, segs, seg_rows, n_probe, sub_start);
+    hj_unpartition_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(row_part, res_part, sub_start, seg_rows, n_probe,
+                                                           gc_by_j, warp_sums);
+    const uint32_t chunks = (pg.warps + HJ_GEOM_CHUNK - 1) / HJ_GEOM_CHUNK;
+    hj_sums_local_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, pg.warps, chunk_sums);
+    hj_sums_scan_kernel<<<1, 1024, 0, s>>>(chunk_sums, chunks, total);
+    hj_geometry_add_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, pg.warps, chunk_sums);
+    return 6;
+}
+
+// the partitioned probe's geometry: one CTA per 4096 probe rows, 512 rows per warp
+HjProbeGeom hj_probe_geom_partitioned(uint32_t n_probe) {
+    HjProbeGeom pg{};
+    pg.blocks = (n_probe + HJ_SUB - 1) / HJ_SUB;
+    if (pg.blocks == 0) pg.blocks = 1;
+    pg.warps = pg.blocks * (HJ_THREADS / kWarp);
+    pg.rows_per_warp = HJ_SUB_WARP;
+    return pg;
+}
+
+int launch_hj_expand(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
-                     int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s) {
+                     int32_t *out_build, int32_t *out_probe, cudaStream_t s) {
     if (n_probe == 0) return 0;
-    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
-    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
-    hj_expand_kernel<<<blocks, HJ_THREADS, 0, s>>>(gc_by_j, off_by_j, n_probe,
-                                                   build_pos_sorted, probe_pos, out_build, out_probe);
+    hj_expand_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(gc_by_j, warp_base, pg.rows_per_warp, n_probe,
+                                                      build_pos_sorted, probe_pos, out_build, out_probe);
     return 1;
 }
 
-int launch_hj_probe_sharded(const uint32_t *pkeys, uint32_t n_probe, const JoinOwners &owners, uint2 *gc_by_j,
-                            int sm_count, cudaStream_t s) {
+int launch_hj_probe_sharded(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &pg, const JoinOwners &owners,
+                            uint2 *gc_by_j, unsigned long long *warp_sums, unsigned long long *total,
+                            cudaStream_t s) {
     if (n_probe == 0) return 0;
-    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
-    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
-    hj_probe_sharded_kernel<<<blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, owners, gc_by_j);
-    return 1;
+    hj_probe_sharded_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, pg.rows_per_warp, owners, gc_by_j,
+                                                             warp_sums);
+    hj_sums_scan_kernel<<<1, 1024, 0, s>>>(warp_sums, pg.warps, total);
+    return 2;
 }
 
-int launch_hj_expand_sharded(const uint2 *gc_by_j, const uint32_t *off_by_j, uint32_t n_probe,
-                             const uint32_t *pkeys, const JoinOwners &owners, const int32_t *probe_pos,
-                             int32_t *out_build, int32_t *out_probe, int sm_count, cudaStream_t s) {
+int launch_hj_expand_sharded(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,
+                             uint32_t n_probe, const uint32_t *pkeys, const JoinOwners &owners,
+                             const int32_t *probe_pos, int32_t *out_build, int32_t *out_probe, cudaStream_t s) {
     if (n_probe == 0) return 0;
-    uint32_t blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
-    if (blocks > (uint32_t)sm_count * 8) blocks = sm_count * 8;
-    hj_expand_sharded_kernel<<<blocks, HJ_THREADS, 0, s>>>(gc_by_j, off_by_j, n_probe, pkeys, owners, probe_pos,
-                                                           out_build, out_probe);
+    hj_expand_sharded_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(gc_by_j, warp_base, pg.rows_per_warp, n_probe, pkeys,
+                                                              owners, probe_pos, out_build, out_probe);
     return 1;
 }
 
@@ -415,8 +729,14 @@ void preload_hash_join() {
     preload_one(reinterpret_cast<const void *>(&hj_probe_sharded_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_expand_sharded_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_expand_kernel));
-    preload_one(reinterpret_cast<const void *>(&hj_geometry_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_geometry_local_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_geometry_add_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_sums_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_probe_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_probe_cells_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_unpartition_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_sub_bounds_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_sums_local_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_table_build_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_bounds_kernel));
 }

@@ -40,7 +40,7 @@ struct RxDigit {
 template <int HASH>
 __global__ void __launch_bounds__(RX_THREADS)
 rx_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t rows_per_cta, RadixPass p,
-               uint32_t *__restrict__ hist /* [bucket][gridDim.x] */) {
+               uint32_t seg_tiles, uint32_t *__restrict__ hist /* [segment][bucket][seg_tiles] */) {
     __shared__ uint32_t s_h[RX_BUCKETS];
     const RxDigit<HASH> digit(p);
     s_h[threadIdx.x] = 0;
@@ -61,14 +61,18 @@ rx_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t rows_per_
             atomicAdd(&s_h[digit(keys[i])], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
+    const uint32_t seg = blockIdx.x / seg_tiles, t = blockIdx.x - seg * seg_tiles;
+    hist[((size_t)seg * RX_BUCKETS + threadIdx.x) * seg_tiles + t] = s_h[threadIdx.x];
 }
 
-// Exclusive scan of every row of a [rows][cols] uint32 matrix in place; row totals out.
+// Exclusive scan of every row of the [segment][bucket][seg_tiles] histogram in place; row totals
+// out.  The last segment may hold fewer than seg_tiles tiles.
 __global__ void __launch_bounds__(1024)
-rx_row_scan_kernel(uint32_t *__restrict__ mat, uint32_t cols, uint32_t *__restrict__ totals) {
+rx_row_scan_kernel(uint32_t *__restrict__ mat, uint32_t seg_tiles, uint32_t tiles, uint32_t *__restrict__ totals) {
     __shared__ uint32_t s_warp[32];
-    uint32_t *row = mat + (size_t)blockIdx.x * cols;
+    uint32_t *row = mat + (size_t)blockIdx.x * seg_tiles;
+    const uint32_t seg = blockIdx.x / RX_BUCKETS;
+    const uint32_t cols = min(seg_tiles, tiles - seg * seg_tiles);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
     for (uint32_t base = 0; base < cols; base += 1024) {
@@ -87,17 +91,43 @@ rx_row_scan_kernel(uint32_t *__restrict__ mat, uint32_t cols, uint32_t *__restri
     if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
-// base[b] = sum of totals[0..b)  (<= 256 buckets, one CTA of 256 threads)
-__global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals, uint32_t *__restrict__ base) {
+// The same for short rows (a segmented pass has 256 x segments rows of a few dozen tiles each:
+// r02y, 65 K CTAs of 1024 threads for two columns took 278 us): one warp per row.
+__global__ void __launch_bounds__(RX_THREADS)
+rx_row_scan_warp_kernel(uint32_t *__restrict__ mat, uint32_t seg_tiles, uint32_t tiles, uint32_t rows,
+                        uint32_t *__restrict__ totals) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * RX_WARPS + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    uint32_t *row = mat + (size_t)r * seg_tiles;
+    const uint32_t seg = r / RX_BUCKETS;
+    const uint32_t cols = min(seg_tiles, tiles - seg * seg_tiles);
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < cols; base += kWarp) {
+        const uint32_t i = base + lane;
+        const uint32_t x = i < cols ? row[i] : 0u;
+        const uint32_t incl = warp_incl_scan(x, lane);
+        if (i < cols) row[i] = carry + incl - x;
+        carry += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) totals[r] = carry;
+}
+
+// base[seg][b] = first row of the segment + sum of totals[seg][0..b)  (one CTA of 256 threads
+// per segment)
+__global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals_all, uint32_t *__restrict__ base_all,
+                                      uint32_t seg_rows) {
     __shared__ uint32_t s_warp[RX_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t *totals = totals_all + blockIdx.x * RX_BUCKETS;
+    uint32_t *base = base_all + blockIdx.x * RX_BUCKETS;
     const uint32_t x = totals[threadIdx.x];
     const uint32_t incl = warp_incl_scan(x, lane);
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     uint32_t wexcl = 0;
     for (uint32_t w = 0; w < warp; ++w) wexcl += s_warp[w];
-    base[threadIdx.x] = wexcl + incl - x;
+    base[threadIdx.x] = blockIdx.x * seg_rows + wexcl + incl - x;
 }
 
 // Stable scatter, one 4096-row tile per CTA.  Warp w owns the contiguous rows
@@ -281,7 +311,8 @@ __device__ __forceinline__ void rx_scatter_tile(RxShared &sh, const uint32_t *__
 template <int HASH, int BITS, bool REMOTE>
 __global__ void __launch_bounds__(RX_THREADS, 4)
 rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
-                  RadixPass p, const uint32_t *__restrict__ hist, const uint32_t *__restrict__ base,
+                  RadixPass p, uint32_t seg_tiles, const uint32_t *__restrict__ hist,
+                  const uint32_t *__restrict__ base,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ pay_out,
                   uint32_t *const *__restrict__ peer_base, unsigned long long key_off,
                   unsigned long long pay_off, const uint32_t *__restrict__ abort_flag) {
@@ -292,7 +323,9 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
         if (threadIdx.x < (1u << p.bits)) sh.peer[threadIdx.x] = peer_base[threadIdx.x];
     }
     // next free global slot of digit `threadIdx.x` for this tile
-    const uint32_t my_off = base[threadIdx.x] + hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    const uint32_t seg = blockIdx.x / seg_tiles, t = blockIdx.x - seg * seg_tiles;
+    const uint32_t my_off = base[seg * RX_BUCKETS + threadIdx.x] +
+                            hist[((size_t)seg * RX_BUCKETS + threadIdx.x) * seg_tiles + t];
     const uint32_t tile = blockIdx.x * RX_TILE;
     if (tile + RX_TILE <= n)
         rx_scatter_tile<HASH, BITS, REMOTE, true>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
@@ -332,27 +365,48 @@ static void rx_set_attributes() {
     done[dev & 63] = true;
 }
 
-static void launch_hist(const uint32_t *keys_in, uint32_t n, const RadixGeom &g, RadixPass p, uint32_t *hist,
-                        cudaStream_t s) {
-    if (p.hash == 1) rx_hist_kernel<1><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
-    else if (p.hash == 2) rx_hist_kernel<2><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
-    else rx_hist_kernel<0><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, hist);
+static void launch_hist(const uint32_t *keys_in, uint32_t n, const RadixGeom &g, RadixPass p, uint32_t seg_tiles,
+                        uint32_t *hist, cudaStream_t s) {
+    if (p.hash == 1) rx_hist_kernel<1><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
+    else if (p.hash == 2) rx_hist_kernel<2><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
+    else rx_hist_kernel<0><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
 }
 
-// scratch: hist = 256 * radix_geom(n).ctas uint32, totals = 256, base = 256
-int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
-                      uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
-                      uint32_t *base, int sm_count, cudaStream_t s) {
+// A pass over consecutive SEGMENTS of seg_tiles tiles each: every segment is partitioned on its
+// own (its rows stay inside its row range), base[seg][d] = first output row of bucket d of
+// segment seg.  seg_tiles >= tiles (or 0) is the plain pass.
+uint32_t radix_segments(uint32_t n, uint32_t seg_tiles) {
+    const uint32_t tiles = (n + RX_TILE - 1) / RX_TILE;
+    if (seg_tiles == 0 || seg_tiles >= tiles) return 1;
+    return (tiles + seg_tiles - 1) / seg_tiles;
+}
+size_t radix_hist_elems(uint32_t n, uint32_t seg_tiles) {
+    const uint32_t tiles = (n + RX_TILE - 1) / RX_TILE;
+    const uint32_t segs = radix_segments(n, seg_tiles);
+    const uint32_t st = segs == 1 ? (tiles ? tiles : 1) : seg_tiles;
+    return (size_t)segs * RX_BUCKETS * st;
+}
+
+// scratch: hist = radix_hist_elems(n, seg_tiles) uint32, totals = base = 256 * radix_segments()
+int launch_radix_pass_segmented(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
+                                uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t seg_tiles, uint32_t *hist,
+                                uint32_t *totals, uint32_t *base, int sm_count, cudaStream_t s) {
     if (n == 0) return 0;
     rx_set_attributes();
     const RadixGeom g = radix_geom(n, sm_count);
-    launch_hist(keys_in, n, g, p, hist, s);
-    rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
-    rx_bucket_base_kernel<<<1, RX_BUCKETS, 0, s>>>(totals, base);
+    const uint32_t segs = radix_segments(n, seg_tiles);
+    if (segs == 1) seg_tiles = g.ctas;
+    launch_hist(keys_in, n, g, p, seg_tiles, hist, s);
+    if (seg_tiles <= 512)
+        rx_row_scan_warp_kernel<<<(segs * RX_BUCKETS + RX_WARPS - 1) / RX_WARPS, RX_THREADS, 0, s>>>(
+            hist, seg_tiles, g.ctas, segs * RX_BUCKETS, totals);
+    else
+        rx_row_scan_kernel<<<segs * RX_BUCKETS, 1024, 0, s>>>(hist, seg_tiles, g.ctas, totals);
+    rx_bucket_base_kernel<<<segs, RX_BUCKETS, 0, s>>>(totals, base, seg_tiles * RX_TILE);
     const size_t sm = sizeof(RxShared);
 #define RX_LAUNCH(H, B)                                                                                       \
-    rx_scatter_kernel<H, B, false><<<g.ctas, RX_THREADS, sm, s>>>(keys_in, pay_in, n, p, hist, base, keys_out, \
-                                                                  pay_out, nullptr, 0, 0, nullptr)
+    rx_scatter_kernel<H, B, false><<<g.ctas, RX_THREADS, sm, s>>>(keys_in, pay_in, n, p, seg_tiles, hist, base, \
+                                                                  keys_out, pay_out, nullptr, 0, 0, nullptr)
     if (p.hash == 0 && p.bits == 8) RX_LAUNCH(0, 8);
     else if (p.hash == 1 && p.bits == 8) RX_LAUNCH(1, 8);
     else if (p.hash == 0) RX_LAUNCH(0, 0);
@@ -362,6 +416,12 @@ int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t 
     return 4;
 }
 
+int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
+                      uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
+                      uint32_t *base, int sm_count, cudaStream_t s) {
+    return launch_radix_pass_segmented(keys_in, pay_in, keys_out, pay_out, n, p, 0, hist, totals, base, sm_count, s);
+}
+
 int launch_radix_hist(const uint32_t *keys_in, uint32_t n, RadixPass p, uint32_t *hist, uint32_t *totals,
                       int sm_count, cudaStream_t s) {
     if (n == 0) {
@@ -369,8 +429,8 @@ int launch_radix_hist(const uint32_t *keys_in, uint32_t n, RadixPass p, uint32_t
         return 0;
     }
     const RadixGeom g = radix_geom(n, sm_count);
-    launch_hist(keys_in, n, g, p, hist, s);
-    rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, totals);
+    launch_hist(keys_in, n, g, p, g.ctas, hist, s);
+    rx_row_scan_kernel<<<RX_BUCKETS, 1024, 0, s>>>(hist, g.ctas, g.ctas, totals);
     return 2;
 }
 
@@ -383,7 +443,7 @@ int launch_radix_scatter_remote(const uint32_t *keys_in, const uint32_t *pay_in,
     rx_set_attributes();
     const RadixGeom g = radix_geom(n, sm_count);
     rx_scatter_kernel<2, 0, true><<<g.ctas, RX_THREADS, sizeof(RxShared), s>>>(
-        keys_in, pay_in, n, p, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
+        keys_in, pay_in, n, p, g.ctas, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
     return 1;
 }
 
@@ -469,6 +529,7 @@ void preload_radix() {
     { auto *fp = &rx_hist_kernel<1>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &rx_hist_kernel<2>; preload_one(reinterpret_cast<const void *>(fp)); }
     preload_one(reinterpret_cast<const void *>(&rx_row_scan_kernel));
+    preload_one(reinterpret_cast<const void *>(&rx_row_scan_warp_kernel));
     preload_one(reinterpret_cast<const void *>(&rx_bucket_base_kernel));
     { auto *fp = &rx_scatter_kernel<0, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &rx_scatter_kernel<1, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }

@@ -20,6 +20,15 @@ def eng():
     e.close()
 
 
+@pytest.fixture(params=["direct", "partitioned"])
+def probe_mode(request, monkeypatch):
+    """Both forms of the probe on the same inputs: rows in their original order (one random slot
+    read each) and rows partitioned by window and table slice (hash_join.cu, P1-P3) -- the engine
+    picks by size, ADB_JOIN_PROBE forces."""
+    monkeypatch.setenv("ADB_JOIN_PROBE", request.param)
+    return request.param
+
+
 def run_join(eng, k1, p1, k2, p2, nested=False):
     d = [eng.upload(x) for x in (k1, p1, k2, p2)]
     o1, o2, m = eng.join(d[0], d[1], k1.size, d[2], d[3], k2.size, nested_loop=nested)
@@ -50,7 +59,7 @@ def inputs(rng, n1, n2, kind):
 @pytest.mark.parametrize("kind", ["uniform", "unique", "zipf", "negative"])
 @pytest.mark.parametrize("n1,n2", [(1, 1), (4, 1), (100, 7), (2000, 1500), (1500, 0), (0, 9),
                                    (5000, 5000), (40000, 9000)])
-def test_hash_join_order(eng, port, rng, kind, n1, n2):
+def test_hash_join_order(eng, port, rng, probe_mode, kind, n1, n2):
     if kind == "zipf" and n1 * n2 > 3e7:
         n2 = 2000                                  # keep the many-many blow-up bounded
     k1, p1, k2, p2 = inputs(rng, n1, n2, kind)
@@ -62,21 +71,21 @@ def test_hash_join_order(eng, port, rng, kind, n1, n2):
 
 @pytest.mark.parametrize("kind", ["uniform", "zipf"])
 @pytest.mark.parametrize("n1,n2", [(1, 1), (300, 200), (1500, 1500), (1500, 0)])
-def test_nested_loop_join_order(eng, port, rng, kind, n1, n2):
+def test_nested_loop_join_order(eng, port, rng, probe_mode, kind, n1, n2):
     k1, p1, k2, p2 = inputs(rng, n1, n2, kind)
     a, b = run_join(eng, k1, p1, k2, p2, nested=True)
     e1, e2 = port.nested_loop_join(k1, p1, k2, p2)
     assert np.array_equal(a, e1) and np.array_equal(b, e2), (kind, n1, n2)
 
 
-def test_hash_join_vs_reference_objects(eng, ref, rng):
+def test_hash_join_vs_reference_objects(eng, ref, rng, probe_mode):
     k1, p1, k2, p2 = inputs(rng, 30000, 20000, "uniform")
     a, b = run_join(eng, k1, p1, k2, p2)
     e1, e2 = ref.hash_join(k1, p1, k2, p2)
     assert np.array_equal(a, e1) and np.array_equal(b, e2)
 
 
-def test_hash_join_skewed_partition(eng, port, rng):
+def test_hash_join_skewed_partition(eng, port, rng, probe_mode):
     """One key owns 40 % of the build side: its partition overflows the shared-memory table
     and takes the global-memory path; the probe side hits it a few times."""
     n1, n2 = 60000, 300
@@ -91,7 +100,7 @@ def test_hash_join_skewed_partition(eng, port, rng):
     assert np.array_equal(a, e1) and np.array_equal(b, e2)
 
 
-def test_hash_join_multi_pass_partitioning(eng, port, rng):
+def test_hash_join_multi_pass_partitioning(eng, port, rng, probe_mode):
     """3 M x 2 M many-one join: 12 partition bits (two probe passes).  Keys stay below the
     reference's table size (1.3 n1): its identity hash `key % size` (multimap.c:60-63) wraps
     larger keys onto an already full region and the CPU probe goes quadratic."""
