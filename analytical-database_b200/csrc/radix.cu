@@ -21,6 +21,7 @@ namespace adb {
 constexpr int RX_THREADS = 256;
 constexpr int RX_WARPS = RX_THREADS / kWarp;
 constexpr int RX_BUCKETS = 256;
+constexpr int RX_DEFAULT_THREADS = 256;
 
 // f(key) of RadixPass::hash; the digit is (f >> shift) & mask.  For the signed order (HASH 0)
 // the sign flip is folded into one constant xor-ed onto the extracted digit.
@@ -155,15 +156,16 @@ __global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals_all, u
 // NVLink (peer_base[d] + key_off / pay_off) instead of one local output array; `base` then
 // holds the offset of this rank's piece inside every destination buffer.  The run-contiguous
 // write-out is what makes the remote stores full 128-byte transactions.
-constexpr int RX_KPT = 16;
-constexpr int RX_TILE = RX_THREADS * RX_KPT;             // 4096 rows
-
+constexpr int RX_TILE = 4096;                            // rows per tile = CTA threads x keys per thread
+// CTA shape: T threads of 4096 / T keys each.  256 x 16: 64 registers, 56 KB -> 4 CTAs = 32 warps
+// per SM; 512 x 8: 40 registers, 60 KB -> 3 CTAs = 48 warps per SM (ADB_RX_THREADS picks; r02zc).
+template <int T>
 struct RxShared {
     uint2 kv[RX_TILE];                                   // tile-sorted {key, payload}
     uint32_t pay_in[RX_TILE];                            // the tile's payloads in row order (cp.async)
-    uint16_t wcnt[RX_WARPS][RX_BUCKETS];                 // per-warp digit counts -> first slot of (warp, digit)
+    uint16_t wcnt[T / kWarp][RX_BUCKETS];                // per-warp digit counts -> first slot of (warp, digit)
     uint32_t gofs[RX_BUCKETS];                           // global address = gofs[d] + tile slot
-    uint32_t ws[RX_WARPS];
+    uint32_t ws[RX_BUCKETS / kWarp];
     uint32_t *peer[kMaxPeers];
 };
 
@@ -192,12 +194,13 @@ __device__ __forceinline__ uint32_t rx_match_bit(uint32_t peers, uint32_t d, uin
     return peers;
 }
 
-template <int HASH, int BITS, bool REMOTE, bool FULL>
-__device__ __forceinline__ void rx_scatter_tile(RxShared &sh, const uint32_t *__restrict__ keys,
+template <int T, int HASH, int BITS, bool REMOTE, bool FULL>
+__device__ __forceinline__ void rx_scatter_tile(RxShared<T> &sh, const uint32_t *__restrict__ keys,
                                                 const uint32_t *__restrict__ pay, uint32_t tile, uint32_t end,
                                                 const RadixPass &p, uint32_t my_off, uint32_t *__restrict__ keys_out,
                                                 uint32_t *__restrict__ pay_out, unsigned long long key_off,
                                                 unsigned long long pay_off) {
+    constexpr int RX_KPT = RX_TILE / T, RX_THREADS = T, RX_WARPS = T / kWarp;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const RxDigit<HASH> digit(p);
     const uint32_t lt = (1u << lane) - 1u;
@@ -261,22 +264,28 @@ __device__ __forceinline__ void rx_scatter_tile(RxShared &sh, const uint32_t *__
         if (live) dr[i] = d | ((before + r) << 8);
     }
     __syncthreads();
-    // 2. digit `threadIdx.x`: exclusive prefix over the warps, then over the digits
+    // 2. digit `threadIdx.x` (the first 256 threads): exclusive prefix over the warps, then over
+    //    the digits
     {
+        const bool digit_thread = T == RX_BUCKETS || threadIdx.x < RX_BUCKETS;
         uint32_t c[RX_WARPS], tot = 0;
+        if (digit_thread) {
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; ++w) { c[w] = sh.wcnt[w][threadIdx.x]; tot += c[w]; }
+            for (int w = 0; w < RX_WARPS; ++w) { c[w] = sh.wcnt[w][threadIdx.x]; tot += c[w]; }
+        }
         const uint32_t incl = warp_incl_scan(tot, lane);
-        if (lane == 31) sh.ws[warp] = incl;
+        if (digit_thread && lane == 31) sh.ws[warp] = incl;
         __syncthreads();
-        uint32_t wexcl = 0;
+        if (digit_thread) {
+            uint32_t wexcl = 0;
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; ++w) wexcl += (uint32_t)w < warp ? sh.ws[w] : 0u;
-        const uint32_t tbase = wexcl + incl - tot;          // first tile slot of this digit
-        sh.gofs[threadIdx.x] = my_off - tbase;              // modular: slot >= tbase for this digit
-        uint32_t run = tbase;
+            for (int w = 0; w < RX_BUCKETS / kWarp; ++w) wexcl += (uint32_t)w < warp ? sh.ws[w] : 0u;
+            const uint32_t tbase = wexcl + incl - tot;      // first tile slot of this digit
+            sh.gofs[threadIdx.x] = my_off - tbase;          // modular: slot >= tbase for this digit
+            uint32_t run = tbase;
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; ++w) { sh.wcnt[w][threadIdx.x] = (uint16_t)run; run += c[w]; }
+            for (int w = 0; w < RX_WARPS; ++w) { sh.wcnt[w][threadIdx.x] = (uint16_t)run; run += c[w]; }
+        }
     }
     if (pay) cp_async_wait_all();
     __syncthreads();
@@ -308,8 +317,8 @@ __device__ __forceinline__ void rx_scatter_tile(RxShared &sh, const uint32_t *__
     }
 }
 
-template <int HASH, int BITS, bool REMOTE>
-__global__ void __launch_bounds__(RX_THREADS, 4)
+template <int T, int HASH, int BITS, bool REMOTE>
+__global__ void __launch_bounds__(T, T == 256 ? 4 : 3)
 rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
                   RadixPass p, uint32_t seg_tiles, const uint32_t *__restrict__ hist,
                   const uint32_t *__restrict__ base,
@@ -317,20 +326,22 @@ rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict_
                   uint32_t *const *__restrict__ peer_base, unsigned long long key_off,
                   unsigned long long pay_off, const uint32_t *__restrict__ abort_flag) {
     extern __shared__ __align__(16) unsigned char rx_smem[];
-    RxShared &sh = *reinterpret_cast<RxShared *>(rx_smem);
+    RxShared<T> &sh = *reinterpret_cast<RxShared<T> *>(rx_smem);
     if (REMOTE) {
         if (*abort_flag) return;                            // a receive region would overflow
         if (threadIdx.x < (1u << p.bits)) sh.peer[threadIdx.x] = peer_base[threadIdx.x];
     }
     // next free global slot of digit `threadIdx.x` for this tile
     const uint32_t seg = blockIdx.x / seg_tiles, t = blockIdx.x - seg * seg_tiles;
-    const uint32_t my_off = base[seg * RX_BUCKETS + threadIdx.x] +
-                            hist[((size_t)seg * RX_BUCKETS + threadIdx.x) * seg_tiles + t];
+    uint32_t my_off = 0;
+    if (T == RX_BUCKETS || threadIdx.x < RX_BUCKETS)
+        my_off = base[seg * RX_BUCKETS + threadIdx.x] +
+                 hist[((size_t)seg * RX_BUCKETS + threadIdx.x) * seg_tiles + t];
     const uint32_t tile = blockIdx.x * RX_TILE;
     if (tile + RX_TILE <= n)
-        rx_scatter_tile<HASH, BITS, REMOTE, true>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
+        rx_scatter_tile<T, HASH, BITS, REMOTE, true>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
     else
-        rx_scatter_tile<HASH, BITS, REMOTE, false>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
+        rx_scatter_tile<T, HASH, BITS, REMOTE, false>(sh, keys, pay, tile, n, p, my_off, keys_out, pay_out, key_off, pay_off);
 }
 
 // One CTA per 4096-row tile, launched in row order: the CTAs resident at any moment work on
@@ -346,9 +357,17 @@ RadixGeom radix_geom(uint32_t n, int sm_count) {
     return g;
 }
 
-template <class K>
-static void rx_allow_smem(K *kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RxShared));
+template <int T>
+static void rx_set_attributes_shape() {
+    auto allow = [](auto *kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RxShared<T>));
+    };
+    allow(&rx_scatter_kernel<T, 0, 8, false>);
+    allow(&rx_scatter_kernel<T, 1, 8, false>);
+    allow(&rx_scatter_kernel<T, 0, 0, false>);
+    allow(&rx_scatter_kernel<T, 1, 0, false>);
+    allow(&rx_scatter_kernel<T, 2, 0, false>);
+    allow(&rx_scatter_kernel<T, 2, 0, true>);
 }
 // function attributes are per device: once per device the engine launches on
 static void rx_set_attributes() {
@@ -356,13 +375,33 @@ static void rx_set_attributes() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (done[dev & 63]) return;
-    rx_allow_smem(&rx_scatter_kernel<0, 8, false>);
-    rx_allow_smem(&rx_scatter_kernel<1, 8, false>);
-    rx_allow_smem(&rx_scatter_kernel<0, 0, false>);
-    rx_allow_smem(&rx_scatter_kernel<1, 0, false>);
-    rx_allow_smem(&rx_scatter_kernel<2, 0, false>);
-    rx_allow_smem(&rx_scatter_kernel<2, 0, true>);
+    rx_set_attributes_shape<256>();
+    rx_set_attributes_shape<512>();
     done[dev & 63] = true;
+}
+static int rx_threads() {
+    static int t = 0;
+    if (!t) {
+        const char *e = getenv("ADB_RX_THREADS");
+        t = e && atoi(e) == 512 ? 512 : e && atoi(e) == 256 ? 256 : RX_DEFAULT_THREADS;
+    }
+    return t;
+}
+
+template <int T>
+static void rx_launch_scatter(uint32_t ctas, const uint32_t *keys_in, const uint32_t *pay_in, uint32_t n, RadixPass p,
+                              uint32_t seg_tiles, const uint32_t *hist, const uint32_t *base, uint32_t *keys_out,
+                              uint32_t *pay_out, cudaStream_t s) {
+    const size_t sm = sizeof(RxShared<T>);
+#define RX_LAUNCH(H, B)                                                                                      \
+    rx_scatter_kernel<T, H, B, false><<<ctas, T, sm, s>>>(keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, \
+                                                          pay_out, nullptr, 0, 0, nullptr)
+    if (p.hash == 0 && p.bits == 8) RX_LAUNCH(0, 8);
+    else if (p.hash == 1 && p.bits == 8) RX_LAUNCH(1, 8);
+    else if (p.hash == 0) RX_LAUNCH(0, 0);
+    else if (p.hash == 1) RX_LAUNCH(1, 0);
+    else RX_LAUNCH(2, 0);
+#undef RX_LAUNCH
 }
 
 static void launch_hist(const uint32_t *keys_in, uint32_t n, const RadixGeom &g, RadixPass p, uint32_t seg_tiles,
@@ -403,16 +442,10 @@ int launch_radix_pass_segmented(const uint32_t *keys_in, const uint32_t *pay_in,
     else
         rx_row_scan_kernel<<<segs * RX_BUCKETS, 1024, 0, s>>>(hist, seg_tiles, g.ctas, totals);
     rx_bucket_base_kernel<<<segs, RX_BUCKETS, 0, s>>>(totals, base, seg_tiles * RX_TILE);
-    const size_t sm = sizeof(RxShared);
-#define RX_LAUNCH(H, B)                                                                                       \
-    rx_scatter_kernel<H, B, false><<<g.ctas, RX_THREADS, sm, s>>>(keys_in, pay_in, n, p, seg_tiles, hist, base, \
-                                                                  keys_out, pay_out, nullptr, 0, 0, nullptr)
-    if (p.hash == 0 && p.bits == 8) RX_LAUNCH(0, 8);
-    else if (p.hash == 1 && p.bits == 8) RX_LAUNCH(1, 8);
-    else if (p.hash == 0) RX_LAUNCH(0, 0);
-    else if (p.hash == 1) RX_LAUNCH(1, 0);
-    else RX_LAUNCH(2, 0);
-#undef RX_LAUNCH
+    if (rx_threads() == 512)
+        rx_launch_scatter<512>(g.ctas, keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, pay_out, s);
+    else
+        rx_launch_scatter<256>(g.ctas, keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, pay_out, s);
     return 4;
 }
 
@@ -442,8 +475,12 @@ int launch_radix_scatter_remote(const uint32_t *keys_in, const uint32_t *pay_in,
     if (p.hash != 2) return -1;                              // the routing hash is the only remote user
     rx_set_attributes();
     const RadixGeom g = radix_geom(n, sm_count);
-    rx_scatter_kernel<2, 0, true><<<g.ctas, RX_THREADS, sizeof(RxShared), s>>>(
-        keys_in, pay_in, n, p, g.ctas, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
+    if (rx_threads() == 512)
+        rx_scatter_kernel<512, 2, 0, true><<<g.ctas, 512, sizeof(RxShared<512>), s>>>(
+            keys_in, pay_in, n, p, g.ctas, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
+    else
+        rx_scatter_kernel<256, 2, 0, true><<<g.ctas, 256, sizeof(RxShared<256>), s>>>(
+            keys_in, pay_in, n, p, g.ctas, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
     return 1;
 }
 
@@ -531,12 +568,15 @@ void preload_radix() {
     preload_one(reinterpret_cast<const void *>(&rx_row_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&rx_row_scan_warp_kernel));
     preload_one(reinterpret_cast<const void *>(&rx_bucket_base_kernel));
-    { auto *fp = &rx_scatter_kernel<0, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }
-    { auto *fp = &rx_scatter_kernel<1, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }
-    { auto *fp = &rx_scatter_kernel<0, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
-    { auto *fp = &rx_scatter_kernel<1, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
-    { auto *fp = &rx_scatter_kernel<2, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
-    { auto *fp = &rx_scatter_kernel<2, 0, true>; preload_one(reinterpret_cast<const void *>(fp)); }
+#define RX_PRELOAD(T)                                                                                        \
+    { auto *fp = &rx_scatter_kernel<T, 0, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
+    { auto *fp = &rx_scatter_kernel<T, 1, 8, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
+    { auto *fp = &rx_scatter_kernel<T, 0, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
+    { auto *fp = &rx_scatter_kernel<T, 1, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
+    { auto *fp = &rx_scatter_kernel<T, 2, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
+    { auto *fp = &rx_scatter_kernel<T, 2, 0, true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    if (rx_threads() == 512) { RX_PRELOAD(512) } else { RX_PRELOAD(256) }
+#undef RX_PRELOAD
     preload_one(reinterpret_cast<const void *>(&sc_chunk_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&sc_chunk_sum_kernel));
     rx_set_attributes();
