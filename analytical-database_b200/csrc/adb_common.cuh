@@ -504,6 +504,7 @@ int launch_radix_pass(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t 
 // partitioned probe: segments = probe-row windows, buckets = table partitions).  totals and
 // base: 256 * radix_segments() words, hist: radix_hist_elems() words.
 uint32_t radix_segments(uint32_t n, uint32_t seg_tiles);
+uint32_t radix_seg_tiles(uint32_t n, uint32_t seg_tiles);   // tiles per segment the pass really uses (all of them when unsegmented)
 size_t radix_hist_elems(uint32_t n, uint32_t seg_tiles);
 int launch_radix_pass_segmented(const uint32_t *keys_in, const uint32_t *pay_in, uint32_t *keys_out,
                                 uint32_t *pay_out, uint32_t n, RadixPass p, uint32_t seg_tiles, uint32_t *hist,
@@ -564,11 +565,12 @@ int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &
 // Probe side partitioned for L2 locality (hash_join.cu): pkeys_part / row_part / cell_base come
 // from launch_radix_pass_segmented(probe keys, NULL, ..., RadixPass{24, 8, 1}, seg_tiles).
 HjProbeGeom hj_probe_geom_partitioned(uint32_t n_probe);   // one CTA per 4096 rows (its pg goes to the expansion too)
-// sub_start: (n_probe / 4096 + segs + 1) * 256 words; chunk_sums: pg.warps / 1024 + 2 64-bit words
+// cell_base / hist / seg_tiles: the segmented pass' base, scanned histogram and effective tiles per
+// window (radix_seg_tiles); chunk_sums: pg.warps / 1024 + 2 64-bit words
 int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_part, const uint32_t *cell_base,
-                                uint32_t segs, uint32_t seg_rows, uint32_t n_probe, const HjProbeGeom &pg,
-                                const unsigned long long *toff, uint32_t part_bits, const uint4 *table,
-                                uint2 *res_part, uint32_t *sub_start, uint2 *gc_by_j,
+                                const uint32_t *hist, uint32_t segs, uint32_t seg_tiles, uint32_t n_probe,
+                                const HjProbeGeom &pg, const unsigned long long *toff, uint32_t part_bits,
+                                const uint4 *table, uint2 *res_part, uint2 *gc_by_j,
                                 unsigned long long *warp_sums, unsigned long long *chunk_sums,
                                 unsigned long long *total, cudaStream_t s);
 int launch_hj_expand(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,

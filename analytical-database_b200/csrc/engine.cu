@@ -2121,9 +2121,8 @@ static bool join_probe_partitioned(uint32_t nb, uint32_t np) {
     return nb >= (6u << 20) && np >= (4u << 20);
 }
 static size_t join_partition_scratch(uint32_t np) {      // keys + row numbers + results in partition order,
-    return 2 * arena_round((size_t)np * 4) + arena_round((size_t)np * 8) +      // 8 piece sums per 4096 rows,
-           arena_round(((size_t)np / 4096 + 2) * 8 * 8) +                          // the cells' sub-window starts
-           arena_round(((size_t)np / 4096 + (size_t)np / (4096 * 256) + 520) * 256 * 4) + 4096;
+    return 2 * arena_round((size_t)np * 4) + arena_round((size_t)np * 8) +      // 8 piece sums per 4096 rows
+           arena_round(((size_t)np / 4096 + 2) * 8 * 8) + 4096;
 }
 
 static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, uint32_t np, int *launches,
@@ -2214,19 +2213,21 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     if (partitioned) {
         // <= 256 windows of whole 4096-row tiles, each partitioned on the top 8 hash bits
         const uint32_t tiles = (np + 4095) / 4096;
-        const uint32_t seg_tiles = (tiles + 255) / 256;
-        const uint32_t segs = adb::radix_segments(np, seg_tiles);
+        const uint32_t want_tiles = (tiles + 255) / 256;
+        const uint32_t segs = adb::radix_segments(np, want_tiles);
+        const uint32_t seg_tiles = adb::radix_seg_tiles(np, want_tiles);
         uint32_t *pk = ARENA_TAKE(uint32_t, np), *rows = ARENA_TAKE(uint32_t, np);
         uint2 *res = ARENA_TAKE(uint2, np);
-        uint32_t *sub_start = ARENA_TAKE(uint32_t, ((size_t)segs * (seg_tiles + 1) + 1) * 256);
         unsigned long long *chunk_sums = ARENA_TAKE(unsigned long long, j.pg.warps / 1024 + 2);
         launches += adb::launch_radix_pass_segmented(reinterpret_cast<const uint32_t *>(pv), nullptr, pk, rows, np,
-                                                     adb::RadixPass{24, 8, 1}, seg_tiles, g.rx_hist, g.rx_totals,
+                                                     adb::RadixPass{24, 8, 1}, want_tiles, g.rx_hist, g.rx_totals,
                                                      g.rx_base, g.sm_count, g.stream);
         tr.lap("probe rows by window and table slice");
-        launches += adb::launch_hj_probe_partitioned(pk, rows, g.rx_base, segs, seg_tiles * 4096, np, j.pg, j.toff,
-                                                     j.part_bits, static_cast<const uint4 *>(g.hj_table), res,
-                                                     sub_start, j.gc_by_j, j.warp_base, chunk_sums, tot, g.stream);
+        // (the pass' scanned histogram stays in g.rx_hist: where each 4096-row tile's entries
+        // sit inside the cells)
+        launches += adb::launch_hj_probe_partitioned(pk, rows, g.rx_base, g.rx_hist, segs, seg_tiles, np, j.pg,
+                                                     j.toff, j.part_bits, static_cast<const uint4 *>(g.hj_table),
+                                                     res, j.gc_by_j, j.warp_base, chunk_sums, tot, g.stream);
     } else {
         launches += adb::launch_hj_probe(reinterpret_cast<const uint32_t *>(pv), np, j.pg, j.toff, j.part_bits,
                                          static_cast<const uint4 *>(g.hj_table), j.gc_by_j, j.warp_base, tot,

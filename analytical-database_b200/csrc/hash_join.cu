@@ -22,12 +22,14 @@
 //      position to out2[off[j] ..]; long groups (skewed keys) are spread over a warp.
 // Partitions too large for the shared-memory table (heavy skew) build directly in their
 // global slots.
+#include <cstdlib>
+#include <cstring>
+
 #include "adb_common.cuh"
 
 namespace adb {
 
 constexpr int HJ_THREADS = 256;
-constexpr uint32_t HJ_SLOTS = 4096;                    // shared-memory table slots
 constexpr uint32_t kHashMul = 0x9E3779B1u;
 
 __device__ __forceinline__ uint32_t hj_pid(uint32_t key, uint32_t part_bits) {
@@ -192,11 +194,17 @@ __device__ __forceinline__ uint32_t hj_mix(uint32_t tag) {
 // adds 1 to the size, the group leader (first row of the run of equal keys) adds its offset
 // in the same atomic -- and stream the finished table out.  Larger partitions (heavy skew)
 // run the same steps directly on their global slots.
-__global__ void __launch_bounds__(HJ_THREADS)
+// CTA shape (r02za: 256 threads around a 4096-slot table = 32 KB kept 7 CTAs per SM resident
+// and the kernel, a string of dependent round trips per partition, ran at 2.9 TB/s): partitions
+// average <= 1024 rows, i.e. <= 2048 slots, so the default is 128 threads around 2048 slots
+// (16 KB, 14 CTAs per SM); the few larger partitions take the global-memory path.
+template <int THREADS, uint32_t SLOTS>
+__global__ void __launch_bounds__(THREADS)
 hj_table_build_kernel(const uint32_t *__restrict__ bkeys /* sorted by hash */,
                       const int32_t *__restrict__ bpos /* build positions in the same order */,
                       const uint32_t *__restrict__ off1, const unsigned long long *__restrict__ toff,
                       uint32_t part_bits, uint4 *__restrict__ table) {
+    constexpr uint32_t HJ_THREADS = THREADS, HJ_SLOTS = SLOTS;    // shared-memory table slots
     __shared__ uint32_t s_tag[HJ_SLOTS];
     __shared__ uint32_t s_gc[HJ_SLOTS];                 // {group start within the partition : 16, size : 16}
     const uint32_t p = blockIdx.x;
@@ -317,6 +325,28 @@ hj_probe_kernel(const uint32_t *__restrict__ pkeys, uint32_t n_probe, uint32_t r
 //       belong to one window, i.e. to a 3 MB piece of the result array, so these scattered
 //       8-byte stores meet in L2 and leave it as full sectors (r01k's scatter straight from the
 //       partitions was a 32-byte read-modify-write in DRAM per row: 1.8 TB/s of traffic).
+// A row is a chain of dependent loads (key -> slot range of its table partition -> slot); a
+// thread keeps two rows in flight and loads the keys of the next two before it resolves the
+// current ones.  (r02zd: four rows per thread without the look-ahead made the kernel slower,
+// 0.92 -> 1.17 ms -- cells are ~1500 rows, the last trip of a CTA then runs half empty; r02ze:
+// asking L2 for the next table slice with prefetch.global.L2, one line per thread in address
+// order, changed nothing: 0.92 ms, +0.3 GB of DRAM reads.)
+__device__ __forceinline__ uint2 hj_lookup(uint32_t k, const unsigned long long *__restrict__ toff,
+                                           uint32_t part_bits, const uint4 *__restrict__ table) {
+    const uint32_t pid = hj_pid(k, part_bits);
+    const unsigned long long t0 = toff[pid], cap = toff[pid + 1] - t0;
+    if (!cap) return make_uint2(0u, 0u);
+    const uint32_t tag = hj_tag(k, part_bits);
+    const unsigned long long mask = cap - 1;
+    unsigned long long s = hj_mix(tag) & mask;
+    while (true) {
+        const uint4 sl = ld_gather(table + t0 + s);
+        if (sl.x == tag) return make_uint2(sl.y, sl.z);
+        if (sl.x == 0u) return make_uint2(0u, 0u);
+        s = (s + 1) & mask;
+    }
+}
+
 __global__ void __launch_bounds__(HJ_THREADS)
 hj_probe_cells_kernel(const uint32_t *__restrict__ pkeys_part, const uint32_t *__restrict__ cell_base,
                       uint32_t segs, uint32_t seg_rows, uint32_t n_probe,
@@ -326,23 +356,42 @@ hj_probe_cells_kernel(const uint32_t *__restrict__ pkeys_part, const uint32_t *_
     const uint32_t b = cell_base[w * 256 + p];
     const unsigned long long seg_end = (unsigned long long)(w + 1) * seg_rows;
     const uint32_t e = p < 255 ? cell_base[w * 256 + p + 1] : (uint32_t)(seg_end < n_probe ? seg_end : n_probe);
-    for (uint32_t i = b + threadIdx.x; i < e; i += HJ_THREADS) {
-        const uint32_t k = (uint32_t)ld_stream(reinterpret_cast<const int32_t *>(pkeys_part) + i);
-        const uint32_t pid = hj_pid(k, part_bits);
-        const unsigned long long t0 = toff[pid], cap = toff[pid + 1] - t0;
-        uint2 r = make_uint2(0u, 0u);
-        if (cap) {
-            const uint32_t tag = hj_tag(k, part_bits);
-            const unsigned long long mask = cap - 1;
-            unsigned long long s = hj_mix(tag) & mask;
-            while (true) {
-                const uint4 sl = ld_gather(table + t0 + s);
-                if (sl.x == tag) { r = make_uint2(sl.y, sl.z); break; }
-                if (sl.x == 0u) break;
-                s = (s + 1) & mask;
-            }
+    const int32_t *__restrict__ pk = reinterpret_cast<const int32_t *>(pkeys_part);
+    uint32_t i = b + threadIdx.x;
+    uint32_t k0 = i < e ? (uint32_t)ld_stream(pk + i) : 0u;
+    uint32_t k1 = i + HJ_THREADS < e ? (uint32_t)ld_stream(pk + i + HJ_THREADS) : 0u;
+    while (i < e) {
+        const uint32_t i2 = i + 2 * HJ_THREADS;
+        const uint32_t n0 = i2 < e ? (uint32_t)ld_stream(pk + i2) : 0u;
+        const uint32_t n1 = i2 + HJ_THREADS < e ? (uint32_t)ld_stream(pk + i2 + HJ_THREADS) : 0u;
+        const bool two = i + HJ_THREADS < e;
+        // both rows' first loads are issued before either is waited for
+        const uint32_t pid0 = hj_pid(k0, part_bits), pid1 = hj_pid(k1, part_bits);
+        const unsigned long long a0 = toff[pid0], c0 = toff[pid0 + 1] - a0;
+        const unsigned long long a1 = two ? toff[pid1] : 0ull, c1 = two ? toff[pid1 + 1] - a1 : 0ull;
+        const uint32_t tag0 = hj_tag(k0, part_bits), tag1 = hj_tag(k1, part_bits);
+        unsigned long long s0 = c0 ? hj_mix(tag0) & (c0 - 1) : 0ull, s1 = c1 ? hj_mix(tag1) & (c1 - 1) : 0ull;
+        uint4 sl0 = make_uint4(0u, 0u, 0u, 0u), sl1 = sl0;
+        if (c0) sl0 = ld_gather(table + a0 + s0);
+        if (c1) sl1 = ld_gather(table + a1 + s1);
+        uint2 r0 = make_uint2(0u, 0u), r1 = r0;
+        while (c0) {                                        // linear probing past the first slot is rare
+            if (sl0.x == tag0) { r0 = make_uint2(sl0.y, sl0.z); break; }
+            if (sl0.x == 0u) break;
+            s0 = (s0 + 1) & (c0 - 1);
+            sl0 = ld_gather(table + a0 + s0);
         }
-        res_part[i] = r;
+        while (c1) {
+            if (sl1.x == tag1) { r1 = make_uint2(sl1.y, sl1.z); break; }
+            if (sl1.x == 0u) break;
+            s1 = (s1 + 1) & (c1 - 1);
+            sl1 = ld_gather(table + a1 + s1);
+        }
+        res_part[i] = r0;
+        if (two) res_part[i + HJ_THREADS] = r1;
+        i = i2;
+        k0 = n0;
+        k1 = n1;
     }
 }
 
@@ -354,7 +403,7 @@ hj_probe_cells_kernel(const uint32_t *__restrict__ pkeys_part, const uint32_t *_
 // ascend inside a cell: two binary searches per cell, ~16 entries each), parks the results in
 // shared memory by row and writes them out as whole lines.  Its eight warps are the expansion's
 // pieces (512 rows each): their match counts go to warp_sums.
-constexpr uint32_t HJ_SUB = 4096;
+constexpr uint32_t HJ_SUB = 4096;                     // = the radix pass' tile (radix.cu RX_TILE)
 constexpr uint32_t HJ_SUB_WARP = HJ_SUB / (HJ_THREADS / kWarp);
 
 __device__ __forceinline__ uint32_t hj_lower_bound(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t v) {
@@ -365,42 +414,34 @@ __device__ __forceinline__ uint32_t hj_lower_bound(const uint32_t *__restrict__ 
     return lo;
 }
 
-// sub_start[(w * (subs + 1) + k) * 256 + p] = first entry of cell (w, p) whose row number is
-// >= w * seg_rows + k * 4096 (k = subs: the end of the cell).  One thread per search, all of them
-// in flight at once: done inside the gathering CTAs the 22 dependent loads per cell were most
-// of their 1.6 ms (r02z).
-__global__ void __launch_bounds__(HJ_THREADS)
-hj_sub_bounds_kernel(const uint32_t *__restrict__ row_part, const uint32_t *__restrict__ cell_base,
-                     uint32_t segs, uint32_t seg_rows, uint32_t n_probe, uint32_t *__restrict__ sub_start) {
-    const uint32_t subs = seg_rows / HJ_SUB;
-    const unsigned long long gid = (unsigned long long)blockIdx.x * HJ_THREADS + threadIdx.x;
-    const uint32_t p = (uint32_t)(gid & 255u);
-    const uint32_t k = (uint32_t)((gid >> 8) % (subs + 1));
-    const uint32_t w = (uint32_t)((gid >> 8) / (subs + 1));
-    if (w >= segs) return;
-    const uint32_t b = cell_base[w * 256 + p];
-    const unsigned long long seg_end = (unsigned long long)(w + 1) * seg_rows;
-    const uint32_t e = p < 255 ? cell_base[w * 256 + p + 1] : (uint32_t)(seg_end < n_probe ? seg_end : n_probe);
-    const unsigned long long first_row = (unsigned long long)w * seg_rows + (unsigned long long)k * HJ_SUB;
-    sub_start[gid] = first_row >= n_probe ? e : hj_lower_bound(row_part, b, e, (uint32_t)first_row);
-}
-
+// Where do the entries of the CTA's 4096 rows sit inside cell (w, p)?  A sub-window is one
+// 4096-row tile of the segmented radix pass, and that pass' histogram, scanned along the tiles
+// of a window, holds exactly this: hist[w][p][t] = entries of the window's tiles before t in
+// bucket p.  (r02z searched the cells' ascending row numbers instead: two binary searches per
+// cell in front of every gather made the kernel 1.58 ms; r02za moved them into a kernel of
+// their own, 0.18 ms; reading the histogram costs nothing.)
 __global__ void __launch_bounds__(HJ_THREADS)
 hj_unpartition_kernel(const uint32_t *__restrict__ row_part, const uint2 *__restrict__ res_part,
-                      const uint32_t *__restrict__ sub_start, uint32_t seg_rows, uint32_t n_probe,
+                      const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ hist,
+                      uint32_t seg_tiles, uint32_t tiles, uint32_t n_probe,
                       uint2 *__restrict__ gc_by_j, unsigned long long *__restrict__ warp_sums) {
     __shared__ uint2 s_res[HJ_SUB];
     __shared__ uint32_t s_lo[256], s_n[256];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t j_lo = blockIdx.x * HJ_SUB;
     const uint32_t j_hi = min(n_probe, j_lo + HJ_SUB);
-    const uint32_t subs = seg_rows / HJ_SUB;
-    const uint32_t w = blockIdx.x / subs, k = blockIdx.x - w * subs;
+    const uint32_t w = blockIdx.x / seg_tiles, t = blockIdx.x - w * seg_tiles;
     {
-        const size_t at = ((size_t)w * (subs + 1) + k) * 256 + threadIdx.x;
-        const uint32_t lo = sub_start[at], hi = sub_start[at + 256];
-        s_lo[threadIdx.x] = lo;
-        s_n[threadIdx.x] = hi - lo;
+        const uint32_t p = threadIdx.x;
+        const uint32_t b = cell_base[w * 256 + p];
+        const uint32_t *h = hist + ((size_t)w * 256 + p) * seg_tiles;
+        const uint32_t tiles_here = min(seg_tiles, tiles - w * seg_tiles);
+        const unsigned long long seg_end = (unsigned long long)(w + 1) * seg_tiles * HJ_SUB;
+        const uint32_t e = p < 255 ? cell_base[w * 256 + p + 1] : (uint32_t)(seg_end < n_probe ? seg_end : n_probe);
+        const uint32_t lo = b + h[t];
+        const uint32_t hi = t + 1 < tiles_here ? b + h[t + 1] : e;
+        s_lo[p] = lo;
+        s_n[p] = hi - lo;
     }
     __syncthreads();
     // warp `warp` gathers cells warp*32 .. +32, four cells' loads in flight at a time
@@ -633,7 +674,10 @@ int launch_hj_geometry(const uint32_t *off1, uint32_t num_parts, unsigned long l
 int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint32_t *off1,
                           const unsigned long long *toff, uint32_t num_parts, uint32_t part_bits,
                           uint4 *table, cudaStream_t s) {
-    hj_table_build_kernel<<<num_parts, HJ_THREADS, 0, s>>>(bkeys, bpos, off1, toff, part_bits, table);
+    static int wide = -1;                                  // ADB_HJ_TABLE_CTA=wide: the 256 x 4096 form
+    if (wide < 0) { const char *e = getenv("ADB_HJ_TABLE_CTA"); wide = e && !strcmp(e, "wide"); }
+    if (wide) hj_table_build_kernel<256, 4096><<<num_parts, 256, 0, s>>>(bkeys, bpos, off1, toff, part_bits, table);
+    else hj_table_build_kernel<128, 2048><<<num_parts, 128, 0, s>>>(bkeys, bpos, off1, toff, part_bits, table);
     return 1;
 }
 
@@ -663,26 +707,25 @@ int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &
 // The partitioned form of launch_hj_probe (P2 + P3 above; P1 is launch_radix_pass_segmented with
 // RadixPass{24, 8, 1}, payload = row number): pkeys_part / row_part = its outputs, cell_base = its
 // `base`, res_part = n_probe scratch entries.
-// sub_start: (n_probe / 4096 + segs + 1) * 256 words; chunk_sums: pg.warps / 1024 + 2 64-bit words
+// cell_base / hist / seg_tiles: the segmented pass' base, scanned histogram and (effective)
+// tiles per window; chunk_sums: pg.warps / 1024 + 2 64-bit words
 int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_part, const uint32_t *cell_base,
-                                uint32_t segs, uint32_t seg_rows, uint32_t n_probe, const HjProbeGeom &pg,
-                                const unsigned long long *toff, uint32_t part_bits, const uint4 *table,
-                                uint2 *res_part, uint32_t *sub_start, uint2 *gc_by_j,
+                                const uint32_t *hist, uint32_t segs, uint32_t seg_tiles, uint32_t n_probe,
+                                const HjProbeGeom &pg, const unsigned long long *toff, uint32_t part_bits,
+                                const uint4 *table, uint2 *res_part, uint2 *gc_by_j,
                                 unsigned long long *warp_sums, unsigned long long *chunk_sums,
                                 unsigned long long *total, cudaStream_t s) {
     if (n_probe == 0) return 0;
-    hj_probe_cells_kernel<<<segs * 256, HJ_THREADS, 0, s>>>(pkeys_part, cell_base, segs, seg_rows, n_probe, toff,
-                                                            part_bits, table, res_part);
-    const unsigned long long searches = (unsigned long long)segs * (seg_rows / HJ_SUB + 1) * 256;
-    hj_sub_bounds_kernel<<<(unsigned)((searches + HJ_THREADS - 1) / HJ_THREADS), HJ_THREADS, 0, s>>>(
-        row_part, cell_base, segs, seg_rows, n_probe, sub_start);
-    hj_unpartition_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(row_part, res_part, sub_start, seg_rows, n_probe,
-                                                           gc_by_j, warp_sums);
+    hj_probe_cells_kernel<<<segs * 256, HJ_THREADS, 0, s>>>(pkeys_part, cell_base, segs, seg_tiles * HJ_SUB, n_probe,
+                                                            toff, part_bits, table, res_part);
+    hj_unpartition_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(row_part, res_part, cell_base, hist, seg_tiles,
+                                                           (n_probe + HJ_SUB - 1) / HJ_SUB, n_probe, gc_by_j,
+                                                           warp_sums);
     const uint32_t chunks = (pg.warps + HJ_GEOM_CHUNK - 1) / HJ_GEOM_CHUNK;
     hj_sums_local_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, pg.warps, chunk_sums);
     hj_sums_scan_kernel<<<1, 1024, 0, s>>>(chunk_sums, chunks, total);
     hj_geometry_add_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, pg.warps, chunk_sums);
-    return 6;
+    return 5;
 }
 
 // the partitioned probe's geometry: one CTA per 4096 probe rows, 512 rows per warp
@@ -735,9 +778,9 @@ void preload_hash_join() {
     preload_one(reinterpret_cast<const void *>(&hj_probe_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_probe_cells_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_unpartition_kernel));
-    preload_one(reinterpret_cast<const void *>(&hj_sub_bounds_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_sums_local_kernel));
-    preload_one(reinterpret_cast<const void *>(&hj_table_build_kernel));
+    { auto *fp = &hj_table_build_kernel<128, 2048>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &hj_table_build_kernel<256, 4096>; preload_one(reinterpret_cast<const void *>(fp)); }
     preload_one(reinterpret_cast<const void *>(&hj_bounds_kernel));
 }
 

@@ -419,6 +419,10 @@ uint32_t radix_segments(uint32_t n, uint32_t seg_tiles) {
     if (seg_tiles == 0 || seg_tiles >= tiles) return 1;
     return (tiles + seg_tiles - 1) / seg_tiles;
 }
+uint32_t radix_seg_tiles(uint32_t n, uint32_t seg_tiles) {
+    const uint32_t tiles = (n + RX_TILE - 1) / RX_TILE;
+    return radix_segments(n, seg_tiles) == 1 ? (tiles ? tiles : 1) : seg_tiles;
+}
 size_t radix_hist_elems(uint32_t n, uint32_t seg_tiles) {
     const uint32_t tiles = (n + RX_TILE - 1) / RX_TILE;
     const uint32_t segs = radix_segments(n, seg_tiles);

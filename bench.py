@@ -1047,7 +1047,8 @@ def api_join(eng, api, q, G, sync_all, n=100_000_000):
             "includes": "hash_join of include/adb_query_api.h, wall clock: "
                         + ("build-side exchange over NVLink peer memory, per-GPU tables, probe in place with "
                            "peer table reads, output sized and written" if G > 1 else
-                           "sort + tables + probe + offsets + expansion on one GPU")}
+                           "build sort + tables, probe rows partitioned by window and table slice, slice-major probe, "
+                           "back to row order, expansion (offsets computed in the expansion) on one GPU")}
         for h_ in (v1, p1, v2, p2):
             api.drop(h_)
     for c, b in bufs:
