@@ -444,8 +444,8 @@ hj_unpartition_kernel(const uint32_t *__restrict__ row_part, const uint2 *__rest
         s_n[p] = hi - lo;
     }
     __syncthreads();
-    // warp `warp` gathers cells warp*32 .. +32, four cells' loads in flight at a time
-    constexpr int U = 4;
+    // warp `warp` gathers cells warp*32 .. +32, eight cells' loads in flight at a time
+    constexpr int U = 8;
     for (uint32_t c0 = warp * 32; c0 < warp * 32 + 32; c0 += U) {
         uint32_t row[U];
         int2 val[U];
@@ -539,11 +539,19 @@ __device__ __forceinline__ void hj_expand_body(const uint2 *__restrict__ gc_by_j
                 out_probe[off] = pp;
                 out_probe[off + 1] = pp;
             } else if (cnt && cnt <= 8) {
+                // all of the group's (random) reads are issued before the first is waited for: nearly
+                // every warp step has a lane in here (8 % of the rows on uniform keys)
                 const int32_t *__restrict__ bp = lists.list(owner_of(jb + u * kWarp + lane));
-                for (uint32_t r = 0; r < cnt; ++r) {
-                    out_build[off + r] = ld_gather(bp + gs + r);
-                    out_probe[off + r] = pp;
-                }
+                int32_t v[8];
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r)
+                    if (r < cnt) v[r] = ld_gather(bp + gs + r);
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r)
+                    if (r < cnt) {
+                        out_build[off + r] = v[r];
+                        out_probe[off + r] = pp;
+                    }
             }
             uint32_t longs = __ballot_sync(kFull, cnt > 8);
             while (longs) {
