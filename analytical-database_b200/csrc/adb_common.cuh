@@ -573,6 +573,16 @@ int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_
                                 const uint4 *table, uint2 *res_part, uint2 *gc_by_j,
                                 unsigned long long *warp_sums, unsigned long long *chunk_sums,
                                 unsigned long long *total, cudaStream_t s);
+// The routed probe of the sharded join: an owner probes the keys it received (results in the
+// same order; scratch_sums: hj_probe_geom(n).warps words), the rows' home takes the results back
+// to row order (cells = owners; cell_base / hist from the unsegmented routing pass).
+int launch_hj_probe_plain(const uint32_t *pkeys, uint32_t n_probe, const unsigned long long *toff,
+                          uint32_t part_bits, const uint4 *table, uint2 *results, unsigned long long *scratch_sums,
+                          int sm_count, cudaStream_t s);
+int launch_hj_unpartition_routed(const uint32_t *row_part, const uint2 *res_part, const uint32_t *cell_base,
+                                 const uint32_t *hist, uint32_t n_probe, uint32_t cells, const HjProbeGeom &pg,
+                                 uint2 *gc_by_j, unsigned long long *warp_sums, unsigned long long *chunk_sums,
+                                 unsigned long long *total, cudaStream_t s);
 int launch_hj_expand(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
                      int32_t *out_build, int32_t *out_probe, cudaStream_t s);

@@ -70,6 +70,12 @@ struct Engine {
         uint2 *gc_by_j = nullptr;           // {group start, match count} per probe row
         unsigned long long *warp_base = nullptr;   // first output slot of every probing warp (pg.warps)
         adb::HjProbeGeom pg{};
+        // routed probe (adb_join_route_probe): this context's probe keys / row numbers by owner,
+        // and where the owners' answers are collected (arena)
+        uint32_t *rt_keys = nullptr, *rt_rows = nullptr;
+        uint2 *rt_res = nullptr;
+        uint32_t rt_rows_n = 0;
+        bool routed = false;
         int32_t *build_pos_sorted = nullptr;   // all three live in the arena
         const int32_t *probe_pos = nullptr;
         bool swapped = false;
@@ -95,6 +101,10 @@ struct Engine {
     // then costs ONE remote read, the slot, instead of two dependent ones)
     unsigned long long *toff_replica = nullptr;
     size_t toff_replica_words = 0;
+    // routed probe, owner side: the keys other contexts sent here and the answers (grow-only)
+    uint32_t *rt_recv_keys = nullptr;
+    uint2 *rt_recv_res = nullptr;
+    size_t rt_recv_cap = 0;
     // bulk CSV load state (adb_csv_index -> adb_csv_parse); scratch is grow-only
     struct CsvState {
         const unsigned char *text = nullptr;
@@ -602,6 +612,8 @@ static adb_status shutdown_current() {
     cudaFree(g.arena);
     cudaFree(g.hj_table);
     cudaFree(g.toff_replica);
+    cudaFree(g.rt_recv_keys);
+    cudaFree(g.rt_recv_res);
     cudaFree(g.fmt.block_len);
     cudaFree(g.fmt.block_off);
     cudaFree(g.fmt.total);
@@ -2261,7 +2273,7 @@ adb_status adb_join_build(const int32_t *d_v, const int32_t *d_p, int64_t n, int
     int launches = 0;
     StageTrace tr;
     if (adb_status s = ensure_radix_scratch((uint32_t)(n ? n : 1))) return s;
-    if (adb_status s = join_build(d_v, d_p, (uint32_t)n, (uint32_t)probe_rows_hint, &launches, tr)) return s;
+    if (adb_status s = join_build(d_v, d_p, (uint32_t)n, (uint32_t)probe_rows_hint, &launches, tr, true)) return s;
     if (adb_status s = after_launch("join_build", launches)) return s;
     CU(cudaStreamSynchronize(g.stream));               // the other contexts' probes read these tables
     g.join.built = true;
@@ -2330,6 +2342,152 @@ adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int3
     return ADB_OK;
 }
 
+// ---- the sharded join's ROUTED probe -------------------------------------------------------------
+// adb_join_probe_sharded reads every remote key's slot over NVLink: 16 useful bytes per 32-byte
+// response, 8.8 G reads/s per GPU -- 1.2 ms for the 11 M remote rows of an 8-GPU 100 M-row probe
+// (profiles/r02_join_sharded.md).  Routed instead: the keys travel to their owners in bulk
+// (4 bytes per row), the owner probes them against its own tables, the 8-byte answers travel
+// back in bulk, and the rows' home puts them back in row order (the same gather as the one-GPU
+// partitioned probe; cells = owners).  Steps, each on every context with a host barrier between:
+//   1. adb_join_route_probe     stable partition of my probe keys by owner; per-owner counts
+//   2. adb_join_recv_buffers + adb_copy_from_ctx per source + adb_join_probe_received
+//   3. adb_copy_from_ctx per owner into *d_answers + adb_join_finish_routed, then adb_join_emit
+adb_status adb_join_route_probe(int32_t world, const int32_t *d_pv, int64_t np64, int64_t *h_counts,
+                                const int32_t **d_routed_keys, void **d_answers) {
+    NEED_UP();
+    auto &j = g.join;
+    if (!j.built) return fail(ADB_ERR_INVALID, "adb_join_route_probe: no preceding adb_join_build on this context");
+    if (world < 2 || world > ADB_MAX_PEERS || (world & (world - 1)))
+        return fail(ADB_ERR_INVALID, "adb_join_route_probe: world %d must be a power of two in [2, %d]", world, ADB_MAX_PEERS);
+    if (adb_status s = check_len(np64, "adb_join_route_probe")) return s;
+    if ((uint32_t)np64 > j.n_probe) return fail(ADB_ERR_INVALID, "adb_join_route_probe: more probe rows than adb_join_build reserved for");
+    if (!h_counts || !d_routed_keys || !d_answers || (np64 > 0 && !d_pv))
+        return fail(ADB_ERR_INVALID, "adb_join_route_probe: NULL pointer");
+    for (int r = 0; r < world; ++r) h_counts[r] = 0;
+    *d_routed_keys = nullptr;
+    *d_answers = nullptr;
+    const uint32_t np = (uint32_t)np64;
+    j.rt_rows_n = np;
+    j.routed = true;
+    if (np == 0) return ADB_OK;
+    if (adb_status s = ensure_radix_scratch(np)) return s;
+    int bits = 0;
+    while ((1 << bits) < world) ++bits;
+    j.rt_keys = ARENA_TAKE(uint32_t, np);
+    j.rt_rows = ARENA_TAKE(uint32_t, np);
+    j.rt_res = ARENA_TAKE(uint2, np);
+    if (g.arena_used > g.arena_cap) return fail(ADB_ERR_NOMEM, "adb_join_route_probe: scratch arena too small");
+    const int k_ = adb::launch_radix_pass_segmented(reinterpret_cast<const uint32_t *>(d_pv), nullptr, j.rt_keys,
+                                                    j.rt_rows, np, adb::RadixPass{32 - bits, bits, 2}, 0, g.rx_hist,
+                                                    g.rx_totals, g.rx_base, g.sm_count, g.stream);
+    if (adb_status s = after_launch("join_route_probe", k_)) return s;
+    uint32_t totals[ADB_MAX_PEERS];
+    CU(cudaMemcpyAsync(totals, g.rx_totals, sizeof(uint32_t) * world, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    for (int r = 0; r < world; ++r) h_counts[r] = totals[r];
+    *d_routed_keys = reinterpret_cast<const int32_t *>(j.rt_keys);
+    *d_answers = j.rt_res;
+    return ADB_OK;
+}
+
+adb_status adb_join_recv_buffers(int64_t n_recv, int32_t **d_keys, void **d_answers) {
+    NEED_UP();
+    if (adb_status s = check_len(n_recv, "adb_join_recv_buffers")) return s;
+    if (!d_keys || !d_answers) return fail(ADB_ERR_INVALID, "adb_join_recv_buffers: NULL pointer");
+    if ((size_t)n_recv > g.rt_recv_cap) {
+        CU(cudaStreamSynchronize(g.stream));
+        if (g.rt_recv_keys) CU(cudaFree(g.rt_recv_keys));
+        if (g.rt_recv_res) CU(cudaFree(g.rt_recv_res));
+        g.rt_recv_keys = nullptr;
+        g.rt_recv_res = nullptr;
+        g.rt_recv_cap = 0;
+        const size_t want = (size_t)n_recv + (size_t)n_recv / 8 + 4096;
+        cudaError_t e = cudaMalloc(&g.rt_recv_keys, want * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&g.rt_recv_res, want * 8);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (g.rt_recv_keys) cudaFree(g.rt_recv_keys);
+            g.rt_recv_keys = nullptr;
+            return fail(ADB_ERR_NOMEM, "routed probe: %zu received keys: %s", want, cudaGetErrorString(e));
+        }
+        g.rt_recv_cap = want;
+    }
+    *d_keys = reinterpret_cast<int32_t *>(g.rt_recv_keys);
+    *d_answers = g.rt_recv_res;
+    return ADB_OK;
+}
+
+adb_status adb_join_probe_received(int64_t n_recv) {
+    NEED_UP();
+    auto &j = g.join;
+    if (!j.built) return fail(ADB_ERR_INVALID, "adb_join_probe_received: no tables on this context");
+    if (adb_status s = check_len(n_recv, "adb_join_probe_received")) return s;
+    if ((size_t)n_recv > g.rt_recv_cap) return fail(ADB_ERR_INVALID, "adb_join_probe_received: more keys than adb_join_recv_buffers made room for");
+    if (n_recv == 0) return ADB_OK;
+    const adb::HjProbeGeom pg = adb::hj_probe_geom((uint32_t)n_recv, g.sm_count);
+    unsigned long long *sums = ARENA_TAKE(unsigned long long, pg.warps);
+    if (g.arena_used > g.arena_cap) return fail(ADB_ERR_NOMEM, "adb_join_probe_received: scratch arena too small");
+    StageTrace tr;
+    const int k_ = adb::launch_hj_probe_plain(g.rt_recv_keys, (uint32_t)n_recv, j.toff, j.part_bits,
+                                              static_cast<const uint4 *>(g.hj_table), g.rt_recv_res, sums,
+                                              g.sm_count, g.stream);
+    tr.lap("probe of the received keys");
+    return after_launch("join_probe_received", k_);
+}
+
+adb_status adb_join_finish_routed(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np64,
+                                  int32_t swapped, int64_t *h_matches) {
+    NEED_UP();
+    auto &j = g.join;
+    if (!j.built || !j.routed) return fail(ADB_ERR_INVALID, "adb_join_finish_routed: no preceding adb_join_route_probe");
+    if (world < 2 || world > ADB_MAX_PEERS || (world & (world - 1)))
+        return fail(ADB_ERR_INVALID, "adb_join_finish_routed: world %d must be a power of two in [2, %d]", world, ADB_MAX_PEERS);
+    if ((uint32_t)np64 != j.rt_rows_n) return fail(ADB_ERR_INVALID, "adb_join_finish_routed: row count differs from adb_join_route_probe");
+    if (np64 > 0 && (!d_pv || !d_pp)) return fail(ADB_ERR_INVALID, "adb_join_finish_routed: NULL device pointer");
+    const uint32_t np = (uint32_t)np64;
+    adb::JoinOwners o{};
+    for (int r = 0; r < world; ++r) {
+        const Engine &E = g_ctx[r];
+        if (!E.up || !E.join.built) return fail(ADB_ERR_INVALID, "adb_join_finish_routed: context %d has built no tables", r);
+        o.toff[r] = E.join.toff;
+        o.table[r] = static_cast<const uint4 *>(E.hj_table);
+        o.bpos[r] = E.join.build_pos_sorted;
+        o.part_bits[r] = E.join.part_bits;
+    }
+    while ((1 << o.route_bits) < world) ++o.route_bits;
+    j.owners = o;
+    j.sharded = true;
+    j.swapped = swapped != 0;
+    j.n_probe = np;
+    j.probe_pos = d_pp;
+    j.probe_keys = reinterpret_cast<const uint32_t *>(d_pv);
+    j.matches = 0;
+    j.routed = false;
+    if (np == 0) {
+        j.ready = true;
+        if (h_matches) *h_matches = 0;
+        return ADB_OK;
+    }
+    unsigned long long *tot = ARENA_TAKE(unsigned long long, 2);
+    j.pg = adb::hj_probe_geom_partitioned(np);
+    j.gc_by_j = ARENA_TAKE(uint2, np);
+    j.warp_base = ARENA_TAKE(unsigned long long, j.pg.warps);
+    unsigned long long *chunk_sums = ARENA_TAKE(unsigned long long, j.pg.warps / 1024 + 2);
+    if (g.arena_used > g.arena_cap) return fail(ADB_ERR_NOMEM, "adb_join_finish_routed: scratch arena too small");
+    StageTrace tr;
+    int launches = adb::launch_hj_unpartition_routed(j.rt_rows, j.rt_res, g.rx_base, g.rx_hist, np, (uint32_t)world,
+                                                     j.pg, j.gc_by_j, j.warp_base, chunk_sums, tot, g.stream);
+    if (adb_status s = read_back(&j.matches, tot, sizeof(int64_t))) return s;
+    tr.lap("answers back to row order + piece offsets");
+    if (adb_status s = after_launch("join_finish_routed", launches)) return s;
+    if (j.matches >= (int64_t)1 << 31)
+        return fail(ADB_ERR_INVALID, "join produces %lld pairs on one context; the result must stay below 2^31",
+                    (long long)j.matches);
+    j.ready = true;
+    if (h_matches) *h_matches = j.matches;
+    return ADB_OK;
+}
+
 // Everything adb_peer_exchange_pairs / adb_join_build allocate, sized up front.  Device memory
 // management can wait for the device to go idle; a context that did that while a peer context
 // ON THE SAME DEVICE sits in the exchange's spin-wait for it would stall both (contexts sharing
@@ -2340,7 +2498,8 @@ adb_status adb_peer_exchange_reserve(int64_t send_pairs, int64_t build_pairs, in
     if (adb_status s = check_len(send_pairs, "adb_peer_exchange_reserve")) return s;
     if (adb_status s = check_len(build_pairs, "adb_peer_exchange_reserve")) return s;
     if (adb_status s = check_len(probe_rows, "adb_peer_exchange_reserve")) return s;
-    const uint32_t big = (uint32_t)(send_pairs > build_pairs ? send_pairs : build_pairs);
+    uint32_t big = (uint32_t)(send_pairs > build_pairs ? send_pairs : build_pairs);
+    if ((uint32_t)probe_rows > big) big = (uint32_t)probe_rows;            // the routed probe's partition pass
     if (adb_status s = ensure_radix_scratch(big ? big : 1)) return s;
     const uint32_t nb = (uint32_t)build_pairs, np = (uint32_t)probe_rows;
     uint32_t part_bits = 1;
@@ -2348,7 +2507,8 @@ adb_status adb_peer_exchange_reserve(int64_t send_pairs, int64_t build_pairs, in
     const uint32_t num_parts = 1u << part_bits;
     if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
                                      arena_round((size_t)(num_parts + 1) * 4) +
-                                     arena_round((size_t)(num_parts + 1) * 8) + kJoinSmallScratch))
+                                     arena_round((size_t)(num_parts + 1) * 8) + join_partition_scratch(np) +
+                                     kJoinSmallScratch))
         return s;
     {
         const size_t words = (size_t)ADB_MAX_PEERS * ((size_t)num_parts + 1);

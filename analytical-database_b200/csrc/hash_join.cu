@@ -483,6 +483,62 @@ hj_unpartition_kernel(const uint32_t *__restrict__ row_part, const uint2 *__rest
     if (lane == 0) warp_sums[blockIdx.x * (HJ_THREADS / kWarp) + warp] = acc;
 }
 
+// The same gather when a tile's rows sit in a FEW fat cells (the routed probe of the sharded
+// join: cells = the owner GPUs, ~4096 / G entries each): the tile's entries, cell after cell,
+// are dealt out to the threads sixteen apiece, all loads issued before the first store.
+constexpr int HJ_FAT_CELLS = ADB_MAX_PEERS;
+__global__ void __launch_bounds__(HJ_THREADS)
+hj_unpartition_routed_kernel(const uint32_t *__restrict__ row_part, const uint2 *__restrict__ res_part,
+                             const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ hist,
+                             uint32_t tiles, uint32_t n_probe, uint32_t cells,
+                             uint2 *__restrict__ gc_by_j, unsigned long long *__restrict__ warp_sums) {
+    __shared__ uint2 s_res[HJ_SUB];
+    __shared__ uint32_t s_lo[HJ_FAT_CELLS], s_pre[HJ_FAT_CELLS + 1];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x;
+    const uint32_t j_lo = t * HJ_SUB, j_hi = min(n_probe, j_lo + HJ_SUB);
+    const uint32_t rows = j_hi - j_lo;
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t c = 0; c < cells; ++c) {
+            const uint32_t b = cell_base[c];
+            const uint32_t *h = hist + (size_t)c * tiles;      // one segment: [bucket][tiles]
+            const uint32_t lo = b + h[t];
+            const uint32_t hi = t + 1 < tiles ? b + h[t + 1] : cell_base[c + 1];   // bucket c + 1 <= 255 exists
+            s_lo[c] = lo;
+            s_pre[c] = run;
+            run += hi - lo;
+        }
+        s_pre[cells] = run;                                     // == rows
+    }
+    __syncthreads();
+    constexpr int PER = HJ_SUB / HJ_THREADS;                    // 16
+    uint32_t row[PER];
+    int2 val[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t e = threadIdx.x + i * HJ_THREADS;
+        row[i] = 0xFFFFFFFFu;
+        if (e < rows) {
+            uint32_t c = 0;
+            while (c + 1 < cells && s_pre[c + 1] <= e) ++c;
+            const uint32_t src = s_lo[c] + (e - s_pre[c]);
+            row[i] = row_part[src];
+            val[i] = *reinterpret_cast<const int2 *>(res_part + src);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+        if (row[i] != 0xFFFFFFFFu) s_res[row[i] - j_lo] = make_uint2((uint32_t)val[i].x, (uint32_t)val[i].y);
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < rows; r += HJ_THREADS) gc_by_j[j_lo + r] = s_res[r];
+    uint32_t acc = 0;
+    for (uint32_t r = warp * HJ_SUB_WARP + lane; r < min(rows, (warp + 1) * HJ_SUB_WARP); r += kWarp)
+        acc += hj_matches(s_res[r].y);
+    acc = warp_sum(acc);
+    if (lane == 0) warp_sums[blockIdx.x * (HJ_THREADS / kWarp) + warp] = acc;
+}
+
 // ---- expand ---------------------------------------------------------------------------------------
 // A warp expands the piece of the probe side it probed: its first output slot comes from the
 // scan of the warps' match counts, the slots inside the piece from a running warp scan.  Four
@@ -715,6 +771,16 @@ int launch_hj_probe(const uint32_t *pkeys, uint32_t n_probe, const HjProbeGeom &
 // The partitioned form of launch_hj_probe (P2 + P3 above; P1 is launch_radix_pass_segmented with
 // RadixPass{24, 8, 1}, payload = row number): pkeys_part / row_part = its outputs, cell_base = its
 // `base`, res_part = n_probe scratch entries.
+// in-place exclusive scan of the pieces' match counts; chunk_sums: warps / 1024 + 2 words
+static int hj_piece_scan(unsigned long long *warp_sums, uint32_t warps, unsigned long long *chunk_sums,
+                         unsigned long long *total, cudaStream_t s) {
+    const uint32_t chunks = (warps + HJ_GEOM_CHUNK - 1) / HJ_GEOM_CHUNK;
+    hj_sums_local_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, warps, chunk_sums);
+    hj_sums_scan_kernel<<<1, 1024, 0, s>>>(chunk_sums, chunks, total);
+    hj_geometry_add_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, warps, chunk_sums);
+    return 3;
+}
+
 // cell_base / hist / seg_tiles: the segmented pass' base, scanned histogram and (effective)
 // tiles per window; chunk_sums: pg.warps / 1024 + 2 64-bit words
 int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_part, const uint32_t *cell_base,
@@ -729,11 +795,30 @@ int launch_hj_probe_partitioned(const uint32_t *pkeys_part, const uint32_t *row_
     hj_unpartition_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(row_part, res_part, cell_base, hist, seg_tiles,
                                                            (n_probe + HJ_SUB - 1) / HJ_SUB, n_probe, gc_by_j,
                                                            warp_sums);
-    const uint32_t chunks = (pg.warps + HJ_GEOM_CHUNK - 1) / HJ_GEOM_CHUNK;
-    hj_sums_local_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, pg.warps, chunk_sums);
-    hj_sums_scan_kernel<<<1, 1024, 0, s>>>(chunk_sums, chunks, total);
-    hj_geometry_add_kernel<<<chunks, HJ_GEOM_CHUNK, 0, s>>>(warp_sums, pg.warps, chunk_sums);
-    return 5;
+    return 2 + hj_piece_scan(warp_sums, pg.warps, chunk_sums, total, s);
+}
+
+// The routed probe of the sharded join (engine.cu: adb_join_route_probe ... adb_join_finish_routed).
+// launch_hj_probe_plain: the keys an owner received, against its own tables, results in place.
+int launch_hj_probe_plain(const uint32_t *pkeys, uint32_t n_probe, const unsigned long long *toff,
+                          uint32_t part_bits, const uint4 *table, uint2 *results, unsigned long long *scratch_sums,
+                          int sm_count, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    const HjProbeGeom pg = hj_probe_geom(n_probe, sm_count);
+    hj_probe_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(pkeys, n_probe, pg.rows_per_warp, toff, part_bits, table,
+                                                     results, scratch_sums);
+    return 1;
+}
+// back to row order on the rows' home: cells = the owners (one window, unsegmented pass)
+int launch_hj_unpartition_routed(const uint32_t *row_part, const uint2 *res_part, const uint32_t *cell_base,
+                                 const uint32_t *hist, uint32_t n_probe, uint32_t cells, const HjProbeGeom &pg,
+                                 uint2 *gc_by_j, unsigned long long *warp_sums, unsigned long long *chunk_sums,
+                                 unsigned long long *total, cudaStream_t s) {
+    if (n_probe == 0) return 0;
+    hj_unpartition_routed_kernel<<<pg.blocks, HJ_THREADS, 0, s>>>(row_part, res_part, cell_base, hist,
+                                                                  (n_probe + HJ_SUB - 1) / HJ_SUB, n_probe, cells,
+                                                                  gc_by_j, warp_sums);
+    return 1 + hj_piece_scan(warp_sums, pg.warps, chunk_sums, total, s);
 }
 
 // the partitioned probe's geometry: one CTA per 4096 probe rows, 512 rows per warp
@@ -786,6 +871,7 @@ void preload_hash_join() {
     preload_one(reinterpret_cast<const void *>(&hj_probe_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_probe_cells_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_unpartition_kernel));
+    preload_one(reinterpret_cast<const void *>(&hj_unpartition_routed_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_sums_local_kernel));
     { auto *fp = &hj_table_build_kernel<128, 2048>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &hj_table_build_kernel<256, 4096>; preload_one(reinterpret_cast<const void *>(fp)); }

@@ -2430,7 +2430,28 @@ typedef struct JoinJob {
     int swapped, phase, overflow;
     size_t cap;                                     /* pairs a GPU can receive */
     Shards o1, o2;
+    /* routed probe (phases 1-3): sent[g][o] = probe keys of GPU g owned by GPU o */
+    int64_t sent[MAXG][MAXG];
+    const int32_t *routed_keys[MAXG];               /* GPU g's keys grouped by owner */
+    void *answers_home[MAXG];                       /* where GPU g collects the owners' answers */
+    void *answers_owner[MAXG];                      /* GPU o's answers, in the order it received the keys */
 } JoinJob;
+
+/* ADB_JOIN_SHARDED_PROBE=peer: every GPU probes its rows in place and reads a remote key's slot
+ * over NVLink (adb_join_probe_sharded) instead of routing the keys to their owners. */
+static int join_probe_routed(void) {
+    const char *e = getenv("ADB_JOIN_SHARDED_PROBE");
+    return !(e && !strcmp(e, "peer"));
+}
+static void join_finish_shard(int g, JoinJob *a, int64_t m) {
+    void *x = NULL, *y = NULL;
+    SCK(adb_alloc(&x, 4 * (size_t)m));
+    a->o1.d[g] = x;
+    SCK(adb_alloc(&y, 4 * (size_t)m));
+    a->o2.d[g] = y;
+    a->o1.n[g] = a->o2.n[g] = (size_t)m;
+    SCK(adb_join_emit(x, y));
+}
 static void join_shard(int g, void *arg) {
     JoinJob *a = arg;
     if (a->phase == -1) {
@@ -2453,15 +2474,46 @@ static void join_shard(int g, void *arg) {
         SCK(adb_join_build(rv, rp, rn, (int64_t)a->pv->n[g]));
         return;
     }
+    if (a->phase == 1) {                            /* probe in place, remote slots over NVLink */
+        int64_t m = 0;
+        SCK(adb_join_probe_sharded(S.G, a->pv->d[g], a->pp->d[g], (int64_t)a->pv->n[g], a->swapped, &m));
+        join_finish_shard(g, a, m);
+        return;
+    }
+    if (a->phase == 2) {                            /* routed probe, 3a: my keys grouped by owner */
+        SCK(adb_join_route_probe(S.G, a->pv->d[g], (int64_t)a->pv->n[g], a->sent[g], &a->routed_keys[g],
+                                 &a->answers_home[g]));
+        return;
+    }
+    if (a->phase == 3) {                            /* 3b: I own what the others sent me */
+        int64_t n_recv = 0;
+        for (int s = 0; s < S.G; ++s) n_recv += a->sent[s][g];
+        int32_t *keys = NULL;
+        SCK(adb_join_recv_buffers(n_recv, &keys, &a->answers_owner[g]));
+        int64_t at = 0;
+        for (int s = 0; s < S.G; ++s) {             /* pieces in source order */
+            int64_t from = 0;
+            for (int o = 0; o < g; ++o) from += a->sent[s][o];
+            if (a->sent[s][g])
+                SCK(adb_copy_from_ctx(keys + at, s, a->routed_keys[s] + from, 4 * (size_t)a->sent[s][g]));
+            at += a->sent[s][g];
+        }
+        SCK(adb_join_probe_received(n_recv));
+        return;
+    }
+    /* phase 4, 3c: the owners' answers come home, back to row order, expand */
+    int64_t at = 0;
+    for (int o = 0; o < S.G; ++o) {
+        int64_t from = 0;                           /* my piece inside owner o's received list */
+        for (int s = 0; s < g; ++s) from += a->sent[s][o];
+        if (a->sent[g][o])
+            SCK(adb_copy_from_ctx((char *)a->answers_home[g] + 8 * (size_t)at, o,
+                                  (const char *)a->answers_owner[o] + 8 * (size_t)from, 8 * (size_t)a->sent[g][o]));
+        at += a->sent[g][o];
+    }
     int64_t m = 0;
-    SCK(adb_join_probe_sharded(S.G, a->pv->d[g], a->pp->d[g], (int64_t)a->pv->n[g], a->swapped, &m));
-    void *x = NULL, *y = NULL;
-    SCK(adb_alloc(&x, 4 * (size_t)m));
-    a->o1.d[g] = x;
-    SCK(adb_alloc(&y, 4 * (size_t)m));
-    a->o2.d[g] = y;
-    a->o1.n[g] = a->o2.n[g] = (size_t)m;
-    SCK(adb_join_emit(x, y));
+    SCK(adb_join_finish_routed(S.G, a->pv->d[g], a->pp->d[g], (int64_t)a->pv->n[g], a->swapped, &m));
+    join_finish_shard(g, a, m);
 }
 
 static int ensure_join_exchange(size_t cap) {
@@ -2516,9 +2568,16 @@ static Result **join_sharded(Result *v1, Result *p1, Result *v2, Result *p2, int
             goto fail;
         }
     }
-    job.phase = 1;
-    run_shards(join_shard, &job);
-    if (shard_errs(&job.err)) goto fail;
+    if (join_probe_routed()) {
+        for (job.phase = 2; job.phase <= 4; ++job.phase) {
+            run_shards(join_shard, &job);
+            if (shard_errs(&job.err)) goto fail;
+        }
+    } else {
+        job.phase = 1;
+        run_shards(join_shard, &job);
+        if (shard_errs(&job.err)) goto fail;
+    }
     unstage(&a); unstage(&b); unstage(&c); unstage(&d);
     results = malloc(2 * sizeof *results);
     if (!results) {

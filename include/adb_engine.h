@@ -455,6 +455,26 @@ ADB_API adb_status adb_join_build(const int32_t *d_v, const int32_t *d_p, int64_
 ADB_API adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np,
                                           int32_t swapped, int64_t *h_matches);
 
+/* Step 3 with the probe keys ROUTED to their owners instead of every remote slot being read over
+ * NVLink (one 32-byte response per 16-byte slot, ~9 G reads/s per GPU): keys out in bulk, answers
+ * back in bulk, the rows' home restores row order.  On every context, a host barrier after each:
+ *   3a. adb_join_route_probe: stable partition of this context's probe keys by owner;
+ *       h_counts[r] = keys bound for context r (they sit at offset sum(h_counts[0..r)) of
+ *       *d_routed_keys, in row order); *d_answers = where context r's answers belong, at the same
+ *       offsets, 8 bytes per key;
+ *   3b. adb_join_recv_buffers(n_recv) + one adb_copy_from_ctx per source context (pieces in
+ *       source-context order) + adb_join_probe_received(n_recv): the answers land in *d_answers
+ *       of adb_join_recv_buffers, in the order of the received keys;
+ *   3c. one adb_copy_from_ctx per owner into 3a's *d_answers + adb_join_finish_routed (what
+ *       adb_join_probe_sharded returns), then adb_join_emit.
+ * Output order and content are those of adb_join_probe_sharded. */
+ADB_API adb_status adb_join_route_probe(int32_t world, const int32_t *d_pv, int64_t np, int64_t *h_counts,
+                                        const int32_t **d_routed_keys, void **d_answers);
+ADB_API adb_status adb_join_recv_buffers(int64_t n_recv, int32_t **d_keys, void **d_answers);
+ADB_API adb_status adb_join_probe_received(int64_t n_recv);
+ADB_API adb_status adb_join_finish_routed(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np,
+                                          int32_t swapped, int64_t *h_matches);
+
 /* ---- multi-GPU join exchange, send side (no reference equivalent: SURVEY.md 8e) ----------
  * Stable partition of a (value, position) pair list by destination rank = the top
  * log2(parts) bits of a routing hash of the value; parts is a power of two <= 256 (the

@@ -771,7 +771,12 @@ def test_long_print_across_shards(api, rng):
     api.drop(s), api.drop(f)
 
 
-def test_join_of_sharded_operands(api, cpu, rng):
+@pytest.mark.parametrize("sharded_probe", ["routed", "peer"])
+def test_join_of_sharded_operands(api, cpu, rng, monkeypatch, sharded_probe):
+    """With several GPUs the probe keys are routed to their owners and the answers gathered back
+    into row order (default), or every GPU probes in place and reads remote slots over peer
+    memory (ADB_JOIN_SHARDED_PROBE=peer): same pairs, same order."""
+    monkeypatch.setenv("ADB_JOIN_SHARDED_PROBE", sharded_probe)
     n1, n2 = 70_000, 50_000
     live0 = api.lib.adb_host_live_device_results()
     k1 = rng.integers(1, 30_000, n1).astype(np.int32)
