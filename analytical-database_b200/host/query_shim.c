@@ -2490,26 +2490,30 @@ static void join_shard(int g, void *arg) {
         for (int s = 0; s < S.G; ++s) n_recv += a->sent[s][g];
         int32_t *keys = NULL;
         SCK(adb_join_recv_buffers(n_recv, &keys, &a->answers_owner[g]));
-        int64_t at = 0;
-        for (int s = 0; s < S.G; ++s) {             /* pieces in source order */
-            int64_t from = 0;
+        /* pieces land in source order; the pulls start at my own piece and go round, so that at
+         * any moment every GPU reads from a different source (r02zj: all eight starting at GPU 0
+         * queued up behind one another on its port) */
+        for (int k = 0; k < S.G; ++k) {
+            const int s = (g + k) % S.G;
+            int64_t at = 0, from = 0;
+            for (int t = 0; t < s; ++t) at += a->sent[t][g];
             for (int o = 0; o < g; ++o) from += a->sent[s][o];
-            if (a->sent[s][g])
-                SCK(adb_copy_from_ctx(keys + at, s, a->routed_keys[s] + from, 4 * (size_t)a->sent[s][g]));
-            at += a->sent[s][g];
+            if (a->sent[s][g])                      /* 3a ended synchronised, a host barrier since */
+                SCK(adb_copy_from_ctx_ready(keys + at, s, a->routed_keys[s] + from, 4 * (size_t)a->sent[s][g]));
         }
         SCK(adb_join_probe_received(n_recv));
         return;
     }
     /* phase 4, 3c: the owners' answers come home, back to row order, expand */
-    int64_t at = 0;
-    for (int o = 0; o < S.G; ++o) {
-        int64_t from = 0;                           /* my piece inside owner o's received list */
+    for (int k = 0; k < S.G; ++k) {
+        const int o = (g + k) % S.G;
+        int64_t at = 0, from = 0;                   /* my piece inside owner o's received list */
+        for (int t = 0; t < o; ++t) at += a->sent[g][t];
         for (int s = 0; s < g; ++s) from += a->sent[s][o];
-        if (a->sent[g][o])
-            SCK(adb_copy_from_ctx((char *)a->answers_home[g] + 8 * (size_t)at, o,
-                                  (const char *)a->answers_owner[o] + 8 * (size_t)from, 8 * (size_t)a->sent[g][o]));
-        at += a->sent[g][o];
+        if (a->sent[g][o])                          /* 3b ended synchronised, a host barrier since */
+            SCK(adb_copy_from_ctx_ready((char *)a->answers_home[g] + 8 * (size_t)at, o,
+                                        (const char *)a->answers_owner[o] + 8 * (size_t)from,
+                                        8 * (size_t)a->sent[g][o]));
     }
     int64_t m = 0;
     SCK(adb_join_finish_routed(S.G, a->pv->d[g], a->pp->d[g], (int64_t)a->pv->n[g], a->swapped, &m));

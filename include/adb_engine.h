@@ -69,6 +69,8 @@ ADB_API adb_status adb_ctx_wait(int32_t other_ctx);
 /* copy into the current context from a buffer of src_ctx (peer DMA across devices), ordered
  * after src_ctx's stream */
 ADB_API adb_status adb_copy_from_ctx(void *d_dst, int32_t src_ctx, const void *d_src, size_t bytes);
+/* the same when the source context has already synchronised its stream (no cross-stream wait) */
+ADB_API adb_status adb_copy_from_ctx_ready(void *d_dst, int32_t src_ctx, const void *d_src, size_t bytes);
 ADB_API const char *adb_last_error(void);
 ADB_API const char *adb_version(void);
 ADB_API int adb_sm_count(void);
@@ -462,11 +464,12 @@ ADB_API adb_status adb_join_probe_sharded(int32_t world, const int32_t *d_pv, co
  *       h_counts[r] = keys bound for context r (they sit at offset sum(h_counts[0..r)) of
  *       *d_routed_keys, in row order); *d_answers = where context r's answers belong, at the same
  *       offsets, 8 bytes per key;
- *   3b. adb_join_recv_buffers(n_recv) + one adb_copy_from_ctx per source context (pieces in
- *       source-context order) + adb_join_probe_received(n_recv): the answers land in *d_answers
- *       of adb_join_recv_buffers, in the order of the received keys;
- *   3c. one adb_copy_from_ctx per owner into 3a's *d_answers + adb_join_finish_routed (what
- *       adb_join_probe_sharded returns), then adb_join_emit.
+ *   3b. adb_join_recv_buffers(n_recv) + one adb_copy_from_ctx[_ready] per source context (pieces
+ *       in source-context order) + adb_join_probe_received(n_recv): the answers land in
+ *       *d_answers of adb_join_recv_buffers, in the order of the received keys.  Synchronises;
+ *   3c. one adb_copy_from_ctx[_ready] per owner into 3a's *d_answers + adb_join_finish_routed
+ *       (what adb_join_probe_sharded returns), then adb_join_emit.
+ * (3a and 3b end synchronised, so with a host barrier after each the _ready copies are safe.)
  * Output order and content are those of adb_join_probe_sharded. */
 ADB_API adb_status adb_join_route_probe(int32_t world, const int32_t *d_pv, int64_t np, int64_t *h_counts,
                                         const int32_t **d_routed_keys, void **d_answers);
