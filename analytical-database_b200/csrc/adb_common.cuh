@@ -115,6 +115,31 @@ __device__ __forceinline__ int32_t warp_max_i32(int32_t x) {
     return x;
 }
 
+// peers &= lanes whose digit agrees with mine in the bit `bitmask`.  Spelled out in PTX: from
+// the C form nvcc derives two predicates per bit (bit != 0 for the select, bit != 1 for the
+// vote) through a shift, an and and a compare -- six instructions where four do.
+__device__ __forceinline__ uint32_t warp_match_bit(uint32_t peers, uint32_t d, uint32_t bitmask) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, v;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+        "selp.b32 t, 0, 0xffffffff, p;\n\t"
+        "lop3.b32 %0, %0, v, t, 0x60;\n\t"
+        "}"
+        : "+r"(peers) : "r"(d), "r"(bitmask));
+    return peers;
+}
+
+// lanes (of `active`) that hold the same 8-bit value as this one
+__device__ __forceinline__ uint32_t warp_match8(uint32_t active, uint32_t v) {
+    uint32_t peers = active;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) peers = warp_match_bit(peers, v, 1u << b);
+    return peers;
+}
+
 // ---- range predicate -------------------------------------------------------------------
 // The reference tests `v >= low && v < high` with either bound optional
 // (src/query.c:97-127).  Host code folds that into an inclusive pair [lo, hi_incl]:

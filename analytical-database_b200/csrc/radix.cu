@@ -177,23 +177,6 @@ __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// peers &= lanes whose digit agrees with mine in the bit `bitmask`.  Spelled out in PTX: from
-// the C form nvcc derives two predicates per bit (bit != 0 for the select, bit != 1 for the
-// vote) through a shift, an and and a compare -- six instructions where four do.
-__device__ __forceinline__ uint32_t rx_match_bit(uint32_t peers, uint32_t d, uint32_t bitmask) {
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 t, v;\n\t"
-        "and.b32 t, %1, %2;\n\t"
-        "setp.ne.u32 p, t, 0;\n\t"
-        "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
-        "selp.b32 t, 0, 0xffffffff, p;\n\t"
-        "lop3.b32 %0, %0, v, t, 0x60;\n\t"
-        "}"
-        : "+r"(peers) : "r"(d), "r"(bitmask));
-    return peers;
-}
-
 template <int T, int HASH, int BITS, bool REMOTE, bool FULL>
 __device__ __forceinline__ void rx_scatter_tile(RxShared<T> &sh, const uint32_t *__restrict__ keys,
                                                 const uint32_t *__restrict__ pay, uint32_t tile, uint32_t end,
@@ -240,7 +223,7 @@ __device__ __forceinline__ void rx_scatter_tile(RxShared<T> &sh, const uint32_t 
         uint32_t peers = FULL ? kFull : __ballot_sync(kFull, live);
         if (BITS > 0) {
 #pragma unroll
-            for (int b = 0; b < BITS; ++b) peers = rx_match_bit(peers, d, 1u << b);
+            for (int b = 0; b < BITS; ++b) peers = warp_match_bit(peers, d, 1u << b);
         } else {
             for (int b = 0; b < p.bits; ++b) {
                 const bool bit = (d & (1u << b)) != 0u;

@@ -288,13 +288,7 @@ __device__ __forceinline__ void ss_drain(uint32_t *queue, uint32_t head, uint32_
     const uint32_t q = x >> 24;
     // (r01s: one MATCH.ANY instead of the eight ballots cut the kernel's instructions by a fifth
     // and made it slower, 110 -> 137 us: the instruction is that expensive on this part)
-    uint32_t peers = __ballot_sync(kFull, live);
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        const bool bit = (q >> b) & 1u;
-        const uint32_t vote = __ballot_sync(kFull, bit);
-        peers &= bit ? vote : ~vote;
-    }
+    const uint32_t peers = warp_match8(__ballot_sync(kFull, live), q);
     uint32_t old = 0;
     if (live) old = run[q];
     __syncwarp();
@@ -349,13 +343,7 @@ ss_emit_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__restrict_
                 avail = 0;
             }
             const uint32_t q = live ? (uint32_t)cov_q[b] : 0u;
-            uint32_t peers = __ballot_sync(kFull, live);
-#pragma unroll
-            for (int bb = 0; bb < 8; ++bb) {
-                const bool bit = (q >> bb) & 1u;
-                const uint32_t vote = __ballot_sync(kFull, bit);
-                peers &= bit ? vote : ~vote;
-            }
+            const uint32_t peers = warp_match8(__ballot_sync(kFull, live), q);
             uint32_t old = 0;
             if (live) old = run[q];
             __syncwarp();
@@ -472,13 +460,7 @@ ss_emit_sorted_kernel(const uint32_t *__restrict__ hitlist, const uint32_t *__re
             const bool live = i0 + lane < tn;
             if (i0 + kWarp + lane < tn) nxt = list[t0 + i0 + kWarp + lane];
             const uint32_t q = live ? x >> 23 : 0u;
-            uint32_t peers = __ballot_sync(kFull, live);
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool bit = (q >> b) & 1u;
-                const uint32_t vote = __ballot_sync(kFull, bit);
-                peers &= bit ? vote : ~vote;
-            }
+            const uint32_t peers = warp_match8(__ballot_sync(kFull, live), q);
             uint32_t old = 0;
             if (live) old = cur[q];
             __syncwarp();
