@@ -76,16 +76,25 @@ rx_row_scan_kernel(uint32_t *__restrict__ mat, uint32_t seg_tiles, uint32_t tile
     const uint32_t cols = min(seg_tiles, tiles - seg * seg_tiles);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
-    for (uint32_t base = 0; base < cols; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t x = i < cols ? row[i] : 0u;
-        const uint32_t incl = warp_incl_scan(x, lane);
+    // four consecutive columns per thread and step: a 500 M-row pass has 122 K columns, and a
+    // step costs three block barriers whatever it covers
+    for (uint32_t base = 0; base < cols; base += 4096) {
+        const uint32_t i = base + threadIdx.x * 4;
+        uint32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = i + k < cols ? row[i + k] : 0u;
+        const uint32_t sum = x[0] + x[1] + x[2] + x[3];
+        const uint32_t incl = warp_incl_scan(sum, lane);
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         if (warp == 0) s_warp[lane] = warp_incl_scan(s_warp[lane], lane);
         __syncthreads();
-        const uint32_t wexcl = warp ? s_warp[warp - 1] : 0u;
-        if (i < cols) row[i] = carry + wexcl + incl - x;
+        uint32_t run = carry + (warp ? s_warp[warp - 1] : 0u) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < cols) row[i + k] = run;
+            run += x[k];
+        }
         carry += s_warp[31];
         __syncthreads();
     }
