@@ -511,6 +511,12 @@ int launch_shared_emit(const uint32_t *hitlist, const uint32_t *chunk_hits,
                        const SharedScanPlan &plan, const SharedScanGeom &g, const uint32_t *offsets,
                        int32_t *const *outs, int64_t capacity, uint32_t base_pos, cudaStream_t s);
 
+// Rows per tile of a radix pass (one CTA); the join's partitioned probe gathers its results back
+// tile by tile and reads the tiles' places from the pass' histogram, so it shares the constant.
+#ifndef ADB_RADIX_TILE
+#define ADB_RADIX_TILE 4096
+#endif
+constexpr uint32_t kRadixTile = ADB_RADIX_TILE;
 // Stable radix partition passes + generic exclusive scan (radix.cu).
 struct RadixPass {
     int shift, bits;           // digit = (f(key) >> shift) & ((1 << bits) - 1), bits <= 8

@@ -2149,7 +2149,7 @@ static bool join_probe_partitioned(uint32_t nb, uint32_t np) {
 }
 static size_t join_partition_scratch(uint32_t np) {      // keys + row numbers + results in partition order,
     return 2 * arena_round((size_t)np * 4) + arena_round((size_t)np * 8) +      // 8 piece sums per 4096 rows
-           arena_round(((size_t)np / 4096 + 2) * 8 * 8) + 4096;
+           arena_round(((size_t)np / adb::kRadixTile + 2) * 8 * 8) + 4096;
 }
 
 static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, uint32_t np, int *launches,
@@ -2239,7 +2239,7 @@ static adb_status join_count(const int32_t *bv, const int32_t *bp, int64_t nb64,
     j.warp_base = ARENA_TAKE(unsigned long long, j.pg.warps);
     if (partitioned) {
         // <= 256 windows of whole 4096-row tiles, each partitioned on the top 8 hash bits
-        const uint32_t tiles = (np + 4095) / 4096;
+        const uint32_t tiles = (np + adb::kRadixTile - 1) / adb::kRadixTile;
         const uint32_t want_tiles = (tiles + 255) / 256;
         const uint32_t segs = adb::radix_segments(np, want_tiles);
         const uint32_t seg_tiles = adb::radix_seg_tiles(np, want_tiles);

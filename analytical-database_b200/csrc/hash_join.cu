@@ -403,7 +403,7 @@ hj_probe_cells_kernel(const uint32_t *__restrict__ pkeys_part, const uint32_t *_
 // ascend inside a cell: two binary searches per cell, ~16 entries each), parks the results in
 // shared memory by row and writes them out as whole lines.  Its eight warps are the expansion's
 // pieces (512 rows each): their match counts go to warp_sums.
-constexpr uint32_t HJ_SUB = 4096;                     // = the radix pass' tile (radix.cu RX_TILE)
+constexpr uint32_t HJ_SUB = kRadixTile;               // = the radix pass' tile
 constexpr uint32_t HJ_SUB_WARP = HJ_SUB / (HJ_THREADS / kWarp);
 
 __device__ __forceinline__ uint32_t hj_lower_bound(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t v) {

@@ -21,7 +21,7 @@ namespace adb {
 constexpr int RX_THREADS = 256;
 constexpr int RX_WARPS = RX_THREADS / kWarp;
 constexpr int RX_BUCKETS = 256;
-constexpr int RX_DEFAULT_THREADS = 256;
+
 
 // f(key) of RadixPass::hash; the digit is (f >> shift) & mask.  For the signed order (HASH 0)
 // the sign flip is folded into one constant xor-ed onto the extracted digit.
@@ -165,9 +165,14 @@ __global__ void rx_bucket_base_kernel(const uint32_t *__restrict__ totals_all, u
 // NVLink (peer_base[d] + key_off / pay_off) instead of one local output array; `base` then
 // holds the offset of this rank's piece inside every destination buffer.  The run-contiguous
 // write-out is what makes the remote stores full 128-byte transactions.
-constexpr int RX_TILE = 4096;                            // rows per tile = CTA threads x keys per thread
+constexpr int RX_TILE = (int)kRadixTile;                 // rows per tile = CTA threads x keys per thread
+constexpr int RX_T_A = RX_TILE / 16 < 256 ? 256 : RX_TILE / 16 > 512 ? 512 : RX_TILE / 16;   // the default shape (16 keys per thread at 4096 rows)
+constexpr int RX_T_B = 2 * RX_T_A;                       // ADB_RX_THREADS=<this>: half the keys per thread
+constexpr int RX_DEFAULT_THREADS = RX_T_A;
 // CTA shape: T threads of 4096 / T keys each.  256 x 16: 64 registers, 56 KB -> 4 CTAs = 32 warps
-// per SM; 512 x 8: 40 registers, 60 KB -> 3 CTAs = 48 warps per SM (ADB_RX_THREADS picks; r02zc).
+// per SM; 512 x 8: 40 registers, 60 KB -> 3 CTAs = 48 warps per SM (ADB_RX_THREADS picks; r02zc:
+// 13.8 vs 12.0 ms per 500 M pairs).  Other tile sizes (-DADB_RADIX_TILE, r02zn): 2048 rows x 8 keys
+// per thread 17.3 ms (runs of 8 rows, twice the histogram), 8192 rows x 512 threads 12.7 ms.
 template <int T>
 struct RxShared {
     uint2 kv[RX_TILE];                                   // tile-sorted {key, payload}
@@ -310,7 +315,7 @@ __device__ __forceinline__ void rx_scatter_tile(RxShared<T> &sh, const uint32_t 
 }
 
 template <int T, int HASH, int BITS, bool REMOTE>
-__global__ void __launch_bounds__(T, T == 256 ? 4 : 3)
+__global__ void __launch_bounds__(T, (RX_TILE / T >= 16 ? 1024 : 1536) / T)
 rx_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay, uint32_t n,
                   RadixPass p, uint32_t seg_tiles, const uint32_t *__restrict__ hist,
                   const uint32_t *__restrict__ base,
@@ -367,15 +372,15 @@ static void rx_set_attributes() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (done[dev & 63]) return;
-    rx_set_attributes_shape<256>();
-    rx_set_attributes_shape<512>();
+    rx_set_attributes_shape<RX_T_A>();
+    rx_set_attributes_shape<RX_T_B>();
     done[dev & 63] = true;
 }
 static int rx_threads() {
     static int t = 0;
     if (!t) {
         const char *e = getenv("ADB_RX_THREADS");
-        t = e && atoi(e) == 512 ? 512 : e && atoi(e) == 256 ? 256 : RX_DEFAULT_THREADS;
+        t = e && atoi(e) == RX_T_B ? RX_T_B : RX_DEFAULT_THREADS;
     }
     return t;
 }
@@ -438,10 +443,10 @@ int launch_radix_pass_segmented(const uint32_t *keys_in, const uint32_t *pay_in,
     else
         rx_row_scan_kernel<<<segs * RX_BUCKETS, 1024, 0, s>>>(hist, seg_tiles, g.ctas, totals);
     rx_bucket_base_kernel<<<segs, RX_BUCKETS, 0, s>>>(totals, base, seg_tiles * RX_TILE);
-    if (rx_threads() == 512)
-        rx_launch_scatter<512>(g.ctas, keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, pay_out, s);
+    if (rx_threads() == RX_T_B)
+        rx_launch_scatter<RX_T_B>(g.ctas, keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, pay_out, s);
     else
-        rx_launch_scatter<256>(g.ctas, keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, pay_out, s);
+        rx_launch_scatter<RX_T_A>(g.ctas, keys_in, pay_in, n, p, seg_tiles, hist, base, keys_out, pay_out, s);
     return 4;
 }
 
@@ -471,11 +476,11 @@ int launch_radix_scatter_remote(const uint32_t *keys_in, const uint32_t *pay_in,
     if (p.hash != 2) return -1;                              // the routing hash is the only remote user
     rx_set_attributes();
     const RadixGeom g = radix_geom(n, sm_count);
-    if (rx_threads() == 512)
-        rx_scatter_kernel<512, 2, 0, true><<<g.ctas, 512, sizeof(RxShared<512>), s>>>(
+    if (rx_threads() == RX_T_B)
+        rx_scatter_kernel<RX_T_B, 2, 0, true><<<g.ctas, RX_T_B, sizeof(RxShared<RX_T_B>), s>>>(
             keys_in, pay_in, n, p, g.ctas, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
     else
-        rx_scatter_kernel<256, 2, 0, true><<<g.ctas, 256, sizeof(RxShared<256>), s>>>(
+        rx_scatter_kernel<RX_T_A, 2, 0, true><<<g.ctas, RX_T_A, sizeof(RxShared<RX_T_A>), s>>>(
             keys_in, pay_in, n, p, g.ctas, hist, base, nullptr, nullptr, peer_base, key_off, pay_off, abort_flag);
     return 1;
 }
@@ -571,7 +576,7 @@ void preload_radix() {
     { auto *fp = &rx_scatter_kernel<T, 1, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
     { auto *fp = &rx_scatter_kernel<T, 2, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
     { auto *fp = &rx_scatter_kernel<T, 2, 0, true>; preload_one(reinterpret_cast<const void *>(fp)); }
-    if (rx_threads() == 512) { RX_PRELOAD(512) } else { RX_PRELOAD(256) }
+    if (rx_threads() == RX_T_B) { RX_PRELOAD(RX_T_B) } else { RX_PRELOAD(RX_T_A) }
 #undef RX_PRELOAD
     preload_one(reinterpret_cast<const void *>(&sc_chunk_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&sc_chunk_sum_kernel));
