@@ -521,7 +521,9 @@ constexpr uint32_t kRadixTile = ADB_RADIX_TILE;
 struct RadixPass {
     int shift, bits;           // digit = (f(key) >> shift) & ((1 << bits) - 1), bits <= 8
     int hash;                  // f = key ^ 0x80000000 (0: signed order), key * 0x9E3779B1 (1: join
-                               // hash) or key * 0x85EBCA6B (2: routing hash, multi-GPU exchange)
+                               // hash) or key * 0x85EBCA6B (2: routing hash, multi-GPU exchange);
+                               // 3: digit = key / div (the shard a row number lives on; shift unused)
+    uint32_t div = 1;
 };
 struct RadixGeom {
     uint32_t rows_per_cta, ctas;
@@ -614,6 +616,10 @@ int launch_hj_unpartition_routed(const uint32_t *row_part, const uint2 *res_part
                                  const uint32_t *hist, uint32_t n_probe, uint32_t cells, const HjProbeGeom &pg,
                                  uint2 *gc_by_j, unsigned long long *warp_sums, unsigned long long *chunk_sums,
                                  unsigned long long *total, cudaStream_t s);
+// 4-byte answers of routed rows back to row order (cells = owners; cell_base / hist from the
+// unsegmented routing pass, RadixPass::hash 3)
+int launch_rows_unpartition32(const uint32_t *row_part, const uint32_t *val_part, const uint32_t *cell_base,
+                              const uint32_t *hist, uint32_t n, uint32_t cells, uint32_t *out, cudaStream_t s);
 int launch_hj_expand(const uint2 *gc_by_j, const unsigned long long *warp_base, const HjProbeGeom &pg,
                      uint32_t n_probe, const int32_t *build_pos_sorted, const int32_t *probe_pos,
                      int32_t *out_build, int32_t *out_probe, cudaStream_t s);

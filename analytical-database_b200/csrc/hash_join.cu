@@ -539,6 +539,52 @@ hj_unpartition_routed_kernel(const uint32_t *__restrict__ row_part, const uint2 
     if (lane == 0) warp_sums[blockIdx.x * (HJ_THREADS / kWarp) + warp] = acc;
 }
 
+// The same gather for 4-byte answers without any counting: the routed fetch over a position list
+// that is not aligned with the column's shards (engine.cu: adb_route_rows ... adb_route_finish32).
+__global__ void __launch_bounds__(HJ_THREADS)
+rows_unpartition32_kernel(const uint32_t *__restrict__ row_part, const uint32_t *__restrict__ val_part,
+                          const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ hist,
+                          uint32_t tiles, uint32_t n, uint32_t cells, uint32_t *__restrict__ out) {
+    __shared__ uint32_t s_val[HJ_SUB];
+    __shared__ uint32_t s_lo[HJ_FAT_CELLS], s_pre[HJ_FAT_CELLS + 1];
+    const uint32_t t = blockIdx.x;
+    const uint32_t j_lo = t * HJ_SUB, j_hi = min(n, j_lo + HJ_SUB);
+    const uint32_t rows = j_hi - j_lo;
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t c = 0; c < cells; ++c) {
+            const uint32_t b = cell_base[c];
+            const uint32_t *h = hist + (size_t)c * tiles;
+            const uint32_t lo = b + h[t];
+            const uint32_t hi = t + 1 < tiles ? b + h[t + 1] : cell_base[c + 1];
+            s_lo[c] = lo;
+            s_pre[c] = run;
+            run += hi - lo;
+        }
+        s_pre[cells] = run;
+    }
+    __syncthreads();
+    constexpr int PER = HJ_SUB / HJ_THREADS;
+    uint32_t row[PER], val[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t e = threadIdx.x + i * HJ_THREADS;
+        row[i] = 0xFFFFFFFFu;
+        if (e < rows && e < s_pre[cells]) {                  // (fewer entries than rows: positions outside every shard)
+            uint32_t c = 0;
+            while (c + 1 < cells && s_pre[c + 1] <= e) ++c;
+            const uint32_t src = s_lo[c] + (e - s_pre[c]);
+            row[i] = row_part[src];
+            val[i] = val_part[src];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+        if (row[i] != 0xFFFFFFFFu) s_val[row[i] - j_lo] = val[i];
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < rows; r += HJ_THREADS) out[j_lo + r] = s_val[r];
+}
+
 // ---- expand ---------------------------------------------------------------------------------------
 // A warp expands the piece of the probe side it probed: its first output slot comes from the
 // scan of the warps' match counts, the slots inside the piece from a running warp scan.  Four
@@ -745,6 +791,14 @@ int launch_hj_table_build(const uint32_t *bkeys, const int32_t *bpos, const uint
     return 1;
 }
 
+int launch_rows_unpartition32(const uint32_t *row_part, const uint32_t *val_part, const uint32_t *cell_base,
+                              const uint32_t *hist, uint32_t n, uint32_t cells, uint32_t *out, cudaStream_t s) {
+    if (n == 0) return 0;
+    const uint32_t tiles = (n + HJ_SUB - 1) / HJ_SUB;
+    rows_unpartition32_kernel<<<tiles, HJ_THREADS, 0, s>>>(row_part, val_part, cell_base, hist, tiles, n, cells, out);
+    return 1;
+}
+
 HjProbeGeom hj_probe_geom(uint32_t n_probe, int sm_count) {
     HjProbeGeom pg{};
     pg.blocks = (n_probe + HJ_THREADS - 1) / HJ_THREADS;
@@ -872,6 +926,7 @@ void preload_hash_join() {
     preload_one(reinterpret_cast<const void *>(&hj_probe_cells_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_unpartition_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_unpartition_routed_kernel));
+    preload_one(reinterpret_cast<const void *>(&rows_unpartition32_kernel));
     preload_one(reinterpret_cast<const void *>(&hj_sums_local_kernel));
     { auto *fp = &hj_table_build_kernel<128, 2048>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &hj_table_build_kernel<256, 4096>; preload_one(reinterpret_cast<const void *>(fp)); }

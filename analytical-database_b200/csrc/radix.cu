@@ -37,6 +37,21 @@ struct RxDigit {
         return ((key >> shift) & mask) ^ flip;
     }
 };
+// digit = key / div, at most mask: floor(2^32 / div) as the multiplier is never more than one
+// below the quotient
+template <>
+struct RxDigit<3> {
+    uint32_t div, magic, mask;
+    __host__ __device__ explicit RxDigit(const RadixPass &p)
+        : div(p.div ? p.div : 1u), magic((uint32_t)(0x100000000ull / (p.div ? p.div : 1u) > 0xFFFFFFFFull
+                                                        ? 0xFFFFFFFFull : 0x100000000ull / (p.div ? p.div : 1u))),
+          mask((1u << p.bits) - 1u) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t key) const {
+        uint32_t q = __umulhi(key, magic);
+        if ((unsigned long long)(q + 1) * div <= key) ++q;
+        return min(q, mask);
+    }
+};
 
 template <int HASH>
 __global__ void __launch_bounds__(RX_THREADS)
@@ -365,6 +380,7 @@ static void rx_set_attributes_shape() {
     allow(&rx_scatter_kernel<T, 1, 0, false>);
     allow(&rx_scatter_kernel<T, 2, 0, false>);
     allow(&rx_scatter_kernel<T, 2, 0, true>);
+    allow(&rx_scatter_kernel<T, 3, 0, false>);
 }
 // function attributes are per device: once per device the engine launches on
 static void rx_set_attributes() {
@@ -397,6 +413,7 @@ static void rx_launch_scatter(uint32_t ctas, const uint32_t *keys_in, const uint
     else if (p.hash == 1 && p.bits == 8) RX_LAUNCH(1, 8);
     else if (p.hash == 0) RX_LAUNCH(0, 0);
     else if (p.hash == 1) RX_LAUNCH(1, 0);
+    else if (p.hash == 3) RX_LAUNCH(3, 0);
     else RX_LAUNCH(2, 0);
 #undef RX_LAUNCH
 }
@@ -405,6 +422,7 @@ static void launch_hist(const uint32_t *keys_in, uint32_t n, const RadixGeom &g,
                         uint32_t *hist, cudaStream_t s) {
     if (p.hash == 1) rx_hist_kernel<1><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
     else if (p.hash == 2) rx_hist_kernel<2><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
+    else if (p.hash == 3) rx_hist_kernel<3><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
     else rx_hist_kernel<0><<<g.ctas, RX_THREADS, 0, s>>>(keys_in, n, g.rows_per_cta, p, seg_tiles, hist);
 }
 
@@ -566,6 +584,7 @@ void preload_radix() {
     { auto *fp = &rx_hist_kernel<0>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &rx_hist_kernel<1>; preload_one(reinterpret_cast<const void *>(fp)); }
     { auto *fp = &rx_hist_kernel<2>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_hist_kernel<3>; preload_one(reinterpret_cast<const void *>(fp)); }
     preload_one(reinterpret_cast<const void *>(&rx_row_scan_kernel));
     preload_one(reinterpret_cast<const void *>(&rx_row_scan_warp_kernel));
     preload_one(reinterpret_cast<const void *>(&rx_bucket_base_kernel));
@@ -575,7 +594,8 @@ void preload_radix() {
     { auto *fp = &rx_scatter_kernel<T, 0, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
     { auto *fp = &rx_scatter_kernel<T, 1, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
     { auto *fp = &rx_scatter_kernel<T, 2, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }         \
-    { auto *fp = &rx_scatter_kernel<T, 2, 0, true>; preload_one(reinterpret_cast<const void *>(fp)); }
+    { auto *fp = &rx_scatter_kernel<T, 2, 0, true>; preload_one(reinterpret_cast<const void *>(fp)); }          \
+    { auto *fp = &rx_scatter_kernel<T, 3, 0, false>; preload_one(reinterpret_cast<const void *>(fp)); }
     if (rx_threads() == RX_T_B) { RX_PRELOAD(RX_T_B) } else { RX_PRELOAD(RX_T_A) }
 #undef RX_PRELOAD
     preload_one(reinterpret_cast<const void *>(&sc_chunk_scan_kernel));

@@ -190,6 +190,9 @@ class Engine:
         "adb_peer_exchange_reserve": (C.c_int32, [C.c_int64, C.c_int64, C.c_int64]),
         "adb_join_probe_sharded": (C.c_int32, [C.c_int32, _I32P, _I32P, C.c_int64, C.c_int32, _I64P]),
         "adb_copy_from_ctx_ready": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
+        "adb_route_rows": (C.c_int32, [C.c_int32, C.c_int64, _I32P, C.c_int64, _I64P, C.POINTER(_I32P),
+                                       C.POINTER(C.c_void_p)]),
+        "adb_route_finish32": (C.c_int32, [C.c_int32, _I32P, C.c_int64]),
         "adb_join_route_probe": (C.c_int32, [C.c_int32, _I32P, C.c_int64, _I64P, C.POINTER(_I32P),
                                              C.POINTER(C.c_void_p)]),
         "adb_join_recv_buffers": (C.c_int32, [C.c_int64, C.POINTER(_I32P), C.POINTER(C.c_void_p)]),

@@ -2115,15 +2115,66 @@ typedef struct FetchJob {
     DevColumn *c;
     Staged *p;
     Shards out;
+    /* routed form (phases 1-3): sent[g][o] = positions of GPU g's list that name rows of GPU o */
+    int phase;
+    int64_t sent[MAXG][MAXG];
+    const int32_t *routed_pos[MAXG];
+    void *answers_home[MAXG], *answers_owner[MAXG];
 } FetchJob;
+/* A position list that is not aligned with the column's shards (index order, a join's output):
+ * above this many positions they are routed to the GPUs that hold the rows and the values come
+ * back in bulk (adb_route_rows); below, every remote row is one NVLink read (adb_fetch_sharded).
+ * ADB_FETCH_ROUTE_MIN overrides (0 = always route, a huge value = never). */
+static size_t fetch_route_min(void) {
+    const char *e = getenv("ADB_FETCH_ROUTE_MIN");
+    const long long v = e ? atoll(e) : 1 << 20;
+    return v < 0 ? 0 : (size_t)v;
+}
 static void fetch_shard(int g, void *arg) {
     FetchJob *a = arg;
     DevColumn *c = a->c;
     const size_t n = a->p->n[g];
+    if (a->phase == 2) {                            /* owner: pull my pieces, gather them from my shard */
+        int64_t n_recv = 0;
+        for (int s = 0; s < S.G; ++s) n_recv += a->sent[s][g];
+        int32_t *pos = NULL;
+        SCK(adb_join_recv_buffers(n_recv, &pos, &a->answers_owner[g]));
+        for (int k = 0; k < S.G; ++k) {
+            const int s = (g + k) % S.G;
+            int64_t at = 0, from = 0;
+            for (int t = 0; t < s; ++t) at += a->sent[t][g];
+            for (int o = 0; o < g; ++o) from += a->sent[s][o];
+            if (a->sent[s][g])
+                SCK(adb_copy_from_ctx_ready(pos + at, s, a->routed_pos[s] + from, 4 * (size_t)a->sent[s][g]));
+        }
+        if (n_recv)
+            SCK(adb_fetch(c->d_data[g], pos, n_recv, NULL, shard_base(g, c->shard_rows), a->answers_owner[g]));
+        SCK(adb_sync());
+        return;
+    }
+    if (a->phase == 3) {                            /* home: the values back into list order */
+        for (int k = 0; k < S.G; ++k) {
+            const int o = (g + k) % S.G;
+            int64_t at = 0, from = 0;
+            for (int t = 0; t < o; ++t) at += a->sent[g][t];
+            for (int s = 0; s < g; ++s) from += a->sent[s][o];
+            if (a->sent[g][o])
+                SCK(adb_copy_from_ctx_ready((char *)a->answers_home[g] + 4 * (size_t)at, o,
+                                            (const char *)a->answers_owner[o] + 4 * (size_t)from,
+                                            4 * (size_t)a->sent[g][o]));
+        }
+        SCK(adb_route_finish32(S.G, a->out.d[g], (int64_t)n));
+        return;
+    }
     void *out = NULL;
     SCK(adb_alloc(&out, 4 * n));
     a->out.d[g] = out;
     a->out.n[g] = n;
+    if (a->phase == 1) {                            /* home: my positions grouped by the shard they name */
+        SCK(adb_route_rows(S.G, (int64_t)c->shard_rows, a->p->d[g], (int64_t)n, a->sent[g], &a->routed_pos[g],
+                           &a->answers_home[g]));
+        return;
+    }
     if (!n) return;
     if (S.G == 1 || (a->p->aligned && a->p->aligned == c->shard_rows))
         SCK(adb_fetch(c->d_data[g], a->p->d[g], (int64_t)n, NULL, shard_base(g, c->shard_rows), out));
@@ -2184,8 +2235,16 @@ static Result *fetch_column_impl(Column *column, Result *position_result, Status
     if (stage(position_result, NULL, &p)) goto fail;
     job.c = c;
     job.p = &p;
-    run_shards(fetch_shard, &job);
-    if (shard_errs(&job.err)) goto fail;
+    if (S.G > 1 && !(p.aligned && p.aligned == c->shard_rows) && p.total >= fetch_route_min() &&
+        c->shard_rows > 0) {
+        for (job.phase = 1; job.phase <= 3; ++job.phase) {
+            run_shards(fetch_shard, &job);
+            if (shard_errs(&job.err)) goto fail;
+        }
+    } else {
+        run_shards(fetch_shard, &job);
+        if (shard_errs(&job.err)) goto fail;
+    }
     job.out.aligned = p.aligned;                    /* values pair with their positions shard by shard */
     unstage(&p);
     {

@@ -478,6 +478,19 @@ ADB_API adb_status adb_join_probe_received(int64_t n_recv);
 ADB_API adb_status adb_join_finish_routed(int32_t world, const int32_t *d_pv, const int32_t *d_pp, int64_t np,
                                           int32_t swapped, int64_t *h_matches);
 
+/* ---- routed fetch (several contexts, a position list that is not aligned with the shards) ----
+ * Instead of adb_fetch_sharded's one NVLink read per remote row: (1) adb_route_rows groups this
+ * context's positions by the shard that holds the row (shard = position / shard_rows, at most
+ * world - 1); h_counts / *d_routed_pos / *d_answers as for adb_join_route_probe, 4-byte answers;
+ * (2) every owner pulls its pieces (adb_join_recv_buffers + adb_copy_from_ctx_ready), gathers
+ * them with adb_fetch(column shard, received positions, n, NULL, shard base, answers) and
+ * synchronises; (3) the list's home pulls the answers into *d_answers and adb_route_finish32
+ * writes d_out[i] = value of position i.  A host barrier after each step.  Uses the sort / join
+ * scratch arena (a join waiting for its emit phase is dropped). */
+ADB_API adb_status adb_route_rows(int32_t world, int64_t shard_rows, const int32_t *d_pos, int64_t n,
+                                  int64_t *h_counts, const int32_t **d_routed_pos, void **d_answers);
+ADB_API adb_status adb_route_finish32(int32_t world, int32_t *d_out, int64_t n);
+
 /* ---- multi-GPU join exchange, send side (no reference equivalent: SURVEY.md 8e) ----------
  * Stable partition of a (value, position) pair list by destination rank = the top
  * log2(parts) bits of a routing hash of the value; parts is a power of two <= 256 (the

@@ -675,10 +675,14 @@ def test_lazy_handles_are_written_only_when_read(api, cpu, rng):
 
 
 # ---- one process, several GPUs: the cases only a sharded layout has ---------------------------
-def test_sharded_lists_that_are_not_row_aligned(api, cpu, rng):
+@pytest.mark.parametrize("route_min", ["0", "1000000000"])
+def test_sharded_lists_that_are_not_row_aligned(api, cpu, rng, monkeypatch, route_min):
     """Position lists in index order, from a join, or built by foreign code name rows of any
-    shard: fetch goes through peer loads (adb_fetch_sharded) and must still be the reference's
-    gather, element for element."""
+    shard: fetch routes the positions to the GPUs that hold the rows and gathers the values back
+    into list order (adb_route_rows; ADB_FETCH_ROUTE_MIN=0 forces it at any size) or reads every
+    remote row with a peer load (adb_fetch_sharded), and must still be the reference's gather,
+    element for element."""
+    monkeypatch.setenv("ADB_FETCH_ROUTE_MIN", route_min)
     n = 100_003
     live0 = api.lib.adb_host_live_device_results()
     data = rng.integers(0, 5000, n).astype(np.int32)
