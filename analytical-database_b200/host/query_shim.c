@@ -2125,10 +2125,19 @@ typedef struct FetchJob {
  * above this many positions they are routed to the GPUs that hold the rows and the values come
  * back in bulk (adb_route_rows); below, every remote row is one NVLink read (adb_fetch_sharded).
  * ADB_FETCH_ROUTE_MIN overrides (0 = always route, a huge value = never). */
+/* Measured (r02zo / r02zp, 500 M-row column, index-ordered lists): two GPUs, 5 M positions 0.39 ->
+ * 0.23 ms, 50 M 3.58 -> 1.40 ms; eight GPUs, 5 M 0.20 -> 0.43 ms, 50 M 0.92 -> 0.98 ms -- the routed
+ * form pays three host phases (~0.3 ms), the peer loads of eight GPUs spread over seven links each.
+ * Default: 1 M positions on two GPUs, 16 x that per doubling of the GPU count. */
 static size_t fetch_route_min(void) {
     const char *e = getenv("ADB_FETCH_ROUTE_MIN");
-    const long long v = e ? atoll(e) : 1 << 20;
-    return v < 0 ? 0 : (size_t)v;
+    if (e) {
+        const long long v = atoll(e);
+        return v < 0 ? 0 : (size_t)v;
+    }
+    size_t m = (size_t)1 << 20;
+    for (int g = 2; g < S.G; g *= 2) m *= 16;
+    return m;
 }
 static void fetch_shard(int g, void *arg) {
     FetchJob *a = arg;
