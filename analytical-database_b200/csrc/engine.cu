@@ -65,7 +65,7 @@ struct Engine {
     unsigned long long *sc_sums = nullptr;
     struct JoinState {
         bool ready = false;
-        uint32_t n_probe = 0;
+        uint32_t n_probe = 0, n_build = 0;
         int64_t matches = 0;
         uint2 *gc_by_j = nullptr;           // {group start, match count} per probe row
         unsigned long long *warp_base = nullptr;   // first output slot of every probing warp (pg.warps)
@@ -2149,13 +2149,21 @@ static bool join_probe_partitioned(uint32_t nb, uint32_t np) {
     }
     return nb >= (6u << 20) && np >= (4u << 20);
 }
+// the routed probe's owner side probing ~np received keys slice by slice: the same buffers once
+// more and the segmented pass' own histogram, totals and bases
+static size_t join_owner_scratch(uint32_t np);
 static size_t join_partition_scratch(uint32_t np) {      // keys + row numbers + results in partition order,
     return 2 * arena_round((size_t)np * 4) + arena_round((size_t)np * 8) +      // 8 piece sums per 4096 rows
            arena_round(((size_t)np / adb::kRadixTile + 2) * 8 * 8) + 4096;
 }
 
+static size_t join_owner_scratch(uint32_t np) {
+    return join_partition_scratch(np) + arena_round(((size_t)np / adb::kRadixTile + 512) * 256 * 4) +
+           2 * arena_round((size_t)256 * 256 * 4) + 8192;
+}
+
 static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, uint32_t np, int *launches,
-                             StageTrace &tr, bool part_scratch = false) {
+                             StageTrace &tr, bool part_scratch = false, bool owner_scratch = false) {
     uint32_t part_bits = 1;                    // >= 1: the table's key tag needs one spare bit
     // (up to 2^20 partitions: a 500 M-row build side still gets ~500-row partitions that fit the
     // shared-memory table, instead of 2^16 oversized ones built slot by slot in global memory)
@@ -2164,10 +2172,12 @@ static adb_status join_build(const int32_t *bv, const int32_t *bp, uint32_t nb, 
     const size_t pbytes = (size_t)(num_parts + 1) * 4;
     if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
                                      arena_round(pbytes) + arena_round((size_t)(num_parts + 1) * 8) +
-                                     (part_scratch ? join_partition_scratch(np) : 0) + kJoinSmallScratch))
+                                     (part_scratch ? join_partition_scratch(np) : 0) +
+                                     (owner_scratch ? join_owner_scratch(np) : 0) + kJoinSmallScratch))
         return s;
     auto &j = g.join;
     j.part_bits = part_bits;
+    j.n_build = nb;
     uint32_t *off1 = ARENA_TAKE(uint32_t, num_parts + 1);
     unsigned long long *toff = ARENA_TAKE(unsigned long long, num_parts + 1);
     j.toff = toff;
@@ -2290,7 +2300,7 @@ adb_status adb_join_build(const int32_t *d_v, const int32_t *d_p, int64_t n, int
     int launches = 0;
     StageTrace tr;
     if (adb_status s = ensure_radix_scratch((uint32_t)(n ? n : 1))) return s;
-    if (adb_status s = join_build(d_v, d_p, (uint32_t)n, (uint32_t)probe_rows_hint, &launches, tr, true)) return s;
+    if (adb_status s = join_build(d_v, d_p, (uint32_t)n, (uint32_t)probe_rows_hint, &launches, tr, true, true)) return s;
     if (adb_status s = after_launch("join_build", launches)) return s;
     CU(cudaStreamSynchronize(g.stream));               // the other contexts' probes read these tables
     g.join.built = true;
@@ -2441,13 +2451,56 @@ adb_status adb_join_probe_received(int64_t n_recv) {
     if (adb_status s = check_len(n_recv, "adb_join_probe_received")) return s;
     if ((size_t)n_recv > g.rt_recv_cap) return fail(ADB_ERR_INVALID, "adb_join_probe_received: more keys than adb_join_recv_buffers made room for");
     if (n_recv == 0) return ADB_OK;
-    const adb::HjProbeGeom pg = adb::hj_probe_geom((uint32_t)n_recv, g.sm_count);
-    unsigned long long *sums = ARENA_TAKE(unsigned long long, pg.warps);
-    if (g.arena_used > g.arena_cap) return fail(ADB_ERR_NOMEM, "adb_join_probe_received: scratch arena too small");
+    const uint32_t n = (uint32_t)n_recv;
     StageTrace tr;
-    const int k_ = adb::launch_hj_probe_plain(g.rt_recv_keys, (uint32_t)n_recv, j.toff, j.part_bits,
-                                              static_cast<const uint4 *>(g.hj_table), g.rt_recv_res, sums,
-                                              g.sm_count, g.stream);
+    int k_ = 0;
+    // A table well beyond L2 (two or four GPUs: >= 24 M build rows here) is probed slice by slice
+    // like the one-GPU join's (hash_join.cu P1-P3), the answers gathered back into the order the
+    // keys arrived in.  The pass needs a histogram of its own: g.rx_hist / g.rx_base still hold
+    // this context's ROUTING pass, which adb_join_finish_routed reads.  No room in the arena (a
+    // skewed key set sent most of the probe side here): the direct probe.
+    bool partitioned = n >= (4u << 20) && j.n_build >= (24u << 20);
+    if (const char *e = getenv("ADB_JOIN_PROBE")) {
+        if (!strcmp(e, "direct")) partitioned = false;
+        if (!strcmp(e, "partitioned")) partitioned = true;
+    }
+    if (partitioned) {
+        const uint32_t tiles = (n + adb::kRadixTile - 1) / adb::kRadixTile;
+        const uint32_t want_tiles = (tiles + 255) / 256;
+        const uint32_t segs = adb::radix_segments(n, want_tiles);
+        const uint32_t seg_tiles = adb::radix_seg_tiles(n, want_tiles);
+        const adb::HjProbeGeom pg = adb::hj_probe_geom_partitioned(n);
+        const size_t hist_elems = adb::radix_hist_elems(n, want_tiles);
+        const size_t need = 2 * arena_round((size_t)n * 4) + arena_round((size_t)n * 8) +
+                            arena_round(hist_elems * 4) + 2 * arena_round((size_t)segs * 256 * 4) +
+                            arena_round((size_t)pg.warps * 8) + arena_round(((size_t)pg.warps / 1024 + 2) * 8) + 4096;
+        // (what adb_join_finish_routed still takes for this context's own probe rows stays free)
+        const size_t finish = arena_round((size_t)j.rt_rows_n * 8) + arena_round(((size_t)j.rt_rows_n / 512 + 8) * 8) +
+                              (1 << 20);
+        if (g.arena_used + need + finish <= g.arena_cap) {
+            uint32_t *pk = ARENA_TAKE(uint32_t, n), *rows = ARENA_TAKE(uint32_t, n);
+            uint2 *res = ARENA_TAKE(uint2, n);
+            uint32_t *hist = ARENA_TAKE(uint32_t, hist_elems);
+            uint32_t *totals = ARENA_TAKE(uint32_t, (size_t)segs * 256), *base = ARENA_TAKE(uint32_t, (size_t)segs * 256);
+            unsigned long long *sums = ARENA_TAKE(unsigned long long, pg.warps);
+            unsigned long long *chunk_sums = ARENA_TAKE(unsigned long long, pg.warps / 1024 + 2);
+            unsigned long long *tot = ARENA_TAKE(unsigned long long, 2);
+            k_ += adb::launch_radix_pass_segmented(g.rt_recv_keys, nullptr, pk, rows, n, adb::RadixPass{24, 8, 1},
+                                                   want_tiles, hist, totals, base, g.sm_count, g.stream);
+            k_ += adb::launch_hj_probe_partitioned(pk, rows, base, hist, segs, seg_tiles, n, pg, j.toff, j.part_bits,
+                                                   static_cast<const uint4 *>(g.hj_table), res, g.rt_recv_res, sums,
+                                                   chunk_sums, tot, g.stream);
+        } else {
+            partitioned = false;
+        }
+    }
+    if (!partitioned) {
+        const adb::HjProbeGeom pg = adb::hj_probe_geom(n, g.sm_count);
+        unsigned long long *sums = ARENA_TAKE(unsigned long long, pg.warps);
+        if (g.arena_used > g.arena_cap) return fail(ADB_ERR_NOMEM, "adb_join_probe_received: scratch arena too small");
+        k_ += adb::launch_hj_probe_plain(g.rt_recv_keys, n, j.toff, j.part_bits, static_cast<const uint4 *>(g.hj_table),
+                                         g.rt_recv_res, sums, g.sm_count, g.stream);
+    }
     if (adb_status s = after_launch("join_probe_received", k_)) return s;
     CU(cudaStreamSynchronize(g.stream));               // the rows' homes pull the answers next
     tr.lap("received keys in + probe");
@@ -2586,7 +2639,7 @@ adb_status adb_peer_exchange_reserve(int64_t send_pairs, int64_t build_pairs, in
     if (adb_status s = arena_reserve(radix_scratch_bytes(nb, 4) + arena_round((size_t)np * 8) +
                                      arena_round((size_t)(num_parts + 1) * 4) +
                                      arena_round((size_t)(num_parts + 1) * 8) + join_partition_scratch(np) +
-                                     kJoinSmallScratch))
+                                     join_owner_scratch(np) + kJoinSmallScratch))
         return s;
     {
         const size_t words = (size_t)ADB_MAX_PEERS * ((size_t)num_parts + 1);

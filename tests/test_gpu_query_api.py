@@ -775,12 +775,16 @@ def test_long_print_across_shards(api, rng):
     api.drop(s), api.drop(f)
 
 
-@pytest.mark.parametrize("sharded_probe", ["routed", "peer"])
+@pytest.mark.parametrize("sharded_probe", ["routed", "routed-partitioned", "peer"])
 def test_join_of_sharded_operands(api, cpu, rng, monkeypatch, sharded_probe):
     """With several GPUs the probe keys are routed to their owners and the answers gathered back
-    into row order (default), or every GPU probes in place and reads remote slots over peer
-    memory (ADB_JOIN_SHARDED_PROBE=peer): same pairs, same order."""
-    monkeypatch.setenv("ADB_JOIN_SHARDED_PROBE", sharded_probe)
+    into row order (default; the owner probes what it received directly or, for a table far
+    beyond L2, slice by slice: ADB_JOIN_PROBE=partitioned forces that at any size), or every GPU
+    probes in place and reads remote slots over peer memory (ADB_JOIN_SHARDED_PROBE=peer): same
+    pairs, same order."""
+    monkeypatch.setenv("ADB_JOIN_SHARDED_PROBE", sharded_probe.split("-")[0])
+    if sharded_probe.endswith("partitioned"):
+        monkeypatch.setenv("ADB_JOIN_PROBE", "partitioned")
     n1, n2 = 70_000, 50_000
     live0 = api.lib.adb_host_live_device_results()
     k1 = rng.integers(1, 30_000, n1).astype(np.int32)
