@@ -399,20 +399,12 @@ hj_probe_cells_kernel(const uint32_t *__restrict__ pkeys_part, const uint32_t *_
 // stay inside one 3 MB window of the result array, still cost a DRAM read-modify-write per
 // 8-byte store (3.9 GB read + 3.0 GB written for 100 M rows, 3.6 ms): partially written sectors
 // do not wait in L2 for their other rows.  So the rows are gathered instead: a CTA owns 4096
-// consecutive probe rows, finds their entries in each of the window's 256 cells (row numbers
-// ascend inside a cell: two binary searches per cell, ~16 entries each), parks the results in
-// shared memory by row and writes them out as whole lines.  Its eight warps are the expansion's
-// pieces (512 rows each): their match counts go to warp_sums.
+// consecutive probe rows, takes their entries out of each of the window's 256 cells (~16 per
+// cell, row numbers ascending), parks the results in shared memory by row and writes them out
+// as whole lines.  Its eight warps are the expansion's pieces (512 rows each): their match
+// counts go to warp_sums.
 constexpr uint32_t HJ_SUB = kRadixTile;               // = the radix pass' tile
 constexpr uint32_t HJ_SUB_WARP = HJ_SUB / (HJ_THREADS / kWarp);
-
-__device__ __forceinline__ uint32_t hj_lower_bound(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t v) {
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (a[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 
 // Where do the entries of the CTA's 4096 rows sit inside cell (w, p)?  A sub-window is one
 // 4096-row tile of the segmented radix pass, and that pass' histogram, scanned along the tiles
